@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""BP5 Poisson (N=7, FP64) throughput: python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A step is one cggos solve (examples/bp5/bp5.usr:367-369: `maxit` fixed CG iterations of Ax + dssum + mask + the
+vector updates) of the BP5 box case; the N=1 workload is BASELINE.json configs[3]'s mesh, E = 64^3 = 262,144
+elements of order N=7 (weak scaling: 64^3 elements per GPU, bricks px*py*pz).  Metric: GDOF/s with the reference's
+own accounting (iterations * E_global * N^3 / seconds, bp5.usr:378-383).
+
+Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM, timed with CUDA events on the library stream, max
+over ranks.  `e2e`: the same solve through the Fortran-named host-buffer entry point cggos_ (pinned host arrays,
+H2D of rhs/weights and D2H of the solution inside the timed region).  `roofline`: the dominant kernel (Ax), its
+algorithmic bytes per launch / its mean launch time measured live with CUDA events.  `cpu_baseline`: the oracle's
+OpenMP restatement of the same loop on the host cores, on a bounded sample.  --impl reference times that CPU
+restatement alone (the Fortran reference cannot be built: no Fortran compiler, gslib not vendored).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LX1 = 8
+NDOF = (LX1 - 1) ** 3            # DOF per element as the reference counts them (N^3, bp5.usr:380)
+NXYZ = LX1 ** 3
+# algorithmic words (8 B) per grid point per CG iteration
+WORDS_AX = 8.0                   # read p, 6 geometric factors, write w
+WORDS_ITER = 19.445              # + gs/mask 1.445 + x,r update 6 + weight 1 + p update 3
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(dev)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if sm:
+            sm.sort()
+            out["sm_mhz"] = sm[len(sm) // 2]
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def cpu_leg(steps: int, warmup: int, m_cpu: int, target_s: float):
+    """The oracle's OpenMP restatement of cggos (oracle/bp5_cpu.c) on a bounded sample of the workload."""
+    import oracle
+    case = oracle.Case(m_cpu, m_cpu, m_cpu, nx=LX1)
+    _, r1 = case.bp5_problem()
+    _, sec, nt = oracle.cpu_cggos(case, r1, 2)
+    its = max(2, min(500, int(target_s / max(sec / 2, 1e-9))))
+    for _ in range(warmup):
+        oracle.cpu_cggos(case, r1, max(1, its // 4))
+    tot = 0.0
+    for _ in range(steps):
+        _, sec, nt = oracle.cpu_cggos(case, r1, its)
+        tot += sec
+    gdofs = steps * its * case.nel * NDOF / tot / 1e9
+    sample = (f"E={m_cpu}^3={case.nel} elements (N=7) of the same box case, {its} CG iterations per step, {steps} steps; "
+              f"gcc -O3 -march=native -fopenmp restatement of bp5.usr cggos/ax_e_bp5 + shared-memory gs")
+    return gdofs, nt, sample, tot / steps * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--m", type=int, default=64, help="elements per direction per GPU (64 -> E=262,144 per GPU)")
+    ap.add_argument("--maxit", type=int, default=500, help="CG iterations per solve (bp5.par:13-15)")
+    ap.add_argument("--m-cpu", type=int, default=32, help="CPU-baseline sample: elements per direction")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
+
+    from nek5000_b200.bp5 import brick_layout
+    px, py, pz = brick_layout(max(a.gpus, 1))
+    config = {"workload": f"BP5 box mesh, N=7 (lx1=8), FP64, E={a.m}^3={a.m ** 3} elements per GPU "
+                          f"({a.m * px}x{a.m * py}x{a.m * pz} global, bricks {px}x{py}x{pz}), cggos {a.maxit} fixed CG "
+                          f"iterations per step (bp5.par), identity preconditioner, all-Dirichlet box [0,1]^3",
+              "elements_global": a.m ** 3 * max(a.gpus, 1), "iterations_per_step": a.maxit,
+              "l2": "inputs larger than L2 (each n-vector 1.07 GB, factors 6.4 GB per GPU at E=262,144)"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        gd, nt, sample, ms = cpu_leg(max(a.steps, 1), a.warmup, a.m_cpu, target_s=4.0)
+        print(json.dumps({"impl": "reference", "metric": "BP5 Poisson GDOF/s (N=7, FP64)", "value": gd, "unit": "GDOF/s",
+                          "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": gd, "unit": "GDOF/s", "cores": nt, "kind": "port", "sample": sample},
+                          "e2e": {"value": gd, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from nek5000_b200 import lib, nek
+    from nek5000_b200._lib import check
+    from nek5000_b200.bp5 import BP5
+    import ctypes as C
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nek.init(local, LX1, 3)
+    if world > 1:
+        nek.comm_init_torch()
+    assert world == max(a.gpus, 1), f"--gpus {a.gpus} but WORLD_SIZE={world}"
+    case = BP5(a.m * px, a.m * py, a.m * pz, lx1=LX1, device=local, rank=rank, nranks=world, layout=(px, py, pz))
+    n, E_glob = case.n, case.nel_global
+    L = lib()
+
+    def barrier():
+        torch.cuda.synchronize()
+        check(L.nekb_sync())
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing ---------------------------------------------------------------------------------
+    for _ in range(warmup):
+        case.solve(-1e-8, a.maxit)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    check(L.nekb_prof_enable(1))
+    nek.launch_count(reset=True)
+    dev_s, t0 = 0.0, time.perf_counter()
+    for _ in range(a.steps):
+        it, sec = case.solve(-1e-8, a.maxit)
+        assert it == a.maxit
+        dev_s += sec
+    barrier()
+    wall_s = time.perf_counter() - t0
+    launches = nek.launch_count()
+    clocks = sampler.stop() if sampler else None
+    relerr = case.relerr()
+    prof = {}
+    for k in ("ax", "gs", "update", "pupdate"):
+        s_, c_ = C.c_double(0), C.c_int64(0)
+        check(L.nekb_prof_get(k.encode(), C.byref(s_), C.byref(c_)))
+        prof[k] = (s_.value, c_.value)
+    check(L.nekb_prof_enable(0))
+    dev_s = max_over_ranks(dev_s)
+    wall_s = max_over_ranks(wall_s)
+    iters = a.steps * a.maxit
+    value = iters * E_glob * NDOF / dev_s / 1e9
+
+    # ---- end to end through cggos_ with host buffers -----------------------------------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        pin = lambda: torch.empty(n, dtype=torch.float64, pin_memory=True)
+        u1_t, rhs_t, x1_t, mult_t, binv_t = pin(), pin(), pin(), pin(), pin()
+        u1, rhs, x1, mult, binv = (t.numpy() for t in (u1_t, rhs_t, x1_t, mult_t, binv_t))
+        rhs[:] = case.get("r1")
+        x1[:] = case.get("e1")
+        mult[:] = case.get("mult")
+        binv[:] = 1.0
+        nek.set_ifield(1)
+        nek.cggos(u1, rhs, x1, mult, binv, -1e-8, min(a.maxit, 20), "bp5")  # warm the staging buffers
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            itn = nek.cggos(u1, rhs, x1, mult, binv, -1e-8, a.maxit, "bp5")
+            assert itn == a.maxit
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": iters * E_glob * NDOF / e2e_s / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": 2 * n * 8 * world,
+               "d2h_bytes_per_step": n * 8 * world, "ms_per_step": e2e_s / a.steps * 1e3,
+               "api": "cggos_(u1,rhs1,x1,rmult,binv,tin,maxit,'bp5') with pinned host arrays"}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    ax_s, ax_n = prof["ax"]
+    ax_bytes = WORDS_AX * 8 * NXYZ * case.nel                      # per launch (this rank's elements)
+    ax_gbs = ax_bytes / (ax_s / max(ax_n, 1)) / 1e9 if ax_s > 0 else None
+    iter_gbs = WORDS_ITER * 8 * NXYZ * case.nel * iters / dev_s / 1e9   # whole iteration, per GPU
+    tot_prof = sum(v[0] for v in prof.values())
+    out = {
+        "metric": "BP5 Poisson GDOF/s (N=7, FP64)", "value": value, "unit": "GDOF/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": warmup, "ms_per_step": dev_s / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+        "relerr": relerr, "wall_ms_per_step": wall_s / a.steps * 1e3, "gpu_launches": launches, "clocks": clocks,
+        "e2e": e2e,
+        "roofline": {"bound": "hbm", "kernel": "ax_kernel (Ax = D^T G D p with fused pap)", "achieved": ax_gbs, "peak": peak,
+                     "unit": "GB/s", "frac": (ax_gbs / peak) if ax_gbs else None, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": ax_bytes, "mean_launch_ms": ax_s / max(ax_n, 1) * 1e3,
+                     "share_of_step": ax_s / tot_prof if tot_prof > 0 else None,
+                     "kernel_ms_per_iteration": {k: v[0] / max(v[1], 1) * 1e3 for k, v in prof.items()},
+                     "whole_iteration": {"achieved": iter_gbs, "frac": iter_gbs / peak,
+                                         "algorithmic_bytes_per_element_iteration": WORDS_ITER * 8 * NXYZ}},
+    }
+    prof_json = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(prof_json):  # dram bytes per Ax launch from the committed ncu --set full capture
+        try:
+            tr = json.load(open(prof_json))
+            if tr.get("elements") == case.nel:
+                out["roofline"]["traffic"] = tr.get("ax_dram_bytes_per_launch")
+        except Exception:
+            pass
+    if a.gpus == 1 and not a.no_cpu:
+        gd, nt, sample, _ = cpu_leg(2, 1, a.m_cpu, target_s=6.0)
+        out["cpu_baseline"] = {"value": gd, "unit": "GDOF/s", "cores": nt, "kind": "port", "sample": sample}
+    print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

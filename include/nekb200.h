@@ -1,0 +1,251 @@
+/*
+ * nekb200.h -- C-ABI of libnekb200.so: the B200-native (sm_100a, FP64 CUDA) replacement for
+ * Nek5000's Helmholtz / gather-scatter / PCG hot path.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * Nek5000 tree).  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * There is no plugin registry in Nek5000: a replacement overrides by SYMBOL NAME at link
+ * time (core/makenek.inc:304-307 adds --allow-multiple-definition; bin/makenek:31-34 lets a
+ * case add objects).  Section A therefore exports the gfortran-mangled names
+ * (lower case + trailing underscore, core/name.h:32-41) with Fortran by-reference
+ * arguments.  Because most operands of those routines are COMMON-block state and not
+ * arguments (SURVEY.md 8b "implicit state"), section B is the explicit registration the
+ * Fortran side performs once after gengeom.  Section C is the same
+ * functionality on device-resident buffers (used by the BP5 driver and by callers that keep
+ * a whole solve on the GPU).  Section D is the host-side setup that feeds the path
+ * (numbering, geometry, synthetic BP5 case).
+ *
+ * Error convention (reference: print on rank 0 + call exitt, core/comm_mpi.f:550-636):
+ * nekb_* functions return 0 on success and non-zero on failure with the message
+ * retrievable through nekb_last_error(); the Fortran-named entry points have no return
+ * value, so on failure they print "nekb200: <file:line> <message>" to stderr and call the
+ * registered exit handler (default: abort()), never returning stale output.
+ *
+ * Threading: one host thread per process, one GPU per process (Nek's rank model); all GPU
+ * work is enqueued on the library's stream; host-buffer entry points are synchronous.
+ */
+#ifndef NEKB200_H
+#define NEKB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------
+ * Lifecycle
+ * ---------------------------------------------------------------------------------- */
+
+/* Selects the CUDA device, creates the stream and scratch.  lx1 = GLL points per direction
+ * (core/SIZE.template:13 lx1); ldim must be 3.  Idempotent for identical arguments. */
+int nekb_init(int device, int lx1, int ldim);
+void nekb_finalize(void);
+const char *nekb_last_error(void);
+/* Handler called by the Fortran-named entry points on failure (reference: exitt,
+ * core/comm_mpi.f:550).  NULL restores abort(). */
+void nekb_set_exit_handler(void (*handler)(void));
+/* Library stream as a cudaStream_t cast to void* (so callers can order their own work). */
+void *nekb_stream(void);
+/* Number of kernel launches issued by the library since the last reset (bench.py's
+ * gpu_launches claim). */
+int64_t nekb_launch_count(int reset);
+
+/* Per-kernel device time of the cggos loop, measured with CUDA events on the library stream while enabled
+ * (reference analogue: the taxhm/tdsum timers, core/hmholtz.f:113,257, core/dssum.f).  kernel: "ax" (Ax incl.
+ * the fused pap), "gs" (gather-scatter incl. exchange), "update" (x,r update + weighted dot), "pupdate". */
+int nekb_prof_enable(int on);
+int nekb_prof_get(const char *kernel, double *seconds, int64_t *launches);
+
+/* ------------------------------------------------------------------------------------
+ * Multi-rank transport (host side, setup only) and device collectives
+ * ---------------------------------------------------------------------------------- */
+
+/* Host collectives the setup code needs when np > 1 (reference: gslib crystal router /
+ * MPI inside fgslib_gs_setup and gbtuple_rank8, core/navier8.f:1934-2002).  Supplied by the
+ * host program: MPI in a Fortran build, torch.distributed (gloo) in the Python harness.
+ * Counts are in bytes.  Both return 0 on success. */
+typedef int (*nekb_allgather_fn)(const void *send, void *recv, size_t bytes_per_rank, void *user);
+typedef int (*nekb_alltoallv_fn)(const void *send, const int64_t *send_bytes, void *recv,
+                                 const int64_t *recv_bytes, void *user);
+int nekb_set_transport(int rank, int nranks, nekb_allgather_fn allgather, nekb_alltoallv_fn alltoallv,
+                       void *user);
+
+/* Device collectives over NCCL (NVLink 5 / NVSwitch); replaces gop -> mpi_allreduce
+ * (core/comm_mpi.f:216-259) and gslib's pairwise exchange.  id_out/id_in: 128-byte
+ * ncclUniqueId produced on rank 0 and distributed by the host program. */
+int nekb_comm_unique_id(void *id_out_128);
+int nekb_comm_init(const void *id_in_128, int rank, int nranks);
+
+/* ------------------------------------------------------------------------------------
+ * A. Fortran-named drop-in entry points (host buffers, synchronous)
+ * ---------------------------------------------------------------------------------- */
+
+/* gslib v1.0.9 Fortran API as called at core/dssum.f:20,79,198,277 and core/hsmg.f:335-362.
+ * dom: 1 = double (only supported datatype here); op: 1 +, 2 *, 3 min, 4 max; transpose 0. */
+void fgslib_gs_setup_(int *handle, const int64_t *id, const int *n, const int *comm, const int *np);
+void fgslib_gs_op_(const int *handle, double *u, const int *dom, const int *op, const int *transpose);
+void fgslib_gs_op_many_(const int *handle, double *u1, double *u2, double *u3, double *u4, double *u5,
+                        double *u6, const int *n, const int *dom, const int *op, const int *transpose);
+void fgslib_gs_op_fields_(const int *handle, double *u, const int *stride, const int *n, const int *dom,
+                          const int *op, const int *transpose);
+void fgslib_gs_free_(const int *handle);
+
+/* core/dssum.f:1 setupds(gs_handle,nx,ny,nz,nel,melg,vertex,glo_num): set_vert
+ * (core/navier8.f:3-33 -> setvert3d :2004-2360) then fgslib_gs_setup. */
+void setupds_(int *gs_handle, const int *nx, const int *ny, const int *nz, const int *nel,
+              const int *melg, const int64_t *vertex, int64_t *glo_num);
+/* core/dssum.f:33 dssum(u,nx,ny,nz): gs_op(+) on gsh_fld(ifield) (see nekb_set_ifield). */
+void dssum_(double *u, const int *nx, const int *ny, const int *nz);
+/* core/dssum.f:100 dsop(u,op,nx,ny,nz), op is character*3: '+  ','sum','*  ','mul','m  ','min','mna',
+ * 'M  ','max','mxa' (core/dssum.f:110-158); trailing hidden length as gfortran passes it. */
+void dsop_(double *u, const char *op, const int *nx, const int *ny, const int *nz, size_t op_len);
+/* core/hmholtz.f:72 axhelm(au,u,helm1,helm2,imesh,isd) -- general 3-D branch :191-217,:225. */
+void axhelm_(double *au, const double *u, const double *helm1, const double *helm2, const int *imesh,
+             const int *isd);
+/* core/hmholtz.f:380 setprec(dpcm1,helm1,helm2,imsh,isd) incl. dssum + invcol1 (:520-521). */
+void setprec_(double *dpcm1, const double *helm1, const double *helm2, const int *imsh, const int *isd);
+/* core/hmholtz.f:611 cggo(x,f,h1,h2,mask,mult,imsh,tin,maxit,isd,binv,name): Jacobi-PCG branch
+ * (kfldfdm<0).  name is character*4 with gfortran's hidden trailing length.  The iteration count
+ * is left in nekb_niterhm() (reference: common /iterhm/ niterhm, :638). */
+void cggo_(double *x, const double *f, const double *h1, const double *h2, const double *mask,
+           const double *mult, const int *imsh, const double *tin, const int *maxit, const int *isd,
+           const double *binv, const char *name, size_t name_len);
+/* examples/bp5/bp5.usr:797 cggos(u1,rhs1,x1,rmult,binv,tin,maxit,bpname) with bpname='bp5'.
+ * On return *maxit holds the iterations performed (bp5.usr:893). */
+void cggos_(double *u1, const double *rhs1, const double *x1, const double *rmult, const double *binv,
+            const double *tin, int *maxit, const char *bpname, size_t bpname_len);
+/* examples/bp5/bp5.usr:1389 axhm1(pap,ap1,p1,h1,h2,bpname) with bpname='bp5' (:1309-1341). */
+void axhm1_(double *pap, double *ap1, const double *p1, const double *h1, const double *h2,
+            const char *bpname, size_t bpname_len);
+/* core/math.f:775 glsc3(a,b,mult,n) = global sum a*b*mult (gop '+'). */
+double glsc3_(const double *a, const double *b, const double *mult, const int *n);
+int nekb_niterhm(void);
+
+/* ------------------------------------------------------------------------------------
+ * B. Registration of the COMMON-block state the Fortran routines read implicitly
+ * ---------------------------------------------------------------------------------- */
+
+/* /dimn/ nelv, nelt (core/SIZE.inc) */
+int nekb_set_nel(int nelv, int nelt);
+/* /dxyz/ dxm1, dxtm1 (core/DXYZ:4-9); dym1/dzm1 are identical on the GLL mesh
+ * (core/coef.f:271-273).  lx1*lx1 doubles each, Fortran order. */
+int nekb_set_dxyz(const double *dxm1, const double *dxtm1);
+/* /gauss/ zgm1(lx1,1), wxm1(lx1) (core/WZ): GLL points and weights.  Optional: without it (and without
+ * nekb_set_dxyz) the library computes its own GLL operators (core/speclib.f:107 ZWGLL, :800 DGLL). */
+int nekb_set_gll(const double *zgm1, const double *wxm1);
+/* /gmfact/ g1m1..g6m1 (core/GEOM:42-48, order rr,ss,tt,rs,rt,st) and /mass/ bm1 (core/MASS:4),
+ * each lx1^3*nelt doubles.  Call again whenever geom_reset/gengeom ran. */
+int nekb_set_geom(const double *g1m1, const double *g2m1, const double *g3m1, const double *g4m1,
+                  const double *g5m1, const double *g6m1, const double *bm1);
+/* BP5's interleaved gf(6,lx1^3,nelt), order rr,rs,rt,ss,st,tt (examples/bp5/bp5.usr:332,623-699). */
+int nekb_set_geom_bp5(const double *gf);
+/* Computes the factors on the device from /gxyz/ xm1,ym1,zm1 (host, lx1^3*nelt each) instead of
+ * uploading them: bp5_form != 0 -> geodatstd (examples/bp5/bp5.usr:623-699), else glmapm1 + geodat1
+ * (core/coef.f:555-631, :633-784), which also yields bm1. */
+int nekb_set_geom_from_xyz(const double *xm1, const double *ym1, const double *zm1, int bp5_form);
+/* Host copies of the registered / computed factors (any pointer may be NULL): core order g1m1..g6m1, bm1, and
+ * BP5's interleaved gf(6,lx1^3,nelt). */
+int nekb_get_geom(double *g1m1, double *g2m1, double *g3m1, double *g4m1, double *g5m1, double *g6m1, double *bm1,
+                  double *gf);
+/* /fastmd/ ifdfrm(lelt) (core/hmholtz.f:89): NULL = all elements deformed (param(59)=1 default,
+ * core/reader_par.f:78). */
+int nekb_set_ifdfrm(const int *ifdfrm);
+/* v1mask of bp5.usr:142-153 xmask1 (COMMON v1mask, core/SOLN). */
+int nekb_set_v1mask(const double *v1mask);
+/* TSTEP ifield and /comm_handles/ gsh_fld(ifield) (core/PARALLEL.default:26-27), istep, and the
+ * scalars cggo reads: volvm1, voltm1 (core/MASS), param(18,22) stay at their defaults. */
+int nekb_set_ifield(int ifield);
+int nekb_set_field_handle(int ifield, int gs_handle);
+int nekb_set_step_info(int istep, double volvm1, double voltm1);
+
+/* ------------------------------------------------------------------------------------
+ * C. Device-resident API (pointers are device pointers valid on the library's device)
+ * ---------------------------------------------------------------------------------- */
+
+int nekb_gs_setup(int *handle, const int64_t *id_host, int64_t n);       /* ids on the host   */
+int nekb_gs_setup_dev(int *handle, const int64_t *id_dev, int64_t n);    /* ids on the device */
+/* In-place gs_op on a device vector; mask_dev may be NULL, else u is multiplied by the mask after
+ * the combine (fuses col2(w,mask), core/hmholtz.f:798 / xmask1 bp5.usr:850). */
+int nekb_gs_op_dev(int handle, double *u_dev, int op, const double *mask_dev);
+int nekb_gs_free(int handle);
+/* Sizes of the handle's local map: groups (ids held by >= 2 local entries) and their members. */
+int nekb_gs_info(int handle, int64_t *ngroups, int64_t *nmembers, int64_t *nshared_remote);
+/* Copies the handle's CSR (group offsets, member indices, ascending) to host arrays for bit-exact
+ * comparison of the gather-scatter index maps. */
+int nekb_gs_get_map(int handle, int64_t *off_host, int32_t *idx_host);
+
+/* Remote half of the handle's map (np > 1): number of neighbour ranks and exchange items; then the neighbour
+ * ranks (ascending), per-neighbour offsets [npeers+1] and, per item, the local index whose value is sent
+ * (items of one neighbour are ordered by ascending global id on both sides). */
+int nekb_gs_remote_info(int handle, int *npeers, int64_t *nitems);
+int nekb_gs_get_remote(int handle, int *peers, int64_t *peer_off, int32_t *item_rep_idx);
+
+/* ap = A p with registered BP5 geometry; pap_dev (device, may be NULL) receives sum p*ap. */
+int nekb_ax_bp5_dev(double *ap_dev, const double *p_dev, double *pap_dev);
+int nekb_axhelm_dev(double *au_dev, const double *u_dev, const double *h1_dev, const double *h2_dev,
+                    int imesh);
+/* dpc = 1/dssum(diag A) on device buffers (core/hmholtz.f:380-524). */
+int nekb_setprec_dev(double *dpc_dev, const double *h1_dev, const double *h2_dev, int imesh);
+/* Whole cggo solve (core/hmholtz.f:611-846, Jacobi branch) on device buffers.  hist_host (may be NULL,
+ * 3*(maxit+2) doubles): per iteration rtz1, rbn2, rho.  *niter = niterhm. */
+int nekb_cggo_dev(double *x_dev, const double *f_dev, const double *h1_dev, const double *h2_dev,
+                  const double *mask_dev, const double *mult_dev, const double *binv_dev, int imsh, double tin,
+                  int maxit, int *niter, double *hist_host);
+/* Whole cggos solve on device buffers.  hist_host (may be NULL, 3*maxit doubles) receives per
+ * iteration pap, rtz, max|u-x1| (the latter only when tol>0, else 0).  Returns iterations in *niter. */
+int nekb_cggos_dev(double *u_dev, const double *rhs_dev, const double *x1_dev, const double *rmult_dev,
+                   double tol, int maxit, int *niter, double *hist_host);
+
+/* ------------------------------------------------------------------------------------
+ * D. Host-side setup feeding the path
+ * ---------------------------------------------------------------------------------- */
+
+/* core/navier8.f:2004-2360 setvert3d with ifcenter=.false.: glo_num(nx^3,nel) from
+ * vertex(8,nel) (symmetric corner order).  Single-process form: np only selects the mod-np
+ * bucketing of gbtuple_rank8 (:1964), so the result equals an np-rank reference run.  With a
+ * transport registered (nekb_set_transport) and np == nranks the tuples are exchanged for real. */
+int nekb_setvert3d(int64_t *glo_num, int64_t *ngv, int nx, int64_t nel, const int64_t *vertex, int np);
+
+/* Host-only: which of this rank's distinct non-zero ids (ascending) also live on other ranks; the rendezvous
+ * on rank (id mod np) that gslib's gs_setup performs, over the registered transport.  Call once with
+ * peers == NULL to obtain the sizes, then again with arrays: peers[npeers], peer_off[npeers+1],
+ * item_ids[nitems] (per neighbour, ascending). */
+int nekb_gs_discover(const int64_t *uniq_ids, int64_t n, int *npeers, int64_t *nitems, int *peers,
+                     int64_t *peer_off, int64_t *item_ids);
+
+/* Synthetic BP5 case (examples/bp5: genbox.in box, bp5.usr usrdat2/bp5): builds on the device the
+ * rank-local part of an nelx*nely*nelz box of [0,1]^3 split into px*py*pz bricks
+ * (rank = ix + px*(iy + px*iz); RCB-equivalent of the reference partition),
+ * its GLL coordinates, gf, numbering, gs handle, mask, multiplicity, e1 = mask*dsavg(ran1 field),
+ * r1 = mask*dssum(A e1).  deform != 0 applies a smooth coordinate perturbation (tests). */
+int nekb_bp5_setup(int nelx, int nely, int nelz, int px, int py, int pz, double deform);
+/* One cggos solve (bp5.usr:367-369 body) on the device-resident case; returns seconds measured
+ * with CUDA events on the library stream (excluded: nothing; the whole call). */
+int nekb_bp5_solve(double tol, int maxit, int *niter, double *seconds, double *hist_host);
+/* glrdif(u1,e1) of bp5.usr:373,422-447 (global max over ranks when NCCL is up). */
+int nekb_bp5_relerr(double *relerr);
+/* Host copies of the case's arrays (for parity tests): which = "u1","e1","r1","mask","mult","gf"
+ * (reference layout gf(6,lx1^3,nelt)),"xm1","ym1","zm1","bm1","glo_num"(int64).  n_bytes is the buffer capacity. */
+int nekb_bp5_get(const char *which, void *host_out, size_t n_bytes);
+int64_t nekb_bp5_nel_local(void);
+/* Device pointer of one of the case arrays (same names; also "bm1" and "g" = device layout
+ * [nelt][6][lx1^3]) for the device-resident API. */
+void *nekb_bp5_devptr(const char *which);
+int nekb_bp5_gs_handle(void);
+
+/* ------------------------------------------------------------------------------------
+ * E. Plain device-memory helpers for host programs without a CUDA binding of their own
+ * ---------------------------------------------------------------------------------- */
+void *nekb_dev_alloc(size_t bytes);
+void nekb_dev_free(void *dev);
+int nekb_h2d(void *dev, const void *host, size_t bytes);
+int nekb_d2h(void *host, const void *dev, size_t bytes);
+int nekb_sync(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEKB200_H */

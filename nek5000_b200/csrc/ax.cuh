@@ -1,0 +1,217 @@
+// ax.cuh -- matrix-free Helmholtz / Poisson operator on (N+1)^3 element tiles.
+//
+// Replaces core/hmholtz.f:72-259 axhelm (general 3-D branch :191-217 + :225) and
+// examples/bp5/bp5.usr:1278-1341 ax_e_bp5 / axhm1_bp5 (incl. the fused pap = sum p.Ap).
+// The six mxm calls + 15 pointwise sweeps of the reference are fused into one pass:
+//   ur,us,ut = D u ; (wr,ws,wt) = G (ur,us,ut) [* h1] ; w = D^T (wr,ws,wt) [+ h2 B u]
+//
+// Data layout in HBM: u, w as in Nek (i fastest, element slowest).  Geometric factors are stored
+// element-major, component-next:  g[e][c][k][j][i], c = rr,rs,rt,ss,st,tt, so that each component
+// of each k-slice is one coalesced 8*NX*NX-byte run and a whole element is one contiguous
+// 6*NX^3*8-byte block (24 KB at N=7) for bulk (TMA) staging.
+//
+// Thread mapping (kernel v1): NX*NX threads per element, thread (i,j) owns the k-column u(i,j,:)
+// in registers; the r/s contractions go through one shared-memory copy of the element tile, the t
+// contraction stays in registers with D read from the constant bank.  EPB elements per CTA,
+// persistent grid (multiple of the SM count) striding over the elements.
+#pragma once
+#include "ctx.cuh"
+
+namespace nekb {
+
+template <int NX, int EPB, bool HELM>
+__global__ void __launch_bounds__(NX *NX *EPB)
+    ax_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__restrict__ w,
+              const double *__restrict__ h1, const double *__restrict__ h2, const double *__restrict__ bm1, int nel,
+              double *__restrict__ partials, unsigned *counter, double *pap_out)
+{
+    constexpr int N2 = NX * NX, N3 = NX * NX * NX;
+    __shared__ double s_u[EPB][N3];
+    __shared__ double s_wr[2][EPB][N2];
+    __shared__ double s_ws[2][EPB][N2];
+    __shared__ double s_red[33];
+
+    const int tid = threadIdx.x;
+    const int es = tid / N2, ij = tid % N2, i = ij % NX, j = ij / NX;
+
+    double Di[NX], Dj[NX], DTi[NX], DTj[NX];
+#pragma unroll
+    for (int m = 0; m < NX; m++) {
+        Di[m] = c_D[i * NX + m];
+        Dj[m] = c_D[j * NX + m];
+        DTi[m] = c_D[m * NX + i];
+        DTj[m] = c_D[m * NX + j];
+    }
+
+    double pap = 0.0;
+    for (int e0 = blockIdx.x * EPB; e0 < nel; e0 += gridDim.x * EPB) {
+        const int e = e0 + es;
+        const bool act = e < nel;
+        const size_t eo = (size_t)(act ? e : 0) * N3;
+        const double *__restrict__ ge = g + 6 * eo;
+
+        double ucol[NX], wcol[NX];
+#pragma unroll
+        for (int k = 0; k < NX; k++) {
+            ucol[k] = act ? u[eo + k * N2 + ij] : 0.0;
+            s_u[es][k * N2 + ij] = ucol[k];
+            wcol[k] = 0.0;
+        }
+        __syncthreads();
+
+#pragma unroll
+        for (int k = 0; k < NX; k++) {
+            const int q = k * N2 + ij;
+            double G0 = 0, G1 = 0, G2 = 0, G3 = 0, G4 = 0, G5 = 0, hh = 1.0;
+            if (act) {
+                G0 = ge[0 * N3 + q];
+                G1 = ge[1 * N3 + q];
+                G2 = ge[2 * N3 + q];
+                G3 = ge[3 * N3 + q];
+                G4 = ge[4 * N3 + q];
+                G5 = ge[5 * N3 + q];
+                if (HELM) hh = h1[eo + q];
+            }
+            double ur = 0.0, us = 0.0, ut = 0.0;
+#pragma unroll
+            for (int m = 0; m < NX; m++) {
+                ur = fma(Di[m], s_u[es][k * N2 + j * NX + m], ur);
+                us = fma(Dj[m], s_u[es][k * N2 + m * NX + i], us);
+                ut = fma(c_D[k * NX + m], ucol[m], ut);
+            }
+            double wr = fma(G0, ur, fma(G1, us, G2 * ut));
+            double ws = fma(G1, ur, fma(G3, us, G4 * ut));
+            double wt = fma(G2, ur, fma(G4, us, G5 * ut));
+            if (HELM) {
+                wr *= hh;
+                ws *= hh;
+                wt *= hh;
+            }
+            s_wr[k & 1][es][ij] = wr;
+            s_ws[k & 1][es][ij] = ws;
+#pragma unroll
+            for (int m = 0; m < NX; m++) wcol[m] = fma(c_D[k * NX + m], wt, wcol[m]);
+            __syncthreads();
+            double acc = wcol[k];
+#pragma unroll
+            for (int m = 0; m < NX; m++) {
+                acc = fma(DTi[m], s_wr[k & 1][es][j * NX + m], acc);
+                acc = fma(DTj[m], s_ws[k & 1][es][m * NX + i], acc);
+            }
+            wcol[k] = acc;
+        }
+        if (act) {
+#pragma unroll
+            for (int k = 0; k < NX; k++) {
+                const int q = k * N2 + ij;
+                double v = wcol[k];
+                if (HELM && h2 != nullptr) v = fma(h2[eo + q] * bm1[eo + q], ucol[k], v);
+                w[eo + q] = v;
+                pap = fma(ucol[k], v, pap);
+            }
+        }
+        // s_u may be overwritten right away: every thread has passed the barrier of k = NX-1, which
+        // follows its last read of s_u; s_wr/s_ws are double buffered across that barrier.
+    }
+    if (pap_out != nullptr) {
+        double b = block_reduce(pap, s_red);
+        grid_reduce(b, partials, counter, s_red, [=](double t) { *pap_out = t; });
+    }
+}
+
+// Jacobi diagonal, core/hmholtz.f:380-524 setprec before its dssum + invcol1 (:520-521).
+// One CTA per element, one thread per node.
+template <int NX>
+__global__ void __launch_bounds__(NX *NX *NX)
+    setprec_kernel(double *__restrict__ dpc, const double *__restrict__ g, const double *__restrict__ h1,
+                   const double *__restrict__ h2, const double *__restrict__ bm1, int nel)
+{
+    constexpr int N2 = NX * NX, N3 = NX * NX * NX, L = NX - 1;
+    __shared__ double s_g[3][N3];
+    const int e = blockIdx.x, q = threadIdx.x;
+    const int i = q % NX, j = (q / NX) % NX, k = q / N2;
+    const double *ge = g + (size_t)e * 6 * N3;
+    s_g[0][q] = ge[0 * N3 + q];  // rr
+    s_g[1][q] = ge[3 * N3 + q];  // ss
+    s_g[2][q] = ge[5 * N3 + q];  // tt
+    __syncthreads();
+    double a = 0.0;
+#pragma unroll
+    for (int m = 0; m < NX; m++) a = fma(s_g[0][k * N2 + j * NX + m], c_D[m * NX + i] * c_D[m * NX + i], a);
+#pragma unroll
+    for (int m = 0; m < NX; m++) a = fma(s_g[1][k * N2 + m * NX + i], c_D[m * NX + j] * c_D[m * NX + j], a);
+#pragma unroll
+    for (int m = 0; m < NX; m++) a = fma(s_g[2][m * N2 + j * NX + i], c_D[m * NX + k] * c_D[m * NX + k], a);
+    // cross terms, added by the reference only at the 8 corners (:440-468); zero factors were stored
+    // for undeformed elements, so no flag is needed here.
+    if ((i == 0 || i == L) && (j == 0 || j == L) && (k == 0 || k == L)) {
+        const double grs = ge[1 * N3 + q], grt = ge[2 * N3 + q], gst = ge[4 * N3 + q];
+        const double di = c_D[i * NX + i], dj = c_D[j * NX + j], dk = c_D[k * NX + k];
+        a = a + grs * di * dj + grt * di * dk;
+        a = a + grs * dj * di + gst * dj * dk;
+        a = a + grt * dk * di + gst * dk * dj;
+    }
+    const size_t o = (size_t)e * N3 + q;
+    a = a * h1[o];
+    a = fma(h2[o], bm1[o], a);
+    dpc[o] = a;
+}
+
+template <int NX, int EPB>
+inline void launch_ax_t(const double *u, double *w, const double *h1, const double *h2, int nel, double *pap_out)
+{
+    Ctx &c = ctx();
+    const int ngroups = (nel + EPB - 1) / EPB;
+    const int grid = grid_for(ngroups, 4);
+    c.partials.ensure(4 * 148 * 16);
+    unsigned *counter = &c.sc.p->counter[0];
+    if (h1 != nullptr)
+        ax_kernel<NX, EPB, true><<<grid, NX * NX * EPB, 0, c.stream>>>(u, c.g.p, w, h1, h2, c.bm1.p, nel,
+                                                                        c.partials.p, counter, pap_out);
+    else
+        ax_kernel<NX, EPB, false><<<grid, NX * NX * EPB, 0, c.stream>>>(u, c.g.p, w, nullptr, nullptr, nullptr, nel,
+                                                                         c.partials.p, counter, pap_out);
+    NEKB_LAUNCHED();
+}
+
+// w = A u (h1 == nullptr: pure stiffness as in BP5) ; optional pap_out (device) = sum u.w
+inline void launch_ax(const double *u, double *w, const double *h1, const double *h2, int nel, double *pap_out)
+{
+    Ctx &c = ctx();
+    NEKB_REQUIRE(c.have_geom && c.have_D, "geometry / derivative matrix not registered");
+    if (nel <= 0) {
+        if (pap_out) NEKB_CUDA(cudaMemsetAsync(pap_out, 0, sizeof(double), c.stream));
+        return;
+    }
+    switch (c.nx) {
+        case 2: launch_ax_t<2, 32>(u, w, h1, h2, nel, pap_out); break;
+        case 3: launch_ax_t<3, 8>(u, w, h1, h2, nel, pap_out); break;
+        case 4: launch_ax_t<4, 8>(u, w, h1, h2, nel, pap_out); break;
+        case 5: launch_ax_t<5, 4>(u, w, h1, h2, nel, pap_out); break;
+        case 6: launch_ax_t<6, 4>(u, w, h1, h2, nel, pap_out); break;
+        case 7: launch_ax_t<7, 2>(u, w, h1, h2, nel, pap_out); break;
+        case 8: launch_ax_t<8, 2>(u, w, h1, h2, nel, pap_out); break;
+        case 10: launch_ax_t<10, 1>(u, w, h1, h2, nel, pap_out); break;
+        case 12: launch_ax_t<12, 1>(u, w, h1, h2, nel, pap_out); break;
+        default: NEKB_REQUIRE(false, "unsupported lx1 (supported: 2-8, 10, 12)");
+    }
+}
+
+inline void launch_setprec(double *dpc, const double *h1, const double *h2, int nel)
+{
+    Ctx &c = ctx();
+    NEKB_REQUIRE(c.have_geom && c.have_D, "geometry / derivative matrix not registered");
+    if (nel <= 0) return;
+    switch (c.nx) {
+#define NEKB_CASE(NXV)                                                                                         \
+    case NXV:                                                                                                  \
+        setprec_kernel<NXV><<<nel, NXV * NXV * NXV, 0, c.stream>>>(dpc, c.g.p, h1, h2, c.bm1.p, nel);        \
+        break;
+        NEKB_CASE(2) NEKB_CASE(3) NEKB_CASE(4) NEKB_CASE(5) NEKB_CASE(6) NEKB_CASE(7) NEKB_CASE(8) NEKB_CASE(10)
+#undef NEKB_CASE
+        default: NEKB_REQUIRE(false, "unsupported lx1 for setprec (supported: 2-8, 10)");
+    }
+    NEKB_LAUNCHED();
+}
+
+}  // namespace nekb

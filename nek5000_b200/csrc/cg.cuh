@@ -1,0 +1,473 @@
+// cg.cuh -- device-resident conjugate-gradient drivers.
+//
+// cggos : examples/bp5/bp5.usr:797-899 (identity preconditioner, fixed iteration count when tol<0)
+// cggo  : core/hmholtz.f:611-846, Jacobi branch (kfldfdm<0), incl. the exit rule of :778
+//
+// All CG scalars live on the device (struct CgScalars); the reductions are two-level with a fixed
+// combination tree (common.cuh grid_reduce), the closing kernel's last block advances the iteration
+// counter, so one iteration is a fixed sequence of launches with constant arguments: no host
+// synchronisation inside the loop, and the sequence can be replayed from a CUDA graph.
+#pragma once
+#include "ax.cuh"
+#include "gs.cuh"
+
+namespace nekb {
+
+inline void comm_allreduce_sum(double *dev, int count);  // comm.cuh (no-op on one rank)
+inline void comm_allreduce_max(double *dev, int count);
+
+constexpr int CG_THREADS = 256;
+constexpr int CG_PART_STRIDE = 1024;  // partial-sum region per kernel kind
+
+inline int cg_grid(int64_t n)
+{
+    int64_t b = (n / 2 + CG_THREADS - 1) / CG_THREADS;
+    int64_t cap = (int64_t)ctx().num_sms * 8;
+    if (cap > CG_PART_STRIDE) cap = CG_PART_STRIDE - (CG_PART_STRIDE % ctx().num_sms);
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// ---------------------------------------------------------------------------------------------- cggos
+// bp5.usr:835-845: u=0, r=rhs, p=dpc*r (dpc=1), rpp1 = sum rmult*p*r
+__global__ void __launch_bounds__(CG_THREADS)
+    cggos_init_kernel(double *__restrict__ u, double *__restrict__ r, double *__restrict__ p,
+                      const double *__restrict__ rhs, const double *__restrict__ mult, int64_t n, CgScalars *sc,
+                      double *partials)
+{
+    __shared__ double red[33];
+    double s = 0.0;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const double rv = rhs[t];
+        u[t] = 0.0;
+        r[t] = rv;
+        p[t] = rv;
+        s = fma(mult[t] * rv, rv, s);
+    }
+    double b = block_reduce(s, red);
+    grid_reduce(b, partials, &sc->counter[1], red, [=](double tot) {
+        sc->rtz1 = tot;
+        sc->it = 0;
+        sc->done = 0;
+    });
+}
+
+// bp5.usr:853-866: alpha = rpp1/pap ; u += alpha p ; r -= alpha (mask*ap) ; rz = sum rmult*r*r ;
+// optional err = max|u-x1|.  (xmask1 of :850 is applied here instead of in a separate sweep.)
+template <bool ERR>
+__global__ void __launch_bounds__(CG_THREADS)
+    cggos_update_kernel(double *__restrict__ u, double *__restrict__ r, const double *__restrict__ p,
+                        const double *__restrict__ ap, const double *__restrict__ mask,
+                        const double *__restrict__ mult, const double *__restrict__ x1, int64_t n, CgScalars *sc,
+                        double *partials, double *hist)
+{
+    __shared__ double red[33];
+    const double pap = sc->work[0];
+    const double alpha = sc->rtz1 / pap;
+    double s = 0.0, emax = 0.0;
+    const int64_t n2 = n >> 1;
+    double2 *u2 = reinterpret_cast<double2 *>(u), *r2 = reinterpret_cast<double2 *>(r);
+    const double2 *p2 = reinterpret_cast<const double2 *>(p), *ap2 = reinterpret_cast<const double2 *>(ap),
+                  *mk2 = reinterpret_cast<const double2 *>(mask), *mu2 = reinterpret_cast<const double2 *>(mult),
+                  *x2 = reinterpret_cast<const double2 *>(x1);
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n2; t += (int64_t)gridDim.x * blockDim.x) {
+        double2 uv = u2[t], rv = r2[t];
+        const double2 pv = p2[t], av = ap2[t], mk = mk2[t], mu = mu2[t];
+        uv.x = fma(alpha, pv.x, uv.x);
+        uv.y = fma(alpha, pv.y, uv.y);
+        rv.x = fma(-alpha, av.x * mk.x, rv.x);
+        rv.y = fma(-alpha, av.y * mk.y, rv.y);
+        u2[t] = uv;
+        r2[t] = rv;
+        s = fma(mu.x * rv.x, rv.x, s);
+        s = fma(mu.y * rv.y, rv.y, s);
+        if (ERR) {
+            const double2 xv = x2[t];
+            emax = fmax(emax, fmax(fabs(uv.x - xv.x), fabs(uv.y - xv.y)));
+        }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // odd tail (never for lx1 even)
+        const int64_t t = n - 1;
+        u[t] = fma(alpha, p[t], u[t]);
+        r[t] = fma(-alpha, ap[t] * mask[t], r[t]);
+        s = fma(mult[t] * r[t], r[t], s);
+        if (ERR) emax = fmax(emax, fabs(u[t] - x1[t]));
+    }
+    double b = block_reduce(s, red);
+    if (ERR) {
+        double bm = block_reduce<true>(emax, red);
+        grid_reduce<true>(bm, partials + CG_PART_STRIDE, &sc->counter[3], red, [=](double tot) { sc->work[1] = tot; });
+    }
+    grid_reduce(b, partials, &sc->counter[2], red, [=](double tot) { sc->rtz2 = tot; });  // new (r,z)
+}
+
+// bp5.usr:879-884: beta = rpp1/rpp2 ; p = z + beta p (z = r).  The last block to finish rotates the
+// scalars and advances the iteration counter.
+__global__ void __launch_bounds__(CG_THREADS)
+    cggos_pupdate_kernel(double *__restrict__ p, const double *__restrict__ r, int64_t n, CgScalars *sc, double *hist)
+{
+    const double rz_old = sc->rtz1, rz_new = sc->rtz2;
+    const double beta = rz_new / rz_old;
+    const int64_t n2 = n >> 1;
+    double2 *p2 = reinterpret_cast<double2 *>(p);
+    const double2 *r2 = reinterpret_cast<const double2 *>(r);
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n2; t += (int64_t)gridDim.x * blockDim.x) {
+        double2 pv = p2[t];
+        const double2 rv = r2[t];
+        pv.x = fma(beta, pv.x, rv.x);
+        pv.y = fma(beta, pv.y, rv.y);
+        p2[t] = pv;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = fma(beta, p[n - 1], r[n - 1]);
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned t = atomicInc(&sc->counter[1], gridDim.x - 1);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        hist[3 * sc->it + 0] = sc->work[0];  // pap (after the all-reduce)
+        hist[3 * sc->it + 1] = rz_new;
+        sc->rtz1 = rz_new;
+        sc->it = sc->it + 1;
+    }
+}
+
+struct CggosArgs {
+    double *u;
+    const double *rhs, *x1, *mult, *mask;
+    int gs_handle;
+    int nel;
+};
+
+// Runs the BP5 solver; returns iterations performed.  hist_host: 3 doubles per iteration
+// (pap, rtz_new, max|u-x1| or 0).
+inline int cggos_run(const CggosArgs &a, double tol, int maxit, double *hist_host)
+{
+    Ctx &c = ctx();
+    const int64_t n = (int64_t)a.nel * c.nxyz;
+    cudaStream_t s = c.stream;
+    DevBuf<double> &r = c.work[0], &p = c.work[1], &ap = c.work[2];
+    r.ensure(n);
+    p.ensure(n);
+    ap.ensure(n);
+    c.hist.ensure((size_t)3 * (maxit + 1));
+    NEKB_CUDA(cudaMemsetAsync(c.hist.p, 0, sizeof(double) * 3 * (maxit + 1), s));
+    c.partials.ensure(4 * CG_PART_STRIDE);
+    CgScalars *sc = c.sc.p;
+    const int grid = cg_grid(n);
+    const bool err = tol > 0.0;
+    GsMap &h = gs_get(a.gs_handle);
+    NEKB_REQUIRE(h.n == n, "cggos: gs handle was set up for a different vector length");
+
+    cggos_init_kernel<<<grid, CG_THREADS, 0, s>>>(a.u, r.p, p.p, a.rhs, a.mult, n, sc, c.partials.p + 1 * CG_PART_STRIDE);
+    NEKB_LAUNCHED();
+    comm_allreduce_sum(&sc->rtz1, 1);
+
+    int iters = 0;
+    bool broke = false;
+    double last_pap = 0.0, last_rz = 0.0;
+    for (int iter = 1; iter <= maxit; iter++) {
+        prof_begin(PROF_AX);
+        launch_ax(p.p, ap.p, nullptr, nullptr, a.nel, &sc->work[0]);
+        prof_end(PROF_AX);
+        comm_allreduce_sum(&sc->work[0], 1);
+        prof_begin(PROF_GS);
+        gs_op(a.gs_handle, ap.p, 1, nullptr);
+        prof_end(PROF_GS);
+        prof_begin(PROF_UPDATE);
+        if (err)
+            cggos_update_kernel<true><<<grid, CG_THREADS, 0, s>>>(a.u, r.p, p.p, ap.p, a.mask, a.mult, a.x1, n, sc,
+                                                                  c.partials.p + 2 * CG_PART_STRIDE, c.hist.p);
+        else
+            cggos_update_kernel<false><<<grid, CG_THREADS, 0, s>>>(a.u, r.p, p.p, ap.p, a.mask, a.mult, a.x1, n, sc,
+                                                                   c.partials.p + 2 * CG_PART_STRIDE, c.hist.p);
+        NEKB_LAUNCHED();
+        prof_end(PROF_UPDATE);
+        comm_allreduce_sum(&sc->rtz2, 1);
+        iters = iter;
+        if (err) {  // bp5.usr:869-874: exit on enorm < tol needs the host in the loop
+            comm_allreduce_max(&sc->work[1], 1);
+            double e = 0.0;
+            NEKB_CUDA(cudaMemcpyAsync(&e, &sc->work[1], sizeof(double), cudaMemcpyDeviceToHost, s));
+            NEKB_CUDA(cudaStreamSynchronize(s));
+            if (hist_host) hist_host[3 * (iter - 1) + 2] = e;
+            if (e < tol) {  // the closing kernel is skipped: record this iteration's scalars here
+                CgScalars hs;
+                NEKB_CUDA(cudaMemcpyAsync(&hs, sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, s));
+                NEKB_CUDA(cudaStreamSynchronize(s));
+                last_pap = hs.work[0];
+                last_rz = hs.rtz2;
+                broke = true;
+                break;
+            }
+        }
+        prof_begin(PROF_PUPDATE);
+        cggos_pupdate_kernel<<<grid, CG_THREADS, 0, s>>>(p.p, r.p, n, sc, c.hist.p);
+        NEKB_LAUNCHED();
+        prof_end(PROF_PUPDATE);
+    }
+    if (prof().on) {
+        NEKB_CUDA(cudaStreamSynchronize(s));
+        prof_collect();
+    }
+    if (hist_host) {
+        std::vector<double> hh((size_t)3 * (maxit + 1));
+        NEKB_CUDA(cudaMemcpyAsync(hh.data(), c.hist.p, sizeof(double) * hh.size(), cudaMemcpyDeviceToHost, s));
+        NEKB_CUDA(cudaStreamSynchronize(s));
+        for (int i = 0; i < iters; i++) {
+            hist_host[3 * i + 0] = hh[3 * i + 0];
+            hist_host[3 * i + 1] = hh[3 * i + 1];
+            if (!err) hist_host[3 * i + 2] = 0.0;
+        }
+        if (broke) {
+            hist_host[3 * (iters - 1) + 0] = last_pap;
+            hist_host[3 * (iters - 1) + 1] = last_rz;
+        }
+    }
+    return iters;
+}
+
+// ---------------------------------------------------------------------------------------------- cggo
+struct CggoArgs {
+    double *x;
+    const double *f, *h1, *h2, *mask, *mult, *binv;
+    int gs_handle;
+    int nel;
+    double vol;
+    int istep;
+};
+
+// hmholtz.f:695-697: r=f, x=0, p=0 ; :699 fmax = glamax(f)
+__global__ void __launch_bounds__(CG_THREADS)
+    cggo_init_kernel(double *__restrict__ x, double *__restrict__ r, double *__restrict__ p,
+                     const double *__restrict__ f, int64_t n, CgScalars *sc, double *partials)
+{
+    __shared__ double red[33];
+    double m = 0.0;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const double fv = f[t];
+        x[t] = 0.0;
+        r[t] = fv;
+        p[t] = 0.0;
+        m = fmax(m, fabs(fv));
+    }
+    double b = block_reduce<true>(m, red);
+    grid_reduce<true>(b, partials, &sc->counter[1], red, [=](double tot) {
+        sc->work[2] = tot;  // fmax
+        sc->it = 0;
+        sc->done = 0;
+        sc->niter = 0;
+        sc->rtz1 = 1.0;  // :723
+        sc->rho = 0.0;
+    });
+}
+
+// :730 z = r*d ; :754-760 scalar(1) = sum z r mult, scalar(2) = sum mult binv r r (vlsc32)
+__global__ void __launch_bounds__(CG_THREADS)
+    cggo_dots_kernel(const double *__restrict__ r, const double *__restrict__ d, const double *__restrict__ mult,
+                     const double *__restrict__ binv, int64_t n, CgScalars *sc, double *partials)
+{
+    __shared__ double red[33];
+    if (sc->done) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const double rv = r[t], mu = mult[t];
+        const double z = rv * d[t];
+        s1 = fma(z * rv, mu, s1);
+        s2 = fma(mu * binv[t] * rv, rv, s2);
+    }
+    double b1 = block_reduce(s1, red);
+    double b2 = block_reduce(s2, red);
+    grid_reduce(b1, partials, &sc->counter[2], red, [=](double tot) { sc->work[0] = tot; });
+    grid_reduce(b2, partials + CG_PART_STRIDE, &sc->counter[3], red, [=](double tot) { sc->work[1] = tot; });
+}
+
+// :761-791 scalar bookkeeping and the convergence test (single thread).
+__global__ void cggo_check_kernel(CgScalars *sc, double vol, double tin, int istep, int niter_max, double *hist)
+{
+    if (sc->done) return;
+    const int iter = sc->it + 1;
+    sc->rtz2 = sc->rtz1;
+    sc->rtz1 = sc->work[0];
+    const double rbn2 = sqrt(sc->work[1] / vol);
+    sc->rbn2 = rbn2;
+    if (iter == 1) {
+        sc->rbn0 = rbn2;
+        sc->tol = (tin < 0) ? fabs(tin) * rbn2 : fabs(tin);  // :673-679,:765
+    }
+    hist[3 * (iter - 1) + 0] = sc->rtz1;
+    hist[3 * (iter - 1) + 1] = rbn2;
+    if (rbn2 <= sc->tol && (iter > 1 || istep <= 5)) {  // :778
+        sc->done = 1;
+        sc->niter = iter - 1;
+    } else if (iter > niter_max) {
+        sc->done = 1;
+        sc->niter = niter_max;
+    }
+}
+
+// :793-795 beta = rtz1/rtz2 (0 on the first iteration) ; p = z + beta p  (add2s1)
+__global__ void __launch_bounds__(CG_THREADS)
+    cggo_pupdate_kernel(double *__restrict__ p, const double *__restrict__ r, const double *__restrict__ d, int64_t n,
+                        const CgScalars *sc)
+{
+    if (sc->done) return;
+    const double beta = (sc->it == 0) ? 0.0 : sc->rtz1 / sc->rtz2;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+        p[t] = fma(beta, p[t], r[t] * d[t]);
+}
+
+// :798 w *= mask ; :801 rho = glsc3(w,p,mult)
+__global__ void __launch_bounds__(CG_THREADS)
+    cggo_rho_kernel(double *__restrict__ w, const double *__restrict__ p, const double *__restrict__ mask,
+                    const double *__restrict__ mult, int64_t n, CgScalars *sc, double *partials)
+{
+    __shared__ double red[33];
+    if (sc->done) return;
+    double s = 0.0;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const double wv = w[t] * mask[t];
+        w[t] = wv;
+        s = fma(wv * p[t], mult[t], s);
+    }
+    double b = block_reduce(s, red);
+    grid_reduce(b, partials, &sc->counter[2], red, [=](double tot) { sc->rho = tot; });
+}
+
+// :802-805 alpha = rtz1/rho ; x += alpha p ; r -= alpha w.  Last block advances the counter.
+__global__ void __launch_bounds__(CG_THREADS)
+    cggo_xr_kernel(double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
+                   const double *__restrict__ w, int64_t n, CgScalars *sc, double *hist)
+{
+    if (sc->done) return;
+    const double rho = sc->rho;
+    const double alpha = sc->rtz1 / rho;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        x[t] = fma(alpha, p[t], x[t]);
+        r[t] = fma(-alpha, w[t], r[t]);
+    }
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned t = atomicInc(&sc->counter[1], gridDim.x - 1);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        hist[3 * sc->it + 2] = rho;
+        sc->it = sc->it + 1;
+    }
+}
+
+__global__ void __launch_bounds__(CG_THREADS)
+    invcol1_kernel(double *__restrict__ a, int64_t n)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+        a[t] = 1.0 / a[t];
+}
+
+__global__ void __launch_bounds__(CG_THREADS)
+    absmax_kernel(const double *__restrict__ a, int64_t n, double *out, double *partials, unsigned *counter)
+{
+    __shared__ double red[33];
+    double m = 0.0;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+        m = fmax(m, fabs(a[t]));
+    double b = block_reduce<true>(m, red);
+    grid_reduce<true>(b, partials, counter, red, [=](double tot) { *out = tot; });
+}
+
+// dpc = 1 / dssum(setprec_local)   (hmholtz.f:380-524)
+inline void setprec_run(double *dpc, const double *h1, const double *h2, int nel, int gs_handle)
+{
+    Ctx &c = ctx();
+    const int64_t n = (int64_t)nel * c.nxyz;
+    launch_setprec(dpc, h1, h2, nel);
+    gs_op(gs_handle, dpc, 1, nullptr);
+    invcol1_kernel<<<cg_grid(n), CG_THREADS, 0, c.stream>>>(dpc, n);
+    NEKB_LAUNCHED();
+}
+
+// Returns niterhm.  hist_host (may be NULL): 3 doubles per executed iteration (rtz1, rbn2, rho).
+// Not supported (documented in DESIGN.md): the all-Neumann null-space correction (ifmcor, :705-720)
+// and the 'PRES' branches (:641-657, :731-746).
+inline int cggo_run(const CggoArgs &a, double tin, int maxit, double *hist_host)
+{
+    Ctx &c = ctx();
+    const int64_t n = (int64_t)a.nel * c.nxyz;
+    cudaStream_t s = c.stream;
+    const int maxcg = 900;
+    const int niter = maxit < maxcg ? maxit : maxcg;
+    DevBuf<double> &r = c.work[0], &p = c.work[1], &w = c.work[2], &d = c.work[3];
+    r.ensure(n);
+    p.ensure(n);
+    w.ensure(n);
+    d.ensure(n);
+    c.hist.ensure((size_t)3 * (niter + 2));
+    NEKB_CUDA(cudaMemsetAsync(c.hist.p, 0, sizeof(double) * 3 * (niter + 2), s));
+    c.partials.ensure(4 * CG_PART_STRIDE);
+    CgScalars *sc = c.sc.p;
+    const int grid = cg_grid(n);
+    GsMap &h = gs_get(a.gs_handle);
+    NEKB_REQUIRE(h.n == n, "cggo: gs handle was set up for a different vector length");
+
+    // ifh2 (setfast :303-305): max|h2| > 0
+    absmax_kernel<<<grid, CG_THREADS, 0, s>>>(a.h2, n, &sc->work[3], c.partials.p, &sc->counter[0]);
+    NEKB_LAUNCHED();
+    comm_allreduce_max(&sc->work[3], 1);
+    double h2max = 0.0;
+    NEKB_CUDA(cudaMemcpyAsync(&h2max, &sc->work[3], sizeof(double), cudaMemcpyDeviceToHost, s));
+    NEKB_CUDA(cudaStreamSynchronize(s));
+    const double *h2_eff = (h2max > 0.0) ? a.h2 : nullptr;
+
+    setprec_run(d.p, a.h1, a.h2, a.nel, a.gs_handle);  // :690
+    cggo_init_kernel<<<grid, CG_THREADS, 0, s>>>(a.x, r.p, p.p, a.f, n, sc, c.partials.p + 1 * CG_PART_STRIDE);
+    NEKB_LAUNCHED();
+    comm_allreduce_max(&sc->work[2], 1);
+    double fmax = 0.0;
+    NEKB_CUDA(cudaMemcpyAsync(&fmax, &sc->work[2], sizeof(double), cudaMemcpyDeviceToHost, s));
+    NEKB_CUDA(cudaStreamSynchronize(s));
+    if (fmax == 0.0) return 0;  // :700-701
+
+    int launched = 0, result = -1;
+    const int batch = 8;  // iterations enqueued between two looks at the convergence flag
+    while (result < 0) {
+        for (int b = 0; b < batch; b++) {
+            cggo_dots_kernel<<<grid, CG_THREADS, 0, s>>>(r.p, d.p, a.mult, a.binv, n, sc, c.partials.p + 2 * CG_PART_STRIDE);
+            NEKB_LAUNCHED();
+            comm_allreduce_sum(&sc->work[0], 2);
+            cggo_check_kernel<<<1, 1, 0, s>>>(sc, a.vol, tin, a.istep, niter, c.hist.p);
+            NEKB_LAUNCHED();
+            cggo_pupdate_kernel<<<grid, CG_THREADS, 0, s>>>(p.p, r.p, d.p, n, sc);
+            NEKB_LAUNCHED();
+            launch_ax(p.p, w.p, a.h1, h2_eff, a.nel, nullptr);
+            gs_op(a.gs_handle, w.p, 1, nullptr);
+            cggo_rho_kernel<<<grid, CG_THREADS, 0, s>>>(w.p, p.p, a.mask, a.mult, n, sc, c.partials.p + 2 * CG_PART_STRIDE);
+            NEKB_LAUNCHED();
+            comm_allreduce_sum(&sc->rho, 1);
+            cggo_xr_kernel<<<grid, CG_THREADS, 0, s>>>(a.x, r.p, p.p, w.p, n, sc, c.hist.p);
+            NEKB_LAUNCHED();
+            launched++;
+        }
+        CgScalars hs;
+        NEKB_CUDA(cudaMemcpyAsync(&hs, sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, s));
+        NEKB_CUDA(cudaStreamSynchronize(s));
+        if (hs.done) result = hs.niter;
+        NEKB_REQUIRE(launched <= niter + 2 * batch, "cggo: convergence flag never raised");
+    }
+    if (hist_host) {
+        std::vector<double> hh((size_t)3 * (niter + 2));
+        NEKB_CUDA(cudaMemcpyAsync(hh.data(), c.hist.p, sizeof(double) * hh.size(), cudaMemcpyDeviceToHost, s));
+        NEKB_CUDA(cudaStreamSynchronize(s));
+        const int rows = result + 1 <= niter + 1 ? result + 1 : niter + 1;
+        for (int i = 0; i < 3 * rows; i++) hist_host[i] = hh[i];
+    }
+    return result;
+}
+
+}  // namespace nekb

@@ -1,0 +1,168 @@
+// ctx.cuh -- process-wide state of libnekb200 (one GPU per process, Nek's rank model).
+#pragma once
+#include "common.cuh"
+
+namespace nekb {
+
+constexpr int MAX_NX = 16;
+
+// Derivative matrix, row-major: c_D[a * nx + b] = D(a,b) = dxm1(a,b) (core/DXYZ:4).
+__constant__ double c_D[MAX_NX * MAX_NX];
+
+// Device-side scalars of the CG drivers (one cache line region, zero-initialised).
+struct CgScalars {
+    int it;                // iteration counter advanced by the last block of the closing kernel
+    int done;              // convergence flag (stock cggo path)
+    int niter;             // iterations performed at convergence
+    int pad0;
+    unsigned counter[4];   // grid_reduce tickets (one per kernel kind)
+    double rtz1, rtz2;     // cggo: (z,r) of this / previous iteration
+    double rho;            // cggo: (w,p)
+    double rbn2, rbn0, tol;
+    double work[4];
+};
+
+// Local gather-scatter map (gslib gs_setup result restated for the device).
+struct GsMap {
+    bool used = false;
+    int64_t n = 0;                 // vector length the handle was set up for
+    int64_t ngroups = 0;           // ids carried by >= 2 local entries
+    int64_t nmembers = 0;          // sum of group sizes
+    DevBuf<int32_t> goff;          // [ngroups+1] CSR offsets, groups ordered by first member
+    DevBuf<int32_t> gidx;          // [nmembers] member indices, ascending inside a group
+    // ---- remote part (np > 1): ids shared with other ranks --------------------------------------
+    int64_t nshared = 0;           // local unique ids that also live on another rank
+    std::vector<int> peers;        // neighbour ranks, ascending
+    std::vector<int64_t> peer_off; // [npeers+1] offsets into the exchange lists
+    DevBuf<int32_t> x_goff;        // [nshared+1] scatter CSR: local members of every shared id
+    DevBuf<int32_t> x_gidx;
+    DevBuf<int32_t> x_rep;         // [nshared] one local member per shared id (holds the local sum)
+    DevBuf<int32_t> x_item_sid;    // [nitems] shared-id slot of every exchange item (peer-major, id ascending)
+    DevBuf<int32_t> x_soff;        // [nshared+1] CSR slot -> contributing recv items, ascending peer
+    DevBuf<int32_t> x_sitems;
+    DevBuf<int32_t> x_nbelow;      // [nshared] how many of those peers have a lower rank than this one
+    DevBuf<double> sendbuf, recvbuf;
+    int64_t nx_members = 0;
+};
+
+struct Ctx {
+    bool inited = false;
+    int device = 0;
+    int nx = 0, nxyz = 0;
+    int nelv = 0, nelt = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string last_error;
+    void (*exit_handler)(void) = nullptr;
+
+    // registered state ----------------------------------------------------------------------------
+    std::vector<double> D_host;    // row-major D(a,b)
+    bool have_D = false;
+    std::vector<double> z_host, w_host;  // GLL points / weights (zgm1, wxm1)
+    bool have_gll = false;
+    DevBuf<double> g;              // [nelt][6][nxyz], order rr,rs,rt,ss,st,tt
+    DevBuf<double> bm1;            // [nelt][nxyz]
+    DevBuf<double> v1mask;         // bp5 mask
+    std::vector<int> ifdfrm;       // empty = all deformed
+    bool have_geom = false;
+    int ifield = 1;
+    int gsh_fld[32];
+    int istep = 0;
+    double volvm1 = 0.0, voltm1 = 0.0;
+    int niterhm = 0;
+
+    // gs handles ---------------------------------------------------------------------------------
+    std::vector<GsMap> gs;
+
+    // reduction scratch ---------------------------------------------------------------------------
+    DevBuf<double> partials;       // >= 4 * max grid
+    DevBuf<CgScalars> sc;
+    DevBuf<double> hist;           // device history arrays
+    DevBuf<double> work[8];        // CG work vectors (r, p, w, d, ...)
+    DevBuf<double> stage[8];       // device staging of the host-buffer (Fortran-named) entry points
+
+    // multi-rank ----------------------------------------------------------------------------------
+    int rank = 0, nranks = 1;
+    void *transport_user = nullptr;
+    int (*allgather)(const void *, void *, size_t, void *) = nullptr;
+    int (*alltoallv)(const void *, const int64_t *, void *, const int64_t *, void *) = nullptr;
+    void *nccl_comm = nullptr;
+};
+
+// Optional per-kernel timing with CUDA events on the library stream (bench.py's live roofline numbers).
+enum ProfCat { PROF_AX = 0, PROF_GS = 1, PROF_UPDATE = 2, PROF_PUPDATE = 3, PROF_NCAT = 4 };
+struct Prof {
+    bool on = false;
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    struct Span {
+        int cat;
+        size_t e0, e1;
+    };
+    std::vector<Span> spans;
+    double secs[PROF_NCAT] = {0, 0, 0, 0};
+    int64_t count[PROF_NCAT] = {0, 0, 0, 0};
+    size_t open_ev[PROF_NCAT] = {0, 0, 0, 0};
+};
+inline Prof &prof()
+{
+    static Prof p;
+    return p;
+}
+
+inline Ctx &ctx()
+{
+    static Ctx c;
+    return c;
+}
+
+inline size_t prof_event(cudaStream_t s)
+{
+    Prof &p = prof();
+    if (p.used == p.pool.size()) {
+        cudaEvent_t e;
+        NEKB_CUDA(cudaEventCreate(&e));
+        p.pool.push_back(e);
+    }
+    NEKB_CUDA(cudaEventRecord(p.pool[p.used], s));
+    return p.used++;
+}
+inline void prof_begin(int cat)
+{
+    if (prof().on) prof().open_ev[cat] = prof_event(ctx().stream);
+}
+inline void prof_end(int cat)
+{
+    Prof &p = prof();
+    if (p.on) p.spans.push_back({cat, p.open_ev[cat], prof_event(ctx().stream)});
+}
+// Call after the stream has been synchronised.
+inline void prof_collect()
+{
+    Prof &p = prof();
+    for (const Prof::Span &sp : p.spans) {
+        float ms = 0.f;
+        NEKB_CUDA(cudaEventElapsedTime(&ms, p.pool[sp.e0], p.pool[sp.e1]));
+        p.secs[sp.cat] += 1e-3 * ms;
+        p.count[sp.cat]++;
+    }
+    p.spans.clear();
+    p.used = 0;
+}
+
+inline void require_init()
+{
+    NEKB_REQUIRE(ctx().inited, "nekb_init has not been called");
+}
+
+// Persistent-grid size: a multiple of the SM count (B200: 148), capped by the work available.
+inline int grid_for(int64_t work_items, int ctas_per_sm)
+{
+    int64_t g = (int64_t)ctx().num_sms * ctas_per_sm;
+    if (g > work_items) g = work_items;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace nekb

@@ -1,0 +1,253 @@
+// gs.cuh -- gather-scatter (direct-stiffness summation).
+//
+// Replaces gslib v1.0.9 gs_setup / gs_op as driven by core/dssum.f:1-31 (setupds), :33-98 (dssum),
+// :100-161 (dsop), :163-208 (vec_dssum -> gs_op_many), :260-287 (nvec_dssum -> gs_op_fields).
+// Semantics: all entries (local and remote) carrying one non-zero id are replaced by their
+// sum / product / min / max; id 0 entries are untouched.
+//
+// Setup (device, CUB): compact non-zero ids -> stable radix sort by id -> run-length encode ->
+// keep runs of length >= 2 -> order groups by their first member -> CSR (goff, gidx).
+// Members are ascending inside a group and combined in that order (deterministic, no atomics).
+#pragma once
+#include <cub/cub.cuh>
+
+#include "ctx.cuh"
+
+namespace nekb {
+
+struct NonZeroId {
+    const int64_t *id;
+    __host__ __device__ bool operator()(const int32_t &i) const { return id[i] != 0; }
+};
+struct CountGe2 {
+    const int32_t *cnt;
+    __host__ __device__ bool operator()(const int32_t &r) const { return cnt[r] >= 2; }
+};
+
+__global__ void gs_gather_keys(int64_t *keys, const int64_t *id, const int32_t *idx, int64_t m)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < m; t += (int64_t)gridDim.x * blockDim.x)
+        keys[t] = id[idx[t]];
+}
+__global__ void gs_group_first(int32_t *first, int32_t *gcnt, const int32_t *sel_run, const int32_t *run_off,
+                               const int32_t *run_cnt, const int32_t *sorted_idx, int64_t ng)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < ng; t += (int64_t)gridDim.x * blockDim.x) {
+        const int r = sel_run[t];
+        first[t] = sorted_idx[run_off[r]];
+        gcnt[t] = run_cnt[r];
+    }
+}
+__global__ void gs_permute_counts(int32_t *cnt_out, const int32_t *gcnt, const int32_t *order, int64_t ng)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < ng; t += (int64_t)gridDim.x * blockDim.x)
+        cnt_out[t] = gcnt[order[t]];
+}
+__global__ void gs_fill_members(int32_t *gidx, const int32_t *goff, const int32_t *order, const int32_t *sel_run,
+                                const int32_t *run_off, const int32_t *sorted_idx, int64_t ng)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < ng; t += (int64_t)gridDim.x * blockDim.x) {
+        const int r = sel_run[order[t]];
+        const int b = goff[t], cnt = goff[t + 1] - b, src = run_off[r];
+        for (int q = 0; q < cnt; q++) gidx[b + q] = sorted_idx[src + q];
+    }
+}
+
+template <int OP>
+__device__ __forceinline__ double gs_combine(double a, double b)
+{
+    if (OP == 1) return a + b;
+    if (OP == 2) return a * b;
+    if (OP == 3) return fmin(a, b);
+    return fmax(a, b);
+}
+
+template <int OP>
+__global__ void __launch_bounds__(256)
+    gs_local_kernel(double *__restrict__ u, const int32_t *__restrict__ goff, const int32_t *__restrict__ gidx,
+                    int ngroups)
+{
+    for (int gI = blockIdx.x * blockDim.x + threadIdx.x; gI < ngroups; gI += gridDim.x * blockDim.x) {
+        const int b = goff[gI], e = goff[gI + 1];
+        double v = u[gidx[b]];
+        for (int q = b + 1; q < e; q++) v = gs_combine<OP>(v, u[gidx[q]]);
+        for (int q = b; q < e; q++) u[gidx[q]] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) col2_kernel(double *__restrict__ a, const double *__restrict__ b, int64_t n)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+        a[t] *= b[t];
+}
+
+inline int blocks_for(int64_t n, int threads = 256)
+{
+    int64_t b = (n + threads - 1) / threads;
+    const int64_t cap = (int64_t)ctx().num_sms * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// Builds the local map of `h` from device-resident ids.
+inline void gs_build_local(GsMap &h, const int64_t *id_dev, int64_t n)
+{
+    Ctx &c = ctx();
+    cudaStream_t s = c.stream;
+    NEKB_REQUIRE(n < (int64_t)2147483647, "gs_setup: local vector too long for int32 indexing");
+    h.n = n;
+    h.ngroups = h.nmembers = 0;
+    if (n == 0) return;
+
+    DevBuf<int32_t> idx_nz, idx_sorted, num;
+    DevBuf<int64_t> keys, keys_sorted;
+    DevBuf<char> tmp;
+    idx_nz.alloc(n);
+    num.alloc(4);
+    size_t tb = 0;
+    cub::CountingInputIterator<int32_t> iota(0);
+    NonZeroId pred{id_dev};
+    NEKB_CUDA(cub::DeviceSelect::If(nullptr, tb, iota, idx_nz.p, num.p, (int)n, pred, s));
+    tmp.alloc(tb);
+    NEKB_CUDA(cub::DeviceSelect::If(tmp.p, tb, iota, idx_nz.p, num.p, (int)n, pred, s));
+    launch_counter() += 1;
+    int m = 0;
+    NEKB_CUDA(cudaMemcpyAsync(&m, num.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    NEKB_CUDA(cudaStreamSynchronize(s));
+    if (m == 0) return;
+
+    keys.alloc(m);
+    keys_sorted.alloc(m);
+    idx_sorted.alloc(m);
+    gs_gather_keys<<<blocks_for(m), 256, 0, s>>>(keys.p, id_dev, idx_nz.p, m);
+    NEKB_LAUNCHED();
+    NEKB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys.p, keys_sorted.p, idx_nz.p, idx_sorted.p, m, 0, 64, s));
+    tmp.ensure(tb);
+    NEKB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.p, keys_sorted.p, idx_nz.p, idx_sorted.p, m, 0, 64, s));
+    launch_counter() += 1;
+    keys.release();
+    idx_nz.release();
+
+    // run-length encode the sorted ids
+    DevBuf<int64_t> uniq;
+    DevBuf<int32_t> run_cnt, run_off;
+    uniq.alloc(m);
+    run_cnt.alloc(m);
+    NEKB_CUDA(cub::DeviceRunLengthEncode::Encode(nullptr, tb, keys_sorted.p, uniq.p, run_cnt.p, num.p, m, s));
+    tmp.ensure(tb);
+    NEKB_CUDA(cub::DeviceRunLengthEncode::Encode(tmp.p, tb, keys_sorted.p, uniq.p, run_cnt.p, num.p, m, s));
+    int nruns = 0;
+    NEKB_CUDA(cudaMemcpyAsync(&nruns, num.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    NEKB_CUDA(cudaStreamSynchronize(s));
+    uniq.release();
+    keys_sorted.release();
+    run_off.alloc(nruns + 1);
+    NEKB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, run_cnt.p, run_off.p, nruns, s));
+    tmp.ensure(tb);
+    NEKB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, run_cnt.p, run_off.p, nruns, s));
+
+    // keep runs with >= 2 members
+    DevBuf<int32_t> sel_run;
+    sel_run.alloc(nruns);
+    CountGe2 p2{run_cnt.p};
+    NEKB_CUDA(cub::DeviceSelect::If(nullptr, tb, iota, sel_run.p, num.p, nruns, p2, s));
+    tmp.ensure(tb);
+    NEKB_CUDA(cub::DeviceSelect::If(tmp.p, tb, iota, sel_run.p, num.p, nruns, p2, s));
+    int ng = 0;
+    NEKB_CUDA(cudaMemcpyAsync(&ng, num.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    NEKB_CUDA(cudaStreamSynchronize(s));
+    if (ng == 0) return;
+
+    // order the groups by their first (smallest) member so neighbouring threads touch neighbouring memory
+    DevBuf<int32_t> first, first_sorted, gcnt, order, order_in, cnt_perm;
+    first.alloc(ng);
+    first_sorted.alloc(ng);
+    gcnt.alloc(ng);
+    order.alloc(ng);
+    order_in.alloc(ng);
+    cnt_perm.alloc(ng);
+    gs_group_first<<<blocks_for(ng), 256, 0, s>>>(first.p, gcnt.p, sel_run.p, run_off.p, run_cnt.p, idx_sorted.p, ng);
+    NEKB_LAUNCHED();
+    {
+        std::vector<int32_t> io(ng);
+        for (int t = 0; t < ng; t++) io[t] = t;
+        NEKB_CUDA(cudaMemcpyAsync(order_in.p, io.data(), sizeof(int32_t) * ng, cudaMemcpyHostToDevice, s));
+        NEKB_CUDA(cudaStreamSynchronize(s));
+    }
+    NEKB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, first.p, first_sorted.p, order_in.p, order.p, ng, 0, 32, s));
+    tmp.ensure(tb);
+    NEKB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, first.p, first_sorted.p, order_in.p, order.p, ng, 0, 32, s));
+    gs_permute_counts<<<blocks_for(ng), 256, 0, s>>>(cnt_perm.p, gcnt.p, order.p, ng);
+    NEKB_LAUNCHED();
+    h.goff.alloc((size_t)ng + 1);
+    NEKB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt_perm.p, h.goff.p, ng, s));
+    tmp.ensure(tb);
+    NEKB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt_perm.p, h.goff.p, ng, s));
+    // total members = last offset + last count
+    int last_off = 0, last_cnt = 0;
+    NEKB_CUDA(cudaMemcpyAsync(&last_off, h.goff.p + (ng - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
+    NEKB_CUDA(cudaMemcpyAsync(&last_cnt, cnt_perm.p + (ng - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
+    NEKB_CUDA(cudaStreamSynchronize(s));
+    const int nm = last_off + last_cnt;
+    NEKB_CUDA(cudaMemcpyAsync(h.goff.p + ng, &nm, sizeof(int), cudaMemcpyHostToDevice, s));
+    h.gidx.alloc(nm);
+    gs_fill_members<<<blocks_for(ng), 256, 0, s>>>(h.gidx.p, h.goff.p, order.p, sel_run.p, run_off.p, idx_sorted.p, ng);
+    NEKB_LAUNCHED();
+    NEKB_CUDA(cudaStreamSynchronize(s));
+    h.ngroups = ng;
+    h.nmembers = nm;
+}
+
+inline int gs_new_handle()
+{
+    Ctx &c = ctx();
+    for (size_t i = 0; i < c.gs.size(); i++)
+        if (!c.gs[i].used) {
+            c.gs[i] = GsMap();
+            c.gs[i].used = true;
+            return (int)i;
+        }
+    c.gs.emplace_back();
+    c.gs.back().used = true;
+    return (int)c.gs.size() - 1;
+}
+
+inline GsMap &gs_get(int handle)
+{
+    Ctx &c = ctx();
+    NEKB_REQUIRE(handle >= 0 && handle < (int)c.gs.size() && c.gs[handle].used, "invalid gs handle");
+    return c.gs[handle];
+}
+
+inline void gs_remote_exchange(GsMap &h, double *u, int op);  // comm.cuh
+
+inline void gs_local(GsMap &h, double *u, int op)
+{
+    Ctx &c = ctx();
+    if (h.ngroups == 0) return;
+    const int grid = blocks_for(h.ngroups);
+    switch (op) {
+        case 1: gs_local_kernel<1><<<grid, 256, 0, c.stream>>>(u, h.goff.p, h.gidx.p, (int)h.ngroups); break;
+        case 2: gs_local_kernel<2><<<grid, 256, 0, c.stream>>>(u, h.goff.p, h.gidx.p, (int)h.ngroups); break;
+        case 3: gs_local_kernel<3><<<grid, 256, 0, c.stream>>>(u, h.goff.p, h.gidx.p, (int)h.ngroups); break;
+        case 4: gs_local_kernel<4><<<grid, 256, 0, c.stream>>>(u, h.goff.p, h.gidx.p, (int)h.ngroups); break;
+        default: NEKB_REQUIRE(false, "gs_op: unsupported op (1 +, 2 *, 3 min, 4 max)");
+    }
+    NEKB_LAUNCHED();
+}
+
+// u <- gs_op(u) [* mask]
+inline void gs_op(int handle, double *u, int op, const double *mask)
+{
+    Ctx &c = ctx();
+    GsMap &h = gs_get(handle);
+    gs_local(h, u, op);
+    if (h.nshared > 0 || c.nranks > 1) gs_remote_exchange(h, u, op);
+    if (mask != nullptr && h.n > 0) {
+        col2_kernel<<<blocks_for(h.n), 256, 0, c.stream>>>(u, mask, h.n);
+        NEKB_LAUNCHED();
+    }
+}
+
+}  // namespace nekb

@@ -1,0 +1,919 @@
+// nekb200.cu -- C-ABI of libnekb200.so (see include/nekb200.h).  Unity build: the kernels live in the
+// headers included below.  Build: nvcc -gencode arch=compute_100a,code=sm_100a (nek5000_b200/build.py).
+#include "../../include/nekb200.h"
+
+#include "setup.cuh"
+
+using namespace nekb;
+
+namespace {
+
+template <class F>
+int guard(F &&f)
+{
+    try {
+        f();
+        return 0;
+    } catch (const std::exception &e) {
+        ctx().last_error = e.what();
+        return 1;
+    }
+}
+
+// Fortran-named entry points have no status argument: report and leave through the exit handler
+// (reference: exitt, core/comm_mpi.f:550-636); never return with stale output.
+template <class F>
+void guard_fortran(const char *who, F &&f)
+{
+    if (guard(f)) {
+        fprintf(stderr, "nekb200: %s: %s\n", who, ctx().last_error.c_str());
+        fflush(stderr);
+        if (ctx().exit_handler)
+            ctx().exit_handler();
+        else
+            abort();
+    }
+}
+
+inline int64_t field_len() { return (int64_t)ctx().nelt * ctx().nxyz; }
+
+// interleaved gf(6,nxyz,nel) -> g[e][c][q]
+__global__ void __launch_bounds__(256) gf_deinterleave_kernel(double *__restrict__ g, const double *__restrict__ gf, int nxyz, int64_t total)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = t / (6 * nxyz);
+        const int r = (int)(t - e * 6 * nxyz), cidx = r / nxyz, q = r % nxyz;
+        g[t] = gf[(e * nxyz + q) * 6 + cidx];
+    }
+}
+__global__ void __launch_bounds__(256) gf_interleave_kernel(double *__restrict__ gf, const double *__restrict__ g, int nxyz, int64_t total)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = t / (6 * nxyz);
+        const int r = (int)(t - e * 6 * nxyz), q = r / 6, cidx = r % 6;
+        gf[t] = g[(e * 6 + cidx) * nxyz + q];
+    }
+}
+// elements that are not deformed use g1..g3 only (core/hmholtz.f:196-206): clear their cross terms
+__global__ void zero_cross_terms_kernel(double *__restrict__ g, const int *__restrict__ dfrm, int nxyz, int nel)
+{
+    const int e = blockIdx.x;
+    if (e >= nel || dfrm[e]) return;
+    double *ge = g + (size_t)e * 6 * nxyz;
+    for (int q = threadIdx.x; q < nxyz; q += blockDim.x) ge[1 * nxyz + q] = 0.0, ge[2 * nxyz + q] = 0.0, ge[4 * nxyz + q] = 0.0;
+}
+
+__global__ void __launch_bounds__(CG_THREADS)
+    glsc3_kernel(const double *__restrict__ a, const double *__restrict__ b, const double *__restrict__ m, int64_t n,
+                 double *out, double *partials, unsigned *counter)
+{
+    __shared__ double red[33];
+    double s = 0.0;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+        s = fma(a[t] * b[t], m[t], s);
+    double bs = block_reduce(s, red);
+    grid_reduce(bs, partials, counter, red, [=](double tot) { *out = tot; });
+}
+
+__global__ void __launch_bounds__(CG_THREADS)
+    glrdif_kernel(const double *__restrict__ x, const double *__restrict__ y, int64_t n, double *out3, double *partials,
+                  unsigned *counter)
+{
+    __shared__ double red[33];
+    double d = 0.0, xm = 0.0, ym = 0.0;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        d = fmax(d, fabs(x[t] - y[t]));
+        xm = fmax(xm, x[t]);
+        ym = fmax(ym, y[t]);
+    }
+    double b0 = block_reduce<true>(d, red), b1 = block_reduce<true>(xm, red), b2 = block_reduce<true>(ym, red);
+    grid_reduce<true>(b0, partials, counter, red, [=](double t) { out3[0] = t; });
+    grid_reduce<true>(b1, partials + CG_PART_STRIDE, counter + 1, red, [=](double t) { out3[1] = t; });
+    grid_reduce<true>(b2, partials + 2 * CG_PART_STRIDE, counter + 2, red, [=](double t) { out3[2] = t; });
+}
+
+void apply_ifdfrm()
+{
+    Ctx &c = ctx();
+    if (!c.have_geom || c.ifdfrm.empty()) return;
+    NEKB_REQUIRE((int)c.ifdfrm.size() >= c.nelt, "ifdfrm shorter than nelt");
+    DevBuf<int> f;
+    f.upload(c.ifdfrm.data(), (size_t)c.nelt, c.stream);
+    zero_cross_terms_kernel<<<c.nelt, 128, 0, c.stream>>>(c.g.p, f.p, c.nxyz, c.nelt);
+    NEKB_LAUNCHED();
+    NEKB_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+int field_handle()
+{
+    Ctx &c = ctx();
+    NEKB_REQUIRE(c.ifield >= 0 && c.ifield < 32, "ifield out of range");
+    const int h = c.gsh_fld[c.ifield];
+    NEKB_REQUIRE(h >= 0, "no gs handle registered for the current ifield (nekb_set_field_handle / setupds_)");
+    return h;
+}
+
+}  // namespace
+
+namespace nekb {
+int gs_setup_from_host_ids(const int64_t *id_host, int64_t n, const int32_t *cand, int64_t ncand)
+{
+    Ctx &c = ctx();
+    const int hnd = gs_new_handle();
+    GsMap &h = c.gs[hnd];
+    DevBuf<int64_t> ids;
+    ids.upload(id_host, (size_t)n, c.stream);
+    gs_build_local(h, ids.p, n);
+    gs_build_remote(h, id_host, n, cand, ncand);
+    return hnd;
+}
+}  // namespace nekb
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------------- lifecycle
+int nekb_init(int device, int lx1, int ldim)
+{
+    return guard([&] {
+        Ctx &c = ctx();
+        NEKB_REQUIRE(ldim == 3, "only ldim = 3 is supported");
+        NEKB_REQUIRE(lx1 >= 2 && lx1 <= MAX_NX, "lx1 out of range");
+        if (c.inited) {
+            NEKB_REQUIRE(c.device == device && c.nx == lx1, "nekb_init called again with different arguments");
+            return;
+        }
+        NEKB_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        NEKB_CUDA(cudaGetDeviceProperties(&prop, device));
+        c.device = device;
+        c.num_sms = prop.multiProcessorCount;
+        c.nx = lx1;
+        c.nxyz = lx1 * lx1 * lx1;
+        NEKB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        NEKB_CUDA(cudaEventCreate(&c.ev0));
+        NEKB_CUDA(cudaEventCreate(&c.ev1));
+        c.sc.alloc(1);
+        c.sc.zero(c.stream);
+        c.partials.alloc(4 * CG_PART_STRIDE);
+        for (int i = 0; i < 32; i++) c.gsh_fld[i] = -1;
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+        c.inited = true;
+    });
+}
+
+void nekb_finalize(void)
+{
+    Ctx &c = ctx();
+    if (!c.inited) return;
+    cudaStreamSynchronize(c.stream);
+    bp5case() = Bp5Case();
+    c.gs.clear();
+    if (c.nccl_comm) nccl().CommDestroy(comm_handle());
+    void (*eh)(void) = c.exit_handler;
+    cudaStream_t s = c.stream;
+    cudaEvent_t e0 = c.ev0, e1 = c.ev1;
+    c = Ctx();
+    c.exit_handler = eh;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaStreamDestroy(s);
+}
+
+const char *nekb_last_error(void) { return ctx().last_error.c_str(); }
+void nekb_set_exit_handler(void (*handler)(void)) { ctx().exit_handler = handler; }
+void *nekb_stream(void) { return (void *)ctx().stream; }
+int64_t nekb_launch_count(int reset)
+{
+    const int64_t v = launch_counter();
+    if (reset) launch_counter() = 0;
+    return v;
+}
+
+int nekb_prof_enable(int on)
+{
+    Prof &p = prof();
+    p.on = on != 0;
+    for (int k = 0; k < PROF_NCAT; k++) p.secs[k] = 0.0, p.count[k] = 0;
+    p.spans.clear();
+    p.used = 0;
+    return 0;
+}
+int nekb_prof_get(const char *kernel, double *seconds, int64_t *launches)
+{
+    return guard([&] {
+        const std::string w(kernel);
+        int cat = -1;
+        if (w == "ax") cat = PROF_AX;
+        if (w == "gs") cat = PROF_GS;
+        if (w == "update") cat = PROF_UPDATE;
+        if (w == "pupdate") cat = PROF_PUPDATE;
+        NEKB_REQUIRE(cat >= 0, "unknown kernel class '" + w + "' (ax, gs, update, pupdate)");
+        if (seconds) *seconds = prof().secs[cat];
+        if (launches) *launches = prof().count[cat];
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------- multi-rank
+int nekb_set_transport(int rank, int nranks, nekb_allgather_fn allgather, nekb_alltoallv_fn alltoallv, void *user)
+{
+    return guard([&] {
+        NEKB_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
+        Ctx &c = ctx();
+        c.rank = rank, c.nranks = nranks;
+        c.allgather = allgather, c.alltoallv = alltoallv, c.transport_user = user;
+    });
+}
+int nekb_comm_unique_id(void *id_out_128)
+{
+    return guard([&] {
+        nccl_unique_id id;
+        NEKB_NCCL(nccl().GetUniqueId(&id));
+        memcpy(id_out_128, &id, sizeof id);
+    });
+}
+int nekb_comm_init(const void *id_in_128, int rank, int nranks)
+{
+    return guard([&] {
+        require_init();
+        Ctx &c = ctx();
+        NEKB_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
+        nccl_unique_id id;
+        memcpy(&id, id_in_128, sizeof id);
+        nccl_comm_t comm = nullptr;
+        NEKB_NCCL(nccl().CommInitRank(&comm, nranks, id, rank));
+        c.nccl_comm = comm;
+        c.rank = rank, c.nranks = nranks;
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------- registration
+int nekb_set_nel(int nelv, int nelt)
+{
+    return guard([&] {
+        NEKB_REQUIRE(nelv >= 0 && nelt >= nelv, "need 0 <= nelv <= nelt");
+        ctx().nelv = nelv, ctx().nelt = nelt;
+    });
+}
+int nekb_set_gll(const double *zgm1, const double *wxm1)
+{
+    return guard([&] {
+        require_init();
+        Ctx &c = ctx();
+        c.z_host.assign(zgm1, zgm1 + c.nx);
+        c.w_host.assign(wxm1, wxm1 + c.nx);
+        c.have_gll = true;
+    });
+}
+int nekb_set_dxyz(const double *dxm1, const double *dxtm1)
+{
+    return guard([&] {
+        require_init();
+        Ctx &c = ctx();
+        const int nx = c.nx;
+        c.D_host.resize((size_t)nx * nx);
+        for (int a = 0; a < nx; a++)
+            for (int b = 0; b < nx; b++) {
+                c.D_host[(size_t)a * nx + b] = dxm1[a + nx * b];  // Fortran dxm1(a,b)
+                NEKB_REQUIRE(dxtm1 == nullptr || dxtm1[b + nx * a] == dxm1[a + nx * b], "dxtm1 is not the transpose of dxm1");
+            }
+        NEKB_CUDA(cudaMemcpyToSymbolAsync(c_D, c.D_host.data(), sizeof(double) * nx * nx, 0, cudaMemcpyHostToDevice, c.stream));
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+        c.have_D = true;
+    });
+}
+int nekb_set_geom(const double *g1m1, const double *g2m1, const double *g3m1, const double *g4m1, const double *g5m1,
+                  const double *g6m1, const double *bm1)
+{
+    return guard([&] {
+        require_init();
+        Ctx &c = ctx();
+        NEKB_REQUIRE(c.nelt > 0, "call nekb_set_nel first");
+        const size_t nxyz = c.nxyz, nel = c.nelt;
+        c.g.alloc(6 * nxyz * nel);
+        // core order g1..g6 = rr,ss,tt,rs,rt,st -> device slots rr,rs,rt,ss,st,tt
+        const double *src[6] = {g1m1, g4m1, g5m1, g2m1, g6m1, g3m1};
+        for (int k = 0; k < 6; k++)
+            NEKB_CUDA(cudaMemcpy2DAsync(c.g.p + k * nxyz, 6 * nxyz * sizeof(double), src[k], nxyz * sizeof(double),
+                                        nxyz * sizeof(double), nel, cudaMemcpyHostToDevice, c.stream));
+        c.bm1.upload(bm1, nxyz * nel, c.stream);
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+        c.have_geom = true;
+        apply_ifdfrm();
+    });
+}
+int nekb_set_geom_bp5(const double *gf)
+{
+    return guard([&] {
+        require_init();
+        Ctx &c = ctx();
+        NEKB_REQUIRE(c.nelt > 0, "call nekb_set_nel first");
+        const int64_t total = (int64_t)6 * c.nxyz * c.nelt;
+        DevBuf<double> tmp;
+        tmp.upload(gf, (size_t)total, c.stream);
+        c.g.alloc((size_t)total);
+        gf_deinterleave_kernel<<<blocks_for(total), 256, 0, c.stream>>>(c.g.p, tmp.p, c.nxyz, total);
+        NEKB_LAUNCHED();
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+        c.have_geom = true;
+    });
+}
+int nekb_set_geom_from_xyz(const double *xm1, const double *ym1, const double *zm1, int bp5_form)
+{
+    return guard([&] {
+        require_init();
+        Ctx &c = ctx();
+        NEKB_REQUIRE(c.nelt > 0, "call nekb_set_nel first");
+        const size_t n = (size_t)field_len();
+        DevBuf<double> x, y, z;
+        x.upload(xm1, n, c.stream), y.upload(ym1, n, c.stream), z.upload(zm1, n, c.stream);
+        const int nelv = c.nelv;
+        geom_from_xyz(x.p, y.p, z.p, c.nelt, bp5_form ? 0 : 1, nullptr);
+        c.nelv = nelv;
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+        apply_ifdfrm();
+    });
+}
+int nekb_get_geom(double *g1m1, double *g2m1, double *g3m1, double *g4m1, double *g5m1, double *g6m1, double *bm1,
+                  double *gf)
+{
+    return guard([&] {
+        require_init();
+        Ctx &c = ctx();
+        NEKB_REQUIRE(c.have_geom, "geometry not registered");
+        const size_t nxyz = c.nxyz, nel = c.nelt;
+        double *dst[6] = {g1m1, g4m1, g5m1, g2m1, g6m1, g3m1};
+        for (int k = 0; k < 6; k++)
+            if (dst[k])
+                NEKB_CUDA(cudaMemcpy2DAsync(dst[k], nxyz * sizeof(double), c.g.p + k * nxyz, 6 * nxyz * sizeof(double),
+                                            nxyz * sizeof(double), nel, cudaMemcpyDeviceToHost, c.stream));
+        if (bm1 && c.bm1.n >= nxyz * nel) NEKB_CUDA(cudaMemcpyAsync(bm1, c.bm1.p, nxyz * nel * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        if (gf) {
+            const int64_t total = (int64_t)6 * nxyz * nel;
+            DevBuf<double> tmp;
+            tmp.alloc((size_t)total);
+            gf_interleave_kernel<<<blocks_for(total), 256, 0, c.stream>>>(tmp.p, c.g.p, c.nxyz, total);
+            NEKB_LAUNCHED();
+            tmp.download(gf, (size_t)total, c.stream);
+        }
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+int nekb_set_ifdfrm(const int *ifdfrm)
+{
+    return guard([&] {
+        Ctx &c = ctx();
+        if (ifdfrm == nullptr) {
+            c.ifdfrm.clear();
+            return;
+        }
+        NEKB_REQUIRE(c.nelt > 0, "call nekb_set_nel first");
+        c.ifdfrm.assign(ifdfrm, ifdfrm + c.nelt);
+        apply_ifdfrm();
+    });
+}
+int nekb_set_v1mask(const double *v1mask)
+{
+    return guard([&] {
+        require_init();
+        ctx().v1mask.upload(v1mask, (size_t)field_len(), ctx().stream);
+        NEKB_CUDA(cudaStreamSynchronize(ctx().stream));
+    });
+}
+int nekb_set_ifield(int ifield)
+{
+    return guard([&] {
+        NEKB_REQUIRE(ifield >= 0 && ifield < 32, "ifield out of range");
+        ctx().ifield = ifield;
+    });
+}
+int nekb_set_field_handle(int ifield, int gs_handle)
+{
+    return guard([&] {
+        NEKB_REQUIRE(ifield >= 0 && ifield < 32, "ifield out of range");
+        gs_get(gs_handle);
+        ctx().gsh_fld[ifield] = gs_handle;
+    });
+}
+int nekb_set_step_info(int istep, double volvm1, double voltm1)
+{
+    ctx().istep = istep, ctx().volvm1 = volvm1, ctx().voltm1 = voltm1;
+    return 0;
+}
+int nekb_niterhm(void) { return ctx().niterhm; }
+
+// ---------------------------------------------------------------------------------------------------- gs (device API)
+int nekb_gs_setup(int *handle, const int64_t *id_host, int64_t n)
+{
+    return guard([&] {
+        require_init();
+        NEKB_REQUIRE(n >= 0, "negative length");
+        *handle = gs_setup_from_host_ids(id_host, n, nullptr, 0);
+    });
+}
+int nekb_gs_setup_dev(int *handle, const int64_t *id_dev, int64_t n)
+{
+    return guard([&] {
+        require_init();
+        Ctx &c = ctx();
+        if (c.nranks > 1) {  // the discovery of remote sharers runs on the host
+            std::vector<int64_t> ids((size_t)n);
+            NEKB_CUDA(cudaMemcpyAsync(ids.data(), id_dev, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, c.stream));
+            NEKB_CUDA(cudaStreamSynchronize(c.stream));
+            *handle = gs_setup_from_host_ids(ids.data(), n, nullptr, 0);
+            return;
+        }
+        const int hnd = gs_new_handle();
+        gs_build_local(c.gs[hnd], id_dev, n);
+        *handle = hnd;
+    });
+}
+int nekb_gs_op_dev(int handle, double *u_dev, int op, const double *mask_dev)
+{
+    return guard([&] {
+        require_init();
+        gs_op(handle, u_dev, op, mask_dev);
+    });
+}
+int nekb_gs_free(int handle)
+{
+    return guard([&] {
+        gs_get(handle);
+        ctx().gs[handle] = GsMap();
+    });
+}
+int nekb_gs_info(int handle, int64_t *ngroups, int64_t *nmembers, int64_t *nshared_remote)
+{
+    return guard([&] {
+        GsMap &h = gs_get(handle);
+        if (ngroups) *ngroups = h.ngroups;
+        if (nmembers) *nmembers = h.nmembers;
+        if (nshared_remote) *nshared_remote = h.nshared;
+    });
+}
+int nekb_gs_get_map(int handle, int64_t *off_host, int32_t *idx_host)
+{
+    return guard([&] {
+        GsMap &h = gs_get(handle);
+        Ctx &c = ctx();
+        std::vector<int32_t> off((size_t)h.ngroups + 1, 0);
+        if (h.ngroups) h.goff.download(off.data(), off.size(), c.stream);
+        for (size_t i = 0; i < off.size(); i++) off_host[i] = off[i];
+        if (h.nmembers) h.gidx.download(idx_host, (size_t)h.nmembers, c.stream);
+    });
+}
+// Remote part of the map (bit-exact comparison of the exchange lists): peers[npeers], per-peer counts, and the
+// concatenated ascending global ids are not kept; what is kept and returned is, per exchange item, the local
+// representative index.  Sizes via nekb_gs_remote_info.
+int nekb_gs_remote_info(int handle, int *npeers, int64_t *nitems)
+{
+    return guard([&] {
+        GsMap &h = gs_get(handle);
+        if (npeers) *npeers = (int)h.peers.size();
+        if (nitems) *nitems = h.peer_off.empty() ? 0 : h.peer_off.back();
+    });
+}
+int nekb_gs_get_remote(int handle, int *peers, int64_t *peer_off, int32_t *item_rep_idx)
+{
+    return guard([&] {
+        GsMap &h = gs_get(handle);
+        Ctx &c = ctx();
+        for (size_t p = 0; p < h.peers.size(); p++) peers[p] = h.peers[p];
+        for (size_t p = 0; p < h.peer_off.size(); p++) peer_off[p] = h.peer_off[p];
+        const int64_t ni = h.peer_off.empty() ? 0 : h.peer_off.back();
+        if (ni == 0) return;
+        std::vector<int32_t> sid((size_t)ni), rep((size_t)h.nshared);
+        h.x_item_sid.download(sid.data(), sid.size(), c.stream);
+        h.x_rep.download(rep.data(), rep.size(), c.stream);
+        for (int64_t q = 0; q < ni; q++) item_rep_idx[q] = rep[sid[q]];
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------- operators (device API)
+int nekb_ax_bp5_dev(double *ap_dev, const double *p_dev, double *pap_dev)
+{
+    return guard([&] {
+        require_init();
+        launch_ax(p_dev, ap_dev, nullptr, nullptr, ctx().nelt, pap_dev);
+        if (pap_dev) comm_allreduce_sum(pap_dev, 1);
+    });
+}
+int nekb_axhelm_dev(double *au_dev, const double *u_dev, const double *h1_dev, const double *h2_dev, int imesh)
+{
+    return guard([&] {
+        require_init();
+        Ctx &c = ctx();
+        launch_ax(u_dev, au_dev, h1_dev, h2_dev, imesh == 1 ? c.nelv : c.nelt, nullptr);
+    });
+}
+int nekb_setprec_dev(double *dpc_dev, const double *h1_dev, const double *h2_dev, int imesh)
+{
+    return guard([&] {
+        require_init();
+        Ctx &c = ctx();
+        setprec_run(dpc_dev, h1_dev, h2_dev, imesh == 1 ? c.nelv : c.nelt, field_handle());
+    });
+}
+int nekb_cggos_dev(double *u_dev, const double *rhs_dev, const double *x1_dev, const double *rmult_dev, double tol,
+                   int maxit, int *niter, double *hist_host)
+{
+    return guard([&] {
+        require_init();
+        Ctx &c = ctx();
+        NEKB_REQUIRE(c.v1mask.n >= (size_t)field_len(), "v1mask not registered");
+        CggosArgs a{u_dev, rhs_dev, x1_dev, rmult_dev, c.v1mask.p, field_handle(), c.nelt};
+        const int it = cggos_run(a, tol, maxit, hist_host);
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+        if (niter) *niter = it;
+    });
+}
+int nekb_cggo_dev(double *x_dev, const double *f_dev, const double *h1_dev, const double *h2_dev, const double *mask_dev,
+                  const double *mult_dev, const double *binv_dev, int imsh, double tin, int maxit, int *niter,
+                  double *hist_host)
+{
+    return guard([&] {
+        require_init();
+        Ctx &c = ctx();
+        const double vol = imsh == 1 ? c.volvm1 : c.voltm1;
+        NEKB_REQUIRE(vol > 0.0, "volvm1/voltm1 not registered (nekb_set_step_info)");
+        CggoArgs a{x_dev, f_dev, h1_dev, h2_dev, mask_dev, mult_dev, binv_dev, field_handle(), imsh == 1 ? c.nelv : c.nelt, vol, c.istep};
+        c.niterhm = cggo_run(a, tin, maxit, hist_host);
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+        if (niter) *niter = c.niterhm;
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------- Fortran-named entry points
+void fgslib_gs_setup_(int *handle, const int64_t *id, const int *n, const int *comm, const int *np)
+{
+    (void)comm;
+    guard_fortran("fgslib_gs_setup", [&] {
+        require_init();
+        NEKB_REQUIRE(*np == ctx().nranks, "gs_setup: np differs from the number of ranks the library was set up for");
+        *handle = gs_setup_from_host_ids(id, *n, nullptr, 0);
+    });
+}
+
+static void gs_op_host(int handle, double *u, int64_t stride, int nfields, int dom, int op, int transpose)
+{
+    Ctx &c = ctx();
+    require_init();
+    NEKB_REQUIRE(dom == 1, "gs_op: only datatype 1 (double) is supported");
+    NEKB_REQUIRE(transpose == 0, "gs_op: transpose must be 0");
+    GsMap &h = gs_get(handle);
+    DevBuf<double> &d = c.stage[0];
+    d.ensure((size_t)h.n);
+    for (int f = 0; f < nfields; f++) {
+        double *uf = u + (int64_t)f * stride;
+        NEKB_CUDA(cudaMemcpyAsync(d.p, uf, sizeof(double) * h.n, cudaMemcpyHostToDevice, c.stream));
+        gs_op(handle, d.p, op, nullptr);
+        NEKB_CUDA(cudaMemcpyAsync(uf, d.p, sizeof(double) * h.n, cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    }
+}
+void fgslib_gs_op_(const int *handle, double *u, const int *dom, const int *op, const int *transpose)
+{
+    guard_fortran("fgslib_gs_op", [&] { gs_op_host(*handle, u, 0, 1, *dom, *op, *transpose); });
+}
+void fgslib_gs_op_many_(const int *handle, double *u1, double *u2, double *u3, double *u4, double *u5, double *u6,
+                        const int *n, const int *dom, const int *op, const int *transpose)
+{
+    guard_fortran("fgslib_gs_op_many", [&] {
+        double *us[6] = {u1, u2, u3, u4, u5, u6};
+        NEKB_REQUIRE(*n >= 0 && *n <= 6, "gs_op_many: n must be 0..6");
+        for (int f = 0; f < *n; f++) gs_op_host(*handle, us[f], 0, 1, *dom, *op, *transpose);
+    });
+}
+void fgslib_gs_op_fields_(const int *handle, double *u, const int *stride, const int *n, const int *dom, const int *op,
+                          const int *transpose)
+{
+    guard_fortran("fgslib_gs_op_fields", [&] { gs_op_host(*handle, u, *stride, *n, *dom, *op, *transpose); });
+}
+void fgslib_gs_free_(const int *handle)
+{
+    guard_fortran("fgslib_gs_free", [&] {
+        gs_get(*handle);
+        ctx().gs[*handle] = GsMap();
+    });
+}
+
+void setupds_(int *gs_handle, const int *nx, const int *ny, const int *nz, const int *nel, const int *melg,
+              const int64_t *vertex, int64_t *glo_num)
+{
+    (void)melg;
+    guard_fortran("setupds", [&] {
+        require_init();
+        Ctx &c = ctx();
+        NEKB_REQUIRE(*nx == *ny && *ny == *nz, "setupds: nx = ny = nz required (3-D)");
+        const int64_t n = (int64_t)(*nx) * (*nx) * (*nx) * (*nel);
+        setvert3d_host(glo_num, *nx, *nel, vertex, c.nranks);
+        *gs_handle = gs_setup_from_host_ids(glo_num, n, nullptr, 0);
+    });
+}
+void dssum_(double *u, const int *nx, const int *ny, const int *nz)
+{
+    (void)nx, (void)ny, (void)nz;
+    guard_fortran("dssum", [&] { gs_op_host(field_handle(), u, 0, 1, 1, 1, 0); });
+}
+void dsop_(double *u, const char *op, const int *nx, const int *ny, const int *nz, size_t op_len)
+{
+    (void)nx, (void)ny, (void)nz;
+    guard_fortran("dsop", [&] {
+        char o[4] = {' ', ' ', ' ', 0};
+        for (size_t i = 0; i < 3 && i < op_len; i++) o[i] = op[i];
+        int code = 0;  // core/dssum.f:110-158
+        if (!strcmp(o, "+  ") || !strcmp(o, "sum") || !strcmp(o, "SUM")) code = 1;
+        else if (!strcmp(o, "*  ") || !strcmp(o, "mul") || !strcmp(o, "MUL")) code = 2;
+        else if (!strcmp(o, "m  ") || !strcmp(o, "min") || !strcmp(o, "mna") || !strcmp(o, "MIN") || !strcmp(o, "MNA")) code = 3;
+        else if (!strcmp(o, "M  ") || !strcmp(o, "max") || !strcmp(o, "mxa") || !strcmp(o, "MAX") || !strcmp(o, "MXA")) code = 4;
+        NEKB_REQUIRE(code != 0, std::string("dsop: unknown operation '") + o + "'");
+        gs_op_host(field_handle(), u, 0, 1, 1, code, 0);
+    });
+}
+
+void axhelm_(double *au, const double *u, const double *helm1, const double *helm2, const int *imesh, const int *isd)
+{
+    (void)isd;
+    guard_fortran("axhelm", [&] {
+        require_init();
+        Ctx &c = ctx();
+        const int nel = *imesh == 1 ? c.nelv : c.nelt;
+        const size_t n = (size_t)nel * c.nxyz;
+        c.stage[0].ensure(n), c.stage[1].ensure(n), c.stage[2].ensure(n), c.stage[3].ensure(n);
+        NEKB_CUDA(cudaMemcpyAsync(c.stage[1].p, u, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        NEKB_CUDA(cudaMemcpyAsync(c.stage[2].p, helm1, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        // ifh2 as setfast decides it (core/hmholtz.f:303-305): any |h2| > 0
+        bool ifh2 = false;
+        for (size_t t = 0; t < n && !ifh2; t++) ifh2 = helm2[t] != 0.0;
+        if (ifh2) NEKB_CUDA(cudaMemcpyAsync(c.stage[3].p, helm2, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        launch_ax(c.stage[1].p, c.stage[0].p, c.stage[2].p, ifh2 ? c.stage[3].p : nullptr, nel, nullptr);
+        NEKB_CUDA(cudaMemcpyAsync(au, c.stage[0].p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+void setprec_(double *dpcm1, const double *helm1, const double *helm2, const int *imsh, const int *isd)
+{
+    (void)isd;
+    guard_fortran("setprec", [&] {
+        require_init();
+        Ctx &c = ctx();
+        const int nel = *imsh == 1 ? c.nelv : c.nelt;
+        const size_t n = (size_t)nel * c.nxyz;
+        c.stage[0].ensure(n), c.stage[2].ensure(n), c.stage[3].ensure(n);
+        NEKB_CUDA(cudaMemcpyAsync(c.stage[2].p, helm1, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        NEKB_CUDA(cudaMemcpyAsync(c.stage[3].p, helm2, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        setprec_run(c.stage[0].p, c.stage[2].p, c.stage[3].p, nel, field_handle());
+        NEKB_CUDA(cudaMemcpyAsync(dpcm1, c.stage[0].p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+void cggo_(double *x, const double *f, const double *h1, const double *h2, const double *mask, const double *mult,
+           const int *imsh, const double *tin, const int *maxit, const int *isd, const double *binv, const char *name,
+           size_t name_len)
+{
+    (void)isd;
+    guard_fortran("cggo", [&] {
+        require_init();
+        Ctx &c = ctx();
+        NEKB_REQUIRE(!(name_len >= 4 && !strncmp(name, "PRES", 4)), "cggo: the 'PRES' (GMRES/flexible-CG) branch is not provided");
+        const int nel = *imsh == 1 ? c.nelv : c.nelt;
+        const size_t n = (size_t)nel * c.nxyz;
+        const double *src[6] = {f, h1, h2, mask, mult, binv};
+        for (int k = 0; k < 7; k++) c.stage[k].ensure(n);
+        for (int k = 0; k < 6; k++)
+            NEKB_CUDA(cudaMemcpyAsync(c.stage[k + 1].p, src[k], n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        const double vol = *imsh == 1 ? c.volvm1 : c.voltm1;
+        NEKB_REQUIRE(vol > 0.0, "volvm1/voltm1 not registered (nekb_set_step_info)");
+        CggoArgs a{c.stage[0].p, c.stage[1].p, c.stage[2].p, c.stage[3].p, c.stage[4].p, c.stage[5].p, c.stage[6].p,
+                   field_handle(), nel, vol, c.istep};
+        c.niterhm = cggo_run(a, *tin, *maxit, nullptr);
+        NEKB_CUDA(cudaMemcpyAsync(x, c.stage[0].p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+void cggos_(double *u1, const double *rhs1, const double *x1, const double *rmult, const double *binv, const double *tin,
+            int *maxit, const char *bpname, size_t bpname_len)
+{
+    (void)binv;  // bp5: dpc = 1 (setprecn, bp5.usr:300-312); binv is not read by cggos
+    guard_fortran("cggos", [&] {
+        require_init();
+        Ctx &c = ctx();
+        NEKB_REQUIRE(bpname_len >= 3 && !strncmp(bpname, "bp5", 3), "cggos: only bpname='bp5' is provided");
+        NEKB_REQUIRE(c.v1mask.n >= (size_t)field_len(), "v1mask not registered");
+        const size_t n = (size_t)field_len();
+        for (int k = 0; k < 4; k++) c.stage[k].ensure(n);
+        NEKB_CUDA(cudaMemcpyAsync(c.stage[1].p, rhs1, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        NEKB_CUDA(cudaMemcpyAsync(c.stage[3].p, rmult, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        if (*tin > 0.0) NEKB_CUDA(cudaMemcpyAsync(c.stage[2].p, x1, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        CggosArgs a{c.stage[0].p, c.stage[1].p, c.stage[2].p, c.stage[3].p, c.v1mask.p, field_handle(), c.nelt};
+        *maxit = cggos_run(a, *tin, *maxit, nullptr);
+        NEKB_CUDA(cudaMemcpyAsync(u1, c.stage[0].p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+void axhm1_(double *pap, double *ap1, const double *p1, const double *h1, const double *h2, const char *bpname,
+            size_t bpname_len)
+{
+    (void)h1, (void)h2;
+    guard_fortran("axhm1", [&] {
+        require_init();
+        Ctx &c = ctx();
+        NEKB_REQUIRE(bpname_len >= 3 && !strncmp(bpname, "bp5", 3), "axhm1: only bpname='bp5' is provided");
+        const size_t n = (size_t)field_len();
+        c.stage[0].ensure(n), c.stage[1].ensure(n);
+        NEKB_CUDA(cudaMemcpyAsync(c.stage[1].p, p1, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        double *pap_dev = &c.sc.p->work[0];
+        launch_ax(c.stage[1].p, c.stage[0].p, nullptr, nullptr, c.nelt, pap_dev);
+        // bp5.usr:1334-1336 accumulates the rank-local pap; the caller applies gop (bp5.usr:852)
+        NEKB_CUDA(cudaMemcpyAsync(pap, pap_dev, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaMemcpyAsync(ap1, c.stage[0].p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+double glsc3_(const double *a, const double *b, const double *mult, const int *n)
+{
+    double out = 0.0;
+    guard_fortran("glsc3", [&] {
+        require_init();
+        Ctx &c = ctx();
+        const size_t nn = (size_t)*n;
+        c.stage[0].ensure(nn), c.stage[1].ensure(nn), c.stage[2].ensure(nn);
+        NEKB_CUDA(cudaMemcpyAsync(c.stage[0].p, a, nn * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        NEKB_CUDA(cudaMemcpyAsync(c.stage[1].p, b, nn * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        NEKB_CUDA(cudaMemcpyAsync(c.stage[2].p, mult, nn * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        double *o = &c.sc.p->work[0];
+        glsc3_kernel<<<cg_grid((int64_t)nn), CG_THREADS, 0, c.stream>>>(c.stage[0].p, c.stage[1].p, c.stage[2].p, (int64_t)nn, o,
+                                                                         c.partials.p, &c.sc.p->counter[0]);
+        NEKB_LAUNCHED();
+        comm_allreduce_sum(o, 1);
+        NEKB_CUDA(cudaMemcpyAsync(&out, o, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------------- host-side setup
+int nekb_setvert3d(int64_t *glo_num, int64_t *ngv, int nx, int64_t nel, const int64_t *vertex, int np)
+{
+    return guard([&] {
+        NEKB_REQUIRE(nx >= 2 && nel >= 0, "setvert3d: bad sizes");
+        const int64_t v = setvert3d_host(glo_num, nx, nel, vertex, np);
+        if (ngv) *ngv = v;
+    });
+}
+// Host-only discovery of the ids shared with other ranks (uses the registered transport).  ids: this rank's
+// distinct non-zero ids, ascending.  Two-call protocol: with out arrays NULL only the sizes are returned.
+int nekb_gs_discover(const int64_t *uniq_ids, int64_t n, int *npeers, int64_t *nitems, int *peers, int64_t *peer_off,
+                     int64_t *item_ids)
+{
+    return guard([&] {
+        std::vector<int64_t> u(uniq_ids, uniq_ids + n);
+        static SharedIds cache;
+        if (peers == nullptr) cache = discover_shared_ids(u);
+        int64_t tot = 0;
+        for (auto &v : cache.ids) tot += (int64_t)v.size();
+        if (npeers) *npeers = (int)cache.peers.size();
+        if (nitems) *nitems = tot;
+        if (peers == nullptr) return;
+        int64_t o = 0;
+        for (size_t p = 0; p < cache.peers.size(); p++) {
+            peers[p] = cache.peers[p];
+            peer_off[p] = o;
+            for (int64_t id : cache.ids[p]) item_ids[o++] = id;
+        }
+        peer_off[cache.peers.size()] = o;
+    });
+}
+
+int nekb_bp5_setup(int nelx, int nely, int nelz, int px, int py, int pz, double deform)
+{
+    return guard([&] {
+        require_init();
+        bp5_setup(nelx, nely, nelz, px, py, pz, deform);
+    });
+}
+int nekb_bp5_solve(double tol, int maxit, int *niter, double *seconds, double *hist_host)
+{
+    return guard([&] {
+        require_init();
+        Ctx &c = ctx();
+        Bp5Case &b = bp5case();
+        NEKB_REQUIRE(b.built, "nekb_bp5_setup has not been called");
+        CggosArgs a{b.u1.p, b.r1.p, b.e1.p, b.mult.p, b.mask.p, b.gs_handle, (int)b.nel};
+        NEKB_CUDA(cudaEventRecord(c.ev0, c.stream));
+        const int it = cggos_run(a, tol, maxit, hist_host);
+        NEKB_CUDA(cudaEventRecord(c.ev1, c.stream));
+        NEKB_CUDA(cudaEventSynchronize(c.ev1));
+        float ms = 0.f;
+        NEKB_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+        if (niter) *niter = it;
+        if (seconds) *seconds = 1e-3 * ms;
+    });
+}
+int nekb_bp5_relerr(double *relerr)
+{
+    return guard([&] {
+        require_init();
+        Ctx &c = ctx();
+        Bp5Case &b = bp5case();
+        NEKB_REQUIRE(b.built, "nekb_bp5_setup has not been called");
+        double *o = &c.sc.p->work[0];
+        glrdif_kernel<<<cg_grid(b.n), CG_THREADS, 0, c.stream>>>(b.u1.p, b.e1.p, b.n, o, c.partials.p, &c.sc.p->counter[0]);
+        NEKB_LAUNCHED();
+        comm_allreduce_max(o, 3);
+        double v[3];
+        NEKB_CUDA(cudaMemcpyAsync(v, o, sizeof v, cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+        const double xm = v[1] > v[2] ? v[1] : v[2];  // bp5.usr:422-447 glrdif
+        *relerr = xm > 0 ? v[0] / xm : -v[0];
+    });
+}
+static void *bp5_ptr(const char *which, size_t *bytes)
+{
+    Ctx &c = ctx();
+    Bp5Case &b = bp5case();
+    NEKB_REQUIRE(b.built, "nekb_bp5_setup has not been called");
+    const size_t nb = (size_t)b.n * sizeof(double);
+    const std::string w(which);
+    *bytes = nb;
+    if (w == "u1") return b.u1.p;
+    if (w == "e1") return b.e1.p;
+    if (w == "r1") return b.r1.p;
+    if (w == "mask") return b.mask.p;
+    if (w == "mult") return b.mult.p;
+    if (w == "xm1") return b.xm1.p;
+    if (w == "ym1") return b.ym1.p;
+    if (w == "zm1") return b.zm1.p;
+    if (w == "bm1") return c.bm1.p;
+    if (w == "glo_num") {
+        *bytes = (size_t)b.n * sizeof(int64_t);
+        return b.glo_num.p;
+    }
+    if (w == "g") {  // device layout [e][6][nxyz]
+        *bytes = 6 * nb;
+        return c.g.p;
+    }
+    NEKB_REQUIRE(false, "unknown array name '" + w + "'");
+    return nullptr;
+}
+int nekb_bp5_get(const char *which, void *host_out, size_t n_bytes)
+{
+    return guard([&] {
+        require_init();
+        Ctx &c = ctx();
+        if (!strcmp(which, "gf")) {  // reference layout gf(6,nxyz,nel)
+            const int64_t total = (int64_t)6 * bp5case().n;
+            NEKB_REQUIRE(n_bytes >= (size_t)total * sizeof(double), "output buffer too small");
+            DevBuf<double> tmp;
+            tmp.alloc((size_t)total);
+            gf_interleave_kernel<<<blocks_for(total), 256, 0, c.stream>>>(tmp.p, c.g.p, c.nxyz, total);
+            NEKB_LAUNCHED();
+            tmp.download((double *)host_out, (size_t)total, c.stream);
+            return;
+        }
+        size_t bytes = 0;
+        void *p = bp5_ptr(which, &bytes);
+        NEKB_REQUIRE(n_bytes >= bytes, "output buffer too small");
+        NEKB_CUDA(cudaMemcpyAsync(host_out, p, bytes, cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+int64_t nekb_bp5_nel_local(void) { return bp5case().nel; }
+int nekb_bp5_gs_handle(void) { return bp5case().gs_handle; }
+void *nekb_bp5_devptr(const char *which)
+{
+    void *p = nullptr;
+    guard([&] {
+        size_t bytes;
+        p = bp5_ptr(which, &bytes);
+    });
+    return p;
+}
+
+// Plain device memory helpers for hosts without a CUDA runtime binding of their own (ctypes tests).
+void *nekb_dev_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (guard([&] { NEKB_CUDA(cudaMalloc(&p, bytes ? bytes : 1)); })) return nullptr;
+    return p;
+}
+void nekb_dev_free(void *p) { cudaFree(p); }
+int nekb_h2d(void *dev, const void *host, size_t bytes)
+{
+    return guard([&] {
+        NEKB_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx().stream));
+        NEKB_CUDA(cudaStreamSynchronize(ctx().stream));
+    });
+}
+int nekb_d2h(void *host, const void *dev, size_t bytes)
+{
+    return guard([&] {
+        NEKB_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx().stream));
+        NEKB_CUDA(cudaStreamSynchronize(ctx().stream));
+    });
+}
+int nekb_sync(void)
+{
+    return guard([&] { NEKB_CUDA(cudaStreamSynchronize(ctx().stream)); });
+}
+
+}  // extern "C"

@@ -1,0 +1,369 @@
+"""Host-side mirror of the Nek5000 interfaces of the hot path, over the C-ABI of libnekb200.so.
+
+The functions carry the reference's names, argument order and in-place semantics (numpy arrays stand in
+for the Fortran arrays; everything is passed by reference exactly as gfortran would), so that a test
+reads like a call site in the reference:
+
+    axhelm(au,u,helm1,helm2,imesh,isd)                      core/hmholtz.f:72
+    cggo(x,f,h1,h2,mask,mult,imsh,tin,maxit,isd,binv,name)  core/hmholtz.f:611
+    setprec(dpcm1,helm1,helm2,imsh,isd)                     core/hmholtz.f:380
+    dssum(u,nx,ny,nz) / dsop(u,op,nx,ny,nz)                 core/dssum.f:33,100
+    setupds(gs_handle,nx,ny,nz,nel,melg,vertex,glo_num)     core/dssum.f:1
+    fgslib_gs_setup/op/op_many/op_fields/free               gslib v1.0.9 (call sites core/dssum.f:20,79,198,277)
+    cggos(u1,rhs1,x1,rmult,binv,tin,maxit,bpname)           examples/bp5/bp5.usr:797
+    axhm1(pap,ap1,p1,h1,h2,bpname)                          examples/bp5/bp5.usr:1389
+    glsc3(a,b,mult,n)                                       core/math.f:775
+
+State that the Fortran routines read from COMMON blocks is registered with the set_* functions
+(include/nekb200.h section B).  All compute runs in hand-written CUDA kernels; a missing library or GPU is
+an error, never a fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import ALLGATHER_FN, ALLTOALLV_FN, NekbError, check, lib
+
+__all__ = [
+    "NekbError", "init", "finalize", "launch_count", "set_nel", "set_gll", "set_dxyz", "set_geom", "set_geom_bp5",
+    "set_geom_from_xyz", "get_geom", "set_ifdfrm", "set_v1mask", "set_ifield", "set_field_handle", "set_step_info",
+    "niterhm", "setvert3d", "setupds", "fgslib_gs_setup", "fgslib_gs_op", "fgslib_gs_op_many", "fgslib_gs_op_fields",
+    "fgslib_gs_free", "gs_get_map", "gs_info", "dssum", "dsop", "axhelm", "setprec", "cggo", "cggos", "axhm1", "glsc3",
+    "DevArray", "set_transport_torch", "comm_init_torch",
+]
+
+_state = {"lx1": 0, "nelt": 0, "np": 1, "keep": []}
+
+
+def _i(v):
+    return C.byref(C.c_int(int(v)))
+
+
+def _ptr(a: np.ndarray):
+    assert a.flags["C_CONTIGUOUS"] and a.dtype in (np.float64, np.int64, np.int32), "contiguous f64/i64/i32 arrays only"
+    return C.c_void_p(a.ctypes.data)
+
+
+# --------------------------------------------------------------------------------------------- lifecycle
+def init(device: int = 0, lx1: int = 8, ldim: int = 3) -> None:
+    check(lib().nekb_init(device, lx1, ldim))
+    _state["lx1"] = lx1
+
+
+def finalize() -> None:
+    lib().nekb_finalize()
+    _state.update(lx1=0, nelt=0, np=1)
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(lib().nekb_launch_count(1 if reset else 0))
+
+
+# --------------------------------------------------------------------------------------------- registration
+def set_nel(nelv: int, nelt: int | None = None) -> None:
+    nelt = nelv if nelt is None else nelt
+    check(lib().nekb_set_nel(nelv, nelt))
+    _state["nelt"] = nelt
+
+
+def set_gll(zgm1, wxm1) -> None:
+    check(lib().nekb_set_gll(np.ascontiguousarray(zgm1, dtype=np.float64), np.ascontiguousarray(wxm1, dtype=np.float64)))
+
+
+def set_dxyz(dxm1, dxtm1=None) -> None:
+    """dxm1(lx1,lx1) as a 2-D array indexed [i,j] = dxm1(i,j) (it is flattened in Fortran order)."""
+    d = np.ascontiguousarray(np.asarray(dxm1, dtype=np.float64).ravel(order="F"))
+    dt = np.ascontiguousarray((np.asarray(dxm1).T if dxtm1 is None else np.asarray(dxtm1, dtype=np.float64)).ravel(order="F"))
+    check(lib().nekb_set_dxyz(d, dt))
+
+
+def set_geom(g1m1, g2m1, g3m1, g4m1, g5m1, g6m1, bm1) -> None:
+    check(lib().nekb_set_geom(*[np.ascontiguousarray(a, dtype=np.float64) for a in (g1m1, g2m1, g3m1, g4m1, g5m1, g6m1, bm1)]))
+
+
+def set_geom_bp5(gf) -> None:
+    check(lib().nekb_set_geom_bp5(np.ascontiguousarray(gf, dtype=np.float64)))
+
+
+def set_geom_from_xyz(xm1, ym1, zm1, bp5_form: bool = False) -> None:
+    check(lib().nekb_set_geom_from_xyz(*[np.ascontiguousarray(a, dtype=np.float64) for a in (xm1, ym1, zm1)], int(bp5_form)))
+
+
+def get_geom(gf: bool = False):
+    """Returns (g1m1..g6m1, bm1) or, with gf=True, the interleaved gf(6,nxyz,nelt) as a flat vector."""
+    n = _state["lx1"] ** 3 * _state["nelt"]
+    if gf:
+        out = np.zeros(6 * n)
+        check(lib().nekb_get_geom(None, None, None, None, None, None, None, _ptr(out)))
+        return out
+    outs = [np.zeros(n) for _ in range(7)]
+    check(lib().nekb_get_geom(*[_ptr(a) for a in outs], None))
+    return outs
+
+
+def set_ifdfrm(ifdfrm) -> None:
+    if ifdfrm is None:
+        check(lib().nekb_set_ifdfrm(None))
+    else:
+        a = np.ascontiguousarray(ifdfrm, dtype=np.int32)
+        check(lib().nekb_set_ifdfrm(_ptr(a)))
+
+
+def set_v1mask(v1mask) -> None:
+    check(lib().nekb_set_v1mask(np.ascontiguousarray(v1mask, dtype=np.float64)))
+
+
+def set_ifield(ifield: int) -> None:
+    check(lib().nekb_set_ifield(ifield))
+
+
+def set_field_handle(ifield: int, gs_handle: int) -> None:
+    check(lib().nekb_set_field_handle(ifield, gs_handle))
+
+
+def set_step_info(istep: int, volvm1: float, voltm1: float | None = None) -> None:
+    check(lib().nekb_set_step_info(istep, volvm1, volvm1 if voltm1 is None else voltm1))
+
+
+def niterhm() -> int:
+    return int(lib().nekb_niterhm())
+
+
+# --------------------------------------------------------------------------------------------- numbering / gs
+def setvert3d(nx: int, nel: int, vertex, np_ranks: int = 1):
+    """core/navier8.f:2004 setvert3d -> (glo_num, ngv).  Host only (no GPU needed)."""
+    v = np.ascontiguousarray(vertex, dtype=np.int64).reshape(-1)
+    glo = np.zeros(nx ** 3 * nel, dtype=np.int64)
+    ngv = C.c_int64(0)
+    check(lib().nekb_setvert3d(glo, C.byref(ngv), nx, nel, v, np_ranks))
+    return glo, int(ngv.value)
+
+
+def setupds(nx: int, nel: int, vertex, melg: int | None = None):
+    """core/dssum.f:1 setupds -> (gs_handle, glo_num)."""
+    v = np.ascontiguousarray(vertex, dtype=np.int64).reshape(-1)
+    glo = np.zeros(nx ** 3 * nel, dtype=np.int64)
+    h = C.c_int(-1)
+    lib().setupds_(C.byref(h), _i(nx), _i(nx), _i(nx), _i(nel), _i(melg or nel), v, glo)
+    return int(h.value), glo
+
+
+def fgslib_gs_setup(ids, comm: int = 0, np_ranks: int | None = None) -> int:
+    ids = np.ascontiguousarray(ids, dtype=np.int64)
+    h = C.c_int(-1)
+    lib().fgslib_gs_setup_(C.byref(h), ids, _i(len(ids)), _i(comm), _i(_state["np"] if np_ranks is None else np_ranks))
+    return int(h.value)
+
+
+def fgslib_gs_op(handle: int, u: np.ndarray, dom: int = 1, op: int = 1, transpose: int = 0) -> None:
+    lib().fgslib_gs_op_(_i(handle), _ptr(u), _i(dom), _i(op), _i(transpose))
+
+
+def fgslib_gs_op_many(handle: int, us, dom: int = 1, op: int = 1, transpose: int = 0) -> None:
+    ptrs = [_ptr(u) for u in us] + [None] * (6 - len(us))
+    lib().fgslib_gs_op_many_(_i(handle), *ptrs, _i(len(us)), _i(dom), _i(op), _i(transpose))
+
+
+def fgslib_gs_op_fields(handle: int, u: np.ndarray, stride: int, n: int, dom: int = 1, op: int = 1, transpose: int = 0) -> None:
+    lib().fgslib_gs_op_fields_(_i(handle), _ptr(u), _i(stride), _i(n), _i(dom), _i(op), _i(transpose))
+
+
+def fgslib_gs_free(handle: int) -> None:
+    lib().fgslib_gs_free_(_i(handle))
+
+
+def gs_info(handle: int):
+    a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    check(lib().nekb_gs_info(handle, C.byref(a), C.byref(b), C.byref(c)))
+    return int(a.value), int(b.value), int(c.value)
+
+
+def gs_get_map(handle: int):
+    """CSR (offsets int64, member indices int32) of the handle's local gather-scatter map."""
+    ng, nm, _ = gs_info(handle)
+    off, idx = np.zeros(ng + 1, dtype=np.int64), np.zeros(max(nm, 1), dtype=np.int32)
+    check(lib().nekb_gs_get_map(handle, off, idx))
+    return off, idx[:nm]
+
+
+def gs_get_remote(handle: int):
+    npeers, nitems = C.c_int(0), C.c_int64(0)
+    check(lib().nekb_gs_remote_info(handle, C.byref(npeers), C.byref(nitems)))
+    peers = np.zeros(max(npeers.value, 1), dtype=np.int32)
+    off = np.zeros(npeers.value + 1, dtype=np.int64)
+    rep = np.zeros(max(nitems.value, 1), dtype=np.int32)
+    if npeers.value:
+        check(lib().nekb_gs_get_remote(handle, peers, off, rep))
+    return peers[:npeers.value], off, rep[:nitems.value]
+
+
+def gs_discover(uniq_ids):
+    """Host-only rendezvous of shared ids over the registered transport -> (peers, peer_off, item_ids)."""
+    u = np.ascontiguousarray(uniq_ids, dtype=np.int64)
+    npeers, nitems = C.c_int(0), C.c_int64(0)
+    check(lib().nekb_gs_discover(u, len(u), C.byref(npeers), C.byref(nitems), None, None, None))
+    peers = np.zeros(max(npeers.value, 1), dtype=np.int32)
+    off = np.zeros(npeers.value + 1, dtype=np.int64)
+    ids = np.zeros(max(nitems.value, 1), dtype=np.int64)
+    check(lib().nekb_gs_discover(u, len(u), C.byref(npeers), C.byref(nitems), _ptr(peers), _ptr(off), _ptr(ids)))
+    return peers[:npeers.value], off, ids[:nitems.value]
+
+
+def dssum(u: np.ndarray, nx: int | None = None, ny: int | None = None, nz: int | None = None) -> None:
+    nx = nx or _state["lx1"]
+    lib().dssum_(_ptr(u), _i(nx), _i(ny or nx), _i(nz or nx))
+
+
+def dsop(u: np.ndarray, op: str, nx: int | None = None, ny: int | None = None, nz: int | None = None) -> None:
+    nx = nx or _state["lx1"]
+    o = op.ljust(3).encode()
+    lib().dsop_(_ptr(u), o, _i(nx), _i(ny or nx), _i(nz or nx), 3)
+
+
+# --------------------------------------------------------------------------------------------- operators / solvers
+def axhelm(au: np.ndarray, u: np.ndarray, helm1: np.ndarray, helm2: np.ndarray, imesh: int = 1, isd: int = 1) -> None:
+    lib().axhelm_(_ptr(au), _ptr(u), _ptr(helm1), _ptr(helm2), _i(imesh), _i(isd))
+
+
+def setprec(dpcm1: np.ndarray, helm1: np.ndarray, helm2: np.ndarray, imsh: int = 1, isd: int = 1) -> None:
+    lib().setprec_(_ptr(dpcm1), _ptr(helm1), _ptr(helm2), _i(imsh), _i(isd))
+
+
+def cggo(x, f, h1, h2, mask, mult, imsh, tin, maxit, isd, binv, name: str = "VELX") -> int:
+    nm = name.ljust(4).encode()
+    lib().cggo_(_ptr(x), _ptr(f), _ptr(h1), _ptr(h2), _ptr(mask), _ptr(mult), _i(imsh), C.byref(C.c_double(tin)), _i(maxit),
+                _i(isd), _ptr(binv), nm, 4)
+    return niterhm()
+
+
+def cggos(u1, rhs1, x1, rmult, binv, tin: float, maxit: int, bpname: str = "bp5") -> int:
+    m = C.c_int(maxit)
+    lib().cggos_(_ptr(u1), _ptr(rhs1), _ptr(x1), _ptr(rmult), _ptr(binv), C.byref(C.c_double(tin)), C.byref(m),
+                 bpname.encode(), len(bpname))
+    return int(m.value)
+
+
+def axhm1(ap1, p1, h1, h2, bpname: str = "bp5") -> float:
+    pap = C.c_double(0.0)
+    lib().axhm1_(C.byref(pap), _ptr(ap1), _ptr(p1), _ptr(h1), _ptr(h2), bpname.encode(), len(bpname))
+    return float(pap.value)
+
+
+def glsc3(a, b, mult) -> float:
+    return float(lib().glsc3_(_ptr(a), _ptr(b), _ptr(mult), _i(len(a))))
+
+
+# --------------------------------------------------------------------------------------------- device arrays
+class DevArray:
+    """A device buffer owned through the C-ABI helpers (section E of the header)."""
+
+    def __init__(self, n: int, dtype=np.float64):
+        self.n, self.dtype = int(n), np.dtype(dtype)
+        self.ptr = lib().nekb_dev_alloc(max(self.n, 1) * self.dtype.itemsize)
+        if not self.ptr:
+            raise NekbError(lib().nekb_last_error().decode())
+
+    @classmethod
+    def from_host(cls, a: np.ndarray) -> "DevArray":
+        a = np.ascontiguousarray(a)
+        d = cls(a.size, a.dtype)
+        check(lib().nekb_h2d(d.ptr, a.ctypes.data, a.nbytes))
+        return d
+
+    def to_host(self) -> np.ndarray:
+        out = np.zeros(self.n, dtype=self.dtype)
+        check(lib().nekb_d2h(out.ctypes.data, self.ptr, out.nbytes))
+        return out
+
+    def free(self) -> None:
+        if self.ptr:
+            lib().nekb_dev_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# --------------------------------------------------------------------------------------------- multi-rank plumbing
+def set_transport_torch(group=None) -> None:
+    """Registers torch.distributed (any backend with CPU tensors, e.g. gloo) as the host transport of the
+    setup code (numbering, shared-id discovery)."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+
+    def _allgather(send, recv, nbytes, _user):
+        try:
+            src = torch.frombuffer((C.c_char * nbytes).from_address(send), dtype=torch.uint8).clone() if nbytes else torch.zeros(0, dtype=torch.uint8)
+            outs = [torch.zeros(nbytes, dtype=torch.uint8) for _ in range(world)]
+            dist.all_gather(outs, src, group=group)
+            for r, t in enumerate(outs):
+                if nbytes:
+                    C.memmove(recv + r * nbytes, t.numpy().ctypes.data, nbytes)
+            return 0
+        except Exception as e:  # pragma: no cover
+            print("transport allgather failed:", e)
+            return 1
+
+    def _alltoallv(send, send_bytes, recv, recv_bytes, _user):
+        try:
+            sb = [int(send_bytes[r]) for r in range(world)]
+            rb = [int(recv_bytes[r]) for r in range(world)]
+            so = np.concatenate([[0], np.cumsum(sb)]).astype(np.int64)
+            ro = np.concatenate([[0], np.cumsum(rb)]).astype(np.int64)
+            reqs, bufs = [], {}
+            for r in range(world):
+                if r == rank:
+                    if sb[r]:
+                        C.memmove(recv + int(ro[r]), send + int(so[r]), sb[r])
+                    continue
+                if rb[r]:
+                    bufs[r] = torch.zeros(rb[r], dtype=torch.uint8)
+                    reqs.append(dist.irecv(bufs[r], src=dist.get_global_rank(group, r) if group is not None else r, group=group))
+                if sb[r]:
+                    t = torch.frombuffer((C.c_char * sb[r]).from_address(send + int(so[r])), dtype=torch.uint8).clone()
+                    reqs.append(dist.isend(t, dst=dist.get_global_rank(group, r) if group is not None else r, group=group))
+            for q in reqs:
+                q.wait()
+            for r, t in bufs.items():
+                C.memmove(recv + int(ro[r]), t.numpy().ctypes.data, rb[r])
+            return 0
+        except Exception as e:  # pragma: no cover
+            print("transport alltoallv failed:", e)
+            return 1
+
+    ag, a2a = ALLGATHER_FN(_allgather), ALLTOALLV_FN(_alltoallv)
+    _state["keep"] = [ag, a2a]  # keep the callbacks alive
+    check(lib().nekb_set_transport(rank, world, ag, a2a, None))
+    _state["np"] = world
+
+
+def clear_transport() -> None:
+    check(lib().nekb_set_transport(0, 1, ALLGATHER_FN(0), ALLTOALLV_FN(0), None))
+    _state["np"] = 1
+    _state["keep"] = []
+
+
+def comm_init_torch(group=None) -> None:
+    """Creates the library's NCCL communicator (one rank per GPU); the 128-byte unique id travels through
+    torch.distributed."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    buf = (C.c_char * 128)()
+    if rank == 0:
+        check(lib().nekb_comm_unique_id(buf))
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    t = torch.frombuffer(buf, dtype=torch.uint8).clone().to(dev)
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    raw = bytes(t.cpu().numpy().tobytes())
+    check(lib().nekb_comm_init(raw, rank, world))
+    _state["np"] = world

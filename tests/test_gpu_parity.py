@@ -1,0 +1,299 @@
+"""GPU parity tests: the CUDA path (through the C-ABI of libnekb200.so and its reference-named host mirror
+nek5000_b200.nek) against the CPU oracle on identical seeded inputs.
+
+Tolerances (BASELINE.json north_star): per-apply Ax and dssum relative error <= 1e-12; gather-scatter index maps
+bit-exact; identical CG iteration counts; residual histories and final fields within 1e-10 relative.
+"""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL_APPLY = 1e-12
+TOL_HIST = 1e-10
+
+
+def relmax(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def nek():
+    from nek5000_b200 import nek as N
+    N.init(0, 8, 3)
+    yield N
+    N.finalize()
+
+
+def register(nek, case, bp5=False):
+    """What the Fortran side does once after gengeom."""
+    nek.set_nel(case.nel, case.nel)
+    nek.set_gll(case.z, case.w)
+    nek.set_dxyz(case.D, case.Dt)
+    if bp5:
+        nek.set_geom_bp5(case.gf())
+        nek.set_v1mask(case.mask)
+    else:
+        g = case.geom()
+        nek.set_geom(*g[:7])
+    nek.set_ifdfrm(None)
+
+
+def canonical_groups(off, idx):
+    groups = [tuple(sorted(idx[off[g]:off[g + 1]].tolist())) for g in range(len(off) - 1)]
+    return sorted(groups)
+
+
+# ------------------------------------------------------------------------------------------------- gather-scatter
+@pytest.mark.parametrize("dims,per", [((3, 2, 2), (0, 0, 0)), ((4, 3, 2), (1, 0, 1)), ((1, 1, 1), (0, 0, 0)), ((2, 1, 1), (1, 1, 1))])
+def test_gs_map_bit_exact_and_ops(nek, dims, per):
+    case = oracle.Case(*dims, nx=8, periodic=per)
+    h, glo = nek.setupds(8, case.nel, case.vertex)
+    assert np.array_equal(glo, case.glo_num)                      # numbering: bit-exact
+    off, idx = nek.gs_get_map(h)
+    ooff, oidx = oracle.gs_groups(case.glo_num)
+    assert canonical_groups(off, idx) == canonical_groups(ooff, oidx)  # index map: bit-exact
+    rng = np.random.default_rng(7)
+    for op in (1, 2, 3, 4):
+        u = rng.uniform(0.5, 1.5, case.n)
+        ref = case.dssum(u, op)
+        v = u.copy()
+        nek.fgslib_gs_op(h, v, 1, op, 0)
+        if op in (3, 4):
+            assert np.array_equal(v, ref)
+        else:
+            assert relmax(v, ref) <= TOL_APPLY
+    # multiplicity is exact (small integers), vmult = 1/dssum(1) (connect1.f:129-134)
+    one = np.ones(case.n)
+    nek.fgslib_gs_op(h, one, 1, 1, 0)
+    assert np.array_equal(1.0 / one, case.mult)
+    # dssum / dsop through the field handle
+    nek.set_ifield(1)
+    nek.set_field_handle(1, h)
+    u = rng.standard_normal(case.n)
+    v = u.copy()
+    nek.dssum(v)
+    assert relmax(v, case.dssum(u, 1)) <= TOL_APPLY
+    for name, op in (("+  ", 1), ("*  ", 2), ("m  ", 3), ("M  ", 4), ("sum", 1), ("max", 4)):
+        v = u.copy()
+        nek.dsop(v, name)
+        assert relmax(v, case.dssum(u, op)) <= TOL_APPLY
+    # op_many / op_fields
+    a, b = rng.standard_normal(case.n), rng.standard_normal(case.n)
+    a2, b2 = a.copy(), b.copy()
+    nek.fgslib_gs_op_many(h, [a2, b2])
+    assert relmax(a2, case.dssum(a)) <= TOL_APPLY and relmax(b2, case.dssum(b)) <= TOL_APPLY
+    ab = np.concatenate([a, b])
+    nek.fgslib_gs_op_fields(h, ab, case.n, 2)
+    assert relmax(ab[:case.n], case.dssum(a)) <= TOL_APPLY and relmax(ab[case.n:], case.dssum(b)) <= TOL_APPLY
+    nek.fgslib_gs_free(h)
+
+
+def test_gs_edge_cases(nek):
+    # no shared ids at all; all-zero ids; a ragged hand-made id vector with collisions
+    ids = np.arange(1, 11, dtype=np.int64)
+    h = nek.fgslib_gs_setup(ids)
+    u = np.arange(10, dtype=np.float64)
+    v = u.copy()
+    nek.fgslib_gs_op(h, v)
+    assert np.array_equal(u, v) and nek.gs_info(h)[0] == 0
+    nek.fgslib_gs_free(h)
+    h = nek.fgslib_gs_setup(np.zeros(7, dtype=np.int64))
+    v = np.ones(7)
+    nek.fgslib_gs_op(h, v)
+    assert np.array_equal(v, np.ones(7))
+    nek.fgslib_gs_free(h)
+    ids = np.array([5, 0, 5, 9, 2 ** 40, 9, 5, 0, 2 ** 40, 1, 9], dtype=np.int64)
+    h = nek.fgslib_gs_setup(ids)
+    u = np.arange(1.0, 12.0)
+    for op in (1, 2, 3, 4):
+        ref = u.copy()
+        oracle.lib().nko_gs_op(ref, ids, len(ids), op)
+        v = u.copy()
+        nek.fgslib_gs_op(h, v, 1, op, 0)
+        assert np.array_equal(v, ref)
+    nek.fgslib_gs_free(h)
+
+
+# ------------------------------------------------------------------------------------------------- operators
+@pytest.mark.parametrize("deform", [0.0, 0.08])
+def test_ax_bp5_per_apply(nek, deform):
+    case = oracle.Case(3, 2, 2, nx=8, deform=deform)
+    register(nek, case, bp5=True)
+    rng = np.random.default_rng(3)
+    p = rng.standard_normal(case.n)
+    ref, pap_ref = case.ax_bp5(p)
+    ap = np.zeros(case.n)
+    pap = nek.axhm1(ap, p, np.ones(case.n), np.zeros(case.n), "bp5")
+    assert relmax(ap, ref) <= TOL_APPLY
+    assert abs(pap - pap_ref) <= TOL_APPLY * abs(pap_ref)
+    # geometry round trip
+    assert np.array_equal(nek.get_geom(gf=True), case.gf())
+
+
+@pytest.mark.parametrize("ifh2", [False, True])
+@pytest.mark.parametrize("mixed_dfrm", [False, True])
+def test_axhelm_per_apply(nek, ifh2, mixed_dfrm):
+    case = oracle.Case(2, 3, 2, nx=8, deform=0.0 if mixed_dfrm else 0.06)
+    register(nek, case)
+    rng = np.random.default_rng(5)
+    u = rng.standard_normal(case.n)
+    h1 = rng.uniform(0.5, 2.0, case.n)
+    h2 = rng.uniform(0.1, 3.0, case.n) if ifh2 else np.zeros(case.n)
+    dfrm = None
+    if mixed_dfrm:  # undeformed box: elements flagged not-deformed use g1..g3 only (hmholtz.f:196-206)
+        dfrm = (np.arange(case.nel) % 2).astype(np.int32)
+        nek.set_ifdfrm(dfrm)
+    ref = case.axhelm(u, h1, h2, ifdfrm=dfrm)
+    au = np.zeros(case.n)
+    nek.axhelm(au, u, h1, h2, 1, 1)
+    assert relmax(au, ref) <= TOL_APPLY
+    nek.set_ifdfrm(None)
+
+
+def test_geometry_kernels_bit_exact(nek):
+    case = oracle.Case(2, 2, 3, nx=8, deform=0.07)
+    nek.set_nel(case.nel, case.nel)
+    nek.set_gll(case.z, case.w)
+    nek.set_dxyz(case.D, case.Dt)
+    nek.set_geom_from_xyz(case.xm1, case.ym1, case.zm1, bp5_form=True)
+    assert np.array_equal(nek.get_geom(gf=True), case.gf())          # geodatstd, bp5.usr:623-699
+    nek.set_geom_from_xyz(case.xm1, case.ym1, case.zm1, bp5_form=False)
+    got = nek.get_geom()
+    for a, b in zip(got, case.geom()[:7]):                           # glmapm1 + geodat1, coef.f:555-784
+        assert np.array_equal(a, b)
+
+
+def test_setprec(nek):
+    case = oracle.Case(2, 2, 2, nx=8, deform=0.05)
+    register(nek, case)
+    h, _ = nek.setupds(8, case.nel, case.vertex)
+    nek.set_field_handle(1, h)
+    nek.set_ifield(1)
+    rng = np.random.default_rng(11)
+    h1, h2 = rng.uniform(0.5, 2.0, case.n), rng.uniform(0.0, 1.0, case.n)
+    ref = case.setprec(h1, h2)
+    d = np.zeros(case.n)
+    nek.setprec(d, h1, h2, 1, 1)
+    assert relmax(d, ref) <= TOL_APPLY
+    nek.fgslib_gs_free(h)
+
+
+# ------------------------------------------------------------------------------------------------- solvers
+def test_cggos_history_and_solution(nek):
+    case = oracle.Case(3, 3, 2, nx=8, deform=0.05)
+    register(nek, case, bp5=True)
+    h, _ = nek.setupds(8, case.nel, case.vertex)
+    nek.set_field_handle(1, h)
+    nek.set_ifield(1)
+    e1, r1 = case.bp5_problem()
+    maxit = 60
+    uref, itref, hist = case.cggos(r1, e1, tol=-1e-8, maxit=maxit, history=True)
+    u = np.zeros(case.n)
+    it = nek.cggos(u, r1, e1, case.mult, np.ones(case.n), -1e-8, maxit, "bp5")
+    assert it == itref == maxit
+    assert relmax(u, uref) <= TOL_HIST
+    # with a positive tolerance the reference exits on max|u-x1| < tol (bp5.usr:869-874): same iteration count
+    tol = float(hist[25, 3]) * 1.5
+    uref2, itref2 = case.cggos(r1, e1, tol=tol, maxit=maxit)
+    u2 = np.zeros(case.n)
+    it2 = nek.cggos(u2, r1, e1, case.mult, np.ones(case.n), tol, maxit, "bp5")
+    assert it2 == itref2 and it2 < maxit
+    assert relmax(u2, uref2) <= TOL_HIST
+    nek.fgslib_gs_free(h)
+
+
+@pytest.mark.parametrize("ifh2", [False, True])
+def test_cggo_iterations_and_solution(nek, ifh2):
+    case = oracle.Case(3, 2, 2, nx=8, deform=0.05)
+    register(nek, case)
+    h, _ = nek.setupds(8, case.nel, case.vertex)
+    nek.set_field_handle(1, h)
+    nek.set_ifield(1)
+    bm1 = case.bm1()
+    nek.set_step_info(1, float(bm1.sum()))
+    rng = np.random.default_rng(2)
+    h1 = np.full(case.n, 1.3)
+    h2 = np.full(case.n, 0.7) if ifh2 else np.zeros(case.n)
+    f = case.dssum(bm1 * rng.standard_normal(case.n)) * case.mask
+    for tin in (1e-6, 1e-10):
+        xref, itref = case.cggo(f, h1, h2, tin=tin, maxit=200, istep=1)
+        x = np.zeros(case.n)
+        it = nek.cggo(x, f, h1, h2, case.mask, case.mult, 1, tin, 200, 1, case.binv(), "VELX")
+        assert it == itref
+        assert relmax(x, xref) <= TOL_HIST
+    nek.fgslib_gs_free(h)
+
+
+# ------------------------------------------------------------------------------------------------- device-built BP5 case
+@pytest.mark.parametrize("deform", [0.0, 0.05])
+def test_bp5_case_matches_oracle(deform):
+    from nek5000_b200 import nek as N
+    from nek5000_b200.bp5 import BP5
+    N.finalize()
+    N.init(0, 8, 3)
+    case = oracle.Case(4, 3, 2, nx=8, deform=deform)
+    N.set_gll(case.z, case.w)
+    N.set_dxyz(case.D, case.Dt)
+    b = BP5(4, 3, 2, lx1=8, deform=deform)
+    assert np.array_equal(b.get("glo_num"), case.glo_num)
+    assert np.array_equal(b.get("mask"), case.mask)
+    assert np.array_equal(b.get("mult"), case.mult)
+    if deform == 0.0:
+        for nm, ref in (("xm1", case.xm1), ("ym1", case.ym1), ("zm1", case.zm1)):
+            assert np.array_equal(b.get(nm), ref)
+        assert np.array_equal(b.get("gf"), case.gf())
+    else:
+        assert relmax(b.get("gf"), case.gf()) <= TOL_APPLY
+    e1, r1 = case.bp5_problem()
+    assert relmax(b.get("e1"), e1) <= TOL_APPLY
+    assert relmax(b.get("r1"), r1) <= TOL_APPLY
+    maxit = 50
+    uref, itref, hist = case.cggos(r1, e1, maxit=maxit, history=True)
+    it, sec, h = b.solve(-1e-8, maxit, history=True)
+    assert it == itref
+    assert np.abs(h[:, 0] - hist[:, 0]).max() <= TOL_HIST * np.abs(hist[:, 0]).max()      # pap history
+    assert np.all(np.abs(h[:, 1] - hist[:, 2]) <= 1e-8 * np.abs(hist[:, 2]) + 1e-300)      # (r,z) history
+    assert relmax(b.get("u1"), uref) <= TOL_HIST
+    assert abs(b.relerr() - oracle.glrdif(uref, e1)) <= 1e-9
+    N.finalize()
+
+
+def test_full_size_properties():
+    """BASELINE config 4 size (E = 64^3 = 262,144, N = 7) through size-independent properties: A symmetric and
+    A.1 = 0, gs(+) idempotent on the multiplicity weights, sum(bm1) = volume, CG error decreases monotonically
+    in the energy norm (pap > 0) and relerr drops."""
+    from nek5000_b200 import nek as N
+    from nek5000_b200.bp5 import BP5
+    N.finalize()
+    b = BP5(64, 64, 64, lx1=8)
+    n = b.n
+    L = __import__("nek5000_b200").lib()
+    rng = np.random.default_rng(0)
+    from nek5000_b200.nek import DevArray
+    u = DevArray.from_host(rng.standard_normal(n))
+    v = DevArray.from_host(rng.standard_normal(n))
+    au, av, s = DevArray(n), DevArray(n), DevArray(1)
+    assert L.nekb_ax_bp5_dev(au.ptr, u.ptr, None) == 0
+    assert L.nekb_ax_bp5_dev(av.ptr, v.ptr, None) == 0
+    hu, hv, hau, hav = u.to_host(), v.to_host(), au.to_host(), av.to_host()
+    s1, s2 = float(hv @ hau), float(hu @ hav)
+    assert abs(s1 - s2) <= 1e-11 * max(abs(s1), abs(s2))             # symmetry
+    one = DevArray.from_host(np.ones(n))
+    assert L.nekb_ax_bp5_dev(au.ptr, one.ptr, s.ptr) == 0
+    assert np.abs(au.to_host()).max() <= 1e-9 * np.abs(hau).max()     # constants are in the null space
+    bm1 = b.get("bm1")
+    assert abs(bm1.sum() - 1.0) <= 1e-12                              # volume of [0,1]^3 (bp5.usr:40-44)
+    mult = b.get("mult")
+    assert set(np.unique(1.0 / mult).round().astype(int)) <= {1, 2, 4, 8}
+    w = DevArray.from_host(mult)
+    assert L.nekb_gs_op_dev(b.gs_handle, w.ptr, 1, None) == 0
+    assert np.array_equal(w.to_host(), np.ones(n))                    # sum of 1/m over m copies = 1 exactly
+    it, sec, h = b.solve(-1e-8, 30, history=True)
+    assert it == 30 and np.all(h[:, 0] > 0) and np.all(np.isfinite(h))
+    r30 = b.relerr()
+    it, sec = b.solve(-1e-8, 120)
+    assert b.relerr() < r30
+    N.finalize()
