@@ -119,6 +119,170 @@ __global__ void __launch_bounds__(NX *NX *EPB)
     }
 }
 
+// ---------------------------------------------------------------------------------------------- kernel v2 (TMA)
+// Persistent CTAs of GROUPS x (NX*NX) threads.  Every group of NX*NX threads streams its own sequence of
+// elements through a ring of STAGES shared-memory stages; a stage holds the element's six geometric-factor
+// tiles and its u tile (one contiguous 6*NX^3*8-byte block + one NX^3*8-byte block in HBM), fetched with
+// cp.async.bulk (TMA bulk copy, SASS UBLKCP) that signals an mbarrier with the byte count.  While a group
+// computes on one stage the TMA engine fills the others, so HBM latency is hidden by the copy engine and not
+// by occupancy; the factors never pass through registers until they are consumed.  Thread (i,j) owns the
+// k-column of its element; r/s contractions read the u tile in place, the two D^T contractions exchange
+// wr/ws through a double-buffered scratch slice with one 64-thread named barrier per k.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void group_barrier(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int NX, int GROUPS, int STAGES>
+struct AxTmaSmem {
+    static constexpr int N2 = NX * NX, N3 = NX * NX * NX;
+    static constexpr size_t stage_doubles = 7 * (size_t)N3;                    // 6 factor tiles + u tile
+    static constexpr size_t scratch_doubles = 4 * (size_t)N2;                  // wr[2], ws[2]
+    static constexpr size_t group_doubles = STAGES * stage_doubles + scratch_doubles;
+    static constexpr size_t bytes = GROUPS * group_doubles * sizeof(double) + GROUPS * STAGES * sizeof(uint64_t) + 64 * sizeof(double);
+};
+
+template <int NX, int GROUPS, int STAGES>
+__global__ void __launch_bounds__(NX *NX *GROUPS, 1)
+    ax_tma_kernel(const double *__restrict__ u, const double *__restrict__ g, double *__restrict__ w, int nel,
+                  double *__restrict__ partials, unsigned *counter, double *pap_out)
+{
+    using L = AxTmaSmem<NX, GROUPS, STAGES>;
+    constexpr int N2 = L::N2, N3 = L::N3;
+    constexpr uint32_t G_BYTES = 6 * N3 * sizeof(double), U_BYTES = N3 * sizeof(double);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *smem = reinterpret_cast<double *>(smem_raw);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + GROUPS * L::group_doubles);
+    double *s_red = reinterpret_cast<double *>(bars + GROUPS * STAGES);
+
+    const int grp = threadIdx.x / N2, ij = threadIdx.x % N2, i = ij % NX, j = ij / NX;
+    double *gbase = smem + grp * L::group_doubles;
+    double *s_w = gbase + STAGES * L::stage_doubles;  // [2][2][N2]: (parity, r|s)
+    uint64_t *full = bars + grp * STAGES;
+    const bool leader = ij == 0;
+
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < GROUPS * STAGES; q++) mbar_init(&bars[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    double Di[NX], Dj[NX], DTi[NX], DTj[NX];
+#pragma unroll
+    for (int m = 0; m < NX; m++) {
+        Di[m] = c_D[i * NX + m];
+        Dj[m] = c_D[j * NX + m];
+        DTi[m] = c_D[m * NX + i];
+        DTj[m] = c_D[m * NX + j];
+    }
+
+    const int first = blockIdx.x * GROUPS + grp, stride = gridDim.x * GROUPS;
+    auto issue = [&](int stage, int e) {
+        double *st = gbase + stage * L::stage_doubles;
+        mbar_expect_tx(&full[stage], G_BYTES + U_BYTES);
+        bulk_g2s(st, g + (size_t)e * 6 * N3, G_BYTES, &full[stage]);
+        bulk_g2s(st + 6 * N3, u + (size_t)e * N3, U_BYTES, &full[stage]);
+    };
+    if (leader) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) {
+            const int e = first + s * stride;
+            if (e < nel) issue(s, e);
+        }
+    }
+
+    double pap = 0.0;
+    int it = 0;
+    for (int e = first; e < nel; e += stride, it++) {
+        const int stage = it % STAGES;
+        const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&full[stage], parity);
+        const double *__restrict__ sg = gbase + stage * L::stage_doubles;
+        const double *__restrict__ su = sg + 6 * N3;
+
+        double ucol[NX], wcol[NX];
+#pragma unroll
+        for (int k = 0; k < NX; k++) {
+            ucol[k] = su[k * N2 + ij];
+            wcol[k] = 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < NX; k++) {
+            const int q = k * N2 + ij;
+            const double G0 = sg[0 * N3 + q], G1 = sg[1 * N3 + q], G2 = sg[2 * N3 + q], G3 = sg[3 * N3 + q],
+                         G4 = sg[4 * N3 + q], G5 = sg[5 * N3 + q];
+            double ur = 0.0, us = 0.0, ut = 0.0;
+#pragma unroll
+            for (int m = 0; m < NX; m++) {
+                ur = fma(Di[m], su[k * N2 + j * NX + m], ur);
+                us = fma(Dj[m], su[k * N2 + m * NX + i], us);
+                ut = fma(c_D[k * NX + m], ucol[m], ut);
+            }
+            const double wr = fma(G0, ur, fma(G1, us, G2 * ut));
+            const double ws = fma(G1, ur, fma(G3, us, G4 * ut));
+            const double wt = fma(G2, ur, fma(G4, us, G5 * ut));
+            double *swr = s_w + (k & 1) * 2 * N2, *sws = swr + N2;
+            swr[ij] = wr;
+            sws[ij] = ws;
+#pragma unroll
+            for (int m = 0; m < NX; m++) wcol[m] = fma(c_D[k * NX + m], wt, wcol[m]);
+            group_barrier(1 + grp, N2);
+            double acc = wcol[k];
+#pragma unroll
+            for (int m = 0; m < NX; m++) {
+                acc = fma(DTi[m], swr[j * NX + m], acc);
+                acc = fma(DTj[m], sws[m * NX + i], acc);
+            }
+            wcol[k] = acc;
+        }
+        double *__restrict__ we = w + (size_t)e * N3;
+#pragma unroll
+        for (int k = 0; k < NX; k++) {
+            we[k * N2 + ij] = wcol[k];
+            pap = fma(ucol[k], wcol[k], pap);
+        }
+        // every thread of the group is past its last read of this stage (and of the scratch slices) once it
+        // has passed this barrier; only then may the TMA engine overwrite the stage
+        group_barrier(1 + grp, N2);
+        if (leader) {
+            const int en = e + STAGES * stride;
+            if (en < nel) issue(stage, en);
+        }
+    }
+    if (pap_out != nullptr) {
+        double b = block_reduce(pap, s_red);
+        grid_reduce(b, partials, counter, s_red, [=](double t) { *pap_out = t; });
+    }
+}
+
 // Jacobi diagonal, core/hmholtz.f:380-524 setprec before its dssum + invcol1 (:520-521).
 // One CTA per element, one thread per node.
 template <int NX>
@@ -175,12 +339,47 @@ inline void launch_ax_t(const double *u, double *w, const double *h1, const doub
 }
 
 // w = A u (h1 == nullptr: pure stiffness as in BP5) ; optional pap_out (device) = sum u.w
+template <int NX, int GROUPS, int STAGES>
+inline void launch_ax_tma(const double *u, double *w, int nel, double *pap_out)
+{
+    Ctx &c = ctx();
+    using L = AxTmaSmem<NX, GROUPS, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        NEKB_CUDA(cudaFuncSetAttribute(ax_tma_kernel<NX, GROUPS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes));
+        configured = true;
+    }
+    const int ngroups = (nel + GROUPS - 1) / GROUPS;
+    const int grid = grid_for(ngroups, 1);
+    ax_tma_kernel<NX, GROUPS, STAGES><<<grid, NX * NX * GROUPS, L::bytes, c.stream>>>(u, c.g.p, w, nel, c.partials.p,
+                                                                                        &c.sc.p->counter[0], pap_out);
+    NEKB_LAUNCHED();
+}
+
+inline int ax_variant()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("NEKB_AX_VARIANT");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+
 inline void launch_ax(const double *u, double *w, const double *h1, const double *h2, int nel, double *pap_out)
 {
     Ctx &c = ctx();
     NEKB_REQUIRE(c.have_geom && c.have_D, "geometry / derivative matrix not registered");
     if (nel <= 0) {
         if (pap_out) NEKB_CUDA(cudaMemsetAsync(pap_out, 0, sizeof(double), c.stream));
+        return;
+    }
+    if (h1 == nullptr && c.nx == 8 && ax_variant() > 0) {
+        switch (ax_variant()) {
+            case 2: launch_ax_tma<8, 2, 3>(u, w, nel, pap_out); break;
+            case 3: launch_ax_tma<8, 2, 2>(u, w, nel, pap_out); break;
+            default: launch_ax_tma<8, 3, 2>(u, w, nel, pap_out); break;
+        }
         return;
     }
     switch (c.nx) {

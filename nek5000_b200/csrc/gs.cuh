@@ -10,6 +10,7 @@
 // Members are ascending inside a group and combined in that order (deterministic, no atomics).
 #pragma once
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include "ctx.cuh"
 
@@ -106,7 +107,7 @@ inline void gs_build_local(GsMap &h, const int64_t *id_dev, int64_t n)
     idx_nz.alloc(n);
     num.alloc(4);
     size_t tb = 0;
-    cub::CountingInputIterator<int32_t> iota(0);
+    thrust::counting_iterator<int32_t> iota(0);
     NonZeroId pred{id_dev};
     NEKB_CUDA(cub::DeviceSelect::If(nullptr, tb, iota, idx_nz.p, num.p, (int)n, pred, s));
     tmp.alloc(tb);
