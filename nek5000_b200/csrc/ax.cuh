@@ -283,6 +283,185 @@ __global__ void __launch_bounds__(NX *NX *GROUPS, 1)
     }
 }
 
+// ---------------------------------------------------------------------------------------------- kernel v3 (TMA, CG-fused)
+// The front half of a cggos iteration in one pass over the element tiles (examples/bp5/bp5.usr:855-856 of the
+// PREVIOUS iteration, :879-884, then :848 of this one):
+//     u += alpha * p_old ;  p = r + beta * p_old ;  w = A p ;  pap = sum p.w
+// Compared with separate kernels this removes one read of p and the read-modify-write of u from the vector
+// update.  FIRST (iteration 1): p = r, u untouched.  alpha and beta come from the device-resident CG scalars.
+template <int NX, int GROUPS, int STAGES>
+struct AxCgSmem {
+    static constexpr int N2 = NX * NX, N3 = NX * NX * NX;
+    static constexpr size_t stage_doubles = 9 * (size_t)N3;                    // 6 factor tiles + r, p, u tiles
+    static constexpr size_t scratch_doubles = 4 * (size_t)N2;
+    static constexpr size_t group_doubles = STAGES * stage_doubles + scratch_doubles;
+    static constexpr size_t bytes = GROUPS * group_doubles * sizeof(double) + GROUPS * STAGES * sizeof(uint64_t) + 64 * sizeof(double);
+};
+
+template <int NX, int GROUPS, int STAGES, bool FIRST>
+__global__ void __launch_bounds__(NX *NX *GROUPS, 1)
+    ax_cg_kernel(const double *__restrict__ r, double *__restrict__ p, double *__restrict__ u,
+                 const double *__restrict__ g, double *__restrict__ w, int nel, const CgScalars *__restrict__ sc,
+                 double *__restrict__ partials, unsigned *counter, double *pap_out)
+{
+    using L = AxCgSmem<NX, GROUPS, STAGES>;
+    constexpr int N2 = L::N2, N3 = L::N3;
+    constexpr uint32_t G_BYTES = 6 * N3 * sizeof(double), T_BYTES = N3 * sizeof(double);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *smem = reinterpret_cast<double *>(smem_raw);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + GROUPS * L::group_doubles);
+    double *s_red = reinterpret_cast<double *>(bars + GROUPS * STAGES);
+
+    const int grp = threadIdx.x / N2, ij = threadIdx.x % N2, i = ij % NX, j = ij / NX;
+    double *gbase = smem + grp * L::group_doubles;
+    double *s_w = gbase + STAGES * L::stage_doubles;
+    uint64_t *full = bars + grp * STAGES;
+    const bool leader = ij == 0;
+
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < GROUPS * STAGES; q++) mbar_init(&bars[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // bp5.usr:853 alpha = rpp1/pap of the previous iteration; :879-881 beta = rpp1/rpp2
+    const double alpha = FIRST ? 0.0 : sc->alpha;
+    const double beta = FIRST ? 0.0 : sc->work[1] / sc->rtz1;
+
+    double Di[NX], Dj[NX], DTi[NX], DTj[NX];
+#pragma unroll
+    for (int m = 0; m < NX; m++) {
+        Di[m] = c_D[i * NX + m];
+        Dj[m] = c_D[j * NX + m];
+        DTi[m] = c_D[m * NX + i];
+        DTj[m] = c_D[m * NX + j];
+    }
+
+    const int first = blockIdx.x * GROUPS + grp, stride = gridDim.x * GROUPS;
+    auto issue = [&](int stage, int e) {
+        double *st = gbase + stage * L::stage_doubles;
+        mbar_expect_tx(&full[stage], G_BYTES + (FIRST ? 1 : 3) * T_BYTES);
+        bulk_g2s(st, g + (size_t)e * 6 * N3, G_BYTES, &full[stage]);
+        bulk_g2s(st + 6 * N3, r + (size_t)e * N3, T_BYTES, &full[stage]);
+        if (!FIRST) {
+            bulk_g2s(st + 7 * N3, p + (size_t)e * N3, T_BYTES, &full[stage]);
+            bulk_g2s(st + 8 * N3, u + (size_t)e * N3, T_BYTES, &full[stage]);
+        }
+    };
+    if (leader) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) {
+            const int e = first + s * stride;
+            if (e < nel) issue(s, e);
+        }
+    }
+
+    double pap = 0.0;
+    int it = 0;
+    for (int e = first; e < nel; e += stride, it++) {
+        const int stage = it % STAGES;
+        const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&full[stage], parity);
+        double *sg = gbase + stage * L::stage_doubles;
+        double *sr = sg + 6 * N3, *sp = sg + 7 * N3;
+        const double *su = sg + 8 * N3;
+        const double *sf = FIRST ? sr : sp;  // the tile holding the search direction p of this iteration
+
+        double ucol[NX], wcol[NX];
+        double *__restrict__ pe = p + (size_t)e * N3;
+        if (FIRST) {
+#pragma unroll
+            for (int k = 0; k < NX; k++) {
+                ucol[k] = sr[k * N2 + ij];
+                pe[k * N2 + ij] = ucol[k];
+                wcol[k] = 0.0;
+            }
+        } else {
+            double *__restrict__ ue = u + (size_t)e * N3;
+#pragma unroll
+            for (int k = 0; k < NX; k++) {
+                const double po = sp[k * N2 + ij];
+                const double pn = fma(beta, po, sr[k * N2 + ij]);
+                ue[k * N2 + ij] = fma(alpha, po, su[k * N2 + ij]);
+                sp[k * N2 + ij] = pn;
+                pe[k * N2 + ij] = pn;
+                ucol[k] = pn;
+                wcol[k] = 0.0;
+            }
+            group_barrier(1 + grp, N2);  // the p tile is complete
+        }
+#pragma unroll
+        for (int k = 0; k < NX; k++) {
+            const int q = k * N2 + ij;
+            const double G0 = sg[0 * N3 + q], G1 = sg[1 * N3 + q], G2 = sg[2 * N3 + q], G3 = sg[3 * N3 + q],
+                         G4 = sg[4 * N3 + q], G5 = sg[5 * N3 + q];
+            double ur = 0.0, us = 0.0, ut = 0.0;
+#pragma unroll
+            for (int m = 0; m < NX; m++) {
+                ur = fma(Di[m], sf[k * N2 + j * NX + m], ur);
+                us = fma(Dj[m], sf[k * N2 + m * NX + i], us);
+                ut = fma(c_D[k * NX + m], ucol[m], ut);
+            }
+            const double wr = fma(G0, ur, fma(G1, us, G2 * ut));
+            const double ws = fma(G1, ur, fma(G3, us, G4 * ut));
+            const double wt = fma(G2, ur, fma(G4, us, G5 * ut));
+            double *swr = s_w + (k & 1) * 2 * N2, *sws = swr + N2;
+            swr[ij] = wr;
+            sws[ij] = ws;
+#pragma unroll
+            for (int m = 0; m < NX; m++) wcol[m] = fma(c_D[k * NX + m], wt, wcol[m]);
+            group_barrier(1 + grp, N2);
+            double acc = wcol[k];
+#pragma unroll
+            for (int m = 0; m < NX; m++) {
+                acc = fma(DTi[m], swr[j * NX + m], acc);
+                acc = fma(DTj[m], sws[m * NX + i], acc);
+            }
+            wcol[k] = acc;
+        }
+        double *__restrict__ we = w + (size_t)e * N3;
+#pragma unroll
+        for (int k = 0; k < NX; k++) {
+            we[k * N2 + ij] = wcol[k];
+            pap = fma(ucol[k], wcol[k], pap);
+        }
+        group_barrier(1 + grp, N2);
+        if (leader) {
+            const int en = e + STAGES * stride;
+            if (en < nel) {
+                // the p tile was written through the generic proxy: order those writes before the async-proxy refill
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(stage, en);
+            }
+        }
+    }
+    if (pap_out != nullptr) {
+        double b = block_reduce(pap, s_red);
+        grid_reduce(b, partials, counter, s_red, [=](double t) { *pap_out = t; });
+    }
+}
+
+template <int NX, int GROUPS, int STAGES>
+inline void launch_ax_cg(const double *r, double *p, double *u, double *w, int nel, bool first, double *pap_out)
+{
+    Ctx &c = ctx();
+    using L = AxCgSmem<NX, GROUPS, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        NEKB_CUDA(cudaFuncSetAttribute(ax_cg_kernel<NX, GROUPS, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes));
+        NEKB_CUDA(cudaFuncSetAttribute(ax_cg_kernel<NX, GROUPS, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes));
+        configured = true;
+    }
+    const int grid = grid_for((nel + GROUPS - 1) / GROUPS, 1);
+    if (first)
+        ax_cg_kernel<NX, GROUPS, STAGES, true><<<grid, NX * NX * GROUPS, L::bytes, c.stream>>>(
+            r, p, u, c.g.p, w, nel, c.sc.p, c.partials.p, &c.sc.p->counter[0], pap_out);
+    else
+        ax_cg_kernel<NX, GROUPS, STAGES, false><<<grid, NX * NX * GROUPS, L::bytes, c.stream>>>(
+            r, p, u, c.g.p, w, nel, c.sc.p, c.partials.p, &c.sc.p->counter[0], pap_out);
+    NEKB_LAUNCHED();
+}
+
 // Jacobi diagonal, core/hmholtz.f:380-524 setprec before its dssum + invcol1 (:520-521).
 // One CTA per element, one thread per node.
 template <int NX>

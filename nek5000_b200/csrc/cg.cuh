@@ -142,12 +142,18 @@ struct CggosArgs {
     int gs_handle;
     int nel;
 };
+inline int cggos_run_fused(const CggosArgs &a, int maxit, double *hist_host, bool &used);  // below
 
 // Runs the BP5 solver; returns iterations performed.  hist_host: 3 doubles per iteration
 // (pap, rtz_new, max|u-x1| or 0).
 inline int cggos_run(const CggosArgs &a, double tol, int maxit, double *hist_host)
 {
     Ctx &c = ctx();
+    if (!(tol > 0.0)) {  // fixed iteration count (bp5.par: tol < 0): no per-iteration host decision needed
+        bool used = false;
+        const int it = cggos_run_fused(a, maxit, hist_host, used);
+        if (used) return it;
+    }
     const int64_t n = (int64_t)a.nel * c.nxyz;
     cudaStream_t s = c.stream;
     DevBuf<double> &r = c.work[0], &p = c.work[1], &ap = c.work[2];
@@ -229,6 +235,187 @@ inline int cggos_run(const CggosArgs &a, double tol, int maxit, double *hist_hos
         }
     }
     return iters;
+}
+
+// ---------------------------------------------------------------------------------------------- cggos, fused path
+// Iteration = ax_cg_kernel (u, p update + Ax + pap)  ->  gs  ->  cggos_update2_kernel (r update + weighted dot).
+// The multiplicity weight and the Dirichlet mask are folded into one byte per node: weights are 1/m with a small
+// integer m (vmult = 1/dssum(1), core/connect1.f:124-135), the mask is 0/1 (bp5.usr:142-153), so the byte
+// (m | mask==0 ? 0x80 : 0) reproduces both exactly; inputs that do not fit this form use the unfused path.
+__global__ void __launch_bounds__(CG_THREADS)
+    encode_weights_kernel(unsigned char *__restrict__ code, const double *__restrict__ mult,
+                          const double *__restrict__ mask, int64_t n, int *bad)
+{
+    int b = 0;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const double m = mult[t], k = mask[t];
+        const double c = rint(1.0 / m);
+        const bool okm = c >= 1.0 && c <= 127.0 && 1.0 / c == m;
+        const bool okk = k == 0.0 || k == 1.0;
+        if (!(okm && okk)) b = 1;
+        code[t] = (unsigned char)((okm ? (int)c : 0) | (k == 0.0 ? 0x80 : 0));
+    }
+    if (b) atomicOr(bad, 1);
+}
+
+// u = 0, r = rhs, (r,z) = sum mult r r  (bp5.usr:835-845; p = r is written by the first ax_cg_kernel)
+__global__ void __launch_bounds__(CG_THREADS)
+    cggos_init2_kernel(double *__restrict__ u, double *__restrict__ r, const double *__restrict__ rhs,
+                       const double *__restrict__ mult, int64_t n, CgScalars *sc, double *partials)
+{
+    __shared__ double red[33];
+    double s = 0.0;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const double rv = rhs[t];
+        u[t] = 0.0;
+        r[t] = rv;
+        s = fma(mult[t] * rv, rv, s);
+    }
+    double b = block_reduce(s, red);
+    grid_reduce(b, partials, &sc->counter[1], red, [=](double tot) {
+        sc->work[1] = tot;
+        sc->rtz1 = tot;
+        sc->alpha = 0.0;
+        sc->it = 0;
+        sc->done = 0;
+    });
+}
+
+// bp5.usr:853-866 without the u update: alpha = rpp1/pap ; r -= alpha*(mask*ap) ; (r,z) = sum mult r r.
+// The last block stores alpha, rotates the (r,z) scalars and advances the iteration counter.
+__global__ void __launch_bounds__(CG_THREADS)
+    cggos_update2_kernel(double *__restrict__ r, const double *__restrict__ ap, const unsigned char *__restrict__ code,
+                         int64_t n, CgScalars *sc, double *partials)
+{
+    __shared__ double red[33];
+    __shared__ double wtab[128];
+    const double pap = sc->work[0], rz = sc->work[1];
+    const double alpha = rz / pap;
+    if (threadIdx.x < 128) wtab[threadIdx.x] = threadIdx.x ? 1.0 / (double)threadIdx.x : 0.0;
+    __syncthreads();
+    double s = 0.0;
+    const int64_t n4 = n >> 2;
+    double2 *r2 = reinterpret_cast<double2 *>(r);
+    const double2 *a2 = reinterpret_cast<const double2 *>(ap);
+    const uchar4 *c4 = reinterpret_cast<const uchar4 *>(code);
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n4; t += (int64_t)gridDim.x * blockDim.x) {
+        double2 ra = r2[2 * t], rb = r2[2 * t + 1];
+        const double2 aa = a2[2 * t], ab = a2[2 * t + 1];
+        const uchar4 c = c4[t];
+        ra.x = fma(-alpha, (c.x & 0x80) ? 0.0 : aa.x, ra.x);
+        ra.y = fma(-alpha, (c.y & 0x80) ? 0.0 : aa.y, ra.y);
+        rb.x = fma(-alpha, (c.z & 0x80) ? 0.0 : ab.x, rb.x);
+        rb.y = fma(-alpha, (c.w & 0x80) ? 0.0 : ab.y, rb.y);
+        r2[2 * t] = ra;
+        r2[2 * t + 1] = rb;
+        s = fma(wtab[c.x & 0x7f] * ra.x, ra.x, s);
+        s = fma(wtab[c.y & 0x7f] * ra.y, ra.y, s);
+        s = fma(wtab[c.z & 0x7f] * rb.x, rb.x, s);
+        s = fma(wtab[c.w & 0x7f] * rb.y, rb.y, s);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t t = n4 << 2; t < n; t++) {
+            const unsigned char c = code[t];
+            r[t] = fma(-alpha, (c & 0x80) ? 0.0 : ap[t], r[t]);
+            s = fma(wtab[c & 0x7f] * r[t], r[t], s);
+        }
+    double b = block_reduce(s, red);
+    grid_reduce(b, partials, &sc->counter[2], red, [=](double tot) {
+        sc->rtz1 = rz;
+        sc->work[1] = tot;
+        sc->alpha = alpha;
+        sc->it = sc->it + 1;
+    });
+}
+
+// u += alpha * p with the device-resident alpha (the u update of the final iteration)
+__global__ void __launch_bounds__(CG_THREADS)
+    axpy_alpha_kernel(double *__restrict__ u, const double *__restrict__ p, int64_t n, const CgScalars *sc)
+{
+    const double alpha = sc->alpha;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+        u[t] = fma(alpha, p[t], u[t]);
+}
+
+__global__ void cggos_hist_kernel(const CgScalars *sc, double *hist, int slot)
+{
+    hist[3 * slot + 0] = sc->work[0];
+    hist[3 * slot + 1] = sc->work[1];
+}
+
+inline int cg_fused_enabled()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("NEKB_CG_FUSED");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+
+inline int cggos_run_fused(const CggosArgs &a, int maxit, double *hist_host, bool &used)
+{
+    Ctx &c = ctx();
+    used = false;
+    if (c.nx != 8 || !cg_fused_enabled() || maxit < 1 || a.nel < 1) return 0;
+    const int64_t n = (int64_t)a.nel * c.nxyz;
+    cudaStream_t s = c.stream;
+    const int grid = cg_grid(n);
+    c.wcode.ensure((size_t)n);
+    c.flags.ensure(4);
+    NEKB_CUDA(cudaMemsetAsync(c.flags.p, 0, sizeof(int), s));
+    encode_weights_kernel<<<grid, CG_THREADS, 0, s>>>(c.wcode.p, a.mult, a.mask, n, c.flags.p);
+    NEKB_LAUNCHED();
+    int bad = 0;
+    NEKB_CUDA(cudaMemcpyAsync(&bad, c.flags.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    NEKB_CUDA(cudaStreamSynchronize(s));
+    if (bad) return 0;
+    used = true;
+    DevBuf<double> &r = c.work[0], &p = c.work[1], &ap = c.work[2];
+    r.ensure(n), p.ensure(n), ap.ensure(n);
+    c.hist.ensure((size_t)3 * (maxit + 1));
+    if (hist_host) NEKB_CUDA(cudaMemsetAsync(c.hist.p, 0, sizeof(double) * 3 * (maxit + 1), s));
+    c.partials.ensure(4 * CG_PART_STRIDE);
+    CgScalars *sc = c.sc.p;
+    GsMap &h = gs_get(a.gs_handle);
+    NEKB_REQUIRE(h.n == n, "cggos: gs handle was set up for a different vector length");
+
+    cggos_init2_kernel<<<grid, CG_THREADS, 0, s>>>(a.u, r.p, a.rhs, a.mult, n, sc, c.partials.p + 1 * CG_PART_STRIDE);
+    NEKB_LAUNCHED();
+    comm_allreduce_sum(&sc->work[1], 1);
+    for (int iter = 1; iter <= maxit; iter++) {
+        prof_begin(PROF_AX);
+        launch_ax_cg<8, 3, 2>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]);
+        prof_end(PROF_AX);
+        comm_allreduce_sum(&sc->work[0], 1);
+        prof_begin(PROF_GS);
+        gs_op(a.gs_handle, ap.p, 1, nullptr);
+        prof_end(PROF_GS);
+        prof_begin(PROF_UPDATE);
+        cggos_update2_kernel<<<grid, CG_THREADS, 0, s>>>(r.p, ap.p, c.wcode.p, n, sc, c.partials.p + 2 * CG_PART_STRIDE);
+        NEKB_LAUNCHED();
+        prof_end(PROF_UPDATE);
+        comm_allreduce_sum(&sc->work[1], 1);
+        if (hist_host) {
+            cggos_hist_kernel<<<1, 1, 0, s>>>(sc, c.hist.p, iter - 1);
+            NEKB_LAUNCHED();
+        }
+    }
+    prof_begin(PROF_PUPDATE);
+    axpy_alpha_kernel<<<grid, CG_THREADS, 0, s>>>(a.u, p.p, n, sc);
+    NEKB_LAUNCHED();
+    prof_end(PROF_PUPDATE);
+    if (prof().on) {
+        NEKB_CUDA(cudaStreamSynchronize(s));
+        prof_collect();
+    }
+    if (hist_host) {
+        std::vector<double> hh((size_t)3 * maxit);
+        NEKB_CUDA(cudaMemcpyAsync(hh.data(), c.hist.p, sizeof(double) * hh.size(), cudaMemcpyDeviceToHost, s));
+        NEKB_CUDA(cudaStreamSynchronize(s));
+        for (size_t q = 0; q < hh.size(); q++) hist_host[q] = hh[q];
+    }
+    return maxit;
 }
 
 // ---------------------------------------------------------------------------------------------- cggo

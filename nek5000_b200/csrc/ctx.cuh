@@ -19,6 +19,7 @@ struct CgScalars {
     double rtz1, rtz2;     // cggo: (z,r) of this / previous iteration
     double rho;            // cggo: (w,p)
     double rbn2, rbn0, tol;
+    double alpha;          // cggos (fused path): step length of the last completed iteration
     double work[4];
 };
 
@@ -79,6 +80,8 @@ struct Ctx {
     DevBuf<double> partials;       // >= 4 * max grid
     DevBuf<CgScalars> sc;
     DevBuf<double> hist;           // device history arrays
+    DevBuf<unsigned char> wcode;   // per-node weight/mask codes of the fused cggos path
+    DevBuf<int> flags;             // small device flag words
     DevBuf<double> work[8];        // CG work vectors (r, p, w, d, ...)
     DevBuf<double> stage[8];       // device staging of the host-buffer (Fortran-named) entry points
 
