@@ -237,6 +237,53 @@ void *nekb_bp5_devptr(const char *which);
 int nekb_bp5_gs_handle(void);
 
 /* ------------------------------------------------------------------------------------
+ * F. Pressure preconditioner (additive Schwarz / FDM multigrid) and its GMRES driver
+ * ---------------------------------------------------------------------------------- */
+
+/* core/hsmg.f:2234 h1mg_setup() (+ core/navier6.f:82 swap_lengths, core/navier8.f:83 set_up_h1_crs).  The
+ * reference routine has no arguments and reads COMMON state; the Fortran glue passes that state here:
+ *   fbc[6*nelv]  (lbr,rbr,lbs,rbs,lbt,rbt) of get_fast_bc (core/fast3d.f:802-877) per element: 0 interior /
+ *                periodic, 1 Dirichlet for the pressure ('O','ON',...), 2 Neumann ('v','W','SYM',...);
+ *   xm1,ym1,zm1  /gxyz/ coordinates (host, lx1^3*nelv each) for swap_lengths / plane_space;
+ *   vertex       /ivrtx/ vertex(8,nelv) in symmetric order (get_vert);
+ *   null_space   ifvcor (core/navier8.f:208-212).
+ * The geometric factors must have been registered (section B); levels follow h1mg_setup_mg_nx (:2272-2337). */
+int nekb_h1mg_setup(const int *fbc, const double *xm1, const double *ym1, const double *zm1, const int64_t *vertex,
+                    int nelv, int null_space);
+/* core/hsmg.f:1855 h1mg_solve(z,rhs,if_hybrid), additive form (if_hybrid = .false., core/gmres.f:330), on device
+ * buffers.  As in the reference, rhs is masked in place (hsmg.f:449). */
+int nekb_h1mg_solve_dev(double *z_dev, double *rhs_dev);
+void h1mg_solve_(double *z, double *rhs, const int *if_hybrid);
+/* One h1mg_schwarz (core/hsmg.f:425-494, sigma = 1) at `level` (1-based as in the reference, 2..lmax); r is masked in
+ * place.  And the coarse solve of hsmg_coarse_solve (:1321-1354 -> crs_solve, core/crs_xxt.c:926-965) on the
+ * 2^3-per-element vertex arrays. */
+int nekb_h1mg_schwarz_dev(int level, double *e_dev, double *r_dev);
+int nekb_crs_solve_dev(double *e_dev, const double *r_dev);
+/* Sizes: number of levels, points per direction of every level (coarse first), distinct 1-D eigen-systems per
+ * level, iterations of the last coarse solve. */
+int nekb_h1mg_info(int *lmax, int *nh3, int *ntab3, int *crs_iters);
+/* Host copies of setup products for parity tests.  which: "mask","rstr_wt","swt" (level-sized, level 1-based),
+ * "J" (interpolation level -> level+1, row-major nf x nc), "lm","ll","lr" (3*nelv, direction-major; level ignored),
+ * "crs_a" (64*nelv, a(i,j,e) as a[e][i][j]). */
+int nekb_h1mg_get(const char *which, int level, double *host_out, size_t n_doubles);
+/* Relative residual and iteration cap of the device coarse solve (defaults 1e-13, 2000). */
+int nekb_crs_set_tolerance(double tol, int maxit);
+void nekb_h1mg_free(void);
+
+/* State hmh_gmres reads from COMMON: pmask (core/SOLN), binvm1 (core/MASS), tolps (core/TSTEP), param(21), ifvcor
+ * (core/INPUT), nelgv; volvm1 and istep come from nekb_set_step_info.  Host arrays of lx1^3*nelv doubles. */
+int nekb_set_pressure_state(const double *pmask, const double *binvm1, double tolps, double param21, int ifvcor,
+                            int64_t nelgv);
+/* core/gmres.f:304 hmh_gmres(res,h1,h2,wt,iter): on entry *iter = maxit, on return the iterations performed; res is
+ * overwritten with the solution.  h1mg_solve is the preconditioner (ifmgrid, param(40) in 0..2). */
+void hmh_gmres_(double *res, const double *h1, const double *h2, const double *wt, int *iter);
+/* The same on device buffers with an explicit tolerance: tol > 0 absolute on |gamma|/sqrt(volvm1), tol < 0 relative
+ * to the initial residual (param(21) < 0).  hist_host (may be NULL, maxit+1 doubles) receives rnorm per iteration;
+ * h2_dev may be NULL (h2 = 0).  ifvcor/nelgv as registered by nekb_set_pressure_state. */
+int nekb_hmh_gmres_dev(double *res_dev, const double *h1_dev, const double *h2_dev, const double *wt_dev,
+                       const double *pmask_dev, double tol, int maxit, int *iter, double *hist_host, double *div0);
+
+/* ------------------------------------------------------------------------------------
  * E. Plain device-memory helpers for host programs without a CUDA binding of their own
  * ---------------------------------------------------------------------------------- */
 void *nekb_dev_alloc(size_t bytes);

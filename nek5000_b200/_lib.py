@@ -136,6 +136,21 @@ def lib() -> C.CDLL:
     L.axhm1_.restype = None
     L.glsc3_.argtypes = [vp, vp, vp, ip]
     L.glsc3_.restype = C.c_double
+    # section F: pressure preconditioner + GMRES
+    L.nekb_h1mg_setup.argtypes = [i32p, f64p, f64p, f64p, i64p, C.c_int, C.c_int]
+    L.nekb_h1mg_solve_dev.argtypes = [vp, vp]
+    L.h1mg_solve_.argtypes = [vp, vp, ip]
+    L.h1mg_solve_.restype = None
+    L.nekb_h1mg_schwarz_dev.argtypes = [C.c_int, vp, vp]
+    L.nekb_crs_solve_dev.argtypes = [vp, vp]
+    L.nekb_h1mg_info.argtypes = [ip, ip, ip, ip]
+    L.nekb_h1mg_get.argtypes = [C.c_char_p, C.c_int, vp, C.c_size_t]
+    L.nekb_crs_set_tolerance.argtypes = [C.c_double, C.c_int]
+    L.nekb_h1mg_free.restype = None
+    L.nekb_set_pressure_state.argtypes = [vp, vp, C.c_double, C.c_double, C.c_int, C.c_int64]
+    L.hmh_gmres_.argtypes = [vp, vp, vp, vp, ip]
+    L.hmh_gmres_.restype = None
+    L.nekb_hmh_gmres_dev.argtypes = [vp, vp, vp, vp, vp, C.c_double, C.c_int, ip, vp, dp]
     _lib = L
     return L
 

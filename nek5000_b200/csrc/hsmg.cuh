@@ -1,0 +1,1093 @@
+// hsmg.cuh -- the pressure preconditioner: additive multilevel overlapping-Schwarz / fast-diagonalisation
+// smoother with a vertex-mesh coarse solve.
+//
+// Replaces core/hsmg.f: h1mg_setup (:2234-2270) and h1mg_solve (:1855-1949, additive: if_hybrid = .false. as
+// hmh_gmres passes it, core/gmres.f:330), built from h1mg_schwarz (:425-494), hsmg_extrude (:368-423),
+// hsmg_schwarz_toext3d / toreg3d (:580-631), hsmg_fdm / hsmg_do_fast (:885-929), hsmg_schwarz_wt3d (:1285-1319),
+// hsmg_do_wt (:932-985), h1mg_rstr (:2216-2232), hsmg_intp (:205-212), h1mg_mask (:2044-2071), the gs wrappers
+// (:326-366) and the coarse solve (:1321-1354 -> crs_solve, core/crs_xxt.c:926-965, operator from
+// core/navier8.f:83-233, 1648-1690).
+//
+// Device design (not the reference's sweep structure):
+//  * The extended (n+2)^3 arrays of the reference exist only inside shared memory.  What crosses element
+//    boundaries in hsmg_extrude + hsmg_schwarz_dssum is, per element face, one n x n layer; those layers live
+//    in compact "face buffers" f[e][6][n*n] with their own gather-scatter handle (ids = the border-face ids of
+//    the reference's (n+2)^3 numbering), so the overlap exchange moves 6 n^2 values per element instead of
+//    sweeping (n+2)^3 arrays four times.
+//  * One CTA pass per element does toext + border fill + S^T (x) S^T (x) S^T, the eigenvalue scaling and
+//    S (x) S (x) S + toreg.  The diagonal D = 1/(lam_r + lam_s + lam_t) is recomputed from the 3 n_l eigenvalues
+//    instead of being streamed ((n+2)^3 doubles per element in the reference, core/HSMG mg_fast_d).
+//  * The 1-D eigen-systems are de-duplicated: elements index a table of distinct (lbc, rbc, ll, lm, lr) systems,
+//    so on regular meshes S stays L2/L1-resident.
+//  * Masks (integer pointer lists in the reference, :2465-2499) and the Schwarz weights (face-layer arrays,
+//    :3044-3100) are stored as full-array multipliers folded into one array per level.
+#pragma once
+#include <cmath>
+#include <map>
+#include <tuple>
+
+#include "setup.cuh"
+
+namespace nekb {
+
+int gs_setup_from_host_ids(const int64_t *id_host, int64_t n, const int32_t *cand, int64_t ncand);  // nekb200.cu
+
+// ================================================================================================ host-side 1-D setup
+// core/fast3d.f:1294-1349 fd_weights_full (Fornberg): c[j*(m+1)+k], j = 0..n, k = 0..m
+inline void fd_weights_full(double xx, const double *x, int n, int m, std::vector<double> &c)
+{
+    c.assign((size_t)(n + 1) * (m + 1), 0.0);
+    auto C = [&](int j, int k) -> double & { return c[(size_t)j * (m + 1) + k]; };
+    double c1 = 1.0, c4 = x[0] - xx;
+    C(0, 0) = 1.0;
+    for (int i = 1; i <= n; i++) {
+        const int mn = i < m ? i : m;
+        double c2 = 1.0;
+        const double c5 = c4;
+        c4 = x[i] - xx;
+        for (int j = 0; j < i; j++) {
+            const double c3 = x[i] - x[j];
+            c2 = c2 * c3;
+            if (j == i - 1) {
+                for (int k = mn; k >= 1; k--) C(i, k) = c1 * (k * C(i - 1, k - 1) - c5 * C(i - 1, k)) / c2;
+                C(i, 0) = -c1 * c5 * C(i - 1, 0) / c2;
+            }
+            for (int k = mn; k >= 1; k--) C(j, k) = (c4 * C(j, k) - k * C(j, k - 1)) / c3;
+            C(j, 0) = c4 * C(j, 0) / c3;
+        }
+        c1 = c2;
+    }
+}
+
+// core/fast3d.f:1215-1292 semhat: ah (n+1)^2 (ah[i*(n+1)+j], symmetric), bh, zh for polynomial order n
+inline void semhat_host(int n, std::vector<double> &ah, std::vector<double> &bh, std::vector<double> &zh)
+{
+    const int np = n + 1;
+    std::vector<double> Dunused;
+    gll_build(np, zh, bh, Dunused);
+    std::vector<double> d((size_t)np * np), c;
+    for (int i = 0; i < np; i++) {
+        fd_weights_full(zh[i], zh.data(), n, 1, c);
+        for (int j = 0; j < np; j++) d[(size_t)i * np + j] = c[(size_t)j * 2 + 1];
+    }
+    ah.assign((size_t)np * np, 0.0);
+    for (int j = 0; j < np; j++)
+        for (int i = 0; i < np; i++) {
+            double s = 0.0;
+            for (int k = 0; k < np; k++) s = s + d[(size_t)k * np + i] * bh[k] * d[(size_t)k * np + j];
+            ah[(size_t)i * np + j] = s;
+        }
+}
+
+// Generalised symmetric-definite eigenproblem A x = lam B x, eigenvalues ascending, eigenvectors B-orthonormal in
+// the columns of Z (Z[i*n+a]) -- what LAPACK dsygv(1,'V','U') returns to generalev (core/hmholtz.f:1369-1418), up
+// to the sign / rotation freedom that S f(lam) S^T does not see.  Cholesky reduction + cyclic Jacobi.
+inline void generalev_host(int n, const std::vector<double> &A, const std::vector<double> &B, std::vector<double> &Z,
+                           std::vector<double> &lam)
+{
+    std::vector<long double> L((size_t)n * n, 0.0L), C((size_t)n * n), V((size_t)n * n, 0.0L);
+    for (int j = 0; j < n; j++) {  // B = L L^T
+        long double s = B[(size_t)j * n + j];
+        for (int k = 0; k < j; k++) s -= L[(size_t)j * n + k] * L[(size_t)j * n + k];
+        NEKB_REQUIRE(s > 0.0L, "generalev: B is not positive definite");
+        L[(size_t)j * n + j] = sqrtl(s);
+        for (int i = j + 1; i < n; i++) {
+            long double t = B[(size_t)i * n + j];
+            for (int k = 0; k < j; k++) t -= L[(size_t)i * n + k] * L[(size_t)j * n + k];
+            L[(size_t)i * n + j] = t / L[(size_t)j * n + j];
+        }
+    }
+    // C = L^-1 A L^-T : first X = L^-1 A (forward substitution on columns), then C = X L^-T
+    std::vector<long double> X((size_t)n * n);
+    for (int c0 = 0; c0 < n; c0++)
+        for (int i = 0; i < n; i++) {
+            long double t = 0.5L * ((long double)A[(size_t)i * n + c0] + (long double)A[(size_t)c0 * n + i]);
+            for (int k = 0; k < i; k++) t -= L[(size_t)i * n + k] * X[(size_t)k * n + c0];
+            X[(size_t)i * n + c0] = t / L[(size_t)i * n + i];
+        }
+    for (int r0 = 0; r0 < n; r0++)
+        for (int j = 0; j < n; j++) {
+            long double t = X[(size_t)r0 * n + j];
+            for (int k = 0; k < j; k++) t -= C[(size_t)r0 * n + k] * L[(size_t)j * n + k];
+            C[(size_t)r0 * n + j] = t / L[(size_t)j * n + j];
+        }
+    for (int i = 0; i < n; i++)
+        for (int j = i + 1; j < n; j++) {
+            const long double a = 0.5L * (C[(size_t)i * n + j] + C[(size_t)j * n + i]);
+            C[(size_t)i * n + j] = C[(size_t)j * n + i] = a;
+        }
+    for (int i = 0; i < n; i++) V[(size_t)i * n + i] = 1.0L;
+    for (int sweep = 0; sweep < 100; sweep++) {
+        long double off = 0.0L, dia = 0.0L;
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) (i == j ? dia : off) += C[(size_t)i * n + j] * C[(size_t)i * n + j];
+        if (off <= 1e-40L * dia || off == 0.0L) break;
+        for (int p = 0; p < n - 1; p++)
+            for (int q = p + 1; q < n; q++) {
+                const long double apq = C[(size_t)p * n + q];
+                if (apq == 0.0L) continue;
+                const long double theta = (C[(size_t)q * n + q] - C[(size_t)p * n + p]) / (2.0L * apq);
+                const long double t = (theta >= 0 ? 1.0L : -1.0L) / (fabsl(theta) + sqrtl(theta * theta + 1.0L));
+                const long double cs = 1.0L / sqrtl(t * t + 1.0L), sn = t * cs;
+                for (int k = 0; k < n; k++) {
+                    const long double akp = C[(size_t)k * n + p], akq = C[(size_t)k * n + q];
+                    C[(size_t)k * n + p] = cs * akp - sn * akq;
+                    C[(size_t)k * n + q] = sn * akp + cs * akq;
+                }
+                for (int k = 0; k < n; k++) {
+                    const long double apk = C[(size_t)p * n + k], aqk = C[(size_t)q * n + k];
+                    C[(size_t)p * n + k] = cs * apk - sn * aqk;
+                    C[(size_t)q * n + k] = sn * apk + cs * aqk;
+                }
+                for (int k = 0; k < n; k++) {
+                    const long double vkp = V[(size_t)k * n + p], vkq = V[(size_t)k * n + q];
+                    V[(size_t)k * n + p] = cs * vkp - sn * vkq;
+                    V[(size_t)k * n + q] = sn * vkp + cs * vkq;
+                }
+            }
+    }
+    std::vector<int> ord(n);
+    for (int i = 0; i < n; i++) ord[i] = i;
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return C[(size_t)a * n + a] < C[(size_t)b * n + b]; });
+    Z.assign((size_t)n * n, 0.0);
+    lam.assign(n, 0.0);
+    for (int a = 0; a < n; a++) {
+        const int src = ord[a];
+        lam[a] = (double)C[(size_t)src * n + src];
+        // z = L^-T v : back substitution
+        std::vector<long double> zc(n);
+        for (int i = n - 1; i >= 0; i--) {
+            long double t = V[(size_t)i * n + src];
+            for (int k = i + 1; k < n; k++) t -= L[(size_t)k * n + i] * zc[k];
+            zc[i] = t / L[(size_t)i * n + i];
+        }
+        for (int i = 0; i < n; i++) Z[(size_t)i * n + a] = (double)zc[i];
+    }
+}
+
+// core/hsmg.f:775-879 hsmg_setup_fast1d (+ _a, _b): S[i*nl+a] with the boundary rows zeroed, lam[nl]
+inline void fast1d_host(int lbc, int rbc, double ll, double lm, double lr, const std::vector<double> &ah,
+                        const std::vector<double> &bh, int n, std::vector<double> &S, std::vector<double> &lam)
+{
+    const int nl = n + 3, np = n + 1;
+    std::vector<double> a((size_t)nl * nl, 0.0), b((size_t)nl * nl, 0.0);
+    auto A = [&](int i, int j) -> double & { return a[(size_t)i * nl + j]; };
+    auto Bm = [&](int i, int j) -> double & { return b[(size_t)i * nl + j]; };
+    auto AH = [&](int i, int j) { return ah[(size_t)i * np + j]; };
+    const int i0 = lbc == 1 ? 1 : 0, i1 = rbc == 1 ? n - 1 : n;
+    double fac = 2.0 / lm;
+    A(1, 1) = 1.0;
+    A(n + 1, n + 1) = 1.0;
+    for (int j = i0; j <= i1; j++)
+        for (int i = i0; i <= i1; i++) A(i + 1, j + 1) = fac * AH(i, j);
+    if (lbc == 0) {
+        fac = 2.0 / ll;
+        A(0, 0) = fac * AH(n - 1, n - 1);
+        A(1, 0) = fac * AH(n, n - 1);
+        A(0, 1) = fac * AH(n - 1, n);
+        A(1, 1) = A(1, 1) + fac * AH(n, n);
+    } else
+        A(0, 0) = 1.0;
+    if (rbc == 0) {
+        fac = 2.0 / lr;
+        A(n + 1, n + 1) = A(n + 1, n + 1) + fac * AH(0, 0);
+        A(n + 2, n + 1) = fac * AH(1, 0);
+        A(n + 1, n + 2) = fac * AH(0, 1);
+        A(n + 2, n + 2) = fac * AH(1, 1);
+    } else
+        A(n + 2, n + 2) = 1.0;
+    fac = 0.5 * lm;
+    Bm(1, 1) = 1.0;
+    Bm(n + 1, n + 1) = 1.0;
+    for (int i = i0; i <= i1; i++) Bm(i + 1, i + 1) = fac * bh[i];
+    if (lbc == 0) {
+        fac = 0.5 * ll;
+        Bm(0, 0) = fac * bh[n - 1];
+        Bm(1, 1) = Bm(1, 1) + fac * bh[n];
+    } else
+        Bm(0, 0) = 1.0;
+    if (rbc == 0) {
+        fac = 0.5 * lr;
+        Bm(n + 1, n + 1) = Bm(n + 1, n + 1) + fac * bh[0];
+        Bm(n + 2, n + 2) = fac * bh[1];
+    } else
+        Bm(n + 2, n + 2) = 1.0;
+    generalev_host(nl, a, b, S, lam);
+    auto zero_row = [&](int r) {
+        for (int j = 0; j < nl; j++) S[(size_t)r * nl + j] = 0.0;
+    };
+    if (lbc > 0) zero_row(0);
+    if (lbc == 1) zero_row(1);
+    if (rbc > 0) zero_row(nl - 1);
+    if (rbc == 1) zero_row(nl - 2);
+}
+
+// core/hsmg.f:2272-2337 h1mg_setup_mg_nx (3-D, lx2 = lx1)
+inline std::vector<int> mg_orders(int lx1)
+{
+    static const int mgn2[10] = {1, 2, 2, 2, 2, 3, 3, 5, 5, 5};
+    const int lmax = lx1 == 4 ? 2 : 3;
+    int mglx2 = 2 * (lx1 / 4) + 1;
+    if (lx1 == 5) mglx2 = 3;
+    if (lx1 <= 10) mglx2 = mgn2[(lx1 < 10 ? lx1 : 10) - 1];
+    if (lx1 == 8) mglx2 = 3;
+    if (mglx2 > 3) mglx2 = 3;
+    std::vector<int> nx = {1, mglx2, mglx2 + 1};
+    nx[lmax - 1] = lx1 - 1;
+    nx.resize(lmax);
+    return nx;
+}
+
+// ================================================================================================ state
+struct MgLevel {
+    int nh = 0, nl = 0;
+    int64_t n = 0;              // nh^3 * nel
+    int gs = -1, gs_face = -1;  // handles: nh^3 grid ; face buffers [nel][6][nh*nh]
+    DevBuf<double> mask;        // 0/1 (h1mg_setup_mask)
+    DevBuf<double> rstr_wt;     // 1 / multiplicity (hsmg_setup_rstr_wt)
+    DevBuf<double> swt;         // mask * Schwarz weight (h1mg_setup_schwarz_wt_1), levels >= 2
+    DevBuf<double> J;           // to the next finer level: J[a*nh + i], a < nh(l+1)
+    DevBuf<double> Stab, lamtab, eps;
+    DevBuf<int32_t> sidx;       // [nel][3] rows of Stab / lamtab
+    int ntab = 0;
+    DevBuf<double> r, e, f_own, f_sum;
+};
+
+struct CrsSolver {
+    int gs = -1;
+    int64_t n = 0;              // 8 * nel
+    DevBuf<double> a;           // [nel][8][8] local Galerkin matrices, a[e][i][j]
+    DevBuf<double> mask, mult, dinv;
+    DevBuf<double> b, x, r, p, w;
+    double ndof = 0.0;          // distinct unmasked dofs (all ranks)
+    int null_space = 0;
+    int last_iters = 0;
+    double tol = 1e-13;
+    int maxit = 2000;
+};
+
+struct H1mg {
+    bool ready = false;
+    int lmax = 0, nel = 0, lx1 = 0;
+    std::vector<MgLevel> lev;
+    CrsSolver crs;
+    // setup products kept on the host for parity tests
+    std::vector<double> lm_host, ll_host, lr_host;  // [3][nel]
+};
+inline H1mg &h1mg()
+{
+    static H1mg m;
+    return m;
+}
+
+// ================================================================================================ kernels
+// Face f of an element: 0 r-, 1 r+, 2 s-, 3 s+, 4 t-, 5 t+.  Entry (a, b) of a face holds the two tangential
+// indices in ascending direction order (r-faces: (j,k); s-faces: (i,k); t-faces: (i,j)), a fastest.
+
+// hsmg.f:449 h1mg_mask + the data hsmg_extrude(work,0,zero,work,2,one) moves (:459): r *= mask in place;
+// f_own = f_sum = r on the first interior layer of every face.
+__global__ void __launch_bounds__(256)
+    mg_mask_faces_kernel(double *__restrict__ r, const double *__restrict__ mask, double *__restrict__ f_own,
+                         double *__restrict__ f_sum, int nh, int64_t n)
+{
+    const int n2 = nh * nh, n3 = n2 * nh;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = t / n3;
+        const int q = (int)(t - e * n3), i = q % nh, j = (q / nh) % nh, k = q / n2;
+        const double v = r[t] * mask[t];
+        r[t] = v;
+        double *fo = f_own + e * 6 * n2, *fs = f_sum + e * 6 * n2;
+        if (i == 1) fo[0 * n2 + k * nh + j] = v, fs[0 * n2 + k * nh + j] = v;
+        if (i == nh - 2) fo[1 * n2 + k * nh + j] = v, fs[1 * n2 + k * nh + j] = v;
+        if (j == 1) fo[2 * n2 + k * nh + i] = v, fs[2 * n2 + k * nh + i] = v;
+        if (j == nh - 2) fo[3 * n2 + k * nh + i] = v, fs[3 * n2 + k * nh + i] = v;
+        if (k == 1) fo[4 * n2 + j * nh + i] = v, fs[4 * n2 + j * nh + i] = v;
+        if (k == nh - 2) fo[5 * n2 + j * nh + i] = v, fs[5 * n2 + j * nh + i] = v;
+    }
+}
+
+// hsmg.f:452-468: toext3d, border := neighbour's first interior layer (f_sum - f_own after the face gs),
+// hsmg_do_fast (S^T x S^T x S^T, D, S x S x S), then the interior (toreg3d) goes to e and the border layer of the
+// local solution to the face buffers for the second exchange (:471).
+// EPB elements per CTA, NL*NL threads per element, thread (p,q) owns one line of the current direction.
+template <int NL, int EPB>
+__global__ void __launch_bounds__(NL *NL *EPB)
+    mg_fdm_kernel(const double *__restrict__ r, double *__restrict__ e, const double *f_in_sum, const double *f_in_own,
+                  double *f_out_own, double *f_out_sum,  // may alias the inputs (each element touches only its own faces)
+                  const double *__restrict__ Stab, const double *__restrict__ lamtab, const int32_t *__restrict__ sidx,
+                  const double *__restrict__ eps, int nel)
+{
+    constexpr int NH = NL - 2, NLP = (NL % 2 == 0) ? NL + 1 : NL, L2 = NL * NL, H2 = NH * NH, H3 = NH * NH * NH;
+    constexpr int TILE = NL * NL * NLP;
+    __shared__ double s_t[EPB][TILE];
+    __shared__ double s_S[EPB][3][L2];
+    __shared__ double s_lam[EPB][3][NL];
+    const int es = threadIdx.x / L2, tl = threadIdx.x % L2, p = tl % NL, q = tl / NL;
+    const int el = blockIdx.x * EPB + es;
+    const bool act = el < nel;
+    double *T = s_t[es];
+    auto at = [](int i, int j, int k) { return (k * NL + j) * NLP + i; };
+
+    if (act) {
+        for (int d = 0; d < 3; d++) {
+            const int row = sidx[(size_t)el * 3 + d];
+            for (int t = tl; t < L2; t += L2) s_S[es][d][t] = Stab[(size_t)row * L2 + t];
+            if (tl < NL) s_lam[es][d][tl] = lamtab[(size_t)row * NL + tl];
+        }
+        for (int t = tl; t < TILE; t += L2) T[t] = 0.0;
+    }
+    __syncthreads();
+    if (act) {
+        const double *re = r + (size_t)el * H3;
+        for (int t = tl; t < H3; t += L2) {
+            const int i = t % NH, j = (t / NH) % NH, k = t / H2;
+            T[at(i + 1, j + 1, k + 1)] = re[t];
+        }
+        const double *fs = f_in_sum + (size_t)el * 6 * H2, *fo = f_in_own + (size_t)el * 6 * H2;
+        for (int t = tl; t < 6 * H2; t += L2) {
+            const int f = t / H2, ab = t - f * H2, a = ab % NH, b = ab / NH;
+            const double v = fs[t] - fo[t];
+            const int side = (f & 1) ? NL - 1 : 0;
+            int idx;
+            if (f < 2) idx = at(side, a + 1, b + 1);
+            else if (f < 4) idx = at(a + 1, side, b + 1);
+            else idx = at(a + 1, b + 1, side);
+            T[idx] = v;
+        }
+    }
+    __syncthreads();
+    double in[NL], out[NL];
+    // forward: S^T in r, s, t
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        if (act) {
+            const int base = d == 0 ? at(0, p, q) : (d == 1 ? at(p, 0, q) : at(p, q, 0));
+            const int stride = d == 0 ? 1 : (d == 1 ? NLP : NL * NLP);
+            const double *S = s_S[es][d];
+#pragma unroll
+            for (int i = 0; i < NL; i++) in[i] = T[base + i * stride];
+#pragma unroll
+            for (int a = 0; a < NL; a++) {
+                double s = 0.0;
+#pragma unroll
+                for (int i = 0; i < NL; i++) s = fma(S[i * NL + a], in[i], s);
+                out[a] = s;
+            }
+            if (d == 2) {  // last forward pass: apply D = 1/(lam_r + lam_s + lam_t) (hsmg.f:740-752)
+                const double ep = eps[el], lrs = s_lam[es][0][p] + s_lam[es][1][q];
+#pragma unroll
+                for (int a = 0; a < NL; a++) {
+                    const double diag = lrs + s_lam[es][2][a];
+                    out[a] = diag > ep ? out[a] * (1.0 / diag) : 0.0;
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < NL; a++) T[base + a * stride] = out[a];
+        }
+        __syncthreads();
+    }
+    // backward: S in t, s, r (the three factors commute; this order keeps the t lines in place after the scaling)
+#pragma unroll
+    for (int dd = 0; dd < 3; dd++) {
+        const int d = 2 - dd;
+        if (act) {
+            const int base = d == 0 ? at(0, p, q) : (d == 1 ? at(p, 0, q) : at(p, q, 0));
+            const int stride = d == 0 ? 1 : (d == 1 ? NLP : NL * NLP);
+            const double *S = s_S[es][d];
+#pragma unroll
+            for (int i = 0; i < NL; i++) in[i] = T[base + i * stride];
+#pragma unroll
+            for (int a = 0; a < NL; a++) {
+                double s = 0.0;
+#pragma unroll
+                for (int i = 0; i < NL; i++) s = fma(S[a * NL + i], in[i], s);
+                out[a] = s;
+            }
+#pragma unroll
+            for (int a = 0; a < NL; a++) T[base + a * stride] = out[a];
+        }
+        __syncthreads();
+    }
+    if (act) {
+        double *ee = e + (size_t)el * H3;
+        for (int t = tl; t < H3; t += L2) {
+            const int i = t % NH, j = (t / NH) % NH, k = t / H2;
+            ee[t] = T[at(i + 1, j + 1, k + 1)];
+        }
+        double *fo = f_out_own + (size_t)el * 6 * H2, *fs = f_out_sum + (size_t)el * 6 * H2;
+        for (int t = tl; t < 6 * H2; t += L2) {
+            const int f = t / H2, ab = t - f * H2, a = ab % NH, b = ab / NH;
+            const int side = (f & 1) ? NL - 1 : 0;
+            int idx;
+            if (f < 2) idx = at(side, a + 1, b + 1);
+            else if (f < 4) idx = at(a + 1, side, b + 1);
+            else idx = at(a + 1, b + 1, side);
+            const double v = T[idx];
+            fo[t] = v;
+            fs[t] = v;
+        }
+    }
+}
+
+// hsmg.f:473-474: e(first interior layer) += neighbour's border solution (f_sum - f_own), r then s then t
+__global__ void __launch_bounds__(256)
+    mg_add_overlap_kernel(double *__restrict__ e, const double *__restrict__ f_sum, const double *__restrict__ f_own,
+                          int nh, int64_t n)
+{
+    const int n2 = nh * nh, n3 = n2 * nh;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t el = t / n3;
+        const int q = (int)(t - el * n3), i = q % nh, j = (q / nh) % nh, k = q / n2;
+        if (!(i == 1 || i == nh - 2 || j == 1 || j == nh - 2 || k == 1 || k == nh - 2)) continue;
+        const double *fs = f_sum + el * 6 * n2, *fo = f_own + el * 6 * n2;
+        double v = e[t];
+        if (i == 1) v += fs[0 * n2 + k * nh + j] - fo[0 * n2 + k * nh + j];
+        if (i == nh - 2) v += fs[1 * n2 + k * nh + j] - fo[1 * n2 + k * nh + j];
+        if (j == 1) v += fs[2 * n2 + k * nh + i] - fo[2 * n2 + k * nh + i];
+        if (j == nh - 2) v += fs[3 * n2 + k * nh + i] - fo[3 * n2 + k * nh + i];
+        if (k == 1) v += fs[4 * n2 + j * nh + i] - fo[4 * n2 + j * nh + i];
+        if (k == nh - 2) v += fs[5 * n2 + j * nh + i] - fo[5 * n2 + j * nh + i];
+        e[t] = v;
+    }
+}
+
+// v = [M (x) M (x) M] (u * wt) per element, M = mat[a*nu + i] (nv x nu); out = v or out += v.
+// h1mg_rstr (hsmg.f:2216-2232): M = J^T, wt = rstr_wt ; hsmg_intp (:205-212): M = J, wt = nullptr, accumulate.
+// One CTA per element; dynamic shared memory: 2 * max(nu,nv)^3 + nv*nu doubles.
+__global__ void __launch_bounds__(256)
+    mg_tensor3_kernel(double *__restrict__ out, const double *__restrict__ u, const double *__restrict__ wt,
+                      const double *__restrict__ mat, int nv, int nu, int transpose, int accumulate)
+{
+    extern __shared__ double s_mg[];
+    const int nm = nv > nu ? nv : nu, m3 = nm * nm * nm;
+    double *A = s_mg, *B = s_mg + m3, *M = s_mg + 2 * m3;
+    const int el = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int nu3 = nu * nu * nu, nv3 = nv * nv * nv;
+    for (int t = tid; t < nv * nu; t += nt) {
+        const int a = t / nu, i = t % nu;
+        M[t] = transpose ? mat[i * nv + a] : mat[t];
+    }
+    const double *ue = u + (size_t)el * nu3;
+    const double *we = wt ? wt + (size_t)el * nu3 : nullptr;
+    for (int t = tid; t < nu3; t += nt) A[t] = we ? ue[t] * we[t] : ue[t];
+    __syncthreads();
+    // r: B[a,j,k] = sum_i M[a,i] A[i,j,k]   (nv x nu x nu)
+    for (int t = tid; t < nv * nu * nu; t += nt) {
+        const int a = t % nv, jk = t / nv;
+        double s = 0.0;
+        for (int i = 0; i < nu; i++) s = fma(M[a * nu + i], A[jk * nu + i], s);
+        B[t] = s;
+    }
+    __syncthreads();
+    // s: A[a,b,k] = sum_j M[b,j] B[a,j,k]   (nv x nv x nu)
+    for (int t = tid; t < nv * nv * nu; t += nt) {
+        const int a = t % nv, b = (t / nv) % nv, k = t / (nv * nv);
+        double s = 0.0;
+        for (int j = 0; j < nu; j++) s = fma(M[b * nu + j], B[(k * nu + j) * nv + a], s);
+        A[t] = s;
+    }
+    __syncthreads();
+    // t: out[a,b,c] = sum_k M[c,k] A[a,b,k]
+    double *oe = out + (size_t)el * nv3;
+    for (int t = tid; t < nv3; t += nt) {
+        const int ab = t % (nv * nv), c = t / (nv * nv);
+        double s = 0.0;
+        for (int k = 0; k < nu; k++) s = fma(M[c * nu + k], A[k * nv * nv + ab], s);
+        oe[t] = accumulate ? oe[t] + s : s;
+    }
+}
+
+__global__ void __launch_bounds__(256) mg_copy_kernel(double *__restrict__ a, const double *__restrict__ b, int64_t n)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) a[t] = b[t];
+}
+
+// ------------------------------------------------------------------------------------------------ coarse grid
+// y[e][i] = sum_j a[e][i][j] x[e][j]
+__global__ void __launch_bounds__(256)
+    crs_matvec_kernel(double *__restrict__ y, const double *__restrict__ a, const double *__restrict__ x, int64_t n)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = t >> 3;
+        const int i = (int)(t & 7);
+        const double *ae = a + e * 64 + i * 8, *xe = x + e * 8;
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) s = fma(ae[j], xe[j], s);
+        y[t] = s;
+    }
+}
+// a[e][i][j] = sum_q b_i[q] * w[e][q] for one column j (get_local_crs_galerkin, navier8.f:1648-1690)
+__global__ void __launch_bounds__(256)
+    crs_galerkin_kernel(double *__restrict__ a, const double *__restrict__ w, const double *__restrict__ basis, int nxyz, int j)
+{
+    __shared__ double red[33];
+    const int e = blockIdx.x;
+    for (int i = 0; i < 8; i++) {
+        double s = 0.0;
+        for (int q = threadIdx.x; q < nxyz; q += blockDim.x) s = fma(basis[(size_t)i * nxyz + q], w[(size_t)e * nxyz + q], s);
+        const double tot = block_reduce(s, red);
+        if (threadIdx.x == 0) a[(size_t)e * 64 + i * 8 + j] = tot;
+    }
+}
+__global__ void __launch_bounds__(256)
+    crs_tile_basis_kernel(double *__restrict__ w, const double *__restrict__ basis_j, int nxyz, int64_t n)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) w[t] = basis_j[t % nxyz];
+}
+__global__ void __launch_bounds__(256)
+    crs_diag_kernel(double *__restrict__ d, const double *__restrict__ a, int64_t n)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) d[t] = a[(t >> 3) * 64 + (t & 7) * 9];
+}
+// d = mask ? 1/d : 0
+__global__ void __launch_bounds__(256)
+    crs_invdiag_kernel(double *__restrict__ d, const double *__restrict__ mask, int64_t n)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) d[t] = (mask[t] != 0.0 && d[t] != 0.0) ? 1.0 / d[t] : 0.0;
+}
+
+// Generic fused vector kernel with one weighted dot: used by the coarse PCG (vectors of 8*nel entries).
+//   MODE 0: out0 = sum a*b*m
+//   MODE 1: x += alpha*p ; r -= alpha*w ; out0 = sum r*(dinv*r)*m ; out1 = sum r*r*m        (alpha = s[0]/s[1])
+//   MODE 2: p = dinv*r + beta*p                                                              (beta  = s[2]/s[0])
+struct CrsScalars {
+    double rz, pw, rz_new, rr, rr0, shift;
+    int it, done;
+    unsigned counter[4];
+};
+__global__ void __launch_bounds__(256)
+    crs_dot_kernel(const double *__restrict__ a, const double *__restrict__ b, const double *__restrict__ m, int64_t n,
+                   double *out, double *partials, unsigned *counter)
+{
+    __shared__ double red[33];
+    double s = 0.0;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) s = fma(a[t] * b[t], m[t], s);
+    const double bs = block_reduce(s, red);
+    grid_reduce(bs, partials, counter, red, [=](double tot) { *out = tot; });
+}
+__global__ void __launch_bounds__(256)
+    crs_xr_kernel(double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p, const double *__restrict__ w,
+                  const double *__restrict__ dinv, const double *__restrict__ m, int64_t n, CrsScalars *sc, double *partials)
+{
+    __shared__ double red[33];
+    if (sc->done) return;
+    const double alpha = sc->rz / sc->pw;
+    double s1 = 0.0, s2 = 0.0;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        x[t] = fma(alpha, p[t], x[t]);
+        const double rv = fma(-alpha, w[t], r[t]);
+        r[t] = rv;
+        s1 = fma(rv * dinv[t] * rv, m[t], s1);
+        s2 = fma(rv * rv, m[t], s2);
+    }
+    const double b1 = block_reduce(s1, red), b2 = block_reduce(s2, red);
+    grid_reduce(b1, partials, &sc->counter[0], red, [=](double tot) { sc->rz_new = tot; });
+    grid_reduce(b2, partials + 1024, &sc->counter[1], red, [=](double tot) { sc->rr = tot; });
+}
+__global__ void crs_check_kernel(CrsScalars *sc, double tol2, int maxit)
+{
+    if (sc->done) return;
+    sc->it = sc->it + 1;
+    if (sc->rr <= tol2 * sc->rr0 || sc->it >= maxit || sc->rz_new == 0.0) sc->done = 1;
+}
+__global__ void __launch_bounds__(256)
+    crs_p_kernel(double *__restrict__ p, const double *__restrict__ r, const double *__restrict__ dinv, int64_t n, CrsScalars *sc,
+                 int first)
+{
+    if (sc->done) return;
+    const double beta = first ? 0.0 : sc->rz_new / sc->rz;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+        p[t] = fma(beta, p[t], dinv[t] * r[t]);
+}
+__global__ void crs_rotate_kernel(CrsScalars *sc)
+{
+    if (sc->done) return;
+    sc->rz = sc->rz_new;
+}
+// w *= mask ; pw = sum p*w*m
+__global__ void __launch_bounds__(256)
+    crs_pw_kernel(double *__restrict__ w, const double *__restrict__ p, const double *__restrict__ mask, const double *__restrict__ m,
+                  int64_t n, CrsScalars *sc, double *partials)
+{
+    __shared__ double red[33];
+    if (sc->done) return;
+    double s = 0.0;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const double wv = w[t] * mask[t];
+        w[t] = wv;
+        s = fma(wv * p[t], m[t], s);
+    }
+    const double b = block_reduce(s, red);
+    grid_reduce(b, partials, &sc->counter[2], red, [=](double tot) { sc->pw = tot; });
+}
+// a = (a - shift*flag) * mask
+__global__ void __launch_bounds__(256)
+    crs_shift_kernel(double *__restrict__ a, const double *__restrict__ mask, int64_t n, const double *sum, double inv_ndof)
+{
+    const double sh = *sum * inv_ndof;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) a[t] = (a[t] - sh) * mask[t];
+}
+
+inline DevBuf<CrsScalars> &crs_scalars()
+{
+    static DevBuf<CrsScalars> s;
+    return s;
+}
+
+inline int vec_grid(int64_t n)
+{
+    int64_t b = (n + 255) / 256;
+    const int64_t cap = (int64_t)ctx().num_sms * 4;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// crs_solve (core/crs_xxt.c:926-965) semantics on the element-local vertex arrays: x = Q A^-1 Q^T b on the unmasked
+// dofs, 0 on masked ones; with a null space the mean over the distinct dofs is removed.  XXT is a direct solver; here
+// the same system is solved by Jacobi-PCG on the device to a relative residual `tol` (documented in DESIGN.md).
+inline void crs_solve_dev(double *x_out, const double *b_in)
+{
+    Ctx &c = ctx();
+    CrsSolver &k = h1mg().crs;
+    cudaStream_t s = c.stream;
+    const int64_t n = k.n;
+    if (n == 0 && c.nranks <= 1) return;
+    const int grid = vec_grid(n);
+    DevBuf<CrsScalars> &scb = crs_scalars();
+    if (!scb.p) {
+        scb.alloc(1);
+        scb.zero(s);
+    }
+    CrsScalars *sc = scb.p;
+    c.partials.ensure(4 * CG_PART_STRIDE);
+    double *part = c.partials.p;
+    // b_glob = Q^T b, copied to every holder; masked dofs dropped
+    mg_copy_kernel<<<grid, 256, 0, s>>>(k.r.p, b_in, n);
+    NEKB_LAUNCHED();
+    gs_op(k.gs, k.r.p, 1, k.mask.p);
+    if (k.null_space) {  // make the right-hand side consistent: remove its mean over the distinct dofs
+        crs_dot_kernel<<<grid, 256, 0, s>>>(k.r.p, k.mask.p, k.mult.p, n, &sc->shift, part, &sc->counter[3]);
+        NEKB_LAUNCHED();
+        comm_allreduce_sum(&sc->shift, 1);
+        crs_shift_kernel<<<grid, 256, 0, s>>>(k.r.p, k.mask.p, n, &sc->shift, 1.0 / k.ndof);
+        NEKB_LAUNCHED();
+    }
+    NEKB_CUDA(cudaMemsetAsync(k.x.p, 0, sizeof(double) * (n ? n : 1), s));
+    NEKB_CUDA(cudaMemsetAsync(k.p.p, 0, sizeof(double) * (n ? n : 1), s));
+    NEKB_CUDA(cudaMemsetAsync(sc, 0, sizeof(CrsScalars), s));
+    // rz = (r, D^-1 r), rr0 = (r, r)
+    crs_dot_kernel<<<grid, 256, 0, s>>>(k.r.p, k.r.p, k.mult.p, n, &sc->rr0, part, &sc->counter[3]);
+    NEKB_LAUNCHED();
+    comm_allreduce_sum(&sc->rr0, 1);
+    double rr0 = 0.0;
+    NEKB_CUDA(cudaMemcpyAsync(&rr0, &sc->rr0, sizeof(double), cudaMemcpyDeviceToHost, s));
+    NEKB_CUDA(cudaStreamSynchronize(s));
+    k.last_iters = 0;
+    if (rr0 > 0.0) {
+        // w = D^-1 r ; rz = (r, w)
+        crs_p_kernel<<<grid, 256, 0, s>>>(k.p.p, k.r.p, k.dinv.p, n, sc, 1);
+        NEKB_LAUNCHED();
+        crs_dot_kernel<<<grid, 256, 0, s>>>(k.r.p, k.p.p, k.mult.p, n, &sc->rz, part, &sc->counter[3]);
+        NEKB_LAUNCHED();
+        comm_allreduce_sum(&sc->rz, 1);
+        const int batch = 16;
+        int launched = 0;
+        bool done = false;
+        while (!done) {
+            for (int b = 0; b < batch; b++) {
+                crs_matvec_kernel<<<grid, 256, 0, s>>>(k.w.p, k.a.p, k.p.p, n);
+                NEKB_LAUNCHED();
+                gs_op(k.gs, k.w.p, 1, nullptr);
+                crs_pw_kernel<<<grid, 256, 0, s>>>(k.w.p, k.p.p, k.mask.p, k.mult.p, n, sc, part);
+                NEKB_LAUNCHED();
+                comm_allreduce_sum(&sc->pw, 1);
+                crs_xr_kernel<<<grid, 256, 0, s>>>(k.x.p, k.r.p, k.p.p, k.w.p, k.dinv.p, k.mult.p, n, sc, part);
+                NEKB_LAUNCHED();
+                comm_allreduce_sum(&sc->rz_new, 2);  // rz_new, rr are adjacent
+                crs_check_kernel<<<1, 1, 0, s>>>(sc, k.tol * k.tol, k.maxit);
+                NEKB_LAUNCHED();
+                crs_p_kernel<<<grid, 256, 0, s>>>(k.p.p, k.r.p, k.dinv.p, n, sc, 0);
+                NEKB_LAUNCHED();
+                crs_rotate_kernel<<<1, 1, 0, s>>>(sc);
+                NEKB_LAUNCHED();
+                launched++;
+            }
+            CrsScalars hs;
+            NEKB_CUDA(cudaMemcpyAsync(&hs, sc, sizeof(CrsScalars), cudaMemcpyDeviceToHost, s));
+            NEKB_CUDA(cudaStreamSynchronize(s));
+            done = hs.done != 0;
+            k.last_iters = hs.it;
+            NEKB_REQUIRE(launched <= k.maxit + 2 * batch, "coarse PCG: convergence flag never raised");
+        }
+    }
+    if (k.null_space) {
+        crs_dot_kernel<<<grid, 256, 0, s>>>(k.x.p, k.mask.p, k.mult.p, n, &sc->shift, part, &sc->counter[3]);
+        NEKB_LAUNCHED();
+        comm_allreduce_sum(&sc->shift, 1);
+        crs_shift_kernel<<<grid, 256, 0, s>>>(k.x.p, k.mask.p, n, &sc->shift, 1.0 / k.ndof);
+        NEKB_LAUNCHED();
+    }
+    mg_copy_kernel<<<grid, 256, 0, s>>>(x_out, k.x.p, n);
+    NEKB_LAUNCHED();
+}
+
+// ================================================================================================ setup
+inline void mg_tensor3(double *out, const double *u, const double *wt, const double *J, int nv, int nu, bool transpose,
+                       bool accumulate, int nel)
+{
+    if (nel <= 0) return;
+    const int nm = nv > nu ? nv : nu;
+    const size_t smem = sizeof(double) * (2 * (size_t)nm * nm * nm + (size_t)nv * nu);
+    NEKB_REQUIRE(smem <= 48 * 1024, "mg_tensor3: level too large for the default shared-memory window");
+    mg_tensor3_kernel<<<nel, 256, smem, ctx().stream>>>(out, u, wt, J, nv, nu, transpose ? 1 : 0, accumulate ? 1 : 0);
+    NEKB_LAUNCHED();
+}
+
+inline std::vector<double> dev_to_host(const DevBuf<double> &b, size_t n)
+{
+    std::vector<double> h(n);
+    b.download(h.data(), n, ctx().stream);
+    return h;
+}
+
+// Face-buffer ids of level nh: the border-face (interior of the face only) ids of the (nh+2)^3 numbering that
+// h1mg_setup_dssum builds (hsmg.f:2383-2390); everything else is 0 (never exchanged: hsmg_extrude leaves the
+// edges and corners of the extended arrays at zero).
+inline std::vector<int64_t> face_ids(int nh, int64_t nel, const int64_t *vertex)
+{
+    const int ne = nh + 2;
+    const int64_t ne3 = (int64_t)ne * ne * ne;
+    std::vector<int64_t> ext((size_t)(ne3 * nel));
+    setvert3d_host(ext.data(), ne, nel, vertex, ctx().nranks);
+    std::vector<int64_t> ids((size_t)(6 * nh * nh * nel));
+    auto at = [ne](int i, int j, int k) { return (int64_t)i + ne * (j + (int64_t)ne * k); };
+    for (int64_t e = 0; e < nel; e++)
+        for (int f = 0; f < 6; f++)
+            for (int b = 0; b < nh; b++)
+                for (int a = 0; a < nh; a++) {
+                    const int side = (f & 1) ? ne - 1 : 0;
+                    int64_t q;
+                    if (f < 2) q = at(side, a + 1, b + 1);
+                    else if (f < 4) q = at(a + 1, side, b + 1);
+                    else q = at(a + 1, b + 1, side);
+                    ids[(size_t)(((e * 6 + f) * nh + b) * nh + a)] = ext[(size_t)(e * ne3 + q)];
+                }
+    return ids;
+}
+
+template <int NL>
+inline void launch_fdm_t(MgLevel &L, const double *r, double *e, int nel)
+{
+    constexpr int EPB = (NL * NL >= 100) ? 2 : (NL * NL >= 64 ? 3 : 6);
+    const int grid = (nel + EPB - 1) / EPB;
+    mg_fdm_kernel<NL, EPB><<<grid, NL * NL * EPB, 0, ctx().stream>>>(r, e, L.f_sum.p, L.f_own.p, L.f_own.p, L.f_sum.p, L.Stab.p,
+                                                                     L.lamtab.p, L.sidx.p, L.eps.p, nel);
+    NEKB_LAUNCHED();
+}
+inline void launch_fdm(MgLevel &L, const double *r, double *e, int nel)
+{
+    if (nel <= 0) return;
+    switch (L.nl) {
+        case 5: launch_fdm_t<5>(L, r, e, nel); break;
+        case 6: launch_fdm_t<6>(L, r, e, nel); break;
+        case 7: launch_fdm_t<7>(L, r, e, nel); break;
+        case 8: launch_fdm_t<8>(L, r, e, nel); break;
+        case 9: launch_fdm_t<9>(L, r, e, nel); break;
+        case 10: launch_fdm_t<10>(L, r, e, nel); break;
+        case 12: launch_fdm_t<12>(L, r, e, nel); break;
+        default: NEKB_REQUIRE(false, "h1mg: unsupported level size for the FDM kernel");
+    }
+}
+
+// h1mg_schwarz (hsmg.f:425-494) on level L: e = sigma * W * Schwarz(r); r is masked in place.
+inline void mg_schwarz(MgLevel &L, double *r, double *e, int nel)
+{
+    Ctx &c = ctx();
+    cudaStream_t s = c.stream;
+    const int grid = vec_grid(L.n);
+    mg_mask_faces_kernel<<<grid, 256, 0, s>>>(r, L.mask.p, L.f_own.p, L.f_sum.p, L.nh, L.n);
+    NEKB_LAUNCHED();
+    gs_op(L.gs_face, L.f_sum.p, 1, nullptr);
+    launch_fdm(L, r, e, nel);  // consumes (f_sum - f_own), then refills both with the border of the local solutions
+    gs_op(L.gs_face, L.f_sum.p, 1, nullptr);
+    mg_add_overlap_kernel<<<grid, 256, 0, s>>>(e, L.f_sum.p, L.f_own.p, L.nh, L.n);
+    NEKB_LAUNCHED();
+    gs_op(L.gs, e, 1, L.swt.p);  // hsmg_dssum + h1mg_mask + hsmg_schwarz_wt (+ sigma = 1)
+}
+
+inline void h1mg_setup_run(const int *fbc, const double *xm1, const double *ym1, const double *zm1, const int64_t *vertex,
+                           int nel, int null_space)
+{
+    Ctx &c = ctx();
+    cudaStream_t s = c.stream;
+    H1mg &M = h1mg();
+    M = H1mg();
+    NEKB_REQUIRE(c.have_geom, "h1mg_setup: geometry must be registered first (nekb_set_geom*)");
+    ensure_operators();
+    const int lx1 = c.nx;
+    const std::vector<int> mg_nx = mg_orders(lx1);
+    const int lmax = (int)mg_nx.size();
+    M.lmax = lmax, M.nel = nel, M.lx1 = lx1;
+    M.lev.resize(lmax);
+    std::vector<std::vector<double>> ah(lmax), bh(lmax), zh(lmax);
+    for (int l = 0; l < lmax; l++) {
+        semhat_host(mg_nx[l], ah[l], bh[l], zh[l]);
+        M.lev[l].nh = mg_nx[l] + 1;
+        M.lev[l].nl = mg_nx[l] + 3;
+        M.lev[l].n = (int64_t)M.lev[l].nh * M.lev[l].nh * M.lev[l].nh * nel;
+    }
+    // hsmg_setup_intp (hsmg.f:83-120)
+    for (int l = 0; l + 1 < lmax; l++) {
+        const int nc = M.lev[l].nh, nf = M.lev[l + 1].nh;
+        std::vector<double> J((size_t)nf * nc), cw;
+        for (int i = 0; i < nf; i++) {
+            fd_weights_full(zh[l + 1][i], zh[l].data(), nc - 1, 1, cw);
+            for (int j = 0; j < nc; j++) J[(size_t)i * nc + j] = cw[(size_t)j * 2];
+        }
+        M.lev[l].J.upload(J.data(), J.size(), s);
+    }
+    // h1mg_setup_dssum (hsmg.f:2360-2393), h1mg_setup_wtmask (:163-183), mg_set_msk (:2395-2419)
+    for (int l = 0; l < lmax; l++) {
+        MgLevel &L = M.lev[l];
+        const int nh = L.nh;
+        std::vector<int64_t> glo((size_t)L.n);
+        setvert3d_host(glo.data(), nh, nel, vertex, c.nranks);
+        L.gs = gs_setup_from_host_ids(glo.data(), L.n, nullptr, 0);
+        std::vector<double> w((size_t)L.n, 0.0), mk((size_t)L.n, 1.0);
+        for (int64_t e = 0; e < nel; e++)
+            for (int k = 0; k < nh; k++)
+                for (int j = 0; j < nh; j++)
+                    for (int i = 0; i < nh; i++) {
+                        const size_t t = (size_t)(((e * nh + k) * nh + j) * nh + i);
+                        if (i == 0 || i == nh - 1 || j == 0 || j == nh - 1 || k == 0 || k == nh - 1) w[t] = 1.0;
+                        const int *f = fbc + e * 6;
+                        if ((i == 0 && f[0] == 1) || (i == nh - 1 && f[1] == 1) || (j == 0 && f[2] == 1) ||
+                            (j == nh - 1 && f[3] == 1) || (k == 0 && f[4] == 1) || (k == nh - 1 && f[5] == 1))
+                            mk[t] = 0.0;
+                    }
+        L.rstr_wt.upload(w.data(), w.size(), s);
+        gs_op(L.gs, L.rstr_wt.p, 1, nullptr);
+        w = dev_to_host(L.rstr_wt, (size_t)L.n);
+        for (double &v : w) v = v != 0.0 ? 1.0 / v : 1.0;
+        L.rstr_wt.upload(w.data(), w.size(), s);
+        L.mask.upload(mk.data(), mk.size(), s);
+        gs_op(L.gs, L.mask.p, 2, nullptr);
+        L.r.alloc((size_t)L.n), L.e.alloc((size_t)L.n);
+        if (l >= 1) {
+            std::vector<int64_t> fid = face_ids(nh, nel, vertex);
+            L.gs_face = gs_setup_from_host_ids(fid.data(), (int64_t)fid.size(), nullptr, 0);
+            L.f_own.alloc(fid.size()), L.f_sum.alloc(fid.size());
+        }
+    }
+    // swap_lengths (core/fast3d.f:1542-1617) with plane_space (:306-423)
+    {
+        const int nx = lx1, n2 = nx - 1, nin = nx - 2;
+        const int64_t n3 = (int64_t)nx * nx * nx;
+        const std::vector<double> &wq = c.w_host;
+        M.lm_host.assign((size_t)3 * nel, 0.0), M.ll_host.assign((size_t)3 * nel, 0.0), M.lr_host.assign((size_t)3 * nel, 0.0);
+        auto at = [nx](int i, int j, int k) { return (int64_t)i + nx * (j + (int64_t)nx * k); };
+        std::vector<double> l((size_t)(n3 * nel), 0.0);
+        for (int64_t e = 0; e < nel; e++) {
+            const double *x = xm1 + e * n3, *y = ym1 + e * n3, *z = zm1 + e * n3;
+            for (int d = 0; d < 3; d++) {
+                double sum = 0.0, wsum = 0.0;
+                for (int k = 1; k <= nin; k++)
+                    for (int j = 1; j <= nin; j++) {
+                        const double wt = wq[j - 1] * wq[k - 1];  // the reference indexes wxm1 from its first entry here
+                        int64_t a, b;
+                        if (d == 0) a = at(n2, j, k), b = at(0, j, k);
+                        else if (d == 1) a = at(j, n2, k), b = at(j, 0, k);
+                        else a = at(j, k, n2), b = at(j, k, 0);
+                        const double dx = x[a] - x[b], dy = y[a] - y[b], dz = z[a] - z[b];
+                        sum = sum + wt / (dx * dx + dy * dy + dz * dz);
+                        wsum = wsum + wt;
+                    }
+                M.lm_host[(size_t)d * nel + e] = 1.0 / sqrt(sum / wsum);
+            }
+            for (int j = 1; j < n2; j++)
+                for (int k = 1; k < n2; k++) {
+                    l[(size_t)(e * n3 + at(0, k, j))] = M.lm_host[0 * nel + e];
+                    l[(size_t)(e * n3 + at(n2, k, j))] = M.lm_host[0 * nel + e];
+                    l[(size_t)(e * n3 + at(k, 0, j))] = M.lm_host[1 * (size_t)nel + e];
+                    l[(size_t)(e * n3 + at(k, n2, j))] = M.lm_host[1 * (size_t)nel + e];
+                    l[(size_t)(e * n3 + at(k, j, 0))] = M.lm_host[2 * (size_t)nel + e];
+                    l[(size_t)(e * n3 + at(k, j, n2))] = M.lm_host[2 * (size_t)nel + e];
+                }
+        }
+        DevBuf<double> ld;
+        ld.upload(l.data(), l.size(), s);
+        gs_op(M.lev[lmax - 1].gs, ld.p, 1, nullptr);
+        ld.download(l.data(), l.size(), s);
+        for (int64_t e = 0; e < nel; e++) {
+            const double *le = l.data() + e * n3;
+            M.ll_host[0 * (size_t)nel + e] = le[at(0, 1, 1)] - M.lm_host[0 * (size_t)nel + e];
+            M.lr_host[0 * (size_t)nel + e] = le[at(n2, 1, 1)] - M.lm_host[0 * (size_t)nel + e];
+            M.ll_host[1 * (size_t)nel + e] = le[at(1, 0, 1)] - M.lm_host[1 * (size_t)nel + e];
+            M.lr_host[1 * (size_t)nel + e] = le[at(1, n2, 1)] - M.lm_host[1 * (size_t)nel + e];
+            M.ll_host[2 * (size_t)nel + e] = le[at(1, 1, 0)] - M.lm_host[2 * (size_t)nel + e];
+            M.lr_host[2 * (size_t)nel + e] = le[at(1, 1, n2)] - M.lm_host[2 * (size_t)nel + e];
+        }
+    }
+    // h1mg_setup_fdm -> hsmg_setup_fast (hsmg.f:632-773): de-duplicated 1-D eigen-systems
+    for (int l = 1; l < lmax; l++) {
+        MgLevel &L = M.lev[l];
+        const int nl = L.nl, n = mg_nx[l];
+        typedef std::tuple<int, int, double, double, double> Key;
+        std::map<Key, int> table;
+        std::vector<double> Stab, lamtab, eps((size_t)nel);
+        std::vector<int32_t> sidx((size_t)3 * nel);
+        std::vector<double> S, lam;
+        for (int64_t e = 0; e < nel; e++) {
+            double emax = 0.0;
+            for (int d = 0; d < 3; d++) {
+                const int lbc = fbc[e * 6 + 2 * d], rbc = fbc[e * 6 + 2 * d + 1];
+                // lengths that the 1-D system does not read (boundary sides) must not split table entries
+                const double ll = lbc == 0 ? M.ll_host[(size_t)d * nel + e] : 0.0, lr = rbc == 0 ? M.lr_host[(size_t)d * nel + e] : 0.0;
+                Key key(lbc, rbc, ll, M.lm_host[(size_t)d * nel + e], lr);
+                auto it = table.find(key);
+                int row;
+                if (it == table.end()) {
+                    fast1d_host(lbc, rbc, ll, M.lm_host[(size_t)d * nel + e], lr, ah[l], bh[l], n, S, lam);
+                    row = (int)table.size();
+                    table[key] = row;
+                    Stab.insert(Stab.end(), S.begin(), S.end());
+                    lamtab.insert(lamtab.end(), lam.begin(), lam.end());
+                } else
+                    row = it->second;
+                sidx[(size_t)e * 3 + d] = row;
+                double mx = lamtab[(size_t)row * nl + 1];
+                for (int q = 1; q < nl - 1; q++) mx = std::max(mx, lamtab[(size_t)row * nl + q]);
+                emax += mx;
+            }
+            eps[(size_t)e] = 1.0e-5 * emax;
+        }
+        L.ntab = (int)table.size();
+        L.Stab.upload(Stab.data(), Stab.size(), s);
+        L.lamtab.upload(lamtab.data(), lamtab.size(), s);
+        L.sidx.upload(sidx.data(), sidx.size(), s);
+        L.eps.upload(eps.data(), eps.size(), s);
+    }
+    // h1mg_setup_schwarz_wt_1 (hsmg.f:3044-3100): run the overlap-sum pipeline on ones
+    for (int l = 1; l < lmax; l++) {
+        MgLevel &L = M.lev[l];
+        const int nh = L.nh;
+        const size_t nf = (size_t)6 * nh * nh * nel;
+        std::vector<double> ones(nf, 1.0), cnt((size_t)L.n, 1.0);
+        L.f_own.upload(ones.data(), nf, s);
+        L.f_sum.upload(ones.data(), nf, s);
+        L.e.upload(cnt.data(), cnt.size(), s);
+        gs_op(L.gs_face, L.f_sum.p, 1, nullptr);
+        mg_add_overlap_kernel<<<vec_grid(L.n), 256, 0, s>>>(L.e.p, L.f_sum.p, L.f_own.p, nh, L.n);
+        NEKB_LAUNCHED();
+        gs_op(L.gs, L.e.p, 1, nullptr);
+        cnt = dev_to_host(L.e, (size_t)L.n);
+        std::vector<double> mk = dev_to_host(L.mask, (size_t)L.n);
+        for (size_t t = 0; t < cnt.size(); t++) cnt[t] = mk[t] * (1.0 / cnt[t]);
+        L.swt.upload(cnt.data(), cnt.size(), s);
+    }
+    // coarse grid: set_up_h1_crs (navier8.f:83-233) with get_local_crs_galerkin (:1648-1690)
+    {
+        CrsSolver &k = M.crs;
+        MgLevel &L0 = M.lev[0];
+        NEKB_REQUIRE(L0.nh == 2, "h1mg: the coarse level must be the vertex mesh");
+        k.n = L0.n;
+        k.gs = L0.gs;
+        k.null_space = null_space;
+        const size_t n = (size_t)k.n;
+        k.a.alloc((size_t)64 * nel);
+        const int nxyz = c.nxyz, nx = c.nx;
+        std::vector<double> basis((size_t)8 * nxyz);
+        for (int j = 1; j <= 8; j++)
+            for (int kk = 0; kk < nx; kk++)
+                for (int jj = 0; jj < nx; jj++)
+                    for (int ii = 0; ii < nx; ii++) {
+                        const double z0r = 0.5 * (1 - c.z_host[ii]), z1r = 0.5 * (1 + c.z_host[ii]);
+                        const double z0s = 0.5 * (1 - c.z_host[jj]), z1s = 0.5 * (1 + c.z_host[jj]);
+                        const double z0t = 0.5 * (1 - c.z_host[kk]), z1t = 0.5 * (1 + c.z_host[kk]);
+                        const double zr = (j % 2 == 0) ? z1r : z0r;
+                        const double zs = (j == 3 || j == 4 || j == 7 || j == 8) ? z1s : z0s;
+                        const double zt = (j > 4) ? z1t : z0t;
+                        basis[(size_t)(j - 1) * nxyz + (size_t)(kk * nx + jj) * nx + ii] = zr * zs * zt;
+                    }
+        DevBuf<double> bd, w1, w2;
+        bd.upload(basis.data(), basis.size(), s);
+        const int64_t nfine = (int64_t)nxyz * nel;
+        w1.alloc((size_t)nfine), w2.alloc((size_t)nfine);
+        for (int j = 0; j < 8 && nel > 0; j++) {
+            crs_tile_basis_kernel<<<vec_grid(nfine), 256, 0, s>>>(w1.p, bd.p + (size_t)j * nxyz, nxyz, nfine);
+            NEKB_LAUNCHED();
+            launch_ax(w1.p, w2.p, nullptr, nullptr, nel, nullptr);  // h1 = 1, h2 = 0 (navier8.f:201-203)
+            crs_galerkin_kernel<<<nel, 256, 0, s>>>(k.a.p, w2.p, bd.p, nxyz, j);
+            NEKB_LAUNCHED();
+        }
+        k.mask.alloc(n), k.mult.alloc(n), k.dinv.alloc(n);
+        k.b.alloc(n), k.x.alloc(n), k.r.alloc(n), k.p.alloc(n), k.w.alloc(n);
+        if (n) {
+            NEKB_CUDA(cudaMemcpyAsync(k.mask.p, L0.mask.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+            NEKB_CUDA(cudaMemcpyAsync(k.mult.p, L0.rstr_wt.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+            crs_diag_kernel<<<vec_grid(k.n), 256, 0, s>>>(k.dinv.p, k.a.p, k.n);
+            NEKB_LAUNCHED();
+        }
+        gs_op(k.gs, k.dinv.p, 1, nullptr);
+        if (n) {
+            crs_invdiag_kernel<<<vec_grid(k.n), 256, 0, s>>>(k.dinv.p, k.mask.p, k.n);
+            NEKB_LAUNCHED();
+        }
+        // number of distinct unmasked dofs = sum mask*mult
+        DevBuf<CrsScalars> &scb = crs_scalars();
+        if (!scb.p) {
+            scb.alloc(1);
+            scb.zero(s);
+        }
+        c.partials.ensure(4 * CG_PART_STRIDE);
+        crs_dot_kernel<<<vec_grid(k.n), 256, 0, s>>>(k.mask.p, k.mask.p, k.mult.p, k.n, &scb.p->shift, c.partials.p,
+                                                     &scb.p->counter[3]);
+        NEKB_LAUNCHED();
+        comm_allreduce_sum(&scb.p->shift, 1);
+        NEKB_CUDA(cudaMemcpyAsync(&k.ndof, &scb.p->shift, sizeof(double), cudaMemcpyDeviceToHost, s));
+        NEKB_CUDA(cudaStreamSynchronize(s));
+    }
+    NEKB_CUDA(cudaStreamSynchronize(s));
+    M.ready = true;
+}
+
+// ================================================================================================ h1mg_solve
+// z = M^-1 rhs ; rhs is masked in place (h1mg_schwarz_part1 does that to its input, hsmg.f:449).
+inline void h1mg_solve_dev(double *z, double *rhs)
+{
+    Ctx &c = ctx();
+    H1mg &M = h1mg();
+    NEKB_REQUIRE(M.ready, "h1mg_solve: nekb_h1mg_setup has not been called");
+    cudaStream_t s = c.stream;
+    const int nel = M.nel, top = M.lmax - 1;
+    mg_schwarz(M.lev[top], rhs, z, nel);                                   // :1890
+    const double *rf = rhs;                                                // :1892 r := rhs
+    for (int l = top - 1; l >= 1; l--) {                                   // :1896-1909
+        MgLevel &L = M.lev[l], &Lf = M.lev[l + 1];
+        mg_tensor3(L.r.p, rf, Lf.rstr_wt.p, L.J.p, L.nh, Lf.nh, true, false, nel);  // h1mg_rstr
+        gs_op(L.gs, L.r.p, 1, nullptr);
+        mg_schwarz(L, L.r.p, L.e.p, nel);
+        rf = L.r.p;
+    }
+    {                                                                       // :1910-1917
+        MgLevel &L = M.lev[0], &Lf = M.lev[1];
+        mg_tensor3(L.r.p, rf, Lf.rstr_wt.p, L.J.p, L.nh, Lf.nh, true, false, nel);
+        if (L.n) {
+            col2_kernel<<<vec_grid(L.n), 256, 0, s>>>(L.r.p, L.mask.p, L.n);
+            NEKB_LAUNCHED();
+        }
+        crs_solve_dev(L.e.p, L.r.p);
+        if (L.n) {
+            col2_kernel<<<vec_grid(L.n), 256, 0, s>>>(L.e.p, L.mask.p, L.n);
+            NEKB_LAUNCHED();
+        }
+    }
+    for (int l = 1; l < top; l++)                                           // :1926-1934 e_l += J e_(l-1)
+        mg_tensor3(M.lev[l].e.p, M.lev[l - 1].e.p, nullptr, M.lev[l - 1].J.p, M.lev[l].nh, M.lev[l - 1].nh, false, true, nel);
+    mg_tensor3(z, M.lev[top - 1].e.p, nullptr, M.lev[top - 1].J.p, M.lev[top].nh, M.lev[top - 1].nh, false, true, nel);  // :1936-1942
+    gs_op(M.lev[top].gs, z, 1, M.lev[top].rstr_wt.p);                       // :1944 dsavg (core/ic.f:1871)
+}
+
+}  // namespace nekb

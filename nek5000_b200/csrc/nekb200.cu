@@ -2,7 +2,7 @@
 // headers included below.  Build: nvcc -gencode arch=compute_100a,code=sm_100a (nek5000_b200/build.py).
 #include "../../include/nekb200.h"
 
-#include "setup.cuh"
+#include "gmres.cuh"
 
 using namespace nekb;
 
@@ -167,6 +167,9 @@ void nekb_finalize(void)
     if (!c.inited) return;
     cudaStreamSynchronize(c.stream);
     bp5case() = Bp5Case();
+    h1mg() = H1mg();
+    gmres_state() = GmresState();
+    crs_scalars().release();
     c.gs.clear();
     if (c.nccl_comm) nccl().CommDestroy(comm_handle());
     void (*eh)(void) = c.exit_handler;
@@ -749,6 +752,177 @@ double glsc3_(const double *a, const double *b, const double *mult, const int *n
         NEKB_CUDA(cudaStreamSynchronize(c.stream));
     });
     return out;
+}
+
+// ---------------------------------------------------------------------------------------------------- h1mg / gmres
+int nekb_h1mg_setup(const int *fbc, const double *xm1, const double *ym1, const double *zm1, const int64_t *vertex, int nelv,
+                    int null_space)
+{
+    return guard([&] {
+        require_init();
+        NEKB_REQUIRE(nelv >= 0 && nelv <= ctx().nelt, "h1mg_setup: nelv exceeds the registered element count");
+        h1mg_setup_run(fbc, xm1, ym1, zm1, vertex, nelv, null_space);
+    });
+}
+int nekb_h1mg_solve_dev(double *z_dev, double *rhs_dev)
+{
+    return guard([&] {
+        require_init();
+        h1mg_solve_dev(z_dev, rhs_dev);
+    });
+}
+void h1mg_solve_(double *z, double *rhs, const int *if_hybrid)
+{
+    guard_fortran("h1mg_solve", [&] {
+        require_init();
+        Ctx &c = ctx();
+        NEKB_REQUIRE(!(if_hybrid && *if_hybrid), "h1mg_solve: the hybrid (multiplicative) variant is not provided");
+        NEKB_REQUIRE(h1mg().ready, "h1mg_solve: nekb_h1mg_setup has not been called");
+        const size_t n = (size_t)h1mg().nel * c.nxyz;
+        c.stage[0].ensure(n), c.stage[1].ensure(n);
+        NEKB_CUDA(cudaMemcpyAsync(c.stage[1].p, rhs, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        h1mg_solve_dev(c.stage[0].p, c.stage[1].p);
+        NEKB_CUDA(cudaMemcpyAsync(z, c.stage[0].p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaMemcpyAsync(rhs, c.stage[1].p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));  // masked in place
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+int nekb_h1mg_schwarz_dev(int level, double *e_dev, double *r_dev)
+{
+    return guard([&] {
+        require_init();
+        H1mg &M = h1mg();
+        NEKB_REQUIRE(M.ready, "nekb_h1mg_setup has not been called");
+        NEKB_REQUIRE(level >= 2 && level <= M.lmax, "h1mg_schwarz: level out of range (2..lmax)");
+        mg_schwarz(M.lev[level - 1], r_dev, e_dev, M.nel);
+    });
+}
+int nekb_crs_solve_dev(double *e_dev, const double *r_dev)
+{
+    return guard([&] {
+        require_init();
+        NEKB_REQUIRE(h1mg().ready, "nekb_h1mg_setup has not been called");
+        crs_solve_dev(e_dev, r_dev);
+    });
+}
+int nekb_h1mg_info(int *lmax, int *nh3, int *ntab3, int *crs_iters)
+{
+    return guard([&] {
+        H1mg &M = h1mg();
+        NEKB_REQUIRE(M.ready, "nekb_h1mg_setup has not been called");
+        if (lmax) *lmax = M.lmax;
+        for (int l = 0; l < M.lmax; l++) {
+            if (nh3) nh3[l] = M.lev[l].nh;
+            if (ntab3) ntab3[l] = M.lev[l].ntab;
+        }
+        if (crs_iters) *crs_iters = M.crs.last_iters;
+    });
+}
+int nekb_h1mg_get(const char *which, int level, double *host_out, size_t n_doubles)
+{
+    return guard([&] {
+        H1mg &M = h1mg();
+        Ctx &c = ctx();
+        NEKB_REQUIRE(M.ready, "nekb_h1mg_setup has not been called");
+        const std::string w(which);
+        auto copy_host = [&](const std::vector<double> &v) {
+            NEKB_REQUIRE(n_doubles >= v.size(), "nekb_h1mg_get: buffer too small");
+            memcpy(host_out, v.data(), v.size() * sizeof(double));
+        };
+        if (w == "lm") return copy_host(M.lm_host);
+        if (w == "ll") return copy_host(M.ll_host);
+        if (w == "lr") return copy_host(M.lr_host);
+        if (w == "crs_a") {
+            NEKB_REQUIRE(n_doubles >= M.crs.a.n, "nekb_h1mg_get: buffer too small");
+            M.crs.a.download(host_out, M.crs.a.n, c.stream);
+            return;
+        }
+        NEKB_REQUIRE(level >= 1 && level <= M.lmax, "nekb_h1mg_get: level out of range");
+        MgLevel &L = M.lev[level - 1];
+        const DevBuf<double> *b = nullptr;
+        if (w == "mask") b = &L.mask;
+        else if (w == "rstr_wt") b = &L.rstr_wt;
+        else if (w == "swt") b = &L.swt;
+        else if (w == "J") b = &L.J;
+        NEKB_REQUIRE(b != nullptr, std::string("nekb_h1mg_get: unknown array '") + which + "'");
+        NEKB_REQUIRE(n_doubles >= b->n, "nekb_h1mg_get: buffer too small");
+        b->download(host_out, b->n, c.stream);
+    });
+}
+int nekb_crs_set_tolerance(double tol, int maxit)
+{
+    return guard([&] {
+        NEKB_REQUIRE(tol > 0.0 && maxit > 0, "nekb_crs_set_tolerance: bad arguments");
+        h1mg().crs.tol = tol;
+        h1mg().crs.maxit = maxit;
+    });
+}
+void nekb_h1mg_free(void)
+{
+    H1mg &M = h1mg();
+    for (MgLevel &L : M.lev) {
+        if (L.gs >= 0 && L.gs < (int)ctx().gs.size()) ctx().gs[L.gs] = GsMap();
+        if (L.gs_face >= 0 && L.gs_face < (int)ctx().gs.size()) ctx().gs[L.gs_face] = GsMap();
+    }
+    M = H1mg();
+    gmres_state() = GmresState();
+}
+
+int nekb_set_pressure_state(const double *pmask, const double *binvm1, double tolps, double param21, int ifvcor, int64_t nelgv)
+{
+    return guard([&] {
+        require_init();
+        Ctx &c = ctx();
+        GmresState &G = gmres_state();
+        const size_t n = (size_t)c.nelv * c.nxyz;
+        if (pmask) G.pmask.upload(pmask, n, c.stream);
+        if (binvm1) G.binvm1.upload(binvm1, n, c.stream);
+        G.tolps = tolps, G.param21 = param21, G.ifvcor = ifvcor;
+        G.ntotg = (double)nelgv * (double)c.nxyz;
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+int nekb_hmh_gmres_dev(double *res_dev, const double *h1_dev, const double *h2_dev, const double *wt_dev, const double *pmask_dev,
+                       double tol, int maxit, int *iter, double *hist_host, double *div0)
+{
+    return guard([&] {
+        require_init();
+        Ctx &c = ctx();
+        NEKB_REQUIRE(h1mg().ready, "hmh_gmres: nekb_h1mg_setup has not been called");
+        NEKB_REQUIRE(c.volvm1 > 0.0, "volvm1 not registered (nekb_set_step_info)");
+        const int it = hmh_gmres_run(res_dev, h1_dev, h2_dev, wt_dev, pmask_dev, h1mg().nel, h1mg().lev[h1mg().lmax - 1].gs,
+                                     c.volvm1, tol, maxit, hist_host, div0);
+        if (iter) *iter = it;
+    });
+}
+void hmh_gmres_(double *res, const double *h1, const double *h2, const double *wt, int *iter)
+{
+    guard_fortran("hmh_gmres", [&] {
+        require_init();
+        Ctx &c = ctx();
+        GmresState &G = gmres_state();
+        H1mg &M = h1mg();
+        NEKB_REQUIRE(M.ready, "hmh_gmres: nekb_h1mg_setup has not been called");
+        NEKB_REQUIRE(c.volvm1 > 0.0, "volvm1 not registered (nekb_set_step_info)");
+        const size_t n = (size_t)M.nel * c.nxyz;
+        NEKB_REQUIRE(G.pmask.n >= n && G.binvm1.n >= n, "hmh_gmres: pmask/binvm1 not registered (nekb_set_pressure_state)");
+        for (int k = 0; k < 4; k++) c.stage[k].ensure(n);
+        const double *src[4] = {res, h1, h2, wt};
+        for (int k = 0; k < 4; k++)
+            NEKB_CUDA(cudaMemcpyAsync(c.stage[k].p, src[k], n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        bool ifh2 = false;
+        for (size_t t = 0; t < n && !ifh2; t++) ifh2 = h2[t] != 0.0;
+        const double *h2d = ifh2 ? c.stage[2].p : nullptr;
+        // gmres.f:338-342: tolerance guard and the param(21) / istep overrides
+        double tolps = chktcg1_dev(G.tolps, c.stage[0].p, c.stage[1].p, h2d, G.pmask.p, c.stage[3].p, G.binvm1.p, M.nel, c.volvm1);
+        if (G.param21 > 0 && tolps > fabs(G.param21)) tolps = fabs(G.param21);
+        if (c.istep == 0) tolps = 1.e-4;
+        const double tol = G.param21 < 0 ? -fabs(G.param21) : tolps;
+        *iter = hmh_gmres_run(c.stage[0].p, c.stage[1].p, h2d, c.stage[3].p, G.pmask.p, M.nel, M.lev[M.lmax - 1].gs, c.volvm1, tol,
+                              *iter, nullptr, nullptr);
+        NEKB_CUDA(cudaMemcpyAsync(res, c.stage[0].p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    });
 }
 
 // ---------------------------------------------------------------------------------------------------- host-side setup

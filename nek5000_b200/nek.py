@@ -13,6 +13,8 @@ reads like a call site in the reference:
     cggos(u1,rhs1,x1,rmult,binv,tin,maxit,bpname)           examples/bp5/bp5.usr:797
     axhm1(pap,ap1,p1,h1,h2,bpname)                          examples/bp5/bp5.usr:1389
     glsc3(a,b,mult,n)                                       core/math.f:775
+    h1mg_setup() / h1mg_solve(z,rhs,if_hybrid)              core/hsmg.f:2234,1855
+    hmh_gmres(res,h1,h2,wt,iter)                            core/gmres.f:304
 
 State that the Fortran routines read from COMMON blocks is registered with the set_* functions
 (include/nekb200.h section B).  All compute runs in hand-written CUDA kernels; a missing library or GPU is
@@ -31,7 +33,8 @@ __all__ = [
     "set_geom_from_xyz", "get_geom", "set_ifdfrm", "set_v1mask", "set_ifield", "set_field_handle", "set_step_info",
     "niterhm", "setvert3d", "setupds", "fgslib_gs_setup", "fgslib_gs_op", "fgslib_gs_op_many", "fgslib_gs_op_fields",
     "fgslib_gs_free", "gs_get_map", "gs_info", "dssum", "dsop", "axhelm", "setprec", "cggo", "cggos", "axhm1", "glsc3",
-    "DevArray", "set_transport_torch", "comm_init_torch",
+    "DevArray", "set_transport_torch", "comm_init_torch", "h1mg_setup", "h1mg_solve", "h1mg_info", "h1mg_get", "h1mg_free",
+    "set_pressure_state", "hmh_gmres",
 ]
 
 _state = {"lx1": 0, "nelt": 0, "np": 1, "keep": []}
@@ -253,6 +256,50 @@ def axhm1(ap1, p1, h1, h2, bpname: str = "bp5") -> float:
 
 def glsc3(a, b, mult) -> float:
     return float(lib().glsc3_(_ptr(a), _ptr(b), _ptr(mult), _i(len(a))))
+
+
+# --------------------------------------------------------------------------------------------- pressure preconditioner
+def h1mg_setup(fbc, xm1, ym1, zm1, vertex, nelv: int, null_space: bool = False) -> None:
+    """core/hsmg.f:2234 h1mg_setup (+ swap_lengths, set_up_h1_crs) from the state the reference reads from COMMON:
+    fbc[nelv,6] = get_fast_bc codes, /gxyz/ coordinates, /ivrtx/ vertex."""
+    f = np.ascontiguousarray(fbc, dtype=np.int32).reshape(-1)
+    v = np.ascontiguousarray(vertex, dtype=np.int64).reshape(-1)
+    check(lib().nekb_h1mg_setup(f, *[np.ascontiguousarray(a, dtype=np.float64) for a in (xm1, ym1, zm1)], v, nelv, int(null_space)))
+
+
+def h1mg_solve(z: np.ndarray, rhs: np.ndarray, if_hybrid: bool = False) -> None:
+    """core/hsmg.f:1855 h1mg_solve(z,rhs,if_hybrid); rhs is masked in place as in the reference."""
+    lib().h1mg_solve_(_ptr(z), _ptr(rhs), _i(1 if if_hybrid else 0))
+
+
+def h1mg_info():
+    lmax, crs = C.c_int(0), C.c_int(0)
+    nh, nt = (C.c_int * 3)(), (C.c_int * 3)()
+    check(lib().nekb_h1mg_info(C.byref(lmax), nh, nt, C.byref(crs)))
+    return {"lmax": lmax.value, "nh": list(nh)[:lmax.value], "ntab": list(nt)[:lmax.value], "crs_iters": crs.value}
+
+
+def h1mg_get(which: str, level: int, n: int) -> np.ndarray:
+    out = np.zeros(n)
+    check(lib().nekb_h1mg_get(which.encode(), level, _ptr(out), n))
+    return out
+
+
+def h1mg_free() -> None:
+    lib().nekb_h1mg_free()
+
+
+def set_pressure_state(pmask, binvm1, tolps: float, param21: float = 0.0, ifvcor: bool = False, nelgv: int = 0) -> None:
+    pm = np.ascontiguousarray(pmask, dtype=np.float64)
+    bi = np.ascontiguousarray(binvm1, dtype=np.float64)
+    check(lib().nekb_set_pressure_state(_ptr(pm), _ptr(bi), tolps, param21, int(ifvcor), nelgv))
+
+
+def hmh_gmres(res: np.ndarray, h1: np.ndarray, h2: np.ndarray, wt: np.ndarray, maxit: int) -> int:
+    """core/gmres.f:304 hmh_gmres(res,h1,h2,wt,iter): res is overwritten with the solution; returns iter."""
+    it = C.c_int(maxit)
+    lib().hmh_gmres_(_ptr(res), _ptr(h1), _ptr(h2), _ptr(wt), C.byref(it))
+    return int(it.value)
 
 
 # --------------------------------------------------------------------------------------------- device arrays

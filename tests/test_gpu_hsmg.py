@@ -1,0 +1,183 @@
+"""GPU parity tests of the pressure preconditioner (h1mg_setup / h1mg_solve, core/hsmg.f) and of hmh_gmres
+(core/gmres.f:304-545) against the numpy oracle (oracle/hsmg.py) on identical seeded inputs, through the C-ABI.
+
+Tolerances: setup products that are small integers or their reciprocals are compared exactly; everything that passes
+through the 1-D generalised eigenproblems (LAPACK dsygv in the oracle, Cholesky + Jacobi in the library) or through
+the coarse solve (dense LU in the oracle, PCG to 1e-13 on the device) is held to 1e-10 relative, the north-star
+tolerance for fields; GMRES iteration counts must be identical.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import hsmg
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+def relmax(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def make(nek, dims, lx1, per, pdir, bc, deform, null_space=False):
+    nek.finalize()
+    nek.init(0, lx1, 3)
+    case = oracle.Case(*dims, nx=lx1, periodic=per, dirichlet=pdir, deform=deform)
+    fbc = hsmg.box_fbc(case, bc)
+    mg = hsmg.H1MG(case, fbc, null_space=null_space)
+    nek.set_nel(case.nel, case.nel)
+    nek.set_gll(case.z, case.w)
+    nek.set_dxyz(case.D, case.Dt)
+    nek.set_geom(*case.geom()[:7])
+    nek.set_ifdfrm(None)
+    nek.h1mg_setup(fbc, case.xm1, case.ym1, case.zm1, case.vertex, case.nel, null_space)
+    return case, mg
+
+
+@pytest.fixture(scope="module")
+def nek():
+    from nek5000_b200 import nek as N
+    yield N
+    N.finalize()
+
+
+CASES = {
+    # name: dims, lx1, periodic, pressure-Dirichlet sides (mask), get_fast_bc codes on the box sides, deformation
+    "outflow_x_deformed": ((3, 3, 2), 8, (0, 0, 0), (0, 1, 0, 0, 0, 0), (2, 1, 2, 2, 2, 2), 0.03),
+    "channel_like_periodic": ((4, 2, 3), 8, (1, 0, 1), (0, 0, 0, 1, 0, 0), (0, 0, 2, 1, 0, 0), 0.0),
+    "lx1_6": ((2, 3, 2), 6, (0, 0, 0), (1, 0, 0, 0, 0, 0), (1, 2, 2, 2, 2, 2), 0.02),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_h1mg_setup_and_levels(nek, name):
+    dims, lx1, per, pdir, bc, deform = CASES[name]
+    case, mg = make(nek, dims, lx1, per, pdir, bc, deform)
+    info = nek.h1mg_info()
+    assert info["lmax"] == mg.lmax and info["nh"] == mg.nh
+    E = case.nel
+    for q, ref in (("lm", mg.lm), ("ll", mg.ll), ("lr", mg.lr)):
+        got = nek.h1mg_get(q, 0, 3 * E).reshape(3, E)
+        assert relmax(got, ref) <= 1e-13, q
+    for l in range(mg.lmax):
+        n = mg.nh[l] ** 3 * E
+        assert np.array_equal(nek.h1mg_get("mask", l + 1, n), mg.mask[l])
+        assert np.array_equal(nek.h1mg_get("rstr_wt", l + 1, n), mg.rstr_wt[l])
+        if l >= 1:
+            assert relmax(nek.h1mg_get("swt", l + 1, n), mg.swt[l] * mg.mask[l]) <= 1e-15
+        if l + 1 < mg.lmax:
+            J = nek.h1mg_get("J", l + 1, mg.nh[l + 1] * mg.nh[l]).reshape(mg.nh[l + 1], mg.nh[l])
+            assert relmax(J, mg.jh[l]) <= 1e-14
+    a = nek.h1mg_get("crs_a", 0, 64 * E).reshape(E, 8, 8)
+    assert relmax(a, mg.crs_a) <= 1e-12
+    # on a box mesh the 1-D eigen-systems de-duplicate to a handful of table rows
+    assert all(t <= 3 * E for t in info["ntab"][1:])
+    if deform == 0.0:
+        assert max(info["ntab"][1:]) <= 9
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_schwarz_crs_and_vcycle(nek, name):
+    from nek5000_b200._lib import check, lib
+    dims, lx1, per, pdir, bc, deform = CASES[name]
+    case, mg = make(nek, dims, lx1, per, pdir, bc, deform)
+    rng = np.random.default_rng(11)
+    L = lib()
+    for l in range(1, mg.lmax):  # h1mg_schwarz per level
+        n = mg.nh[l] ** 3 * case.nel
+        r = rng.standard_normal(n)
+        ref_r = r.copy()
+        ref = mg.schwarz(ref_r, 1.0, l)
+        rd, ed = nek.DevArray.from_host(r), nek.DevArray(n)
+        check(L.nekb_h1mg_schwarz_dev(l + 1, ed.ptr, rd.ptr))
+        assert np.array_equal(rd.to_host(), ref_r)          # masked in place
+        assert relmax(ed.to_host(), ref) <= TOL, f"schwarz level {l + 1}"
+    # coarse solve
+    n0 = 8 * case.nel
+    b = rng.standard_normal(n0) * mg.mask[0]
+    ref = mg.crs_solve(b)
+    bd, xd = nek.DevArray.from_host(b), nek.DevArray(n0)
+    check(L.nekb_crs_solve_dev(xd.ptr, bd.ptr))
+    assert relmax(xd.to_host(), ref) <= TOL
+    assert 0 < nek.h1mg_info()["crs_iters"] <= mg.crs_n + 2
+    # whole V-cycle through the Fortran-named entry point
+    rhs = case.dssum(rng.standard_normal(case.n)) * case.mult
+    ref_rhs = rhs.copy()
+    zref = mg.solve(ref_rhs)
+    z = np.zeros(case.n)
+    nek.h1mg_solve(z, rhs, False)
+    assert np.array_equal(rhs, ref_rhs)
+    assert relmax(z, zref) <= TOL
+    # linear operator
+    r2 = case.dssum(rng.standard_normal(case.n)) * case.mult
+    z2, z3 = np.zeros(case.n), np.zeros(case.n)
+    nek.h1mg_solve(z2, r2.copy(), False)
+    nek.h1mg_solve(z3, (2.0 * ref_rhs - 3.0 * r2 * mg.mask[-1]).copy(), False)
+    assert relmax(z3, 2.0 * z - 3.0 * z2) <= 1e-11
+
+
+@pytest.mark.parametrize("name", ["outflow_x_deformed", "channel_like_periodic"])
+def test_hmh_gmres_iteration_counts_and_history(nek, name):
+    from nek5000_b200._lib import check, lib
+    import ctypes as C
+    dims, lx1, per, pdir, bc, deform = CASES[name]
+    case, mg = make(nek, dims, lx1, per, pdir, bc, deform)
+    rng = np.random.default_rng(5)
+    n = case.n
+    pmask = case.mask
+    h1, h2 = np.ones(n), np.zeros(n)
+    xe = case.dssum(rng.standard_normal(n)) * case.mult * pmask
+    b = case.dssum(case.axhelm(xe, h1, h2)) * pmask
+    vol = case.bm1().sum()
+    nek.set_step_info(1, vol)
+    tol, maxit = 1e-9, 60
+    xref, itref, hist_ref, div0_ref = hsmg.hmh_gmres(case, mg, b, h1, h2, pmask, case.mult, tol, maxit, history=True)
+    L = lib()
+    bd, h1d, wtd, pmd = (nek.DevArray.from_host(a) for a in (b, h1, case.mult, pmask))
+    it, div0 = C.c_int(0), C.c_double(0)
+    hist = np.zeros(maxit + 1)
+    check(L.nekb_hmh_gmres_dev(bd.ptr, h1d.ptr, None, wtd.ptr, pmd.ptr, tol, maxit, C.byref(it), hist.ctypes.data, C.byref(div0)))
+    x = bd.to_host()
+    assert it.value == itref and itref < maxit
+    assert abs(div0.value - div0_ref) <= 1e-12 * div0_ref
+    # residual history: relative to the initial residual (late entries sit 9 orders below it)
+    assert np.abs(hist[:itref] - hist_ref).max() <= 1e-10 * div0_ref
+    assert relmax(x, xref) <= TOL
+    assert relmax(x, xe) <= 1e-7
+    # Fortran-named entry point with the registered COMMON state (tolps, param(21) < 0 => relative tolerance)
+    nek.set_pressure_state(pmask, case.binv(), 1e-20, -1e-6, False, case.nel)
+    res = b.copy()
+    it2 = nek.hmh_gmres(res, h1, h2, case.mult, maxit)
+    _, it2ref, h2ref, _ = hsmg.hmh_gmres(case, mg, b, h1, h2, pmask, case.mult, 1e-6 * div0_ref, maxit, history=True)
+    assert it2 == it2ref
+
+
+def test_h1mg_all_neumann_null_space(nek):
+    from nek5000_b200._lib import check, lib
+    import ctypes as C
+    case, mg = make(nek, (3, 2, 2), 8, (0, 0, 0), (0, 0, 0, 0, 0, 0), (2, 2, 2, 2, 2, 2), 0.0, null_space=True)
+    rng = np.random.default_rng(3)
+    n = case.n
+    h1, h2 = np.ones(n), np.zeros(n)
+    xe = case.dssum(rng.standard_normal(n)) * case.mult
+    b = case.dssum(case.axhelm(xe, h1, h2))           # consistent right-hand side (range of the singular operator)
+    # coarse solve with the null space: consistent coarse rhs
+    L = lib()
+    bc = mg.rstr(mg.rstr(b.copy(), 1, True), 0, False)
+    ref = mg.crs_solve(bc)
+    bd, xd = nek.DevArray.from_host(bc), nek.DevArray(len(bc))
+    check(L.nekb_crs_solve_dev(xd.ptr, bd.ptr))
+    assert relmax(xd.to_host(), ref) <= 1e-9
+    vol = case.bm1().sum()
+    nek.set_step_info(1, vol)
+    nek.set_pressure_state(case.mask, case.binv(), 1e-8, 0.0, True, case.nel)
+    tol, maxit = 1e-8, 60
+    xref, itref, hist_ref, div0 = hsmg.hmh_gmres(case, mg, b, h1, h2, case.mask, case.mult, tol, maxit, ifvcor=True, history=True)
+    bdv, h1d, wtd, pmd = (nek.DevArray.from_host(a) for a in (b, h1, case.mult, case.mask))
+    it = C.c_int(0)
+    check(L.nekb_hmh_gmres_dev(bdv.ptr, h1d.ptr, None, wtd.ptr, pmd.ptr, tol, maxit, C.byref(it), None, None))
+    assert abs(it.value - itref) <= 1 and itref < maxit
+    x = bdv.to_host()
+    assert relmax(x, xref) <= 1e-6
