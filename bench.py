@@ -31,6 +31,7 @@ NDOF = (LX1 - 1) ** 3            # DOF per element as the reference counts them 
 NXYZ = LX1 ** 3
 # algorithmic words (8 B) per grid point per CG iteration
 WORDS_AX = 8.0                   # read p, 6 geometric factors, write w
+WORDS_AX_CG = 12.0               # fused kernel: + read/write u (x += alpha p) + read r, write p (p = r + beta p); the p read is shared
 WORDS_ITER = 19.445              # + gs/mask 1.445 + x,r update 6 + weight 1 + p update 3
 
 
@@ -233,7 +234,11 @@ def main():
 
     peak, peak_src = peaks()
     ax_s, ax_n = prof["ax"]
-    ax_bytes = WORDS_AX * 8 * NXYZ * case.nel                      # per launch (this rank's elements)
+    fused = os.environ.get("NEKB_CG_FUSED", "1") != "0"
+    ax_words = WORDS_AX_CG if fused else WORDS_AX
+    ax_name = ("ax_cg_kernel<8,3,2> (u += alpha p; p = r + beta p; w = A p; pap -- 12 words/pt)" if fused
+               else "ax_tma_kernel<8,3,2> (w = A p with fused pap -- 8 words/pt)")
+    ax_bytes = ax_words * 8 * NXYZ * case.nel                      # per launch (this rank's elements)
     ax_gbs = ax_bytes / (ax_s / max(ax_n, 1)) / 1e9 if ax_s > 0 else None
     iter_gbs = WORDS_ITER * 8 * NXYZ * case.nel * iters / dev_s / 1e9   # whole iteration, per GPU
     tot_prof = sum(v[0] for v in prof.values())
@@ -243,7 +248,7 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
         "relerr": relerr, "wall_ms_per_step": wall_s / a.steps * 1e3, "gpu_launches": launches, "clocks": clocks,
         "e2e": e2e,
-        "roofline": {"bound": "hbm", "kernel": "ax_kernel (Ax = D^T G D p with fused pap)", "achieved": ax_gbs, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": ax_name, "achieved": ax_gbs, "peak": peak,
                      "unit": "GB/s", "frac": (ax_gbs / peak) if ax_gbs else None, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ax_bytes, "mean_launch_ms": ax_s / max(ax_n, 1) * 1e3,
                      "share_of_step": ax_s / tot_prof if tot_prof > 0 else None,
@@ -251,14 +256,16 @@ def main():
                      "whole_iteration": {"achieved": iter_gbs, "frac": iter_gbs / peak,
                                          "algorithmic_bytes_per_element_iteration": WORDS_ITER * 8 * NXYZ}},
     }
-    prof_json = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(prof_json):  # dram bytes per Ax launch from the committed ncu --set full capture
-        try:
-            tr = json.load(open(prof_json))
-            if tr.get("elements") == case.nel:
-                out["roofline"]["traffic"] = tr.get("ax_dram_bytes_per_launch")
-        except Exception:
-            pass
+    # dram__bytes_read+write per launch of the same kernel from the committed ncu --set full captures (E = 262,144)
+    if case.nel == 262144:
+        for fn, key in (("r1b_ncu_traffic.json", "ax_cg_kernel<8, 3, 2, 0>"), ("r1a_ncu_traffic.json", "ax_tma_kernel<8, 3, 2>")):
+            pj = os.path.join(ROOT, "profiles", fn)
+            if os.path.exists(pj) and (key.startswith("ax_cg") == fused):
+                try:
+                    out["roofline"]["traffic"] = json.load(open(pj)).get(key)
+                    out["roofline"]["traffic_source"] = f"profiles/{fn}"
+                except Exception:
+                    pass
     if a.gpus == 1 and not a.no_cpu:
         gd, nt, sample, _ = cpu_leg(2, 1, a.m_cpu, target_s=6.0)
         out["cpu_baseline"] = {"value": gd, "unit": "GDOF/s", "cores": nt, "kind": "port", "sample": sample}

@@ -1,0 +1,83 @@
+"""torchrun worker: BP5 on N GPUs (one rank per GPU, NCCL) against the single-domain oracle.
+Checks, per rank: numbering classes consistent with the global numbering, e1/r1, the CG history (global scalars) and
+the solution after `maxit` iterations, all within 1e-10 of the oracle's global solve.  Prints 'MGPU-OK rank r'."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import oracle
+    from nek5000_b200 import nek
+    from nek5000_b200.bp5 import BP5, brick_layout
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nek.init(local, 8, 3)
+    nek.comm_init_torch()
+    px, py, pz = brick_layout(world)
+    mx, my, mz = 2, 2, 1
+    nelx, nely, nelz = mx * px, my * py, mz * pz
+    deform = 0.04
+    b = BP5(nelx, nely, nelz, lx1=8, device=local, rank=rank, nranks=world, layout=(px, py, pz), deform=deform)
+    maxit = 40
+    it, sec, hist = b.solve(-1e-8, maxit, history=True)
+    u = b.get("u1")
+
+    # ---- oracle: the undivided mesh; every rank draws the seed-1 ran1 stream over its local nodes (navier5.f:2665-2674)
+    case = oracle.Case(nelx, nely, nelz, nx=8, deform=deform)
+    nxyz = 512
+    owner = np.zeros(case.nel, dtype=np.int64)
+    local_of = np.zeros(case.nel, dtype=np.int64)
+    lx, ly, lz = nelx // px, nely // py, nelz // pz
+    for eg in range(case.nel):
+        ex, ey, ez = eg % nelx, (eg // nelx) % nely, eg // (nelx * nely)
+        r = (ex // lx) + px * ((ey // ly) + py * (ez // lz))
+        owner[eg] = r
+        local_of[eg] = (ex % lx) + lx * ((ey % ly) + ly * (ez % lz))
+    rnd = np.zeros(case.n)
+    nloc = lx * ly * lz * nxyz
+    stream = np.zeros(nloc)
+    oracle.lib().nko_rand_fld(stream, nloc)
+    for eg in range(case.nel):
+        rnd[eg * nxyz:(eg + 1) * nxyz] = stream[local_of[eg] * nxyz:(local_of[eg] + 1) * nxyz]
+    e1 = case.dssum(rnd) * case.mult * case.mask
+    ap, _ = case.ax_bp5(e1)
+    r1 = case.dssum(ap) * case.mask
+    uref, itref, href = case.cggos(r1, e1, maxit=maxit, history=True)
+
+    mine = np.flatnonzero(owner == rank)
+    order = mine[np.argsort(local_of[mine])]
+    take = (order[:, None] * nxyz + np.arange(nxyz)[None, :]).reshape(-1)
+    rel = lambda a, c: np.abs(a - c).max() / max(np.abs(c).max(), 1e-300)
+    assert it == itref == maxit
+    assert rel(b.get("e1"), e1[take]) <= 1e-12, "e1"
+    assert rel(b.get("r1"), r1[take]) <= 1e-10, "r1"
+    assert np.array_equal(b.get("mult"), case.mult[take]), "mult"
+    assert rel(hist[:, 0], href[:, 0]) <= 1e-10, "pap history"
+    assert np.all(np.abs(hist[:, 1] - href[:, 2]) <= 1e-8 * np.abs(href[:, 2]) + 1e-300), "(r,z) history"
+    assert rel(u, uref[take]) <= 1e-10, "solution"
+    # numbering: same equivalence classes as the global numbering restricted to this rank
+    g = b.get("glo_num")
+    gref = case.glo_num[take]
+    _, inv_a = np.unique(g, return_inverse=True)
+    _, inv_b = np.unique(gref, return_inverse=True)
+    first_a = {}
+    first_b = {}
+    ca = np.array([first_a.setdefault(v, i) for i, v in enumerate(inv_a)])
+    cb = np.array([first_b.setdefault(v, i) for i, v in enumerate(inv_b)])
+    assert np.array_equal(ca, cb), "numbering classes"
+    print(f"MGPU-OK rank {rank} of {world}: its={it} rel(u)={rel(u, uref[take]):.2e}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -333,3 +333,23 @@ def test_full_size_properties():
     it, sec = b.solve(-1e-8, 120)
     assert b.relerr() < r30
     N.finalize()
+
+
+# ------------------------------------------------------------------------------------------------- multi-GPU (NCCL)
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_gpu_bp5_matches_single_domain_oracle(world):
+    """Element-partitioned BP5 over NCCL: every rank's part of numbering, rhs, CG history and solution equals the
+    undivided oracle solve.  Skipped when the box has fewer GPUs."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    port = 29500 + world
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(here, "_mgpu_worker.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("MGPU-OK") == world
