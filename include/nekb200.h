@@ -270,6 +270,24 @@ int nekb_h1mg_get(const char *which, int level, double *host_out, size_t n_doubl
 int nekb_crs_set_tolerance(double tol, int maxit);
 void nekb_h1mg_free(void);
 
+/* Single-level Schwarz / FDM preconditioner on the lx1^3 tiles (core/FDMH1).
+ * nekb_fdm_h1_setup = set_fdm_prec_h1A (core/hmholtz.f:1028-1220) for one field: face_internal[6*nel] is 1 where cbc is
+ * 'E  ','P  ','p  ' (faces r-,r+,s-,s+,t-,t+), mask the field's Dirichlet mask, xm1..zm1 /gxyz/ (all host arrays).
+ * nekb_set_kfldfdm = common /fdmh1i/ kfldfdm: >= 0 makes cggo take its Schwarz branch (:686-691, :731-746). */
+int nekb_fdm_h1_setup(const int *face_internal, const double *mask, const double *xm1, const double *ym1, const double *zm1,
+                      int nel);
+int nekb_set_kfldfdm(int kfldfdm);
+/* core/hmholtz.f:1222 set_fdm_prec_h1b(d,h1,h2,nel) and :937 fdm_h1(z,r,d,mask,mult,nel,kt,rr).  kt is not read: it is
+ * ktype(1,1,kfldfdm) of the same COMMON the setup call registered; mult and rr are unused by the reference too. */
+int nekb_set_fdm_prec_h1b_dev(double *d_dev, const double *h1_dev, const double *h2_dev);
+int nekb_fdm_h1_dev(double *z_dev, const double *r_dev, const double *d_dev, const double *mask_dev);
+void set_fdm_prec_h1b_(double *d, const double *h1, const double *h2, const int *nel);
+void fdm_h1_(double *z, const double *r, const double *d, const double *mask, const double *mult, const int *nel, const int *kt,
+             double *rr);
+/* Host copies of the setup products: which = "ktype" (int32 [nel][3], 1..9 as in the reference), "elsize" (double
+ * [nel][3]), "dd" (double [9][lx1]). */
+int nekb_fdm_h1_get(const char *which, void *host_out, size_t n_bytes);
+
 /* State hmh_gmres reads from COMMON: pmask (core/SOLN), binvm1 (core/MASS), tolps (core/TSTEP), param(21), ifvcor
  * (core/INPUT), nelgv; volvm1 and istep come from nekb_set_step_info.  Host arrays of lx1^3*nelv doubles. */
 int nekb_set_pressure_state(const double *pmask, const double *binvm1, double tolps, double param21, int ifvcor,

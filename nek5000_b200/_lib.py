@@ -147,6 +147,15 @@ def lib() -> C.CDLL:
     L.nekb_h1mg_get.argtypes = [C.c_char_p, C.c_int, vp, C.c_size_t]
     L.nekb_crs_set_tolerance.argtypes = [C.c_double, C.c_int]
     L.nekb_h1mg_free.restype = None
+    L.nekb_fdm_h1_setup.argtypes = [i32p, f64p, f64p, f64p, f64p, C.c_int]
+    L.nekb_set_kfldfdm.argtypes = [C.c_int]
+    L.nekb_set_fdm_prec_h1b_dev.argtypes = [vp, vp, vp]
+    L.nekb_fdm_h1_dev.argtypes = [vp, vp, vp, vp]
+    L.set_fdm_prec_h1b_.argtypes = [vp, vp, vp, ip]
+    L.set_fdm_prec_h1b_.restype = None
+    L.fdm_h1_.argtypes = [vp, vp, vp, vp, vp, ip, vp, vp]
+    L.fdm_h1_.restype = None
+    L.nekb_fdm_h1_get.argtypes = [C.c_char_p, vp, C.c_size_t]
     L.nekb_set_pressure_state.argtypes = [vp, vp, C.c_double, C.c_double, C.c_int, C.c_int64]
     L.hmh_gmres_.argtypes = [vp, vp, vp, vp, ip]
     L.hmh_gmres_.restype = None

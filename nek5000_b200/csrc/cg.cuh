@@ -15,6 +15,10 @@ namespace nekb {
 
 inline void comm_allreduce_sum(double *dev, int count);  // comm.cuh (no-op on one rank)
 inline void comm_allreduce_max(double *dev, int count);
+// fdm_h1.cuh: the Schwarz branch of cggo (kfldfdm >= 0, core/hmholtz.f:731-746)
+inline int fdm_h1_kfldfdm();
+inline void set_fdm_prec_h1b_dev(double *d, const double *h1, const double *h2, int nel);
+inline void fdm_h1_apply(double *z, const double *r, const double *d, const double *mask, int nel, int gs_handle);
 
 constexpr int CG_THREADS = 256;
 constexpr int CG_PART_STRIDE = 1024;  // partial-sum region per kernel kind
@@ -473,6 +477,33 @@ __global__ void __launch_bounds__(CG_THREADS)
     grid_reduce(b2, partials + CG_PART_STRIDE, &sc->counter[3], red, [=](double tot) { sc->work[1] = tot; });
 }
 
+// the same with an explicit preconditioned residual z (Schwarz branch, :737-745)
+__global__ void __launch_bounds__(CG_THREADS)
+    cggo_dots_z_kernel(const double *__restrict__ r, const double *__restrict__ z, const double *__restrict__ mult,
+                       const double *__restrict__ binv, int64_t n, CgScalars *sc, double *partials)
+{
+    __shared__ double red[33];
+    if (sc->done) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const double rv = r[t], mu = mult[t];
+        s1 = fma(z[t] * rv, mu, s1);
+        s2 = fma(mu * binv[t] * rv, rv, s2);
+    }
+    double b1 = block_reduce(s1, red);
+    double b2 = block_reduce(s2, red);
+    grid_reduce(b1, partials, &sc->counter[2], red, [=](double tot) { sc->work[0] = tot; });
+    grid_reduce(b2, partials + CG_PART_STRIDE, &sc->counter[3], red, [=](double tot) { sc->work[1] = tot; });
+}
+__global__ void __launch_bounds__(CG_THREADS)
+    cggo_pupdate_z_kernel(double *__restrict__ p, const double *__restrict__ z, int64_t n, const CgScalars *sc)
+{
+    if (sc->done) return;
+    const double beta = (sc->it == 0) ? 0.0 : sc->rtz1 / sc->rtz2;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+        p[t] = fma(beta, p[t], z[t]);
+}
+
 // :761-791 scalar bookkeeping and the convergence test (single thread).
 __global__ void cggo_check_kernel(CgScalars *sc, double vol, double tin, int istep, int niter_max, double *hist)
 {
@@ -612,7 +643,13 @@ inline int cggo_run(const CggoArgs &a, double tin, int maxit, double *hist_host)
     NEKB_CUDA(cudaStreamSynchronize(s));
     const double *h2_eff = (h2max > 0.0) ? a.h2 : nullptr;
 
-    setprec_run(d.p, a.h1, a.h2, a.nel, a.gs_handle);  // :690
+    const bool schwarz = fdm_h1_kfldfdm() >= 0;  // :686-691
+    DevBuf<double> &z = c.work[4];
+    if (schwarz) {
+        z.ensure(n);
+        set_fdm_prec_h1b_dev(d.p, a.h1, a.h2, a.nel);
+    } else
+        setprec_run(d.p, a.h1, a.h2, a.nel, a.gs_handle);  // :690
     cggo_init_kernel<<<grid, CG_THREADS, 0, s>>>(a.x, r.p, p.p, a.f, n, sc, c.partials.p + 1 * CG_PART_STRIDE);
     NEKB_LAUNCHED();
     comm_allreduce_max(&sc->work[2], 1);
@@ -625,12 +662,19 @@ inline int cggo_run(const CggoArgs &a, double tin, int maxit, double *hist_host)
     const int batch = 8;  // iterations enqueued between two looks at the convergence flag
     while (result < 0) {
         for (int b = 0; b < batch; b++) {
-            cggo_dots_kernel<<<grid, CG_THREADS, 0, s>>>(r.p, d.p, a.mult, a.binv, n, sc, c.partials.p + 2 * CG_PART_STRIDE);
+            if (schwarz) {  // :737-745 (fields other than 'PRES': no coarse correction)
+                fdm_h1_apply(z.p, r.p, d.p, a.mask, a.nel, a.gs_handle);
+                cggo_dots_z_kernel<<<grid, CG_THREADS, 0, s>>>(r.p, z.p, a.mult, a.binv, n, sc, c.partials.p + 2 * CG_PART_STRIDE);
+            } else
+                cggo_dots_kernel<<<grid, CG_THREADS, 0, s>>>(r.p, d.p, a.mult, a.binv, n, sc, c.partials.p + 2 * CG_PART_STRIDE);
             NEKB_LAUNCHED();
             comm_allreduce_sum(&sc->work[0], 2);
             cggo_check_kernel<<<1, 1, 0, s>>>(sc, a.vol, tin, a.istep, niter, c.hist.p);
             NEKB_LAUNCHED();
-            cggo_pupdate_kernel<<<grid, CG_THREADS, 0, s>>>(p.p, r.p, d.p, n, sc);
+            if (schwarz)
+                cggo_pupdate_z_kernel<<<grid, CG_THREADS, 0, s>>>(p.p, z.p, n, sc);
+            else
+                cggo_pupdate_kernel<<<grid, CG_THREADS, 0, s>>>(p.p, r.p, d.p, n, sc);
             NEKB_LAUNCHED();
             launch_ax(p.p, w.p, a.h1, h2_eff, a.nel, nullptr);
             gs_op(a.gs_handle, w.p, 1, nullptr);

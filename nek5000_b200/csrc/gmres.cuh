@@ -10,7 +10,7 @@
 // produces (w,w).  The small Hessenberg / Givens recurrences run on the host exactly as written in the reference
 // (one device->host copy of j+1 numbers per column, where the reference has an MPI_Allreduce).
 #pragma once
-#include "hsmg.cuh"
+#include "fdm_h1.cuh"
 
 namespace nekb {
 

@@ -258,7 +258,9 @@ struct CrsSolver {
     int64_t n = 0;              // 8 * nel
     DevBuf<double> a;           // [nel][8][8] local Galerkin matrices, a[e][i][j]
     DevBuf<double> mask, mult, dinv;
-    DevBuf<double> b, x, r, p, w;
+    DevBuf<double> b, x, r, p, p2, w;
+    cudaGraphExec_t graph = nullptr;  // one batch of PCG iterations (single rank), replayed
+    int64_t graph_launches = 0;
     double ndof = 0.0;          // distinct unmasked dofs (all ranks)
     int null_space = 0;
     int last_iters = 0;
@@ -278,6 +280,12 @@ inline H1mg &h1mg()
 {
     static H1mg m;
     return m;
+}
+inline void crs_release_graph()
+{
+    CrsSolver &k = h1mg().crs;
+    if (k.graph) cudaGraphExecDestroy(k.graph);
+    k.graph = nullptr;
 }
 
 // ================================================================================================ kernels
@@ -566,9 +574,19 @@ __global__ void __launch_bounds__(256)
     const double bs = block_reduce(s, red);
     grid_reduce(bs, partials, counter, red, [=](double tot) { *out = tot; });
 }
+// x += alpha p ; r -= alpha w ; rz_new = (r, D^-1 r) ; rr = (r, r).  With `finish` (single rank) the last block also
+// runs the bookkeeping of crs_check_kernel.
+__device__ __forceinline__ void crs_bookkeeping(CrsScalars *sc, double tol2, int maxit)
+{
+    sc->it = sc->it + 1;
+    if (sc->rr <= tol2 * sc->rr0 || sc->it >= maxit || sc->rz_new == 0.0) sc->done = 1;
+    sc->shift = sc->rz_new / sc->rz;  // beta of the next direction update
+    sc->rz = sc->rz_new;
+}
 __global__ void __launch_bounds__(256)
     crs_xr_kernel(double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p, const double *__restrict__ w,
-                  const double *__restrict__ dinv, const double *__restrict__ m, int64_t n, CrsScalars *sc, double *partials)
+                  const double *__restrict__ dinv, const double *__restrict__ m, int64_t n, CrsScalars *sc, double *partials,
+                  int finish, double tol2, int maxit)
 {
     __shared__ double red[33];
     if (sc->done) return;
@@ -582,28 +600,56 @@ __global__ void __launch_bounds__(256)
         s2 = fma(rv * rv, m[t], s2);
     }
     const double b1 = block_reduce(s1, red), b2 = block_reduce(s2, red);
-    grid_reduce(b1, partials, &sc->counter[0], red, [=](double tot) { sc->rz_new = tot; });
-    grid_reduce(b2, partials + 1024, &sc->counter[1], red, [=](double tot) { sc->rr = tot; });
+    // one ticket for both sums: the last block combines them in index order
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = b1;
+        partials[1024 + blockIdx.x] = b2;
+        __threadfence();
+        const unsigned t = atomicInc(&sc->counter[0], gridDim.x - 1);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double a1 = 0.0, a2 = 0.0;
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) a1 += __ldcg(partials + i), a2 += __ldcg(partials + 1024 + i);
+        const double t1 = block_reduce(a1, red), t2 = block_reduce(a2, red);
+        if (threadIdx.x == 0) {
+            sc->rz_new = t1;
+            sc->rr = t2;
+            if (finish) crs_bookkeeping(sc, tol2, maxit);
+        }
+    }
 }
 __global__ void crs_check_kernel(CrsScalars *sc, double tol2, int maxit)
 {
     if (sc->done) return;
-    sc->it = sc->it + 1;
-    if (sc->rr <= tol2 * sc->rr0 || sc->it >= maxit || sc->rz_new == 0.0) sc->done = 1;
+    crs_bookkeeping(sc, tol2, maxit);
 }
+// p_out = D^-1 r + beta p_in ; w = A_loc p_out (per element 8x8).  Every thread rebuilds the 8 new direction entries
+// of its element, so no barrier between the update and the product is needed; p is double buffered.
 __global__ void __launch_bounds__(256)
-    crs_p_kernel(double *__restrict__ p, const double *__restrict__ r, const double *__restrict__ dinv, int64_t n, CrsScalars *sc,
-                 int first)
+    crs_pmv_kernel(double *__restrict__ p_out, const double *__restrict__ p_in, double *__restrict__ w, const double *__restrict__ r,
+                   const double *__restrict__ dinv, const double *__restrict__ a, int64_t n, const CrsScalars *sc)
 {
     if (sc->done) return;
-    const double beta = first ? 0.0 : sc->rz_new / sc->rz;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
-        p[t] = fma(beta, p[t], dinv[t] * r[t]);
-}
-__global__ void crs_rotate_kernel(CrsScalars *sc)
-{
-    if (sc->done) return;
-    sc->rz = sc->rz_new;
+    const double beta = sc->it == 0 ? 0.0 : sc->shift;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e8 = t & ~(int64_t)7;
+        const int i = (int)(t & 7);
+        const double *ae = a + (t >> 3) * 64 + i * 8;
+        double s = 0.0, mine = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const double pj = fma(beta, p_in[e8 + j], dinv[e8 + j] * r[e8 + j]);
+            if (j == i) mine = pj;
+            s = fma(ae[j], pj, s);
+        }
+        p_out[t] = mine;
+        w[t] = s;
+    }
 }
 // w *= mask ; pw = sum p*w*m
 __global__ void __launch_bounds__(256)
@@ -676,6 +722,7 @@ inline void crs_solve_dev(double *x_out, const double *b_in)
     }
     NEKB_CUDA(cudaMemsetAsync(k.x.p, 0, sizeof(double) * (n ? n : 1), s));
     NEKB_CUDA(cudaMemsetAsync(k.p.p, 0, sizeof(double) * (n ? n : 1), s));
+    NEKB_CUDA(cudaMemsetAsync(k.p2.p, 0, sizeof(double) * (n ? n : 1), s));
     NEKB_CUDA(cudaMemsetAsync(sc, 0, sizeof(CrsScalars), s));
     // rz = (r, D^-1 r), rr0 = (r, r)
     crs_dot_kernel<<<grid, 256, 0, s>>>(k.r.p, k.r.p, k.mult.p, n, &sc->rr0, part, &sc->counter[3]);
@@ -686,34 +733,56 @@ inline void crs_solve_dev(double *x_out, const double *b_in)
     NEKB_CUDA(cudaStreamSynchronize(s));
     k.last_iters = 0;
     if (rr0 > 0.0) {
-        // w = D^-1 r ; rz = (r, w)
-        crs_p_kernel<<<grid, 256, 0, s>>>(k.p.p, k.r.p, k.dinv.p, n, sc, 1);
+        // rz = (r, D^-1 r): p2 = D^-1 r as scratch (the first direction update rebuilds it with beta = 0)
+        mg_copy_kernel<<<grid, 256, 0, s>>>(k.p2.p, k.r.p, n);
         NEKB_LAUNCHED();
-        crs_dot_kernel<<<grid, 256, 0, s>>>(k.r.p, k.p.p, k.mult.p, n, &sc->rz, part, &sc->counter[3]);
+        col2_kernel<<<grid, 256, 0, s>>>(k.p2.p, k.dinv.p, n);
+        NEKB_LAUNCHED();
+        crs_dot_kernel<<<grid, 256, 0, s>>>(k.r.p, k.p2.p, k.mult.p, n, &sc->rz, part, &sc->counter[3]);
         NEKB_LAUNCHED();
         comm_allreduce_sum(&sc->rz, 1);
-        const int batch = 16;
+        const int batch = 16;  // even: the double-buffered direction vector ends where it started
+        const bool single = c.nranks <= 1;
+        const double tol2 = k.tol * k.tol;
+        auto enqueue_batch = [&]() {
+            for (int b = 0; b < batch; b++) {
+                double *pin = (b & 1) ? k.p2.p : k.p.p, *pout = (b & 1) ? k.p.p : k.p2.p;
+                crs_pmv_kernel<<<grid, 256, 0, s>>>(pout, pin, k.w.p, k.r.p, k.dinv.p, k.a.p, n, sc);
+                NEKB_LAUNCHED();
+                gs_op(k.gs, k.w.p, 1, nullptr);
+                crs_pw_kernel<<<grid, 256, 0, s>>>(k.w.p, pout, k.mask.p, k.mult.p, n, sc, part + 2048);
+                NEKB_LAUNCHED();
+                comm_allreduce_sum(&sc->pw, 1);
+                crs_xr_kernel<<<grid, 256, 0, s>>>(k.x.p, k.r.p, pout, k.w.p, k.dinv.p, k.mult.p, n, sc, part, single ? 1 : 0, tol2,
+                                                   k.maxit);
+                NEKB_LAUNCHED();
+                if (!single) {
+                    comm_allreduce_sum(&sc->rz_new, 2);  // rz_new, rr are adjacent
+                    crs_check_kernel<<<1, 1, 0, s>>>(sc, tol2, k.maxit);
+                    NEKB_LAUNCHED();
+                }
+            }
+        };
         int launched = 0;
         bool done = false;
         while (!done) {
-            for (int b = 0; b < batch; b++) {
-                crs_matvec_kernel<<<grid, 256, 0, s>>>(k.w.p, k.a.p, k.p.p, n);
-                NEKB_LAUNCHED();
-                gs_op(k.gs, k.w.p, 1, nullptr);
-                crs_pw_kernel<<<grid, 256, 0, s>>>(k.w.p, k.p.p, k.mask.p, k.mult.p, n, sc, part);
-                NEKB_LAUNCHED();
-                comm_allreduce_sum(&sc->pw, 1);
-                crs_xr_kernel<<<grid, 256, 0, s>>>(k.x.p, k.r.p, k.p.p, k.w.p, k.dinv.p, k.mult.p, n, sc, part);
-                NEKB_LAUNCHED();
-                comm_allreduce_sum(&sc->rz_new, 2);  // rz_new, rr are adjacent
-                crs_check_kernel<<<1, 1, 0, s>>>(sc, k.tol * k.tol, k.maxit);
-                NEKB_LAUNCHED();
-                crs_p_kernel<<<grid, 256, 0, s>>>(k.p.p, k.r.p, k.dinv.p, n, sc, 0);
-                NEKB_LAUNCHED();
-                crs_rotate_kernel<<<1, 1, 0, s>>>(sc);
-                NEKB_LAUNCHED();
-                launched++;
-            }
+            if (single) {
+                if (!k.graph) {  // capture one batch once; the arguments never change for this handle
+                    const int64_t before = launch_counter();
+                    cudaGraph_t g = nullptr;
+                    NEKB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+                    enqueue_batch();
+                    NEKB_CUDA(cudaStreamEndCapture(s, &g));
+                    NEKB_CUDA(cudaGraphInstantiate(&k.graph, g, 0));
+                    NEKB_CUDA(cudaGraphDestroy(g));
+                    k.graph_launches = launch_counter() - before;
+                    launch_counter() = before;
+                }
+                NEKB_CUDA(cudaGraphLaunch(k.graph, s));
+                launch_counter() += k.graph_launches;
+            } else
+                enqueue_batch();
+            launched += batch;
             CrsScalars hs;
             NEKB_CUDA(cudaMemcpyAsync(&hs, sc, sizeof(CrsScalars), cudaMemcpyDeviceToHost, s));
             NEKB_CUDA(cudaStreamSynchronize(s));
@@ -823,6 +892,7 @@ inline void h1mg_setup_run(const int *fbc, const double *xm1, const double *ym1,
     Ctx &c = ctx();
     cudaStream_t s = c.stream;
     H1mg &M = h1mg();
+    crs_release_graph();
     M = H1mg();
     NEKB_REQUIRE(c.have_geom, "h1mg_setup: geometry must be registered first (nekb_set_geom*)");
     ensure_operators();
@@ -1023,7 +1093,7 @@ inline void h1mg_setup_run(const int *fbc, const double *xm1, const double *ym1,
             NEKB_LAUNCHED();
         }
         k.mask.alloc(n), k.mult.alloc(n), k.dinv.alloc(n);
-        k.b.alloc(n), k.x.alloc(n), k.r.alloc(n), k.p.alloc(n), k.w.alloc(n);
+        k.b.alloc(n), k.x.alloc(n), k.r.alloc(n), k.p.alloc(n), k.p2.alloc(n), k.w.alloc(n);
         if (n) {
             NEKB_CUDA(cudaMemcpyAsync(k.mask.p, L0.mask.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
             NEKB_CUDA(cudaMemcpyAsync(k.mult.p, L0.rstr_wt.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));

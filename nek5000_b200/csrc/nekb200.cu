@@ -167,7 +167,9 @@ void nekb_finalize(void)
     if (!c.inited) return;
     cudaStreamSynchronize(c.stream);
     bp5case() = Bp5Case();
+    crs_release_graph();
     h1mg() = H1mg();
+    fdm_h1_state() = FdmH1State();
     gmres_state() = GmresState();
     crs_scalars().release();
     c.gs.clear();
@@ -853,6 +855,7 @@ int nekb_crs_set_tolerance(double tol, int maxit)
 {
     return guard([&] {
         NEKB_REQUIRE(tol > 0.0 && maxit > 0, "nekb_crs_set_tolerance: bad arguments");
+        crs_release_graph();  // tolerance and cap are baked into the captured batch
         h1mg().crs.tol = tol;
         h1mg().crs.maxit = maxit;
     });
@@ -860,12 +863,91 @@ int nekb_crs_set_tolerance(double tol, int maxit)
 void nekb_h1mg_free(void)
 {
     H1mg &M = h1mg();
+    crs_release_graph();
     for (MgLevel &L : M.lev) {
         if (L.gs >= 0 && L.gs < (int)ctx().gs.size()) ctx().gs[L.gs] = GsMap();
         if (L.gs_face >= 0 && L.gs_face < (int)ctx().gs.size()) ctx().gs[L.gs_face] = GsMap();
     }
     M = H1mg();
     gmres_state() = GmresState();
+}
+
+int nekb_fdm_h1_setup(const int *face_internal, const double *mask, const double *xm1, const double *ym1, const double *zm1, int nel)
+{
+    return guard([&] {
+        require_init();
+        fdm_h1_setup(face_internal, mask, xm1, ym1, zm1, nel);
+    });
+}
+int nekb_set_kfldfdm(int kfldfdm)
+{
+    return guard([&] { fdm_h1_state().kfldfdm = kfldfdm; });
+}
+int nekb_set_fdm_prec_h1b_dev(double *d_dev, const double *h1_dev, const double *h2_dev)
+{
+    return guard([&] {
+        require_init();
+        set_fdm_prec_h1b_dev(d_dev, h1_dev, h2_dev, fdm_h1_state().nel);
+    });
+}
+int nekb_fdm_h1_dev(double *z_dev, const double *r_dev, const double *d_dev, const double *mask_dev)
+{
+    return guard([&] {
+        require_init();
+        fdm_h1_apply(z_dev, r_dev, d_dev, mask_dev, fdm_h1_state().nel, field_handle());
+    });
+}
+void set_fdm_prec_h1b_(double *d, const double *h1, const double *h2, const int *nel)
+{
+    guard_fortran("set_fdm_prec_h1b", [&] {
+        require_init();
+        Ctx &c = ctx();
+        const size_t n = (size_t)(*nel) * c.nxyz;
+        for (int k = 0; k < 3; k++) c.stage[k].ensure(n);
+        NEKB_CUDA(cudaMemcpyAsync(c.stage[1].p, h1, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        NEKB_CUDA(cudaMemcpyAsync(c.stage[2].p, h2, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        set_fdm_prec_h1b_dev(c.stage[0].p, c.stage[1].p, c.stage[2].p, *nel);
+        NEKB_CUDA(cudaMemcpyAsync(d, c.stage[0].p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+void fdm_h1_(double *z, const double *r, const double *d, const double *mask, const double *mult, const int *nel, const int *kt,
+             double *rr)
+{
+    (void)mult, (void)kt;
+    guard_fortran("fdm_h1", [&] {
+        require_init();
+        Ctx &c = ctx();
+        const size_t n = (size_t)(*nel) * c.nxyz;
+        for (int k = 0; k < 4; k++) c.stage[k].ensure(n);
+        NEKB_CUDA(cudaMemcpyAsync(c.stage[1].p, r, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        NEKB_CUDA(cudaMemcpyAsync(c.stage[2].p, d, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        NEKB_CUDA(cudaMemcpyAsync(c.stage[3].p, mask, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        fdm_h1_apply(c.stage[0].p, c.stage[1].p, c.stage[2].p, c.stage[3].p, *nel, field_handle());
+        NEKB_CUDA(cudaMemcpyAsync(z, c.stage[0].p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+        if (rr) memcpy(rr, r, n * sizeof(double));  // hmholtz.f:965 rr = r (ifbhalf = .false.)
+    });
+}
+int nekb_fdm_h1_get(const char *which, void *host_out, size_t n_bytes)
+{
+    return guard([&] {
+        FdmH1State &F = fdm_h1_state();
+        NEKB_REQUIRE(F.ready, "nekb_fdm_h1_setup has not been called");
+        const std::string w(which);
+        if (w == "ktype") {
+            NEKB_REQUIRE(n_bytes >= F.ktype_host.size() * sizeof(int32_t), "nekb_fdm_h1_get: buffer too small");
+            int32_t *o = (int32_t *)host_out;
+            for (size_t i = 0; i < F.ktype_host.size(); i++) o[i] = F.ktype_host[i] + 1;
+        } else if (w == "elsize") {
+            NEKB_REQUIRE(n_bytes >= F.elsize_host.size() * sizeof(double), "nekb_fdm_h1_get: buffer too small");
+            memcpy(host_out, F.elsize_host.data(), F.elsize_host.size() * sizeof(double));
+        } else if (w == "dd") {
+            NEKB_REQUIRE(n_bytes >= F.dd_host.size() * sizeof(double), "nekb_fdm_h1_get: buffer too small");
+            memcpy(host_out, F.dd_host.data(), F.dd_host.size() * sizeof(double));
+        } else
+            NEKB_REQUIRE(false, std::string("nekb_fdm_h1_get: unknown array '") + which + "'");
+    });
 }
 
 int nekb_set_pressure_state(const double *pmask, const double *binvm1, double tolps, double param21, int ifvcor, int64_t nelgv)

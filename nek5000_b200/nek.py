@@ -34,7 +34,7 @@ __all__ = [
     "niterhm", "setvert3d", "setupds", "fgslib_gs_setup", "fgslib_gs_op", "fgslib_gs_op_many", "fgslib_gs_op_fields",
     "fgslib_gs_free", "gs_get_map", "gs_info", "dssum", "dsop", "axhelm", "setprec", "cggo", "cggos", "axhm1", "glsc3",
     "DevArray", "set_transport_torch", "comm_init_torch", "h1mg_setup", "h1mg_solve", "h1mg_info", "h1mg_get", "h1mg_free",
-    "set_pressure_state", "hmh_gmres",
+    "set_pressure_state", "hmh_gmres", "fdm_h1_setup", "set_kfldfdm", "set_fdm_prec_h1b", "fdm_h1", "fdm_h1_get",
 ]
 
 _state = {"lx1": 0, "nelt": 0, "np": 1, "keep": []}
@@ -287,6 +287,32 @@ def h1mg_get(which: str, level: int, n: int) -> np.ndarray:
 
 def h1mg_free() -> None:
     lib().nekb_h1mg_free()
+
+
+def fdm_h1_setup(face_internal, mask, xm1, ym1, zm1, nel: int) -> None:
+    """core/hmholtz.f:1028-1220 set_fdm_prec_h1A for one field."""
+    f = np.ascontiguousarray(face_internal, dtype=np.int32).reshape(-1)
+    check(lib().nekb_fdm_h1_setup(f, *[np.ascontiguousarray(a, dtype=np.float64) for a in (mask, xm1, ym1, zm1)], nel))
+
+
+def set_kfldfdm(kfldfdm: int) -> None:
+    check(lib().nekb_set_kfldfdm(kfldfdm))
+
+
+def set_fdm_prec_h1b(d: np.ndarray, h1: np.ndarray, h2: np.ndarray, nel: int) -> None:
+    lib().set_fdm_prec_h1b_(_ptr(d), _ptr(h1), _ptr(h2), _i(nel))
+
+
+def fdm_h1(z, r, d, mask, mult, nel: int, kt=None, rr=None) -> None:
+    """core/hmholtz.f:937 fdm_h1(z,r,d,mask,mult,nel,kt,rr)."""
+    lib().fdm_h1_(_ptr(z), _ptr(r), _ptr(d), _ptr(mask), _ptr(mult), _i(nel), None, None if rr is None else _ptr(rr))
+
+
+def fdm_h1_get(which: str, nel: int):
+    lx1 = _state["lx1"]
+    out = {"ktype": np.zeros(3 * nel, dtype=np.int32), "elsize": np.zeros(3 * nel), "dd": np.zeros(9 * lx1)}[which]
+    check(lib().nekb_fdm_h1_get(which.encode(), _ptr(out), out.nbytes))
+    return out
 
 
 def set_pressure_state(pmask, binvm1, tolps: float, param21: float = 0.0, ifvcor: bool = False, nelgv: int = 0) -> None:

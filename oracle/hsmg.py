@@ -543,3 +543,141 @@ def hmh_gmres(case, mg, res, h1, h2, pmask, wt, tol, maxit, m=30, ifvcor=False, 
     if history:
         return x, it, np.array(hist), div0
     return x, it
+
+
+# ----------------------------------------------------------------------------- fdm_h1 (single-level Schwarz / FDM)
+class FdmH1:
+    """core/hmholtz.f:1028-1112 set_fdm_prec_h1A_gen, :1114-1220 set_fdm_prec_h1A_els, :1222-1290 set_fdm_prec_h1b and
+    :937-1026 fdm_h1 for one field.
+
+    face_internal[e, 6]: 1 where cbc is 'E  ', 'P  ' or 'p  ' (faces in symmetric order r-, r+, s-, s+, t-, t+);
+    mask: the field's Dirichlet mask (decides Dirichlet vs Neumann on the remaining faces)."""
+
+    def __init__(self, case, face_internal, mask):
+        n = case.nx
+        self.case, self.n = case, n
+        z, w = case.z, case.w
+        D = case.D
+        delta = abs(z[1] - z[0])
+        bbh, aah = 0.5 * delta, 1.0 / delta
+        self.dd = np.zeros((9, n))
+        self.fds = np.zeros((9, n, n))
+        l = 0
+        for right in (1, 2, 3):
+            for left in (1, 2, 3):
+                bb = np.diag(w).astype(np.float64)
+                aa = D.T @ (bb @ D)
+                if left == 1:
+                    bb[0, 0] += bbh
+                    aa[0, 0] += aah
+                elif left == 2:
+                    bb[0, 0] = 1.0
+                    aa[:, 0] = 0.0
+                    aa[0, :] = 0.0
+                    aa[0, 0] = 1.0
+                if right == 1:
+                    bb[-1, -1] += bbh
+                    aa[-1, -1] += aah
+                elif right == 2:
+                    bb[-1, -1] = 1.0
+                    aa[:, -1] = 0.0
+                    aa[-1, :] = 0.0
+                    aa[-1, -1] = 1.0
+                lam, s = scipy.linalg.eigh(aa, bb, lower=False, driver="gv")
+                self.dd[l], self.fds[l] = lam, s
+                l += 1
+        E = case.nel
+        fi = np.asarray(face_internal).reshape(E, 6)
+        m = _r(np.asarray(mask), n)
+        self.ktype = np.zeros((E, 3), dtype=np.int32)
+        pts = (((1, 1, 0), (1, 1, n - 1)), ((1, 0, 1), (1, n - 1, 1)), ((0, 1, 1), (n - 1, 1, 1)))  # [k, j, i] of k1, k2
+        for e in range(E):
+            for d in range(3):
+                code = []
+                for side in (0, 1):
+                    k, j, i = pts[d][side]
+                    if fi[e, 2 * d + side]:
+                        code.append(1)
+                    elif m[e, k, j, i] == 0:
+                        code.append(2)
+                    else:
+                        code.append(3)
+                self.ktype[e, d] = code[0] + 3 * (code[1] - 1)
+        x, y, zz = _r(case.xm1, n), _r(case.ym1, n), _r(case.zm1, n)
+        self.elsize = np.zeros((3, E))
+        w3 = [w[0] * w[:, None] * w[None, :]] * 3  # wxm1(i)*wxm1(j)*wxm1(k) with the normal index fixed at 1
+        for e in range(E):
+            for d in range(3):
+                if d == 0:
+                    a, b = (e, slice(None), slice(None), n - 1), (e, slice(None), slice(None), 0)
+                elif d == 1:
+                    a, b = (e, slice(None), n - 1, slice(None)), (e, slice(None), 0, slice(None))
+                else:
+                    a, b = (e, n - 1, slice(None), slice(None)), (e, 0, slice(None), slice(None))
+                dl2 = (x[a] - x[b]) ** 2 + (y[a] - y[b]) ** 2 + (zz[a] - zz[b]) ** 2
+                self.elsize[d, e] = np.sqrt((dl2 * w3[d]).sum() / w3[d].sum()) / 2.0
+
+    def set_prec_h1b(self, h1, h2):
+        n, E = self.n, self.case.nel
+        d = np.zeros((E, n, n, n))
+        h1b = h1.reshape(E, -1).sum(axis=1) / n ** 3
+        h2b = h2.reshape(E, -1).sum(axis=1) / n ** 3
+        for e in range(E):
+            k1, k2, k3 = self.ktype[e] - 1
+            s = self.elsize[:, e]
+            vol = s[0] * s[1] * s[2]
+            vl1, vl2, vl3 = s[1] * s[2] / s[0], s[0] * s[2] / s[1], s[0] * s[1] / s[2]
+            den = h1b[e] * (vl1 * self.dd[k1][None, None, :] + vl2 * self.dd[k2][None, :, None] + vl3 * self.dd[k3][:, None, None]) + h2b[e] * vol
+            nzm = den != 0
+            d[e][nzm] = 1.0 / den[nzm]
+        return d.reshape(-1)
+
+    def apply(self, r, d, mask):
+        n, E = self.n, self.case.nel
+        S = self.fds[self.ktype - 1]  # [E, 3, n, n]
+        t = np.einsum("eia,ejb,ekc,ekji->ecba", S[:, 0], S[:, 1], S[:, 2], _r(r, n))
+        t = t * _r(d, n)
+        z = np.einsum("eai,ebj,eck,ekji->ecba", S[:, 0], S[:, 1], S[:, 2], t).reshape(-1)
+        return self.case.dssum(z) * mask
+
+
+def cggo_schwarz(case, fdm, f, h1, h2, mask, tin, maxit, istep=1, history=False):
+    """core/hmholtz.f:611-846 cggo with kfldfdm >= 0 (Schwarz branch :737-745) for a field other than 'PRES', without the
+    null-space correction.  Returns (x, niter[, hist rows (rtz1, rbn2, rho)])."""
+    n = case.n
+    mult, binv = case.mult, case.binv()
+    vol = case.bm1().sum()
+    tol = abs(tin)
+    niter = min(maxit, 900)
+    d = fdm.set_prec_h1b(h1, h2)
+    r, x, p = f.copy(), np.zeros(n), np.zeros(n)
+    hist = []
+    if np.abs(f).max() == 0.0:
+        return (x, 0, np.zeros((0, 3))) if history else (x, 0)
+    rtz1, rho, rbn0 = 1.0, 0.0, 0.0
+    it_done = niter
+    for it in range(1, niter + 1):
+        z = fdm.apply(r, d, mask)
+        rtz2 = rtz1
+        rtz1 = float(np.sum(z * r * mult))
+        rbn2 = float(np.sqrt(np.sum(mult * binv * r * r) / vol))
+        if it == 1:
+            rbn0 = rbn2
+        if tin < 0:
+            tol = abs(tin) * rbn0
+        row = [rtz1, rbn2, 0.0]
+        hist.append(row)
+        if rbn2 <= tol and (it > 1 or istep <= 5):
+            it_done = it - 1
+            break
+        beta = 0.0 if it == 1 else rtz1 / rtz2
+        p = z + beta * p
+        w = case.dssum(case.axhelm(p, h1, h2)) * mask
+        rho = float(np.sum(w * p * mult))
+        row[2] = rho
+        alpha = rtz1 / rho
+        x = x + alpha * p
+        r = r - alpha * w
+    if history:
+        return x, it_done, np.array(hist)
+    return x, it_done

@@ -181,3 +181,51 @@ def test_h1mg_all_neumann_null_space(nek):
     assert abs(it.value - itref) <= 1 and itref < maxit
     x = bdv.to_host()
     assert relmax(x, xref) <= 1e-6
+
+
+@pytest.mark.parametrize("deform", [0.0, 0.02])
+def test_fdm_h1_and_cggo_schwarz_branch(nek, deform):
+    """core/hmholtz.f:937-1290 (fdm_h1, set_fdm_prec_h1A/h1b) and the Schwarz branch of cggo (:731-746)."""
+    nek.finalize()
+    nek.init(0, 8, 3)
+    case = oracle.Case(3, 3, 2, nx=8, dirichlet=(1, 1, 0, 0, 1, 1), deform=deform)
+    fi = (hsmg.box_fbc(case, (1, 1, 1, 1, 1, 1)) == 0).astype(np.int32)
+    fdm = hsmg.FdmH1(case, fi, case.mask)
+    nek.set_nel(case.nel, case.nel)
+    nek.set_gll(case.z, case.w)
+    nek.set_dxyz(case.D, case.Dt)
+    nek.set_geom(*case.geom()[:7])
+    nek.set_ifdfrm(None)
+    h, _ = nek.setupds(8, case.nel, case.vertex)
+    nek.set_ifield(1)
+    nek.set_field_handle(1, h)
+    nek.fdm_h1_setup(fi, case.mask, case.xm1, case.ym1, case.zm1, case.nel)
+    E, n = case.nel, case.n
+    assert np.array_equal(nek.fdm_h1_get("ktype", E).reshape(E, 3), fdm.ktype)
+    assert relmax(nek.fdm_h1_get("elsize", E).reshape(E, 3).T, fdm.elsize) <= 1e-14
+    assert relmax(nek.fdm_h1_get("dd", E).reshape(9, 8), fdm.dd) <= 1e-11
+    rng = np.random.default_rng(4)
+    h1 = 1.0 + 0.3 * rng.random(n)
+    h2 = 0.5 + 0.2 * rng.random(n)
+    dref = fdm.set_prec_h1b(h1, h2)
+    d = np.zeros(n)
+    nek.set_fdm_prec_h1b(d, h1, h2, E)
+    assert relmax(d, dref) <= TOL
+    r = rng.standard_normal(n)
+    zref = fdm.apply(r, dref, case.mask)
+    z, rr = np.zeros(n), np.zeros(n)
+    nek.fdm_h1(z, r, dref, case.mask, case.mult, E, None, rr)
+    assert relmax(z, zref) <= TOL and np.array_equal(rr, r)
+    # cggo with kfldfdm >= 0: identical iteration count, history and solution
+    xe = case.dssum(rng.standard_normal(n)) * case.mult * case.mask
+    f = case.dssum(case.axhelm(xe, h1, h2)) * case.mask
+    nek.set_step_info(1, case.bm1().sum())
+    xref, itref, hist = hsmg.cggo_schwarz(case, fdm, f, h1, h2, case.mask, 1e-8, 200, history=True)
+    _, itjac = case.cggo(f, h1, h2, tin=1e-8, maxit=400)
+    nek.set_kfldfdm(1)
+    x = np.zeros(n)
+    it = nek.cggo(x, f, h1, h2, case.mask, case.mult, 1, 1e-8, 200, 1, case.binv(), "VELX")
+    nek.set_kfldfdm(-1)
+    assert it == itref and it < itjac
+    assert relmax(x, xref) <= 1e-9 and relmax(x, xe) <= 1e-6
+    nek.fgslib_gs_free(h)
