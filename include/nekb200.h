@@ -122,6 +122,11 @@ void axhm1_(double *pap, double *ap1, const double *p1, const double *h1, const 
             const char *bpname, size_t bpname_len);
 /* core/math.f:775 glsc3(a,b,mult,n) = global sum a*b*mult (gop '+'). */
 double glsc3_(const double *a, const double *b, const double *mult, const int *n);
+/* core/hmholtz.f:2 hmholtz(name,u,rhs,h1,h2,mask,mult,imsh,tli,maxit,isd): dssum + mask of rhs (in place, as the reference),
+ * chktcg1 (:527-609) when param(22) = 0 or istep <= 10, then cggo with binvm1/bintm1.  name is character*4; gfortran
+ * appends its hidden length after the last argument. */
+void hmholtz_(const char *name, double *u, double *rhs, const double *h1, const double *h2, const double *mask,
+              const double *mult, const int *imsh, const double *tli, const int *maxit, const int *isd, size_t name_len);
 int nekb_niterhm(void);
 
 /* ------------------------------------------------------------------------------------
@@ -160,6 +165,10 @@ int nekb_set_v1mask(const double *v1mask);
 int nekb_set_ifield(int ifield);
 int nekb_set_field_handle(int ifield, int gs_handle);
 int nekb_set_step_info(int istep, double volvm1, double voltm1);
+/* INPUT param(idx), 1-based: the path reads param(21) (pressure tolerance), param(22) (Helmholtz tolerance; < 0 relative,
+ * core/hmholtz.f:764).  MASS binvm1 / bintm1 (host, lx1^3*nelv / nelt doubles; bintm1 may be NULL) for hmholtz. */
+int nekb_set_param(int idx, double value);
+int nekb_set_binv(const double *binvm1, const double *bintm1);
 
 /* ------------------------------------------------------------------------------------
  * C. Device-resident API (pointers are device pointers valid on the library's device)

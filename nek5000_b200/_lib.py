@@ -136,6 +136,10 @@ def lib() -> C.CDLL:
     L.axhm1_.restype = None
     L.glsc3_.argtypes = [vp, vp, vp, ip]
     L.glsc3_.restype = C.c_double
+    L.hmholtz_.argtypes = [C.c_char_p, vp, vp, vp, vp, vp, vp, ip, dp, ip, ip, C.c_size_t]
+    L.hmholtz_.restype = None
+    L.nekb_set_param.argtypes = [C.c_int, C.c_double]
+    L.nekb_set_binv.argtypes = [vp, vp]
     # section F: pressure preconditioner + GMRES
     L.nekb_h1mg_setup.argtypes = [i32p, f64p, f64p, f64p, i64p, C.c_int, C.c_int]
     L.nekb_h1mg_solve_dev.argtypes = [vp, vp]

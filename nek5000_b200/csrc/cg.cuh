@@ -504,8 +504,45 @@ __global__ void __launch_bounds__(CG_THREADS)
         p[t] = fma(beta, p[t], z[t]);
 }
 
+// z = r * d (explicit, for the null-space correction) ; a += s[0]*s[1]*b ; a += s[0]*s[1]
+__global__ void __launch_bounds__(CG_THREADS)
+    cggo_z_kernel(double *__restrict__ z, const double *__restrict__ r, const double *__restrict__ d, int64_t n, const CgScalars *sc)
+{
+    if (sc->done) return;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) z[t] = r[t] * d[t];
+}
+__global__ void __launch_bounds__(CG_THREADS)
+    cggo_sum2_kernel(const double *__restrict__ a, const double *__restrict__ b, int64_t n, double *out, const CgScalars *sc,
+                     double *partials, unsigned *counter)
+{
+    __shared__ double red[33];
+    if (sc->done) return;
+    double s = 0.0;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) s = fma(a[t], b ? b[t] : 1.0, s);
+    const double bs = block_reduce(s, red);
+    grid_reduce(bs, partials, counter, red, [=](double tot) { *out = tot; });
+}
+// a += smean * (*dot) * (b ? b : 1)   (hmholtz.f:713-718 with b = dssum(bm1), :750-751 with b absent)
+__global__ void __launch_bounds__(CG_THREADS)
+    cggo_mcor_kernel(double *__restrict__ a, const double *__restrict__ b, double smean, const double *dot, int64_t n, const CgScalars *sc)
+{
+    if (sc->done) return;
+    const double rmean = smean * *dot;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+        a[t] = b ? fma(rmean, b[t], a[t]) : a[t] + rmean;
+}
+__global__ void __launch_bounds__(CG_THREADS)
+    negmax_kernel(const double *__restrict__ a, int64_t n, double *out, double *partials, unsigned *counter)
+{
+    __shared__ double red[33];
+    double m = -1.0e300;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) m = fmax(m, -a[t]);
+    const double b = block_reduce<true>(m, red);
+    grid_reduce<true>(b, partials, counter, red, [=](double tot) { *out = tot; });  // max(-a) = -min a
+}
+
 // :761-791 scalar bookkeeping and the convergence test (single thread).
-__global__ void cggo_check_kernel(CgScalars *sc, double vol, double tin, int istep, int niter_max, double *hist)
+__global__ void cggo_check_kernel(CgScalars *sc, double vol, double tin, int istep, int niter_max, double *hist, double param22)
 {
     if (sc->done) return;
     const int iter = sc->it + 1;
@@ -515,7 +552,10 @@ __global__ void cggo_check_kernel(CgScalars *sc, double vol, double tin, int ist
     sc->rbn2 = rbn2;
     if (iter == 1) {
         sc->rbn0 = rbn2;
-        sc->tol = (tin < 0) ? fabs(tin) * rbn2 : fabs(tin);  // :673-679,:765
+        double tol = fabs(tin);                               // :673
+        if (param22 < 0) tol = fabs(param22) * rbn2;          // :764
+        if (tin < 0) tol = fabs(tin) * rbn2;                  // :765
+        sc->tol = tol;
     }
     hist[3 * (iter - 1) + 0] = sc->rtz1;
     hist[3 * (iter - 1) + 1] = rbn2;
@@ -612,8 +652,8 @@ inline void setprec_run(double *dpc, const double *h1, const double *h2, int nel
 }
 
 // Returns niterhm.  hist_host (may be NULL): 3 doubles per executed iteration (rtz1, rbn2, rho).
-// Not supported (documented in DESIGN.md): the all-Neumann null-space correction (ifmcor, :705-720)
-// and the 'PRES' branches (:641-657, :731-746).
+// Includes the all-Neumann null-space correction (ifmcor, :705-720, :749-752).  Not provided: the 'PRES' branches
+// (:641-657 forward to hmh_gmres, which is exported separately; :731-746 adds crs_solve_h1).
 inline int cggo_run(const CggoArgs &a, double tin, int maxit, double *hist_host)
 {
     Ctx &c = ctx();
@@ -658,20 +698,63 @@ inline int cggo_run(const CggoArgs &a, double tin, int maxit, double *hist_host)
     NEKB_CUDA(cudaStreamSynchronize(s));
     if (fmax == 0.0) return 0;  // :700-701
 
+    // :705-720 non-trivial null space: h2 = 0 everywhere and no Dirichlet node
+    negmax_kernel<<<grid, CG_THREADS, 0, s>>>(a.mask, n, &sc->work[3], c.partials.p, &sc->counter[0]);
+    NEKB_LAUNCHED();
+    comm_allreduce_max(&sc->work[3], 1);
+    double skmin = 0.0;
+    NEKB_CUDA(cudaMemcpyAsync(&skmin, &sc->work[3], sizeof(double), cudaMemcpyDeviceToHost, s));
+    NEKB_CUDA(cudaStreamSynchronize(s));
+    skmin = -skmin;  // glmin(mask)
+    const bool ifmcor = skmin > 0.0 && h2max == 0.0;
+    double smean = 0.0;
+    DevBuf<double> &bsum = c.work[5];
+    const bool explicit_z = schwarz || ifmcor;
+    if (ifmcor) {
+        NEKB_REQUIRE(c.bm1.n >= (size_t)n, "cggo: bm1 must be registered for the null-space correction");
+        z.ensure(n), bsum.ensure(n);
+        cggo_sum2_kernel<<<grid, CG_THREADS, 0, s>>>(c.bm1.p, nullptr, n, &sc->work[3], sc, c.partials.p, &sc->counter[0]);
+        NEKB_LAUNCHED();
+        comm_allreduce_sum(&sc->work[3], 1);
+        double vsum = 0.0;
+        NEKB_CUDA(cudaMemcpyAsync(&vsum, &sc->work[3], sizeof(double), cudaMemcpyDeviceToHost, s));
+        NEKB_CUDA(cudaStreamSynchronize(s));
+        smean = -1.0 / vsum;                                                   // :711
+        cggo_sum2_kernel<<<grid, CG_THREADS, 0, s>>>(r.p, a.mult, n, &sc->work[3], sc, c.partials.p, &sc->counter[0]);  // :712
+        NEKB_LAUNCHED();
+        comm_allreduce_sum(&sc->work[3], 1);
+        NEKB_CUDA(cudaMemcpyAsync(bsum.p, c.bm1.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+        gs_op(a.gs_handle, bsum.p, 1, nullptr);                                // :713-714
+        cggo_mcor_kernel<<<grid, CG_THREADS, 0, s>>>(r.p, bsum.p, smean, &sc->work[3], n, sc);  // :715
+        NEKB_LAUNCHED();
+    }
+
     int launched = 0, result = -1;
     const int batch = 8;  // iterations enqueued between two looks at the convergence flag
     while (result < 0) {
         for (int b = 0; b < batch; b++) {
-            if (schwarz) {  // :737-745 (fields other than 'PRES': no coarse correction)
-                fdm_h1_apply(z.p, r.p, d.p, a.mask, a.nel, a.gs_handle);
+            if (explicit_z) {
+                if (schwarz)  // :737-745 (fields other than 'PRES': no coarse correction)
+                    fdm_h1_apply(z.p, r.p, d.p, a.mask, a.nel, a.gs_handle);
+                else {
+                    cggo_z_kernel<<<grid, CG_THREADS, 0, s>>>(z.p, r.p, d.p, n, sc);
+                    NEKB_LAUNCHED();
+                }
+                if (ifmcor) {  // :749-752 rmean = smean*glsc2(z,bm1) ; z += rmean
+                    cggo_sum2_kernel<<<grid, CG_THREADS, 0, s>>>(z.p, c.bm1.p, n, &sc->work[3], sc, c.partials.p, &sc->counter[0]);
+                    NEKB_LAUNCHED();
+                    comm_allreduce_sum(&sc->work[3], 1);
+                    cggo_mcor_kernel<<<grid, CG_THREADS, 0, s>>>(z.p, nullptr, smean, &sc->work[3], n, sc);
+                    NEKB_LAUNCHED();
+                }
                 cggo_dots_z_kernel<<<grid, CG_THREADS, 0, s>>>(r.p, z.p, a.mult, a.binv, n, sc, c.partials.p + 2 * CG_PART_STRIDE);
             } else
                 cggo_dots_kernel<<<grid, CG_THREADS, 0, s>>>(r.p, d.p, a.mult, a.binv, n, sc, c.partials.p + 2 * CG_PART_STRIDE);
             NEKB_LAUNCHED();
             comm_allreduce_sum(&sc->work[0], 2);
-            cggo_check_kernel<<<1, 1, 0, s>>>(sc, a.vol, tin, a.istep, niter, c.hist.p);
+            cggo_check_kernel<<<1, 1, 0, s>>>(sc, a.vol, tin, a.istep, niter, c.hist.p, c.param[22]);
             NEKB_LAUNCHED();
-            if (schwarz)
+            if (explicit_z)
                 cggo_pupdate_z_kernel<<<grid, CG_THREADS, 0, s>>>(p.p, z.p, n, sc);
             else
                 cggo_pupdate_kernel<<<grid, CG_THREADS, 0, s>>>(p.p, r.p, d.p, n, sc);

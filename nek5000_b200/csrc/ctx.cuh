@@ -72,6 +72,8 @@ struct Ctx {
     int istep = 0;
     double volvm1 = 0.0, voltm1 = 0.0;
     int niterhm = 0;
+    double param[201] = {0};       // INPUT param(1:200) entries the path reads (18, 21, 22); 1-based
+    DevBuf<double> binvm1, bintm1; // MASS binvm1 / bintm1 for hmholtz
 
     // gs handles ---------------------------------------------------------------------------------
     std::vector<GsMap> gs;

@@ -404,6 +404,23 @@ int nekb_set_step_info(int istep, double volvm1, double voltm1)
     ctx().istep = istep, ctx().volvm1 = volvm1, ctx().voltm1 = voltm1;
     return 0;
 }
+int nekb_set_param(int idx, double value)
+{
+    return guard([&] {
+        NEKB_REQUIRE(idx >= 1 && idx <= 200, "nekb_set_param: index out of range (1..200)");
+        ctx().param[idx] = value;
+    });
+}
+int nekb_set_binv(const double *binvm1, const double *bintm1)
+{
+    return guard([&] {
+        require_init();
+        Ctx &c = ctx();
+        if (binvm1) c.binvm1.upload(binvm1, (size_t)c.nelv * c.nxyz, c.stream);
+        if (bintm1) c.bintm1.upload(bintm1, (size_t)c.nelt * c.nxyz, c.stream);
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
 int nekb_niterhm(void) { return ctx().niterhm; }
 
 // ---------------------------------------------------------------------------------------------------- gs (device API)
@@ -692,6 +709,41 @@ void cggo_(double *x, const double *f, const double *h1, const double *h2, const
                    field_handle(), nel, vol, c.istep};
         c.niterhm = cggo_run(a, *tin, *maxit, nullptr);
         NEKB_CUDA(cudaMemcpyAsync(x, c.stage[0].p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+void hmholtz_(const char *name, double *u, double *rhs, const double *h1, const double *h2, const double *mask, const double *mult,
+              const int *imsh, const double *tli, const int *maxit, const int *isd, size_t name_len)
+{
+    (void)isd;
+    guard_fortran("hmholtz", [&] {
+        require_init();
+        Ctx &c = ctx();
+        NEKB_REQUIRE(!(name_len >= 4 && !strncmp(name, "PRES", 4)), "hmholtz: 'PRES' goes through hmh_gmres (cggo :641-657)");
+        const int nel = *imsh == 1 ? c.nelv : c.nelt;
+        const size_t n = (size_t)nel * c.nxyz;
+        const DevBuf<double> &binv = *imsh == 1 ? c.binvm1 : (c.bintm1.n ? c.bintm1 : c.binvm1);
+        NEKB_REQUIRE(binv.n >= n, "hmholtz: binvm1/bintm1 not registered (nekb_set_binv)");
+        const double vol = *imsh == 1 ? c.volvm1 : c.voltm1;
+        NEKB_REQUIRE(vol > 0.0, "volvm1/voltm1 not registered (nekb_set_step_info)");
+        for (int k = 0; k < 6; k++) c.stage[k].ensure(n);
+        const double *src[5] = {rhs, h1, h2, mask, mult};
+        for (int k = 0; k < 5; k++)
+            NEKB_CUDA(cudaMemcpyAsync(c.stage[k + 1].p, src[k], n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        double *d_rhs = c.stage[1].p;
+        const double *d_h1 = c.stage[2].p, *d_h2 = c.stage[3].p, *d_mask = c.stage[4].p, *d_mult = c.stage[5].p;
+        gs_op(field_handle(), d_rhs, 1, d_mask);                                   // :55-56
+        double tol = fabs(*tli);
+        if (c.param[22] == 0.0 || c.istep <= 10) {                                  // :59-60
+            bool ifh2 = false;
+            for (size_t t = 0; t < n && !ifh2; t++) ifh2 = h2[t] != 0.0;
+            tol = chktcg1_dev(tol, d_rhs, d_h1, ifh2 ? d_h2 : nullptr, d_mask, d_mult, binv.p, nel, vol);
+        }
+        if (*tli < 0) tol = *tli;                                                  // :62
+        CggoArgs a{c.stage[0].p, d_rhs, d_h1, d_h2, d_mask, d_mult, binv.p, field_handle(), nel, vol, c.istep};
+        c.niterhm = cggo_run(a, tol, *maxit, nullptr);
+        NEKB_CUDA(cudaMemcpyAsync(u, c.stage[0].p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaMemcpyAsync(rhs, d_rhs, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
         NEKB_CUDA(cudaStreamSynchronize(c.stream));
     });
 }

@@ -34,7 +34,7 @@ __all__ = [
     "niterhm", "setvert3d", "setupds", "fgslib_gs_setup", "fgslib_gs_op", "fgslib_gs_op_many", "fgslib_gs_op_fields",
     "fgslib_gs_free", "gs_get_map", "gs_info", "dssum", "dsop", "axhelm", "setprec", "cggo", "cggos", "axhm1", "glsc3",
     "DevArray", "set_transport_torch", "comm_init_torch", "h1mg_setup", "h1mg_solve", "h1mg_info", "h1mg_get", "h1mg_free",
-    "set_pressure_state", "hmh_gmres", "fdm_h1_setup", "set_kfldfdm", "set_fdm_prec_h1b", "fdm_h1", "fdm_h1_get",
+    "set_pressure_state", "hmh_gmres", "hmholtz", "set_param", "set_binv", "fdm_h1_setup", "set_kfldfdm", "set_fdm_prec_h1b", "fdm_h1", "fdm_h1_get",
 ]
 
 _state = {"lx1": 0, "nelt": 0, "np": 1, "keep": []}
@@ -239,6 +239,24 @@ def cggo(x, f, h1, h2, mask, mult, imsh, tin, maxit, isd, binv, name: str = "VEL
     lib().cggo_(_ptr(x), _ptr(f), _ptr(h1), _ptr(h2), _ptr(mask), _ptr(mult), _i(imsh), C.byref(C.c_double(tin)), _i(maxit),
                 _i(isd), _ptr(binv), nm, 4)
     return niterhm()
+
+
+def hmholtz(name: str, u, rhs, h1, h2, mask, mult, imsh: int, tli: float, maxit: int, isd: int = 1) -> int:
+    """core/hmholtz.f:2 hmholtz(name,u,rhs,h1,h2,mask,mult,imsh,tli,maxit,isd); rhs is dssum'ed and masked in place."""
+    nm = name.ljust(4).encode()
+    lib().hmholtz_(nm, _ptr(u), _ptr(rhs), _ptr(h1), _ptr(h2), _ptr(mask), _ptr(mult), _i(imsh), C.byref(C.c_double(tli)),
+                   _i(maxit), _i(isd), 4)
+    return niterhm()
+
+
+def set_param(idx: int, value: float) -> None:
+    check(lib().nekb_set_param(idx, float(value)))
+
+
+def set_binv(binvm1, bintm1=None) -> None:
+    a = np.ascontiguousarray(binvm1, dtype=np.float64)
+    b = None if bintm1 is None else np.ascontiguousarray(bintm1, dtype=np.float64)
+    check(lib().nekb_set_binv(_ptr(a), None if b is None else _ptr(b)))
 
 
 def cggos(u1, rhs1, x1, rmult, binv, tin: float, maxit: int, bpname: str = "bp5") -> int:

@@ -263,6 +263,48 @@ def test_cggo_iterations_and_solution(nek, ifh2):
     nek.fgslib_gs_free(h)
 
 
+def test_cggo_null_space_correction_and_hmholtz_wrapper(nek):
+    """cggo's ifmcor branch (hmholtz.f:705-720, :749-752: all-Neumann, h2 = 0) and the hmholtz wrapper (:2-69: dssum +
+    mask of the right-hand side in place, chktcg1, cggo with binvm1)."""
+    case = oracle.Case(3, 2, 2, nx=8, dirichlet=(0, 0, 0, 0, 0, 0), deform=0.04)
+    register(nek, case)
+    h, _ = nek.setupds(8, case.nel, case.vertex)
+    nek.set_field_handle(1, h)
+    nek.set_ifield(1)
+    bm1 = case.bm1()
+    nek.set_step_info(1, float(bm1.sum()))
+    rng = np.random.default_rng(9)
+    h1, h2 = np.full(case.n, 1.1), np.zeros(case.n)
+    xe = case.dssum(rng.standard_normal(case.n)) * case.mult
+    f = case.dssum(case.axhelm(xe, h1, h2))
+    assert case.mask.min() == 1.0
+    _, itfull, href = case.cggo(f, h1, h2, tin=1e-30, maxit=60, istep=1, history=True)
+    for k in (10, 31):
+        tin = float(np.sqrt(href[k, 1] * href[k + 1, 1]))
+        xref, itref = case.cggo(f, h1, h2, tin=tin, maxit=200, istep=1)
+        x = np.zeros(case.n)
+        it = nek.cggo(x, f, h1, h2, case.mask, case.mult, 1, tin, 200, 1, case.binv(), "VELX")
+        assert it == itref
+        assert relmax(x, xref) <= TOL_HIST
+    # hmholtz: Dirichlet case, un-assembled right-hand side
+    case = oracle.Case(3, 2, 2, nx=8, deform=0.04)
+    register(nek, case)
+    bm1 = case.bm1()
+    nek.set_step_info(1, float(bm1.sum()))
+    nek.set_binv(case.binv())
+    nek.set_param(22, 0.0)
+    h2 = np.full(case.n, 0.4)
+    rhs = bm1 * rng.standard_normal(case.n)
+    rhs_ref = case.dssum(rhs) * case.mask
+    for tli in (1e-7, -1e-5):
+        xref, itref = case.cggo(rhs_ref, h1, h2, tin=tli, maxit=300, istep=1)
+        u, r = np.zeros(case.n), rhs.copy()
+        it = nek.hmholtz("VELX", u, r, h1, h2, case.mask, case.mult, 1, tli, 300, 1)
+        assert relmax(r, rhs_ref) <= TOL_APPLY            # rhs is assembled and masked in place
+        assert it == itref and relmax(u, xref) <= 1e-8
+    nek.fgslib_gs_free(h)
+
+
 # ------------------------------------------------------------------------------------------------- device-built BP5 case
 @pytest.mark.parametrize("deform", [0.0, 0.05])
 def test_bp5_case_matches_oracle(deform):
