@@ -395,3 +395,20 @@ def test_multi_gpu_bp5_matches_single_domain_oracle(world):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("MGPU-OK") == world
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_multi_gpu_h1mg_and_gmres_match_single_domain_oracle(world):
+    """Element-partitioned pressure preconditioner + GMRES over NCCL against the undivided numpy oracle."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(29540 + world), os.path.join(here, "_mgpu_hsmg_worker.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("MGPU-HSMG-OK") == world
