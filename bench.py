@@ -25,6 +25,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) out of it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("NCCL_DEBUG_FILE"):
+    os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
 
 LX1 = 8
 NDOF = (LX1 - 1) ** 3            # DOF per element as the reference counts them (N^3, bp5.usr:380)

@@ -279,6 +279,23 @@ int nekb_h1mg_get(const char *which, int level, double *host_out, size_t n_doubl
 int nekb_crs_set_tolerance(double tol, int maxit);
 void nekb_h1mg_free(void);
 
+/* Pn-Pn-2 pressure preconditioner: core/hsmg.f:22-47 hsmg_setup, :1376-1602 hsmg_solve(e,r) and its top level
+ * core/fasts.f:2-94 local_solves_fdm(u,v), on the lx2 = lx1-2 Gauss grid (arrays of (lx1-2)^3*nelv doubles).
+ * The levels below the top, the coarse solve and all exchanges are built here exactly as for h1mg; the top-level
+ * fast-diagonalisation data is what gen_fast (core/fast3d.f) leaves in common /fastd/ and is REGISTERED, not recomputed:
+ * df(lx1^3,nelv), sr/ss/st(2*lx1^2,nelv) (S in the first half of each, column-major; host arrays).  That setup
+ * depends on the E operator of the Pn-Pn-2 splitting and stays with the host program.
+ * nelgv: global element count (ortho, core/navier1.f:223).  fbc, xm1.., vertex as for nekb_h1mg_setup. */
+int nekb_hsmg_setup(const int *fbc, const double *xm1, const double *ym1, const double *zm1, const int64_t *vertex,
+                    int nelv, int null_space, int64_t nelgv, const double *df, const double *sr, const double *ss,
+                    const double *st);
+int nekb_hsmg_solve_dev(double *e_dev, const double *r_dev);
+int nekb_local_solves_fdm_dev(double *u_dev, const double *v_dev);
+void hsmg_solve_(double *e, const double *r);
+void local_solves_fdm_(double *u, const double *v);
+/* Host copies for parity tests: "J" (level -> level+1), "owt" (top-level overlap weight), "swt", "mask". */
+int nekb_hsmg_get(const char *which, int level, double *host_out, size_t n_doubles);
+
 /* Single-level Schwarz / FDM preconditioner on the lx1^3 tiles (core/FDMH1).
  * nekb_fdm_h1_setup = set_fdm_prec_h1A (core/hmholtz.f:1028-1220) for one field: face_internal[6*nel] is 1 where cbc is
  * 'E  ','P  ','p  ' (faces r-,r+,s-,s+,t-,t+), mask the field's Dirichlet mask, xm1..zm1 /gxyz/ (all host arrays).

@@ -250,7 +250,10 @@ struct MgLevel {
     DevBuf<double> Stab, lamtab, eps;
     DevBuf<int32_t> sidx;       // [nel][3] rows of Stab / lamtab
     int ntab = 0;
-    DevBuf<double> r, e, f_own, f_sum;
+    DevBuf<double> r, e, w, f_own, f_sum;
+    int lay = 1;                // overlap layer (see mg_mask_faces_kernel)
+    DevBuf<double> dfull;       // optional registered diagonal [nel][nl^3] (Pn-Pn-2 top level)
+    DevBuf<double> owt;         // optional overlap weight applied without a level dssum (do_weight_op)
 };
 
 struct CrsSolver {
@@ -270,6 +273,8 @@ struct CrsSolver {
 
 struct H1mg {
     bool ready = false;
+    bool pnpn2 = false;          // hsmg_setup / hsmg_solve (pressure on the lx1-2 Gauss grid) instead of h1mg_*
+    double ntotg = 0.0;          // lx2^3 * nelgv for ortho (pnpn2 with a null space)
     int lmax = 0, nel = 0, lx1 = 0;
     std::vector<MgLevel> lev;
     CrsSolver crs;
@@ -281,11 +286,60 @@ inline H1mg &h1mg()
     static H1mg m;
     return m;
 }
-inline void crs_release_graph()
+inline H1mg &hsmg2()  // the Pn-Pn-2 instance (hsmg_setup / hsmg_solve)
 {
-    CrsSolver &k = h1mg().crs;
+    static H1mg m;
+    return m;
+}
+inline void crs_release_graph(H1mg &M)
+{
+    CrsSolver &k = M.crs;
     if (k.graph) cudaGraphExecDestroy(k.graph);
     k.graph = nullptr;
+}
+inline void crs_release_graph()
+{
+    crs_release_graph(h1mg());
+    crs_release_graph(hsmg2());
+}
+
+// core/hsmg.f:1604-1664 hsmg_setup_mg_nx (Pn-Pn-2: lx2 = lx1-2, no clamp of the middle level)
+inline std::vector<int> mg_orders_pnpn2(int lx1)
+{
+    static const int mgn2[10] = {1, 2, 2, 2, 2, 3, 3, 5, 5, 5};
+    const int lmax = lx1 == 4 ? 2 : 3, lx2 = lx1 - 2;
+    int mglx2 = 2 * (lx2 / 4) + 1;
+    if (lx1 == 5) mglx2 = 3;
+    if (lx1 <= 10) mglx2 = mgn2[(lx1 < 10 ? lx1 : 10) - 1];
+    if (lx1 == 8) mglx2 = 3;
+    std::vector<int> nx = {1, mglx2, mglx2 + 1};
+    nx[lmax - 1] = lx1 - 1;
+    nx.resize(lmax);
+    return nx;
+}
+
+// Gauss-Legendre points on (-1,1), ascending (core/speclib.f ZWGL): Newton on P_n
+inline std::vector<double> gauss_points(int n)
+{
+    std::vector<double> z(n);
+    const long double pi = 3.141592653589793238462643383279502884L;
+    for (int i = 0; i < n; i++) {
+        long double x = -cosl(pi * (i + 0.75L) / (n + 0.5L));
+        for (int it = 0; it < 100; it++) {
+            long double p0 = 1.0L, p1 = x;
+            for (int k = 2; k <= n; k++) {
+                const long double p2 = ((2 * k - 1) * x * p1 - (k - 1) * p0) / k;
+                p0 = p1, p1 = p2;
+            }
+            if (n == 1) p0 = 1.0L, p1 = x;
+            const long double dp = n * (x * p1 - p0) / (x * x - 1.0L);
+            const long double dx = p1 / dp;
+            x -= dx;
+            if (fabsl(dx) < 1e-19L) break;
+        }
+        z[i] = (double)x;
+    }
+    return z;
 }
 
 // ================================================================================================ kernels
@@ -296,21 +350,26 @@ inline void crs_release_graph()
 // f_own = f_sum = r on the first interior layer of every face.
 __global__ void __launch_bounds__(256)
     mg_mask_faces_kernel(double *__restrict__ r, const double *__restrict__ mask, double *__restrict__ f_own,
-                         double *__restrict__ f_sum, int nh, int64_t n)
+                         double *__restrict__ f_sum, int nh, int lay, int64_t n)
 {
-    const int n2 = nh * nh, n3 = n2 * nh;
+    // lay = 1: GLL levels (the layer next to the shared element boundary, hsmg_extrude l2 = 2);
+    // lay = 0: the Pn-Pn-2 pressure grid, whose outermost Gauss points are interior to the element (dface_ext, fasts.f:214)
+    const int n2 = nh * nh, n3 = n2 * nh, lo = lay, hi = nh - 1 - lay;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t e = t / n3;
         const int q = (int)(t - e * n3), i = q % nh, j = (q / nh) % nh, k = q / n2;
-        const double v = r[t] * mask[t];
-        r[t] = v;
+        double v = r[t];
+        if (mask) {
+            v *= mask[t];
+            r[t] = v;
+        }
         double *fo = f_own + e * 6 * n2, *fs = f_sum + e * 6 * n2;
-        if (i == 1) fo[0 * n2 + k * nh + j] = v, fs[0 * n2 + k * nh + j] = v;
-        if (i == nh - 2) fo[1 * n2 + k * nh + j] = v, fs[1 * n2 + k * nh + j] = v;
-        if (j == 1) fo[2 * n2 + k * nh + i] = v, fs[2 * n2 + k * nh + i] = v;
-        if (j == nh - 2) fo[3 * n2 + k * nh + i] = v, fs[3 * n2 + k * nh + i] = v;
-        if (k == 1) fo[4 * n2 + j * nh + i] = v, fs[4 * n2 + j * nh + i] = v;
-        if (k == nh - 2) fo[5 * n2 + j * nh + i] = v, fs[5 * n2 + j * nh + i] = v;
+        if (i == lo) fo[0 * n2 + k * nh + j] = v, fs[0 * n2 + k * nh + j] = v;
+        if (i == hi) fo[1 * n2 + k * nh + j] = v, fs[1 * n2 + k * nh + j] = v;
+        if (j == lo) fo[2 * n2 + k * nh + i] = v, fs[2 * n2 + k * nh + i] = v;
+        if (j == hi) fo[3 * n2 + k * nh + i] = v, fs[3 * n2 + k * nh + i] = v;
+        if (k == lo) fo[4 * n2 + j * nh + i] = v, fs[4 * n2 + j * nh + i] = v;
+        if (k == hi) fo[5 * n2 + j * nh + i] = v, fs[5 * n2 + j * nh + i] = v;
     }
 }
 
@@ -323,7 +382,7 @@ __global__ void __launch_bounds__(NL *NL *EPB)
     mg_fdm_kernel(const double *__restrict__ r, double *__restrict__ e, const double *f_in_sum, const double *f_in_own,
                   double *f_out_own, double *f_out_sum,  // may alias the inputs (each element touches only its own faces)
                   const double *__restrict__ Stab, const double *__restrict__ lamtab, const int32_t *__restrict__ sidx,
-                  const double *__restrict__ eps, int nel)
+                  const double *__restrict__ eps, const double *__restrict__ dfull, int nel)
 {
     constexpr int NH = NL - 2, NLP = (NL % 2 == 0) ? NL + 1 : NL, L2 = NL * NL, H2 = NH * NH, H3 = NH * NH * NH;
     constexpr int TILE = NL * NL * NLP;
@@ -340,7 +399,7 @@ __global__ void __launch_bounds__(NL *NL *EPB)
         for (int d = 0; d < 3; d++) {
             const int row = sidx[(size_t)el * 3 + d];
             for (int t = tl; t < L2; t += L2) s_S[es][d][t] = Stab[(size_t)row * L2 + t];
-            if (tl < NL) s_lam[es][d][tl] = lamtab[(size_t)row * NL + tl];
+            if (tl < NL) s_lam[es][d][tl] = dfull ? 0.0 : lamtab[(size_t)row * NL + tl];
         }
         for (int t = tl; t < TILE; t += L2) T[t] = 0.0;
     }
@@ -381,13 +440,17 @@ __global__ void __launch_bounds__(NL *NL *EPB)
                 for (int i = 0; i < NL; i++) s = fma(S[i * NL + a], in[i], s);
                 out[a] = s;
             }
-            if (d == 2) {  // last forward pass: apply D = 1/(lam_r + lam_s + lam_t) (hsmg.f:740-752)
+            if (d == 2 && dfull == nullptr) {  // last forward pass: apply D = 1/(lam_r + lam_s + lam_t) (hsmg.f:740-752)
                 const double ep = eps[el], lrs = s_lam[es][0][p] + s_lam[es][1][q];
 #pragma unroll
                 for (int a = 0; a < NL; a++) {
                     const double diag = lrs + s_lam[es][2][a];
                     out[a] = diag > ep ? out[a] * (1.0 / diag) : 0.0;
                 }
+            } else if (d == 2) {  // registered diagonal df(lx1^3, e) (common /fastd/, fasts.f:30)
+                const double *de = dfull + (size_t)el * NL * NL * NL;
+#pragma unroll
+                for (int a = 0; a < NL; a++) out[a] *= de[(a * NL + q) * NL + p];
             }
 #pragma unroll
             for (int a = 0; a < NL; a++) T[base + a * stride] = out[a];
@@ -440,21 +503,25 @@ __global__ void __launch_bounds__(NL *NL *EPB)
 // hsmg.f:473-474: e(first interior layer) += neighbour's border solution (f_sum - f_own), r then s then t
 __global__ void __launch_bounds__(256)
     mg_add_overlap_kernel(double *__restrict__ e, const double *__restrict__ f_sum, const double *__restrict__ f_own,
-                          int nh, int64_t n)
+                          const double *__restrict__ wt, int nh, int lay, int64_t n)
 {
-    const int n2 = nh * nh, n3 = n2 * nh;
+    const int n2 = nh * nh, n3 = n2 * nh, lo = lay, hi = nh - 1 - lay;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t el = t / n3;
         const int q = (int)(t - el * n3), i = q % nh, j = (q / nh) % nh, k = q / n2;
-        if (!(i == 1 || i == nh - 2 || j == 1 || j == nh - 2 || k == 1 || k == nh - 2)) continue;
-        const double *fs = f_sum + el * 6 * n2, *fo = f_own + el * 6 * n2;
+        const bool touched = i == lo || i == hi || j == lo || j == hi || k == lo || k == hi;
+        if (!touched && !wt) continue;
         double v = e[t];
-        if (i == 1) v += fs[0 * n2 + k * nh + j] - fo[0 * n2 + k * nh + j];
-        if (i == nh - 2) v += fs[1 * n2 + k * nh + j] - fo[1 * n2 + k * nh + j];
-        if (j == 1) v += fs[2 * n2 + k * nh + i] - fo[2 * n2 + k * nh + i];
-        if (j == nh - 2) v += fs[3 * n2 + k * nh + i] - fo[3 * n2 + k * nh + i];
-        if (k == 1) v += fs[4 * n2 + j * nh + i] - fo[4 * n2 + j * nh + i];
-        if (k == nh - 2) v += fs[5 * n2 + j * nh + i] - fo[5 * n2 + j * nh + i];
+        if (touched) {
+            const double *fs = f_sum + el * 6 * n2, *fo = f_own + el * 6 * n2;
+            if (i == lo) v += fs[0 * n2 + k * nh + j] - fo[0 * n2 + k * nh + j];
+            if (i == hi) v += fs[1 * n2 + k * nh + j] - fo[1 * n2 + k * nh + j];
+            if (j == lo) v += fs[2 * n2 + k * nh + i] - fo[2 * n2 + k * nh + i];
+            if (j == hi) v += fs[3 * n2 + k * nh + i] - fo[3 * n2 + k * nh + i];
+            if (k == lo) v += fs[4 * n2 + j * nh + i] - fo[4 * n2 + j * nh + i];
+            if (k == hi) v += fs[5 * n2 + j * nh + i] - fo[5 * n2 + j * nh + i];
+        }
+        if (wt) v *= wt[t];  // do_weight_op (fasts.f:415-460) for the level without a dssum of its own
         e[t] = v;
     }
 }
@@ -693,10 +760,10 @@ inline int vec_grid(int64_t n)
 // crs_solve (core/crs_xxt.c:926-965) semantics on the element-local vertex arrays: x = Q A^-1 Q^T b on the unmasked
 // dofs, 0 on masked ones; with a null space the mean over the distinct dofs is removed.  XXT is a direct solver; here
 // the same system is solved by Jacobi-PCG on the device to a relative residual `tol` (documented in DESIGN.md).
-inline void crs_solve_dev(double *x_out, const double *b_in)
+inline void crs_solve_dev(H1mg &MM, double *x_out, const double *b_in)
 {
     Ctx &c = ctx();
-    CrsSolver &k = h1mg().crs;
+    CrsSolver &k = MM.crs;
     cudaStream_t s = c.stream;
     const int64_t n = k.n;
     if (n == 0 && c.nranks <= 1) return;
@@ -852,7 +919,7 @@ inline void launch_fdm_t(MgLevel &L, const double *r, double *e, int nel)
     constexpr int EPB = (NL * NL >= 100) ? 2 : (NL * NL >= 64 ? 3 : 6);
     const int grid = (nel + EPB - 1) / EPB;
     mg_fdm_kernel<NL, EPB><<<grid, NL * NL * EPB, 0, ctx().stream>>>(r, e, L.f_sum.p, L.f_own.p, L.f_own.p, L.f_sum.p, L.Stab.p,
-                                                                     L.lamtab.p, L.sidx.p, L.eps.p, nel);
+                                                                     L.lamtab.p, L.sidx.p, L.eps.p, L.dfull.p, nel);
     NEKB_LAUNCHED();
 }
 inline void launch_fdm(MgLevel &L, const double *r, double *e, int nel)
@@ -876,36 +943,54 @@ inline void mg_schwarz(MgLevel &L, double *r, double *e, int nel)
     Ctx &c = ctx();
     cudaStream_t s = c.stream;
     const int grid = vec_grid(L.n);
-    mg_mask_faces_kernel<<<grid, 256, 0, s>>>(r, L.mask.p, L.f_own.p, L.f_sum.p, L.nh, L.n);
+    mg_mask_faces_kernel<<<grid, 256, 0, s>>>(r, L.mask.p, L.f_own.p, L.f_sum.p, L.nh, L.lay, L.n);
     NEKB_LAUNCHED();
     gs_op(L.gs_face, L.f_sum.p, 1, nullptr);
     launch_fdm(L, r, e, nel);  // consumes (f_sum - f_own), then refills both with the border of the local solutions
     gs_op(L.gs_face, L.f_sum.p, 1, nullptr);
-    mg_add_overlap_kernel<<<grid, 256, 0, s>>>(e, L.f_sum.p, L.f_own.p, L.nh, L.n);
+    mg_add_overlap_kernel<<<grid, 256, 0, s>>>(e, L.f_sum.p, L.f_own.p, L.owt.p, L.nh, L.lay, L.n);
     NEKB_LAUNCHED();
-    gs_op(L.gs, e, 1, L.swt.p);  // hsmg_dssum + h1mg_mask + hsmg_schwarz_wt (+ sigma = 1)
+    if (L.gs >= 0) gs_op(L.gs, e, 1, L.swt.p);  // hsmg_dssum + h1mg_mask + hsmg_schwarz_wt (+ sigma = 1)
 }
 
-inline void h1mg_setup_run(const int *fbc, const double *xm1, const double *ym1, const double *zm1, const int64_t *vertex,
-                           int nel, int null_space)
+// Registered FDM data of the Pn-Pn-2 top level: common /fastd/ df(lx1^3,nelv), sr/ss/st(2*lx1^2,nelv) as gen_fast
+// (core/fast3d.f) leaves them; that setup stays on the host program's side.
+struct FastdArrays {
+    const double *df = nullptr, *sr = nullptr, *ss = nullptr, *st = nullptr;
+    int64_t nelgv = 0;
+};
+
+inline void h1mg_setup_run(H1mg &M, const int *fbc, const double *xm1, const double *ym1, const double *zm1,
+                           const int64_t *vertex, int nel, int null_space, const FastdArrays *fastd = nullptr)
 {
     Ctx &c = ctx();
     cudaStream_t s = c.stream;
-    H1mg &M = h1mg();
-    crs_release_graph();
+    crs_release_graph(M);
+    for (MgLevel &L : M.lev) {  // release the handles of a previous setup
+        if (L.gs >= 0 && L.gs < (int)c.gs.size()) c.gs[L.gs] = GsMap();
+        if (L.gs_face >= 0 && L.gs_face < (int)c.gs.size()) c.gs[L.gs_face] = GsMap();
+    }
     M = H1mg();
     NEKB_REQUIRE(c.have_geom, "h1mg_setup: geometry must be registered first (nekb_set_geom*)");
     ensure_operators();
     const int lx1 = c.nx;
-    const std::vector<int> mg_nx = mg_orders(lx1);
+    const bool pnpn2 = fastd != nullptr;
+    const std::vector<int> mg_nx = pnpn2 ? mg_orders_pnpn2(lx1) : mg_orders(lx1);
     const int lmax = (int)mg_nx.size();
-    M.lmax = lmax, M.nel = nel, M.lx1 = lx1;
+    M.lmax = lmax, M.nel = nel, M.lx1 = lx1, M.pnpn2 = pnpn2;
     M.lev.resize(lmax);
     std::vector<std::vector<double>> ah(lmax), bh(lmax), zh(lmax);
     for (int l = 0; l < lmax; l++) {
         semhat_host(mg_nx[l], ah[l], bh[l], zh[l]);
         M.lev[l].nh = mg_nx[l] + 1;
         M.lev[l].nl = mg_nx[l] + 3;
+        if (pnpn2 && l == lmax - 1) {  // hsmg_setup_semhat (hsmg.f:51-60): the top level lives on the lx1-2 Gauss points
+            M.lev[l].nh = lx1 - 2;
+            M.lev[l].nl = lx1;
+            M.lev[l].lay = 0;
+            zh[l] = gauss_points(lx1 - 2);
+            M.ntotg = (double)fastd->nelgv * (double)(lx1 - 2) * (lx1 - 2) * (lx1 - 2);
+        }
         M.lev[l].n = (int64_t)M.lev[l].nh * M.lev[l].nh * M.lev[l].nh * nel;
     }
     // hsmg_setup_intp (hsmg.f:83-120)
@@ -922,6 +1007,13 @@ inline void h1mg_setup_run(const int *fbc, const double *xm1, const double *ym1,
     for (int l = 0; l < lmax; l++) {
         MgLevel &L = M.lev[l];
         const int nh = L.nh;
+        if (pnpn2 && l == lmax - 1) {  // no dssum, mask or restriction weight on the Gauss grid (hsmg.f:223-226, 1453)
+            L.r.alloc((size_t)L.n), L.e.alloc((size_t)L.n), L.w.alloc((size_t)L.n);
+            std::vector<int64_t> fid = face_ids(nh, nel, vertex);
+            L.gs_face = gs_setup_from_host_ids(fid.data(), (int64_t)fid.size(), nullptr, 0);
+            L.f_own.alloc(fid.size()), L.f_sum.alloc(fid.size());
+            continue;
+        }
         std::vector<int64_t> glo((size_t)L.n);
         setvert3d_host(glo.data(), nh, nel, vertex, c.nranks);
         L.gs = gs_setup_from_host_ids(glo.data(), L.n, nullptr, 0);
@@ -944,7 +1036,7 @@ inline void h1mg_setup_run(const int *fbc, const double *xm1, const double *ym1,
         L.rstr_wt.upload(w.data(), w.size(), s);
         L.mask.upload(mk.data(), mk.size(), s);
         gs_op(L.gs, L.mask.p, 2, nullptr);
-        L.r.alloc((size_t)L.n), L.e.alloc((size_t)L.n);
+        L.r.alloc((size_t)L.n), L.e.alloc((size_t)L.n), L.w.alloc((size_t)L.n);
         if (l >= 1) {
             std::vector<int64_t> fid = face_ids(nh, nel, vertex);
             L.gs_face = gs_setup_from_host_ids(fid.data(), (int64_t)fid.size(), nullptr, 0);
@@ -988,8 +1080,17 @@ inline void h1mg_setup_run(const int *fbc, const double *xm1, const double *ym1,
         }
         DevBuf<double> ld;
         ld.upload(l.data(), l.size(), s);
-        gs_op(M.lev[lmax - 1].gs, ld.p, 1, nullptr);
+        int fine_gs = M.lev[lmax - 1].gs;
+        bool temp_gs = false;
+        if (fine_gs < 0) {  // Pn-Pn-2: swap_lengths sums on the velocity mesh
+            std::vector<int64_t> glo((size_t)(n3 * nel));
+            setvert3d_host(glo.data(), nx, nel, vertex, c.nranks);
+            fine_gs = gs_setup_from_host_ids(glo.data(), n3 * nel, nullptr, 0);
+            temp_gs = true;
+        }
+        gs_op(fine_gs, ld.p, 1, nullptr);
         ld.download(l.data(), l.size(), s);
+        if (temp_gs) c.gs[fine_gs] = GsMap();
         for (int64_t e = 0; e < nel; e++) {
             const double *le = l.data() + e * n3;
             M.ll_host[0 * (size_t)nel + e] = le[at(0, 1, 1)] - M.lm_host[0 * (size_t)nel + e];
@@ -1003,6 +1104,27 @@ inline void h1mg_setup_run(const int *fbc, const double *xm1, const double *ym1,
     // h1mg_setup_fdm -> hsmg_setup_fast (hsmg.f:632-773): de-duplicated 1-D eigen-systems
     for (int l = 1; l < lmax; l++) {
         MgLevel &L = M.lev[l];
+        if (pnpn2 && l == lmax - 1) {  // registered /fastd/ arrays: S = s?(:,1) (column-major lx1 x lx1), D = df
+            const int nl = L.nl;
+            const size_t l2 = (size_t)nl * nl;
+            std::vector<double> Stab((size_t)3 * nel * l2);
+            std::vector<int32_t> sidx((size_t)3 * nel);
+            const double *src[3] = {fastd->sr, fastd->ss, fastd->st};
+            for (int64_t e = 0; e < nel; e++)
+                for (int d = 0; d < 3; d++) {
+                    const double *sm = src[d] + (size_t)e * 2 * l2;
+                    double *dst = Stab.data() + ((size_t)e * 3 + d) * l2;
+                    for (int i = 0; i < nl; i++)
+                        for (int a = 0; a < nl; a++) dst[(size_t)i * nl + a] = sm[(size_t)i + (size_t)nl * a];
+                    sidx[(size_t)e * 3 + d] = (int32_t)(e * 3 + d);
+                }
+            L.ntab = 3 * nel;
+            L.Stab.upload(Stab.data(), Stab.size(), s);
+            L.sidx.upload(sidx.data(), sidx.size(), s);
+            L.dfull.upload(fastd->df, (size_t)nel * nl * nl * nl, s);
+            L.lamtab.alloc(1), L.eps.alloc(1);
+            continue;
+        }
         const int nl = L.nl, n = mg_nx[l];
         typedef std::tuple<int, int, double, double, double> Key;
         std::map<Key, int> table;
@@ -1049,7 +1171,15 @@ inline void h1mg_setup_run(const int *fbc, const double *xm1, const double *ym1,
         L.f_sum.upload(ones.data(), nf, s);
         L.e.upload(cnt.data(), cnt.size(), s);
         gs_op(L.gs_face, L.f_sum.p, 1, nullptr);
-        mg_add_overlap_kernel<<<vec_grid(L.n), 256, 0, s>>>(L.e.p, L.f_sum.p, L.f_own.p, nh, L.n);
+        if (pnpn2 && l == lmax - 1) {  // init_weight_op (fasts.f:310-413): 1 / overlap count on the outer Gauss layer
+            mg_add_overlap_kernel<<<vec_grid(L.n), 256, 0, s>>>(L.e.p, L.f_sum.p, L.f_own.p, nullptr, nh, 0, L.n);
+            NEKB_LAUNCHED();
+            cnt = dev_to_host(L.e, (size_t)L.n);
+            for (double &v : cnt) v = 1.0 / v;
+            L.owt.upload(cnt.data(), cnt.size(), s);
+            continue;
+        }
+        mg_add_overlap_kernel<<<vec_grid(L.n), 256, 0, s>>>(L.e.p, L.f_sum.p, L.f_own.p, nullptr, nh, 1, L.n);
         NEKB_LAUNCHED();
         gs_op(L.gs, L.e.p, 1, nullptr);
         cnt = dev_to_host(L.e, (size_t)L.n);
@@ -1129,7 +1259,7 @@ inline void h1mg_solve_dev(double *z, double *rhs)
 {
     Ctx &c = ctx();
     H1mg &M = h1mg();
-    NEKB_REQUIRE(M.ready, "h1mg_solve: nekb_h1mg_setup has not been called");
+    NEKB_REQUIRE(M.ready && !M.pnpn2, "h1mg_solve: nekb_h1mg_setup has not been called");
     cudaStream_t s = c.stream;
     const int nel = M.nel, top = M.lmax - 1;
     mg_schwarz(M.lev[top], rhs, z, nel);                                   // :1890
@@ -1148,7 +1278,7 @@ inline void h1mg_solve_dev(double *z, double *rhs)
             col2_kernel<<<vec_grid(L.n), 256, 0, s>>>(L.r.p, L.mask.p, L.n);
             NEKB_LAUNCHED();
         }
-        crs_solve_dev(L.e.p, L.r.p);
+        crs_solve_dev(M, L.e.p, L.r.p);
         if (L.n) {
             col2_kernel<<<vec_grid(L.n), 256, 0, s>>>(L.e.p, L.mask.p, L.n);
             NEKB_LAUNCHED();
@@ -1158,6 +1288,79 @@ inline void h1mg_solve_dev(double *z, double *rhs)
         mg_tensor3(M.lev[l].e.p, M.lev[l - 1].e.p, nullptr, M.lev[l - 1].J.p, M.lev[l].nh, M.lev[l - 1].nh, false, true, nel);
     mg_tensor3(z, M.lev[top - 1].e.p, nullptr, M.lev[top - 1].J.p, M.lev[top].nh, M.lev[top - 1].nh, false, true, nel);  // :1936-1942
     gs_op(M.lev[top].gs, z, 1, M.lev[top].rstr_wt.p);                       // :1944 dsavg (core/ic.f:1871)
+}
+
+
+// ================================================================================================ hsmg_solve (Pn-Pn-2)
+__global__ void __launch_bounds__(256) mg_sum_kernel(const double *__restrict__ a, int64_t n, double *out, double *partials, unsigned *counter)
+{
+    __shared__ double red[33];
+    double s = 0.0;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) s += a[t];
+    const double b = block_reduce(s, red);
+    grid_reduce(b, partials, counter, red, [=](double tot) { *out = tot; });
+}
+__global__ void __launch_bounds__(256) mg_cadd_dev_kernel(double *__restrict__ a, const double *sum, double scale, int64_t n)
+{
+    const double sh = *sum * scale;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) a[t] += sh;
+}
+
+// local_solves_fdm (core/fasts.f:2-94): e = W * sum_i R_i^T A_i^-1 R_i r on the lx2^3 Gauss grid (param(42) = 0)
+inline void local_solves_fdm_dev(double *e, const double *r)
+{
+    H1mg &M = hsmg2();
+    NEKB_REQUIRE(M.ready && M.pnpn2, "local_solves_fdm: nekb_hsmg_setup has not been called");
+    MgLevel &L = M.lev[M.lmax - 1];
+    mg_schwarz(L, const_cast<double *>(r), e, M.nel);  // no mask on this level: r is not written
+}
+
+// hsmg_solve (core/hsmg.f:1376-1602), additive (if_hybrid = .false., :1447): e = M^-1 r ; r is not modified
+inline void hsmg_solve_dev(double *e, const double *r)
+{
+    Ctx &c = ctx();
+    H1mg &M = hsmg2();
+    NEKB_REQUIRE(M.ready && M.pnpn2, "hsmg_solve: nekb_hsmg_setup has not been called");
+    cudaStream_t s = c.stream;
+    const int nel = M.nel, top = M.lmax - 1;
+    local_solves_fdm_dev(e, r);                                             // :1442
+    const double *rf = r;                                                   // :1477-1480 w := r
+    for (int l = top - 1; l >= 1; l--) {                                    // :1483-1516
+        MgLevel &L = M.lev[l], &Lf = M.lev[l + 1];
+        // hsmg_rstr (:214-226): weights except from the top level, J^T, dssum
+        mg_tensor3(L.r.p, rf, (l + 1 == top) ? nullptr : Lf.rstr_wt.p, L.J.p, L.nh, Lf.nh, true, false, nel);
+        gs_op(L.gs, L.r.p, 1, nullptr);
+        mg_copy_kernel<<<vec_grid(L.n), 256, 0, s>>>(L.w.p, L.r.p, L.n);   // :1495 w := r_l (hsmg_schwarz masks its input)
+        NEKB_LAUNCHED();
+        mg_schwarz(L, L.w.p, L.e.p, nel);                                  // :1498-1503
+        rf = L.r.p;                                                         // :1509-1512 w := r_l
+    }
+    {
+        MgLevel &L = M.lev[0], &Lf = M.lev[1];
+        mg_tensor3(L.r.p, rf, (1 == top) ? nullptr : Lf.rstr_wt.p, L.J.p, L.nh, Lf.nh, true, false, nel);  // :1518-1519
+        if (L.n) {
+            col2_kernel<<<vec_grid(L.n), 256, 0, s>>>(L.r.p, L.mask.p, L.n);  // :1523-1524
+            NEKB_LAUNCHED();
+        }
+        crs_solve_dev(M, L.e.p, L.r.p);                                     // :1529-1530
+        if (L.n) {
+            col2_kernel<<<vec_grid(L.n), 256, 0, s>>>(L.e.p, L.mask.p, L.n);  // :1532-1533
+            NEKB_LAUNCHED();
+        }
+    }
+    for (int l = 1; l < top; l++)                                           // :1535-1548
+        mg_tensor3(M.lev[l].e.p, M.lev[l - 1].e.p, nullptr, M.lev[l - 1].J.p, M.lev[l].nh, M.lev[l - 1].nh, false, true, nel);
+    mg_tensor3(e, M.lev[top - 1].e.p, nullptr, M.lev[top - 1].J.p, M.lev[top].nh, M.lev[top - 1].nh, false, true, nel);  // :1554-1574
+    if (M.crs.null_space) {                                                 // :1596 ortho (core/navier1.f:223-257)
+        NEKB_REQUIRE(M.ntotg > 0, "hsmg_solve: nelgv was not registered");
+        const int64_t n = M.lev[top].n;
+        DevBuf<CrsScalars> &scb = crs_scalars();
+        mg_sum_kernel<<<vec_grid(n), 256, 0, s>>>(e, n, &scb.p->shift, c.partials.p, &scb.p->counter[3]);
+        NEKB_LAUNCHED();
+        comm_allreduce_sum(&scb.p->shift, 1);
+        mg_cadd_dev_kernel<<<vec_grid(n), 256, 0, s>>>(e, &scb.p->shift, -1.0 / M.ntotg, n);
+        NEKB_LAUNCHED();
+    }
 }
 
 }  // namespace nekb

@@ -169,6 +169,7 @@ void nekb_finalize(void)
     bp5case() = Bp5Case();
     crs_release_graph();
     h1mg() = H1mg();
+    hsmg2() = H1mg();
     fdm_h1_state() = FdmH1State();
     gmres_state() = GmresState();
     crs_scalars().release();
@@ -815,7 +816,7 @@ int nekb_h1mg_setup(const int *fbc, const double *xm1, const double *ym1, const 
     return guard([&] {
         require_init();
         NEKB_REQUIRE(nelv >= 0 && nelv <= ctx().nelt, "h1mg_setup: nelv exceeds the registered element count");
-        h1mg_setup_run(fbc, xm1, ym1, zm1, vertex, nelv, null_space);
+        h1mg_setup_run(h1mg(), fbc, xm1, ym1, zm1, vertex, nelv, null_space);
     });
 }
 int nekb_h1mg_solve_dev(double *z_dev, double *rhs_dev)
@@ -856,7 +857,7 @@ int nekb_crs_solve_dev(double *e_dev, const double *r_dev)
     return guard([&] {
         require_init();
         NEKB_REQUIRE(h1mg().ready, "nekb_h1mg_setup has not been called");
-        crs_solve_dev(e_dev, r_dev);
+        crs_solve_dev(h1mg(), e_dev, r_dev);
     });
 }
 int nekb_h1mg_info(int *lmax, int *nh3, int *ntab3, int *crs_iters)
@@ -914,14 +915,83 @@ int nekb_crs_set_tolerance(double tol, int maxit)
 }
 void nekb_h1mg_free(void)
 {
-    H1mg &M = h1mg();
     crs_release_graph();
-    for (MgLevel &L : M.lev) {
-        if (L.gs >= 0 && L.gs < (int)ctx().gs.size()) ctx().gs[L.gs] = GsMap();
-        if (L.gs_face >= 0 && L.gs_face < (int)ctx().gs.size()) ctx().gs[L.gs_face] = GsMap();
+    for (H1mg *M : {&h1mg(), &hsmg2()}) {
+        for (MgLevel &L : M->lev) {
+            if (L.gs >= 0 && L.gs < (int)ctx().gs.size()) ctx().gs[L.gs] = GsMap();
+            if (L.gs_face >= 0 && L.gs_face < (int)ctx().gs.size()) ctx().gs[L.gs_face] = GsMap();
+        }
+        *M = H1mg();
     }
-    M = H1mg();
     gmres_state() = GmresState();
+}
+
+// ---------------------------------------------------------------------------------------------------- hsmg (Pn-Pn-2)
+int nekb_hsmg_setup(const int *fbc, const double *xm1, const double *ym1, const double *zm1, const int64_t *vertex, int nelv,
+                    int null_space, int64_t nelgv, const double *df, const double *sr, const double *ss, const double *st)
+{
+    return guard([&] {
+        require_init();
+        NEKB_REQUIRE(nelv >= 0 && nelv <= ctx().nelt, "hsmg_setup: nelv exceeds the registered element count");
+        NEKB_REQUIRE(df && sr && ss && st, "hsmg_setup: the /fastd/ arrays df, sr, ss, st are required");
+        NEKB_REQUIRE(ctx().nx >= 4, "hsmg_setup: lx1 >= 4 required");
+        FastdArrays f;
+        f.df = df, f.sr = sr, f.ss = ss, f.st = st, f.nelgv = nelgv;
+        h1mg_setup_run(hsmg2(), fbc, xm1, ym1, zm1, vertex, nelv, null_space, &f);
+    });
+}
+int nekb_hsmg_solve_dev(double *e_dev, const double *r_dev)
+{
+    return guard([&] {
+        require_init();
+        hsmg_solve_dev(e_dev, r_dev);
+    });
+}
+int nekb_local_solves_fdm_dev(double *u_dev, const double *v_dev)
+{
+    return guard([&] {
+        require_init();
+        local_solves_fdm_dev(u_dev, v_dev);
+    });
+}
+static void pnpn2_host(const char *who, double *out, const double *in, bool whole)
+{
+    guard_fortran(who, [&] {
+        require_init();
+        Ctx &c = ctx();
+        H1mg &M = hsmg2();
+        NEKB_REQUIRE(M.ready, "nekb_hsmg_setup has not been called");
+        const size_t n = (size_t)M.lev[M.lmax - 1].n;
+        c.stage[0].ensure(n), c.stage[1].ensure(n);
+        NEKB_CUDA(cudaMemcpyAsync(c.stage[1].p, in, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        if (whole)
+            hsmg_solve_dev(c.stage[0].p, c.stage[1].p);
+        else
+            local_solves_fdm_dev(c.stage[0].p, c.stage[1].p);
+        NEKB_CUDA(cudaMemcpyAsync(out, c.stage[0].p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+void hsmg_solve_(double *e, const double *r) { pnpn2_host("hsmg_solve", e, r, true); }
+void local_solves_fdm_(double *u, const double *v) { pnpn2_host("local_solves_fdm", u, v, false); }
+int nekb_hsmg_get(const char *which, int level, double *host_out, size_t n_doubles)
+{
+    return guard([&] {
+        H1mg &M = hsmg2();
+        Ctx &c = ctx();
+        NEKB_REQUIRE(M.ready, "nekb_hsmg_setup has not been called");
+        NEKB_REQUIRE(level >= 1 && level <= M.lmax, "nekb_hsmg_get: level out of range");
+        MgLevel &L = M.lev[level - 1];
+        const std::string w(which);
+        const DevBuf<double> *b = nullptr;
+        if (w == "J") b = &L.J;
+        else if (w == "owt") b = &L.owt;
+        else if (w == "swt") b = &L.swt;
+        else if (w == "mask") b = &L.mask;
+        NEKB_REQUIRE(b != nullptr && b->n > 0, std::string("nekb_hsmg_get: unknown or empty array '") + which + "'");
+        NEKB_REQUIRE(n_doubles >= b->n, "nekb_hsmg_get: buffer too small");
+        b->download(host_out, b->n, c.stream);
+    });
 }
 
 int nekb_fdm_h1_setup(const int *face_internal, const double *mask, const double *xm1, const double *ym1, const double *zm1, int nel)
