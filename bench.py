@@ -25,9 +25,15 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) out of it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("NCCL_DEBUG_FILE"):
-    os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+# stdout carries exactly one JSON line: anything a library prints there (e.g. NCCL's version banner when NCCL_DEBUG is set)
+# is sent to stderr by pointing fd 1 at fd 2 for the duration of the run; emit() writes the line to the real stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
 
 LX1 = 8
 NDOF = (LX1 - 1) ** 3            # DOF per element as the reference counts them (N^3, bp5.usr:380)
@@ -135,7 +141,7 @@ def main():
         if rank != 0:
             return
         gd, nt, sample, ms = cpu_leg(max(a.steps, 1), a.warmup, a.m_cpu, target_s=4.0)
-        print(json.dumps({"impl": "reference", "metric": "BP5 Poisson GDOF/s (N=7, FP64)", "value": gd, "unit": "GDOF/s",
+        emit(({"impl": "reference", "metric": "BP5 Poisson GDOF/s (N=7, FP64)", "value": gd, "unit": "GDOF/s",
                           "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                           "data": "synthetic", "config": config,
@@ -272,7 +278,7 @@ def main():
     if a.gpus == 1 and not a.no_cpu:
         gd, nt, sample, _ = cpu_leg(2, 1, a.m_cpu, target_s=6.0)
         out["cpu_baseline"] = {"value": gd, "unit": "GDOF/s", "cores": nt, "kind": "port", "sample": sample}
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -151,6 +151,14 @@ def lib() -> C.CDLL:
     L.nekb_h1mg_get.argtypes = [C.c_char_p, C.c_int, vp, C.c_size_t]
     L.nekb_crs_set_tolerance.argtypes = [C.c_double, C.c_int]
     L.nekb_h1mg_free.restype = None
+    L.nekb_hsmg_setup.argtypes = [i32p, f64p, f64p, f64p, i64p, C.c_int, C.c_int, C.c_int64, f64p, f64p, f64p, f64p]
+    L.nekb_hsmg_solve_dev.argtypes = [vp, vp]
+    L.nekb_local_solves_fdm_dev.argtypes = [vp, vp]
+    L.hsmg_solve_.argtypes = [vp, vp]
+    L.hsmg_solve_.restype = None
+    L.local_solves_fdm_.argtypes = [vp, vp]
+    L.local_solves_fdm_.restype = None
+    L.nekb_hsmg_get.argtypes = [C.c_char_p, C.c_int, vp, C.c_size_t]
     L.nekb_fdm_h1_setup.argtypes = [i32p, f64p, f64p, f64p, f64p, C.c_int]
     L.nekb_set_kfldfdm.argtypes = [C.c_int]
     L.nekb_set_fdm_prec_h1b_dev.argtypes = [vp, vp, vp]

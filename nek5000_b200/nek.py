@@ -34,7 +34,7 @@ __all__ = [
     "niterhm", "setvert3d", "setupds", "fgslib_gs_setup", "fgslib_gs_op", "fgslib_gs_op_many", "fgslib_gs_op_fields",
     "fgslib_gs_free", "gs_get_map", "gs_info", "dssum", "dsop", "axhelm", "setprec", "cggo", "cggos", "axhm1", "glsc3",
     "DevArray", "set_transport_torch", "comm_init_torch", "h1mg_setup", "h1mg_solve", "h1mg_info", "h1mg_get", "h1mg_free",
-    "set_pressure_state", "hmh_gmres", "hmholtz", "set_param", "set_binv", "fdm_h1_setup", "set_kfldfdm", "set_fdm_prec_h1b", "fdm_h1", "fdm_h1_get",
+    "hsmg_setup", "hsmg_solve", "local_solves_fdm", "hsmg_get", "set_pressure_state", "hmh_gmres", "hmholtz", "set_param", "set_binv", "fdm_h1_setup", "set_kfldfdm", "set_fdm_prec_h1b", "fdm_h1", "fdm_h1_get",
 ]
 
 _state = {"lx1": 0, "nelt": 0, "np": 1, "keep": []}
@@ -305,6 +305,32 @@ def h1mg_get(which: str, level: int, n: int) -> np.ndarray:
 
 def h1mg_free() -> None:
     lib().nekb_h1mg_free()
+
+
+def hsmg_setup(fbc, xm1, ym1, zm1, vertex, nelv: int, null_space: bool, nelgv: int, df, sr, ss, st) -> None:
+    """core/hsmg.f:22 hsmg_setup for the Pn-Pn-2 splitting; df, sr, ss, st are common /fastd/ as gen_fast leaves them
+    (df(lx1^3,nelv); s?(2*lx1^2,nelv), S in the first half, column-major)."""
+    f = np.ascontiguousarray(fbc, dtype=np.int32).reshape(-1)
+    v = np.ascontiguousarray(vertex, dtype=np.int64).reshape(-1)
+    a = [np.ascontiguousarray(q, dtype=np.float64).reshape(-1) for q in (xm1, ym1, zm1)]
+    b = [np.ascontiguousarray(q, dtype=np.float64).reshape(-1) for q in (df, sr, ss, st)]
+    check(lib().nekb_hsmg_setup(f, *a, v, nelv, int(null_space), nelgv, *b))
+
+
+def hsmg_solve(e: np.ndarray, r: np.ndarray) -> None:
+    """core/hsmg.f:1376 hsmg_solve(e,r) on the (lx1-2)^3 pressure grid."""
+    lib().hsmg_solve_(_ptr(e), _ptr(r))
+
+
+def local_solves_fdm(u: np.ndarray, v: np.ndarray) -> None:
+    """core/fasts.f:2 local_solves_fdm(u,v)."""
+    lib().local_solves_fdm_(_ptr(u), _ptr(v))
+
+
+def hsmg_get(which: str, level: int, n: int) -> np.ndarray:
+    out = np.zeros(n)
+    check(lib().nekb_hsmg_get(which.encode(), level, _ptr(out), n))
+    return out
 
 
 def fdm_h1_setup(face_internal, mask, xm1, ym1, zm1, nel: int) -> None:

@@ -681,3 +681,144 @@ def cggo_schwarz(case, fdm, f, h1, h2, mask, tin, maxit, istep=1, history=False)
     if history:
         return x, it_done, np.array(hist)
     return x, it_done
+
+
+# ----------------------------------------------------------------------------- hsmg_solve (Pn-Pn-2)
+class Hsmg2:
+    """core/hsmg.f:22-47 hsmg_setup and :1376-1602 hsmg_solve (additive) with the top level of core/fasts.f:2-94
+    (local_solves_fdm, fastdm1, dface_ext, dface_add1si, s_face_to_int, init_weight_op, do_weight_op) on the lx2 = lx1-2
+    Gauss grid.  The top-level FDM data S[e,3,lx1,lx1] (eigenvectors in columns), D[e,lx1,lx1,lx1] is an INPUT, as it is for
+    the library (common /fastd/ produced by gen_fast)."""
+
+    def __init__(self, case, fbc, S, D, null_space=False):
+        self.case = case
+        self.low = H1MG(case, fbc, null_space)      # levels below the top are built by the same routines
+        lx1 = case.nx
+        assert hsmg_orders_pnpn2(lx1)[:-1] == mg_orders(lx1)[:-1]
+        self.lmax = self.low.lmax
+        self.n2 = lx1 - 2
+        self.S, self.D = S, D
+        zgl = np.polynomial.legendre.leggauss(self.n2)[0]
+        self.jtop = intp_matrix(zgl, self.low.zh[self.lmax - 2])   # hsmg_setup_intp with mg_zh(lmax) = zglhat (hsmg.f:57)
+        # init_weight_op (fasts.f:310-413)
+        E, n = case.nel, lx1
+        l = np.zeros((E, n, n, n))
+        l[:, 1:-1, 1:-1, 1], l[:, 1:-1, 1:-1, n - 2] = 1, 1
+        l[:, 1:-1, 1, 1:-1], l[:, 1:-1, n - 2, 1:-1] = 1, 1
+        l[:, 1, 1:-1, 1:-1], l[:, n - 2, 1:-1, 1:-1] = 1, 1
+        self.dface_ext(l)
+        l = _r(case.dssum(l.reshape(-1)), n)
+        self.dface_add1si(l, -1.0)
+        self.s_face_to_int(l, 1.0)
+        cnt = l[:, 1:-1, 1:-1, 1:-1].copy()
+        w = np.ones_like(cnt)
+        outer = np.zeros_like(cnt, dtype=bool)
+        outer[:, :, :, 0] = outer[:, :, :, -1] = outer[:, :, 0, :] = outer[:, :, -1, :] = outer[:, 0, :, :] = outer[:, -1, :, :] = True
+        w[outer] = 1.0 / cnt[outer]
+        self.owt = w.reshape(-1)
+
+    @staticmethod
+    def dface_ext(x):
+        s = slice(1, -1)
+        x[:, s, 0, s], x[:, s, -1, s] = x[:, s, 1, s], x[:, s, -2, s]
+        x[:, s, s, 0], x[:, s, s, -1] = x[:, s, s, 1], x[:, s, s, -2]
+        x[:, 0, s, s], x[:, -1, s, s] = x[:, 1, s, s], x[:, -2, s, s]
+
+    @staticmethod
+    def dface_add1si(x, c):
+        s = slice(1, -1)
+        x[:, s, 0, s] += c * x[:, s, 1, s]
+        x[:, s, -1, s] += c * x[:, s, -2, s]
+        x[:, s, s, 0] += c * x[:, s, s, 1]
+        x[:, s, s, -1] += c * x[:, s, s, -2]
+        x[:, 0, s, s] += c * x[:, 1, s, s]
+        x[:, -1, s, s] += c * x[:, -2, s, s]
+
+    @staticmethod
+    def s_face_to_int(x, c):
+        s = slice(1, -1)
+        x[:, s, 1, s] = c * x[:, s, 0, s] + x[:, s, 1, s]
+        x[:, s, -2, s] = c * x[:, s, -1, s] + x[:, s, -2, s]
+        x[:, s, s, 1] = c * x[:, s, s, 0] + x[:, s, s, 1]
+        x[:, s, s, -2] = c * x[:, s, s, -1] + x[:, s, s, -2]
+        x[:, 1, s, s] = c * x[:, 0, s, s] + x[:, 1, s, s]
+        x[:, -2, s, s] = c * x[:, -1, s, s] + x[:, -2, s, s]
+
+    def local_solves_fdm(self, v):
+        c, n, n2 = self.case, self.case.nx, self.n2
+        v1 = np.zeros((c.nel, n, n, n))
+        v1[:, 1:-1, 1:-1, 1:-1] = _r(v, n2)
+        self.dface_ext(v1)
+        v1 = _r(c.dssum(v1.reshape(-1)), n)
+        self.dface_add1si(v1, -1.0)
+        S = self.S
+        t = np.einsum("eia,ejb,ekc,ekji->ecba", S[:, 0], S[:, 1], S[:, 2], v1) * self.D
+        v1 = np.einsum("eai,ebj,eck,ekji->ecba", S[:, 0], S[:, 1], S[:, 2], t)
+        self.s_face_to_int(v1, -1.0)
+        v1 = _r(c.dssum(v1.reshape(-1)), n)
+        self.s_face_to_int(v1, 1.0)
+        return np.ascontiguousarray(v1[:, 1:-1, 1:-1, 1:-1]).reshape(-1) * self.owt
+
+    def solve(self, r):
+        lo, lm = self.low, self.lmax - 1
+        e = self.local_solves_fdm(r)
+        w = r.copy()
+        el = [None] * self.lmax
+        for l in range(lm - 1, 0, -1):
+            if l + 1 == lm:   # hsmg_rstr from the top: no weights (hsmg.f:220-222), J^T, dssum
+                J = self.jtop
+                rl = lo.dssum(np.ascontiguousarray(np.einsum("ia,jb,kc,ekji->ecba", J, J, J, _r(w, self.n2)).reshape(-1)), l)
+            else:
+                rl = lo.rstr(w, l, True)
+            el[l] = lo.schwarz(rl.copy(), 1.0, l)    # hsmg_schwarz + hsmg_schwarz_wt; masks only its copy
+            w = rl
+        if lm == 1:
+            J = self.jtop
+            r1 = np.ascontiguousarray(np.einsum("ia,jb,kc,ekji->ecba", J, J, J, _r(w, self.n2)).reshape(-1))
+        else:
+            r1 = lo.rstr(w, 0, False)
+        r1 = r1 * lo.mask[0]
+        el[0] = lo.crs_solve(r1) * lo.mask[0]
+        for l in range(1, lm):
+            el[l] = el[l] + lo.intp(el[l - 1], l - 1)
+        J = self.jtop
+        e = e + np.einsum("ai,bj,ck,ekji->ecba", J, J, J, _r(el[lm - 1], lo.nh[lm - 1])).reshape(-1)
+        if lo.null_space:
+            e = e - e.sum() / len(e)
+        return e
+
+
+def hsmg_orders_pnpn2(lx1):
+    """core/hsmg.f:1604-1664 hsmg_setup_mg_nx."""
+    mgn2 = [1, 2, 2, 2, 2, 3, 3, 5, 5, 5]
+    lmax = 2 if lx1 == 4 else 3
+    mglx2 = 2 * ((lx1 - 2) // 4) + 1
+    if lx1 == 5:
+        mglx2 = 3
+    if lx1 <= 10:
+        mglx2 = mgn2[min(lx1, 10) - 1]
+    if lx1 == 8:
+        mglx2 = 3
+    nx = [1, mglx2, mglx2 + 1]
+    nx[lmax - 1] = lx1 - 1
+    return nx[:lmax]
+
+
+def standin_fastd(case, fbc):
+    """A realistic stand-in for common /fastd/ (gen_fast is not restated): the 1-D systems of hsmg_setup_fast1d for the
+    order lx1-3 (so that nl = lx1), with the element lengths of swap_lengths.  Returns S[e,3,lx1,lx1], D[e,lx1,lx1,lx1]."""
+    mg = H1MG(case, fbc)
+    n = case.nx - 3
+    a, b, _, _ = semhat(n)
+    E, nl = case.nel, case.nx
+    S, D = np.zeros((E, 3, nl, nl)), np.zeros((E, nl, nl, nl))
+    for e in range(E):
+        lam = []
+        for d in range(3):
+            s, l = fast1d(int(mg.fbc[e, 2 * d]), int(mg.fbc[e, 2 * d + 1]), mg.ll[d, e], mg.lm[d, e], mg.lr[d, e], a, b, n)
+            S[e, d] = s
+            lam.append(l)
+        diag = lam[0][None, None, :] + lam[1][None, :, None] + lam[2][:, None, None]
+        eps = 1e-5 * (lam[0][1:-1].max() + lam[1][1:-1].max() + lam[2][1:-1].max())
+        D[e] = np.where(diag > eps, 1.0 / np.where(diag > eps, diag, 1.0), 0.0)
+    return S, D

@@ -229,3 +229,42 @@ def test_fdm_h1_and_cggo_schwarz_branch(nek, deform):
     assert it == itref and it < itjac
     assert relmax(x, xref) <= 1e-9 and relmax(x, xe) <= 1e-6
     nek.fgslib_gs_free(h)
+
+
+def fastd_arrays(S, D):
+    """common /fastd/ layout: df(lx1^3,e); s?(lx1*lx1,2,e) with S column-major in the first half, S^T in the second."""
+    E, _, nl, _ = S.shape
+    out = []
+    for d in range(3):
+        a = np.zeros((E, 2, nl * nl))
+        a[:, 0] = S[:, d].transpose(0, 2, 1).reshape(E, -1)   # column-major S(i,a): index i + nl*a
+        a[:, 1] = S[:, d].reshape(E, -1)                      # column-major S^T
+        out.append(a.reshape(-1))
+    return D.reshape(-1), out[0], out[1], out[2]
+
+
+@pytest.mark.parametrize("name,null_space", [("outflow_x_deformed", False), ("channel_like_periodic", False)])
+def test_hsmg_solve_pnpn2(nek, name, null_space):
+    """core/hsmg.f:1376 hsmg_solve and core/fasts.f:2 local_solves_fdm (Pn-Pn-2) with registered /fastd/ data."""
+    dims, lx1, per, pdir, bc, deform = CASES[name]
+    case, _ = make(nek, dims, lx1, per, pdir, bc, deform)
+    fbc = hsmg.box_fbc(case, bc)
+    S, D = hsmg.standin_fastd(case, fbc)
+    ref = hsmg.Hsmg2(case, fbc, S, D, null_space=null_space)
+    df, sr, ss, st = fastd_arrays(S, D)
+    nek.hsmg_setup(fbc, case.xm1, case.ym1, case.zm1, case.vertex, case.nel, null_space, case.nel, df, sr, ss, st)
+    n2 = (lx1 - 2) ** 3 * case.nel
+    top = ref.lmax
+    assert np.array_equal(nek.hsmg_get("owt", top, n2), ref.owt)
+    J = nek.hsmg_get("J", top - 1, (lx1 - 2) * ref.low.nh[top - 2]).reshape(lx1 - 2, -1)
+    assert relmax(J, ref.jtop) <= 1e-13
+    rng = np.random.default_rng(17)
+    v = rng.standard_normal(n2)
+    u = np.zeros(n2)
+    nek.local_solves_fdm(u, v)
+    assert relmax(u, ref.local_solves_fdm(v)) <= TOL
+    e = np.zeros(n2)
+    r = v.copy()
+    nek.hsmg_solve(e, r)
+    assert np.array_equal(r, v)                                   # the residual is not modified
+    assert relmax(e, ref.solve(v)) <= TOL

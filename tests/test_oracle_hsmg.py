@@ -126,3 +126,27 @@ def test_all_neumann_null_space():
     assert it < 40
     d = x - xe
     assert np.abs(d - d.mean()).max() <= 1e-6 * np.abs(xe).max()   # equal up to the constant null-space mode
+
+
+def test_pnpn2_top_level_reduces_to_the_local_fdm_solve_on_one_element():
+    """One element, no neighbours: local_solves_fdm is the interior of S D S^T applied to the zero-extended input and the
+    overlap weights are 1; the whole hsmg_solve is linear."""
+    case = oracle.Case(1, 1, 1, nx=8, dirichlet=(0, 1, 0, 0, 0, 0))
+    fbc = hsmg.box_fbc(case, (2, 1, 2, 2, 2, 2))
+    S, D = hsmg.standin_fastd(case, fbc)
+    h = hsmg.Hsmg2(case, fbc, S, D)
+    assert np.array_equal(h.owt, np.ones(216))
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal(216)
+    ext = np.zeros((1, 8, 8, 8))
+    ext[:, 1:-1, 1:-1, 1:-1] = v.reshape(1, 6, 6, 6)
+    t = np.einsum("eia,ejb,ekc,ekji->ecba", S[:, 0], S[:, 1], S[:, 2], ext) * D
+    z = np.einsum("eai,ebj,eck,ekji->ecba", S[:, 0], S[:, 1], S[:, 2], t)[:, 1:-1, 1:-1, 1:-1].reshape(-1)
+    assert np.abs(h.local_solves_fdm(v) - z).max() <= 1e-13 * np.abs(z).max()
+    case = oracle.Case(3, 2, 2, nx=8, dirichlet=(0, 1, 0, 0, 0, 0), deform=0.02)
+    fbc = hsmg.box_fbc(case, (2, 1, 2, 2, 2, 2))
+    h = hsmg.Hsmg2(case, fbc, *hsmg.standin_fastd(case, fbc))
+    cnt = 1.0 / h.owt
+    assert np.array_equal(cnt, np.rint(cnt)) and cnt.max() == 4 and cnt.min() == 1
+    r1, r2 = rng.standard_normal(216 * 12), rng.standard_normal(216 * 12)
+    assert np.abs(h.solve(2 * r1 - 3 * r2) - (2 * h.solve(r1) - 3 * h.solve(r2))).max() <= 1e-10
