@@ -390,6 +390,10 @@ __global__ void __launch_bounds__(NX *NX *GROUPS, 1)
             }
             group_barrier(1 + grp, N2);  // the p tile is complete
         }
+        // The r and u tiles of this stage are dead once p is built (FIRST: the unused p and u slots): they take the
+        // r- and s-fluxes of all NX planes, so the two D^T contractions need ONE group barrier per element instead of one
+        // per plane.
+        double *swr = FIRST ? sg + 7 * N3 : sr, *sws = sg + 8 * N3;
 #pragma unroll
         for (int k = 0; k < NX; k++) {
             const int q = k * N2 + ij;
@@ -405,17 +409,19 @@ __global__ void __launch_bounds__(NX *NX *GROUPS, 1)
             const double wr = fma(G0, ur, fma(G1, us, G2 * ut));
             const double ws = fma(G1, ur, fma(G3, us, G4 * ut));
             const double wt = fma(G2, ur, fma(G4, us, G5 * ut));
-            double *swr = s_w + (k & 1) * 2 * N2, *sws = swr + N2;
-            swr[ij] = wr;
-            sws[ij] = ws;
+            swr[q] = wr;
+            sws[q] = ws;
 #pragma unroll
             for (int m = 0; m < NX; m++) wcol[m] = fma(c_D[k * NX + m], wt, wcol[m]);
-            group_barrier(1 + grp, N2);
+        }
+        group_barrier(1 + grp, N2);
+#pragma unroll
+        for (int k = 0; k < NX; k++) {
             double acc = wcol[k];
 #pragma unroll
             for (int m = 0; m < NX; m++) {
-                acc = fma(DTi[m], swr[j * NX + m], acc);
-                acc = fma(DTj[m], sws[m * NX + i], acc);
+                acc = fma(DTi[m], swr[k * N2 + j * NX + m], acc);
+                acc = fma(DTj[m], sws[k * N2 + m * NX + i], acc);
             }
             wcol[k] = acc;
         }

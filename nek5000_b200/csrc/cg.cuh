@@ -347,6 +347,15 @@ __global__ void cggos_hist_kernel(const CgScalars *sc, double *hist, int slot)
     hist[3 * slot + 1] = sc->work[1];
 }
 
+inline int axcg_variant()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("NEKB_AXCG_VARIANT");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
 inline int cg_fused_enabled()
 {
     static int v = -1;
@@ -389,7 +398,11 @@ inline int cggos_run_fused(const CggosArgs &a, int maxit, double *hist_host, boo
     comm_allreduce_sum(&sc->work[1], 1);
     for (int iter = 1; iter <= maxit; iter++) {
         prof_begin(PROF_AX);
-        launch_ax_cg<8, 3, 2>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]);
+        switch (axcg_variant()) {  // element groups per CTA x ring stages (36 KB each): bytes in flight vs. threads per SM
+            case 1: launch_ax_cg<8, 2, 3>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
+            case 2: launch_ax_cg<8, 2, 2>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
+            default: launch_ax_cg<8, 3, 2>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
+        }
         prof_end(PROF_AX);
         comm_allreduce_sum(&sc->work[0], 1);
         prof_begin(PROF_GS);

@@ -26,6 +26,8 @@
 #include <map>
 #include <tuple>
 
+#include <cooperative_groups.h>
+
 #include "setup.cuh"
 
 namespace nekb {
@@ -267,6 +269,7 @@ struct CrsSolver {
     double ndof = 0.0;          // distinct unmasked dofs (all ranks)
     int null_space = 0;
     int last_iters = 0;
+    bool iters_on_device = false;  // the cooperative kernel leaves its count in the device scalars
     double tol = 1e-13;
     int maxit = 2000;
 };
@@ -742,10 +745,145 @@ __global__ void __launch_bounds__(256)
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) a[t] = (a[t] - sh) * mask[t];
 }
 
+// ------------------------------------------------------------------------------------------------ coarse PCG, one launch
+// The whole Jacobi-PCG of the coarse solve as ONE cooperative kernel (single rank): the coarse problem is far too small to
+// fill the machine, so its cost is launch latency and host round trips; here an iteration costs four grid barriers.
+// Scalars are reduced redundantly by every CTA from per-CTA partials in index order => identical values everywhere,
+// uniform exit, run-to-run deterministic.
+struct CrsCoopArgs {
+    double *x, *r, *p0, *p1, *w;
+    const double *a, *dinv, *mask, *mult;
+    const int32_t *goff, *gidx;
+    int ngroups;
+    int64_t n;
+    double tol2;
+    int maxit;
+    double *partials;  // >= 4 * gridDim doubles
+    CrsScalars *sc;
+};
+__device__ __forceinline__ double coop_total(const double *partials, int count, double *red, double *s_bcast)
+{
+    double a = 0.0;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) a += __ldcg(partials + i);
+    const double t = block_reduce(a, red);
+    if (threadIdx.x == 0) *s_bcast = t;
+    __syncthreads();
+    const double out = *s_bcast;
+    __syncthreads();
+    return out;
+}
+__global__ void __launch_bounds__(256) crs_pcg_coop_kernel(CrsCoopArgs A)
+{
+    namespace cgr = cooperative_groups;
+    cgr::grid_group grid = cgr::this_grid();
+    __shared__ double red[33];
+    __shared__ double s_b;
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    const int G = gridDim.x;
+    double *P0 = A.partials, *P1 = A.partials + G, *P2 = A.partials + 2 * G, *P3 = A.partials + 3 * G;
+    // (r,r) and (r, D^-1 r)
+    {
+        double s1 = 0.0, s2 = 0.0;
+        for (int64_t t = tid; t < A.n; t += nth) {
+            const double rv = A.r[t], m = A.mult[t];
+            s1 = fma(rv * rv, m, s1);
+            s2 = fma(rv * A.dinv[t] * rv, m, s2);
+        }
+        const double b1 = block_reduce(s1, red);
+        const double b2 = block_reduce(s2, red);
+        if (threadIdx.x == 0) P0[blockIdx.x] = b1, P1[blockIdx.x] = b2;
+    }
+    grid.sync();
+    const double rr0 = coop_total(P0, G, red, &s_b);
+    double rz = coop_total(P1, G, red, &s_b);
+    int it = 0;
+    if (rr0 > 0.0) {
+        double beta = 0.0;
+        double *pin = A.p0, *pout = A.p1;
+        for (; it < A.maxit;) {
+            // p = D^-1 r + beta p ; w = A_loc p
+            for (int64_t t = tid; t < A.n; t += nth) {
+                const int64_t e8 = t & ~(int64_t)7;
+                const int i = (int)(t & 7);
+                const double *ae = A.a + (t >> 3) * 64 + i * 8;
+                double s = 0.0, mine = 0.0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const double pj = fma(beta, pin[e8 + j], A.dinv[e8 + j] * A.r[e8 + j]);
+                    if (j == i) mine = pj;
+                    s = fma(ae[j], pj, s);
+                }
+                pout[t] = mine;
+                A.w[t] = s;
+            }
+            grid.sync();
+            // w <- Q Q^T w
+            for (int64_t g = tid; g < A.ngroups; g += nth) {
+                const int b = A.goff[g], e = A.goff[g + 1];
+                double v = A.w[A.gidx[b]];
+                for (int q = b + 1; q < e; q++) v += A.w[A.gidx[q]];
+                for (int q = b; q < e; q++) A.w[A.gidx[q]] = v;
+            }
+            grid.sync();
+            {
+                double s = 0.0;
+                for (int64_t t = tid; t < A.n; t += nth) {
+                    const double wv = A.w[t] * A.mask[t];
+                    A.w[t] = wv;
+                    s = fma(wv * pout[t], A.mult[t], s);
+                }
+                const double b = block_reduce(s, red);
+                if (threadIdx.x == 0) P2[blockIdx.x] = b;
+            }
+            grid.sync();
+            const double pw = coop_total(P2, G, red, &s_b);
+            const double alpha = rz / pw;
+            {
+                double s1 = 0.0, s2 = 0.0;
+                for (int64_t t = tid; t < A.n; t += nth) {
+                    A.x[t] = fma(alpha, pout[t], A.x[t]);
+                    const double rv = fma(-alpha, A.w[t], A.r[t]);
+                    A.r[t] = rv;
+                    const double m = A.mult[t];
+                    s1 = fma(rv * A.dinv[t] * rv, m, s1);
+                    s2 = fma(rv * rv, m, s2);
+                }
+                const double b1 = block_reduce(s1, red);
+                const double b2 = block_reduce(s2, red);
+                if (threadIdx.x == 0) P0[blockIdx.x] = b1, P3[blockIdx.x] = b2;
+            }
+            grid.sync();
+            const double rz_new = coop_total(P0, G, red, &s_b);
+            const double rr = coop_total(P3, G, red, &s_b);
+            it++;
+            if (rr <= A.tol2 * rr0 || rz_new == 0.0) break;
+            beta = rz_new / rz;
+            rz = rz_new;
+            double *tmp = pin;
+            pin = pout, pout = tmp;
+        }
+    }
+    if (tid == 0) {
+        A.sc->it = it;
+        A.sc->done = 1;
+        A.sc->rr0 = rr0;
+    }
+}
+
 inline DevBuf<CrsScalars> &crs_scalars()
 {
     static DevBuf<CrsScalars> s;
     return s;
+}
+
+inline int crs_coop_enabled()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("NEKB_CRS_COOP");
+        v = e ? atoi(e) : 0;  // measured (E = 32,768, 183 iterations): graph replay 6.6 ms per V-cycle, cooperative 7.4 ms
+    }
+    return v;
 }
 
 inline int vec_grid(int64_t n)
@@ -787,6 +925,38 @@ inline void crs_solve_dev(H1mg &MM, double *x_out, const double *b_in)
         crs_shift_kernel<<<grid, 256, 0, s>>>(k.r.p, k.mask.p, n, &sc->shift, 1.0 / k.ndof);
         NEKB_LAUNCHED();
     }
+    if (c.nranks <= 1 && crs_coop_enabled()) {  // one cooperative launch, no host round trip
+        NEKB_CUDA(cudaMemsetAsync(k.x.p, 0, sizeof(double) * (size_t)n, s));
+        NEKB_CUDA(cudaMemsetAsync(k.p.p, 0, sizeof(double) * (size_t)n, s));
+        GsMap &h = gs_get(k.gs);
+        CrsCoopArgs A;
+        A.x = k.x.p, A.r = k.r.p, A.p0 = k.p.p, A.p1 = k.p2.p, A.w = k.w.p;
+        A.a = k.a.p, A.dinv = k.dinv.p, A.mask = k.mask.p, A.mult = k.mult.p;
+        A.goff = h.goff.p, A.gidx = h.gidx.p, A.ngroups = (int)h.ngroups;
+        A.n = n, A.tol2 = k.tol * k.tol, A.maxit = k.maxit, A.partials = part, A.sc = sc;
+        static int per_sm = 0;  // co-resident CTAs per SM: the phases are latency-bound, so fill the SMs with warps
+        if (!per_sm) {
+            NEKB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, crs_pcg_coop_kernel, 256, 0));
+            if (per_sm > 4) per_sm = 4;
+            if (per_sm < 1) per_sm = 1;
+        }
+        int gridc = (int)((n + 255) / 256);
+        if (gridc > c.num_sms * per_sm) gridc = c.num_sms * per_sm;
+        void *args[] = {&A};
+        NEKB_CUDA(cudaLaunchCooperativeKernel((void *)crs_pcg_coop_kernel, dim3(gridc), dim3(256), args, 0, s));
+        NEKB_LAUNCHED();
+        k.iters_on_device = true;
+        if (k.null_space) {
+            crs_dot_kernel<<<grid, 256, 0, s>>>(k.x.p, k.mask.p, k.mult.p, n, &sc->shift, part, &sc->counter[3]);
+            NEKB_LAUNCHED();
+            crs_shift_kernel<<<grid, 256, 0, s>>>(k.x.p, k.mask.p, n, &sc->shift, 1.0 / k.ndof);
+            NEKB_LAUNCHED();
+        }
+        mg_copy_kernel<<<grid, 256, 0, s>>>(x_out, k.x.p, n);
+        NEKB_LAUNCHED();
+        return;
+    }
+    k.iters_on_device = false;
     NEKB_CUDA(cudaMemsetAsync(k.x.p, 0, sizeof(double) * (n ? n : 1), s));
     NEKB_CUDA(cudaMemsetAsync(k.p.p, 0, sizeof(double) * (n ? n : 1), s));
     NEKB_CUDA(cudaMemsetAsync(k.p2.p, 0, sizeof(double) * (n ? n : 1), s));

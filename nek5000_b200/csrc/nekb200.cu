@@ -870,7 +870,15 @@ int nekb_h1mg_info(int *lmax, int *nh3, int *ntab3, int *crs_iters)
             if (nh3) nh3[l] = M.lev[l].nh;
             if (ntab3) ntab3[l] = M.lev[l].ntab;
         }
-        if (crs_iters) *crs_iters = M.crs.last_iters;
+        if (crs_iters) {
+            if (M.crs.iters_on_device && crs_scalars().p) {
+                CrsScalars hs;
+                NEKB_CUDA(cudaMemcpyAsync(&hs, crs_scalars().p, sizeof(CrsScalars), cudaMemcpyDeviceToHost, ctx().stream));
+                NEKB_CUDA(cudaStreamSynchronize(ctx().stream));
+                M.crs.last_iters = hs.it;
+            }
+            *crs_iters = M.crs.last_iters;
+        }
     });
 }
 int nekb_h1mg_get(const char *which, int level, double *host_out, size_t n_doubles)
