@@ -27,8 +27,8 @@ __global__ void __launch_bounds__(NX *NX *EPB)
 {
     constexpr int N2 = NX * NX, N3 = NX * NX * NX;
     __shared__ double s_u[EPB][N3];
-    __shared__ double s_wr[2][EPB][N2];
-    __shared__ double s_ws[2][EPB][N2];
+    __shared__ double s_wr[EPB][N3];  // r- and s-fluxes of all planes: one barrier per element instead of one per plane
+    __shared__ double s_ws[EPB][N3];
     __shared__ double s_red[33];
 
     const int tid = threadIdx.x;
@@ -87,19 +87,24 @@ __global__ void __launch_bounds__(NX *NX *EPB)
                 ws *= hh;
                 wt *= hh;
             }
-            s_wr[k & 1][es][ij] = wr;
-            s_ws[k & 1][es][ij] = ws;
+            s_wr[es][q] = wr;
+            s_ws[es][q] = ws;
 #pragma unroll
             for (int m = 0; m < NX; m++) wcol[m] = fma(c_D[k * NX + m], wt, wcol[m]);
-            __syncthreads();
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < NX; k++) {
             double acc = wcol[k];
 #pragma unroll
             for (int m = 0; m < NX; m++) {
-                acc = fma(DTi[m], s_wr[k & 1][es][j * NX + m], acc);
-                acc = fma(DTj[m], s_ws[k & 1][es][m * NX + i], acc);
+                acc = fma(DTi[m], s_wr[es][k * N2 + j * NX + m], acc);
+                acc = fma(DTj[m], s_ws[es][k * N2 + m * NX + i], acc);
             }
             wcol[k] = acc;
         }
+        // no barrier needed here: the next element first rewrites s_u (not read above) and meets the barrier that follows
+        // its load before any thread touches the flux tiles again
         if (act) {
 #pragma unroll
             for (int k = 0; k < NX; k++) {
@@ -110,8 +115,6 @@ __global__ void __launch_bounds__(NX *NX *EPB)
                 pap = fma(ucol[k], v, pap);
             }
         }
-        // s_u may be overwritten right away: every thread has passed the barrier of k = NX-1, which
-        // follows its last read of s_u; s_wr/s_ws are double buffered across that barrier.
     }
     if (pap_out != nullptr) {
         double b = block_reduce(pap, s_red);
@@ -225,8 +228,9 @@ __global__ void __launch_bounds__(NX *NX *GROUPS, 1)
         const int stage = it % STAGES;
         const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
         mbar_wait(&full[stage], parity);
-        const double *__restrict__ sg = gbase + stage * L::stage_doubles;
-        const double *__restrict__ su = sg + 6 * N3;
+        double *sgw = gbase + stage * L::stage_doubles;
+        const double *sg = sgw;
+        const double *su = sg + 6 * N3;
 
         double ucol[NX], wcol[NX];
 #pragma unroll
@@ -249,17 +253,21 @@ __global__ void __launch_bounds__(NX *NX *GROUPS, 1)
             const double wr = fma(G0, ur, fma(G1, us, G2 * ut));
             const double ws = fma(G1, ur, fma(G3, us, G4 * ut));
             const double wt = fma(G2, ur, fma(G4, us, G5 * ut));
-            double *swr = s_w + (k & 1) * 2 * N2, *sws = swr + N2;
-            swr[ij] = wr;
-            sws[ij] = ws;
+            // the factor entries at q are read by this thread only: their slots take the r- and s-flux of the plane, so
+            // one group barrier per element (instead of one per plane) separates the fluxes from their D^T contractions
+            sgw[0 * N3 + q] = wr;
+            sgw[1 * N3 + q] = ws;
 #pragma unroll
             for (int m = 0; m < NX; m++) wcol[m] = fma(c_D[k * NX + m], wt, wcol[m]);
-            group_barrier(1 + grp, N2);
+        }
+        group_barrier(1 + grp, N2);
+#pragma unroll
+        for (int k = 0; k < NX; k++) {
             double acc = wcol[k];
 #pragma unroll
             for (int m = 0; m < NX; m++) {
-                acc = fma(DTi[m], swr[j * NX + m], acc);
-                acc = fma(DTj[m], sws[m * NX + i], acc);
+                acc = fma(DTi[m], sgw[k * N2 + j * NX + m], acc);
+                acc = fma(DTj[m], sgw[N3 + k * N2 + m * NX + i], acc);
             }
             wcol[k] = acc;
         }
@@ -274,7 +282,11 @@ __global__ void __launch_bounds__(NX *NX *GROUPS, 1)
         group_barrier(1 + grp, N2);
         if (leader) {
             const int en = e + STAGES * stride;
-            if (en < nel) issue(stage, en);
+            if (en < nel) {
+                // flux values were written into the stage through the generic proxy: order them before the refill
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(stage, en);
+            }
         }
     }
     if (pap_out != nullptr) {
