@@ -267,12 +267,14 @@ def main():
     }
     # dram__bytes_read+write per launch of the same kernel from the committed ncu --set full captures (E = 262,144)
     if case.nel == 262144:
-        for fn, key in (("r1b_ncu_traffic.json", "ax_cg_kernel<8, 3, 2, 0>"), ("r1a_ncu_traffic.json", "ax_tma_kernel<8, 3, 2>")):
+        for fn, key in (("r1c_ncu_traffic.json", "ax_cg_kernel<8, 3, 2, 0>"), ("r1b_ncu_traffic.json", "ax_cg_kernel<8, 3, 2, 0>"),
+                        ("r1a_ncu_traffic.json", "ax_tma_kernel<8, 3, 2>")):
             pj = os.path.join(ROOT, "profiles", fn)
             if os.path.exists(pj) and (key.startswith("ax_cg") == fused):
                 try:
                     out["roofline"]["traffic"] = json.load(open(pj)).get(key)
                     out["roofline"]["traffic_source"] = f"profiles/{fn}"
+                    break
                 except Exception:
                     pass
     if a.gpus == 1 and not a.no_cpu:
