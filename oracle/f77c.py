@@ -874,7 +874,8 @@ class Unit:
             self.tr.common_size[blk] = max(self.tr.common_size.get(blk, 0), off)
             self.tr.common_views.setdefault(blk, {})[self.name] = [
                 (n, self.syms[n].common[1], self.typeof_sym(self.syms[n]), self.elem_size(self.syms[n]),
-                 self.const_extents(self.syms[n]) if self.syms[n].dims else []) for n in names]
+                 self.const_extents(self.syms[n]) if self.syms[n].dims else [],
+                 [self.const(lo) for lo, _ in self.syms[n].dims] if self.syms[n].dims else []) for n in names]
         # equivalence: resolve to (anchor, byte offset); anchors in COMMON give every member a COMMON address
         k = 0
         for grp in self.equivs:
@@ -1547,6 +1548,26 @@ class Unit:
             decl.append(f"  {rt} {cname(self.name)}_result = 0;")
         for blob, size in self.eqv_blobs.items():
             decl.append(f"  static char {blob}[{size}] __attribute__((aligned(16)));")
+        # DATA for variables the body never touches (include-file boilerplate) is dropped
+        live = []
+        for targets, vals in self.datas:
+            if any(t[1] in self.used for t in targets):
+                live.append((targets, vals))
+                for t in targets:
+                    self.used.add(t[1])
+        self.datas = live
+        # names that only appear in the bounds of used arrays must be declared too
+        changed = True
+        while changed:
+            before = len(self.used)
+            for n in list(self.used) + list(self.args):
+                sy = self.syms.get(n)
+                if sy is not None and sy.dims:
+                    for lo, hi in sy.dims:
+                        for b in (lo, hi):
+                            if b is not None and not self.is_const(b):
+                                self.cx(b)
+            changed = len(self.used) != before
         # scalars first (array extents may need them), then arrays
         names = [n for n in self.syms if n in self.used or self.syms[n].arg]
         late = []
@@ -1719,6 +1740,7 @@ class Translator:
         self.externs = {}         # name -> return C type as seen by callers
         self.defined = {}
         self.known_units = set()
+        self.failed = {}
 
     def add_file(self, path, only=None, skip=()):
         for u in split_units(self.reader.read(path)):
@@ -1749,15 +1771,26 @@ class Translator:
             if n not in self.units:
                 missing.add(n)
                 continue
-            u = Unit(self, self.units[n])
-            code = u.translate()
+            if n in stop_at:
+                missing.add(n)
+                continue
+            try:
+                u = Unit(self, self.units[n])
+                code = u.translate()
+            except (TranslationError, SyntaxError) as e:
+                # not translatable: a stub that aborts loudly if it is ever executed
+                self.failed[n] = str(e)
+                rt = "double" if self.units[n]["kind"] == "function" else "void"
+                self.defined[n] = rt
+                msg = (n + ": " + str(e).splitlines()[0]).replace("\\", "/").replace('"', "'")
+                done[n] = [f'{rt} {n}_() {{ f77_unsupported("{msg}"); {"return 0;" if rt != "void" else ""} }}', ""]
+                order.append(n)
+                continue
             done[n] = code
             order.append(n)
             for c in sorted(u.calls):
-                if c not in done and c not in stop_at:
+                if c not in done:
                     work.append(c)
-                elif c in stop_at:
-                    missing.add(c)
         out = ["/* generated by oracle/f77c.py from the reference sources; do not commit */", RUNTIME]
         for blk in sorted(self.common_size):
             out.append(f"char cb_{blk}[{max(self.common_size[blk], 1)}] __attribute__((aligned(64)));")
@@ -1771,14 +1804,32 @@ class Translator:
         return "\n".join(out), sorted(missing - set(done))
 
     def common_map(self):
-        """{var: {block, offset, type, elsize, dims}} merged over all views that agree; conflicting views keep the first."""
-        m = {}
+        """{var: {block, offset, type, elsize, dims, lows}}: for a name that different routines place differently (local
+        COMMON declarations with their own names), the placement used by the most routines wins (the include files')."""
+        votes = {}
         for blk, views in self.common_views.items():
             for unit, lst in views.items():
-                for n, off, t, es, dims in lst:
-                    if n not in m:
-                        m[n] = dict(block=blk, offset=off, type=t, elsize=es, dims=dims, unit=unit)
+                for n, off, t, es, dims, lows in lst:
+                    key = (blk, off, t, es, tuple(dims), tuple(lows))
+                    votes.setdefault(n, {}).setdefault(key, 0)
+                    votes[n][key] += 1
+        m = {}
+        for n, d in votes.items():
+            (blk, off, t, es, dims, lows), _ = max(d.items(), key=lambda kv: kv[1])
+            m[n] = dict(block=blk, offset=off, type=t, elsize=es, dims=list(dims), lows=list(lows))
         return m
+
+    def common_alt(self):
+        """{unit: {var: entry}} for the placements that differ from common_map()'s winner (routine-local COMMON views)."""
+        m = self.common_map()
+        alt = {}
+        for blk, views in self.common_views.items():
+            for unit, lst in views.items():
+                for n, off, t, es, dims, lows in lst:
+                    e = dict(block=blk, offset=off, type=t, elsize=es, dims=list(dims), lows=list(lows))
+                    if m[n] != e:
+                        alt.setdefault(unit, {})[n] = e
+        return alt
 
 
 if __name__ == "__main__":
