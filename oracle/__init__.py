@@ -4,8 +4,10 @@ numpy/ctypes front end of ``oracle/nek_oracle.c`` (statement-level C restatement
 the reference Fortran; each C function cites the reference file:line it follows) and
 of ``oracle/bp5_cpu.c`` (OpenMP "restated CPU baseline" for bench.py).
 
-PARITY UNPINNED: the reference cannot be compiled here (no Fortran compiler, gslib not
-vendored) and holds no golden vectors for this path; see the header of nek_oracle.c.
+PARITY PINNED against the reference itself: ``oracle/ref_build.py`` transpiles the reference's own
+Fortran (``oracle/f77c.py``; there is no Fortran compiler here) into ``oracle/_ref/`` and
+``tests/test_ref_pins.py`` holds this restatement to its outputs bit for bit (golden vectors:
+``tests/golden/ref_golden.npz``); see the header of nek_oracle.c.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
 ``--impl reference`` legs may import this package.  The product (``nek5000_b200``)
@@ -120,6 +122,7 @@ class Case:
         L = lib()
         self.nx, self.nel = nx, nelx * nely * nelz
         self.nelx, self.nely, self.nelz = nelx, nely, nelz
+        self.periodic, self.dirichlet = tuple(periodic), tuple(dirichlet)
         self.nxyz = nx ** 3
         self.n = self.nxyz * self.nel
         E = self.nel

@@ -6,9 +6,11 @@ its setup ``h1mg_setup`` (core/hsmg.f:2234-2270), the single-level FDM pieces it
 1542-1617), the vertex-mesh coarse solve (core/navier8.f:83-233, 1648-1690; core/crs_xxt.c:926-965) and the
 right-preconditioned GMRES ``hmh_gmres`` (core/gmres.f:284-545).
 
-PARITY UNPINNED (see oracle/nek_oracle.c): the reference cannot be compiled here and holds no golden vector for
-these routines.  The generalised eigenproblems go through LAPACK ``dsygv`` itself (scipy.linalg.eigh(driver="gv")),
-the routine the reference calls (core/hmholtz.f:1398).  tests/test_oracle_hsmg.py holds the known-answer checks.
+PARITY PINNED against the reference itself (see oracle/nek_oracle.c): tests/test_ref_pins.py compares h1mg_solve,
+hmh_gmres, fdm_h1 / the Schwarz branch of cggo and hsmg_solve with the outputs of the reference's own Fortran
+(oracle/_ref, transpiled by oracle/f77c.py) -- <= 1e-12 relative, identical iteration counts; the difference from
+bit-exactness is the eigen-solver (the reference's 3rd_party/blasLapack dsygv vs SciPy's LAPACK dsygv,
+scipy.linalg.eigh(driver="gv")) and the coarse factorisation.  tests/test_oracle_hsmg.py adds known-answer checks.
 
 Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this module.
 

@@ -6,13 +6,19 @@
  * cpu_baseline / --impl reference leg use it, and only as the checker / the
  * CPU arm, never as the shipped path.
  *
- * PARITY UNPINNED: the reference (Fortran 77 + external gslib v1.0.9) cannot be
- * compiled in the authoring container (no Fortran compiler, no MPI, gslib not
- * vendored) and its own tests hold no golden vector for axhelm / dssum / cggo /
- * bp5.  This restatement follows the Fortran statement by
- * statement (same loop and summation order) and is pinned only by (i) the
- * reference's mesh fixtures examples/bp5/bp5.{re2,ma2} (tests/golden) and (ii)
- * the analytic known-answer tests listed in tests/test_oracle.py.
+ * PARITY PINNED AGAINST THE REFERENCE ITSELF: no Fortran compiler exists in the
+ * authoring container and gslib v1.0.9 is not vendored, so the reference cannot
+ * be built with its own toolchain; instead oracle/f77c.py transpiles the
+ * reference's own Fortran for this path (read where it lies under
+ * /root/reference) to C, oracle/ref_build.py compiles it (gcc -O2
+ * -ffp-contract=off) with serial stand-ins for gslib / crs (oracle/ref_stubs.c)
+ * into oracle/_ref/, and tests/test_ref_pins.py holds this restatement to the
+ * reference's outputs (tests/golden/ref_golden.npz): BIT FOR BIT for speclib,
+ * numbering, geometry, masks, axhelm, setprec, the gs ops, cggo and the whole
+ * BP5 driver.  What stays a stand-in: the gather-scatter and the coarse solve
+ * are single-rank restatements of gslib's / XXT's published semantics.
+ * Additional pins: the reference's mesh fixtures examples/bp5/bp5.{re2,ma2}
+ * (tests/golden) and the analytic known-answer tests in tests/test_oracle.py.
  *
  * Conventions: all arrays are Fortran column-major, u(i,j,k,e) lives at
  * u[i + nx*(j + nx*k) + nx^3*e] with 0-based i,j,k,e.  "real" is double

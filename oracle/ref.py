@@ -29,18 +29,33 @@ def available(lx1=8, lx2=None, lelt=64) -> bool:
 class Ref:
     _cache = {}
 
-    def __new__(cls, lx1=8, lx2=None, lelt=64, lgmres=30):
+    def __new__(cls, lx1=8, lx2=None, lelt=64, lgmres=30, fresh=False):
+        """fresh=True loads a private copy of the library: the reference keeps state in SAVE variables (icalld counters,
+        hmh_gmres' norm_fac, ...) and in the stand-ins' handle tables, which must not leak from one test case to the next."""
         key = (lx1, lx2 or lx1, lelt, lgmres)
+        if fresh:
+            self = super().__new__(cls)
+            self._init(*key, fresh=True)
+            return self
         if key not in cls._cache:
             self = super().__new__(cls)
             self._init(*key)
             cls._cache[key] = self
         return cls._cache[key]
 
-    def _init(self, lx1, lx2, lelt, lgmres):
+    def _init(self, lx1, lx2, lelt, lgmres, fresh=False):
         so = ref_build.build(lx1, lx2, lelt, lgmres)
         self.meta = json.load(open(so.replace("libnekref_", "nekref_").replace(".so", ".json")))
-        self.lib = C.CDLL(so)
+        if fresh:
+            import shutil
+            import tempfile
+            fd, tmp = tempfile.mkstemp(suffix=".so", prefix="nekref_")
+            os.close(fd)
+            shutil.copyfile(so, tmp)
+            self.lib = C.CDLL(tmp)      # a distinct path gives distinct globals
+            os.unlink(tmp)
+        else:
+            self.lib = C.CDLL(so)
         self.lx1, self.lx2, self.lelt = lx1, lx2, lelt
         self._blocks = {}
         self._keep = []
@@ -118,11 +133,10 @@ class RefCase:
     initds/dsset/setedge + setupds + multiplicity (connect1.f:43-135), genwz, geom1/geom2/volume/setinvm/setdef
     (gengeom, core/coef.f / drive2.f), bcmask."""
 
-    def __init__(self, case, lelt=None, lx2=None, ifsplit=True, nfield=1):
-        import numpy as _np
+    def __init__(self, case, lelt=None, lx2=None, ifsplit=True, nfield=1, fresh=True, lgmres=30):
         nx, E = case.nx, case.nel
         lelt = lelt or max(64, E)
-        R = self.R = Ref(nx, lx2 or nx, lelt)
+        R = self.R = Ref(nx, lx2 or nx, lelt, lgmres, fresh=fresh)
         self.case, self.E, self.nx = case, E, nx
         R.call("initdim")
         R.call("initdat")
@@ -133,26 +147,21 @@ class RefCase:
                 R.set(k, v)
         R.var("nelfld")[:] = E
         R.var("param")[58] = 1.0               # param(59)=1: every element takes the general (deformed) branch
-        for e in range(E):
-            R.var("lglel")[e] = e + 1
-            R.var("gllel")[e] = e + 1
-            R.var("gllnid")[e] = 0
+        R.var("lglel")[:E] = np.arange(1, E + 1)
+        R.var("gllel")[:E] = np.arange(1, E + 1)
+        R.var("gllnid")[:E] = 0
         # boundary conditions in preprocessor face order (1:y-,2:x+,3:y+,4:x-,5:z-,6:z+)
         cbc = R.var("cbc")
         cbc[...] = b"E  "
         per = getattr(case, "periodic", (0, 0, 0))
         dflag = getattr(case, "dirichlet", (1, 1, 1, 1, 1, 1))
-        e = 0
-        for ez in range(case.nelz):
-            for ey in range(case.nely):
-                for ex in range(case.nelx):
-                    sides = {4: (ex == 0, 0, 0), 2: (ex == case.nelx - 1, 0, 1), 1: (ey == 0, 1, 2),
-                             3: (ey == case.nely - 1, 1, 3), 5: (ez == 0, 2, 4), 6: (ez == case.nelz - 1, 2, 5)}
-                    for f, (on, ax, di) in sides.items():
-                        if on:
-                            cb = b"P  " if per[ax] else (b"v  " if dflag[di] else b"O  ")
-                            cbc[f - 1, e, 1] = cb
-                    e += 1
+        eid = np.arange(E)
+        ex, ey, ez = eid % case.nelx, (eid // case.nelx) % case.nely, eid // (case.nelx * case.nely)
+        for f, on, ax, di in ((4, ex == 0, 0, 0), (2, ex == case.nelx - 1, 0, 1), (1, ey == 0, 1, 2),
+                              (3, ey == case.nely - 1, 1, 3), (5, ez == 0, 2, 4), (6, ez == case.nelz - 1, 2, 5)):
+            cbc[f - 1, eid[on], 1] = b"P  " if per[ax] else (b"v  " if dflag[di] else b"O  ")
+        # setlog (core/bdry.f:24,50-57): no outflow face anywhere -> the pressure has the constant null space
+        R.set("ifvcor", int(not (cbc[:, :E, 1] == b"O  ").any()))
         sh = (nx, nx, nx, E)
         R.var("xc")[:, :E] = case.xc.reshape(8, E, order="F")
         R.var("yc")[:, :E] = case.yc.reshape(8, E, order="F")
@@ -184,4 +193,6 @@ class RefCase:
     def fld(self, name):
         """Flat copy (Nek memory order) of the first E elements of a field in COMMON."""
         v = self.R.var(name)
+        if v.ndim == 1:
+            return v[:v.size // self.R.lelt * self.E].copy()
         return v[..., :self.E].ravel(order="F").copy()

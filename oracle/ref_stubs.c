@@ -215,7 +215,14 @@ double etime_(float *t) { return 0.0; }
 double dnekclock_(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec; }
 double dnekclock_sync_(void) { return dnekclock_(); }
 void cexit_(void) { fprintf(stderr, "ref_stubs: cexit\n"); abort(); }
-void exitt_(void) { fprintf(stderr, "ref_stubs: the reference called exitt\n"); abort(); }
+#include <execinfo.h>
+static void where(void)
+{ /* which translated routine gave up (the reference's own message went to a dropped WRITE) */
+  void *bt[16];
+  int n = backtrace(bt, 16);
+  backtrace_symbols_fd(bt, n, 2);
+}
+void exitt_(void) { fprintf(stderr, "ref_stubs: the reference called exitt\n"); where(); abort(); }
 void exitti_(const char *msg, const int *i, long len)
 {
   fprintf(stderr, "ref_stubs: the reference called exitti: %.*s %d\n", (int)len, msg, *i);

