@@ -114,13 +114,16 @@ def cpu_leg(steps: int, warmup: int, m_cpu: int, target_s: float):
 
 
 def ref_leg(steps: int, warmup: int, target_s: float):
-    """The reference's own loop (oracle/_ref) on all host cores; None when the prebuilt library is absent."""
+    """The reference's own loop (oracle/_ref) on all host cores; None when the prebuilt library is absent.  Runs in a
+    fresh interpreter (python -m oracle.ref_bench): the CPU arm shares neither the CUDA context nor a single symbol with
+    the product library loaded in this process."""
     try:
-        from oracle import ref_bench
-        if not ref_bench.available(16):
-            return None
-        r = ref_bench.run(steps, warmup, m=16, target_s=target_s)
-        return r["gdofs"], r["cores"], r["sample"], r["ms_per_step"]
+        r = subprocess.run([sys.executable, "-m", "oracle.ref_bench", "--steps", str(steps), "--warmup", str(warmup),
+                            "--target-s", str(target_s)], cwd=ROOT, capture_output=True, text=True, timeout=900)
+        if r.returncode != 0:
+            raise RuntimeError(r.stderr.strip().splitlines()[-1] if r.stderr.strip() else f"exit code {r.returncode}")
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        return d["gdofs"], d["cores"], d["sample"], d["ms_per_step"]
     except Exception as ex:
         print(f"bench.py: reference leg unavailable ({ex}); falling back to the OpenMP port", file=sys.stderr)
         return None

@@ -212,6 +212,26 @@ int nekb_cggos_dev(double *u_dev, const double *rhs_dev, const double *x1_dev, c
  * D. Host-side setup feeding the path
  * ---------------------------------------------------------------------------------- */
 
+/* ---- mesh files: the reference's binary fixtures, read on the host -------------------------
+ * .re2: core/reader_re2.f:543-639 header ('#v001' 4-byte words, '#v002'/'#v003' 8-byte words; endian tag 6.54321),
+ * :65-158/:391-471 mesh records (group, x(2^ldim), y, z in PREPROCESSOR corner order), :160-290 curved sides,
+ * :292-389/:473-541 one boundary-condition section per field (element, face, bl(5), cbl).
+ * nekb_re2_info: sizes + the number of records of each BC section (nbc[0..nbc_cap)).
+ * nekb_re2_read_mesh: elements [e0,e0+nel) in global order -> xc,yc,zc(2^ldim,nel) (core/INPUT), igroup(nel) (may be NULL).
+ * nekb_re2_read_bc: one section -> cbc(3 chars,6,nelgt) and bc(5,6,nelgt), global arrays pre-filled by the caller
+ *   (slots without a record are left untouched). */
+int nekb_re2_info(const char *path, int64_t *nelgt, int *ldim, int64_t *nelgv, int *wdsize, int64_t *ncurve, int *nsections,
+                  int64_t *nbc, int nbc_cap);
+int nekb_re2_read_mesh(const char *path, int64_t e0, int64_t nel, double *xc, double *yc, double *zc, int *igroup);
+int nekb_re2_read_bc(const char *path, int section, char *cbc, double *bc);
+/* .ma2: core/map2.f:712-941 read_map -- 132-byte '#v001' header (7 integers: nel, nactive, depth, d2, npts, nrank,
+ * noutflow), endian tag, then 1 + nlv int32 per element: RSB leaf and the vertex ids in SYMMETRIC corner order
+ * (-> vertex(nlv,nel) int64 as setupds takes them).  nekb_assign_gllnid: core/map2.f:943-1026 assign_gllnid, in place:
+ * leaf -> 0-based rank for np ranks (power-of-two shortcut; otherwise the reference's isort-based contiguous split). */
+int nekb_ma2_info(const char *path, int64_t *nel, int64_t *hdr7);
+int nekb_ma2_read(const char *path, int nlv, int64_t e0, int64_t nel, int32_t *leaf, int64_t *vertex);
+int nekb_assign_gllnid(int *gllnid, int64_t nelgt, int64_t nelgv, int np);
+
 /* core/navier8.f:2004-2360 setvert3d with ifcenter=.false.: glo_num(nx^3,nel) from
  * vertex(8,nel) (symmetric corner order).  Single-process form: np only selects the mod-np
  * bucketing of gbtuple_rank8 (:1964), so the result equals an np-rank reference run.  With a
@@ -281,10 +301,12 @@ void nekb_h1mg_free(void);
 
 /* Pn-Pn-2 pressure preconditioner: core/hsmg.f:22-47 hsmg_setup, :1376-1602 hsmg_solve(e,r) and its top level
  * core/fasts.f:2-94 local_solves_fdm(u,v), on the lx2 = lx1-2 Gauss grid (arrays of (lx1-2)^3*nelv doubles).
- * The levels below the top, the coarse solve and all exchanges are built here exactly as for h1mg; the top-level
- * fast-diagonalisation data is what gen_fast (core/fast3d.f) leaves in common /fastd/ and is REGISTERED, not recomputed:
- * df(lx1^3,nelv), sr/ss/st(2*lx1^2,nelv) (S in the first half of each, column-major; host arrays).  That setup
- * depends on the E operator of the Pn-Pn-2 splitting and stays with the host program.
+ * The levels below the top, the coarse solve and all exchanges are built here exactly as for h1mg.  The top-level
+ * fast-diagonalisation data (common /fastd/: df(lx1^3,nelv), sr/ss/st(2*lx1^2,nelv), S in the first half of each,
+ * column-major; host arrays) is either REGISTERED -- what gen_fast (core/fast3d.f:2-140) left in COMMON -- or, when all
+ * four pointers are NULL, COMPUTED here: gen_fast with param(44) = 0 (set_up_fast_1D_sem :1351-1408, _sem_op :1410-1540,
+ * load_semhat_weighted :1181-1213) from the lengths of swap_lengths and the fbc codes (0 element, 1 outflow, 2 wall,
+ * 3 symmetry).
  * nelgv: global element count (ortho, core/navier1.f:223).  fbc, xm1.., vertex as for nekb_h1mg_setup. */
 int nekb_hsmg_setup(const int *fbc, const double *xm1, const double *ym1, const double *zm1, const int64_t *vertex,
                     int nelv, int null_space, int64_t nelgv, const double *df, const double *sr, const double *ss,

@@ -102,6 +102,12 @@ def lib() -> C.CDLL:
     L.nekb_cggos_dev.argtypes = [vp, vp, vp, vp, C.c_double, C.c_int, ip, vp]
     L.nekb_cggo_dev.argtypes = [vp] * 7 + [C.c_int, C.c_double, C.c_int, ip, vp]
     L.nekb_setvert3d.argtypes = [i64p, C.POINTER(C.c_int64), C.c_int, C.c_int64, i64p, C.c_int]
+    L.nekb_re2_info.argtypes = [C.c_char_p, C.POINTER(C.c_int64), ip, C.POINTER(C.c_int64), ip, C.POINTER(C.c_int64), ip, vp, C.c_int]
+    L.nekb_re2_read_mesh.argtypes = [C.c_char_p, C.c_int64, C.c_int64, vp, vp, vp, vp]
+    L.nekb_re2_read_bc.argtypes = [C.c_char_p, C.c_int, vp, vp]
+    L.nekb_ma2_info.argtypes = [C.c_char_p, C.POINTER(C.c_int64), vp]
+    L.nekb_ma2_read.argtypes = [C.c_char_p, C.c_int, C.c_int64, C.c_int64, vp, vp]
+    L.nekb_assign_gllnid.argtypes = [vp, C.c_int64, C.c_int64, C.c_int]
     L.nekb_gs_discover.argtypes = [i64p, C.c_int64, ip, C.POINTER(C.c_int64), vp, vp, vp]
     L.nekb_bp5_setup.argtypes = [C.c_int] * 6 + [C.c_double]
     L.nekb_bp5_solve.argtypes = [C.c_double, C.c_int, ip, dp, vp]
@@ -151,7 +157,7 @@ def lib() -> C.CDLL:
     L.nekb_h1mg_get.argtypes = [C.c_char_p, C.c_int, vp, C.c_size_t]
     L.nekb_crs_set_tolerance.argtypes = [C.c_double, C.c_int]
     L.nekb_h1mg_free.restype = None
-    L.nekb_hsmg_setup.argtypes = [i32p, f64p, f64p, f64p, i64p, C.c_int, C.c_int, C.c_int64, f64p, f64p, f64p, f64p]
+    L.nekb_hsmg_setup.argtypes = [i32p, f64p, f64p, f64p, i64p, C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 4
     L.nekb_hsmg_solve_dev.argtypes = [vp, vp]
     L.nekb_local_solves_fdm_dev.argtypes = [vp, vp]
     L.hsmg_solve_.argtypes = [vp, vp]

@@ -349,6 +349,113 @@ inline std::vector<double> gauss_points(int n)
 // Face f of an element: 0 r-, 1 r+, 2 s-, 3 s+, 4 t-, 5 t+.  Entry (a, b) of a face holds the two tangential
 // indices in ascending direction order (r-faces: (j,k); s-faces: (i,k); t-faces: (i,j)), a fastest.
 
+// Gauss-Legendre weights for the points of gauss_points (core/speclib.f ZWGL): w = 2 / ((1 - x^2) P_n'(x)^2)
+inline std::vector<double> gauss_weights(const std::vector<double> &z)
+{
+    const int n = (int)z.size();
+    std::vector<double> w(n);
+    for (int i = 0; i < n; i++) {
+        const long double x = z[i];
+        long double p0 = 1.0L, p1 = x;
+        for (int k = 2; k <= n; k++) {
+            const long double p2 = ((2 * k - 1) * x * p1 - (k - 1) * p0) / k;
+            p0 = p1, p1 = p2;
+        }
+        if (n == 1) p0 = 1.0L, p1 = x;
+        const long double dp = n * (x * p1 - p0) / (x * x - 1.0L);
+        w[i] = (double)(2.0L / ((1.0L - x * x) * dp * dp));
+    }
+    return w;
+}
+
+// core/fast3d.f:1181-1213 load_semhat_weighted: bh (GLL weights, order n) and the GLL -> GL interpolation / derivative
+// matrices (semhat :1280-1289) pre-multiplied by the GL weights: jgl[(i-1)*(n+1)+k], dgl[...], i = 1..n-1, k = 0..n
+inline void semhat_weighted_host(int n, std::vector<double> &bh, std::vector<double> &jgl, std::vector<double> &dgl)
+{
+    std::vector<double> zh, Dunused, c;
+    gll_build(n + 1, zh, bh, Dunused);
+    const std::vector<double> zgl = gauss_points(n - 1), bgl = gauss_weights(zgl);
+    jgl.assign((size_t)(n - 1) * (n + 1), 0.0), dgl.assign((size_t)(n - 1) * (n + 1), 0.0);
+    for (int i = 0; i < n - 1; i++) {
+        fd_weights_full(zgl[i], zh.data(), n, 1, c);
+        for (int k = 0; k <= n; k++) {
+            jgl[(size_t)i * (n + 1) + k] = bgl[i] * c[(size_t)k * 2 + 0];
+            dgl[(size_t)i * (n + 1) + k] = bgl[i] * c[(size_t)k * 2 + 1];
+        }
+    }
+}
+
+// core/fast3d.f:1410-1540 set_up_fast_1D_sem_op: g = J B^-1 J^T on an element plus one node on either side (g[i*(n+1)+j])
+inline void fast1d_sem_op_host(std::vector<double> &g, int b0, int b1, bool l, bool r, double ll, double lm, double lr,
+                               const std::vector<double> &bh, const std::vector<double> &jm, int jscl)
+{
+    const int n = (int)bh.size() - 1, np = n + 1;
+    auto J = [&](int i, int k) { return jm[(size_t)(i - 1) * np + k]; };
+    auto G = [&](int i, int j) -> double & { return g[(size_t)i * np + j]; };
+    const double gl = jscl ? 0.5 * ll : 1.0, gm = jscl ? 0.5 * lm : 1.0, gr = jscl ? 0.5 * lr : 1.0;
+    const double gll = gl * gl, glm = gl * gm, gmm = gm * gm, gmr = gm * gr, grr = gr * gr;
+    std::vector<double> bm(np, 0.0), bl(np, 0.0), br(np, 0.0);
+    for (int i = 1; i < n; i++) bm[i] = 2.0 / (lm * bh[i]);
+    if (b0 == 0) {
+        bm[0] = 0.5 * lm * bh[0];
+        if (l) bm[0] = bm[0] + 0.5 * ll * bh[n];
+        bm[0] = 1.0 / bm[0];
+    }
+    if (b1 == n) {
+        bm[n] = 0.5 * lm * bh[n];
+        if (r) bm[n] = bm[n] + 0.5 * lr * bh[0];
+        bm[n] = 1.0 / bm[n];
+    }
+    if (l) {
+        for (int i = 0; i < n; i++) bl[i] = 2.0 / (ll * bh[i]);
+        bl[n] = bm[0];
+    }
+    if (r) {
+        for (int i = 1; i <= n; i++) br[i] = 2.0 / (lr * bh[i]);
+        br[0] = bm[n];
+    }
+    g.assign((size_t)np * np, 0.0);
+    for (int j = 1; j < n; j++)
+        for (int i = 1; i < n; i++)
+            for (int k = b0; k <= b1; k++) G(i, j) = G(i, j) + gmm * J(i, k) * bm[k] * J(j, k);
+    if (l) {
+        for (int i = 1; i < n; i++) {
+            G(i, 0) = glm * J(i, 0) * bm[0] * J(n - 1, n);
+            G(0, i) = G(i, 0);
+        }
+        for (int i = 0; i <= n; i++) G(0, 0) = G(0, 0) + gll * J(n - 1, i) * bl[i] * J(n - 1, i);
+    } else
+        G(0, 0) = 1.0;
+    if (r) {
+        for (int i = 1; i < n; i++) {
+            G(i, n) = gmr * J(i, n) * bm[n] * J(1, 0);
+            G(n, i) = G(i, n);
+        }
+        for (int i = 0; i <= n; i++) G(n, n) = G(n, n) + grr * J(1, i) * br[i] * J(1, i);
+    } else
+        G(n, n) = 1.0;
+}
+
+// core/fast3d.f:1351-1408 set_up_fast_1D_sem: 1-D eigen-system E~ s = lam B~ s of the Pn-Pn-2 top level; bc codes of
+// get_fast_bc with bsym = 3 (0 element, 1 outflow, 2 wall, 3 symmetry).  S[i*np+a] with the boundary rows zeroed.
+inline void fast1d_sem_host(int lbc, int rbc, double ll, double lm, double lr, const std::vector<double> &bh,
+                            const std::vector<double> &jgl, const std::vector<double> &dgl, std::vector<double> &S,
+                            std::vector<double> &lam)
+{
+    const int n = (int)bh.size() - 1, np = n + 1;
+    const int eb0 = (lbc == 2 || lbc == 3) ? 1 : 0, eb1 = (rbc == 2 || rbc == 3) ? n - 1 : n;
+    const int bb0 = lbc == 2 ? 1 : 0, bb1 = rbc == 2 ? n - 1 : n;
+    const bool l = lbc == 0, r = rbc == 0;
+    std::vector<double> e, b;
+    fast1d_sem_op_host(e, eb0, eb1, l, r, ll, lm, lr, bh, dgl, 0);
+    fast1d_sem_op_host(b, bb0, bb1, l, r, ll, lm, lr, bh, jgl, 1);
+    generalev_host(np, e, b, S, lam);
+    if (!l)
+        for (int a = 0; a < np; a++) S[a] = 0.0;
+    if (!r)
+        for (int a = 0; a < np; a++) S[(size_t)n * np + a] = 0.0;
+}
+
 // hsmg.f:449 h1mg_mask + the data hsmg_extrude(work,0,zero,work,2,one) moves (:459): r *= mask in place;
 // f_own = f_sum = r on the first interior layer of every face.
 __global__ void __launch_bounds__(256)
@@ -1280,18 +1387,57 @@ inline void h1mg_setup_run(H1mg &M, const int *fbc, const double *xm1, const dou
             std::vector<double> Stab((size_t)3 * nel * l2);
             std::vector<int32_t> sidx((size_t)3 * nel);
             const double *src[3] = {fastd->sr, fastd->ss, fastd->st};
-            for (int64_t e = 0; e < nel; e++)
-                for (int d = 0; d < 3; d++) {
-                    const double *sm = src[d] + (size_t)e * 2 * l2;
-                    double *dst = Stab.data() + ((size_t)e * 3 + d) * l2;
-                    for (int i = 0; i < nl; i++)
-                        for (int a = 0; a < nl; a++) dst[(size_t)i * nl + a] = sm[(size_t)i + (size_t)nl * a];
-                    sidx[(size_t)e * 3 + d] = (int32_t)(e * 3 + d);
+            std::vector<double> dfh;
+            if (!fastd->df) {
+                // gen_fast (core/fast3d.f:2-140, param(44) = 0): the /fastd/ data computed here from the lengths of
+                // swap_lengths and the boundary codes; 1-D systems de-duplicated before the eigen-solves
+                std::vector<double> bh, jgl, dgl, S1, lam1;
+                semhat_weighted_host(nl - 1, bh, jgl, dgl);
+                typedef std::tuple<int, int, double, double, double> Key;
+                std::map<Key, std::pair<std::vector<double>, std::vector<double>>> table;
+                dfh.assign((size_t)nel * nl * nl * nl, 0.0);
+                for (int64_t e = 0; e < nel; e++) {
+                    const std::vector<double> *lam[3];
+                    for (int d = 0; d < 3; d++) {
+                        const int lbc = fbc[e * 6 + 2 * d], rbc = fbc[e * 6 + 2 * d + 1];
+                        Key key(lbc, rbc, M.ll_host[(size_t)d * nel + e], M.lm_host[(size_t)d * nel + e], M.lr_host[(size_t)d * nel + e]);
+                        auto it = table.find(key);
+                        if (it == table.end()) {
+                            fast1d_sem_host(lbc, rbc, std::get<2>(key), std::get<3>(key), std::get<4>(key), bh, jgl, dgl, S1, lam1);
+                            it = table.emplace(key, std::make_pair(S1, lam1)).first;
+                        }
+                        memcpy(Stab.data() + ((size_t)e * 3 + d) * l2, it->second.first.data(), l2 * sizeof(double));
+                        sidx[(size_t)e * 3 + d] = (int32_t)(e * 3 + d);
+                        lam[d] = &it->second.second;
+                    }
+                    double mx[3];
+                    for (int d = 0; d < 3; d++) {
+                        mx[d] = (*lam[d])[1];
+                        for (int i = 2; i < nl - 1; i++) mx[d] = std::max(mx[d], (*lam[d])[i]);
+                    }
+                    const double eps = 1.e-5 * (mx[0] + mx[1] + mx[2]);
+                    double *de = dfh.data() + (size_t)e * nl * nl * nl;
+                    for (int k = 0; k < nl; k++)
+                        for (int j = 0; j < nl; j++)
+                            for (int i = 0; i < nl; i++) {
+                                const double diag = (*lam[0])[i] + (*lam[1])[j] + (*lam[2])[k];
+                                de[((size_t)k * nl + j) * nl + i] = diag > eps ? 1.0 / diag : 0.0;
+                            }
                 }
+            } else {
+                for (int64_t e = 0; e < nel; e++)
+                    for (int d = 0; d < 3; d++) {
+                        const double *sm = src[d] + (size_t)e * 2 * l2;
+                        double *dst = Stab.data() + ((size_t)e * 3 + d) * l2;
+                        for (int i = 0; i < nl; i++)
+                            for (int a = 0; a < nl; a++) dst[(size_t)i * nl + a] = sm[(size_t)i + (size_t)nl * a];
+                        sidx[(size_t)e * 3 + d] = (int32_t)(e * 3 + d);
+                    }
+            }
             L.ntab = 3 * nel;
             L.Stab.upload(Stab.data(), Stab.size(), s);
             L.sidx.upload(sidx.data(), sidx.size(), s);
-            L.dfull.upload(fastd->df, (size_t)nel * nl * nl * nl, s);
+            L.dfull.upload(fastd->df ? fastd->df : dfh.data(), (size_t)nel * nl * nl * nl, s);
             L.lamtab.alloc(1), L.eps.alloc(1);
             continue;
         }

@@ -3,6 +3,7 @@
 #include "../../include/nekb200.h"
 
 #include "gmres.cuh"
+#include "readers.cuh"
 
 using namespace nekb;
 
@@ -697,7 +698,19 @@ void cggo_(double *x, const double *f, const double *h1, const double *h2, const
     guard_fortran("cggo", [&] {
         require_init();
         Ctx &c = ctx();
-        NEKB_REQUIRE(!(name_len >= 4 && !strncmp(name, "PRES", 4)), "cggo: the 'PRES' (GMRES/flexible-CG) branch is not provided");
+        if (name_len >= 4 && !strncmp(name, "PRES", 4)) {
+            // hmholtz.f:641-657: ifsplit .and. name.eq.'PRES' -> x = f; hmh_gmres(x,h1,h2,mult,iter); niterhm = iter.
+            // (ifsplit is implied by a completed h1mg_setup, which only the Pn-Pn pressure solver performs.)
+            NEKB_REQUIRE(h1mg().ready, "cggo('PRES'): the pressure multigrid is not set up (nekb_h1mg_setup); the plain-PCG pressure "
+                                       "branch (ifsplit = .false.) is not provided");
+            NEKB_REQUIRE(c.param[42] == 0.0, "cggo('PRES'): param(42) = 2 (hmh_flex_cg) / 1 (PCG) are not provided, only GMRES (param(42)=0)");
+            const size_t np_ = (size_t)c.nelv * c.nxyz;
+            if (x != f) memcpy(x, f, np_ * sizeof(double));
+            int iter = *maxit;
+            hmh_gmres_(x, h1, h2, mult, &iter);
+            c.niterhm = iter;
+            return;
+        }
         const int nel = *imsh == 1 ? c.nelv : c.nelt;
         const size_t n = (size_t)nel * c.nxyz;
         const double *src[6] = {f, h1, h2, mask, mult, binv};
@@ -720,7 +733,7 @@ void hmholtz_(const char *name, double *u, double *rhs, const double *h1, const 
     guard_fortran("hmholtz", [&] {
         require_init();
         Ctx &c = ctx();
-        NEKB_REQUIRE(!(name_len >= 4 && !strncmp(name, "PRES", 4)), "hmholtz: 'PRES' goes through hmh_gmres (cggo :641-657)");
+        const bool pres = name_len >= 4 && !strncmp(name, "PRES", 4);
         const int nel = *imsh == 1 ? c.nelv : c.nelt;
         const size_t n = (size_t)nel * c.nxyz;
         const DevBuf<double> &binv = *imsh == 1 ? c.binvm1 : (c.bintm1.n ? c.bintm1 : c.binvm1);
@@ -741,6 +754,12 @@ void hmholtz_(const char *name, double *u, double *rhs, const double *h1, const 
             tol = chktcg1_dev(tol, d_rhs, d_h1, ifh2 ? d_h2 : nullptr, d_mask, d_mult, binv.p, nel, vol);
         }
         if (*tli < 0) tol = *tli;                                                  // :62
+        if (pres) {  // cggo forwards 'PRES' to hmh_gmres (:641-657), which takes host arrays
+            NEKB_CUDA(cudaMemcpyAsync(rhs, d_rhs, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+            NEKB_CUDA(cudaStreamSynchronize(c.stream));
+            cggo_(u, rhs, h1, h2, mask, mult, imsh, &tol, maxit, isd, nullptr, name, name_len);
+            return;
+        }
         CggoArgs a{c.stage[0].p, d_rhs, d_h1, d_h2, d_mask, d_mult, binv.p, field_handle(), nel, vol, c.istep};
         c.niterhm = cggo_run(a, tol, *maxit, nullptr);
         NEKB_CUDA(cudaMemcpyAsync(u, c.stage[0].p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
@@ -941,7 +960,8 @@ int nekb_hsmg_setup(const int *fbc, const double *xm1, const double *ym1, const 
     return guard([&] {
         require_init();
         NEKB_REQUIRE(nelv >= 0 && nelv <= ctx().nelt, "hsmg_setup: nelv exceeds the registered element count");
-        NEKB_REQUIRE(df && sr && ss && st, "hsmg_setup: the /fastd/ arrays df, sr, ss, st are required");
+        NEKB_REQUIRE((df && sr && ss && st) || (!df && !sr && !ss && !st),
+                     "hsmg_setup: pass all four /fastd/ arrays df, sr, ss, st (registered) or none (computed here: gen_fast)");
         NEKB_REQUIRE(ctx().nx >= 4, "hsmg_setup: lx1 >= 4 required");
         FastdArrays f;
         f.df = df, f.sr = sr, f.ss = ss, f.st = st, f.nelgv = nelgv;
@@ -1138,6 +1158,76 @@ void hmh_gmres_(double *res, const double *h1, const double *h2, const double *w
 }
 
 // ---------------------------------------------------------------------------------------------------- host-side setup
+// ---------------------------------------------------------------------------------------------------- mesh files
+int nekb_re2_info(const char *path, int64_t *nelgt, int *ldim, int64_t *nelgv, int *wdsize, int64_t *ncurve, int *nsections,
+                  int64_t *nbc, int nbc_cap)
+{
+    return guard([&] {
+        FileHandle fh(path);
+        NEKB_REQUIRE(fh.f != nullptr, std::string("Cannot open .re2 file! ") + path);
+        const Re2Header h = re2_header(fh);
+        const Re2Sections s = re2_sections(fh, h);
+        if (nelgt) *nelgt = h.nelgt;
+        if (ldim) *ldim = h.ldim;
+        if (nelgv) *nelgv = h.nelgv;
+        if (wdsize) *wdsize = h.wdsize;
+        if (ncurve) *ncurve = s.ncurve;
+        if (nsections) *nsections = (int)s.nbc.size();
+        for (int k = 0; nbc && k < nbc_cap && k < (int)s.nbc.size(); k++) nbc[k] = s.nbc[k];
+    });
+}
+int nekb_re2_read_mesh(const char *path, int64_t e0, int64_t nel, double *xc, double *yc, double *zc, int *igroup)
+{
+    return guard([&] {
+        FileHandle fh(path);
+        NEKB_REQUIRE(fh.f != nullptr, std::string("Cannot open .re2 file! ") + path);
+        const Re2Header h = re2_header(fh);
+        NEKB_REQUIRE(xc && yc && (zc || h.ldim == 2), "re2_read_mesh: output arrays required");
+        re2_read_mesh(fh, h, e0, nel, xc, yc, zc, igroup);
+    });
+}
+int nekb_re2_read_bc(const char *path, int section, char *cbc, double *bc)
+{
+    return guard([&] {
+        FileHandle fh(path);
+        NEKB_REQUIRE(fh.f != nullptr, std::string("Cannot open .re2 file! ") + path);
+        const Re2Header h = re2_header(fh);
+        const Re2Sections s = re2_sections(fh, h);
+        re2_read_bc(fh, h, s, section, cbc, bc);
+    });
+}
+int nekb_ma2_info(const char *path, int64_t *nel, int64_t *hdr7)
+{
+    return guard([&] {
+        FileHandle fh(path);
+        NEKB_REQUIRE(fh.f != nullptr, std::string("Cannot find map file! ") + path);
+        const Ma2Header h = ma2_header(fh);
+        if (nel) *nel = h.nel;
+        if (hdr7) {
+            const int64_t v[7] = {h.nel, h.nactive, h.depth, h.d2, h.npts, h.nrank, h.noutflow};
+            for (int k = 0; k < 7; k++) hdr7[k] = v[k];
+        }
+    });
+}
+int nekb_ma2_read(const char *path, int nlv, int64_t e0, int64_t nel, int32_t *leaf, int64_t *vertex)
+{
+    return guard([&] {
+        FileHandle fh(path);
+        NEKB_REQUIRE(fh.f != nullptr, std::string("Cannot find map file! ") + path);
+        NEKB_REQUIRE(nlv == 4 || nlv == 8, "ma2_read: nlv must be 4 or 8");
+        const Ma2Header h = ma2_header(fh);
+        ma2_read(fh, h, nlv, e0, nel, leaf, vertex);
+    });
+}
+int nekb_assign_gllnid(int *gllnid, int64_t nelgt, int64_t nelgv, int np)
+{
+    return guard([&] {
+        NEKB_REQUIRE(gllnid && nelgt >= 0, "assign_gllnid: bad arguments");
+        std::vector<int> g(gllnid, gllnid + nelgt);
+        assign_gllnid(g, nelgt, nelgv, np);
+        memcpy(gllnid, g.data(), (size_t)nelgt * sizeof(int));
+    });
+}
 int nekb_setvert3d(int64_t *glo_num, int64_t *ngv, int nx, int64_t nel, const int64_t *vertex, int np)
 {
     return guard([&] {

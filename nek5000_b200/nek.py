@@ -134,6 +134,58 @@ def niterhm() -> int:
     return int(lib().nekb_niterhm())
 
 
+# --------------------------------------------------------------------------------------------- mesh files (host only)
+def re2_info(path: str) -> dict:
+    """core/reader_re2.f:543-639 header + section table of a .re2 file."""
+    nelgt, nelgv, ncurve = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    ldim, wd, nsec = C.c_int(0), C.c_int(0), C.c_int(0)
+    nbc = np.zeros(16, dtype=np.int64)
+    check(lib().nekb_re2_info(path.encode(), C.byref(nelgt), C.byref(ldim), C.byref(nelgv), C.byref(wd), C.byref(ncurve),
+                              C.byref(nsec), _ptr(nbc), 16))
+    return dict(nelgt=int(nelgt.value), ldim=int(ldim.value), nelgv=int(nelgv.value), wdsize=int(wd.value),
+                ncurve=int(ncurve.value), nbc=[int(v) for v in nbc[:nsec.value]])
+
+
+def re2_read_mesh(path: str, e0: int = 0, nel: int | None = None):
+    """Elements [e0, e0+nel) -> xc, yc, zc (nel, 2^ldim; preprocessor corner order), igroup."""
+    info = re2_info(path)
+    nel = info["nelgt"] - e0 if nel is None else nel
+    nv = 1 << info["ldim"]
+    xc, yc, zc = (np.zeros((nel, nv)) for _ in range(3))
+    grp = np.zeros(nel, dtype=np.int32)
+    check(lib().nekb_re2_read_mesh(path.encode(), e0, nel, _ptr(xc), _ptr(yc), _ptr(zc), _ptr(grp)))
+    return xc, yc, zc, grp
+
+
+def re2_read_bc(path: str, section: int = 0):
+    """One boundary-condition section -> cbc (nelgt, 6) of 3-character codes (blank where the file has no record),
+    bc (nelgt, 6, 5)."""
+    info = re2_info(path)
+    cbc = np.full((info["nelgt"], 6), b"   ", dtype="S3")
+    bc = np.zeros((info["nelgt"], 6, 5))
+    check(lib().nekb_re2_read_bc(path.encode(), section, C.c_void_p(cbc.ctypes.data), _ptr(bc)))
+    return cbc, bc
+
+
+def ma2_read(path: str, nlv: int = 8, e0: int = 0, nel: int | None = None):
+    """core/map2.f:712-941: (header[7], leaf[nel], vertex[nel, nlv]) of a .ma2 file."""
+    n = C.c_int64(0)
+    hdr = np.zeros(7, dtype=np.int64)
+    check(lib().nekb_ma2_info(path.encode(), C.byref(n), _ptr(hdr)))
+    nel = int(n.value) - e0 if nel is None else nel
+    leaf = np.zeros(nel, dtype=np.int32)
+    vertex = np.zeros((nel, nlv), dtype=np.int64)
+    check(lib().nekb_ma2_read(path.encode(), nlv, e0, nel, _ptr(leaf), _ptr(vertex)))
+    return hdr, leaf, vertex
+
+
+def assign_gllnid(leaf, nelgv: int | None = None, np_ranks: int = 1) -> np.ndarray:
+    """core/map2.f:943-1026 assign_gllnid: RSB leaves -> 0-based rank of every global element."""
+    g = np.ascontiguousarray(leaf, dtype=np.int32).copy()
+    check(lib().nekb_assign_gllnid(_ptr(g), len(g), len(g) if nelgv is None else nelgv, np_ranks))
+    return g
+
+
 # --------------------------------------------------------------------------------------------- numbering / gs
 def setvert3d(nx: int, nel: int, vertex, np_ranks: int = 1):
     """core/navier8.f:2004 setvert3d -> (glo_num, ngv).  Host only (no GPU needed)."""
@@ -307,13 +359,15 @@ def h1mg_free() -> None:
     lib().nekb_h1mg_free()
 
 
-def hsmg_setup(fbc, xm1, ym1, zm1, vertex, nelv: int, null_space: bool, nelgv: int, df, sr, ss, st) -> None:
+def hsmg_setup(fbc, xm1, ym1, zm1, vertex, nelv: int, null_space: bool, nelgv: int, df=None, sr=None, ss=None, st=None) -> None:
     """core/hsmg.f:22 hsmg_setup for the Pn-Pn-2 splitting; df, sr, ss, st are common /fastd/ as gen_fast leaves them
-    (df(lx1^3,nelv); s?(2*lx1^2,nelv), S in the first half, column-major)."""
+    (df(lx1^3,nelv); s?(2*lx1^2,nelv), S in the first half, column-major), or all None: gen_fast (core/fast3d.f:2-140) is
+    run by the library."""
     f = np.ascontiguousarray(fbc, dtype=np.int32).reshape(-1)
     v = np.ascontiguousarray(vertex, dtype=np.int64).reshape(-1)
     a = [np.ascontiguousarray(q, dtype=np.float64).reshape(-1) for q in (xm1, ym1, zm1)]
-    b = [np.ascontiguousarray(q, dtype=np.float64).reshape(-1) for q in (df, sr, ss, st)]
+    keep = [None if q is None else np.ascontiguousarray(q, dtype=np.float64).reshape(-1) for q in (df, sr, ss, st)]
+    b = [None if q is None else _ptr(q) for q in keep]
     check(lib().nekb_hsmg_setup(f, *a, v, nelv, int(null_space), nelgv, *b))
 
 

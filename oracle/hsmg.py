@@ -790,6 +790,113 @@ class Hsmg2:
         return e
 
 
+def semhat_weighted(n):
+    """core/fast3d.f:1181-1213 load_semhat_weighted: bh (GLL weights), and jgl, dgl (velocity GLL nodes -> pressure GL
+    nodes interpolation / derivative, :1280-1289) pre-multiplied by the GL weights bgl.  Returns bh[n+1], jgl[n-1,n+1],
+    dgl[n-1,n+1]."""
+    z, bh = zwgll(n + 1)
+    zgl, bgl = np.polynomial.legendre.leggauss(n - 1)
+    jgl, dgl = np.zeros((n - 1, n + 1)), np.zeros((n - 1, n + 1))
+    for i in range(n - 1):
+        w = fd_weights_full(zgl[i], z, 1)
+        jgl[i], dgl[i] = w[:, 0], w[:, 1]
+    return bh, bgl[:, None] * jgl, bgl[:, None] * dgl
+
+
+def fast1d_sem_op(b0, b1, l, r, ll, lm, lr, bh, jgl, jscl):
+    """core/fast3d.f:1410-1540 set_up_fast_1D_sem_op: G = J B^-1 J^T restricted to an element plus one node either side.
+    jgl[i-1, k] is the Fortran jgl(i,k), i = 1..n-1, k = 0..n."""
+    n = len(bh) - 1
+    J = lambda i, k: jgl[i - 1, k]
+    gl, gm, gr = (1.0, 1.0, 1.0) if jscl == 0 else (0.5 * ll, 0.5 * lm, 0.5 * lr)
+    gll, glm, gmm, gmr, grr = gl * gl, gl * gm, gm * gm, gm * gr, gr * gr
+    bm, bl, br = np.zeros(n + 1), np.zeros(n + 1), np.zeros(n + 1)
+    for i in range(1, n):
+        bm[i] = 2.0 / (lm * bh[i])
+    if b0 == 0:
+        bm[0] = 0.5 * lm * bh[0]
+        if l:
+            bm[0] = bm[0] + 0.5 * ll * bh[n]
+        bm[0] = 1.0 / bm[0]
+    if b1 == n:
+        bm[n] = 0.5 * lm * bh[n]
+        if r:
+            bm[n] = bm[n] + 0.5 * lr * bh[0]
+        bm[n] = 1.0 / bm[n]
+    if l:
+        for i in range(n):
+            bl[i] = 2.0 / (ll * bh[i])
+        bl[n] = bm[0]
+    if r:
+        for i in range(1, n + 1):
+            br[i] = 2.0 / (lr * bh[i])
+        br[0] = bm[n]
+    g = np.zeros((n + 1, n + 1))
+    for j in range(1, n):
+        for i in range(1, n):
+            for k in range(b0, b1 + 1):
+                g[i, j] = g[i, j] + gmm * J(i, k) * bm[k] * J(j, k)
+    if l:
+        for i in range(1, n):
+            g[i, 0] = glm * J(i, 0) * bm[0] * J(n - 1, n)
+            g[0, i] = g[i, 0]
+        for i in range(n + 1):
+            g[0, 0] = g[0, 0] + gll * J(n - 1, i) * bl[i] * J(n - 1, i)
+    else:
+        g[0, 0] = 1.0
+    if r:
+        for i in range(1, n):
+            g[i, n] = gmr * J(i, n) * bm[n] * J(1, 0)
+            g[n, i] = g[i, n]
+        for i in range(n + 1):
+            g[n, n] = g[n, n] + grr * J(1, i) * br[i] * J(1, i)
+    else:
+        g[n, n] = 1.0
+    return g
+
+
+def fast1d_sem(lbc, rbc, ll, lm, lr, bh, jgl, dgl):
+    """core/fast3d.f:1351-1408 set_up_fast_1D_sem: eigen-system of the 1-D E~ x = lam B~ x; codes of get_fast_bc with
+    bsym = 3 (0 element, 1 outflow, 2 wall, 3 symmetry).  Returns S (eigenvectors in columns, boundary rows zeroed), lam."""
+    n = len(bh) - 1
+    eb0 = 1 if lbc in (2, 3) else 0
+    eb1 = n - 1 if rbc in (2, 3) else n
+    bb0 = 1 if lbc == 2 else 0
+    bb1 = n - 1 if rbc == 2 else n
+    l, r = lbc == 0, rbc == 0
+    e = fast1d_sem_op(eb0, eb1, l, r, ll, lm, lr, bh, dgl, 0)
+    b = fast1d_sem_op(bb0, bb1, l, r, ll, lm, lr, bh, jgl, 1)
+    lam, s = scipy.linalg.eigh(e, b, lower=False, driver="gv")     # generalev -> dsygv(1,'V','U')
+    if not l:
+        s[0, :] = 0.0
+    if not r:
+        s[n, :] = 0.0
+    return s, lam
+
+
+def gen_fast(case, fbc):
+    """core/fast3d.f:2-140 gen_fast with param(44) = 0 (the default: top-level Schwarz on restrictions of E): the
+    common /fastd/ data of the Pn-Pn-2 preconditioner.  Returns S[e,3,lx1,lx1], D[e,lx1,lx1,lx1] (D = df)."""
+    mg = H1MG(case, fbc)                      # swap_lengths: ll, lm, lr
+    nl = case.nx
+    bh, jgl, dgl = semhat_weighted(nl - 1)
+    E = case.nel
+    S, D = np.zeros((E, 3, nl, nl)), np.zeros((E, nl, nl, nl))
+    cache = {}
+    for e in range(E):
+        lam = []
+        for d in range(3):
+            key = (int(mg.fbc[e, 2 * d]), int(mg.fbc[e, 2 * d + 1]), mg.ll[d, e], mg.lm[d, e], mg.lr[d, e])
+            if key not in cache:
+                cache[key] = fast1d_sem(*key, bh, jgl, dgl)
+            S[e, d], l1 = cache[key]
+            lam.append(l1)
+        eps = 1e-5 * (lam[0][1:-1].max() + lam[1][1:-1].max() + lam[2][1:-1].max())
+        diag = lam[0][None, None, :] + lam[1][None, :, None] + lam[2][:, None, None]
+        D[e] = np.where(diag > eps, 1.0 / np.where(diag > eps, diag, 1.0), 0.0)
+    return S, D
+
+
 def hsmg_orders_pnpn2(lx1):
     """core/hsmg.f:1604-1664 hsmg_setup_mg_nx."""
     mgn2 = [1, 2, 2, 2, 2, 3, 3, 5, 5, 5]

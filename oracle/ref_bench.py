@@ -67,9 +67,16 @@ def _worker(rank, m, plan, bar, q):
 
 def host_cores() -> int:
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except Exception:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    try:  # a cgroup CPU quota below the visible core count would make P processes time-share
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return n
 
 
 def run(steps: int, warmup: int, m: int = 16, nproc: int | None = None, target_s: float = 5.0, max_its: int = 500):
@@ -91,9 +98,14 @@ def run(steps: int, warmup: int, m: int = 16, nproc: int | None = None, target_s
         ps = [ctx.Process(target=_worker, args=(r, m, plan, bar, q)) for r in range(nproc)]
         for p in ps:
             p.start()
-        res = [q.get() for _ in ps]
+        try:
+            res = [q.get(timeout=600) for _ in ps]          # a worker that died without reporting must not hang the bench
+        except Exception:
+            for p in ps:
+                p.kill()
+            raise RuntimeError("reference worker did not report within 600 s")
         for p in ps:
-            p.join()
+            p.join(30)
         bad = [r for r in res if r[1] is None]
         if bad:
             raise RuntimeError(f"reference worker failed: {bad[0][2]}")
@@ -115,5 +127,14 @@ def run(steps: int, warmup: int, m: int = 16, nproc: int | None = None, target_s
 
 
 if __name__ == "__main__":
+    import argparse
     import json
-    print(json.dumps(run(steps=2, warmup=1, target_s=float(sys.argv[1]) if len(sys.argv) > 1 else 3.0)))
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--target-s", type=float, default=3.0)
+    ap.add_argument("--nproc", type=int, default=None)
+    a = ap.parse_args()
+    if not available(16):
+        raise SystemExit("oracle/_ref/libnekref_lx8e4096g2.so is neither prebuilt nor buildable here")
+    print(json.dumps(run(steps=a.steps, warmup=a.warmup, nproc=a.nproc, target_s=a.target_s)))

@@ -191,7 +191,24 @@ def ref_pnpn2():
     return out
 
 
-REFERENCE = dict(core=ref_core, bp5=ref_bp5, h1mg=ref_h1mg, h1mg_neumann=ref_h1mg_neumann, fdm=ref_fdm, pnpn2=ref_pnpn2)
+MAP_NP = (1, 2, 3, 4, 5, 7, 8, 16, 48)
+
+
+def ref_map():
+    """core/map2.f:943-1026 assign_gllnid (incl. core/math.f isort / iswapt_ip for rank counts that are not a power of
+    two) on the RSB leaves of the reference's examples/bp5/bp5.ma2 (tests/golden/bp5_fixture.npz)."""
+    from oracle.ref import Ref
+    R = Ref(8, 8, 64, fresh=True)
+    leaf = np.load(os.path.join(os.path.dirname(GOLDEN), "bp5_fixture.npz"))["leaf"].astype(np.int32)
+    out = {}
+    for npr in MAP_NP:
+        g, scratch = leaf.copy(), np.zeros(len(leaf), dtype=np.int32)
+        R.call("assign_gllnid", g, scratch, len(g), len(g), npr)
+        out[f"gllnid_np{npr}"] = g
+    return out
+
+
+REFERENCE = dict(core=ref_core, map=ref_map, bp5=ref_bp5, h1mg=ref_h1mg, h1mg_neumann=ref_h1mg_neumann, fdm=ref_fdm, pnpn2=ref_pnpn2)
 
 
 def reference_all():

@@ -16,6 +16,10 @@ pytestmark = pytest.mark.gpu
 
 TOL_APPLY = 1e-12
 TOL_FIELD = 1e-10
+# A solve run to convergence is compared at the accuracy the solver was asked for, not at 1e-10: CG amplifies the 1e-16
+# differences of FMA contraction and of the reduction order by the condition number over its ~100 iterations (the fixed
+# 20-iteration runs next to each converged run are held to 1e-10, and the iteration counts must be identical).
+TOL_CONVERGED = 1e-7
 
 G = refcases.load_golden()
 
@@ -86,12 +90,12 @@ def test_cggo_and_hmholtz_against_the_reference(nek):
     x = np.zeros(n)
     it = nek.cggo(x, g["cggo_f"], g["h1"], g["h2"], g["v1mask"], g["vmult"], 1, 1e-6, 500, 1, g["binvm1"], "VELX")
     assert it == g["cggo_it"][0]                                               # identical iteration count
-    assert relmax(x, g["cggo_x"]) <= TOL_FIELD
+    assert relmax(x, g["cggo_x"]) <= TOL_CONVERGED
     nek.set_param(22, 0.0)
     x, rhs = np.zeros(n), g["hmh_rhs"].copy()
     it = nek.hmholtz("VELX", x, rhs, g["h1"], g["h2"], g["v1mask"], g["vmult"], 1, 1e-7, 300, 1)
     assert relmax(rhs, g["hmh_rhs_out"]) <= TOL_APPLY                          # dssum + mask in place
-    assert it == g["hmh_it"][0] and relmax(x, g["hmh_x"]) <= TOL_FIELD
+    assert it == g["hmh_it"][0] and relmax(x, g["hmh_x"]) <= TOL_CONVERGED
 
 
 def test_bp5_driver_against_the_reference(nek):
@@ -206,3 +210,25 @@ def test_pnpn2_hsmg_solve_against_the_reference(nek):
     e, r = np.zeros(6 ** 3 * E), g["r"].copy()
     nek.hsmg_solve(e, r)
     assert relmax(e, g["e"]) <= TOL_FIELD
+
+
+def test_pnpn2_gen_fast_on_the_library_side_against_the_reference(nek):
+    """nekb_hsmg_setup with no /fastd/ arrays: gen_fast (core/fast3d.f:2-140) runs in the library; the resulting
+    preconditioner must equal the reference's hsmg_solve, and local_solves_fdm the oracle's with the reference's data."""
+    g, case = G["pnpn2"], refcases.case_of("pnpn2")
+    E = case.nel
+    nek.set_nel(E, E)
+    nek.set_gll(case.z, case.w)
+    nek.set_dxyz(case.D, case.Dt)
+    nek.set_geom(*case.geom()[:7])
+    nek.set_ifdfrm(None)
+    fbc = refcases.fbc_of("pnpn2", case)
+    nek.hsmg_setup(fbc, case.xm1, case.ym1, case.zm1, case.vertex, E, False, E)
+    e, r = np.zeros(6 ** 3 * E), g["r"].copy()
+    nek.hsmg_solve(e, r)
+    assert relmax(e, g["e"]) <= TOL_FIELD
+    S, D = refcases.fastd_to_S(g, E)
+    ref = hsmg.Hsmg2(case, fbc, S, D)
+    u = np.zeros(6 ** 3 * E)
+    nek.local_solves_fdm(u, g["r"])
+    assert relmax(u, ref.local_solves_fdm(g["r"])) <= TOL_FIELD

@@ -137,3 +137,16 @@ def test_pnpn2_hsmg_solve_with_the_reference_fastd():
     S, D = refcases.fastd_to_S(g, c.nel)
     h = hsmg.Hsmg2(c, refcases.fbc_of("pnpn2", c), S, D)
     assert relmax(h.solve(g["r"].copy()), g["e"]) <= 1e-12
+
+
+def test_gen_fast_reproduces_the_reference_fastd():
+    """core/fast3d.f:2-140 gen_fast (param(44) = 0): eigenvalues through df, eigenvectors up to the sign LAPACK leaves free,
+    and the preconditioner built from the oracle's own /fastd/ data equals the reference's hsmg_solve."""
+    g, c = G["pnpn2"], refcases.case_of("pnpn2")
+    Sr, Dr = refcases.fastd_to_S(g, c.nel)
+    fbc = refcases.fbc_of("pnpn2", c)
+    S, D = hsmg.gen_fast(c, fbc)
+    assert relmax(D, Dr) <= 1e-12
+    assert np.abs(np.abs(S) - np.abs(Sr)).max() <= 1e-11
+    h = hsmg.Hsmg2(c, fbc, S, D)
+    assert relmax(h.solve(g["r"].copy()), g["e"]) <= 1e-12
