@@ -25,14 +25,14 @@ def lib_path(m: int) -> str:
 
 
 def available(m: int = 16) -> bool:
-    if os.path.exists(lib_path(m)):
-        return True
+    """Builds / refreshes the library ONCE, in the calling process (the forked workers must find it up to date: eight of
+    them rebuilding the same file at once is a race).  On the GPU box, where /root/reference is absent, the prebuilt file
+    is used as it is."""
     try:
         from . import ref_build
-        ref_build.build(LX1, LX1, m ** 3, LGMRES)
-        return True
+        return os.path.exists(ref_build.build(LX1, LX1, m ** 3, LGMRES))
     except Exception:
-        return False
+        return os.path.exists(lib_path(m)) and not os.path.isdir(os.path.join(os.environ.get("NEK_REFERENCE", "/root/reference"), "core"))
 
 
 def _worker(rank, m, plan, bar, q):
