@@ -123,10 +123,14 @@ def _pressure(name):
     R.call("set_overlap")
     pmask = rc.fld("pmask")
     rng = np.random.default_rng(3)
-    rhs = rng.standard_normal(n)
+    h1, h2 = np.ones(n), np.zeros(n)
+    # a right-hand side in the range of the operator (A times a continuous field): with the all-Neumann null space an
+    # inconsistent coarse rhs has no meaningful answer -- XXT pins a different unknown for every rank count
+    # (crs_xxt.c:893-899, 926-949) -- and the residuals the preconditioner sees in hmh_gmres are consistent
+    xr = case.dssum(rng.standard_normal(n)) * case.mult * pmask
+    rhs = case.dssum(case.axhelm(xr, h1, h2)) * pmask
     z, r = np.zeros(n), rhs.copy()
     R.call("h1mg_solve", z, r, False)
-    h1, h2 = np.ones(n), np.zeros(n)
     xe = case.dssum(rng.standard_normal(n)) * case.mult * pmask
     b = case.dssum(case.axhelm(xe, h1, h2)) * pmask
     tol = 1e-8
