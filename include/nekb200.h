@@ -165,6 +165,23 @@ int nekb_set_v1mask(const double *v1mask);
 int nekb_set_ifield(int ifield);
 int nekb_set_field_handle(int ifield, int gs_handle);
 int nekb_set_step_info(int istep, double volvm1, double voltm1);
+/* core/induct.f:1022-1090 ophinv(o1,o2,o3,i1,i2,i3,h1,h2,tolh,nmxhi): o_k = (h1 A + h2 B)^-1 i_k for the three velocity
+ * components -- in the reference three hsolve -> hmholtz -> cggo calls in a row (standard branch: ifstrs = .false., no
+ * residual projection), here ONE fused 3-right-hand-side PCG (hcg.cuh: factors, h1, h2 B and the diagonal are streamed once
+ * per element for all three components; each component keeps its own scalars, tolerance (chktcg1) and exit test, so
+ * iteration counts equal those of the three separate solves).  i1..i3 return dssum'ed and masked as hmholtz leaves them.
+ * COMMON state: v1mask, v2mask, v3mask, vmult (core/SOLN) via nekb_set_velocity_state; binvm1 via nekb_set_binv;
+ * volvm1/istep via nekb_set_step_info; param(22).  nekb_niterhm3: niterhm of the three solves (the reference's /iterhm/
+ * holds the last).  nekb_ophinv_dev: the same on device pointers with explicit masks/mult/binv; hist_host (may be NULL)
+ * receives 3 rows of 3*(min(maxit,900)+2) doubles (rtz1, rbn2, rho per iteration). */
+void ophinv_(double *o1, double *o2, double *o3, double *i1, double *i2, double *i3, const double *h1, const double *h2,
+             const double *tolh, const int *nmxhi);
+int nekb_set_velocity_state(const double *v1mask, const double *v2mask, const double *v3mask, const double *vmult);
+int nekb_niterhm3(int *niter3);
+int nekb_ophinv_dev(double *o1, double *o2, double *o3, double *i1, double *i2, double *i3, const double *h1, const double *h2,
+                    const double *m1, const double *m2, const double *m3, const double *mult, const double *binv, double tolh,
+                    int maxit, int *niter3, double *hist_host);
+
 /* INPUT param(idx), 1-based: the path reads param(21) (pressure tolerance), param(22) (Helmholtz tolerance; < 0 relative,
  * core/hmholtz.f:764).  MASS binvm1 / bintm1 (host, lx1^3*nelv / nelt doubles; bintm1 may be NULL) for hmholtz. */
 int nekb_set_param(int idx, double value);

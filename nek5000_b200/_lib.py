@@ -102,6 +102,9 @@ def lib() -> C.CDLL:
     L.nekb_cggos_dev.argtypes = [vp, vp, vp, vp, C.c_double, C.c_int, ip, vp]
     L.nekb_cggo_dev.argtypes = [vp] * 7 + [C.c_int, C.c_double, C.c_int, ip, vp]
     L.nekb_setvert3d.argtypes = [i64p, C.POINTER(C.c_int64), C.c_int, C.c_int64, i64p, C.c_int]
+    L.nekb_set_velocity_state.argtypes = [vp, vp, vp, vp]
+    L.nekb_niterhm3.argtypes = [vp]
+    L.nekb_ophinv_dev.argtypes = [vp] * 13 + [C.c_double, C.c_int, vp, vp]
     L.nekb_re2_info.argtypes = [C.c_char_p, C.POINTER(C.c_int64), ip, C.POINTER(C.c_int64), ip, C.POINTER(C.c_int64), ip, vp, C.c_int]
     L.nekb_re2_read_mesh.argtypes = [C.c_char_p, C.c_int64, C.c_int64, vp, vp, vp, vp]
     L.nekb_re2_read_bc.argtypes = [C.c_char_p, C.c_int, vp, vp]
@@ -144,6 +147,8 @@ def lib() -> C.CDLL:
     L.glsc3_.restype = C.c_double
     L.hmholtz_.argtypes = [C.c_char_p, vp, vp, vp, vp, vp, vp, ip, dp, ip, ip, C.c_size_t]
     L.hmholtz_.restype = None
+    L.ophinv_.argtypes = [vp] * 8 + [dp, ip]
+    L.ophinv_.restype = None
     L.nekb_set_param.argtypes = [C.c_int, C.c_double]
     L.nekb_set_binv.argtypes = [vp, vp]
     # section F: pressure preconditioner + GMRES

@@ -74,6 +74,8 @@ struct Ctx {
     int niterhm = 0;
     double param[201] = {0};       // INPUT param(1:200) entries the path reads (18, 21, 22); 1-based
     DevBuf<double> binvm1, bintm1; // MASS binvm1 / bintm1 for hmholtz
+    DevBuf<double> vmask[3], vmult; // SOLN v1mask,v2mask,v3mask and vmult for ophinv
+    int niter3[3] = {0, 0, 0};     // niterhm of the three component solves of the last ophinv
 
     // gs handles ---------------------------------------------------------------------------------
     std::vector<GsMap> gs;

@@ -3,6 +3,7 @@
 #include "../../include/nekb200.h"
 
 #include "gmres.cuh"
+#include "hcg.cuh"
 #include "readers.cuh"
 
 using namespace nekb;
@@ -424,6 +425,105 @@ int nekb_set_binv(const double *binvm1, const double *bintm1)
     });
 }
 int nekb_niterhm(void) { return ctx().niterhm; }
+int nekb_set_velocity_state(const double *v1mask, const double *v2mask, const double *v3mask, const double *vmult)
+{
+    return guard([&] {
+        require_init();
+        Ctx &c = ctx();
+        const size_t n = (size_t)c.nelv * c.nxyz;
+        const double *m[3] = {v1mask, v2mask, v3mask};
+        for (int k = 0; k < 3; k++)
+            if (m[k]) c.vmask[k].upload(m[k], n, c.stream);
+        if (vmult) c.vmult.upload(vmult, n, c.stream);
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+int nekb_niterhm3(int *niter3)
+{
+    return guard([&] {
+        for (int k = 0; k < 3; k++) niter3[k] = ctx().niter3[k];
+    });
+}
+
+// Three Helmholtz solves sharing h1, h2 (ophinv's body): rhs_c <- mask_c * dssum(rhs_c) in place, tolerance per component
+// through chktcg1 exactly as hmholtz does, then the fused 3-right-hand-side PCG (hcg.cuh) or, when a branch it does not
+// provide is needed, cggo_run component by component.  All pointers are device pointers.
+static void ophinv_dev(double *const *o, double *const *rhs, const double *h1, const double *h2, const double *const *mask,
+                       const double *mult, const double *binv, double tolh, int maxit, int *niter3, double *hist_host)
+{
+    Ctx &c = ctx();
+    const int nel = c.nelv;
+    const int64_t n = (int64_t)nel * c.nxyz;
+    NEKB_REQUIRE(c.volvm1 > 0.0, "volvm1 not registered (nekb_set_step_info)");
+    // ifh2 decides whether chktcg1's axhelm carries the mass term
+    absmax_kernel<<<cg_grid(n), CG_THREADS, 0, c.stream>>>(h2, n, &c.sc.p->work[3], c.partials.p, &c.sc.p->counter[0]);
+    NEKB_LAUNCHED();
+    comm_allreduce_max(&c.sc.p->work[3], 1);
+    double h2max = 0.0;
+    NEKB_CUDA(cudaMemcpyAsync(&h2max, &c.sc.p->work[3], sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    double tol[3];
+    for (int k = 0; k < 3; k++) {
+        gs_op(field_handle(), rhs[k], 1, mask[k]);                                   // hmholtz.f:55-56
+        tol[k] = fabs(tolh);
+        if (c.param[22] == 0.0 || c.istep <= 10)                                     // :59-60
+            tol[k] = chktcg1_dev(tol[k], rhs[k], h1, h2max > 0.0 ? h2 : nullptr, mask[k], mult, binv, nel, c.volvm1);
+        if (tolh < 0) tol[k] = tolh;                                                 // :62
+    }
+    const double *f[3] = {rhs[0], rhs[1], rhs[2]};
+    if (hcg_applicable(3) &&
+        hcg_run(3, o, f, h1, h2, mask, mult, binv, field_handle(), nel, c.volvm1, tol, maxit, c.istep, niter3, hist_host))
+        return;
+    for (int k = 0; k < 3; k++) {
+        CggoArgs a{o[k], rhs[k], h1, h2, mask[k], mult, binv, field_handle(), nel, c.volvm1, c.istep};
+        niter3[k] = cggo_run(a, tol[k], maxit, nullptr);
+    }
+}
+int nekb_ophinv_dev(double *o1, double *o2, double *o3, double *i1, double *i2, double *i3, const double *h1, const double *h2,
+                    const double *m1, const double *m2, const double *m3, const double *mult, const double *binv, double tolh, int maxit,
+                    int *niter3, double *hist_host)
+{
+    return guard([&] {
+        require_init();
+        double *o[3] = {o1, o2, o3}, *r[3] = {i1, i2, i3};
+        const double *m[3] = {m1, m2, m3};
+        int it[3] = {0, 0, 0};
+        ophinv_dev(o, r, h1, h2, m, mult, binv, tolh, maxit, it, hist_host);
+        for (int k = 0; k < 3; k++) ctx().niter3[k] = it[k];
+        ctx().niterhm = it[2];
+        if (niter3)
+            for (int k = 0; k < 3; k++) niter3[k] = it[k];
+    });
+}
+// core/induct.f:1022-1090 ophinv(o1,o2,o3,i1,i2,i3,h1,h2,tolh,nmxhi): the standard branch (ifstrs = .false., no residual
+// projection: param(93) = 0 or ifprojfld(ifield) = .false.), ifield = 1.  v1mask..v3mask, vmult (nekb_set_velocity_state) and
+// binvm1 (nekb_set_binv) are the COMMON state the reference reads.  i1..i3 come back dssum'ed and masked, as hmholtz leaves them.
+void ophinv_(double *o1, double *o2, double *o3, double *i1, double *i2, double *i3, const double *h1, const double *h2,
+             const double *tolh, const int *nmxhi)
+{
+    guard_fortran("ophinv", [&] {
+        require_init();
+        Ctx &c = ctx();
+        const size_t n = (size_t)c.nelv * c.nxyz;
+        NEKB_REQUIRE(c.vmask[0].n >= n && c.vmask[1].n >= n && c.vmask[2].n >= n && c.vmult.n >= n,
+                     "ophinv: v1mask, v2mask, v3mask, vmult not registered (nekb_set_velocity_state)");
+        NEKB_REQUIRE(c.binvm1.n >= n, "ophinv: binvm1 not registered (nekb_set_binv)");
+        for (int k = 0; k < 8; k++) c.stage[k].ensure(n);
+        const double *src[5] = {i1, i2, i3, h1, h2};
+        for (int k = 0; k < 5; k++)
+            NEKB_CUDA(cudaMemcpyAsync(c.stage[k + 3].p, src[k], n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        double *o[3] = {c.stage[0].p, c.stage[1].p, c.stage[2].p}, *r[3] = {c.stage[3].p, c.stage[4].p, c.stage[5].p};
+        const double *m[3] = {c.vmask[0].p, c.vmask[1].p, c.vmask[2].p};
+        ophinv_dev(o, r, c.stage[6].p, c.stage[7].p, m, c.vmult.p, c.binvm1.p, *tolh, *nmxhi, c.niter3, nullptr);
+        c.niterhm = c.niter3[2];
+        double *dst[3] = {o1, o2, o3}, *rdst[3] = {i1, i2, i3};
+        for (int k = 0; k < 3; k++) {
+            NEKB_CUDA(cudaMemcpyAsync(dst[k], o[k], n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+            NEKB_CUDA(cudaMemcpyAsync(rdst[k], r[k], n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        }
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
 
 // ---------------------------------------------------------------------------------------------------- gs (device API)
 int nekb_gs_setup(int *handle, const int64_t *id_host, int64_t n)
@@ -560,7 +660,7 @@ int nekb_cggo_dev(double *x_dev, const double *f_dev, const double *h1_dev, cons
         const double vol = imsh == 1 ? c.volvm1 : c.voltm1;
         NEKB_REQUIRE(vol > 0.0, "volvm1/voltm1 not registered (nekb_set_step_info)");
         CggoArgs a{x_dev, f_dev, h1_dev, h2_dev, mask_dev, mult_dev, binv_dev, field_handle(), imsh == 1 ? c.nelv : c.nelt, vol, c.istep};
-        c.niterhm = cggo_run(a, tin, maxit, hist_host);
+        c.niterhm = cggo_solve(a, tin, maxit, hist_host);
         NEKB_CUDA(cudaStreamSynchronize(c.stream));
         if (niter) *niter = c.niterhm;
     });
@@ -721,7 +821,7 @@ void cggo_(double *x, const double *f, const double *h1, const double *h2, const
         NEKB_REQUIRE(vol > 0.0, "volvm1/voltm1 not registered (nekb_set_step_info)");
         CggoArgs a{c.stage[0].p, c.stage[1].p, c.stage[2].p, c.stage[3].p, c.stage[4].p, c.stage[5].p, c.stage[6].p,
                    field_handle(), nel, vol, c.istep};
-        c.niterhm = cggo_run(a, *tin, *maxit, nullptr);
+        c.niterhm = cggo_solve(a, *tin, *maxit, nullptr);
         NEKB_CUDA(cudaMemcpyAsync(x, c.stage[0].p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
         NEKB_CUDA(cudaStreamSynchronize(c.stream));
     });
@@ -761,7 +861,7 @@ void hmholtz_(const char *name, double *u, double *rhs, const double *h1, const 
             return;
         }
         CggoArgs a{c.stage[0].p, d_rhs, d_h1, d_h2, d_mask, d_mult, binv.p, field_handle(), nel, vol, c.istep};
-        c.niterhm = cggo_run(a, tol, *maxit, nullptr);
+        c.niterhm = cggo_solve(a, tol, *maxit, nullptr);
         NEKB_CUDA(cudaMemcpyAsync(u, c.stage[0].p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
         NEKB_CUDA(cudaMemcpyAsync(rhs, d_rhs, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
         NEKB_CUDA(cudaStreamSynchronize(c.stream));

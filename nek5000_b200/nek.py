@@ -301,6 +301,21 @@ def hmholtz(name: str, u, rhs, h1, h2, mask, mult, imsh: int, tli: float, maxit:
     return niterhm()
 
 
+def set_velocity_state(v1mask, v2mask, v3mask, vmult) -> None:
+    """COMMON state ophinv reads: core/SOLN v1mask, v2mask, v3mask, vmult."""
+    a = [np.ascontiguousarray(q, dtype=np.float64).reshape(-1) for q in (v1mask, v2mask, v3mask, vmult)]
+    check(lib().nekb_set_velocity_state(*[_ptr(q) for q in a]))
+
+
+def ophinv(o1, o2, o3, i1, i2, i3, h1, h2, tolh: float, nmxhi: int):
+    """core/induct.f:1022 ophinv(o1,o2,o3,i1,i2,i3,h1,h2,tolh,nmxhi); returns the three iteration counts."""
+    lib().ophinv_(_ptr(o1), _ptr(o2), _ptr(o3), _ptr(i1), _ptr(i2), _ptr(i3), _ptr(h1), _ptr(h2),
+                  C.byref(C.c_double(tolh)), _i(nmxhi))
+    it = np.zeros(3, dtype=np.int32)
+    check(lib().nekb_niterhm3(_ptr(it)))
+    return [int(v) for v in it]
+
+
 def set_param(idx: int, value: float) -> None:
     check(lib().nekb_set_param(idx, float(value)))
 

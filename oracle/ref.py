@@ -159,7 +159,7 @@ class RefCase:
         ex, ey, ez = eid % case.nelx, (eid // case.nelx) % case.nely, eid // (case.nelx * case.nely)
         for f, on, ax, di in ((4, ex == 0, 0, 0), (2, ex == case.nelx - 1, 0, 1), (1, ey == 0, 1, 2),
                               (3, ey == case.nely - 1, 1, 3), (5, ez == 0, 2, 4), (6, ez == case.nelz - 1, 2, 5)):
-            cbc[f - 1, eid[on], 1] = b"P  " if per[ax] else (b"v  " if dflag[di] else b"O  ")
+            cbc[f - 1, eid[on], 1] = b"P  " if per[ax] else {0: b"O  ", 1: b"v  ", 2: b"SYM"}[int(dflag[di])]
         # setlog (core/bdry.f:24,50-57): no outflow face anywhere -> the pressure has the constant null space
         R.set("ifvcor", int(not (cbc[:, :E, 1] == b"O  ").any()))
         sh = (nx, nx, nx, E)

@@ -25,6 +25,7 @@ MESH = {
     "neumann": ((3, 2, 2), (1, 1, 1, 1, 1, 1), 0.05),
     "fdm": ((3, 3, 2), (1, 1, 0, 0, 1, 1), 0.02),
     "pnpn2": ((3, 2, 2), (1, 1, 1, 1, 1, 0), 0.0),
+    "ophinv": ((3, 2, 2), (1, 2, 1, 2, 1, 0), 0.05),      # 2 = 'SYM': the three velocity masks differ
 }
 
 
@@ -195,6 +196,38 @@ def ref_pnpn2():
     return out
 
 
+def ref_ophinv():
+    """core/induct.f:1022-1090 ophinv (standard branch: three hsolve -> hmholtz -> cggo calls, core/navier4.f:562-634,
+    core/hmholtz.f:2-69,611-846) on a box with wall, symmetry and outflow sides, variable h1 and h2; once to convergence and
+    once with 15 fixed iterations.  The per-component iteration counts come from three separate hmholtz calls, which the
+    reference's ophinv must (and does) reproduce exactly."""
+    case = case_of("ophinv")
+    rc = _ref(case)
+    R, n = rc.R, case.n
+    masks = [rc.fld(m) for m in ("v1mask", "v2mask", "v3mask")]
+    rng = np.random.default_rng(7)
+    h1, h2 = 1.0 + 0.3 * rng.random(n), 5.0 + rng.random(n)
+    rhs = [case.bm1() * rng.standard_normal(n) for _ in range(3)]
+    out = dict(v1mask=masks[0], v2mask=masks[1], v3mask=masks[2], vmult=rc.fld("vmult"), binvm1=rc.fld("binvm1"),
+               volvm1=np.array([R.get("volvm1")]), h1=h1, h2=h2, i1=rhs[0], i2=rhs[1], i3=rhs[2])
+    R.var("param")[21] = 0.0
+    R.var("param")[92] = 0.0
+    R.set("istep", 20), R.set("ifield", 1), R.set("ifstrs", 0)
+    for key, tol, maxit in (("", 1e-8, 300), ("_15", -1e-30, 15)):
+        o = [np.zeros(n) for _ in range(3)]
+        ii = [a.copy() for a in rhs]
+        R.call("ophinv", o[0], o[1], o[2], ii[0], ii[1], ii[2], h1, h2, tol, maxit)
+        its = []
+        for k, nm in enumerate(("VELX", "VELY", "VELZ")):
+            x, r = np.zeros(n), rhs[k].copy()
+            R.call("hmholtz", nm, x, r, h1, h2, masks[k], out["vmult"], 1, tol, maxit, k + 1)
+            its.append(int(R.get("niterhm")))
+            assert np.array_equal(x, o[k]) and np.array_equal(r, ii[k])
+            out[f"o{k + 1}{key}"], out[f"r{k + 1}{key}"] = o[k], ii[k]
+        out["its" + key] = np.array(its)
+    return out
+
+
 MAP_NP = (1, 2, 3, 4, 5, 7, 8, 16, 48)
 
 
@@ -212,7 +245,7 @@ def ref_map():
     return out
 
 
-REFERENCE = dict(core=ref_core, map=ref_map, bp5=ref_bp5, h1mg=ref_h1mg, h1mg_neumann=ref_h1mg_neumann, fdm=ref_fdm, pnpn2=ref_pnpn2)
+REFERENCE = dict(core=ref_core, map=ref_map, ophinv=ref_ophinv, bp5=ref_bp5, h1mg=ref_h1mg, h1mg_neumann=ref_h1mg_neumann, fdm=ref_fdm, pnpn2=ref_pnpn2)
 
 
 def reference_all():

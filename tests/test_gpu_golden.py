@@ -232,3 +232,66 @@ def test_pnpn2_gen_fast_on_the_library_side_against_the_reference(nek):
     u = np.zeros(6 ** 3 * E)
     nek.local_solves_fdm(u, g["r"])
     assert relmax(u, ref.local_solves_fdm(g["r"])) <= TOL_FIELD
+
+
+def _register_ophinv(nek, g, case):
+    E = case.nel
+    nek.set_nel(E, E)
+    nek.set_gll(case.z, case.w)
+    nek.set_dxyz(case.D, case.Dt)
+    nek.set_geom(*case.geom()[:7])
+    nek.set_ifdfrm(None)
+    h, _ = nek.setupds(8, E, case.vertex)
+    nek.set_ifield(1)
+    nek.set_field_handle(1, h)
+    nek.set_step_info(20, float(g["volvm1"][0]))
+    nek.set_binv(g["binvm1"])
+    nek.set_param(22, 0.0)
+    nek.set_velocity_state(g["v1mask"], g["v2mask"], g["v3mask"], g["vmult"])
+
+
+def test_ophinv_fused_three_rhs_against_the_reference(nek):
+    """core/induct.f:1022-1090 ophinv: the reference runs three hmholtz/cggo solves in a row; the library runs ONE fused
+    3-right-hand-side PCG (hcg.cuh).  Every component must stop at the reference's own iteration count (133 / 128 / 153 here)
+    and reproduce its iterates."""
+    g, case = G["ophinv"], refcases.case_of("ophinv")
+    _register_ophinv(nek, g, case)
+    n = case.n
+    for key, tol, maxit, ftol in (("_15", -1e-30, 15, TOL_FIELD), ("", 1e-8, 300, TOL_CONVERGED)):
+        o = [np.zeros(n) for _ in range(3)]
+        i = [g[f"i{k + 1}"].copy() for k in range(3)]
+        its = nek.ophinv(*o, *i, g["h1"], g["h2"], tol, maxit)
+        assert its == g["its" + key].tolist()                                   # identical iteration counts, per component
+        for k in range(3):
+            assert relmax(i[k], g[f"r{k + 1}{key}"]) <= TOL_APPLY                # rhs dssum'ed + masked in place
+            assert relmax(o[k], g[f"o{k + 1}{key}"]) <= ftol, (key, k)
+
+
+def test_fused_and_stock_cggo_agree(nek, monkeypatch):
+    """The fused path (hcg.cuh, default for lx1 = 8 Jacobi solves) against the kernel-per-statement cggo_run (NEKB_HCG=0 is
+    read once per process, so the stock path is reached through a right-hand side the fused path declines: here a mask that
+    is not 0/1)."""
+    from nek5000_b200._lib import check, lib
+    g, case = G["ophinv"], refcases.case_of("ophinv")
+    _register_ophinv(nek, g, case)
+    n = case.n
+    mask = g["v2mask"]
+    f = case.dssum(g["i2"]) * mask
+    xs = []
+    for mk in (mask, np.where(mask != 0, 1.0 + 0.0, 0.0), mask * (1.0 + 1e-300)):
+        x = np.zeros(n)
+        it = nek.cggo(x, f, g["h1"], g["h2"], mk, g["vmult"], 1, -1e-30, 25, 1, g["binvm1"], "VELY")
+        assert it == 25
+        xs.append(x)
+    assert relmax(xs[0], xs[1]) == 0.0
+    # a genuinely non-binary mask (0 / 0.5) takes the stock path; scaling the masked rows by 1/2 changes the operator, so
+    # compare against the oracle instead of against the fused run
+    half = np.where(mask != 0, 0.5, 0.0)
+    x = np.zeros(n)
+    it = nek.cggo(x, f, g["h1"], g["h2"], half, g["vmult"], 1, -1e-30, 12, 1, g["binvm1"], "VELY")
+    xo, ito = case.cggo(f, g["h1"], g["h2"], mask=half, tin=-1e-30, maxit=12, istep=20)
+    assert it == ito == 12 and relmax(x, xo) <= TOL_FIELD
+    x = np.zeros(n)
+    it = nek.cggo(x, f, g["h1"], g["h2"], mask, g["vmult"], 1, -1e-30, 12, 1, g["binvm1"], "VELY")
+    xo, ito = case.cggo(f, g["h1"], g["h2"], mask=mask, tin=-1e-30, maxit=12, istep=20)
+    assert it == ito == 12 and relmax(x, xo) <= TOL_FIELD

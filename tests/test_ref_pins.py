@@ -150,3 +150,18 @@ def test_gen_fast_reproduces_the_reference_fastd():
     assert np.abs(np.abs(S) - np.abs(Sr)).max() <= 1e-11
     h = hsmg.Hsmg2(c, fbc, S, D)
     assert relmax(h.solve(g["r"].copy()), g["e"]) <= 1e-12
+
+
+def test_ophinv_three_helmholtz_solves():
+    """core/induct.f:1022-1090: per component dssum + mask of the rhs, chktcg1, cggo -- bit for bit, identical counts."""
+    g, c = G["ophinv"], refcases.case_of("ophinv")
+    assert len({g["v1mask"].sum(), g["v2mask"].sum(), g["v3mask"].sum()}) == 3      # SYM sides: three different masks
+    assert len(set(g["its"].tolist())) > 1 or g["its"].min() > 15
+    for k in range(3):
+        mask = g[f"v{k + 1}mask"]
+        rhs = c.dssum(g[f"i{k + 1}"]) * mask
+        assert np.array_equal(rhs, g[f"r{k + 1}"])
+        x, it = c.cggo(rhs, g["h1"], g["h2"], mask=mask, tin=1e-8, maxit=300, istep=20)
+        assert it == g["its"][k] and np.array_equal(x, g[f"o{k + 1}"])
+        x, it = c.cggo(rhs, g["h1"], g["h2"], mask=mask, tin=-1e-30, maxit=15, istep=20)
+        assert it == g["its_15"][k] == 15 and np.array_equal(x, g[f"o{k + 1}_15"])
