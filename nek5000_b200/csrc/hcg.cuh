@@ -198,12 +198,20 @@ __global__ void __launch_bounds__(CG_THREADS)
     double s[NRHS];
 #pragma unroll
     for (int c = 0; c < NRHS; c++) act[c] = sc->c[c].done == 0, s[c] = 0.0;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
-        const unsigned mc = mcode[t];
-        const double m = mult[t];
+    const int64_t n2 = n >> 1;
+    const double2 *__restrict__ mult2 = reinterpret_cast<const double2 *>(mult);
+    const uchar2 *__restrict__ mc2 = reinterpret_cast<const uchar2 *>(mcode);
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n2; t += (int64_t)gridDim.x * blockDim.x) {
+        const uchar2 mc = mc2[t];
+        const double2 m = mult2[t];
 #pragma unroll
         for (int c = 0; c < NRHS; c++)
-            if (act[c] && ((mc >> c) & 1u)) s[c] = fma(P.w[c][t] * P.p[c][t], m, s[c]);
+            if (act[c]) {
+                const double2 w = reinterpret_cast<const double2 *>(P.w[c])[t], p = reinterpret_cast<const double2 *>(P.p[c])[t];
+                const double mx = ((mc.x >> c) & 1u) ? m.x : 0.0, my = ((mc.y >> c) & 1u) ? m.y : 0.0;
+                s[c] = fma(w.x * p.x, mx, s[c]);
+                s[c] = fma(w.y * p.y, my, s[c]);
+            }
     }
 #pragma unroll
     for (int c = 0; c < NRHS; c++) {
@@ -216,6 +224,7 @@ __global__ void __launch_bounds__(CG_THREADS)
 
 // alpha = rtz1/rho ; r -= alpha mask w (:802-805) fused with the two sums that open the next iteration (:755-760):
 // (z,r)_mult with z = d r, and (r,r)_{mult binv}.  FIRST: r is the right-hand side, nothing to subtract.
+// Two nodes per thread and step (16-byte loads, all loads of a step independent of the mask byte).
 template <int NRHS, bool FIRST>
 __global__ void __launch_bounds__(CG_THREADS)
     hcg_update_kernel(HcgPtrs P, const unsigned char *__restrict__ mcode, const double *__restrict__ mult, const double *__restrict__ d,
@@ -230,19 +239,34 @@ __global__ void __launch_bounds__(CG_THREADS)
         al[c] = (!FIRST && act[c]) ? sc->c[c].rtz1 / sc->c[c].rho : 0.0;
         s1[c] = s2[c] = 0.0;
     }
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
-        const unsigned mc = mcode[t];
-        const double m = mult[t], dd = d[t], bi = binv[t];
+    const int64_t n2 = n >> 1;  // n = 512 * nel is even
+    const double2 *__restrict__ mult2 = reinterpret_cast<const double2 *>(mult), *__restrict__ d2 = reinterpret_cast<const double2 *>(d),
+                               *__restrict__ binv2 = reinterpret_cast<const double2 *>(binv);
+    const uchar2 *__restrict__ mc2 = reinterpret_cast<const uchar2 *>(mcode);
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n2; t += (int64_t)gridDim.x * blockDim.x) {
+        const uchar2 mc = mc2[t];
+        const double2 m = mult2[t], dd = d2[t], bi = binv2[t];
+        double2 rv[NRHS], wv[NRHS];
+#pragma unroll
+        for (int c = 0; c < NRHS; c++)
+            if (act[c]) {
+                rv[c] = reinterpret_cast<const double2 *>(P.r[c])[t];
+                if (!FIRST) wv[c] = reinterpret_cast<const double2 *>(P.w[c])[t];
+            }
 #pragma unroll
         for (int c = 0; c < NRHS; c++) {
             if (!act[c]) continue;
-            double rv = P.r[c][t];
+            double2 r = rv[c];
             if (!FIRST) {
-                if ((mc >> c) & 1u) rv = fma(-al[c], P.w[c][t], rv);
-                P.r[c][t] = rv;
+                const double rx = fma(-al[c], wv[c].x, r.x), ry = fma(-al[c], wv[c].y, r.y);
+                r.x = ((mc.x >> c) & 1u) ? rx : r.x;
+                r.y = ((mc.y >> c) & 1u) ? ry : r.y;
+                reinterpret_cast<double2 *>(P.r[c])[t] = r;
             }
-            s1[c] = fma(rv * dd * rv, m, s1[c]);
-            s2[c] = fma(rv * rv * m, bi, s2[c]);
+            s1[c] = fma(r.x * dd.x * r.x, m.x, s1[c]);
+            s1[c] = fma(r.y * dd.y * r.y, m.y, s1[c]);
+            s2[c] = fma(r.x * r.x * m.x, bi.x, s2[c]);
+            s2[c] = fma(r.y * r.y * m.y, bi.y, s2[c]);
         }
     }
 #pragma unroll
@@ -398,6 +422,10 @@ inline bool hcg_run(int nrhs, double *const *x, const double *const *f, const do
     NEKB_REQUIRE(nrhs == 1 || nrhs == 3, "hcg: 1 or 3 right-hand sides");
     GsMap &h = gs_get(gs_handle);
     NEKB_REQUIRE(h.n == n, "hcg: gs handle was set up for a different vector length");
+    auto misaligned = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) != 0; };  // 16-byte loads, TMA sources
+    for (int k = 0; k < nrhs; k++)
+        if (misaligned(x[k]) || misaligned(f[k])) return false;
+    if (misaligned(h1) || misaligned(mult) || misaligned(binv)) return false;
     S.sc.ensure(1), S.mcode.ensure((size_t)n), S.d.ensure((size_t)n), S.flag.ensure(1);
     S.partials.ensure((size_t)8 * CG_PART_STRIDE);
     const int hstride = 3 * (niter + 2);

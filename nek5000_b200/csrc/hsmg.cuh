@@ -272,6 +272,14 @@ struct CrsSolver {
     bool iters_on_device = false;  // the cooperative kernel leaves its count in the device scalars
     double tol = 1e-13;
     int maxit = 2000;
+    // ---- direct solver (the XXT role): explicit inverse of the assembled coarse matrix, applied as one GEMV --------
+    bool dense = false;
+    int64_t nc = 0;                  // global coarse dofs (distinct vertex ids, all ranks)
+    DevBuf<double> ainv;             // [nc][nc]
+    DevBuf<double> gmask;            // [nc] 1 = unmasked
+    DevBuf<double> g, y;             // [nc] assembled right-hand side / solution
+    DevBuf<int32_t> vid;             // [8 nel] global dof of every local vertex (0-based)
+    DevBuf<int32_t> voff, vmem;      // CSR: local members of every global dof (empty rows for dofs of other ranks)
 };
 
 struct H1mg {
@@ -993,6 +1001,297 @@ inline int crs_coop_enabled()
     return v;
 }
 
+// ================================================================================================ direct coarse solve
+// The reference's coarse solver is XXT (core/crs_xxt.c): a DIRECT solver whose application is two sparse mat-vecs.  The
+// device analogue for coarse problems up to NEKB_CRS_DENSE_MAX dofs (default 12288; e.g. examples/turbChannel: 1989) is
+// the explicit inverse of the assembled vertex-mesh matrix, applied as one dense GEMV: one launch instead of ~270 PCG
+// iterations.  Setup = blocked Gauss-Jordan inversion (no pivoting: the matrix is SPD) in 64x64 tiles.
+constexpr int CRS_NB = 64;
+
+// pivot tile P <- P^-1 (SPD, Gauss-Jordan in shared memory, 64 sequential eliminations); one CTA
+__global__ void __launch_bounds__(256) crsd_pivot_kernel(double *__restrict__ M, int64_t ld, int kb)
+{
+    __shared__ double P[CRS_NB][CRS_NB + 1];
+    __shared__ double col[CRS_NB], row[CRS_NB];
+    double *Mk = M + ((size_t)kb * CRS_NB) * ld + (size_t)kb * CRS_NB;
+    for (int t = threadIdx.x; t < CRS_NB * CRS_NB; t += 256) P[t / CRS_NB][t % CRS_NB] = Mk[(size_t)(t / CRS_NB) * ld + t % CRS_NB];
+    __syncthreads();
+    for (int q = 0; q < CRS_NB; q++) {
+        if (threadIdx.x < CRS_NB) col[threadIdx.x] = P[threadIdx.x][q], row[threadIdx.x] = P[q][threadIdx.x];
+        __syncthreads();
+        const double piv = 1.0 / row[q];
+        for (int t = threadIdx.x; t < CRS_NB * CRS_NB; t += 256) {  // every entry from its own old value + the snapshots
+            const int i = t / CRS_NB, j = t % CRS_NB;
+            double v;
+            if (i == q && j == q)
+                v = piv;
+            else if (i == q)
+                v = row[j] * piv;
+            else if (j == q)
+                v = -col[i] * piv;
+            else
+                v = P[i][j] - col[i] * (row[j] * piv);
+            P[i][j] = v;
+        }
+        __syncthreads();
+    }
+    for (int t = threadIdx.x; t < CRS_NB * CRS_NB; t += 256) Mk[(size_t)(t / CRS_NB) * ld + t % CRS_NB] = P[t / CRS_NB][t % CRS_NB];
+}
+
+// C = alpha * A * B (+ C if ACC) on 64x64 tiles of a matrix with leading dimension ld; 256 threads, 4x4 outputs each.
+// A and B are staged in shared memory before anything is written, so C may alias A or B.
+template <bool ACC>
+__device__ __forceinline__ void crsd_tile_mm(double *C, const double *A, const double *B, int64_t ld, double alpha)
+{
+    constexpr int H = CRS_NB / 2;  // the inner dimension goes through shared memory in two halves (48 KB static limit)
+    __shared__ double sA[CRS_NB][H + 1], sB[H][CRS_NB + 1];
+    const int ti = (threadIdx.x / 16) * 4, tj = (threadIdx.x % 16) * 4;
+    double acc[4][4] = {};
+    for (int h = 0; h < 2; h++) {
+        if (h) __syncthreads();
+        for (int t = threadIdx.x; t < CRS_NB * H; t += 256) {
+            sA[t / H][t % H] = A[(size_t)(t / H) * ld + h * H + t % H];
+            sB[t / CRS_NB][t % CRS_NB] = B[(size_t)(h * H + t / CRS_NB) * ld + t % CRS_NB];
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int q = 0; q < H; q++) {
+            double a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) a[u] = sA[ti + u][q], b[u] = sB[q][tj + u];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int v = 0; v < 4; v++) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+        }
+    }
+    __syncthreads();  // C may alias A or B: every read of both tiles is complete
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            double *c = C + (size_t)(ti + u) * ld + tj + v;
+            *c = ACC ? fma(alpha, acc[u][v], *c) : alpha * acc[u][v];
+        }
+}
+// Blocked Gauss-Jordan step k on the tiles M_ij:  P = M_kk^-1 (pivot kernel) ; row: M_kj <- P M_kj (j != k) ;
+// trailing: M_ij -= M_ik M_kj (i, j != k) ; column: M_ik <- -M_ik P (i != k).  After the last step M holds the inverse.
+__global__ void __launch_bounds__(256) crsd_row_kernel(double *M, int64_t ld, int kb)
+{
+    const int jb = blockIdx.x;
+    if (jb == kb) return;
+    double *T = M + ((size_t)kb * CRS_NB) * ld + (size_t)jb * CRS_NB;
+    crsd_tile_mm<false>(T, M + ((size_t)kb * CRS_NB) * ld + (size_t)kb * CRS_NB, T, ld, 1.0);
+}
+__global__ void __launch_bounds__(256) crsd_trail_kernel(double *M, int64_t ld, int kb)
+{
+    const int ib = blockIdx.y, jb = blockIdx.x;
+    if (ib == kb || jb == kb) return;
+    crsd_tile_mm<true>(M + ((size_t)ib * CRS_NB) * ld + (size_t)jb * CRS_NB, M + ((size_t)ib * CRS_NB) * ld + (size_t)kb * CRS_NB,
+                       M + ((size_t)kb * CRS_NB) * ld + (size_t)jb * CRS_NB, ld, -1.0);
+}
+__global__ void __launch_bounds__(256) crsd_col_kernel(double *M, int64_t ld, int kb)
+{
+    const int ib = blockIdx.x;
+    if (ib == kb) return;
+    double *T = M + ((size_t)ib * CRS_NB) * ld + (size_t)kb * CRS_NB;
+    crsd_tile_mm<false>(T, T, M + ((size_t)kb * CRS_NB) * ld + (size_t)kb * CRS_NB, ld, -1.0);
+}
+
+// g[v] = sum of the local contributions of global dof v in a fixed order (rows of other ranks' dofs are empty -> 0)
+__global__ void __launch_bounds__(256)
+    crsd_gather_kernel(double *__restrict__ g, const double *__restrict__ b, const int32_t *__restrict__ voff, const int32_t *__restrict__ vmem,
+                       int64_t nc)
+{
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nc; v += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int q = voff[v]; q < voff[v + 1]; q++) s += b[vmem[q]];
+        g[v] = s;
+    }
+}
+// masked right-hand side; with a null space its mean over the unmasked dofs is removed first (consistent system)
+__global__ void __launch_bounds__(1024) crsd_prep_kernel(double *__restrict__ g, const double *__restrict__ gmask, int64_t nc, int null_space, double ndof)
+{
+    __shared__ double red[33];
+    __shared__ double mean;
+    double s = 0.0;
+    for (int64_t v = threadIdx.x; v < nc; v += blockDim.x) {
+        const double t = g[v] * gmask[v];
+        g[v] = t;
+        s += t;
+    }
+    const double tot = block_reduce(s, red);
+    if (threadIdx.x == 0) mean = null_space ? tot / ndof : 0.0;
+    __syncthreads();
+    if (null_space)
+        for (int64_t v = threadIdx.x; v < nc; v += blockDim.x) g[v] = (g[v] - mean) * gmask[v];
+}
+// y = Ainv g, one warp per row
+__global__ void __launch_bounds__(256)
+    crsd_gemv_kernel(double *__restrict__ y, const double *__restrict__ ainv, const double *__restrict__ g, int64_t nc, int64_t ld)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = w0; r < nc; r += nw) {
+        const double *row = ainv + (size_t)r * ld;
+        double s = 0.0;
+        for (int64_t j = lane; j < nc; j += 32) s = fma(row[j], g[j], s);
+        s = warp_sum(s);
+        if (lane == 0) y[r] = s;
+    }
+}
+// x_loc[t] = mask (y[vid[t]] - mean(y)) : back to the element-local vertex arrays
+__global__ void __launch_bounds__(1024) crsd_mean_kernel(double *__restrict__ y, const double *__restrict__ gmask, int64_t nc, int null_space, double ndof)
+{
+    __shared__ double red[33];
+    __shared__ double mean;
+    double s = 0.0;
+    for (int64_t v = threadIdx.x; v < nc; v += blockDim.x) s += y[v] * gmask[v];
+    const double tot = block_reduce(s, red);
+    if (threadIdx.x == 0) mean = null_space ? tot / ndof : 0.0;
+    __syncthreads();
+    for (int64_t v = threadIdx.x; v < nc; v += blockDim.x) y[v] = (y[v] - mean) * gmask[v];
+}
+__global__ void __launch_bounds__(256)
+    crsd_scatter_kernel(double *__restrict__ x, const double *__restrict__ y, const int32_t *__restrict__ vid, int64_t n)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) x[t] = y[vid[t]];
+}
+
+inline int crs_dense_max()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("NEKB_CRS_DENSE_MAX");
+        v = e ? atoi(e) : 12288;
+    }
+    return v;
+}
+
+inline int64_t crsd_ld(int64_t nc) { return (nc + CRS_NB - 1) / CRS_NB * CRS_NB; }
+
+// x = Q A^-1 Q^T b through the explicit inverse (see crs_dense_setup)
+inline void crs_dense_solve(CrsSolver &k, double *x_out, const double *b_in)
+{
+    Ctx &c = ctx();
+    cudaStream_t s = c.stream;
+    const int64_t nc = k.nc, ld = crsd_ld(nc);
+    const int gv = (int)std::max<int64_t>(1, std::min<int64_t>((nc + 255) / 256, (int64_t)c.num_sms * 4));
+    crsd_gather_kernel<<<gv, 256, 0, s>>>(k.g.p, b_in, k.voff.p, k.vmem.p, nc);
+    NEKB_LAUNCHED();
+    if (c.nranks > 1) comm_allreduce_sum(k.g.p, (int)nc);   // contributions of the other ranks' elements
+    crsd_prep_kernel<<<1, 1024, 0, s>>>(k.g.p, k.gmask.p, nc, k.null_space, k.ndof);
+    NEKB_LAUNCHED();
+    const int gw = (int)std::max<int64_t>(1, std::min<int64_t>((nc * 32 + 255) / 256, (int64_t)c.num_sms * 8));
+    crsd_gemv_kernel<<<gw, 256, 0, s>>>(k.y.p, k.ainv.p, k.g.p, nc, ld);
+    NEKB_LAUNCHED();
+    crsd_mean_kernel<<<1, 1024, 0, s>>>(k.y.p, k.gmask.p, nc, k.null_space, k.ndof);
+    NEKB_LAUNCHED();
+    if (k.n > 0) {
+        const int gx = (int)std::max<int64_t>(1, std::min<int64_t>((k.n + 255) / 256, (int64_t)c.num_sms * 4));
+        crsd_scatter_kernel<<<gx, 256, 0, s>>>(x_out, k.y.p, k.vid.p, k.n);
+        NEKB_LAUNCHED();
+    }
+}
+
+// Assembles the global vertex-mesh matrix from the element matrices of ALL ranks (host transport, setup only; fixed
+// summation order so that every rank holds the same bits), imposes the masked dofs as identity rows, regularises the
+// all-Neumann null space with (trace/ndof^2) m m^T (m = unmasked dofs: for a consistent right-hand side the solution of the
+// regularised system is the mean-free solution of the singular one), and inverts it on the device.  COLLECTIVE.
+inline void crs_dense_setup(CrsSolver &k, int nel, const int64_t *vertex)
+{
+    Ctx &c = ctx();
+    cudaStream_t s = c.stream;
+    k.dense = false;
+    const char *env = getenv("NEKB_CRS_DENSE");
+    const bool enabled = !env || atoi(env) != 0;
+    std::vector<int64_t> glo((size_t)8 * std::max(nel, 1));
+    const int64_t ngv = setvert3d_host(glo.data(), 2, nel, vertex, c.nranks);
+    int64_t ngv_all = ngv;
+    if (c.nranks > 1) {  // the largest id over all ranks = number of distinct vertices
+        int64_t mx = 0;
+        for (int t = 0; t < 8 * nel; t++) mx = std::max(mx, glo[t]);
+        std::vector<int64_t> all((size_t)c.nranks);
+        host_allgather(&mx, all.data(), sizeof(int64_t));
+        ngv_all = 0;
+        for (int64_t v : all) ngv_all = std::max(ngv_all, v);
+    }
+    if (!enabled || ngv_all <= 0 || ngv_all > crs_dense_max()) return;
+    const int64_t nc = ngv_all, ld = crsd_ld(nc);
+    // gather ids / element matrices / masks of every rank, padded to the largest element count
+    int64_t nel_loc = nel;
+    std::vector<int64_t> nels((size_t)c.nranks);
+    host_allgather(&nel_loc, nels.data(), sizeof(int64_t));
+    int64_t nelmax = 1;
+    for (int64_t v : nels) nelmax = std::max(nelmax, v);
+    std::vector<double> a_loc((size_t)64 * nelmax, 0.0), m_loc((size_t)8 * nelmax, 0.0);
+    std::vector<int64_t> id_loc((size_t)8 * nelmax, 0);
+    if (nel > 0) {
+        k.a.download(a_loc.data(), (size_t)64 * nel, s);
+        k.mask.download(m_loc.data(), (size_t)8 * nel, s);
+        memcpy(id_loc.data(), glo.data(), sizeof(int64_t) * 8 * (size_t)nel);
+    }
+    std::vector<double> a_all((size_t)64 * nelmax * c.nranks), m_all((size_t)8 * nelmax * c.nranks);
+    std::vector<int64_t> id_all((size_t)8 * nelmax * c.nranks);
+    host_allgather(a_loc.data(), a_all.data(), sizeof(double) * a_loc.size());
+    host_allgather(m_loc.data(), m_all.data(), sizeof(double) * m_loc.size());
+    host_allgather(id_loc.data(), id_all.data(), sizeof(int64_t) * id_loc.size());
+    std::vector<double> A((size_t)ld * ld, 0.0), gmask((size_t)ld, 1.0);
+    for (int r = 0; r < c.nranks; r++)
+        for (int64_t e = 0; e < nels[r]; e++) {
+            const double *ae = a_all.data() + ((size_t)r * nelmax + e) * 64, *me = m_all.data() + ((size_t)r * nelmax + e) * 8;
+            const int64_t *ie = id_all.data() + ((size_t)r * nelmax + e) * 8;
+            for (int i = 0; i < 8; i++) {
+                NEKB_REQUIRE(ie[i] >= 1 && ie[i] <= nc, "coarse numbering out of range");
+                if (me[i] == 0.0) gmask[ie[i] - 1] = 0.0;
+                for (int j = 0; j < 8; j++) A[(size_t)(ie[i] - 1) * ld + (ie[j] - 1)] += ae[i * 8 + j];
+            }
+        }
+    double trace = 0.0, ndof = 0.0;
+    for (int64_t v = 0; v < nc; v++)
+        if (gmask[v] != 0.0) trace += A[(size_t)v * ld + v], ndof += 1.0;
+    for (int64_t v = 0; v < ld; v++)
+        if (v >= nc || gmask[v] == 0.0) {  // masked dofs and padding: identity
+            for (int64_t j = 0; j < ld; j++) A[(size_t)v * ld + j] = 0.0, A[(size_t)j * ld + v] = 0.0;
+            A[(size_t)v * ld + v] = 1.0;
+            if (v >= nc) gmask[v] = 0.0;
+        }
+    if (k.null_space && ndof > 0.0) {
+        const double gam = trace / (ndof * ndof);
+        for (int64_t i = 0; i < nc; i++)
+            if (gmask[i] != 0.0)
+                for (int64_t j = 0; j < nc; j++)
+                    if (gmask[j] != 0.0) A[(size_t)i * ld + j] += gam;
+    }
+    k.ainv.upload(A.data(), A.size(), s);
+    const int nb = (int)(ld / CRS_NB);
+    for (int kb = 0; kb < nb; kb++) {
+        crsd_pivot_kernel<<<1, 256, 0, s>>>(k.ainv.p, ld, kb);
+        NEKB_LAUNCHED();
+        if (nb > 1) {
+            crsd_row_kernel<<<nb, 256, 0, s>>>(k.ainv.p, ld, kb);
+            NEKB_LAUNCHED();
+            crsd_trail_kernel<<<dim3(nb, nb), 256, 0, s>>>(k.ainv.p, ld, kb);
+            NEKB_LAUNCHED();
+            crsd_col_kernel<<<nb, 256, 0, s>>>(k.ainv.p, ld, kb);
+            NEKB_LAUNCHED();
+        }
+    }
+    // local members of every global dof (counting sort, ascending local index inside a row)
+    std::vector<int32_t> vid((size_t)8 * std::max(nel, 1), 0), voff((size_t)nc + 1, 0), vmem((size_t)8 * std::max(nel, 1), 0);
+    for (int t = 0; t < 8 * nel; t++) vid[t] = (int32_t)(glo[t] - 1), voff[(size_t)vid[t] + 1]++;
+    for (int64_t v = 0; v < nc; v++) voff[v + 1] += voff[v];
+    std::vector<int32_t> cur(voff.begin(), voff.end() - 1);
+    for (int t = 0; t < 8 * nel; t++) vmem[cur[vid[t]]++] = t;
+    k.vid.upload(vid.data(), vid.size(), s), k.voff.upload(voff.data(), voff.size(), s), k.vmem.upload(vmem.data(), vmem.size(), s);
+    k.gmask.upload(gmask.data(), (size_t)ld, s);
+    k.g.alloc((size_t)ld), k.y.alloc((size_t)ld);
+    k.g.zero(s), k.y.zero(s);
+    k.nc = nc;
+    NEKB_CUDA(cudaStreamSynchronize(s));
+    k.dense = true;
+}
+
 inline int vec_grid(int64_t n)
 {
     int64_t b = (n + 255) / 256;
@@ -1011,6 +1310,11 @@ inline void crs_solve_dev(H1mg &MM, double *x_out, const double *b_in)
     CrsSolver &k = MM.crs;
     cudaStream_t s = c.stream;
     const int64_t n = k.n;
+    if (k.dense) {  // direct solve (the XXT role): one GEMV with the explicit inverse
+        crs_dense_solve(k, x_out, b_in);
+        k.last_iters = 1, k.iters_on_device = false;
+        return;
+    }
     if (n == 0 && c.nranks <= 1) return;
     const int grid = vec_grid(n);
     DevBuf<CrsScalars> &scb = crs_scalars();
@@ -1564,6 +1868,7 @@ inline void h1mg_setup_run(H1mg &M, const int *fbc, const double *xm1, const dou
         comm_allreduce_sum(&scb.p->shift, 1);
         NEKB_CUDA(cudaMemcpyAsync(&k.ndof, &scb.p->shift, sizeof(double), cudaMemcpyDeviceToHost, s));
         NEKB_CUDA(cudaStreamSynchronize(s));
+        crs_dense_setup(k, nel, vertex);
     }
     NEKB_CUDA(cudaStreamSynchronize(s));
     M.ready = true;

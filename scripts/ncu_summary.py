@@ -33,7 +33,8 @@ def main():
         ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
         data = rows[1:]
         # the last cggos solve = the timed step: everything after the last init kernel
-        last = max((i for i, r in enumerate(data) if "cggos_init" in r[ki]), default=0)
+        marker = os.environ.get("NCU_STEP_MARKER", "cggos_init")   # first kernel of a solve (ophinv: hcg_prep_kernel)
+        last = max((i for i, r in enumerate(data) if marker in r[ki]), default=0)
         agg, cnt = collections.OrderedDict(), collections.Counter()
         for r in data[last:]:
             k = short(r[ki])

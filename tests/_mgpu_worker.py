@@ -74,7 +74,37 @@ def main():
     ca = np.array([first_a.setdefault(v, i) for i, v in enumerate(inv_a)])
     cb = np.array([first_b.setdefault(v, i) for i, v in enumerate(inv_b)])
     assert np.array_equal(ca, cb), "numbering classes"
-    print(f"MGPU-OK rank {rank} of {world}: its={it} rel(u)={rel(u, uref[take]):.2e}", flush=True)
+    # ---- ophinv on N ranks: the fused 3-right-hand-side PCG (hcg.cuh) with its NCCL reductions and gs exchange against the
+    # oracle's three undivided cggo solves (which tests/test_ref_pins.py pins to the reference bit for bit)
+    from nek5000_b200._lib import check, lib
+    L = lib()
+    rng = np.random.default_rng(11)
+    h1g, h2g = 1.0 + 0.3 * rng.random(case.n), 20.0 * (5.0 + rng.random(case.n))
+    rhsg = [case.bm1() * rng.standard_normal(case.n) for _ in range(3)]
+    vol = float(case.bm1().sum())
+    nek.set_ifield(1)
+    nek.set_field_handle(1, b.gs_handle)
+    nek.set_step_info(20, vol)
+    nek.set_param(22, 0.0)
+    D = nek.DevArray
+    h1d, h2d, binvd = D.from_host(h1g[take]), D.from_host(h2g[take]), D.from_host(case.binv()[take])
+    maskp, multp = b.devptr("mask"), b.devptr("mult")
+    itv = np.zeros(3, dtype=np.int32)
+    worst = 0.0
+    for tol, maxit3, ftol in ((-1e-30, 15, 1e-10), (1e-8, 300, 1e-7)):
+        outs = [D(b.n) for _ in range(3)]
+        rh = [D.from_host(r[take]) for r in rhsg]
+        check(L.nekb_ophinv_dev(outs[0].ptr, outs[1].ptr, outs[2].ptr, rh[0].ptr, rh[1].ptr, rh[2].ptr, h1d.ptr, h2d.ptr,
+                                maskp, maskp, maskp, multp, binvd.ptr, tol, maxit3, itv.ctypes.data, None))
+        for k in range(3):
+            f = case.dssum(rhsg[k]) * case.mask
+            assert rel(rh[k].to_host(), f[take]) <= 1e-12, "ophinv rhs"
+            xo, ito = case.cggo(f, h1g, h2g, tin=tol, maxit=maxit3, istep=20)
+            assert itv[k] == ito, ("ophinv iteration count", k, itv[k], ito)
+            d = rel(outs[k].to_host(), xo[take])
+            worst = max(worst, d) if tol < 0 else worst
+            assert d <= ftol, ("ophinv solution", k, d)
+    print(f"MGPU-OK rank {rank} of {world}: its={it} rel(u)={rel(u, uref[take]):.2e} ophinv its={itv.tolist()} rel={worst:.1e}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

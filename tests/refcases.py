@@ -206,7 +206,10 @@ def ref_ophinv():
     R, n = rc.R, case.n
     masks = [rc.fld(m) for m in ("v1mask", "v2mask", "v3mask")]
     rng = np.random.default_rng(7)
-    h1, h2 = 1.0 + 0.3 * rng.random(n), 5.0 + rng.random(n)
+    # h2/h1 ~ 100: the conditioning of a velocity solve with a small time step (72 / 76 / 79 iterations to 1e-8).  Runs of
+    # 130+ iterations exist too, but there the exit test (hmholtz.f:778) of any re-ordered summation sits within rounding
+    # of the reference's and the count may move by one.
+    h1, h2 = 1.0 + 0.3 * rng.random(n), 20.0 * (5.0 + rng.random(n))
     rhs = [case.bm1() * rng.standard_normal(n) for _ in range(3)]
     out = dict(v1mask=masks[0], v2mask=masks[1], v3mask=masks[2], vmult=rc.fld("vmult"), binvm1=rc.fld("binvm1"),
                volvm1=np.array([R.get("volvm1")]), h1=h1, h2=h2, i1=rhs[0], i2=rhs[1], i3=rhs[2])

@@ -252,7 +252,7 @@ def _register_ophinv(nek, g, case):
 
 def test_ophinv_fused_three_rhs_against_the_reference(nek):
     """core/induct.f:1022-1090 ophinv: the reference runs three hmholtz/cggo solves in a row; the library runs ONE fused
-    3-right-hand-side PCG (hcg.cuh).  Every component must stop at the reference's own iteration count (133 / 128 / 153 here)
+    3-right-hand-side PCG (hcg.cuh).  Every component must stop at the reference's own iteration count (72 / 76 / 79 here)
     and reproduce its iterates."""
     g, case = G["ophinv"], refcases.case_of("ophinv")
     _register_ophinv(nek, g, case)

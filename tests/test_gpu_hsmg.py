@@ -78,9 +78,12 @@ def test_h1mg_setup_and_levels(nek, name):
         assert max(info["ntab"][1:]) <= 9
 
 
-@pytest.mark.parametrize("name", list(CASES))
-def test_schwarz_crs_and_vcycle(nek, name):
+@pytest.mark.parametrize("name,dense", [(n, "1") for n in CASES] + [("outflow_x_deformed", "0"), ("channel_like_periodic", "0")])
+def test_schwarz_crs_and_vcycle(nek, name, dense, monkeypatch):
+    """dense = "1": the coarse problem is solved directly (explicit inverse of the assembled vertex-mesh matrix, the XXT
+    role); "0": Jacobi-PCG to 1e-13 (the path taken above NEKB_CRS_DENSE_MAX dofs).  Both against the oracle's dense solve."""
     from nek5000_b200._lib import check, lib
+    monkeypatch.setenv("NEKB_CRS_DENSE", dense)
     dims, lx1, per, pdir, bc, deform = CASES[name]
     case, mg = make(nek, dims, lx1, per, pdir, bc, deform)
     rng = np.random.default_rng(11)
@@ -101,7 +104,8 @@ def test_schwarz_crs_and_vcycle(nek, name):
     bd, xd = nek.DevArray.from_host(b), nek.DevArray(n0)
     check(L.nekb_crs_solve_dev(xd.ptr, bd.ptr))
     assert relmax(xd.to_host(), ref) <= TOL
-    assert 0 < nek.h1mg_info()["crs_iters"] <= mg.crs_n + 2
+    its = nek.h1mg_info()["crs_iters"]
+    assert its == 1 if dense == "1" else 1 < its <= mg.crs_n + 2      # direct: one application
     # whole V-cycle through the Fortran-named entry point
     rhs = case.dssum(rng.standard_normal(case.n)) * case.mult
     ref_rhs = rhs.copy()
