@@ -29,9 +29,9 @@ MESH = {
 }
 
 
-def case_of(name):
+def case_of(name, nx=8):
     dims, dirich, deform = MESH[name]
-    return oracle.Case(*dims, nx=8, dirichlet=dirich, deform=deform)
+    return oracle.Case(*dims, nx=nx, dirichlet=dirich, deform=deform)
 
 
 def fbc_of(name, case):
@@ -45,11 +45,11 @@ def _ref(case, **kw):
 
 
 # --------------------------------------------------------------------------------------------------- reference runs
-def ref_core():
+def ref_core(nx=8):
     """setupds/setvert3d (navier8.f:2004-2360), geom1/geom2/setinvm (coef.f:555-784), bcmask (bdry.f:317+), axhelm
     (hmholtz.f:72-259), setprec (:380-524), dssum/dsop (dssum.f:33-161), cggo (:611-846), hmholtz (:2-69), and the BP5
     driver bp5/cggos/geodatstd/rand_fld_h1 (examples/bp5/bp5.usr:324-395,797-899,623-699; navier5.f:2650-2700)."""
-    case = case_of("core")
+    case = case_of("core", nx)
     rc = _ref(case)
     R, n = rc.R, case.n
     out = dict(glo_num=R.var("glo_num").ravel(order="F")[:n].copy(), vmult=rc.fld("vmult"), bm1=rc.fld("bm1"), binvm1=rc.fld("binvm1"),
@@ -74,7 +74,7 @@ def ref_core():
     out["setprec"] = dp
     for op, key in (("+  ", "dsop_add"), ("*  ", "dsop_mul"), ("m  ", "dsop_min"), ("M  ", "dsop_max")):
         v = u.copy()
-        R.call("dsop", v, op, 8, 8, 8)
+        R.call("dsop", v, op, nx, nx, nx)
         out[key] = v
     # cggo, Jacobi branch
     f = case.dssum(rng.standard_normal(n) * case.bm1()) * case.mask
@@ -98,6 +98,15 @@ def ref_core():
     v = lambda nm: R.var(nm, "bp5").ravel(order="F")
     out.update(bp5_gf=v("gf")[:6 * n].copy(), bp5_e1=v("e1")[:n].copy(), bp5_r1=v("r1")[:n].copy(), bp5_u1=v("u1")[:n].copy())
     return out
+
+
+def ref_core_lx6():
+    """The same routines at lx1 = 6 (the library's generic, non-TMA kernels; a second polynomial order for the oracle)."""
+    keep = ("glo_num", "vmult", "bm1", "binvm1", "v1mask", "volvm1", "zgm1", "wxm1", "dxm1", "g1m1", "g2m1", "g3m1", "g4m1", "g5m1",
+            "g6m1", "u", "h1", "h2", "axhelm", "axhelm_poisson", "setprec", "dsop_add", "cggo_f", "cggo20_x", "cggo20_it", "cggo_x",
+            "cggo_it", "bp5_gf", "bp5_e1", "bp5_r1", "bp5_u1")
+    full = ref_core(6)
+    return {k: full[k] for k in keep}
 
 
 def ref_bp5():
@@ -248,7 +257,7 @@ def ref_map():
     return out
 
 
-REFERENCE = dict(core=ref_core, map=ref_map, ophinv=ref_ophinv, bp5=ref_bp5, h1mg=ref_h1mg, h1mg_neumann=ref_h1mg_neumann, fdm=ref_fdm, pnpn2=ref_pnpn2)
+REFERENCE = dict(core=ref_core, core_lx6=ref_core_lx6, map=ref_map, ophinv=ref_ophinv, bp5=ref_bp5, h1mg=ref_h1mg, h1mg_neumann=ref_h1mg_neumann, fdm=ref_fdm, pnpn2=ref_pnpn2)
 
 
 def reference_all():

@@ -295,3 +295,42 @@ def test_fused_and_stock_cggo_agree(nek, monkeypatch):
     it = nek.cggo(x, f, g["h1"], g["h2"], mask, g["vmult"], 1, -1e-30, 12, 1, g["binvm1"], "VELY")
     xo, ito = case.cggo(f, g["h1"], g["h2"], mask=mask, tin=-1e-30, maxit=12, istep=20)
     assert it == ito == 12 and relmax(x, xo) <= TOL_FIELD
+
+
+def test_lx1_6_generic_kernels_against_the_reference():
+    """lx1 = 6: the generic (non-TMA) Ax / setprec / cggo kernels against the reference's own output at that order."""
+    from nek5000_b200 import nek
+    g, case = G["core_lx6"], refcases.case_of("core", 6)
+    nek.finalize()
+    nek.init(0, 6, 3)
+    try:
+        E, n = case.nel, case.n
+        nek.set_nel(E, E)
+        nek.set_gll(g["zgm1"], g["wxm1"])
+        nek.set_dxyz(g["dxm1"], np.ascontiguousarray(g["dxm1"].T))
+        nek.set_geom(*[g[f"g{i}m1"] for i in range(1, 7)], g["bm1"])
+        nek.set_ifdfrm(None)
+        h, glo = nek.setupds(6, E, case.vertex)
+        assert np.array_equal(glo, g["glo_num"])
+        nek.set_ifield(1)
+        nek.set_field_handle(1, h)
+        nek.set_step_info(1, float(g["volvm1"][0]))
+        au = np.zeros(n)
+        nek.axhelm(au, g["u"], g["h1"], g["h2"], 1, 1)
+        assert relmax(au, g["axhelm"]) <= TOL_APPLY
+        dp = np.zeros(n)
+        nek.setprec(dp, g["h1"], g["h2"], 1, 1)
+        assert relmax(dp, g["setprec"]) <= TOL_APPLY
+        x = np.zeros(n)
+        it = nek.cggo(x, g["cggo_f"], g["h1"], g["h2"], g["v1mask"], g["vmult"], 1, 1e-30, 20, 1, g["binvm1"], "VELX")
+        assert it == 20 and relmax(x, g["cggo20_x"]) <= TOL_FIELD
+        x = np.zeros(n)
+        it = nek.cggo(x, g["cggo_f"], g["h1"], g["h2"], g["v1mask"], g["vmult"], 1, 1e-6, 500, 1, g["binvm1"], "VELX")
+        assert it == g["cggo_it"][0] and relmax(x, g["cggo_x"]) <= TOL_CONVERGED
+        nek.set_geom_bp5(g["bp5_gf"])
+        nek.set_v1mask(g["v1mask"])
+        u = np.zeros(n)
+        it = nek.cggos(u, g["bp5_r1"], g["bp5_e1"], g["vmult"], g["binvm1"], -1e-8, 40)
+        assert it == 40 and relmax(u, g["bp5_u1"]) <= TOL_FIELD
+    finally:
+        nek.finalize()

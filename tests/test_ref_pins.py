@@ -37,10 +37,11 @@ def _ref_available():
 @pytest.mark.skipif(not _ref_available(), reason="oracle/_ref neither prebuilt nor buildable (no /root/reference)")
 @pytest.mark.parametrize("name", list(refcases.REFERENCE))
 def test_golden_file_is_what_the_reference_computes_now(name):
-    if name == "pnpn2":
-        from oracle import ref
-        if not ref.available(8, 6, 64):
-            pytest.skip("Pn-Pn-2 build of oracle/_ref not available")
+    from oracle import ref
+    if name == "pnpn2" and not ref.available(8, 6, 64):
+        pytest.skip("Pn-Pn-2 build of oracle/_ref not available")
+    if name == "core_lx6" and not ref.available(6, 6, 64):
+        pytest.skip("lx1 = 6 build of oracle/_ref not available")
     live = refcases.REFERENCE[name]()
     assert set(live) == set(G[name])
     for k, v in live.items():
@@ -165,3 +166,21 @@ def test_ophinv_three_helmholtz_solves():
         assert it == g["its"][k] and np.array_equal(x, g[f"o{k + 1}"])
         x, it = c.cggo(rhs, g["h1"], g["h2"], mask=mask, tin=-1e-30, maxit=15, istep=20)
         assert it == g["its_15"][k] == 15 and np.array_equal(x, g[f"o{k + 1}_15"])
+
+
+def test_second_polynomial_order_lx1_6_bit_exact():
+    g, c = G["core_lx6"], refcases.case_of("core", 6)
+    assert np.array_equal(g["zgm1"], c.z) and np.array_equal(g["dxm1"], c.D) and np.array_equal(g["glo_num"], c.glo_num)
+    geo = c.geom()
+    for i in range(6):
+        assert np.array_equal(g[f"g{i + 1}m1"], geo[i]), i
+    assert np.array_equal(g["bm1"], geo[6]) and np.array_equal(g["vmult"], c.mult)
+    assert np.array_equal(g["axhelm"], c.axhelm(g["u"], g["h1"], g["h2"]))
+    assert np.array_equal(g["setprec"], c.setprec(g["h1"], g["h2"]))
+    x, it = c.cggo(g["cggo_f"], g["h1"], g["h2"], tin=1e-30, maxit=20, istep=1)
+    assert it == 20 and np.array_equal(x, g["cggo20_x"])
+    x, it = c.cggo(g["cggo_f"], g["h1"], g["h2"], tin=1e-6, maxit=500, istep=1)
+    assert it == g["cggo_it"][0] and np.array_equal(x, g["cggo_x"])
+    e1, r1 = c.bp5_problem()
+    assert np.array_equal(g["bp5_gf"], c.gf()) and np.array_equal(g["bp5_e1"], e1) and np.array_equal(g["bp5_r1"], r1)
+    assert np.array_equal(g["bp5_u1"], c.cggos(r1, e1, tol=-1e-8, maxit=40)[0])
