@@ -182,6 +182,22 @@ int nekb_ophinv_dev(double *o1, double *o2, double *o3, double *i1, double *i2, 
                     const double *m1, const double *m2, const double *m3, const double *mult, const double *binv, double tolh,
                     int maxit, int *niter3, double *hist_host);
 
+/* core/navier4.f:562-634 hsolve(name,u,r,h1,h2,vmk,vml,imsh,tol,maxit,isd,approx,napprox,bi): the standard branch is
+ * hmholtz; with residual projection (ifprojfld(ifield) or name = 'PRES', param(93) > 0, param(94)/param(95) > 0 and
+ * istep >= that value) it is  r <- dssum(mask r) ; project1 ; hmhzpf (chktcg1 + cggo, 'PRES' -> hmh_gmres) ; project2
+ * (navier4.f:513-560,636-1199).  The approximation space {X, B = A X, xbar, bbar, h1old, h2old} is kept ON THE DEVICE, one
+ * set per solver name (proj.cuh); `approx` is not touched and napprox(1:2) = (mmx, m) is mirrored back (a caller that sets
+ * napprox(2) below the stored m restarts the space).  mxprev = 20 (SIZE.template) => mmx = 8 vectors.
+ * nekb_set_projection: INPUT ifprojfld(ifield) and SIZE ldimt_proj (-1 keeps it).  nekb_projection_reset drops all spaces.
+ * nekb_hsolve_dev: the same on device pointers (name4: 4 characters, NUL terminated). */
+void hsolve_(const char *name, double *u, double *r, const double *h1, const double *h2, const double *vmk, const double *vml,
+             const int *imsh, const double *tol, const int *maxit, const int *isd, double *approx, int *napprox, const double *bi,
+             size_t name_len);
+int nekb_set_projection(int ifield, int ifprojfld, int ldimt_proj);
+int nekb_projection_reset(void);
+int nekb_hsolve_dev(const char *name4, double *u, double *r, const double *h1, const double *h2, const double *vmk, const double *vml,
+                    int imsh, double tol, int maxit, const double *bi, int *napprox, int *niter);
+
 /* INPUT param(idx), 1-based: the path reads param(21) (pressure tolerance), param(22) (Helmholtz tolerance; < 0 relative,
  * core/hmholtz.f:764).  MASS binvm1 / bintm1 (host, lx1^3*nelv / nelt doubles; bintm1 may be NULL) for hmholtz. */
 int nekb_set_param(int idx, double value);

@@ -149,6 +149,10 @@ def lib() -> C.CDLL:
     L.hmholtz_.restype = None
     L.ophinv_.argtypes = [vp] * 8 + [dp, ip]
     L.ophinv_.restype = None
+    L.hsolve_.argtypes = [C.c_char_p, vp, vp, vp, vp, vp, vp, ip, dp, ip, ip, vp, vp, vp, C.c_size_t]
+    L.hsolve_.restype = None
+    L.nekb_set_projection.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.nekb_hsolve_dev.argtypes = [C.c_char_p] + [vp] * 6 + [C.c_int, C.c_double, C.c_int, vp, vp, ip]
     L.nekb_set_param.argtypes = [C.c_int, C.c_double]
     L.nekb_set_binv.argtypes = [vp, vp]
     # section F: pressure preconditioner + GMRES

@@ -76,6 +76,8 @@ struct Ctx {
     DevBuf<double> binvm1, bintm1; // MASS binvm1 / bintm1 for hmholtz
     DevBuf<double> vmask[3], vmult; // SOLN v1mask,v2mask,v3mask and vmult for ophinv
     int niter3[3] = {0, 0, 0};     // niterhm of the three component solves of the last ophinv
+    bool ifprojfld[16] = {false};  // INPUT ifprojfld(0:ldimt1): residual projection per field (hsolve)
+    int ldimt_proj = 3;            // SIZE ldimt_proj
 
     // gs handles ---------------------------------------------------------------------------------
     std::vector<GsMap> gs;

@@ -4,6 +4,7 @@
 
 #include "gmres.cuh"
 #include "hcg.cuh"
+#include "proj.cuh"
 #include "readers.cuh"
 
 using namespace nekb;
@@ -1227,32 +1228,148 @@ int nekb_hmh_gmres_dev(double *res_dev, const double *h1_dev, const double *h2_d
         if (iter) *iter = it;
     });
 }
+// gmres.f:338-342 (tolerance guard, param(21) / istep overrides) + the solve, on device pointers; h2 == nullptr: h2 = 0
+static int hmh_gmres_body(double *res, const double *h1, const double *h2, const double *wt, int maxit)
+{
+    Ctx &c = ctx();
+    GmresState &G = gmres_state();
+    H1mg &M = h1mg();
+    NEKB_REQUIRE(M.ready, "hmh_gmres: nekb_h1mg_setup has not been called");
+    NEKB_REQUIRE(c.volvm1 > 0.0, "volvm1 not registered (nekb_set_step_info)");
+    const size_t n = (size_t)M.nel * c.nxyz;
+    NEKB_REQUIRE(G.pmask.n >= n && G.binvm1.n >= n, "hmh_gmres: pmask/binvm1 not registered (nekb_set_pressure_state)");
+    double tolps = chktcg1_dev(G.tolps, res, h1, h2, G.pmask.p, wt, G.binvm1.p, M.nel, c.volvm1);
+    if (G.param21 > 0 && tolps > fabs(G.param21)) tolps = fabs(G.param21);
+    if (c.istep == 0) tolps = 1.e-4;
+    const double tol = G.param21 < 0 ? -fabs(G.param21) : tolps;
+    return hmh_gmres_run(res, h1, h2, wt, G.pmask.p, M.nel, M.lev[M.lmax - 1].gs, c.volvm1, tol, maxit, nullptr, nullptr);
+}
 void hmh_gmres_(double *res, const double *h1, const double *h2, const double *wt, int *iter)
 {
     guard_fortran("hmh_gmres", [&] {
         require_init();
         Ctx &c = ctx();
-        GmresState &G = gmres_state();
         H1mg &M = h1mg();
         NEKB_REQUIRE(M.ready, "hmh_gmres: nekb_h1mg_setup has not been called");
-        NEKB_REQUIRE(c.volvm1 > 0.0, "volvm1 not registered (nekb_set_step_info)");
         const size_t n = (size_t)M.nel * c.nxyz;
-        NEKB_REQUIRE(G.pmask.n >= n && G.binvm1.n >= n, "hmh_gmres: pmask/binvm1 not registered (nekb_set_pressure_state)");
         for (int k = 0; k < 4; k++) c.stage[k].ensure(n);
         const double *src[4] = {res, h1, h2, wt};
         for (int k = 0; k < 4; k++)
             NEKB_CUDA(cudaMemcpyAsync(c.stage[k].p, src[k], n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
         bool ifh2 = false;
         for (size_t t = 0; t < n && !ifh2; t++) ifh2 = h2[t] != 0.0;
-        const double *h2d = ifh2 ? c.stage[2].p : nullptr;
-        // gmres.f:338-342: tolerance guard and the param(21) / istep overrides
-        double tolps = chktcg1_dev(G.tolps, c.stage[0].p, c.stage[1].p, h2d, G.pmask.p, c.stage[3].p, G.binvm1.p, M.nel, c.volvm1);
-        if (G.param21 > 0 && tolps > fabs(G.param21)) tolps = fabs(G.param21);
-        if (c.istep == 0) tolps = 1.e-4;
-        const double tol = G.param21 < 0 ? -fabs(G.param21) : tolps;
-        *iter = hmh_gmres_run(c.stage[0].p, c.stage[1].p, h2d, c.stage[3].p, G.pmask.p, M.nel, M.lev[M.lmax - 1].gs, c.volvm1, tol,
-                              *iter, nullptr, nullptr);
+        *iter = hmh_gmres_body(c.stage[0].p, c.stage[1].p, ifh2 ? c.stage[2].p : nullptr, c.stage[3].p, *iter);
         NEKB_CUDA(cudaMemcpyAsync(res, c.stage[0].p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------- hsolve + projection
+int nekb_set_projection(int ifield, int ifprojfld, int ldimt_proj)
+{
+    return guard([&] {
+        require_init();
+        NEKB_REQUIRE(ifield >= 0 && ifield < 16, "set_projection: ifield out of range");
+        ctx().ifprojfld[ifield] = ifprojfld != 0;
+        if (ldimt_proj >= 0) ctx().ldimt_proj = ldimt_proj;
+    });
+}
+int nekb_projection_reset(void)
+{
+    return guard([&] { proj_states().clear(); });
+}
+// navier4.f:562-634 on device pointers.  Returns niterhm.  napprox (host, may be NULL): ivar(1) = mmx, ivar(2) = m.
+static int hsolve_dev(const char *name, size_t name_len, double *u, double *r, const double *h1, const double *h2, const double *vmk,
+                      const double *vml, int imsh, double tol, int maxit, const double *bi, int *napprox)
+{
+    Ctx &c = ctx();
+    char cname[5] = "    ";
+    for (size_t k = 0; k < 4 && k < name_len; k++) cname[k] = (char)toupper((unsigned char)name[k]);
+    const bool pres = !strncmp(cname, "PRES", 4);
+    const int nel = imsh == 1 ? c.nelv : c.nelt;
+    const int64_t n = (int64_t)nel * c.nxyz;
+    const double vol = imsh == 1 ? c.volvm1 : c.voltm1;
+    NEKB_REQUIRE(vol > 0.0, "volvm1/voltm1 not registered (nekb_set_step_info)");
+    const DevBuf<double> &binvc = imsh == 1 ? c.binvm1 : (c.bintm1.n ? c.bintm1 : c.binvm1);
+    const double *binv_chk = binvc.n >= (size_t)n ? binvc.p : bi;   // hmholtz / hmhzpf read binvm1 from COMMON
+    // ifh2
+    absmax_kernel<<<cg_grid(n), CG_THREADS, 0, c.stream>>>(h2, n, &c.sc.p->work[3], c.partials.p, &c.sc.p->counter[0]);
+    NEKB_LAUNCHED();
+    comm_allreduce_max(&c.sc.p->work[3], 1);
+    double h2max = 0.0;
+    NEKB_CUDA(cudaMemcpyAsync(&h2max, &c.sc.p->work[3], sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    const bool ifh2 = h2max > 0.0;
+
+    bool ifstdh = true;                                                        // :588-601
+    if (c.ifprojfld[c.ifield < 16 ? c.ifield : 0]) ifstdh = false;
+    double p945 = c.param[94];
+    if (pres) ifstdh = false, p945 = c.param[95];
+    if (c.ifield > c.ldimt_proj + 1) ifstdh = true;
+    if (c.param[93] == 0.0) ifstdh = true;
+    if (p945 == 0.0) ifstdh = true;
+    if ((double)c.istep < p945) ifstdh = true;
+
+    auto solve = [&](double tolin, bool through_hmholtz) -> int {
+        double t = tolin;
+        if (through_hmholtz) {                                                 // hmholtz.f:55-62
+            gs_op(field_handle(), r, 1, vmk);
+            t = fabs(tolin);
+            if (c.param[22] == 0.0 || c.istep <= 10) t = chktcg1_dev(t, r, h1, ifh2 ? h2 : nullptr, vmk, vml, binv_chk, nel, vol);
+            if (tolin < 0) t = tolin;
+        } else {                                                               // hmhzpf, navier4.f:536-538
+            if (c.param[22] != 0.0) t = fabs(c.param[22]);
+            t = chktcg1_dev(t, r, h1, ifh2 ? h2 : nullptr, vmk, vml, binv_chk, nel, vol);
+        }
+        if (pres) {                                                            // cggo :641-657
+            NEKB_REQUIRE(h1mg().ready && c.param[42] == 0.0, "hsolve('PRES'): needs nekb_h1mg_setup and param(42) = 0 (GMRES)");
+            NEKB_CUDA(cudaMemcpyAsync(u, r, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c.stream));
+            return hmh_gmres_body(u, h1, ifh2 ? h2 : nullptr, vml, maxit);
+        }
+        CggoArgs a{u, r, h1, h2, vmk, vml, bi, field_handle(), nel, vol, c.istep};
+        return cggo_solve(a, t, maxit, nullptr);
+    };
+    if (ifstdh) return solve(tol, true);
+
+    col2_kernel<<<cg_grid(n), 256, 0, c.stream>>>(r, vmk, n);                  // :607-608
+    NEKB_LAUNCHED();
+    gs_op(field_handle(), r, 1, nullptr);
+    ProjState &S = proj_get(std::string(cname, 4), n, 20);
+    if (napprox && napprox[1] >= 0 && napprox[1] < S.m) S.m = napprox[1];      // the caller restarted the space
+    project1_dev(S, r, h1, h2, vmk, vml, nel, field_handle(), ifh2);
+    const int it = solve(tol, false);
+    project2_dev(S, u, h1, h2, vmk, vml, nel, field_handle(), ifh2);
+    if (napprox) napprox[0] = S.mmx, napprox[1] = S.m;
+    return it;
+}
+int nekb_hsolve_dev(const char *name4, double *u, double *r, const double *h1, const double *h2, const double *vmk, const double *vml,
+                    int imsh, double tol, int maxit, const double *bi, int *napprox, int *niter)
+{
+    return guard([&] {
+        require_init();
+        const int it = hsolve_dev(name4, strlen(name4), u, r, h1, h2, vmk, vml, imsh, tol, maxit, bi, napprox);
+        ctx().niterhm = it;
+        if (niter) *niter = it;
+    });
+}
+void hsolve_(const char *name, double *u, double *r, const double *h1, const double *h2, const double *vmk, const double *vml,
+             const int *imsh, const double *tol, const int *maxit, const int *isd, double *approx, int *napprox, const double *bi,
+             size_t name_len)
+{
+    (void)isd, (void)approx;  // the approximation space lives on the device (proj.cuh); ivar(1:2) are mirrored into napprox
+    guard_fortran("hsolve", [&] {
+        require_init();
+        Ctx &c = ctx();
+        const int nel = *imsh == 1 ? c.nelv : c.nelt;
+        const size_t n = (size_t)nel * c.nxyz;
+        for (int k = 0; k < 7; k++) c.stage[k].ensure(n);
+        const double *src[6] = {r, h1, h2, vmk, vml, bi};
+        for (int k = 0; k < 6; k++)
+            NEKB_CUDA(cudaMemcpyAsync(c.stage[k + 1].p, src[k], n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        c.niterhm = hsolve_dev(name, name_len, c.stage[0].p, c.stage[1].p, c.stage[2].p, c.stage[3].p, c.stage[4].p, c.stage[5].p, *imsh,
+                               *tol, *maxit, c.stage[6].p, napprox);
+        NEKB_CUDA(cudaMemcpyAsync(u, c.stage[0].p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaMemcpyAsync(r, c.stage[1].p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
         NEKB_CUDA(cudaStreamSynchronize(c.stream));
     });
 }

@@ -316,6 +316,23 @@ def ophinv(o1, o2, o3, i1, i2, i3, h1, h2, tolh: float, nmxhi: int):
     return [int(v) for v in it]
 
 
+def set_projection(ifield: int, ifprojfld: bool, ldimt_proj: int = -1) -> None:
+    check(lib().nekb_set_projection(ifield, int(ifprojfld), ldimt_proj))
+
+
+def projection_reset() -> None:
+    check(lib().nekb_projection_reset())
+
+
+def hsolve(name: str, u, r, h1, h2, vmk, vml, imsh: int, tol: float, maxit: int, isd: int, approx, napprox, bi) -> int:
+    """core/navier4.f:562 hsolve(name,u,r,h1,h2,vmk,vml,imsh,tol,maxit,isd,approx,napprox,bi); returns niterhm.
+    napprox: int32 array (>= 2 entries) that receives ivar(1:2) = (mmx, m); approx is not used (device-resident space)."""
+    nm = name.encode().ljust(4)[:4]
+    lib().hsolve_(nm, _ptr(u), _ptr(r), _ptr(h1), _ptr(h2), _ptr(vmk), _ptr(vml), _i(imsh), C.byref(C.c_double(tol)), _i(maxit),
+                  _i(isd), None if approx is None else _ptr(approx), _ptr(napprox), _ptr(bi), len(nm))
+    return niterhm()
+
+
 def set_param(idx: int, value: float) -> None:
     check(lib().nekb_set_param(idx, float(value)))
 

@@ -240,6 +240,63 @@ def ref_ophinv():
     return out
 
 
+def hsolve_inputs(case, pres=False):
+    """A slowly varying sequence of right-hand sides (what successive time steps hand to hsolve) and the h1/h2 of each call;
+    h2 changes at call 4, which makes project1 rebuild B = A X and re-orthogonalise (iproj_chk)."""
+    n = case.n
+    rng = np.random.default_rng(21)
+    f = [case.bm1() * rng.standard_normal(n) for _ in range(3)]
+    h1 = np.ones(n) if pres else 1.0 + 0.3 * rng.random(n)
+    h2 = np.zeros(n) if pres else 20.0 * (5.0 + rng.random(n))
+    calls = []
+    for k in range(4 if pres else 7):
+        rhs = f[0] + np.sin(0.3 * k) * f[1] + 0.05 * k * k * f[2]
+        calls.append((rhs, h1, h2 * (1.1 if (k >= 4 and not pres) else 1.0), 10 + k))
+    return calls
+
+
+def _ref_hsolve(name, pres):
+    case = case_of("core")
+    rc = _ref(case)
+    R, n = rc.R, case.n
+    if pres:
+        R.set("ifmgrid", 1)
+        R.var("param")[[39, 40, 41, 42, 43]] = 0.0
+        R.call("set_overlap")
+        R.var("param")[20] = 1e-7       # param(21)
+        R.set("tolps", 1e-7)
+    mask = rc.fld("pmask" if pres else "v1mask")
+    R.var("param")[21] = 0.0            # param(22)
+    R.var("param")[92] = 20.0           # param(93): projection on, mxprev vectors
+    R.var("param")[93] = 5.0            # param(94): from step 5 (velocity)
+    R.var("param")[94] = 5.0            # param(95): from step 5 (pressure)
+    R.var("ifprojfld")[1] = 1
+    R.set("ifield", 1)
+    approx, napprox = np.zeros(24 * n), np.zeros(10, dtype=np.int32)
+    out = dict(mask=mask, vmult=rc.fld("vmult"), binvm1=rc.fld("binvm1"), volvm1=np.array([R.get("volvm1")]))
+    its, ms = [], []
+    for k, (rhs, h1, h2, istep) in enumerate(hsolve_inputs(case, pres)):
+        R.set("istep", istep)
+        u, r = np.zeros(n), rhs.copy()
+        R.call("hsolve", name, u, r, h1, h2, mask, out["vmult"], 1, 1e-7, 200, 1, approx, napprox, out["binvm1"])
+        its.append(int(R.get("niterhm"))), ms.append(int(napprox[1]))
+        out[f"u{k}"], out[f"r{k}"] = u, r
+    out["its"], out["m"] = np.array(its), np.array(ms)
+    return out
+
+
+def ref_hsolve():
+    """core/navier4.f:562-634 hsolve with residual projection (project1/project2, :636-1199) around hmhzpf -> cggo (Jacobi
+    PCG): seven successive 'VELX' solves; the space grows to mmx = 8 vectors and is rebuilt when h2 changes."""
+    return _ref_hsolve("VELX", False)
+
+
+def ref_hsolve_pres():
+    """The same around the pressure solver of the Pn-Pn formulation: hsolve('PRES') -> project1 -> hmhzpf -> cggo('PRES') ->
+    hmh_gmres (gmres.f:304-545) with h1mg_solve as preconditioner -> project2; four successive solves."""
+    return _ref_hsolve("PRES", True)
+
+
 MAP_NP = (1, 2, 3, 4, 5, 7, 8, 16, 48)
 
 
@@ -257,7 +314,7 @@ def ref_map():
     return out
 
 
-REFERENCE = dict(core=ref_core, core_lx6=ref_core_lx6, map=ref_map, ophinv=ref_ophinv, bp5=ref_bp5, h1mg=ref_h1mg, h1mg_neumann=ref_h1mg_neumann, fdm=ref_fdm, pnpn2=ref_pnpn2)
+REFERENCE = dict(core=ref_core, core_lx6=ref_core_lx6, map=ref_map, hsolve=ref_hsolve, hsolve_pres=ref_hsolve_pres, ophinv=ref_ophinv, bp5=ref_bp5, h1mg=ref_h1mg, h1mg_neumann=ref_h1mg_neumann, fdm=ref_fdm, pnpn2=ref_pnpn2)
 
 
 def reference_all():

@@ -334,3 +334,56 @@ def test_lx1_6_generic_kernels_against_the_reference():
         assert it == 40 and relmax(u, g["bp5_u1"]) <= TOL_FIELD
     finally:
         nek.finalize()
+
+
+def test_hsolve_with_residual_projection_against_the_reference(nek):
+    """core/navier4.f:562-634 hsolve + project1/project2 (:636-1199), device-resident approximation space: seven successive
+    'VELX' solves (h2 changes at call 4).  Iteration counts within 1 of the reference's 64 58 55 6 49 43 38 (the projected
+    right-hand side is a difference of nearly equal vectors, its sums run in another order), space size m identical."""
+    g, case = G["hsolve"], refcases.case_of("core")
+    gc = G["core"]
+    register_core(nek, gc, case)
+    nek.set_param(22, 0.0), nek.set_param(93, 20.0), nek.set_param(94, 5.0)
+    nek.set_projection(1, True, 3)
+    nek.projection_reset()
+    n = case.n
+    napprox = np.zeros(10, dtype=np.int32)
+    its = []
+    for k, (rhs, h1, h2, istep) in enumerate(refcases.hsolve_inputs(case)):
+        nek.set_step_info(istep, float(g["volvm1"][0]))
+        u, r = np.zeros(n), rhs.copy()
+        it = nek.hsolve("VELX", u, r, h1, h2, g["mask"], g["vmult"], 1, 1e-7, 200, 1, None, napprox, g["binvm1"])
+        its.append(it)
+        assert napprox[0] == 8 and napprox[1] == g["m"][k]
+        assert abs(it - g["its"][k]) <= 1, (k, its, g["its"])
+        scale = np.abs(case.dssum(rhs * g["mask"])).max()
+        assert np.abs(r - g[f"r{k}"]).max() <= 1e-9 * scale, k              # projected right-hand side
+        assert relmax(u, g[f"u{k}"]) <= 1e-6, k
+    assert its[3] < 10 < its[0]
+    # without projection (param(93) = 0) hsolve is hmholtz
+    nek.set_param(93, 0.0)
+    rhs, h1, h2, _ = refcases.hsolve_inputs(case)[0]
+    u, r = np.zeros(n), rhs.copy()
+    it = nek.hsolve("VELX", u, r, h1, h2, g["mask"], g["vmult"], 1, 1e-7, 200, 1, None, napprox, g["binvm1"])
+    xo, ito = case.cggo(case.dssum(rhs) * g["mask"], h1, h2, mask=g["mask"], tin=1e-7, maxit=200, istep=10)
+    assert it == ito and relmax(u, xo) <= TOL_CONVERGED
+
+
+def test_hsolve_pres_with_residual_projection_against_the_reference(nek):
+    """hsolve('PRES') of the Pn-Pn formulation: project1 -> hmhzpf -> cggo('PRES') -> hmh_gmres with h1mg_solve -> project2."""
+    g, case = G["hsolve_pres"], refcases.case_of("core")
+    gc = G["core"]
+    register_core(nek, gc, case)
+    E, n = case.nel, case.n
+    nek.h1mg_setup(refcases.fbc_of("core", case), case.xm1, case.ym1, case.zm1, case.vertex, E, False)
+    nek.set_pressure_state(g["mask"], g["binvm1"], 1e-7, 1e-7, False, E)
+    nek.set_param(22, 0.0), nek.set_param(42, 0.0), nek.set_param(93, 20.0), nek.set_param(95, 5.0)
+    nek.projection_reset()
+    napprox = np.zeros(10, dtype=np.int32)
+    for k, (rhs, h1, h2, istep) in enumerate(refcases.hsolve_inputs(case, pres=True)):
+        nek.set_step_info(istep, float(g["volvm1"][0]))
+        u, r = np.zeros(n), rhs.copy()
+        it = nek.hsolve("PRES", u, r, h1, h2, g["mask"], g["vmult"], 1, 1e-7, 200, 1, None, napprox, g["binvm1"])
+        assert napprox[1] == g["m"][k]
+        assert abs(it - g["its"][k]) <= 1, (k, it, g["its"])
+        assert relmax(u, g[f"u{k}"]) <= 1e-5, k

@@ -184,3 +184,39 @@ def test_second_polynomial_order_lx1_6_bit_exact():
     e1, r1 = c.bp5_problem()
     assert np.array_equal(g["bp5_gf"], c.gf()) and np.array_equal(g["bp5_e1"], e1) and np.array_equal(g["bp5_r1"], r1)
     assert np.array_equal(g["bp5_u1"], c.cggos(r1, e1, tol=-1e-8, maxit=40)[0])
+
+
+def test_hsolve_with_residual_projection():
+    """core/navier4.f:562-634 + project1/project2 (:636-1199): seven successive 'VELX' solves.  The restatement reproduces
+    the reference's iteration counts, the size of the approximation space, and the solutions (to the solver tolerance: the
+    Gram-Schmidt sums run in a different order, which CG amplifies over ~60 iterations)."""
+    from oracle import proj
+    g, c = G["hsolve"], refcases.case_of("core")
+    P = proj.Projection(c, g["mask"], g["vmult"])
+    vol = float(g["volvm1"][0])
+    assert g["its"].tolist()[3] < 10 < g["its"].tolist()[0]        # call 3: the rhs lies in the span of the first three
+    for k, (rhs, h1, h2, istep) in enumerate(refcases.hsolve_inputs(c)):
+        solver = lambda f, t: c.cggo(f, h1, h2, mask=g["mask"], tin=t, maxit=200, istep=istep)
+        u, r, it = proj.hsolve_projected(c, P, rhs, h1, h2, 1e-7, 200, istep, g["binvm1"], vol, solver)
+        assert P.m == g["m"][k]
+        assert abs(it - g["its"][k]) <= 1, (k, it, g["its"][k])
+        scale = np.abs(c.dssum(rhs * g["mask"])).max()
+        assert np.abs(r - g[f"r{k}"]).max() <= 1e-9 * scale, k
+        assert relmax(u, g[f"u{k}"]) <= 1e-6, k
+
+
+def test_hsolve_pres_with_residual_projection():
+    from oracle import proj
+    g, c = G["hsolve_pres"], refcases.case_of("core")
+    mg = hsmg.H1MG(c, refcases.fbc_of("core", c), null_space=False)
+    P = proj.Projection(c, g["mask"], g["vmult"])
+    vol = float(g["volvm1"][0])
+    n = c.n
+    for k, (rhs, h1, h2, istep) in enumerate(refcases.hsolve_inputs(c, pres=True)):
+        def solver(f, t):
+            tolps = min(proj.chktcg1(c, 1e-7, f, h1, h2, g["mask"], g["vmult"], g["binvm1"], vol), 1e-7)   # gmres.f:338-341
+            return hsmg.hmh_gmres(c, mg, f, h1, h2, g["mask"], g["vmult"], tolps, 200)
+        u, r, it = proj.hsolve_projected(c, P, rhs, h1, h2, 1e-7, 200, istep, g["binvm1"], vol, solver)
+        assert P.m == g["m"][k]
+        assert abs(it - g["its"][k]) <= 1, (k, it, g["its"][k])
+        assert relmax(u, g[f"u{k}"]) <= 1e-5, k
