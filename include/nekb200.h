@@ -198,6 +198,23 @@ int nekb_projection_reset(void);
 int nekb_hsolve_dev(const char *name4, double *u, double *r, const double *h1, const double *h2, const double *vmk, const double *vml,
                     int imsh, double tol, int maxit, const double *bi, int *napprox, int *niter);
 
+/* ---- Pn-Pn-2 pressure operator E = D (h2 B)^-1 D^T (3-D, lx1 = 8, lx2 = 6) -------------------------
+ * core/navier1.f:4095 opgradt(outx,outy,outz,inpfld) -> cdtp (:330-536);  :4064 opdiv(outfld,inpx,inpy,inpz) -> multd
+ * (:538-714);  :775 opbinv(out1,out2,out3,inp1,inp2,inp3,h2inv) (inp_i return masked + dssum'ed, as in the reference);
+ * :258 cdabdtp(ap,wp,h1,h2,h2inv,intype): intype = 1 -> opbinv, intype = 0 / -1 -> ophinv with (tolhs, nmxv).
+ * nekb_set_mesh2 registers what these read from COMMON: ixm12, dxm12 (lx2,lx1 column-major; core/IXYZ, DXYZ), w3m2 (WZ),
+ * the nine metric arrays in the order rxm2, sxm2, txm2, rym2, sym2, tym2, rzm2, szm2, tzm2 (GEOM), bm2, bm2inv (MASS; may be
+ * NULL when uzawa_gmres is not used), volvm2, tolhs (TSTEP), nmxv (INPUT), nelgv and ifvcor (for ortho). */
+int nekb_set_mesh2(int lx2, const double *ixm12, const double *dxm12, const double *w3m2, const double *const *metrics9, const double *bm2,
+                   const double *bm2inv, double volvm2, double tolhs, int nmxv, int64_t nelgv, int ifvcor);
+void opgradt_(double *outx, double *outy, double *outz, const double *inpfld);
+void opdiv_(double *outfld, const double *inpx, const double *inpy, const double *inpz);
+void opbinv_(double *out1, double *out2, double *out3, double *inp1, double *inp2, double *inp3, const double *h2inv);
+void cdabdtp_(double *ap, const double *wp, const double *h1, const double *h2, const double *h2inv, const int *intype);
+int nekb_opgradt_dev(double *ox, double *oy, double *oz, const double *p);
+int nekb_opdiv_dev(double *out, const double *ux, const double *uy, const double *uz);
+int nekb_cdabdtp_dev(double *ap, const double *wp, const double *h1, const double *h2, const double *h2inv, int intype);
+
 /* INPUT param(idx), 1-based: the path reads param(21) (pressure tolerance), param(22) (Helmholtz tolerance; < 0 relative,
  * core/hmholtz.f:764).  MASS binvm1 / bintm1 (host, lx1^3*nelv / nelt doubles; bintm1 may be NULL) for hmholtz. */
 int nekb_set_param(int idx, double value);

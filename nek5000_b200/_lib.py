@@ -151,6 +151,12 @@ def lib() -> C.CDLL:
     L.ophinv_.restype = None
     L.hsolve_.argtypes = [C.c_char_p, vp, vp, vp, vp, vp, vp, ip, dp, ip, ip, vp, vp, vp, C.c_size_t]
     L.hsolve_.restype = None
+    L.nekb_set_mesh2.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, C.c_int64, C.c_int]
+    for nm, k in (("opgradt_", 4), ("opdiv_", 4), ("opbinv_", 7)):
+        getattr(L, nm).argtypes = [vp] * k
+        getattr(L, nm).restype = None
+    L.cdabdtp_.argtypes = [vp] * 5 + [ip]
+    L.cdabdtp_.restype = None
     L.nekb_set_projection.argtypes = [C.c_int, C.c_int, C.c_int]
     L.nekb_hsolve_dev.argtypes = [C.c_char_p] + [vp] * 6 + [C.c_int, C.c_double, C.c_int, vp, vp, ip]
     L.nekb_set_param.argtypes = [C.c_int, C.c_double]

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnekb200.so")
 SOURCES = ["nekb200.cu"]
 HEADERS = ["common.cuh", "ctx.cuh", "ax.cuh", "gs.cuh", "cg.cuh", "comm.cuh", "setup.cuh", "hsmg.cuh", "fdm_h1.cuh", "gmres.cuh", "hcg.cuh",
-           "readers.cuh", "proj.cuh"]
+           "readers.cuh", "proj.cuh", "pnpn2.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

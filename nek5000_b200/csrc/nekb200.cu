@@ -5,6 +5,7 @@
 #include "gmres.cuh"
 #include "hcg.cuh"
 #include "proj.cuh"
+#include "pnpn2.cuh"
 #include "readers.cuh"
 
 using namespace nekb;
@@ -1260,6 +1261,133 @@ void hmh_gmres_(double *res, const double *h1, const double *h2, const double *w
         for (size_t t = 0; t < n && !ifh2; t++) ifh2 = h2[t] != 0.0;
         *iter = hmh_gmres_body(c.stage[0].p, c.stage[1].p, ifh2 ? c.stage[2].p : nullptr, c.stage[3].p, *iter);
         NEKB_CUDA(cudaMemcpyAsync(res, c.stage[0].p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------- Pn-Pn-2 E operator
+// core/navier1.f:258-293 cdabdtp(ap,wp,h1,h2,h2inv,intype) on device pointers
+static void cdabdtp_dev(double *ap, const double *wp, const double *h1, const double *h2, const double *h2inv, int intype)
+{
+    Ctx &c = ctx();
+    const size_t n = (size_t)c.nelv * c.nxyz;
+    Pnpn2Work &W = pnpn2_work();
+    for (int k = 0; k < 3; k++) W.ta[k].ensure(n), W.tb[k].ensure(n);
+    opgradt_dev(W.ta[0].p, W.ta[1].p, W.ta[2].p, wp);
+    if (intype == 0 || intype == -1) {   // D (h1 A + h2 B)^-1 D^T: the three velocity solves (tolhs, nmxv)
+        NEKB_REQUIRE(c.vmask[0].n >= n && c.vmask[1].n >= n && c.vmask[2].n >= n && c.vmult.n >= n && c.binvm1.n >= n,
+                     "cdabdtp(intype 0/-1): v1mask..v3mask, vmult, binvm1 not registered");
+        double *o[3] = {W.tb[0].p, W.tb[1].p, W.tb[2].p}, *r[3] = {W.ta[0].p, W.ta[1].p, W.ta[2].p};
+        const double *m[3] = {c.vmask[0].p, c.vmask[1].p, c.vmask[2].p};
+        ophinv_dev(o, r, h1, h2, m, c.vmult.p, c.binvm1.p, mesh2().tolhs, mesh2().nmxv, c.niter3, nullptr);
+    } else
+        opbinv_dev(W.tb[0].p, W.tb[1].p, W.tb[2].p, W.ta[0].p, W.ta[1].p, W.ta[2].p, h2inv, field_handle());
+    opdiv_dev(ap, W.tb[0].p, W.tb[1].p, W.tb[2].p);
+}
+int nekb_set_mesh2(int lx2, const double *ixm12, const double *dxm12, const double *w3m2, const double *const *metrics9, const double *bm2,
+                   const double *bm2inv, double volvm2, double tolhs, int nmxv, int64_t nelgv, int ifvcor)
+{
+    return guard([&] {
+        require_init();
+        Ctx &c = ctx();
+        Mesh2 &M = mesh2();
+        NEKB_REQUIRE(lx2 == c.nx - 2, "set_mesh2: lx2 must be lx1 - 2");
+        const int lx1 = c.nx;
+        // ixm12(lx2,lx1), dxm12(lx2,lx1) arrive column-major (Fortran): element (a,i) at a + lx2*i
+        std::vector<double> I((size_t)lx2 * lx1), D((size_t)lx2 * lx1);
+        for (int a = 0; a < lx2; a++)
+            for (int i = 0; i < lx1; i++) I[(size_t)a * lx1 + i] = ixm12[a + lx2 * i], D[(size_t)a * lx1 + i] = dxm12[a + lx2 * i];
+        M.i12.upload(I.data(), I.size(), c.stream), M.d12.upload(D.data(), D.size(), c.stream);
+        const size_t p2 = (size_t)lx2 * lx2 * lx2, n2 = p2 * c.nelv;
+        M.w3.upload(w3m2, p2, c.stream);
+        for (int k = 0; k < 9; k++) M.met[k].upload(metrics9[k], n2, c.stream);
+        if (bm2) M.bm2.upload(bm2, n2, c.stream);
+        if (bm2inv) M.bm2inv.upload(bm2inv, n2, c.stream);
+        M.lx2 = lx2, M.volvm2 = volvm2, M.tolhs = tolhs, M.nmxv = nmxv, M.nelgv = nelgv, M.ifvcor = ifvcor != 0;
+        M.ml.release(), M.mu.release();
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+        M.ready = true;
+    });
+}
+int nekb_opgradt_dev(double *ox, double *oy, double *oz, const double *p)
+{
+    return guard([&] {
+        require_init();
+        opgradt_dev(ox, oy, oz, p);
+    });
+}
+int nekb_opdiv_dev(double *out, const double *ux, const double *uy, const double *uz)
+{
+    return guard([&] {
+        require_init();
+        opdiv_dev(out, ux, uy, uz);
+    });
+}
+int nekb_cdabdtp_dev(double *ap, const double *wp, const double *h1, const double *h2, const double *h2inv, int intype)
+{
+    return guard([&] {
+        require_init();
+        cdabdtp_dev(ap, wp, h1, h2, h2inv, intype);
+    });
+}
+void opgradt_(double *outx, double *outy, double *outz, const double *inpfld)
+{
+    guard_fortran("opgradt", [&] {
+        require_init();
+        Ctx &c = ctx();
+        require_mesh2();
+        const size_t n = (size_t)c.nelv * c.nxyz, n2 = (size_t)c.nelv * 216;
+        for (int k = 0; k < 4; k++) c.stage[k].ensure(n);
+        NEKB_CUDA(cudaMemcpyAsync(c.stage[3].p, inpfld, n2 * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        opgradt_dev(c.stage[0].p, c.stage[1].p, c.stage[2].p, c.stage[3].p);
+        double *dst[3] = {outx, outy, outz};
+        for (int k = 0; k < 3; k++) NEKB_CUDA(cudaMemcpyAsync(dst[k], c.stage[k].p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+void opdiv_(double *outfld, const double *inpx, const double *inpy, const double *inpz)
+{
+    guard_fortran("opdiv", [&] {
+        require_init();
+        Ctx &c = ctx();
+        require_mesh2();
+        const size_t n = (size_t)c.nelv * c.nxyz, n2 = (size_t)c.nelv * 216;
+        for (int k = 0; k < 4; k++) c.stage[k].ensure(n);
+        const double *src[3] = {inpx, inpy, inpz};
+        for (int k = 0; k < 3; k++) NEKB_CUDA(cudaMemcpyAsync(c.stage[k].p, src[k], n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        opdiv_dev(c.stage[3].p, c.stage[0].p, c.stage[1].p, c.stage[2].p);
+        NEKB_CUDA(cudaMemcpyAsync(outfld, c.stage[3].p, n2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+void opbinv_(double *out1, double *out2, double *out3, double *inp1, double *inp2, double *inp3, const double *h2inv)
+{
+    guard_fortran("opbinv", [&] {
+        require_init();
+        Ctx &c = ctx();
+        const size_t n = (size_t)c.nelv * c.nxyz;
+        for (int k = 0; k < 7; k++) c.stage[k].ensure(n);
+        const double *src[4] = {inp1, inp2, inp3, h2inv};
+        for (int k = 0; k < 4; k++) NEKB_CUDA(cudaMemcpyAsync(c.stage[k + 3].p, src[k], n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        opbinv_dev(c.stage[0].p, c.stage[1].p, c.stage[2].p, c.stage[3].p, c.stage[4].p, c.stage[5].p, c.stage[6].p, field_handle());
+        double *dst[6] = {out1, out2, out3, inp1, inp2, inp3};
+        for (int k = 0; k < 6; k++) NEKB_CUDA(cudaMemcpyAsync(dst[k], c.stage[k].p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+void cdabdtp_(double *ap, const double *wp, const double *h1, const double *h2, const double *h2inv, const int *intype)
+{
+    guard_fortran("cdabdtp", [&] {
+        require_init();
+        Ctx &c = ctx();
+        require_mesh2();
+        const size_t n = (size_t)c.nelv * c.nxyz, n2 = (size_t)c.nelv * 216;
+        for (int k = 0; k < 5; k++) c.stage[k].ensure(n);
+        NEKB_CUDA(cudaMemcpyAsync(c.stage[1].p, wp, n2 * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        const double *src[3] = {h1, h2, h2inv};
+        for (int k = 0; k < 3; k++) NEKB_CUDA(cudaMemcpyAsync(c.stage[k + 2].p, src[k], n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        cdabdtp_dev(c.stage[0].p, c.stage[1].p, c.stage[2].p, c.stage[3].p, c.stage[4].p, *intype);
+        NEKB_CUDA(cudaMemcpyAsync(ap, c.stage[0].p, n2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
         NEKB_CUDA(cudaStreamSynchronize(c.stream));
     });
 }

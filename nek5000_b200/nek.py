@@ -333,6 +333,41 @@ def hsolve(name: str, u, r, h1, h2, vmk, vml, imsh: int, tol: float, maxit: int,
     return niterhm()
 
 
+def set_mesh2(lx2: int, ixm12, dxm12, w3m2, metrics9, bm2=None, bm2inv=None, volvm2: float = 0.0, tolhs: float = 1e-8,
+              nmxv: int = 1000, nelgv: int = 0, ifvcor: bool = False) -> None:
+    """Mesh-2 (pressure, Gauss points) state of the Pn-Pn-2 operators.  ixm12, dxm12: (lx2, lx1) arrays as numpy sees the
+    Fortran arrays (element [a, i] = ixm12(a,i)); metrics9: rxm2, sxm2, txm2, rym2, sym2, tym2, rzm2, szm2, tzm2."""
+    f = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float64).T).reshape(-1)     # -> column-major bytes
+    I, D = f(ixm12), f(dxm12)
+    w = np.ascontiguousarray(w3m2, dtype=np.float64).reshape(-1)
+    mets = [np.ascontiguousarray(m, dtype=np.float64).reshape(-1) for m in metrics9]
+    arr = (C.c_void_p * 9)(*[m.ctypes.data for m in mets])
+    b = None if bm2 is None else np.ascontiguousarray(bm2, dtype=np.float64).reshape(-1)
+    bi = None if bm2inv is None else np.ascontiguousarray(bm2inv, dtype=np.float64).reshape(-1)
+    check(lib().nekb_set_mesh2(lx2, _ptr(I), _ptr(D), _ptr(w), C.cast(arr, C.c_void_p), None if b is None else _ptr(b),
+                               None if bi is None else _ptr(bi), volvm2, tolhs, nmxv, nelgv, int(ifvcor)))
+
+
+def opgradt(outx, outy, outz, inpfld) -> None:
+    """core/navier1.f:4095 opgradt."""
+    lib().opgradt_(_ptr(outx), _ptr(outy), _ptr(outz), _ptr(inpfld))
+
+
+def opdiv(outfld, inpx, inpy, inpz) -> None:
+    """core/navier1.f:4064 opdiv."""
+    lib().opdiv_(_ptr(outfld), _ptr(inpx), _ptr(inpy), _ptr(inpz))
+
+
+def opbinv(out1, out2, out3, inp1, inp2, inp3, h2inv) -> None:
+    """core/navier1.f:775 opbinv."""
+    lib().opbinv_(_ptr(out1), _ptr(out2), _ptr(out3), _ptr(inp1), _ptr(inp2), _ptr(inp3), _ptr(h2inv))
+
+
+def cdabdtp(ap, wp, h1, h2, h2inv, intype: int) -> None:
+    """core/navier1.f:258 cdabdtp."""
+    lib().cdabdtp_(_ptr(ap), _ptr(wp), _ptr(h1), _ptr(h2), _ptr(h2inv), _i(intype))
+
+
 def set_param(idx: int, value: float) -> None:
     check(lib().nekb_set_param(idx, float(value)))
 

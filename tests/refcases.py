@@ -25,7 +25,8 @@ MESH = {
     "neumann": ((3, 2, 2), (1, 1, 1, 1, 1, 1), 0.05),
     "fdm": ((3, 3, 2), (1, 1, 0, 0, 1, 1), 0.02),
     "pnpn2": ((3, 2, 2), (1, 1, 1, 1, 1, 0), 0.0),
-    "ophinv": ((3, 2, 2), (1, 2, 1, 2, 1, 0), 0.05),      # 2 = 'SYM': the three velocity masks differ
+    "ophinv": ((3, 2, 2), (1, 2, 1, 2, 1, 0), 0.05),
+    "eop": ((3, 2, 2), (1, 2, 1, 1, 1, 0), 0.05),          # Pn-Pn-2 E operator: deformed, wall / symmetry / outflow sides      # 2 = 'SYM': the three velocity masks differ
 }
 
 
@@ -297,6 +298,40 @@ def ref_hsolve_pres():
     return _ref_hsolve("PRES", True)
 
 
+MET9 = ("rxm2", "sxm2", "txm2", "rym2", "sym2", "tym2", "rzm2", "szm2", "tzm2")
+
+
+def ref_eop():
+    """The Pn-Pn-2 pressure operator: opgradt / cdtp, opdiv / multd, opbinv, cdabdtp(intype = 1) (core/navier1.f:258-850,
+    4064-4114) with the mesh-2 geometry of geom2 (core/coef.f) on a deformed box."""
+    case = case_of("eop")
+    rc = _ref(case, lx2=6, ifsplit=False)
+    R, E, n = rc.R, case.nel, case.n
+    n2 = 216 * E
+    f2 = lambda nm: R.var(nm)[..., :E].ravel(order="F").copy()
+    out = dict(ixm12=R.var("ixm12").copy(), dxm12=R.var("dxm12").copy(), w3m2=R.var("w3m2").ravel(order="F").copy(),
+               bm2=f2("bm2"), bm2inv=f2("bm2inv"), volvm2=np.array([R.get("volvm2")]), volvm1=np.array([R.get("volvm1")]),
+               v1mask=rc.fld("v1mask"), v2mask=rc.fld("v2mask"), v3mask=rc.fld("v3mask"), vmult=rc.fld("vmult"),
+               binvm1=rc.fld("binvm1"), bm1=rc.fld("bm1"))
+    for nm in MET9:
+        out[nm] = f2(nm)
+    rng = np.random.default_rng(31)
+    p = rng.standard_normal(n2)
+    o = [np.zeros(n) for _ in range(3)]
+    R.call("opgradt", o[0], o[1], o[2], p)
+    u = [rng.standard_normal(n) for _ in range(3)]
+    d = np.zeros(n2)
+    R.call("opdiv", d, u[0], u[1], u[2])
+    h2inv = 1.0 / (50.0 + rng.random(n))
+    bo, bi = [np.zeros(n) for _ in range(3)], [a.copy() for a in u]
+    R.call("opbinv", bo[0], bo[1], bo[2], bi[0], bi[1], bi[2], h2inv)
+    ap = np.zeros(n2)
+    R.call("cdabdtp", ap, p, np.ones(n), 1.0 / h2inv, h2inv, 1)
+    out.update(p=p, gx=o[0], gy=o[1], gz=o[2], ux=u[0], uy=u[1], uz=u[2], div=d, h2inv=h2inv, bo1=bo[0], bo2=bo[1], bo3=bo[2],
+               bi1=bi[0], bi2=bi[1], bi3=bi[2], ap=ap)
+    return out
+
+
 MAP_NP = (1, 2, 3, 4, 5, 7, 8, 16, 48)
 
 
@@ -314,7 +349,7 @@ def ref_map():
     return out
 
 
-REFERENCE = dict(core=ref_core, core_lx6=ref_core_lx6, map=ref_map, hsolve=ref_hsolve, hsolve_pres=ref_hsolve_pres, ophinv=ref_ophinv, bp5=ref_bp5, h1mg=ref_h1mg, h1mg_neumann=ref_h1mg_neumann, fdm=ref_fdm, pnpn2=ref_pnpn2)
+REFERENCE = dict(core=ref_core, core_lx6=ref_core_lx6, map=ref_map, eop=ref_eop, hsolve=ref_hsolve, hsolve_pres=ref_hsolve_pres, ophinv=ref_ophinv, bp5=ref_bp5, h1mg=ref_h1mg, h1mg_neumann=ref_h1mg_neumann, fdm=ref_fdm, pnpn2=ref_pnpn2)
 
 
 def reference_all():

@@ -387,3 +387,49 @@ def test_hsolve_pres_with_residual_projection_against_the_reference(nek):
         assert napprox[1] == g["m"][k]
         assert abs(it - g["its"][k]) <= 1, (k, it, g["its"])
         assert relmax(u, g[f"u{k}"]) <= 1e-5, k
+
+
+def _register_eop(nek, g, case):
+    E = case.nel
+    nek.set_nel(E, E)
+    nek.set_gll(case.z, case.w)
+    nek.set_dxyz(case.D, case.Dt)
+    nek.set_geom(*case.geom()[:6], g["bm1"])
+    nek.set_ifdfrm(None)
+    h, _ = nek.setupds(8, E, case.vertex)
+    nek.set_ifield(1)
+    nek.set_field_handle(1, h)
+    nek.set_step_info(20, float(g["volvm1"][0]))
+    nek.set_binv(g["binvm1"])
+    nek.set_velocity_state(g["v1mask"], g["v2mask"], g["v3mask"], g["vmult"])
+    nek.set_mesh2(6, g["ixm12"], g["dxm12"], g["w3m2"], [g[k] for k in refcases.MET9], g["bm2"], g["bm2inv"],
+                  float(g["volvm2"][0]), 1e-8, 200, E, False)
+
+
+def test_pnpn2_pressure_operator_against_the_reference(nek):
+    """opgradt (D^T), opdiv (D), opbinv and cdabdtp(intype = 1) = D (h2 B)^-1 D^T of the Pn-Pn-2 formulation
+    (core/navier1.f:258-850, 4064-4114) on a deformed box with wall, symmetry and outflow sides."""
+    g, case = G["eop"], refcases.case_of("eop")
+    _register_eop(nek, g, case)
+    n, n2 = case.n, 216 * case.nel
+    o = [np.zeros(n) for _ in range(3)]
+    nek.opgradt(*o, g["p"])
+    for a, k in zip(o, ("gx", "gy", "gz")):
+        assert relmax(a, g[k]) <= TOL_APPLY, k
+    d = np.zeros(n2)
+    nek.opdiv(d, g["ux"], g["uy"], g["uz"])
+    assert relmax(d, g["div"]) <= TOL_APPLY
+    bo = [np.zeros(n) for _ in range(3)]
+    bi = [g["ux"].copy(), g["uy"].copy(), g["uz"].copy()]
+    nek.opbinv(*bo, *bi, g["h2inv"])
+    for k in range(3):
+        assert relmax(bi[k], g[f"bi{k + 1}"]) <= TOL_APPLY and relmax(bo[k], g[f"bo{k + 1}"]) <= TOL_APPLY
+    ap = np.zeros(n2)
+    nek.cdabdtp(ap, g["p"], np.ones(n), 1.0 / g["h2inv"], g["h2inv"], 1)
+    assert relmax(ap, g["ap"]) <= TOL_APPLY
+    # E is symmetric positive semi-definite: (q, E p) = (p, E q), (p, E p) > 0
+    rng = np.random.default_rng(2)
+    q = rng.standard_normal(n2)
+    aq = np.zeros(n2)
+    nek.cdabdtp(aq, q, np.ones(n), 1.0 / g["h2inv"], g["h2inv"], 1)
+    assert abs(np.dot(q, ap) - np.dot(g["p"], aq)) <= 1e-11 * abs(np.dot(q, ap)) and np.dot(g["p"], ap) > 0

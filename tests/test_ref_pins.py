@@ -38,7 +38,7 @@ def _ref_available():
 @pytest.mark.parametrize("name", list(refcases.REFERENCE))
 def test_golden_file_is_what_the_reference_computes_now(name):
     from oracle import ref
-    if name == "pnpn2" and not ref.available(8, 6, 64):
+    if name in ("pnpn2", "eop") and not ref.available(8, 6, 64):
         pytest.skip("Pn-Pn-2 build of oracle/_ref not available")
     if name == "core_lx6" and not ref.available(6, 6, 64):
         pytest.skip("lx1 = 6 build of oracle/_ref not available")
@@ -220,3 +220,27 @@ def test_hsolve_pres_with_residual_projection():
         assert P.m == g["m"][k]
         assert abs(it - g["its"][k]) <= 1, (k, it, g["its"][k])
         assert relmax(u, g[f"u{k}"]) <= 1e-5, k
+
+
+def _mesh2(g, c):
+    from oracle import pnpn2
+    return pnpn2.Mesh2(c, g["ixm12"], g["dxm12"], g["w3m2"], [g[k] for k in refcases.MET9], g["bm2"], g["bm2inv"], float(g["volvm2"][0]))
+
+
+def test_pnpn2_pressure_operator_pieces():
+    """opgradt / opdiv / opbinv / cdabdtp(intype = 1) against the reference (core/navier1.f:258-850,4064-4114); D and D^T are
+    adjoint under the plain dot product."""
+    g, c = G["eop"], refcases.case_of("eop")
+    M = _mesh2(g, c)
+    gx, gy, gz = M.opgradt(g["p"])
+    for a, k in ((gx, "gx"), (gy, "gy"), (gz, "gz")):
+        assert relmax(a, g[k]) <= 1e-13, k
+    u = [g["ux"], g["uy"], g["uz"]]
+    d = M.opdiv(u)
+    assert relmax(d, g["div"]) <= 1e-13
+    assert abs(np.dot(d, g["p"]) - sum(np.dot(u[i], (gx, gy, gz)[i]) for i in range(3))) <= 1e-12 * abs(np.dot(d, g["p"]))
+    masks = [g["v1mask"], g["v2mask"], g["v3mask"]]
+    bo, bi = M.opbinv(u, g["h2inv"], masks)
+    for k in range(3):
+        assert np.array_equal(bi[k], g[f"bi{k + 1}"]) and relmax(bo[k], g[f"bo{k + 1}"]) <= 1e-14
+    assert relmax(M.cdabdtp(g["p"], g["h2inv"], masks), g["ap"]) <= 1e-12
