@@ -211,6 +211,14 @@ void opgradt_(double *outx, double *outy, double *outz, const double *inpfld);
 void opdiv_(double *outfld, const double *inpx, const double *inpy, const double *inpz);
 void opbinv_(double *out1, double *out2, double *out3, double *inp1, double *inp2, double *inp3, const double *h2inv);
 void cdabdtp_(double *ap, const double *wp, const double *h1, const double *h2, const double *h2inv, const int *intype);
+/* core/gmres.f:2-237 uzawa_gmres(res,h1,h2,h2inv,intype,iter): right-preconditioned GMRES(lgmres) on E = cdabdtp with
+ * hsmg_solve as preconditioner (nekb_hsmg_setup first; param(43) = 0), split weights sqrt(bm2inv) / sqrt(bm2), tolerance
+ * through chktcg2 (core/navier1.f:1089-1154).  res is overwritten with the pressure update; iter returns the count.
+ * nekb_set_uzawa_state: TSTEP tolps, INPUT param(21), TSTEP prelax, tolpdf. */
+void uzawa_gmres_(double *res, const double *h1, const double *h2, const double *h2inv, const int *intype, int *iter);
+int nekb_set_uzawa_state(double tolps, double param21, double prelax, double tolpdf);
+int nekb_uzawa_gmres_dev(double *res, const double *h1, const double *h2, const double *h2inv, int intype, int *iter, double *div0,
+                         double *divex);
 int nekb_opgradt_dev(double *ox, double *oy, double *oz, const double *p);
 int nekb_opdiv_dev(double *out, const double *ux, const double *uy, const double *uz);
 int nekb_cdabdtp_dev(double *ap, const double *wp, const double *h1, const double *h2, const double *h2inv, int intype);

@@ -1284,6 +1284,200 @@ static void cdabdtp_dev(double *ap, const double *wp, const double *h1, const do
         opbinv_dev(W.tb[0].p, W.tb[1].p, W.tb[2].p, W.ta[0].p, W.ta[1].p, W.ta[2].p, h2inv, field_handle());
     opdiv_dev(ap, W.tb[0].p, W.tb[1].p, W.tb[2].p);
 }
+// core/navier1.f:1089-1154 chktcg2
+static double chktcg2_dev(double tol, const double *res, int64_t n2)
+{
+    Ctx &c = ctx();
+    Mesh2 &M = mesh2();
+    const double eps = M.prelax != 0.0 ? M.prelax : 1.e-10;
+    M.t1.ensure((size_t)n2);
+    uz_resid_kernel<<<cg_grid(n2), 256, 0, c.stream>>>(M.t1.p, M.bm2inv.p, res, nullptr, n2);   // ta = res*bm2inv
+    NEKB_LAUNCHED();
+    const double rinit = sqrt(gm_glsc3(M.t1.p, M.t1.p, M.bm2.p, n2) / M.volvm2);
+    if (rinit < tol) return tol;
+    const double rmin = M.tolpdf > 0.0 ? M.tolpdf : eps * rinit;
+    if (tol < rmin) tol = rmin;
+    if (M.ifvcor) {
+        const double otr = gm_glsc3(res, M.ones.p, M.ones.p, n2);
+        const double tolmin = fabs(otr) * 100.0;
+        if (tol < tolmin) tol = tolmin;
+    }
+    return tol;
+}
+// core/gmres.f:2-237 uzawa_gmres(res,h1,h2,h2inv,intype,iter) on device pointers: right-preconditioned GMRES(lgmres) on
+// E = cdabdtp with hsmg_solve as preconditioner, split weights ml = sqrt(bm2inv), mu = sqrt(bm2).  Returns iter.
+static int uzawa_gmres_dev(double *res, const double *h1, const double *h2, const double *h2inv, int intype)
+{
+    Ctx &c = ctx();
+    Mesh2 &M = mesh2();
+    require_mesh2();
+    cudaStream_t s = c.stream;
+    const int64_t n2 = (int64_t)c.nelv * 216;
+    NEKB_REQUIRE(M.bm2.n >= (size_t)n2 && M.bm2inv.n >= (size_t)n2 && M.volvm2 > 0.0, "uzawa_gmres: bm2, bm2inv, volvm2 not registered");
+    const int m = gmres_state().m, grid = cg_grid(n2);
+    GmresState &G = gmres_state();
+    G.scal.ensure(64);
+    c.partials.ensure((size_t)(GM_NV > 4 ? GM_NV : 4) * CG_PART_STRIDE);
+    if ((int)M.V.size() != m + 1) M.V.resize(m + 1), M.Z.resize(m);
+    M.r.ensure((size_t)n2), M.w.ensure((size_t)n2), M.x.ensure((size_t)n2);
+    if (M.ones.n < (size_t)n2) {
+        M.ones.alloc((size_t)n2);
+        fill_kernel<<<grid, 256, 0, s>>>(M.ones.p, 1.0, n2);
+        NEKB_LAUNCHED();
+    }
+    if (M.ml.n < (size_t)n2) {
+        M.ml.alloc((size_t)n2), M.mu.alloc((size_t)n2);
+        uz_split_kernel<<<grid, 256, 0, s>>>(M.ml.p, M.mu.p, M.bm2.p, M.bm2inv.p, n2);
+        NEKB_LAUNCHED();
+    }
+    auto Vj = [&](int j) -> double * {
+        M.V[j].ensure((size_t)n2);
+        return M.V[j].p;
+    };
+    auto Zj = [&](int j) -> double * {
+        M.Z[j].ensure((size_t)n2);
+        return M.Z[j].p;
+    };
+    const double norm_fac = 1.0 / sqrt(M.volvm2);
+    double tolps = chktcg2_dev(M.tolps, res, n2);
+    if (M.param21 > 0 && tolps > fabs(M.param21)) tolps = fabs(M.param21);
+    if (c.istep == 0) tolps = 1.e-4;
+    double tolpss = tolps;
+    std::vector<double> H((size_t)(m + 1) * m, 0.0), cg(m, 0.0), sg(m, 0.0), gam(m + 1, 0.0), cvec(m, 0.0), hcol(m + 1);
+    auto Hm = [&](int i, int j) -> double & { return H[(size_t)i * m + j]; };
+    NEKB_CUDA(cudaMemsetAsync(M.x.p, 0, sizeof(double) * (size_t)n2, s));
+    int iter = 0, j = 0;
+    bool conv = false;
+    double div0 = 0.0, rnorm = 0.0;
+    unsigned *counter = &c.sc.p->counter[0];
+    const double *wt = M.ones.p;
+    while (!conv && iter < 100) {
+        if (iter == 0)
+            uz_resid_kernel<<<grid, 256, 0, s>>>(M.r.p, M.ml.p, res, nullptr, n2);
+        else {
+            cdabdtp_dev(M.w.p, M.x.p, h1, h2, h2inv, intype);
+            uz_resid_kernel<<<grid, 256, 0, s>>>(M.r.p, M.ml.p, res, M.w.p, n2);
+        }
+        NEKB_LAUNCHED();
+        gam[0] = sqrt(gm_glsc3(M.r.p, M.r.p, wt, n2));
+        if (iter == 0) {
+            div0 = gam[0] * norm_fac;
+            if (M.param21 < 0) tolpss = fabs(M.param21) * div0;
+        }
+        rnorm = 0.0;
+        if (gam[0] == 0.0) break;
+        gm_cmult2_kernel<<<grid, 256, 0, s>>>(Vj(0), M.r.p, 1.0 / gam[0], n2);
+        NEKB_LAUNCHED();
+        for (j = 0; j < m; j++) {
+            iter++;
+            uz_resid_kernel<<<grid, 256, 0, s>>>(M.w.p, M.mu.p, Vj(j), nullptr, n2);     // w = U^-1 v_j
+            NEKB_LAUNCHED();
+            hsmg_solve_dev(Zj(j), M.w.p);                                                 // z_j = M^-1 w
+            cdabdtp_dev(M.w.p, Zj(j), h1, h2, h2inv, intype);                             // w = E z_j
+            col2_kernel<<<grid, 256, 0, s>>>(M.w.p, M.ml.p, n2);                          // w = L^-1 w
+            NEKB_LAUNCHED();
+            for (int i0 = 0; i0 <= j; i0 += GM_NV) {
+                const int nv = (j + 1 - i0) < GM_NV ? (j + 1 - i0) : GM_NV;
+                GmPtrs P;
+                for (int q = 0; q < GM_NV; q++) P.v[q] = Vj(i0 + (q < nv ? q : 0)), P.h[q] = 0.0;
+                gm_dots_kernel<<<grid, 256, 0, s>>>(M.w.p, wt, P, nv, n2, G.scal.p + i0, c.partials.p, counter);
+                NEKB_LAUNCHED();
+            }
+            gm_reduce_to_host(G.scal.p, j + 1, hcol.data());
+            for (int i = 0; i <= j; i++) Hm(i, j) = hcol[i];
+            double alpha2 = 0.0;
+            for (int i0 = 0; i0 <= j; i0 += GM_NV) {
+                const int nv = (j + 1 - i0) < GM_NV ? (j + 1 - i0) : GM_NV;
+                const bool last = i0 + GM_NV > j;
+                GmPtrs P;
+                for (int q = 0; q < GM_NV; q++) P.v[q] = Vj(i0 + (q < nv ? q : 0)), P.h[q] = q < nv ? hcol[i0 + q] : 0.0;
+                gm_project_kernel<<<grid, 256, 0, s>>>(M.w.p, wt, P, nv, n2, last ? 1 : 0, G.scal.p + 40, c.partials.p, counter);
+                NEKB_LAUNCHED();
+            }
+            gm_reduce_to_host(G.scal.p + 40, 1, &alpha2);
+            for (int i = 0; i < j; i++) {
+                const double t = Hm(i, j);
+                Hm(i, j) = cg[i] * t + sg[i] * Hm(i + 1, j);
+                Hm(i + 1, j) = -sg[i] * t + cg[i] * Hm(i + 1, j);
+            }
+            const double alpha = sqrt(alpha2);
+            rnorm = 0.0;
+            if (alpha == 0.0) {
+                conv = true;
+                break;
+            }
+            const double l = sqrt(Hm(j, j) * Hm(j, j) + alpha * alpha), t = 1.0 / l;
+            cg[j] = Hm(j, j) * t;
+            sg[j] = alpha * t;
+            Hm(j, j) = l;
+            gam[j + 1] = -sg[j] * gam[j];
+            gam[j] = cg[j] * gam[j];
+            rnorm = fabs(gam[j + 1]) * norm_fac;
+            if (rnorm < tolpss) {
+                conv = true;
+                break;
+            }
+            if (j == m - 1) break;  // restart
+            gm_cmult2_kernel<<<grid, 256, 0, s>>>(Vj(j + 1), M.w.p, 1.0 / alpha, n2);
+            NEKB_LAUNCHED();
+        }
+        const int kk = j + 1 > m ? m : j + 1;
+        for (int k = kk - 1; k >= 0; k--) {
+            double t = gam[k];
+            for (int i = kk - 1; i > k; i--) t = t - Hm(k, i) * cvec[i];
+            cvec[k] = t / Hm(k, k);
+        }
+        for (int i0 = 0; i0 < kk; i0 += GM_NV) {
+            const int nv = (kk - i0) < GM_NV ? (kk - i0) : GM_NV;
+            GmPtrs P;
+            for (int q = 0; q < GM_NV; q++) P.v[q] = Zj(i0 + (q < nv ? q : 0)), P.h[q] = q < nv ? cvec[i0 + q] : 0.0;
+            gm_combine_kernel<<<grid, 256, 0, s>>>(M.x.p, P, nv, n2);
+            NEKB_LAUNCHED();
+        }
+    }
+    M.divex = rnorm, M.div0 = div0;
+    NEKB_CUDA(cudaMemcpyAsync(res, M.x.p, sizeof(double) * (size_t)n2, cudaMemcpyDeviceToDevice, s));
+    if (M.ifvcor) {  // ortho (core/navier1.f:223-257)
+        const double sum = gm_glsc3(res, M.ones.p, M.ones.p, n2);
+        gm_cadd_kernel<<<grid, 256, 0, s>>>(res, -sum / ((double)M.nelgv * 216.0), n2);
+        NEKB_LAUNCHED();
+    }
+    NEKB_CUDA(cudaStreamSynchronize(s));
+    return iter;
+}
+int nekb_set_uzawa_state(double tolps, double param21, double prelax, double tolpdf)
+{
+    return guard([&] {
+        Mesh2 &M = mesh2();
+        M.tolps = tolps, M.param21 = param21, M.prelax = prelax, M.tolpdf = tolpdf;
+    });
+}
+int nekb_uzawa_gmres_dev(double *res, const double *h1, const double *h2, const double *h2inv, int intype, int *iter, double *div0,
+                         double *divex)
+{
+    return guard([&] {
+        require_init();
+        const int it = uzawa_gmres_dev(res, h1, h2, h2inv, intype);
+        if (iter) *iter = it;
+        if (div0) *div0 = mesh2().div0;
+        if (divex) *divex = mesh2().divex;
+    });
+}
+void uzawa_gmres_(double *res, const double *h1, const double *h2, const double *h2inv, const int *intype, int *iter)
+{
+    guard_fortran("uzawa_gmres", [&] {
+        require_init();
+        Ctx &c = ctx();
+        const size_t n = (size_t)c.nelv * c.nxyz, n2 = (size_t)c.nelv * 216;
+        for (int k = 0; k < 4; k++) c.stage[k].ensure(n);
+        NEKB_CUDA(cudaMemcpyAsync(c.stage[0].p, res, n2 * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        const double *src[3] = {h1, h2, h2inv};
+        for (int k = 0; k < 3; k++) NEKB_CUDA(cudaMemcpyAsync(c.stage[k + 1].p, src[k], n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        *iter = uzawa_gmres_dev(c.stage[0].p, c.stage[1].p, c.stage[2].p, c.stage[3].p, *intype);
+        NEKB_CUDA(cudaMemcpyAsync(res, c.stage[0].p, n2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
 int nekb_set_mesh2(int lx2, const double *ixm12, const double *dxm12, const double *w3m2, const double *const *metrics9, const double *bm2,
                    const double *bm2inv, double volvm2, double tolhs, int nmxv, int64_t nelgv, int ifvcor)
 {

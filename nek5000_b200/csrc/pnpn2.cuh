@@ -23,6 +23,11 @@ struct Mesh2 {
     int nmxv = 1000;
     int64_t nelgv = 0;
     bool ifvcor = false;
+    double tolps = 1e-8, param21 = 0.0, prelax = 0.0, tolpdf = 0.0;   // TSTEP tolps, INPUT param(21), TSTEP prelax, tolpdf
+    // uzawa_gmres storage (core/GMRES: v_gmres, z_gmres, ...)
+    std::vector<DevBuf<double>> V, Z;
+    DevBuf<double> r, w, x, ones, scal, t1;
+    double div0 = 0.0, divex = 0.0;
 };
 inline Mesh2 &mesh2()
 {
@@ -165,6 +170,19 @@ __global__ void __launch_bounds__(256)
 }
 
 // out_i = inp_i / dssum(bm1 / h2inv)  after  inp_i <- dssum(mask_i inp_i)   (opbinv; inp is modified as in the reference)
+__global__ void __launch_bounds__(256)
+    uz_split_kernel(double *__restrict__ ml, double *__restrict__ mu, const double *__restrict__ b, const double *__restrict__ binv, int64_t n)
+{   // core/gmres.f:240-252 uzawa_gmres_split0
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+        ml[t] = sqrt(binv[t]), mu[t] = sqrt(b[t]);
+}
+// a = m * (b - c)  (c == nullptr: a = m * b)
+__global__ void __launch_bounds__(256)
+    uz_resid_kernel(double *__restrict__ a, const double *__restrict__ m, const double *__restrict__ b, const double *__restrict__ c, int64_t n)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+        a[t] = m[t] * (c ? b[t] - c[t] : b[t]);
+}
 __global__ void __launch_bounds__(256) invcol3_kernel(double *__restrict__ o, const double *__restrict__ a, const double *__restrict__ b, int64_t n)
 {
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) o[t] = a[t] / b[t];

@@ -368,6 +368,17 @@ def cdabdtp(ap, wp, h1, h2, h2inv, intype: int) -> None:
     lib().cdabdtp_(_ptr(ap), _ptr(wp), _ptr(h1), _ptr(h2), _ptr(h2inv), _i(intype))
 
 
+def set_uzawa_state(tolps: float, param21: float = 0.0, prelax: float = 0.0, tolpdf: float = 0.0) -> None:
+    check(lib().nekb_set_uzawa_state(tolps, param21, prelax, tolpdf))
+
+
+def uzawa_gmres(res, h1, h2, h2inv, intype: int) -> int:
+    """core/gmres.f:2 uzawa_gmres(res,h1,h2,h2inv,intype,iter); res is overwritten; returns iter."""
+    it = C.c_int(0)
+    lib().uzawa_gmres_(_ptr(res), _ptr(h1), _ptr(h2), _ptr(h2inv), _i(intype), C.byref(it))
+    return int(it.value)
+
+
 def set_param(idx: int, value: float) -> None:
     check(lib().nekb_set_param(idx, float(value)))
 

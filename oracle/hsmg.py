@@ -877,7 +877,8 @@ def fast1d_sem(lbc, rbc, ll, lm, lr, bh, jgl, dgl):
 def gen_fast(case, fbc):
     """core/fast3d.f:2-140 gen_fast with param(44) = 0 (the default: top-level Schwarz on restrictions of E): the
     common /fastd/ data of the Pn-Pn-2 preconditioner.  Returns S[e,3,lx1,lx1], D[e,lx1,lx1,lx1] (D = df)."""
-    mg = H1MG(case, fbc)                      # swap_lengths: ll, lm, lr
+    fbc = np.asarray(fbc).reshape(case.nel, 6)
+    mg = H1MG(case, np.where(fbc == 3, 2, fbc))   # swap_lengths: ll, lm, lr (symmetry faces count as walls there)
     nl = case.nx
     bh, jgl, dgl = semhat_weighted(nl - 1)
     E = case.nel
@@ -886,7 +887,7 @@ def gen_fast(case, fbc):
     for e in range(E):
         lam = []
         for d in range(3):
-            key = (int(mg.fbc[e, 2 * d]), int(mg.fbc[e, 2 * d + 1]), mg.ll[d, e], mg.lm[d, e], mg.lr[d, e])
+            key = (int(fbc[e, 2 * d]), int(fbc[e, 2 * d + 1]), mg.ll[d, e], mg.lm[d, e], mg.lr[d, e])
             if key not in cache:
                 cache[key] = fast1d_sem(*key, bh, jgl, dgl)
             S[e, d], l1 = cache[key]

@@ -68,3 +68,91 @@ class Mesh2:
         """intype = 1."""
         tb, _ = self.opbinv(self.opgradt(wp), h2inv, masks)
         return self.opdiv(tb)
+
+
+def chktcg2(M, tol, res, ifvcor=False, prelax=0.0, tolpdf=0.0):
+    """core/navier1.f:1089-1154."""
+    eps = prelax if prelax != 0.0 else 1.0e-10
+    ta = res * M.bm2inv
+    rinit = np.sqrt(np.sum(ta * ta * M.bm2) / M.volvm2)
+    if rinit < tol:
+        return tol
+    rmin = tolpdf if tolpdf > 0.0 else eps * rinit
+    if tol < rmin:
+        tol = rmin
+    if ifvcor:
+        tolmin = abs(np.sum(res)) * 100.0
+        if tol < tolmin:
+            tol = tolmin
+    return tol
+
+
+def uzawa_gmres(M, precond, res, h2inv, masks, tolps, param21=0.0, istep=1, m=30, ifvcor=False, ntotg=None):
+    """core/gmres.f:2-237 with intype = 1; precond(w) = hsmg_solve.  Returns (x, iter)."""
+    n2 = len(res)
+    ml, mu = np.sqrt(M.bm2inv), np.sqrt(M.bm2)
+    norm_fac = 1.0 / np.sqrt(M.volvm2)
+    tolps = chktcg2(M, tolps, res, ifvcor)
+    if param21 > 0 and tolps > abs(param21):
+        tolps = abs(param21)
+    if istep == 0:
+        tolps = 1.0e-4
+    tolpss = tolps
+    E = lambda p: M.cdabdtp(p, h2inv, masks)
+    x = np.zeros(n2)
+    V, Z = np.zeros((m + 1, n2)), np.zeros((m, n2))
+    H = np.zeros((m + 1, m))
+    cg, sg, gam = np.zeros(m), np.zeros(m), np.zeros(m + 1)
+    it, conv = 0, False
+    while not conv and it < 100:
+        r = ml * res if it == 0 else ml * (res - E(x))
+        gam[0] = np.sqrt(np.sum(r * r))
+        if it == 0:
+            div0 = gam[0] * norm_fac
+            if param21 < 0:
+                tolpss = abs(param21) * div0
+        if gam[0] == 0.0:
+            break
+        V[0] = r / gam[0]
+        j = 0
+        for j in range(m):
+            it += 1
+            Z[j] = precond(mu * V[j])
+            w = ml * E(Z[j])
+            for i in range(j + 1):
+                H[i, j] = np.sum(w * V[i])
+            for i in range(j + 1):
+                w = w - H[i, j] * V[i]
+            for i in range(j):
+                t = H[i, j]
+                H[i, j] = cg[i] * t + sg[i] * H[i + 1, j]
+                H[i + 1, j] = -sg[i] * t + cg[i] * H[i + 1, j]
+            alpha = np.sqrt(np.sum(w * w))
+            if alpha == 0.0:
+                conv = True
+                break
+            l = np.sqrt(H[j, j] * H[j, j] + alpha * alpha)
+            t = 1.0 / l
+            cg[j], sg[j] = H[j, j] * t, alpha * t
+            H[j, j] = l
+            gam[j + 1] = -sg[j] * gam[j]
+            gam[j] = cg[j] * gam[j]
+            rnorm = abs(gam[j + 1]) * norm_fac
+            if rnorm < tolpss:
+                conv = True
+                break
+            if j == m - 1:
+                break
+            V[j + 1] = w / alpha
+        k = j + 1
+        cvec = np.zeros(k)
+        for q in range(k - 1, -1, -1):
+            t = gam[q]
+            for i in range(k - 1, q, -1):
+                t = t - H[q, i] * cvec[i]
+            cvec[q] = t / H[q, q]
+        for i in range(k):
+            x = x + cvec[i] * Z[i]
+    if ifvcor:
+        x = x - np.sum(x) / ntotg
+    return x, it

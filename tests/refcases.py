@@ -35,9 +35,10 @@ def case_of(name, nx=8):
     return oracle.Case(*dims, nx=nx, dirichlet=dirich, deform=deform)
 
 
-def fbc_of(name, case):
-    """get_fast_bc codes (core/fast3d.f:802-877) on the box sides: 'v  ' -> 2 (Neumann for p), 'O  ' -> 1 (Dirichlet)."""
-    return hsmg.box_fbc(case, tuple(2 if d else 1 for d in MESH[name][1]))
+def fbc_of(name, case, bsym=2):
+    """get_fast_bc codes (core/fast3d.f:802-877) on the box sides: 'v  ' -> 2 (Neumann for p), 'O  ' -> 1 (Dirichlet),
+    'SYM' -> bsym (2 for the multigrid levels, hsmg.f:725; 3 for gen_fast, fast3d.f:38)."""
+    return hsmg.box_fbc(case, tuple({0: 1, 1: 2, 2: bsym}[int(d)] for d in MESH[name][1]))
 
 
 def _ref(case, **kw):
@@ -332,6 +333,35 @@ def ref_eop():
     return out
 
 
+def ref_uzawa():
+    """core/gmres.f:2-237 uzawa_gmres: GMRES on E = cdabdtp(intype = 1) preconditioned by hsmg_solve (core/hsmg.f:1376-1602,
+    set up by set_overlap -> gen_fast, hsmg_setup), tolerance through chktcg2 (core/navier1.f:1089-1154)."""
+    case = case_of("eop")
+    rc = _ref(case, lx2=6, ifsplit=False)
+    R, E, n = rc.R, case.nel, case.n
+    n2 = 216 * E
+    R.set("ifmgrid", 1)
+    R.var("param")[[39, 40, 41, 42, 43]] = 0.0
+    R.call("set_overlap")
+    rng = np.random.default_rng(41)
+    h2inv = 1.0 / (50.0 + rng.random(n))
+    h1, h2 = np.ones(n), 1.0 / h2inv
+    pe = rng.standard_normal(n2)
+    res = np.zeros(n2)
+    R.call("cdabdtp", res, pe, h1, h2, h2inv, 1)
+    out = dict(h2inv=h2inv, pe=pe, rhs=res.copy(), df=R.var("df")[:, :E].T.copy(), prelax=np.array([R.get("prelax")]),
+               tolpdf=np.array([R.get("tolpdf")]))
+    for nm in ("sr", "ss", "st"):
+        out[nm] = R.var(nm)[:, :E].T.copy()
+    R.var("param")[20] = 0.0
+    R.set("tolps", 1e-7), R.set("istep", 5)
+    it = C.c_int(0)
+    x = res.copy()
+    R.call("uzawa_gmres", x, h1, h2, h2inv, 1, it)
+    out.update(x=x, it=np.array([it.value]))
+    return out
+
+
 MAP_NP = (1, 2, 3, 4, 5, 7, 8, 16, 48)
 
 
@@ -349,7 +379,7 @@ def ref_map():
     return out
 
 
-REFERENCE = dict(core=ref_core, core_lx6=ref_core_lx6, map=ref_map, eop=ref_eop, hsolve=ref_hsolve, hsolve_pres=ref_hsolve_pres, ophinv=ref_ophinv, bp5=ref_bp5, h1mg=ref_h1mg, h1mg_neumann=ref_h1mg_neumann, fdm=ref_fdm, pnpn2=ref_pnpn2)
+REFERENCE = dict(core=ref_core, core_lx6=ref_core_lx6, map=ref_map, eop=ref_eop, uzawa=ref_uzawa, hsolve=ref_hsolve, hsolve_pres=ref_hsolve_pres, ophinv=ref_ophinv, bp5=ref_bp5, h1mg=ref_h1mg, h1mg_neumann=ref_h1mg_neumann, fdm=ref_fdm, pnpn2=ref_pnpn2)
 
 
 def reference_all():

@@ -244,3 +244,20 @@ def test_pnpn2_pressure_operator_pieces():
     for k in range(3):
         assert np.array_equal(bi[k], g[f"bi{k + 1}"]) and relmax(bo[k], g[f"bo{k + 1}"]) <= 1e-14
     assert relmax(M.cdabdtp(g["p"], g["h2inv"], masks), g["ap"]) <= 1e-12
+
+
+def test_uzawa_gmres_on_the_pnpn2_pressure_operator():
+    """core/gmres.f:2-237: GMRES on E preconditioned by hsmg_solve; identical iteration count, solution to 1e-9."""
+    from oracle import pnpn2
+    g, c = G["uzawa"], refcases.case_of("eop")
+    M = _mesh2(G["eop"], c)
+    masks = [G["eop"][k] for k in ("v1mask", "v2mask", "v3mask")]
+    assert relmax(M.cdabdtp(g["pe"], g["h2inv"], masks), g["rhs"]) <= 1e-12
+    fbc = refcases.fbc_of("eop", c)                                 # multigrid levels: SYM counts as a wall (bsym = 2)
+    S, D = refcases.fastd_to_S(g, c.nel)
+    Sg, Dg = hsmg.gen_fast(c, refcases.fbc_of("eop", c, bsym=3))    # gen_fast: SYM has its own code (bsym = 3)
+    assert relmax(Dg, D) <= 1e-12 and np.abs(np.abs(Sg) - np.abs(S)).max() <= 1e-10   # deformed mesh, wall/SYM/outflow
+    h = hsmg.Hsmg2(c, fbc, S, D)
+    x, it = pnpn2.uzawa_gmres(M, lambda w: h.solve(w), g["rhs"], g["h2inv"], masks, 1e-7, 0.0, istep=5)
+    assert it == g["it"][0]
+    assert relmax(x, g["x"]) <= 1e-9 and relmax(x, g["pe"]) <= 1e-6
