@@ -160,6 +160,10 @@ def lib() -> C.CDLL:
     L.uzawa_gmres_.argtypes = [vp] * 4 + [ip, ip]
     L.uzawa_gmres_.restype = None
     L.nekb_set_uzawa_state.argtypes = [C.c_double] * 4
+    L.nekb_opgradt_dev.argtypes = [vp] * 4
+    L.nekb_opdiv_dev.argtypes = [vp] * 4
+    L.nekb_cdabdtp_dev.argtypes = [vp] * 5 + [C.c_int]
+    L.nekb_uzawa_gmres_dev.argtypes = [vp] * 4 + [C.c_int, ip, dp, dp]
     L.nekb_set_projection.argtypes = [C.c_int, C.c_int, C.c_int]
     L.nekb_hsolve_dev.argtypes = [C.c_char_p] + [vp] * 6 + [C.c_int, C.c_double, C.c_int, vp, vp, ip]
     L.nekb_set_param.argtypes = [C.c_int, C.c_double]

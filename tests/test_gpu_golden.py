@@ -443,8 +443,6 @@ def test_uzawa_gmres_against_the_reference(nek):
     _register_eop(nek, ge, case)
     E, n, n2 = case.nel, case.n, 216 * case.nel
     nek.hsmg_setup(refcases.fbc_of("eop", case, bsym=3), case.xm1, case.ym1, case.zm1, case.vertex, E, False, E)
-    S, D = refcases.fastd_to_S(g, E)
-    assert relmax(nek.hsmg_get("df", 3, 512 * E), D.reshape(-1)) <= 1e-10 if _has_df(nek) else True
     nek.set_uzawa_state(1e-7, 0.0, float(g["prelax"][0]), float(g["tolpdf"][0]))
     nek.set_step_info(5, float(ge["volvm1"][0]))
     h1, h2 = np.ones(n), 1.0 / g["h2inv"]
@@ -456,10 +454,3 @@ def test_uzawa_gmres_against_the_reference(nek):
     assert it == g["it"][0]
     assert relmax(x, g["x"]) <= 1e-8 and relmax(x, g["pe"]) <= 1e-6
 
-
-def _has_df(nek):
-    try:
-        nek.hsmg_get("df", 3, 1)
-        return True
-    except Exception:
-        return False
