@@ -1492,6 +1492,9 @@ int nekb_set_mesh2(int lx2, const double *ixm12, const double *dxm12, const doub
         for (int a = 0; a < lx2; a++)
             for (int i = 0; i < lx1; i++) I[(size_t)a * lx1 + i] = ixm12[a + lx2 * i], D[(size_t)a * lx1 + i] = dxm12[a + lx2 * i];
         M.i12.upload(I.data(), I.size(), c.stream), M.d12.upload(D.data(), D.size(), c.stream);
+        NEKB_REQUIRE(lx2 == 6 && lx1 == 8, "set_mesh2: the Pn-Pn-2 kernels are built for lx1 = 8, lx2 = 6");
+        NEKB_CUDA(cudaMemcpyToSymbolAsync(c_I12, I.data(), 48 * sizeof(double), 0, cudaMemcpyHostToDevice, c.stream));
+        NEKB_CUDA(cudaMemcpyToSymbolAsync(c_D12, D.data(), 48 * sizeof(double), 0, cudaMemcpyHostToDevice, c.stream));
         const size_t p2 = (size_t)lx2 * lx2 * lx2, n2 = p2 * c.nelv;
         M.w3.upload(w3m2, p2, c.stream);
         for (int k = 0; k < 9; k++) M.met[k].upload(metrics9[k], n2, c.stream);

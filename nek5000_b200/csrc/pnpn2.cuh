@@ -3,7 +3,7 @@
 //   opdiv   -> multd  core/navier1.f:4064-4093, :538-714   D   : velocity -> pressure mesh
 //   opbinv            core/navier1.f:775-850               (h2 B)^-1 with mask + dssum
 //   cdabdtp           core/navier1.f:258-293               intype = 1: D (B/dt)^-1 D^T ; 0 / -1: D (h1 A + h2 B)^-1 D^T via ophinv
-// 3-D, non-axisymmetric, ifsplit = .false. branch.  One CTA per element: the (lx2)^3 <-> (lx1)^3 tensor contractions with the
+// 3-D, non-axisymmetric, ifsplit = .false. branch.  One WARP per element: the (lx2)^3 <-> (lx1)^3 tensor contractions with the
 // 6x8 interpolation / derivative matrices ixm12, dxm12 run through shared memory; the nine mesh-2 metric arrays (rxm2 ...
 // tzm2) are streamed once per element (opgradt: 10 x 216 words in, 3 x 512 out; opdiv: 3 x 512 + 10 x 216 in, 216 out).
 #pragma once
@@ -38,134 +38,247 @@ struct Met9 {
     const double *p[9];
 };
 
-// One term of cdtp: out(i,j,k) = sum_{a,b,c} Ax(a,i) Ay(b,j) Az(c,k) f(a,b,c), f on the N2^3 grid; mxm order x, y, z
-template <int N1, int N2>
-__device__ __forceinline__ void up_term(const double *f, double *t1, double *t2, const double *Ax, const double *Ay, const double *Az,
-                                        double *term, int nthreads)
+// Warp-per-element kernels.  A warp owns one element at a time (8 warps per CTA); every lane owns whole LINES of a tensor
+// contraction: it loads the 6 (or 8) inputs of a line once and produces its 8 (or 6) outputs with the interpolation /
+// derivative matrices read from the constant bank as immediate FMA operands (fully unrolled), so a line costs 6 + 8 shared-
+// memory accesses for 48 FMAs instead of 96.  Stages of a contraction are separated by __syncwarp only.
+constexpr int PN_WARPS = 8;
+__constant__ double c_I12[48], c_D12[48];   // [a*8 + i] = ixm12(a,i), dxm12(a,i)  (lx2 = 6, lx1 = 8)
+
+template <bool DER>
+__device__ __forceinline__ double m12(int a, int i)
 {
-    for (int o = threadIdx.x; o < N1 * N2 * N2; o += nthreads) {  // t1[c][b][i]
-        const int i = o % N1, cb = o / N1;
+    return DER ? c_D12[a * 8 + i] : c_I12[a * 8 + i];
+}
+// 6 -> 8 along one line: out[i] = sum_a A(a,i) in[a]
+template <bool DER>
+__device__ __forceinline__ void line_up(const double (&in)[6], double (&out)[8])
+{
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
         double s = 0.0;
 #pragma unroll
-        for (int a = 0; a < N2; a++) s = fma(Ax[a * N1 + i], f[cb * N2 + a], s);
-        t1[o] = s;
+        for (int a = 0; a < 6; a++) s = fma(m12<DER>(a, i), in[a], s);
+        out[i] = s;
     }
-    __syncthreads();
-    for (int o = threadIdx.x; o < N1 * N1 * N2; o += nthreads) {  // t2[c][j][i]
-        const int i = o % N1, j = (o / N1) % N1, c = o / (N1 * N1);
+}
+// 8 -> 6 along one line: out[a] = sum_i A(a,i) in[i]
+template <bool DER>
+__device__ __forceinline__ void line_down(const double (&in)[8], double (&out)[6])
+{
+#pragma unroll
+    for (int a = 0; a < 6; a++) {
         double s = 0.0;
 #pragma unroll
-        for (int b = 0; b < N2; b++) s = fma(t1[(c * N2 + b) * N1 + i], Ay[b * N1 + j], s);
-        t2[o] = s;
+        for (int i = 0; i < 8; i++) s = fma(m12<DER>(a, i), in[i], s);
+        out[a] = s;
     }
-    __syncthreads();
-    int slot = 0;
-    for (int o = threadIdx.x; o < N1 * N1 * N1; o += nthreads, slot++) {
-        const int ij = o % (N1 * N1), k = o / (N1 * N1);
-        double s = 0.0;
+}
+
+constexpr int FP = 7;   // pitch of the 6-wide rows of f (bank-conflict-free line loads)
+constexpr int UP = 9;   // pitch of the 8-wide rows of u
+
+// One term of cdtp (mxm order x, y, z): term(i,j,k) = sum_abc Ax(a,i) Ay(b,j) Az(c,k) f(a,b,c); Q = direction of the derivative.
+// f[cb*FP + a]; t1[(c*6+b)*8 + i]; t2[(c*8+j)*8 + i]; term slot 8*l2 + k <-> node (ij = lane + 32 l2, k)
+template <int Q>
+__device__ __forceinline__ void up_term(const double *f, double *t1, double *t2, double (&term)[16], int lane)
+{
+    for (int cb = lane; cb < 36; cb += 32) {
+        double in[6], out[8];
 #pragma unroll
-        for (int c = 0; c < N2; c++) s = fma(t2[c * N1 * N1 + ij], Az[c * N1 + k], s);
-        term[slot] = s;
+        for (int a = 0; a < 6; a++) in[a] = f[cb * FP + a];
+        line_up<Q == 0>(in, out);
+#pragma unroll
+        for (int i = 0; i < 8; i++) t1[cb * 8 + i] = out[i];
     }
-    __syncthreads();
+    __syncwarp();
+    for (int ci = lane; ci < 48; ci += 32) {
+        const int i = ci % 8, c = ci / 8;
+        double in[6], out[8];
+#pragma unroll
+        for (int b = 0; b < 6; b++) in[b] = t1[(c * 6 + b) * 8 + i];
+        line_up<Q == 1>(in, out);
+#pragma unroll
+        for (int j = 0; j < 8; j++) t2[(c * 8 + j) * 8 + i] = out[j];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int l2 = 0; l2 < 2; l2++) {
+        const int ij = lane + 32 * l2;
+        double in[6], out[8];
+#pragma unroll
+        for (int c = 0; c < 6; c++) in[c] = t2[c * 64 + ij];
+        line_up<Q == 2>(in, out);
+#pragma unroll
+        for (int k = 0; k < 8; k++) term[8 * l2 + k] = out[k];
+    }
+    __syncwarp();
 }
 
 // opgradt: out_isd = sum_q T_q( w3m2 * p * q_isd,m2 ),  T_r = I^T (x) I^T (x) D^T etc.
-template <int N1, int N2>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * PN_WARPS, 1)
     opgradt_kernel(double *__restrict__ ox, double *__restrict__ oy, double *__restrict__ oz, const double *__restrict__ p, Met9 M,
-                   const double *__restrict__ w3, const double *__restrict__ i12, const double *__restrict__ d12, int nel)
+                   const double *__restrict__ w3, int nel)
 {
-    constexpr int P2 = N2 * N2 * N2, P1 = N1 * N1 * N1, SL = (P1 + 255) / 256;
-    __shared__ double sI[N2 * N1], sD[N2 * N1], wx[P2], f[P2], t1[N1 * N2 * N2], t2[N1 * N1 * N2];
-    for (int t = threadIdx.x; t < N2 * N1; t += 256) sI[t] = i12[t], sD[t] = d12[t];
-    for (int e = blockIdx.x; e < nel; e += gridDim.x) {
-        __syncthreads();
-        for (int t = threadIdx.x; t < P2; t += 256) wx[t] = w3[t] * p[(size_t)e * P2 + t];   // col3(wx,w3m2,x)
-        __syncthreads();
-        double *outs[3] = {ox, oy, oz};
+    constexpr int P2 = 216, P1 = 512, PER = P2 + 36 * FP + 288 + 384;
+    extern __shared__ double sm_up[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *wx = sm_up + warp * PER, *f = wx + P2, *t1 = f + 36 * FP, *t2 = t1 + 288;
+    double *outs[3] = {ox, oy, oz};
+    for (int e = blockIdx.x * PN_WARPS + warp; e < nel; e += gridDim.x * PN_WARPS) {
+        __syncwarp();
+        for (int t = lane; t < P2; t += 32) wx[t] = w3[t] * p[(size_t)e * P2 + t];   // col3(wx,w3m2,x)
+        // the metric tile of the NEXT (isd, q) term is fetched into registers while the current term is contracted
+        double mreg[7];
+#pragma unroll
+        for (int s7 = 0; s7 < 7; s7++) {
+            const int t = lane + 32 * s7;
+            mreg[s7] = t < P2 ? M.p[0][(size_t)e * P2 + t] : 0.0;
+        }
+        __syncwarp();
 #pragma unroll 1
         for (int isd = 0; isd < 3; isd++) {
-            double acc[SL], term[SL];
-#pragma unroll 1
-            for (int q = 0; q < 3; q++) {
-                const double *mq = M.p[isd * 3 + q] + (size_t)e * P2;
-                for (int t = threadIdx.x; t < P2; t += 256) f[t] = wx[t] * mq[t];
-                __syncthreads();
-                up_term<N1, N2>(f, t1, t2, q == 0 ? sD : sI, q == 1 ? sD : sI, q == 2 ? sD : sI, term, 256);
+            double acc[16], term[16];
 #pragma unroll
-                for (int sl = 0; sl < SL; sl++) acc[sl] = q == 0 ? term[sl] : acc[sl] + term[sl];   // add2
+            for (int q = 0; q < 3; q++) {
+#pragma unroll
+                for (int s7 = 0; s7 < 7; s7++) {
+                    const int t = lane + 32 * s7;
+                    if (t < P2) f[(t / 6) * FP + t % 6] = wx[t] * mreg[s7];
+                }
+                const int nxt = isd * 3 + q + 1;
+                if (nxt < 9) {
+                    const double *mq = M.p[nxt] + (size_t)e * P2;
+#pragma unroll
+                    for (int s7 = 0; s7 < 7; s7++) {
+                        const int t = lane + 32 * s7;
+                        mreg[s7] = t < P2 ? mq[t] : 0.0;
+                    }
+                }
+                __syncwarp();
+                if (q == 0) up_term<0>(f, t1, t2, term, lane);
+                if (q == 1) up_term<1>(f, t1, t2, term, lane);
+                if (q == 2) up_term<2>(f, t1, t2, term, lane);
+#pragma unroll
+                for (int sl = 0; sl < 16; sl++) acc[sl] = q == 0 ? term[sl] : acc[sl] + term[sl];   // add2
             }
-            int sl = 0;
-            for (int o = threadIdx.x; o < P1; o += 256, sl++) outs[isd][(size_t)e * P1 + o] = acc[sl];
+            double *o = outs[isd] + (size_t)e * P1;
+#pragma unroll
+            for (int l2 = 0; l2 < 2; l2++)
+#pragma unroll
+                for (int k = 0; k < 8; k++) o[k * 64 + lane + 32 * l2] = acc[8 * l2 + k];
         }
     }
 }
 
-// One term of multd: v(a,b,c) = sum_{i,j,k} Ax(a,i) Ay(b,j) Az(c,k) u(i,j,k)
-template <int N1, int N2>
-__device__ __forceinline__ double down_term(const double *u, double *t1, double *t2, const double *Ax, const double *Ay, const double *Az,
-                                            int nthreads)
+// One term of multd: v(a,b,c) = sum_ijk Ax(a,i) Ay(b,j) Az(c,k) u(i,j,k).  u[jk*UP + i]; t1[(k*8+j)*6 + a]; t2[(k*6+b)*6 + a];
+// v slot 6*l2 + c <-> node (ab = lane + 32 l2 < 36, c)
+template <int Q>
+__device__ __forceinline__ void down_term(const double *u, double *t1, double *t2, double (&v)[12], int lane)
 {
-    for (int o = threadIdx.x; o < N2 * N1 * N1; o += nthreads) {  // t1[k][j][a]
-        const int a = o % N2, jk = o / N2;
-        double s = 0.0;
 #pragma unroll
-        for (int i = 0; i < N1; i++) s = fma(Ax[a * N1 + i], u[jk * N1 + i], s);
-        t1[o] = s;
-    }
-    __syncthreads();
-    for (int o = threadIdx.x; o < N2 * N2 * N1; o += nthreads) {  // t2[k][b][a]
-        const int a = o % N2, b = (o / N2) % N2, k = o / (N2 * N2);
-        double s = 0.0;
+    for (int l2 = 0; l2 < 2; l2++) {
+        const int jk = lane + 32 * l2;
+        double in[8], out[6];
 #pragma unroll
-        for (int j = 0; j < N1; j++) s = fma(t1[(k * N1 + j) * N2 + a], Ay[b * N1 + j], s);
-        t2[o] = s;
-    }
-    __syncthreads();
-    double v = 0.0;
-    if (threadIdx.x < N2 * N2 * N2) {
-        const int ab = threadIdx.x % (N2 * N2), c = threadIdx.x / (N2 * N2);
+        for (int i = 0; i < 8; i++) in[i] = u[jk * UP + i];
+        line_down<Q == 0>(in, out);
 #pragma unroll
-        for (int k = 0; k < N1; k++) v = fma(t2[k * N2 * N2 + ab], Az[c * N1 + k], v);
+        for (int a = 0; a < 6; a++) t1[jk * 6 + a] = out[a];
     }
-    __syncthreads();
-    return v;
+    __syncwarp();
+    for (int ka = lane; ka < 48; ka += 32) {
+        const int a = ka % 6, k = ka / 6;
+        double in[8], out[6];
+#pragma unroll
+        for (int j = 0; j < 8; j++) in[j] = t1[(k * 8 + j) * 6 + a];
+        line_down<Q == 1>(in, out);
+#pragma unroll
+        for (int b = 0; b < 6; b++) t2[(k * 6 + b) * 6 + a] = out[b];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int l2 = 0; l2 < 2; l2++) {
+        const int ab = lane + 32 * l2;
+        double in[8], out[6];
+        if (ab < 36) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) in[k] = t2[k * 36 + ab];
+            line_down<Q == 2>(in, out);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 6; c++) out[c] = 0.0;
+        }
+#pragma unroll
+        for (int c = 0; c < 6; c++) v[6 * l2 + c] = out[c];
+    }
+    __syncwarp();
 }
 
 // opdiv: out = sum_isd w3m2 * sum_q q_isd,m2 * T_q^T( u_isd )
-template <int N1, int N2>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * PN_WARPS, 1)
     opdiv_kernel(double *__restrict__ out, const double *__restrict__ ux, const double *__restrict__ uy, const double *__restrict__ uz, Met9 M,
-                 const double *__restrict__ w3, const double *__restrict__ i12, const double *__restrict__ d12, int nel)
+                 const double *__restrict__ w3, int nel)
 {
-    constexpr int P2 = N2 * N2 * N2, P1 = N1 * N1 * N1;
-    static_assert(P2 <= 256, "one pressure node per thread");
-    __shared__ double sI[N2 * N1], sD[N2 * N1], u[P1], t1[N2 * N1 * N1], t2[N2 * N2 * N1];
-    for (int t = threadIdx.x; t < N2 * N1; t += 256) sI[t] = i12[t], sD[t] = d12[t];
-    for (int e = blockIdx.x; e < nel; e += gridDim.x) {
-        const double *us[3] = {ux, uy, uz};
-        double tot = 0.0;
+    constexpr int P2 = 216, P1 = 512, PER = 64 * UP + 384 + 288;
+    extern __shared__ double sm_dn[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *u = sm_dn + warp * PER, *t1 = u + 64 * UP, *t2 = t1 + 384;
+    const double *us[3] = {ux, uy, uz};
+    for (int e = blockIdx.x * PN_WARPS + warp; e < nel; e += gridDim.x * PN_WARPS) {
+        double tot[12], ureg[16];
+#pragma unroll
+        for (int s = 0; s < 16; s++) ureg[s] = us[0][(size_t)e * P1 + lane + 32 * s];
 #pragma unroll 1
         for (int isd = 0; isd < 3; isd++) {
-            __syncthreads();
-            for (int t = threadIdx.x; t < P1; t += 256) u[t] = us[isd][(size_t)e * P1 + t];
-            __syncthreads();
-            double dx = 0.0;
-#pragma unroll 1
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < 16; s++) {
+                const int t = lane + 32 * s;
+                u[(t / 8) * UP + t % 8] = ureg[s];
+            }
+            if (isd < 2) {  // the next component streams in while this one is contracted
+#pragma unroll
+                for (int s = 0; s < 16; s++) ureg[s] = us[isd + 1][(size_t)e * P1 + lane + 32 * s];
+            }
+            double mreg[3][12];  // the three metric tiles of this component
+#pragma unroll
             for (int q = 0; q < 3; q++) {
-                const double v = down_term<N1, N2>(u, t1, t2, q == 0 ? sD : sI, q == 1 ? sD : sI, q == 2 ? sD : sI, 256);
-                if (threadIdx.x < P2) {
-                    const double mq = M.p[isd * 3 + q][(size_t)e * P2 + threadIdx.x];
-                    dx = q == 0 ? v * mq : dx + v * mq;                                    // col2 / addcol3
+                const double *mq = M.p[isd * 3 + q] + (size_t)e * P2;
+#pragma unroll
+                for (int l2 = 0; l2 < 2; l2++)
+#pragma unroll
+                    for (int c = 0; c < 6; c++) {
+                        const int ab = lane + 32 * l2;
+                        mreg[q][6 * l2 + c] = ab < 36 ? mq[c * 36 + ab] : 0.0;
+                    }
+            }
+            __syncwarp();
+            double dx[12], v[12];
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                if (q == 0) down_term<0>(u, t1, t2, v, lane);
+                if (q == 1) down_term<1>(u, t1, t2, v, lane);
+                if (q == 2) down_term<2>(u, t1, t2, v, lane);
+#pragma unroll
+                for (int sl = 0; sl < 12; sl++) dx[sl] = q == 0 ? v[sl] * mreg[q][sl] : dx[sl] + v[sl] * mreg[q][sl];   // col2 / addcol3
+            }
+#pragma unroll
+            for (int l2 = 0; l2 < 2; l2++)
+#pragma unroll
+                for (int c = 0; c < 6; c++) {
+                    const int ab = lane + 32 * l2;
+                    const double d = dx[6 * l2 + c] * (ab < 36 ? w3[c * 36 + ab] : 0.0);                    // col2(dx,w3m2)
+                    tot[6 * l2 + c] = isd == 0 ? d : tot[6 * l2 + c] + d;                                 // copy / add2
                 }
-            }
-            if (threadIdx.x < P2) {
-                dx = dx * w3[threadIdx.x];                                                 // col2(dx,w3m2)
-                tot = isd == 0 ? dx : tot + dx;                                            // copy / add2
-            }
         }
-        if (threadIdx.x < P2) out[(size_t)e * P2 + threadIdx.x] = tot;
+#pragma unroll
+        for (int l2 = 0; l2 < 2; l2++)
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                const int ab = lane + 32 * l2;
+                if (ab < 36) out[(size_t)e * P2 + c * 36 + ab] = tot[6 * l2 + c];
+            }
     }
 }
 
@@ -216,7 +329,14 @@ inline void opgradt_dev(double *ox, double *oy, double *oz, const double *p)
     Ctx &c = ctx();
     require_mesh2();
     if (c.nelv <= 0) return;
-    opgradt_kernel<8, 6><<<grid_for(c.nelv, 4), 256, 0, c.stream>>>(ox, oy, oz, p, met9(), mesh2().w3.p, mesh2().i12.p, mesh2().d12.p, c.nelv);
+    constexpr size_t smem = (size_t)PN_WARPS * (216 + 36 * FP + 288 + 384) * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        NEKB_CUDA(cudaFuncSetAttribute(opgradt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    opgradt_kernel<<<grid_for((c.nelv + PN_WARPS - 1) / PN_WARPS, 2), 32 * PN_WARPS, smem, c.stream>>>(ox, oy, oz, p, met9(), mesh2().w3.p,
+                                                                                                        c.nelv);
     NEKB_LAUNCHED();
 }
 inline void opdiv_dev(double *out, const double *ux, const double *uy, const double *uz)
@@ -224,7 +344,13 @@ inline void opdiv_dev(double *out, const double *ux, const double *uy, const dou
     Ctx &c = ctx();
     require_mesh2();
     if (c.nelv <= 0) return;
-    opdiv_kernel<8, 6><<<grid_for(c.nelv, 4), 256, 0, c.stream>>>(out, ux, uy, uz, met9(), mesh2().w3.p, mesh2().i12.p, mesh2().d12.p, c.nelv);
+    constexpr size_t smem = (size_t)PN_WARPS * (64 * UP + 384 + 288) * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        NEKB_CUDA(cudaFuncSetAttribute(opdiv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    opdiv_kernel<<<grid_for((c.nelv + PN_WARPS - 1) / PN_WARPS, 2), 32 * PN_WARPS, smem, c.stream>>>(out, ux, uy, uz, met9(), mesh2().w3.p, c.nelv);
     NEKB_LAUNCHED();
 }
 inline void opbinv_dev(double *o1, double *o2, double *o3, double *i1, double *i2, double *i3, const double *h2inv, int gs_handle)
