@@ -102,6 +102,13 @@ void dssum_(double *u, const int *nx, const int *ny, const int *nz);
 /* core/dssum.f:100 dsop(u,op,nx,ny,nz), op is character*3: '+  ','sum','*  ','mul','m  ','min','mna',
  * 'M  ','max','mxa' (core/dssum.f:110-158); trailing hidden length as gfortran passes it. */
 void dsop_(double *u, const char *op, const int *nx, const int *ny, const int *nz, size_t op_len);
+/* core/dssum.f:163 vec_dssum(u,v,w,nx,ny,nz), :198 vec_dsop(u,v,w,nx,ny,nz,op), :260 nvec_dssum(u,stride,n,gs_handle);
+ * core/ic.f:1871 dsavg(u) = vmult * dssum(u) (vmult from nekb_set_velocity_state). */
+void vec_dssum_(double *u, double *v, double *w, const int *nx, const int *ny, const int *nz);
+void vec_dsop_(double *u, double *v, double *w, const int *nx, const int *ny, const int *nz, const char *op, size_t op_len);
+void nvec_dssum_(double *u, const int *stride, const int *n, const int *gs_handle);
+void dsavg_(double *u);
+
 /* core/hmholtz.f:72 axhelm(au,u,helm1,helm2,imesh,isd) -- general 3-D branch :191-217,:225. */
 void axhelm_(double *au, const double *u, const double *helm1, const double *helm2, const int *imesh,
              const int *isd);

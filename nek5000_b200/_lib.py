@@ -147,6 +147,14 @@ def lib() -> C.CDLL:
     L.glsc3_.restype = C.c_double
     L.hmholtz_.argtypes = [C.c_char_p, vp, vp, vp, vp, vp, vp, ip, dp, ip, ip, C.c_size_t]
     L.hmholtz_.restype = None
+    L.vec_dssum_.argtypes = [vp, vp, vp, ip, ip, ip]
+    L.vec_dssum_.restype = None
+    L.vec_dsop_.argtypes = [vp, vp, vp, ip, ip, ip, C.c_char_p, C.c_size_t]
+    L.vec_dsop_.restype = None
+    L.nvec_dssum_.argtypes = [vp, ip, ip, ip]
+    L.nvec_dssum_.restype = None
+    L.dsavg_.argtypes = [vp]
+    L.dsavg_.restype = None
     L.ophinv_.argtypes = [vp] * 8 + [dp, ip]
     L.ophinv_.restype = None
     L.hsolve_.argtypes = [C.c_char_p, vp, vp, vp, vp, vp, vp, ip, dp, ip, ip, vp, vp, vp, C.c_size_t]

@@ -756,6 +756,55 @@ void dsop_(double *u, const char *op, const int *nx, const int *ny, const int *n
     });
 }
 
+static int dsop_code(const char *op, size_t op_len)
+{
+    char o[4] = {' ', ' ', ' ', 0};
+    for (size_t i = 0; i < 3 && i < op_len; i++) o[i] = op[i];
+    if (!strcmp(o, "+  ") || !strcmp(o, "sum") || !strcmp(o, "SUM")) return 1;
+    if (!strcmp(o, "*  ") || !strcmp(o, "mul") || !strcmp(o, "MUL")) return 2;
+    if (!strcmp(o, "m  ") || !strcmp(o, "min") || !strcmp(o, "mna") || !strcmp(o, "MIN") || !strcmp(o, "MNA")) return 3;
+    if (!strcmp(o, "M  ") || !strcmp(o, "max") || !strcmp(o, "mxa") || !strcmp(o, "MAX") || !strcmp(o, "MXA")) return 4;
+    return 0;
+}
+// core/dssum.f:163-196 vec_dssum, :198-258 vec_dsop (fgslib_gs_op_many over the ldim components), :260-287 nvec_dssum
+void vec_dssum_(double *u, double *v, double *w, const int *nx, const int *ny, const int *nz)
+{
+    (void)nx, (void)ny, (void)nz;
+    guard_fortran("vec_dssum", [&] {
+        double *us[3] = {u, v, w};
+        for (int f = 0; f < 3; f++) gs_op_host(field_handle(), us[f], 0, 1, 1, 1, 0);
+    });
+}
+void vec_dsop_(double *u, double *v, double *w, const int *nx, const int *ny, const int *nz, const char *op, size_t op_len)
+{
+    (void)nx, (void)ny, (void)nz;
+    guard_fortran("vec_dsop", [&] {
+        const int code = dsop_code(op, op_len);
+        if (code == 0) return;  // the reference falls through silently for an unknown op (dssum.f:232-256)
+        double *us[3] = {u, v, w};
+        for (int f = 0; f < 3; f++) gs_op_host(field_handle(), us[f], 0, 1, 1, code, 0);
+    });
+}
+void nvec_dssum_(double *u, const int *stride, const int *n, const int *gs_handle)
+{
+    guard_fortran("nvec_dssum", [&] { gs_op_host(*gs_handle, u, *stride, *n, 1, 1, 0); });
+}
+// core/ic.f:1871-1895 dsavg(u): u <- vmult * dssum(u) on the velocity mesh (vmult from nekb_set_velocity_state)
+void dsavg_(double *u)
+{
+    guard_fortran("dsavg", [&] {
+        require_init();
+        Ctx &c = ctx();
+        const size_t n = (size_t)c.nelv * c.nxyz;
+        NEKB_REQUIRE(c.vmult.n >= n, "dsavg: vmult not registered (nekb_set_velocity_state)");
+        c.stage[0].ensure(n);
+        NEKB_CUDA(cudaMemcpyAsync(c.stage[0].p, u, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        gs_op(field_handle(), c.stage[0].p, 1, c.vmult.p);
+        NEKB_CUDA(cudaMemcpyAsync(u, c.stage[0].p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+
 void axhelm_(double *au, const double *u, const double *helm1, const double *helm2, const int *imesh, const int *isd)
 {
     (void)isd;

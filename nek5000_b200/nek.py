@@ -278,6 +278,29 @@ def dsop(u: np.ndarray, op: str, nx: int | None = None, ny: int | None = None, n
 
 
 # --------------------------------------------------------------------------------------------- operators / solvers
+def vec_dssum(u, v, w, nx: int | None = None, ny: int | None = None, nz: int | None = None) -> None:
+    """core/dssum.f:163 vec_dssum."""
+    n = _state["lx1"]
+    lib().vec_dssum_(_ptr(u), _ptr(v), _ptr(w), _i(nx or n), _i(ny or n), _i(nz or n))
+
+
+def vec_dsop(u, v, w, op: str, nx: int | None = None, ny: int | None = None, nz: int | None = None) -> None:
+    """core/dssum.f:198 vec_dsop."""
+    n = _state["lx1"]
+    o = op.encode().ljust(3)[:3]
+    lib().vec_dsop_(_ptr(u), _ptr(v), _ptr(w), _i(nx or n), _i(ny or n), _i(nz or n), o, len(o))
+
+
+def nvec_dssum(u, stride: int, n: int, gs_handle: int) -> None:
+    """core/dssum.f:260 nvec_dssum."""
+    lib().nvec_dssum_(_ptr(u), _i(stride), _i(n), _i(gs_handle))
+
+
+def dsavg(u) -> None:
+    """core/ic.f:1871 dsavg."""
+    lib().dsavg_(_ptr(u))
+
+
 def axhelm(au: np.ndarray, u: np.ndarray, helm1: np.ndarray, helm2: np.ndarray, imesh: int = 1, isd: int = 1) -> None:
     lib().axhelm_(_ptr(au), _ptr(u), _ptr(helm1), _ptr(helm2), _i(imesh), _i(isd))
 

@@ -454,3 +454,26 @@ def test_uzawa_gmres_against_the_reference(nek):
     assert it == g["it"][0]
     assert relmax(x, g["x"]) <= 1e-8 and relmax(x, g["pe"]) <= 1e-6
 
+
+
+def test_vec_dssum_family_against_the_reference(nek):
+    """core/dssum.f:163-287 vec_dssum / vec_dsop / nvec_dssum and core/ic.f:1871 dsavg: the same gather-scatter as dsop, whose
+    reference outputs are in the golden file."""
+    g, case = G["core"], refcases.case_of("core")
+    h, _ = register_core(nek, g, case)
+    nek.set_velocity_state(g["v1mask"], g["v1mask"], g["v1mask"], g["vmult"])
+    n = case.n
+    u = g["u"]
+    a, b, c3 = u.copy(), (2.0 * u).copy(), (-u).copy()
+    nek.vec_dssum(a, b, c3)
+    assert relmax(a, g["dsop_add"]) <= TOL_APPLY and relmax(b, 2.0 * g["dsop_add"]) <= TOL_APPLY and relmax(c3, -g["dsop_add"]) <= TOL_APPLY
+    for op, key in (("*  ", "dsop_mul"), ("MIN", "dsop_min"), ("mxa", "dsop_max")):
+        a, b, c3 = u.copy(), u.copy(), u.copy()
+        nek.vec_dsop(a, b, c3, op)
+        assert relmax(a, g[key]) <= TOL_APPLY and np.array_equal(a, b) and np.array_equal(a, c3), op
+    ab = np.concatenate([u, 3.0 * u])
+    nek.nvec_dssum(ab, n, 2, h)
+    assert relmax(ab[:n], g["dsop_add"]) <= TOL_APPLY and relmax(ab[n:], 3.0 * g["dsop_add"]) <= TOL_APPLY
+    a = u.copy()
+    nek.dsavg(a)
+    assert relmax(a, g["dsop_add"] * g["vmult"]) <= TOL_APPLY
