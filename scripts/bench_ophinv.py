@@ -60,8 +60,22 @@ def leg(m, iters):
     t1 = time.perf_counter() - t0
     best = min(t)
     per = (best - t1) / (iters - 1) / 3
+    # one right-hand side through cggo (the fused path with NRHS = 1, or cggo_run)
+    it1 = C.c_int(0)
+
+    def run1(k):
+        check(L.nekb_cggo_dev(out[0].ptr, rhs[0].ptr, h1.ptr, h2.ptr, mask, mult, binv.ptr, 1, -1e-200, k, C.byref(it1), None))
+        check(L.nekb_sync())
+    run1(4)
+    t0 = time.perf_counter()
+    run1(iters)
+    ta = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    run1(1)
+    tb = time.perf_counter() - t0
+    per1 = (ta - tb) / (iters - 1)
     return dict(ms_per_iteration_component=per * 1e3, solve_ms=best * 1e3, setup_ms=t1 * 1e3, n=n, nel=b.nel,
-                checksum=float(np.abs(out[2].to_host()).max()))
+                checksum=float(np.abs(out[2].to_host()).max()), cggo_1rhs_ms_per_iteration=per1 * 1e3)
 
 
 def main():
@@ -92,6 +106,9 @@ def main():
            "fused_ms_per_iteration_component": f, "stock_ms_per_iteration_component": s, "speedup": s / f,
            "fused_GBps": WORDS_FUSED * 8 * n / (f * 1e-3) / 1e9, "stock_GBps": WORDS_STOCK * 8 * n / (s * 1e-3) / 1e9,
            "hbm_peak_GBps": peak, "fused_frac_of_peak": WORDS_FUSED * 8 * n / (f * 1e-3) / 1e9 / peak,
+           "cggo_1rhs_fused_ms_per_iteration": res["fused"]["cggo_1rhs_ms_per_iteration"],
+           "cggo_1rhs_stock_ms_per_iteration": res["stock"]["cggo_1rhs_ms_per_iteration"],
+           "cggo_1rhs_speedup": res["stock"]["cggo_1rhs_ms_per_iteration"] / res["fused"]["cggo_1rhs_ms_per_iteration"],
            "relative_difference_of_results": abs(res["fused"]["checksum"] - res["stock"]["checksum"]) / res["stock"]["checksum"],
            "legs": res}
     print(json.dumps(out))
