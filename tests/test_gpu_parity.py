@@ -377,6 +377,50 @@ def test_full_size_properties():
     N.finalize()
 
 
+def test_full_size_fused_helmholtz_solves():
+    """E = 64^3 = 262,144: the fused 3-right-hand-side PCG (ophinv, hcg.cuh) through size-independent properties: linearity
+    (right-hand sides f, 2f, -f/2 with a relative tolerance give identical iteration counts and solutions x, 2x, -x/2), the
+    residual of the converged solution, and agreement of the one-right-hand-side path (cggo) with component 1."""
+    import ctypes as C
+    from nek5000_b200 import nek as N
+    from nek5000_b200._lib import check
+    from nek5000_b200.bp5 import BP5
+    from nek5000_b200.nek import DevArray
+    N.finalize()
+    b = BP5(64, 64, 64, lx1=8)
+    n = b.n
+    L = __import__("nek5000_b200").lib()
+    N.set_ifield(1)
+    N.set_field_handle(1, b.gs_handle)
+    N.set_step_info(20, 1.0)
+    N.set_param(22, 0.0)
+    rng = np.random.default_rng(5)
+    mask, mult = b.devptr("mask"), b.devptr("mult")
+    h1, h2 = DevArray.from_host(1.0 + 0.2 * rng.random(n)), DevArray.from_host(80.0 + 10.0 * rng.random(n))
+    binv = DevArray.from_host(1.0 / np.maximum(b.get("bm1"), 1e-300))
+    f0 = b.get("bm1") * rng.standard_normal(n)
+    rhs = [DevArray.from_host(f0 * s) for s in (1.0, 2.0, -0.5)]
+    out = [DevArray(n) for _ in range(3)]
+    it = np.zeros(3, dtype=np.int32)
+    check(L.nekb_ophinv_dev(out[0].ptr, out[1].ptr, out[2].ptr, rhs[0].ptr, rhs[1].ptr, rhs[2].ptr, h1.ptr, h2.ptr, mask, mask, mask,
+                            mult, binv.ptr, -1e-9, 400, it.ctypes.data, None))
+    assert it[0] == it[1] == it[2] and 10 < it[0] < 400
+    x = [o.to_host() for o in out]
+    scale = np.abs(x[0]).max()
+    assert np.abs(x[1] - 2.0 * x[0]).max() <= 1e-12 * scale and np.abs(x[2] + 0.5 * x[0]).max() <= 1e-12 * scale
+    # residual: mask * dssum(A x) against the (dssum'ed, masked) right-hand side that ophinv left in rhs[0]
+    ax = DevArray(n)
+    check(L.nekb_axhelm_dev(ax.ptr, out[0].ptr, h1.ptr, h2.ptr, 1))
+    check(L.nekb_gs_op_dev(b.gs_handle, ax.ptr, 1, mask))
+    r = ax.to_host() - rhs[0].to_host()
+    assert np.abs(r).max() <= 1e-6 * np.abs(rhs[0].to_host()).max()
+    # one right-hand side through cggo_: same recurrence, same count
+    x1, it1 = DevArray(n), C.c_int(0)
+    check(L.nekb_cggo_dev(x1.ptr, rhs[0].ptr, h1.ptr, h2.ptr, mask, mult, binv.ptr, 1, -1e-9, 400, C.byref(it1), None))
+    assert it1.value == it[0] and np.abs(x1.to_host() - x[0]).max() <= 1e-9 * scale
+    N.finalize()
+
+
 # ------------------------------------------------------------------------------------------------- multi-GPU (NCCL)
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_multi_gpu_bp5_matches_single_domain_oracle(world):
