@@ -396,7 +396,8 @@ def test_full_size_fused_helmholtz_solves():
     N.set_param(22, 0.0)
     rng = np.random.default_rng(5)
     mask, mult = b.devptr("mask"), b.devptr("mult")
-    h1, h2 = DevArray.from_host(1.0 + 0.2 * rng.random(n)), DevArray.from_host(80.0 + 10.0 * rng.random(n))
+    # h2/h1 = 1e6: lambda_max(B^-1 A) ~ N^4 / h^2 ~ 1e7 on this mesh, so the operator is moderately conditioned (tens of iterations)
+    h1, h2 = DevArray.from_host(1.0 + 0.2 * rng.random(n)), DevArray.from_host(1.0e6 * (1.0 + 0.1 * rng.random(n)))
     binv = DevArray.from_host(1.0 / np.maximum(b.get("bm1"), 1e-300))
     f0 = b.get("bm1") * rng.standard_normal(n)
     rhs = [DevArray.from_host(f0 * s) for s in (1.0, 2.0, -0.5)]
@@ -404,7 +405,7 @@ def test_full_size_fused_helmholtz_solves():
     it = np.zeros(3, dtype=np.int32)
     check(L.nekb_ophinv_dev(out[0].ptr, out[1].ptr, out[2].ptr, rhs[0].ptr, rhs[1].ptr, rhs[2].ptr, h1.ptr, h2.ptr, mask, mask, mask,
                             mult, binv.ptr, -1e-9, 400, it.ctypes.data, None))
-    assert it[0] == it[1] == it[2] and 10 < it[0] < 400
+    assert it[0] == it[1] == it[2] and 5 < it[0] < 400, it
     x = [o.to_host() for o in out]
     scale = np.abs(x[0]).max()
     assert np.abs(x[1] - 2.0 * x[0]).max() <= 1e-12 * scale and np.abs(x[2] + 0.5 * x[0]).max() <= 1e-12 * scale
