@@ -235,6 +235,10 @@ int nekb_cdabdtp_dev(double *ap, const double *wp, const double *h1, const doubl
 int nekb_set_param(int idx, double value);
 int nekb_set_binv(const double *binvm1, const double *bintm1);
 
+/* How the inter-rank part of gs_op runs for this handle: 0 = nothing shared with other ranks, 1 = pack -> grouped
+ * ncclSend/ncclRecv -> unpack, 2 = peer-memory exchange (pack kernel stores into the peers' receive areas over NVLink through
+ * CUDA IPC mappings and raises epoch flags, unpack kernel waits on them; default on one node, NEKB_GS_P2P=0 selects 1). */
+int nekb_gs_exchange_mode(int handle);
 /* ------------------------------------------------------------------------------------
  * C. Device-resident API (pointers are device pointers valid on the library's device)
  * ---------------------------------------------------------------------------------- */

@@ -224,6 +224,197 @@ inline SharedIds discover_shared_ids(const std::vector<int64_t> &uniq)
     return out;
 }
 
+// ---- peer-memory exchange (NVLink 5 / NVSwitch, CUDA IPC) -----------------------------------------------------------
+// The exchange of gs_op without a communication library call: every rank exports one device allocation per handle
+// (double-buffered receive area + flag words) through CUDA IPC; the PACK kernel stores each value straight into the peer's
+// receive area over NVLink and then raises an epoch flag in the peer's memory; the UNPACK kernel waits for the flags of
+// its peers, combines, and tells the peers that the buffer of this epoch has been consumed.  A buffer is rewritten two
+// exchanges later, and only after the owner's "consumed" flag allows it, so back-to-back gs_ops need no other barrier.
+// One-node only (all ranks must see each other's memory); NEKB_GS_P2P=0 or any IPC failure keeps the NCCL send/recv path.
+constexpr int GS_P2P_MAXPEERS = 32;
+struct GsP2pRecord {
+    cudaIpcMemHandle_t handle;
+    int64_t nitems;
+    int32_t ok, npeers;
+    int32_t peers[GS_P2P_MAXPEERS];
+    int64_t peer_off[GS_P2P_MAXPEERS + 1];
+};
+
+inline void gs_p2p_release(GsMap &h)
+{
+    h.peer_map.close();
+    h.p2p = false;
+}
+
+inline void gs_p2p_setup(GsMap &h)
+{
+    Ctx &c = ctx();
+    h.p2p = false;
+    if (c.nranks <= 1) return;
+    const char *env = getenv("NEKB_GS_P2P");
+    const bool want = (!env || atoi(env) != 0) && c.nccl_comm != nullptr;
+    const int np = (int)h.peers.size();
+    const int64_t nitems = h.peer_off.empty() ? 0 : h.peer_off.back();
+    GsP2pRecord mine;
+    memset(&mine, 0, sizeof mine);
+    mine.nitems = nitems, mine.npeers = np;
+    mine.ok = want && np <= GS_P2P_MAXPEERS;
+    const size_t bytes = (size_t)2 * nitems * sizeof(double) + (size_t)2 * GS_P2P_MAXPEERS * sizeof(unsigned long long) + 64;
+    if (mine.ok) {
+        h.xmem.alloc(bytes);
+        h.xmem.zero(c.stream);
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+        if (cudaIpcGetMemHandle(&mine.handle, h.xmem.p) != cudaSuccess) {
+            cudaGetLastError();
+            mine.ok = 0;
+        }
+        for (int p = 0; p < np; p++) mine.peers[p] = h.peers[p];
+        for (int p = 0; p <= np; p++) mine.peer_off[p] = h.peer_off[p];
+    }
+    std::vector<GsP2pRecord> all((size_t)c.nranks);
+    host_allgather(&mine, all.data(), sizeof mine);
+    bool ok = true;
+    for (const GsP2pRecord &r : all) ok = ok && r.ok;   // the same decision on every rank
+    if (!ok || np == 0) {
+        if (!ok) h.xmem.release();
+        h.p2p = ok;     // a rank without peers has nothing to exchange but stays in step
+        return;
+    }
+    std::vector<double *> precv(np);
+    std::vector<int64_t> pstride(np), myoff(np);
+    std::vector<unsigned long long *> parr(np), pdone(np);
+    h.peer_map.close();
+    h.peer_map.v.assign(np, nullptr);
+    for (int p = 0; p < np && ok; p++) {
+        const GsP2pRecord &r = all[h.peers[p]];
+        int slot = -1;
+        for (int q = 0; q < r.npeers; q++)
+            if (r.peers[q] == c.rank) slot = q;
+        const int64_t cnt = h.peer_off[p + 1] - h.peer_off[p];
+        if (slot < 0 || r.peer_off[slot + 1] - r.peer_off[slot] != cnt) {
+            ok = false;
+            break;
+        }
+        void *base = nullptr;
+        if (cudaIpcOpenMemHandle(&base, r.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = false;
+            break;
+        }
+        h.peer_map.v[p] = base;
+        unsigned char *b = static_cast<unsigned char *>(base);
+        unsigned long long *flags = reinterpret_cast<unsigned long long *>(b + (size_t)2 * r.nitems * sizeof(double));
+        precv[p] = reinterpret_cast<double *>(b) + r.peer_off[slot];
+        pstride[p] = r.nitems;
+        myoff[p] = h.peer_off[p];
+        parr[p] = flags + slot;
+        pdone[p] = flags + GS_P2P_MAXPEERS + slot;
+    }
+    // every rank must reach the same verdict, or some would wait for flags that never come
+    int32_t v = ok ? 1 : 0;
+    std::vector<int32_t> vs((size_t)c.nranks);
+    host_allgather(&v, vs.data(), sizeof v);
+    for (int32_t q : vs) ok = ok && q;
+    if (!ok) {
+        gs_p2p_release(h);
+        h.xmem.release();
+        return;
+    }
+    std::vector<unsigned char> ip((size_t)nitems);
+    for (int p = 0; p < np; p++)
+        for (int64_t q = h.peer_off[p]; q < h.peer_off[p + 1]; q++) ip[q] = (unsigned char)p;
+    cudaStream_t st = c.stream;
+    h.item_peer.upload(ip.data(), ip.size(), st);
+    h.d_peer_recv.upload(precv.data(), precv.size(), st);
+    h.d_peer_stride.upload(pstride.data(), pstride.size(), st);
+    h.d_my_off.upload(myoff.data(), myoff.size(), st);
+    h.d_peer_arrived.upload(parr.data(), parr.size(), st);
+    h.d_peer_done.upload(pdone.data(), pdone.size(), st);
+    NEKB_CUDA(cudaStreamSynchronize(st));
+    h.epoch = 0;
+    h.p2p = true;
+}
+
+__device__ __forceinline__ void gs_spin_until(const volatile unsigned long long *flag, unsigned long long want)
+{
+    const long long t0 = clock64();
+    while (*flag < want) {
+        if (clock64() - t0 > 40000000000LL) {  // ~20 s: a peer never arrived -- fail loudly instead of hanging the GPU
+            printf("nekb200: gs peer-memory exchange timed out (flag %llu < %llu)\n", (unsigned long long)*flag, want);
+            __trap();
+        }
+    }
+}
+
+// pack + send: u -> the peers' receive areas (remote stores over NVLink), then the epoch flag
+__global__ void __launch_bounds__(256)
+    gs_pack_p2p_kernel(const double *__restrict__ u, const int32_t *__restrict__ item_sid, const int32_t *__restrict__ rep,
+                       const unsigned char *__restrict__ item_peer, double *const *__restrict__ peer_recv, const int64_t *__restrict__ peer_stride,
+                       const int64_t *__restrict__ my_off, unsigned long long *const *__restrict__ peer_arrived,
+                       const unsigned long long *done_flags, unsigned *ticket, int nitems, int npeers, unsigned long long epoch)
+{
+    __shared__ double *s_dst[GS_P2P_MAXPEERS];
+    __shared__ int s_last;
+    if (threadIdx.x < npeers) {
+        // the buffer of this parity was last used at epoch - 2: wait until the peer has consumed it
+        if (epoch > 2) gs_spin_until(done_flags + threadIdx.x, epoch - 2);
+        s_dst[threadIdx.x] = peer_recv[threadIdx.x] + (epoch & 1ull) * peer_stride[threadIdx.x] - my_off[threadIdx.x];
+    }
+    __syncthreads();
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nitems; q += gridDim.x * blockDim.x)
+        s_dst[item_peer[q]][q] = u[rep[item_sid[q]]];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicInc(ticket, gridDim.x - 1);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < npeers) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(peer_arrived[threadIdx.x]) = epoch;
+    }
+}
+
+template <int OP>
+__global__ void __launch_bounds__(256)
+    gs_unpack_p2p_kernel(double *__restrict__ u, const double *recvbuf, const int32_t *__restrict__ s_off, const int32_t *__restrict__ s_items,
+                         const int32_t *__restrict__ s_nbelow, const int32_t *__restrict__ rep, const int32_t *__restrict__ x_goff,
+                         const int32_t *__restrict__ x_gidx, int nslots, const unsigned long long *arrived_flags,
+                         unsigned long long *const *__restrict__ peer_done, unsigned *ticket, int npeers, unsigned long long epoch)
+{
+    __shared__ int s_last;
+    if (threadIdx.x < npeers) gs_spin_until(arrived_flags + threadIdx.x, epoch);
+    __syncthreads();
+    __threadfence_system();
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += gridDim.x * blockDim.x) {
+        const int b = s_off[s], e = s_off[s + 1], nb = s_nbelow[s];
+        const double mine = u[rep[s]];
+        double v;
+        if (nb == 0) {
+            v = mine;
+            for (int q = b; q < e; q++) v = gs_combine<OP>(v, __ldcg(recvbuf + s_items[q]));
+        } else {
+            v = __ldcg(recvbuf + s_items[b]);
+            for (int q = b + 1; q < b + nb; q++) v = gs_combine<OP>(v, __ldcg(recvbuf + s_items[q]));
+            v = gs_combine<OP>(v, mine);
+            for (int q = b + nb; q < e; q++) v = gs_combine<OP>(v, __ldcg(recvbuf + s_items[q]));
+        }
+        for (int q = x_goff[s]; q < x_goff[s + 1]; q++) u[x_gidx[q]] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned t = atomicInc(ticket, gridDim.x - 1);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < npeers) {   // every block has read its part of the buffer: the peers may reuse it
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(peer_done[threadIdx.x]) = epoch;
+    }
+}
+
 // ---- remote part of a gs handle ----------------------------------------------------------------------------------
 // cand_idx: local indices whose ids may live on other ranks (nullptr = every non-zero id).  All local copies of
 // a shared id must be among the candidates.
@@ -266,7 +457,10 @@ inline void gs_build_remote(GsMap &h, const int64_t *id_host, int64_t n, const i
     const int64_t ns = (int64_t)sids.size();
     h.nshared = ns;
     h.peers = sh.peers;
-    if (ns == 0) return;
+    if (ns == 0) {
+        gs_p2p_setup(h);  // collective: ranks without shared ids still take part in the handle exchange
+        return;
+    }
     NEKB_REQUIRE(ns < 2147483647, "gs_setup: too many shared ids");
 
     std::vector<int32_t> x_goff(ns + 1), x_gidx, rep(ns);
@@ -311,6 +505,7 @@ inline void gs_build_remote(GsMap &h, const int64_t *id_host, int64_t n, const i
     h.recvbuf.alloc(nitems);
     h.nx_members = (int64_t)x_gidx.size();
     NEKB_CUDA(cudaStreamSynchronize(st));
+    gs_p2p_setup(h);
 }
 
 __global__ void __launch_bounds__(256)
@@ -351,6 +546,33 @@ inline void gs_remote_exchange(GsMap &h, double *u, int op)
     if (c.nranks <= 1 || h.nshared == 0) return;
     NEKB_REQUIRE(c.nccl_comm != nullptr, "gs_op: ids are shared between ranks but nekb_comm_init was not called");
     const int nitems = (int)h.peer_off.back();
+    if (h.p2p) {
+        const int npeers = (int)h.peers.size();
+        const unsigned long long epoch = ++h.epoch;
+        unsigned char *base = h.xmem.p;
+        const double *recv = reinterpret_cast<const double *>(base) + (epoch & 1ull) * (size_t)nitems;
+        unsigned long long *flags = reinterpret_cast<unsigned long long *>(base + (size_t)2 * nitems * sizeof(double));
+        unsigned *tickets = reinterpret_cast<unsigned *>(flags + 2 * GS_P2P_MAXPEERS);
+        int gp = blocks_for(nitems), gu = blocks_for(h.nshared);
+        if (gp > c.num_sms * 4) gp = c.num_sms * 4;   // all blocks are co-resident: the flag protocol never waits on an unscheduled block
+        if (gu > c.num_sms * 4) gu = c.num_sms * 4;
+        gs_pack_p2p_kernel<<<gp, 256, 0, c.stream>>>(u, h.x_item_sid.p, h.x_rep.p, h.item_peer.p, h.d_peer_recv.p, h.d_peer_stride.p,
+                                                     h.d_my_off.p, h.d_peer_arrived.p, flags + GS_P2P_MAXPEERS, tickets, nitems, npeers, epoch);
+        NEKB_LAUNCHED();
+        const int ns2 = (int)h.nshared;
+#define NEKB_UNPACK_P2P(OPV)                                                                                                   \
+    gs_unpack_p2p_kernel<OPV><<<gu, 256, 0, c.stream>>>(u, recv, h.x_soff.p, h.x_sitems.p, h.x_nbelow.p, h.x_rep.p, h.x_goff.p,   \
+                                                        h.x_gidx.p, ns2, flags, h.d_peer_done.p, tickets + 1, npeers, epoch)
+        switch (op) {
+            case 1: NEKB_UNPACK_P2P(1); break;
+            case 2: NEKB_UNPACK_P2P(2); break;
+            case 3: NEKB_UNPACK_P2P(3); break;
+            default: NEKB_UNPACK_P2P(4); break;
+        }
+#undef NEKB_UNPACK_P2P
+        NEKB_LAUNCHED();
+        return;
+    }
     gs_pack_kernel<<<blocks_for(nitems), 256, 0, c.stream>>>(h.sendbuf.p, u, h.x_item_sid.p, h.x_rep.p, nitems);
     NEKB_LAUNCHED();
     NEKB_NCCL(nccl().GroupStart());

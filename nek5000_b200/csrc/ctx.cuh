@@ -23,6 +23,31 @@ struct CgScalars {
     double work[4];
 };
 
+// CUDA IPC mappings of peer allocations, closed when the owning handle goes away
+struct IpcMaps {
+    std::vector<void *> v;
+    IpcMaps() = default;
+    IpcMaps(const IpcMaps &) = delete;
+    IpcMaps &operator=(const IpcMaps &) = delete;
+    IpcMaps(IpcMaps &&o) noexcept : v(std::move(o.v)) { o.v.clear(); }
+    IpcMaps &operator=(IpcMaps &&o) noexcept
+    {
+        if (this != &o) {
+            close();
+            v = std::move(o.v);
+            o.v.clear();
+        }
+        return *this;
+    }
+    ~IpcMaps() { close(); }
+    void close()
+    {
+        for (void *q : v)
+            if (q) cudaIpcCloseMemHandle(q);
+        v.clear();
+    }
+};
+
 // Local gather-scatter map (gslib gs_setup result restated for the device).
 struct GsMap {
     bool used = false;
@@ -44,6 +69,16 @@ struct GsMap {
     DevBuf<int32_t> x_nbelow;      // [nshared] how many of those peers have a lower rank than this one
     DevBuf<double> sendbuf, recvbuf;
     int64_t nx_members = 0;
+    // ---- peer-memory exchange over NVLink (CUDA IPC; comm.cuh gs_p2p_*) -------------------------------------------
+    bool p2p = false;
+    uint64_t epoch = 0;                // exchanges done with this handle (identical on every rank)
+    DevBuf<unsigned char> xmem;        // [2][nitems] doubles (double-buffered receive) | arrived[npeers] | done[npeers] | tickets
+    IpcMaps peer_map;                  // IPC mappings of the peers' xmem (closed with the handle)
+    DevBuf<unsigned char> item_peer;   // [nitems] peer index of every exchange item
+    DevBuf<double *> d_peer_recv;      // [npeers] peer's receive area for my segment (buffer 0)
+    DevBuf<int64_t> d_peer_stride;     // [npeers] peer's nitems (distance between its two buffers)
+    DevBuf<int64_t> d_my_off;          // [npeers] start of the segment in my own item list
+    DevBuf<unsigned long long *> d_peer_arrived, d_peer_done;   // [npeers] my slots in the peer's flag arrays
 };
 
 struct Ctx {

@@ -528,6 +528,15 @@ void ophinv_(double *o1, double *o2, double *o3, double *i1, double *i2, double 
 }
 
 // ---------------------------------------------------------------------------------------------------- gs (device API)
+int nekb_gs_exchange_mode(int handle)
+{
+    int mode = -1;
+    guard([&] {
+        GsMap &h = gs_get(handle);
+        mode = (ctx().nranks <= 1 || h.nshared == 0) ? 0 : (h.p2p ? 2 : 1);
+    });
+    return mode;
+}
 int nekb_gs_setup(int *handle, const int64_t *id_host, int64_t n)
 {
     return guard([&] {

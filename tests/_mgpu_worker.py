@@ -28,6 +28,10 @@ def main():
     deform = 0.04
     b = BP5(nelx, nely, nelz, lx1=8, device=local, rank=rank, nranks=world, layout=(px, py, pz), deform=deform)
     maxit = 40
+    from nek5000_b200 import lib as _lib
+    mode = _lib().nekb_gs_exchange_mode(b.gs_handle)
+    want = 1 if os.environ.get("NEKB_GS_P2P", "1") == "0" else 2     # peer-memory exchange over NVLink unless switched off
+    assert mode == want, f"gs exchange mode {mode}, expected {want}"
     it, sec, hist = b.solve(-1e-8, maxit, history=True)
     u = b.get("u1")
 
@@ -104,7 +108,7 @@ def main():
             d = rel(outs[k].to_host(), xo[take])
             worst = max(worst, d) if tol < 0 else worst
             assert d <= ftol, ("ophinv solution", k, d)
-    print(f"MGPU-OK rank {rank} of {world}: its={it} rel(u)={rel(u, uref[take]):.2e} ophinv its={itv.tolist()} rel={worst:.1e}", flush=True)
+    print(f"MGPU-OK rank {rank} of {world}: its={it} rel(u)={rel(u, uref[take]):.2e} ophinv its={itv.tolist()} rel={worst:.1e} gs-exchange-mode={mode}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -423,11 +423,13 @@ def test_full_size_fused_helmholtz_solves():
 
 
 # ------------------------------------------------------------------------------------------------- multi-GPU (NCCL)
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_multi_gpu_bp5_matches_single_domain_oracle(world):
-    """Element-partitioned BP5 over NCCL: every rank's part of numbering, rhs, CG history and solution equals the
-    undivided oracle solve.  Skipped when the box has fewer GPUs."""
+@pytest.mark.parametrize("world,p2p", [(2, "1"), (2, "0"), (4, "1"), (8, "1"), (8, "0")])
+def test_multi_gpu_bp5_matches_single_domain_oracle(world, p2p, monkeypatch):
+    """Element-partitioned BP5 and ophinv on N GPUs: every rank's part of numbering, rhs, CG history and solution equals the
+    undivided oracle solve (SURVEY.md 8e).  p2p = "1": gs exchange through peer memory over NVLink (CUDA IPC, flag protocol);
+    "0": pack -> ncclSend/ncclRecv -> unpack.  Skipped when the box has fewer GPUs."""
     import os
+    monkeypatch.setenv("NEKB_GS_P2P", p2p)
     import subprocess
     import sys
     import torch
