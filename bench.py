@@ -189,6 +189,11 @@ def main():
     case = BP5(a.m * px, a.m * py, a.m * pz, lx1=LX1, device=local, rank=rank, nranks=world, layout=(px, py, pz))
     n, E_glob = case.n, case.nel_global
     L = lib()
+    try:  # how the inter-rank part of gs_op runs (0 single rank, 1 NCCL send/recv, 2 peer memory over NVLink)
+        config["gs_exchange"] = {0: "none (one rank)", 1: "pack + ncclSend/ncclRecv + unpack",
+                                 2: "peer-memory stores over NVLink (CUDA IPC) + epoch flags"}[int(L.nekb_gs_exchange_mode(case.gs_handle))]
+    except Exception:
+        pass
 
     def barrier():
         torch.cuda.synchronize()

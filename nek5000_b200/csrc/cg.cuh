@@ -665,8 +665,9 @@ inline void setprec_run(double *dpc, const double *h1, const double *h2, int nel
 }
 
 // Returns niterhm.  hist_host (may be NULL): 3 doubles per executed iteration (rtz1, rbn2, rho).
-// Includes the all-Neumann null-space correction (ifmcor, :705-720, :749-752).  Not provided: the 'PRES' branches
-// (:641-657 forward to hmh_gmres, which is exported separately; :731-746 adds crs_solve_h1).
+// Includes the all-Neumann null-space correction (ifmcor, :705-720, :749-752).  The 'PRES' branch (:641-657) is taken by
+// the callers (cggo_, hmholtz_, hsolve_ forward to hmh_gmres); :731-746 (crs_solve_h1 inside PCG for 'PRES') is not provided.
+// lx1 = 8 Jacobi solves normally go through the fused path (hcg.cuh cggo_solve); this routine is the general one.
 inline int cggo_run(const CggoArgs &a, double tin, int maxit, double *hist_host)
 {
     Ctx &c = ctx();

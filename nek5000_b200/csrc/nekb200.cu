@@ -177,6 +177,11 @@ void nekb_finalize(void)
     fdm_h1_state() = FdmH1State();
     gmres_state() = GmresState();
     crs_scalars().release();
+    hcg_state() = HcgState();
+    proj_states().clear();
+    proj_scratch() = ProjScratch();
+    mesh2() = Mesh2();
+    pnpn2_work() = Pnpn2Work();
     c.gs.clear();
     if (c.nccl_comm) nccl().CommDestroy(comm_handle());
     void (*eh)(void) = c.exit_handler;

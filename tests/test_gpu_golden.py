@@ -267,7 +267,7 @@ def test_ophinv_fused_three_rhs_against_the_reference(nek):
             assert relmax(o[k], g[f"o{k + 1}{key}"]) <= ftol, (key, k)
 
 
-def test_fused_and_stock_cggo_agree(nek, monkeypatch):
+def test_fused_and_stock_cggo_agree(nek):
     """The fused path (hcg.cuh, default for lx1 = 8 Jacobi solves) against the kernel-per-statement cggo_run (NEKB_HCG=0 is
     read once per process, so the stock path is reached through a right-hand side the fused path declines: here a mask that
     is not 0/1)."""
