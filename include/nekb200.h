@@ -380,6 +380,12 @@ void nekb_h1mg_free(void);
 int nekb_hsmg_setup(const int *fbc, const double *xm1, const double *ym1, const double *zm1, const int64_t *vertex,
                     int nelv, int null_space, int64_t nelgv, const double *df, const double *sr, const double *ss,
                     const double *st);
+/* Host-only (no GPU needed): the 1-D generalised eigen-systems the preconditioner setup is built from, for the CPU tests.
+ * nekb_fast1d_sem_host: gen_fast's set_up_fast_1D_sem (core/fast3d.f:1351-1408) at order lx1-1 -> S[lx1*lx1] (row-major,
+ * eigenvectors in columns, boundary rows zeroed), lam[lx1].  nekb_fast1d_host: hsmg_setup_fast1d (core/hsmg.f:775-879) for
+ * polynomial order n -> S[(n+3)^2], lam[n+3].  bc codes of get_fast_bc. */
+int nekb_fast1d_sem_host(int lx1, int lbc, int rbc, double ll, double lm, double lr, double *S, double *lam);
+int nekb_fast1d_host(int n, int lbc, int rbc, double ll, double lm, double lr, double *S, double *lam);
 int nekb_hsmg_solve_dev(double *e_dev, const double *r_dev);
 int nekb_local_solves_fdm_dev(double *u_dev, const double *v_dev);
 void hsmg_solve_(double *e, const double *r);

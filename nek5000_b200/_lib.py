@@ -94,6 +94,8 @@ def lib() -> C.CDLL:
     L.nekb_gs_free.argtypes = [C.c_int]
     L.nekb_gs_info.argtypes = [C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.nekb_gs_exchange_mode.argtypes = [C.c_int]
+    L.nekb_fast1d_sem_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, vp, vp]
+    L.nekb_fast1d_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, vp, vp]
     L.nekb_gs_get_map.argtypes = [C.c_int, i64p, i32p]
     L.nekb_gs_remote_info.argtypes = [C.c_int, ip, C.POINTER(C.c_int64)]
     L.nekb_gs_get_remote.argtypes = [C.c_int, i32p, i64p, i32p]

@@ -1133,6 +1133,31 @@ int nekb_hsmg_setup(const int *fbc, const double *xm1, const double *ym1, const 
         h1mg_setup_run(hsmg2(), fbc, xm1, ym1, zm1, vertex, nelv, null_space, &f);
     });
 }
+// Host-only pieces of the setup, exported so that the CPU test-suite can check them against the reference without a GPU:
+// the 1-D eigen-systems of gen_fast (core/fast3d.f:1351-1408) and of hsmg_setup_fast1d (core/hsmg.f:775-879).
+int nekb_fast1d_sem_host(int lx1, int lbc, int rbc, double ll, double lm, double lr, double *S, double *lam)
+{
+    return guard([&] {
+        NEKB_REQUIRE(lx1 >= 4 && lx1 <= 16, "fast1d_sem: lx1 out of range");
+        std::vector<double> bh, jgl, dgl, Sv, lv;
+        semhat_weighted_host(lx1 - 1, bh, jgl, dgl);
+        fast1d_sem_host(lbc, rbc, ll, lm, lr, bh, jgl, dgl, Sv, lv);
+        memcpy(S, Sv.data(), sizeof(double) * (size_t)lx1 * lx1);
+        memcpy(lam, lv.data(), sizeof(double) * (size_t)lx1);
+    });
+}
+int nekb_fast1d_host(int n, int lbc, int rbc, double ll, double lm, double lr, double *S, double *lam)
+{
+    return guard([&] {
+        NEKB_REQUIRE(n >= 1 && n <= 16, "fast1d: polynomial order out of range");
+        std::vector<double> ah, bh, zh, Sv, lv;
+        semhat_host(n, ah, bh, zh);
+        fast1d_host(lbc, rbc, ll, lm, lr, ah, bh, n, Sv, lv);
+        const int nl = n + 3;
+        memcpy(S, Sv.data(), sizeof(double) * (size_t)nl * nl);
+        memcpy(lam, lv.data(), sizeof(double) * (size_t)nl);
+    });
+}
 int nekb_hsmg_solve_dev(double *e_dev, const double *r_dev)
 {
     return guard([&] {

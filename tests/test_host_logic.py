@@ -105,3 +105,31 @@ def test_multirank_numbering_and_shared_ids_gloo(nb, tmp_path, world, dims, nx):
         for k, b in enumerate(peers.tolist()):
             got = ids[off[k]:off[k + 1]]
             assert got.tolist() == sorted(sets[a] & sets[b])
+
+
+def test_fast_diagonalisation_1d_systems_on_the_host(nb):
+    """The 1-D generalised eigen-systems of the preconditioner setup are host code (Cholesky + Jacobi in long double): checked
+    here without a GPU against the oracle restatements that tests/test_ref_pins.py pins to the reference's own gen_fast /
+    hsmg_setup_fast (LAPACK dsygv): same eigenvalues, same S f(lam) S^T (eigenvector signs are free)."""
+    import ctypes as C
+    from oracle import hsmg
+    L = nb.lib()
+    P = lambda a: C.c_void_p(a.ctypes.data)
+    bh, jgl, dgl = hsmg.semhat_weighted(7)
+    for lbc, rbc, ll, lm, lr in ((0, 0, 0.3, 0.35, 0.4), (2, 0, 0.0, 0.5, 0.25), (0, 1, 0.2, 0.2, 0.0), (3, 2, 0.0, 1.0, 0.0), (1, 3, 0.0, 0.7, 0.0)):
+        S, lam = np.zeros(64), np.zeros(8)
+        assert L.nekb_fast1d_sem_host(8, lbc, rbc, ll, lm, lr, P(S), P(lam)) == 0
+        So, lo = hsmg.fast1d_sem(lbc, rbc, ll, lm, lr, bh, jgl, dgl)
+        assert np.abs(lam - lo).max() <= 1e-10 * np.abs(lo).max()
+        S = S.reshape(8, 8)
+        f = 1.0 / (1.0 + np.abs(lo))
+        assert np.abs((S * f) @ S.T - (So * f) @ So.T).max() <= 1e-10 * np.abs((So * f) @ So.T).max()
+    a7, b7, _, _ = hsmg.semhat(7)
+    for lbc, rbc, ll, lm, lr in ((0, 0, 0.7, 1.0, 1.3), (1, 2, 0.0, 1.0, 0.0), (2, 0, 0.0, 0.4, 0.6)):
+        S, lam = np.zeros(100), np.zeros(10)
+        assert L.nekb_fast1d_host(7, lbc, rbc, ll, lm, lr, P(S), P(lam)) == 0
+        So, lo = hsmg.fast1d(lbc, rbc, ll, lm, lr, a7, b7, 7)
+        assert np.abs(lam - lo).max() <= 1e-10 * np.abs(lo).max()
+        S = S.reshape(10, 10)
+        f = 1.0 / (1.0 + np.abs(lo))
+        assert np.abs((S * f) @ S.T - (So * f) @ So.T).max() <= 1e-10 * np.abs((So * f) @ So.T).max()
