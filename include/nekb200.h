@@ -418,6 +418,9 @@ int nekb_set_pressure_state(const double *pmask, const double *binvm1, double to
 /* core/gmres.f:304 hmh_gmres(res,h1,h2,wt,iter): on entry *iter = maxit, on return the iterations performed; res is
  * overwritten with the solution.  h1mg_solve is the preconditioner (ifmgrid, param(40) in 0..2). */
 void hmh_gmres_(double *res, const double *h1, const double *h2, const double *wt, int *iter);
+/* core/hmholtz.f:2164 hmh_flex_cg(res,h1,h2,wt,iter): flexible PCG with h1mg_solve as preconditioner (param(42) = 2); the same
+ * COMMON state as hmh_gmres.  cggo_/hmholtz_/hsolve_ forward name = 'PRES' here when param(42) = 2. */
+void hmh_flex_cg_(double *res, const double *h1, const double *h2, const double *wt, int *iter);
 /* The same on device buffers with an explicit tolerance: tol > 0 absolute on |gamma|/sqrt(volvm1), tol < 0 relative
  * to the initial residual (param(21) < 0).  hist_host (may be NULL, maxit+1 doubles) receives rnorm per iteration;
  * h2_dev may be NULL (h2 = 0).  ifvcor/nelgv as registered by nekb_set_pressure_state. */

@@ -168,6 +168,8 @@ def lib() -> C.CDLL:
         getattr(L, nm).restype = None
     L.cdabdtp_.argtypes = [vp] * 5 + [ip]
     L.cdabdtp_.restype = None
+    L.hmh_flex_cg_.argtypes = [vp] * 4 + [ip]
+    L.hmh_flex_cg_.restype = None
     L.uzawa_gmres_.argtypes = [vp] * 4 + [ip, ip]
     L.uzawa_gmres_.restype = None
     L.nekb_set_uzawa_state.argtypes = [C.c_double] * 4

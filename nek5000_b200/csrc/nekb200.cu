@@ -868,11 +868,15 @@ void cggo_(double *x, const double *f, const double *h1, const double *h2, const
             // (ifsplit is implied by a completed h1mg_setup, which only the Pn-Pn pressure solver performs.)
             NEKB_REQUIRE(h1mg().ready, "cggo('PRES'): the pressure multigrid is not set up (nekb_h1mg_setup); the plain-PCG pressure "
                                        "branch (ifsplit = .false.) is not provided");
-            NEKB_REQUIRE(c.param[42] == 0.0, "cggo('PRES'): param(42) = 2 (hmh_flex_cg) / 1 (PCG) are not provided, only GMRES (param(42)=0)");
+            NEKB_REQUIRE(c.param[42] == 0.0 || c.param[42] == 2.0,
+                         "cggo('PRES'): param(42) = 1 (plain PCG with crs_solve_h1) is not provided; 0 = GMRES, 2 = flexible CG");
             const size_t np_ = (size_t)c.nelv * c.nxyz;
             if (x != f) memcpy(x, f, np_ * sizeof(double));
             int iter = *maxit;
-            hmh_gmres_(x, h1, h2, mult, &iter);
+            if (c.param[42] == 2.0)
+                hmh_flex_cg_(x, h1, h2, mult, &iter);
+            else
+                hmh_gmres_(x, h1, h2, mult, &iter);
             c.niterhm = iter;
             return;
         }
@@ -1333,6 +1337,76 @@ static int hmh_gmres_body(double *res, const double *h1, const double *h2, const
     const double tol = G.param21 < 0 ? -fabs(G.param21) : tolps;
     return hmh_gmres_run(res, h1, h2, wt, G.pmask.p, M.nel, M.lev[M.lmax - 1].gs, c.volvm1, tol, maxit, nullptr, nullptr);
 }
+// core/hmholtz.f:2164-2290 hmh_flex_cg(res,h1,h2,wt,iter): flexible PCG with h1mg_solve (param(42) = 2) on device pointers
+static int hmh_flex_cg_body(double *res, const double *h1, const double *h2, const double *wt, int maxit)
+{
+    Ctx &c = ctx();
+    GmresState &G = gmres_state();
+    H1mg &M = h1mg();
+    NEKB_REQUIRE(M.ready, "hmh_flex_cg: nekb_h1mg_setup has not been called");
+    NEKB_REQUIRE(c.volvm1 > 0.0, "volvm1 not registered (nekb_set_step_info)");
+    const int64_t n = (int64_t)M.nel * c.nxyz;
+    NEKB_REQUIRE(G.pmask.n >= (size_t)n && G.binvm1.n >= (size_t)n, "hmh_flex_cg: pmask/binvm1 not registered (nekb_set_pressure_state)");
+    cudaStream_t s = c.stream;
+    const int grid = cg_grid(n), gsh = M.lev[M.lmax - 1].gs;
+    double tolps = chktcg1_dev(G.tolps, res, h1, h2, G.pmask.p, wt, G.binvm1.p, M.nel, c.volvm1);   // :2204-2208
+    if (G.param21 > 0 && tolps > fabs(G.param21)) tolps = fabs(G.param21);
+    if (c.istep == 0) tolps = 1.e-4;
+    double tolpss = tolps;
+    static DevBuf<double> r, r1, p, z, w;
+    r.ensure((size_t)n), r1.ensure((size_t)n), p.ensure((size_t)n), z.ensure((size_t)n), w.ensure((size_t)n);
+    NEKB_CUDA(cudaMemcpyAsync(r.p, res, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+    NEKB_CUDA(cudaMemsetAsync(r1.p, 0, sizeof(double) * (size_t)n, s));
+    NEKB_CUDA(cudaMemsetAsync(p.p, 0, sizeof(double) * (size_t)n, s));
+    NEKB_CUDA(cudaMemsetAsync(res, 0, sizeof(double) * (size_t)n, s));
+    double rho1 = 1.0;
+    const double div0 = sqrt(gm_glsc3(r.p, wt, r.p, n) / c.volvm1);
+    if (G.param21 < 0) tolpss = fabs(G.param21) * div0;
+    int iter = 0;
+    for (int k = 1; k <= maxit; k++) {
+        h1mg_solve_dev(z.p, r.p);                                               // z = M^-1 r (masks r in place, as the reference)
+        gm_sub3_kernel<<<grid, 256, 0, s>>>(r1.p, r1.p, r.p, n);                // sub2(r1,r)
+        NEKB_LAUNCHED();
+        const double rho0 = rho1;
+        rho1 = gm_glsc3(z.p, wt, r.p, n);
+        const double rho2 = -gm_glsc3(z.p, wt, r1.p, n);
+        const double beta = rho2 / rho0;
+        NEKB_CUDA(cudaMemcpyAsync(r1.p, r.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+        gm_cmult2_kernel<<<grid, 256, 0, s>>>(p.p, p.p, beta, n);               // add2s1(p,z,beta): p = beta p + z
+        NEKB_LAUNCHED();
+        proj_axpy(p.p, z.p, 1.0, n);
+        gm_ax(w.p, p.p, h1, h2, G.pmask.p, M.nel, gsh);                          // w = A p
+        const double den = gm_glsc3(w.p, wt, p.p, n);
+        const double alpha = rho1 / den;
+        proj_axpy(res, p.p, alpha, n);
+        proj_axpy(r.p, w.p, -alpha, n);
+        const double rnorm = sqrt(gm_glsc3(r.p, r.p, wt, n) / c.volvm1);
+        iter++;
+        if (rnorm < tolpss) break;
+    }
+    gm_ortho(res, n);
+    NEKB_CUDA(cudaStreamSynchronize(s));
+    return iter;
+}
+void hmh_flex_cg_(double *res, const double *h1, const double *h2, const double *wt, int *iter)
+{
+    guard_fortran("hmh_flex_cg", [&] {
+        require_init();
+        Ctx &c = ctx();
+        H1mg &M = h1mg();
+        NEKB_REQUIRE(M.ready, "hmh_flex_cg: nekb_h1mg_setup has not been called");
+        const size_t n = (size_t)M.nel * c.nxyz;
+        for (int k = 0; k < 4; k++) c.stage[k].ensure(n);
+        const double *src[4] = {res, h1, h2, wt};
+        for (int k = 0; k < 4; k++)
+            NEKB_CUDA(cudaMemcpyAsync(c.stage[k].p, src[k], n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        bool ifh2 = false;
+        for (size_t t = 0; t < n && !ifh2; t++) ifh2 = h2[t] != 0.0;
+        *iter = hmh_flex_cg_body(c.stage[0].p, c.stage[1].p, ifh2 ? c.stage[2].p : nullptr, c.stage[3].p, *iter);
+        NEKB_CUDA(cudaMemcpyAsync(res, c.stage[0].p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
 void hmh_gmres_(double *res, const double *h1, const double *h2, const double *wt, int *iter)
 {
     guard_fortran("hmh_gmres", [&] {
@@ -1735,8 +1809,10 @@ static int hsolve_dev(const char *name, size_t name_len, double *u, double *r, c
             t = chktcg1_dev(t, r, h1, ifh2 ? h2 : nullptr, vmk, vml, binv_chk, nel, vol);
         }
         if (pres) {                                                            // cggo :641-657
-            NEKB_REQUIRE(h1mg().ready && c.param[42] == 0.0, "hsolve('PRES'): needs nekb_h1mg_setup and param(42) = 0 (GMRES)");
+            NEKB_REQUIRE(h1mg().ready && (c.param[42] == 0.0 || c.param[42] == 2.0),
+                         "hsolve('PRES'): needs nekb_h1mg_setup and param(42) = 0 (GMRES) or 2 (flexible CG)");
             NEKB_CUDA(cudaMemcpyAsync(u, r, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c.stream));
+            if (c.param[42] == 2.0) return hmh_flex_cg_body(u, h1, ifh2 ? h2 : nullptr, vml, maxit);
             return hmh_gmres_body(u, h1, ifh2 ? h2 : nullptr, vml, maxit);
         }
         CggoArgs a{u, r, h1, h2, vmk, vml, bi, field_handle(), nel, vol, c.istep};

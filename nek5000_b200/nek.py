@@ -527,6 +527,13 @@ def hmh_gmres(res: np.ndarray, h1: np.ndarray, h2: np.ndarray, wt: np.ndarray, m
     return int(it.value)
 
 
+def hmh_flex_cg(res: np.ndarray, h1: np.ndarray, h2: np.ndarray, wt: np.ndarray, maxit: int) -> int:
+    """core/hmholtz.f:2164 hmh_flex_cg(res,h1,h2,wt,iter): res is overwritten with the solution; returns iter."""
+    it = C.c_int(maxit)
+    lib().hmh_flex_cg_(_ptr(res), _ptr(h1), _ptr(h2), _ptr(wt), C.byref(it))
+    return int(it.value)
+
+
 # --------------------------------------------------------------------------------------------- device arrays
 class DevArray:
     """A device buffer owned through the C-ABI helpers (section E of the header)."""

@@ -547,6 +547,36 @@ def hmh_gmres(case, mg, res, h1, h2, pmask, wt, tol, maxit, m=30, ifvcor=False, 
     return x, it
 
 
+def hmh_flex_cg(case, mg, res, h1, h2, pmask, wt, tol, maxit, ifvcor=False):
+    """core/hmholtz.f:2164-2290: flexible PCG with h1mg_solve (param(42) = 2); `tol` is tolpss.  Returns (x, iterations)."""
+    n = case.n
+    vol = case.bm1().sum()
+    glsc3 = lambda a, b: float(np.sum(a * wt * b))
+    ax = lambda x: case.dssum(case.axhelm(x, h1, h2)) * pmask
+    r, r1, p, x = res.copy(), np.zeros(n), np.zeros(n), np.zeros(n)
+    rho1, it = 1.0, 0
+    for _ in range(maxit):
+        z = mg.solve(r)                       # masks r in place, as the reference does
+        r1 = r1 - r
+        rho0 = rho1
+        rho1 = glsc3(z, r)
+        rho2 = -glsc3(z, r1)
+        beta = rho2 / rho0
+        r1 = r.copy()
+        p = beta * p + z
+        w = ax(p)
+        alpha = rho1 / glsc3(w, p)
+        x = x + alpha * p
+        r = r - alpha * w
+        rnorm = np.sqrt(float(np.sum(r * r * wt)) / vol)
+        it += 1
+        if rnorm < tol:
+            break
+    if ifvcor:
+        x = x - x.sum() / n
+    return x, it
+
+
 # ----------------------------------------------------------------------------- fdm_h1 (single-level Schwarz / FDM)
 class FdmH1:
     """core/hmholtz.f:1028-1112 set_fdm_prec_h1A_gen, :1114-1220 set_fdm_prec_h1A_els, :1222-1290 set_fdm_prec_h1b and

@@ -150,7 +150,10 @@ def _pressure(name):
     R.set("tolps", tol), R.set("istep", 1)
     x, it = b.copy(), C.c_int(100)
     R.call("hmh_gmres", x, h1, h2, case.mult, it)
+    xf, itf = b.copy(), C.c_int(100)
+    R.call("hmh_flex_cg", xf, h1, h2, case.mult, itf)            # core/hmholtz.f:2164 (param(42) = 2)
     return dict(pmask=pmask, rhs=rhs, rhs_out=r, z=z, b=b, x=x, it=np.array([it.value]), tol=np.array([tol]),
+                x_fcg=xf, it_fcg=np.array([itf.value]),
                 ifvcor=np.array([int(R.get("ifvcor"))]), volvm1=np.array([R.get("volvm1")]))
 
 

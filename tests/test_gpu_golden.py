@@ -160,6 +160,9 @@ def test_h1mg_solve_and_hmh_gmres_against_the_reference(nek, name, mesh):
     it = nek.hmh_gmres(res, np.ones(n), np.zeros(n), gc["vmult"], 100)
     assert it == g["it"][0]                                                    # identical iteration count
     assert relmax(res, g["x"]) <= TOL_FIELD
+    res = g["b"].copy()                                                        # flexible PCG (param(42) = 2)
+    it = nek.hmh_flex_cg(res, np.ones(n), np.zeros(n), gc["vmult"], 100)
+    assert it == g["it_fcg"][0] and relmax(res, g["x_fcg"]) <= 1e-9
 
 
 def test_fdm_h1_and_schwarz_cggo_against_the_reference(nek):

@@ -114,6 +114,8 @@ def test_h1mg_solve_and_hmh_gmres(name, mesh):
     x, it = hsmg.hmh_gmres(c, mg, g["b"], np.ones(n), np.zeros(n), g["pmask"], c.mult, float(g["tol"][0]), 100, ifvcor=null)
     assert it == g["it"][0] and it < 40                          # identical iteration count
     assert relmax(x, g["x"]) <= 1e-11
+    x, it = hsmg.hmh_flex_cg(c, mg, g["b"], np.ones(n), np.zeros(n), g["pmask"], c.mult, float(g["tol"][0]), 100, ifvcor=null)
+    assert it == g["it_fcg"][0] and relmax(x, g["x_fcg"]) <= 1e-10      # hmh_flex_cg (param(42) = 2)
 
 
 def test_fdm_h1_and_cggo_schwarz_branch():
