@@ -69,6 +69,17 @@ class Mesh2:
         tb, _ = self.opbinv(self.opgradt(wp), h2inv, masks)
         return self.opdiv(tb)
 
+    def cdabdtp_helm(self, wp, h1, h2, masks, tolhs, nmxv, istep=20):
+        """intype = 0 / -1: the three velocity solves of ophinv (hmholtz -> cggo) between D^T and D."""
+        c = self.case
+        ta = self.opgradt(wp)
+        tb = []
+        for k in range(3):
+            rhs = c.dssum(ta[k]) * masks[k]
+            x, _ = c.cggo(rhs, h1, h2, mask=masks[k], tin=tolhs, maxit=nmxv, istep=istep)
+            tb.append(x)
+        return self.opdiv(tb)
+
 
 def chktcg2(M, tol, res, ifvcor=False, prelax=0.0, tolpdf=0.0):
     """core/navier1.f:1089-1154."""

@@ -331,6 +331,13 @@ def ref_eop():
     R.call("opbinv", bo[0], bo[1], bo[2], bi[0], bi[1], bi[2], h2inv)
     ap = np.zeros(n2)
     R.call("cdabdtp", ap, p, np.ones(n), 1.0 / h2inv, h2inv, 1)
+    # intype = -1: D (h1 A + h2 B)^-1 D^T, the velocity solves through ophinv with (tolhs, nmxv)
+    R.set("tolhs", 1e-11), R.set("nmxv", 300), R.set("istep", 20), R.set("ifield", 1), R.set("ifstrs", 0)
+    R.var("param")[21] = 0.0
+    R.var("param")[92] = 0.0
+    apm = np.zeros(n2)
+    R.call("cdabdtp", apm, p, np.ones(n), 1.0 / h2inv, h2inv, -1)
+    out["ap_m1"] = apm
     out.update(p=p, gx=o[0], gy=o[1], gz=o[2], ux=u[0], uy=u[1], uz=u[2], div=d, h2inv=h2inv, bo1=bo[0], bo2=bo[1], bo3=bo[2],
                bi1=bi[0], bi2=bi[1], bi3=bi[2], ap=ap)
     return out

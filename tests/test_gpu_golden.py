@@ -430,6 +430,13 @@ def test_pnpn2_pressure_operator_against_the_reference(nek):
     ap = np.zeros(n2)
     nek.cdabdtp(ap, g["p"], np.ones(n), 1.0 / g["h2inv"], g["h2inv"], 1)
     assert relmax(ap, g["ap"]) <= TOL_APPLY
+    # intype = -1: the three velocity solves (fused 3-right-hand-side PCG, tolhs = 1e-11, nmxv = 300) between D^T and D
+    nek.set_mesh2(6, g["ixm12"], g["dxm12"], g["w3m2"], [g[k] for k in refcases.MET9], g["bm2"], g["bm2inv"],
+                  float(g["volvm2"][0]), 1e-11, 300, case.nel, False)
+    nek.set_param(22, 0.0)
+    apm = np.zeros(n2)
+    nek.cdabdtp(apm, g["p"], np.ones(n), 1.0 / g["h2inv"], g["h2inv"], -1)
+    assert relmax(apm, g["ap_m1"]) <= 1e-8
     # E is symmetric positive semi-definite: (q, E p) = (p, E q), (p, E p) > 0
     rng = np.random.default_rng(2)
     q = rng.standard_normal(n2)

@@ -246,6 +246,8 @@ def test_pnpn2_pressure_operator_pieces():
     for k in range(3):
         assert np.array_equal(bi[k], g[f"bi{k + 1}"]) and relmax(bo[k], g[f"bo{k + 1}"]) <= 1e-14
     assert relmax(M.cdabdtp(g["p"], g["h2inv"], masks), g["ap"]) <= 1e-12
+    n = c.n
+    assert relmax(M.cdabdtp_helm(g["p"], np.ones(n), 1.0 / g["h2inv"], masks, 1e-11, 300), g["ap_m1"]) <= 1e-9   # intype = -1
 
 
 def test_uzawa_gmres_on_the_pnpn2_pressure_operator():
