@@ -254,7 +254,7 @@ def hsolve_inputs(case, pres=False):
     h1 = np.ones(n) if pres else 1.0 + 0.3 * rng.random(n)
     h2 = np.zeros(n) if pres else 20.0 * (5.0 + rng.random(n))
     calls = []
-    for k in range(4 if pres else 7):
+    for k in range(4 if pres else 11):     # 11 > mmx + 1: the space saturates at mmx = 8 and the oldest vector is rotated out
         rhs = f[0] + np.sin(0.3 * k) * f[1] + 0.05 * k * k * f[2]
         calls.append((rhs, h1, h2 * (1.1 if (k >= 4 and not pres) else 1.0), 10 + k))
     return calls
@@ -292,7 +292,8 @@ def _ref_hsolve(name, pres):
 
 def ref_hsolve():
     """core/navier4.f:562-634 hsolve with residual projection (project1/project2, :636-1199) around hmhzpf -> cggo (Jacobi
-    PCG): seven successive 'VELX' solves; the space grows to mmx = 8 vectors and is rebuilt when h2 changes."""
+    PCG): eleven successive 'VELX' solves; the space grows to mmx = 8 vectors, is rebuilt when h2 changes (call 4) and then
+    rotates its oldest vector out."""
     return _ref_hsolve("VELX", False)
 
 

@@ -270,6 +270,20 @@ def test_ophinv_fused_three_rhs_against_the_reference(nek):
             assert relmax(o[k], g[f"o{k + 1}{key}"]) <= ftol, (key, k)
 
 
+def test_ophinv_with_a_zero_component(nek):
+    """cggo returns at once with niterhm = 0 and x = 0 for a zero right-hand side (hmholtz.f:697-699): in the fused solve that
+    component is switched off from the start while the other two run to their own counts."""
+    g, case = G["ophinv"], refcases.case_of("ophinv")
+    _register_ophinv(nek, g, case)
+    n = case.n
+    o = [np.ones(n) for _ in range(3)]
+    i = [g["i1"].copy(), np.zeros(n), g["i3"].copy()]
+    its = nek.ophinv(*o, *i, g["h1"], g["h2"], 1e-8, 300)
+    assert its[1] == 0 and not o[1].any()
+    assert its[0] == g["its"][0] and its[2] == g["its"][2]
+    assert relmax(o[0], g["o1"]) <= TOL_CONVERGED and relmax(o[2], g["o3"]) <= TOL_CONVERGED
+
+
 def test_fused_and_stock_cggo_agree(nek):
     """The fused path (hcg.cuh, default for lx1 = 8 Jacobi solves) against the kernel-per-statement cggo_run (NEKB_HCG=0 is
     read once per process, so the stock path is reached through a right-hand side the fused path declines: here a mask that
@@ -340,9 +354,10 @@ def test_lx1_6_generic_kernels_against_the_reference():
 
 
 def test_hsolve_with_residual_projection_against_the_reference(nek):
-    """core/navier4.f:562-634 hsolve + project1/project2 (:636-1199), device-resident approximation space: seven successive
-    'VELX' solves (h2 changes at call 4).  Iteration counts within 1 of the reference's 64 58 55 6 49 43 38 (the projected
-    right-hand side is a difference of nearly equal vectors, its sums run in another order), space size m identical."""
+    """core/navier4.f:562-634 hsolve + project1/project2 (:636-1199), device-resident approximation space: eleven successive
+    'VELX' solves (h2 changes at call 4; the space saturates at mmx = 8 and drops rank-deficient vectors afterwards: m = 1 2 3 4
+    5 6 7 8 7 8 7).  Iteration counts within 1 of the reference's 64 58 55 6 49 43 38 6 5 8 1 (the projected right-hand side is
+    a difference of nearly equal vectors, its sums run in another order), space size m identical."""
     g, case = G["hsolve"], refcases.case_of("core")
     gc = G["core"]
     register_core(nek, gc, case)
