@@ -84,6 +84,25 @@ inline void comm_allreduce_sum(double *dev, int count) { comm_allreduce(dev, cou
 inline void comm_allreduce_max(double *dev, int count) { comm_allreduce(dev, count, NCCL_MAX); }
 inline void comm_allreduce_min(double *dev, int count) { comm_allreduce(dev, count, NCCL_MIN); }
 
+// All ranks' streams are drained (each rank syncs its own stream, then joins a one-word all-reduce).  Needed before memory
+// that peers write into (the peer-memory gs exchange: receive areas, consumed-flags) is released.
+inline void comm_quiesce()
+{
+    Ctx &c = ctx();
+    if (!c.stream) return;
+    cudaStreamSynchronize(c.stream);
+    if (c.nranks > 1 && c.nccl_comm != nullptr && c.sc.p != nullptr) {
+        NEKB_NCCL(nccl().AllReduce(&c.sc.p->work[3], &c.sc.p->work[3], 1, NCCL_FLOAT64, NCCL_MAX, comm_handle(), c.stream));
+        cudaStreamSynchronize(c.stream);
+    }
+}
+// release a gs handle whose exchange memory may still be written by peers
+inline void gs_release(GsMap &h)
+{
+    if (h.p2p) comm_quiesce();
+    h = GsMap();
+}
+
 // ---- host collectives used by the setup code (numbering, shared-id discovery) ----------------------------
 // Callbacks registered with nekb_set_transport win (MPI in a Fortran build, gloo in the CPU tests); otherwise
 // the bytes are staged through device memory and moved with NCCL.

@@ -1548,8 +1548,8 @@ inline void h1mg_setup_run(H1mg &M, const int *fbc, const double *xm1, const dou
     cudaStream_t s = c.stream;
     crs_release_graph(M);
     for (MgLevel &L : M.lev) {  // release the handles of a previous setup
-        if (L.gs >= 0 && L.gs < (int)c.gs.size()) c.gs[L.gs] = GsMap();
-        if (L.gs_face >= 0 && L.gs_face < (int)c.gs.size()) c.gs[L.gs_face] = GsMap();
+        if (L.gs >= 0 && L.gs < (int)c.gs.size()) gs_release(c.gs[L.gs]);
+        if (L.gs_face >= 0 && L.gs_face < (int)c.gs.size()) gs_release(c.gs[L.gs_face]);
     }
     M = H1mg();
     NEKB_REQUIRE(c.have_geom, "h1mg_setup: geometry must be registered first (nekb_set_geom*)");
@@ -1671,7 +1671,7 @@ inline void h1mg_setup_run(H1mg &M, const int *fbc, const double *xm1, const dou
         }
         gs_op(fine_gs, ld.p, 1, nullptr);
         ld.download(l.data(), l.size(), s);
-        if (temp_gs) c.gs[fine_gs] = GsMap();
+        if (temp_gs) gs_release(c.gs[fine_gs]);
         for (int64_t e = 0; e < nel; e++) {
             const double *le = l.data() + e * n3;
             M.ll_host[0 * (size_t)nel + e] = le[at(0, 1, 1)] - M.lm_host[0 * (size_t)nel + e];

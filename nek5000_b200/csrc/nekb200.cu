@@ -169,7 +169,10 @@ void nekb_finalize(void)
 {
     Ctx &c = ctx();
     if (!c.inited) return;
-    cudaStreamSynchronize(c.stream);
+    try {
+        comm_quiesce();   // peers may still be raising flags in this rank's exchange memory
+    } catch (...) {
+    }
     bp5case() = Bp5Case();
     crs_release_graph();
     h1mg() = H1mg();
@@ -578,7 +581,7 @@ int nekb_gs_free(int handle)
 {
     return guard([&] {
         gs_get(handle);
-        ctx().gs[handle] = GsMap();
+        gs_release(ctx().gs[handle]);
     });
 }
 int nekb_gs_info(int handle, int64_t *ngroups, int64_t *nmembers, int64_t *nshared_remote)
@@ -732,7 +735,7 @@ void fgslib_gs_free_(const int *handle)
 {
     guard_fortran("fgslib_gs_free", [&] {
         gs_get(*handle);
-        ctx().gs[*handle] = GsMap();
+        gs_release(ctx().gs[*handle]);
     });
 }
 
@@ -1114,8 +1117,8 @@ void nekb_h1mg_free(void)
     crs_release_graph();
     for (H1mg *M : {&h1mg(), &hsmg2()}) {
         for (MgLevel &L : M->lev) {
-            if (L.gs >= 0 && L.gs < (int)ctx().gs.size()) ctx().gs[L.gs] = GsMap();
-            if (L.gs_face >= 0 && L.gs_face < (int)ctx().gs.size()) ctx().gs[L.gs_face] = GsMap();
+            if (L.gs >= 0 && L.gs < (int)ctx().gs.size()) gs_release(ctx().gs[L.gs]);
+            if (L.gs_face >= 0 && L.gs_face < (int)ctx().gs.size()) gs_release(ctx().gs[L.gs_face]);
         }
         *M = H1mg();
     }

@@ -563,7 +563,7 @@ inline void bp5_setup(int nelx, int nely, int nelz, int px, int py, int pz, doub
     NEKB_REQUIRE(nelx % px == 0 && nely % py == 0 && nelz % pz == 0, "bp5_setup: bricks must divide the box");
     NEKB_REQUIRE(c.nx >= 2, "bp5_setup: lx1 must be >= 2");
     if (b.gs_handle >= 0) {
-        gs_get(b.gs_handle) = GsMap();
+        gs_release(gs_get(b.gs_handle));
         b.gs_handle = -1;
     }
     BoxDesc d;
