@@ -124,10 +124,10 @@ def ref_bp5():
                 r1=v("r1")[:n].copy(), u1=v("u1")[:n].copy())
 
 
-def _pressure(name):
+def _pressure(name, nx=8):
     """set_overlap -> hsmg_setup/h1mg_setup/set_up_h1_crs (navier6.f:29-101, hsmg.f:22-47,2234-2270, navier8.f:83-233),
     h1mg_solve (hsmg.f:1855-1949) and hmh_gmres (gmres.f:304-545) incl. chktcg1 and ortho."""
-    case = case_of(name)
+    case = case_of(name, nx)
     rc = _ref(case)
     R, n = rc.R, case.n
     R.set("ifmgrid", 1)
@@ -163,6 +163,23 @@ def ref_h1mg():
 
 def ref_h1mg_neumann():
     return _pressure("neumann")
+
+
+def ref_h1mg_lx6():
+    """The same at lx1 = 6 (multigrid orders 1, 3, 5; core/hsmg.f:2272-2337)."""
+    return _pressure("core", 6)
+
+
+def ref_periodic():
+    """setupds / setvert3d (core/navier8.f:2004-2360) and the multiplicity on a box that is periodic in x and z: the vertex
+    ids identify opposite sides, so faces, edges and corners wrap around."""
+    case = oracle.Case(4, 3, 2, nx=8, periodic=(1, 0, 1))
+    rc = _ref(case)
+    R, n = rc.R, case.n
+    u = np.random.default_rng(9).standard_normal(n)
+    v = u.copy()
+    R.call("dssum", v, 8, 8, 8)
+    return dict(glo_num=R.var("glo_num").ravel(order="F")[:n].copy(), vmult=rc.fld("vmult"), v1mask=rc.fld("v1mask"), u=u, dssum=v)
 
 
 def ref_fdm():
@@ -390,7 +407,7 @@ def ref_map():
     return out
 
 
-REFERENCE = dict(core=ref_core, core_lx6=ref_core_lx6, map=ref_map, eop=ref_eop, uzawa=ref_uzawa, hsolve=ref_hsolve, hsolve_pres=ref_hsolve_pres, ophinv=ref_ophinv, bp5=ref_bp5, h1mg=ref_h1mg, h1mg_neumann=ref_h1mg_neumann, fdm=ref_fdm, pnpn2=ref_pnpn2)
+REFERENCE = dict(core=ref_core, core_lx6=ref_core_lx6, h1mg_lx6=ref_h1mg_lx6, periodic=ref_periodic, map=ref_map, eop=ref_eop, uzawa=ref_uzawa, hsolve=ref_hsolve, hsolve_pres=ref_hsolve_pres, ophinv=ref_ophinv, bp5=ref_bp5, h1mg=ref_h1mg, h1mg_neumann=ref_h1mg_neumann, fdm=ref_fdm, pnpn2=ref_pnpn2)
 
 
 def reference_all():

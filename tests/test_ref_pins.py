@@ -40,7 +40,7 @@ def test_golden_file_is_what_the_reference_computes_now(name):
     from oracle import ref
     if name in ("pnpn2", "eop") and not ref.available(8, 6, 64):
         pytest.skip("Pn-Pn-2 build of oracle/_ref not available")
-    if name == "core_lx6" and not ref.available(6, 6, 64):
+    if name in ("core_lx6", "h1mg_lx6") and not ref.available(6, 6, 64):
         pytest.skip("lx1 = 6 build of oracle/_ref not available")
     live = refcases.REFERENCE[name]()
     assert set(live) == set(G[name])
@@ -265,3 +265,28 @@ def test_uzawa_gmres_on_the_pnpn2_pressure_operator():
     x, it = pnpn2.uzawa_gmres(M, lambda w: h.solve(w), g["rhs"], g["h2inv"], masks, 1e-7, 0.0, istep=5)
     assert it == g["it"][0]
     assert relmax(x, g["x"]) <= 1e-9 and relmax(x, g["pe"]) <= 1e-6
+
+
+def test_h1mg_and_gmres_at_lx1_6():
+    """Multigrid orders (1, 3, 5) at lx1 = 6: the restatement against the reference's own h1mg_solve / hmh_gmres / hmh_flex_cg."""
+    g, c = G["h1mg_lx6"], refcases.case_of("core", 6)
+    mg = hsmg.H1MG(c, refcases.fbc_of("core", c), null_space=False)
+    assert mg.mg_nx == [1, 3, 5]
+    r = g["rhs"].copy()
+    assert relmax(mg.solve(r), g["z"]) <= 1e-12 and np.array_equal(r, g["rhs_out"])
+    n = c.n
+    x, it = hsmg.hmh_gmres(c, mg, g["b"], np.ones(n), np.zeros(n), g["pmask"], c.mult, float(g["tol"][0]), 100)
+    assert it == g["it"][0] and relmax(x, g["x"]) <= 1e-11
+    x, it = hsmg.hmh_flex_cg(c, mg, g["b"], np.ones(n), np.zeros(n), g["pmask"], c.mult, float(g["tol"][0]), 100)
+    assert it == g["it_fcg"][0] and relmax(x, g["x_fcg"]) <= 1e-10
+
+
+def test_periodic_numbering_bit_exact():
+    g = G["periodic"]
+    c = oracle.Case(4, 3, 2, nx=8, periodic=(1, 0, 1))
+    assert np.array_equal(g["glo_num"], c.glo_num)                 # integer: bit-exact, wrap-around included
+    assert np.array_equal(g["vmult"], c.mult) and np.array_equal(g["v1mask"], c.mask)
+    assert np.array_equal(g["dssum"], c.dssum(g["u"]))
+    # two elements across a periodic direction: setvert3d keys edges / faces by their vertex ids, so the two z-edges between
+    # the same pair of vertices share their numbers (the reference's behaviour, reproduced bit for bit)
+    assert (1.0 / g["vmult"]).max() == 8.0 and len(np.unique(g["glo_num"])) - 1 < 3440   # 3440 = distinct surface nodes
