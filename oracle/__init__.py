@@ -118,7 +118,10 @@ class Case:
     """
 
     def __init__(self, nelx, nely, nelz, nx=8, periodic=(0, 0, 0), dirichlet=(1, 1, 1, 1, 1, 1), np_ranks=1,
-                 lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0), deform=0.0, rescale=True):
+                 lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0), deform=0.0, rescale=True, vertex_map=None):
+        """rescale: True = usrdat2 of bp5.usr:40-44 (rescale_x to [0,1]), (a, b) = rescale_x to [a,b] (ethier.usr:224-228),
+        False = none.  vertex_map(xc, yc, zc) -> (xc, yc, zc) moves the element vertices before the GLL points are
+        generated, the way a case's usrdat does (examples/turbChannel/turbChannel.usr:334-358)."""
         L = lib()
         self.nx, self.nel = nx, nelx * nely * nelz
         self.nelx, self.nely, self.nelz = nelx, nely, nelz
@@ -135,11 +138,14 @@ class Case:
         self.vertex = np.zeros(8 * E, dtype=np.int64)
         L.nko_box_mesh(nelx, nely, nelz, np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64), per,
                        self.xc, self.yc, self.zc, self.vertex)
+        if vertex_map is not None:
+            self.xc, self.yc, self.zc = (np.ascontiguousarray(a, dtype=np.float64) for a in vertex_map(self.xc, self.yc, self.zc))
         self.xm1, self.ym1, self.zm1 = np.zeros(self.n), np.zeros(self.n), np.zeros(self.n)
         L.nko_xyzlin(nx, E, self.z, self.xc, self.yc, self.zc, self.xm1, self.ym1, self.zm1)
         if rescale:  # bp5.usr:40-44 usrdat2
+            ra, rb = (0.0, 1.0) if rescale is True else rescale
             for a in (self.xm1, self.ym1, self.zm1):
-                L.nko_rescale_x(a, self.n, 0.0, 1.0)
+                L.nko_rescale_x(a, self.n, float(ra), float(rb))
         if deform:  # smooth, continuous deformation so all six factors are exercised
             x, y, z = self.xm1.copy(), self.ym1.copy(), self.zm1.copy()
             s = np.sin(np.pi * x) * np.sin(np.pi * y) * np.sin(np.pi * z)

@@ -305,9 +305,14 @@ class H1MG:
         """core/hsmg.f:896-929 hsmg_do_fast (3-D): e = S D S^T r on (nh+2)^3 tiles."""
         f = self.fdm[l]
         S, D = f["S"], f["D"]
-        t = np.einsum("eia,ejb,ekc,ekji->ecba", S[:, 0], S[:, 1], S[:, 2], r_ext)
+        # three successive 1-D contractions in the order of hsmg_tnsr3d_el (core/hsmg.f:309-324): r, then s, then t
+        t = np.einsum("eia,ekji->ekja", S[:, 0], r_ext)
+        t = np.einsum("ejb,ekja->ekba", S[:, 1], t)
+        t = np.einsum("ekc,ekba->ecba", S[:, 2], t)
         t = D * t
-        return np.einsum("eai,ebj,eck,ekji->ecba", S[:, 0], S[:, 1], S[:, 2], t)
+        t = np.einsum("eai,ekji->ekja", S[:, 0], t)
+        t = np.einsum("ebj,ekja->ekba", S[:, 1], t)
+        return np.einsum("eck,ekba->ecba", S[:, 2], t)
 
     # -- hsmg_extrude (core/hsmg.f:368-423, 3-D) ------------------------------------------------
     @staticmethod

@@ -125,9 +125,44 @@ def ref_bp5():
 
 
 def _pressure(name, nx=8):
+    return _pressure_case(case_of(name, nx))
+
+
+def channel_case(dims=(4, 4, 4), nx=8):
+    """The mesh of examples/turbChannel (BASELINE config 5) at a size the 64-element reference build holds: genbox box that
+    is periodic in x and z with walls in y (turbChannel.box), element vertices moved by the case's usrdat
+    (turbChannel.usr:334-358: x scaled to XLEN = 2 pi, z to ZLEN = pi, y = tanh(BETAM (2y-1)) / tanh(BETAM), BETAM = 2.4)
+    before the GLL points are generated."""
+    def usrdat(xc, yc, zc):
+        xs, ys, zs = 2 * np.pi / (xc.max() - xc.min()), 1.0 / (yc.max() - yc.min()), np.pi / (zc.max() - zc.min())
+        return xs * xc, np.tanh(2.4 * (2 * (ys * yc) - 1)) / np.tanh(2.4), zs * zc
+    return oracle.Case(*dims, nx=nx, periodic=(1, 0, 1), dirichlet=(1, 1, 1, 1, 1, 1), rescale=False, vertex_map=usrdat)
+
+
+def channel_fbc(case):
+    """get_fast_bc codes of the channel: periodic sides 0, walls 2 (Neumann for the pressure)."""
+    return hsmg.box_fbc(case, (0, 0, 2, 2, 0, 0))
+
+
+def ethier_case(nx=8):
+    """The box of short_tests/ethier (BASELINE config 2; ethier.box: 3 x 3 x 3 elements, every side 'v  '), rescaled to
+    [-1, 1]^3 by the case's usrdat2 (ethier.usr:220-228)."""
+    return oracle.Case(3, 3, 3, nx=nx, lo=(-1.0, -1.0, -1.0), hi=(1.0, 1.0, 1.0), rescale=(-1.0, 1.0))
+
+
+def geometry_of(rc):
+    """What the device side registers for a case, as the reference computed it."""
+    R = rc.R
+    out = dict(vmult=rc.fld("vmult"), bm1=rc.fld("bm1"), binvm1=rc.fld("binvm1"), v1mask=rc.fld("v1mask"),
+               zgm1=R.var("zgm1")[:, 0].copy(), wxm1=R.var("wxm1").copy(), dxm1=R.var("dxm1").copy(order="C"))
+    for i in range(1, 7):
+        out[f"g{i}m1"] = rc.fld(f"g{i}m1")
+    return out
+
+
+def _pressure_case(case, with_geometry=False):
     """set_overlap -> hsmg_setup/h1mg_setup/set_up_h1_crs (navier6.f:29-101, hsmg.f:22-47,2234-2270, navier8.f:83-233),
     h1mg_solve (hsmg.f:1855-1949) and hmh_gmres (gmres.f:304-545) incl. chktcg1 and ortho."""
-    case = case_of(name, nx)
     rc = _ref(case)
     R, n = rc.R, case.n
     R.set("ifmgrid", 1)
@@ -152,9 +187,38 @@ def _pressure(name, nx=8):
     R.call("hmh_gmres", x, h1, h2, case.mult, it)
     xf, itf = b.copy(), C.c_int(100)
     R.call("hmh_flex_cg", xf, h1, h2, case.mult, itf)            # core/hmholtz.f:2164 (param(42) = 2)
-    return dict(pmask=pmask, rhs=rhs, rhs_out=r, z=z, b=b, x=x, it=np.array([it.value]), tol=np.array([tol]),
-                x_fcg=xf, it_fcg=np.array([itf.value]),
-                ifvcor=np.array([int(R.get("ifvcor"))]), volvm1=np.array([R.get("volvm1")]))
+    out = dict(pmask=pmask, rhs=rhs, rhs_out=r, z=z, b=b, x=x, it=np.array([it.value]), tol=np.array([tol]),
+               x_fcg=xf, it_fcg=np.array([itf.value]),
+               ifvcor=np.array([int(R.get("ifvcor"))]), volvm1=np.array([R.get("volvm1")]))
+    if with_geometry:
+        out.update(geometry_of(rc))
+        out.update(_velocity_solve(rc, case))
+    return out
+
+
+def _velocity_solve(rc, case):
+    """One velocity Helmholtz solve of a time step on the same mesh: hmholtz('VELX') (hmholtz.f:2-69 -> cggo :611-846) with
+    h1 = 1/Re, h2 = bd(1)/dt (the constants of ethier.par: viscosity 0.01, dt 2e-3) on an un-assembled right-hand side."""
+    R, n = rc.R, case.n
+    rng = np.random.default_rng(11)
+    h1, h2 = np.full(n, 0.01), np.full(n, 1.0 / 2e-3)
+    rhs = rc.fld("bm1") * rng.standard_normal(n)
+    x, r = np.zeros(n), rhs.copy()
+    R.var("param")[21] = 0.0
+    R.set("ifsolv", 0), R.set("kfldfdm", -1), R.set("istep", 1), R.set("ifield", 1)
+    R.call("hmholtz", "VELX", x, r, h1, h2, rc.fld("v1mask"), rc.fld("vmult"), 1, 1e-9, 200, 1)
+    return dict(vel_h1=h1[:1].copy(), vel_h2=h2[:1].copy(), vel_rhs=rhs, vel_x=x, vel_it=np.array([R.get("niterhm")]))
+
+
+def ref_channel():
+    """BASELINE config 5 (turbChannel mesh, 4 x 4 x 4 elements): pressure multigrid / GMRES / flexible CG with the constant
+    null space on a periodic, wall-stretched box, and one velocity Helmholtz solve."""
+    return _pressure_case(channel_case(), with_geometry=True)
+
+
+def ref_ethier():
+    """BASELINE config 2 (ethier box, 27 elements on [-1,1]^3, all sides 'v  '): the same set."""
+    return _pressure_case(ethier_case(), with_geometry=True)
 
 
 def ref_h1mg():
@@ -407,7 +471,7 @@ def ref_map():
     return out
 
 
-REFERENCE = dict(core=ref_core, core_lx6=ref_core_lx6, h1mg_lx6=ref_h1mg_lx6, periodic=ref_periodic, map=ref_map, eop=ref_eop, uzawa=ref_uzawa, hsolve=ref_hsolve, hsolve_pres=ref_hsolve_pres, ophinv=ref_ophinv, bp5=ref_bp5, h1mg=ref_h1mg, h1mg_neumann=ref_h1mg_neumann, fdm=ref_fdm, pnpn2=ref_pnpn2)
+REFERENCE = dict(channel=ref_channel, ethier=ref_ethier, core=ref_core, core_lx6=ref_core_lx6, h1mg_lx6=ref_h1mg_lx6, periodic=ref_periodic, map=ref_map, eop=ref_eop, uzawa=ref_uzawa, hsolve=ref_hsolve, hsolve_pres=ref_hsolve_pres, ophinv=ref_ophinv, bp5=ref_bp5, h1mg=ref_h1mg, h1mg_neumann=ref_h1mg_neumann, fdm=ref_fdm, pnpn2=ref_pnpn2)
 
 
 def reference_all():

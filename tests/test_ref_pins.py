@@ -290,3 +290,37 @@ def test_periodic_numbering_bit_exact():
     # two elements across a periodic direction: setvert3d keys edges / faces by their vertex ids, so the two z-edges between
     # the same pair of vertices share their numbers (the reference's behaviour, reproduced bit for bit)
     assert (1.0 / g["vmult"]).max() == 8.0 and len(np.unique(g["glo_num"])) - 1 < 3440   # 3440 = distinct surface nodes
+
+
+@pytest.mark.parametrize("name", ["channel", "ethier"])
+def test_baseline_config_meshes(name):
+    """BASELINE configs 5 and 2 at reference-build size: the turbChannel mesh (periodic x/z, tanh-stretched walls, 4^3
+    elements) and the ethier box (27 elements on [-1,1]^3).  Geometry, masks and the velocity Helmholtz solve bit for bit;
+    pressure multigrid / GMRES / flexible CG (constant null space) to 1e-12 / 1e-10 with identical iteration counts."""
+    g = G[name]
+    c = refcases.channel_case() if name == "channel" else refcases.ethier_case()
+    fbc = refcases.channel_fbc(c) if name == "channel" else hsmg.box_fbc(c, (2,) * 6)
+    geo = c.geom()
+    for i in range(6):
+        assert np.array_equal(geo[i], g[f"g{i + 1}m1"]), i
+    assert np.array_equal(geo[6], g["bm1"]) and np.array_equal(c.binv(), g["binvm1"])
+    assert np.array_equal(c.mult, g["vmult"]) and np.array_equal(c.mask, g["v1mask"])
+    assert abs(geo[6].sum() - g["volvm1"][0]) <= 1e-13 * g["volvm1"][0]
+    assert np.isclose(g["volvm1"][0], 2 * np.pi * 2 * np.pi if name == "channel" else 8.0, rtol=1e-13)
+    # velocity: hmholtz('VELX') = dssum + mask of the rhs, cggo (Jacobi)
+    n = c.n
+    rhs = c.dssum(g["vel_rhs"]) * c.mask
+    x, it = c.cggo(rhs, np.full(n, g["vel_h1"][0]), np.full(n, g["vel_h2"][0]), tin=1e-9, maxit=200, istep=1)
+    assert it == g["vel_it"][0] and np.array_equal(x, g["vel_x"])
+    # pressure
+    assert bool(g["ifvcor"][0])
+    mg = hsmg.H1MG(c, fbc, null_space=True)
+    assert np.array_equal(mg.mask[-1], g["pmask"])
+    r = g["rhs"].copy()
+    z = mg.solve(r)
+    assert np.array_equal(r, g["rhs_out"]) and relmax(z, g["z"]) <= 1e-12
+    tol = float(g["tol"][0])
+    x, it = hsmg.hmh_gmres(c, mg, g["b"], np.ones(n), np.zeros(n), g["pmask"], c.mult, tol, 100, ifvcor=True)
+    assert it == g["it"][0] and relmax(x, g["x"]) <= 1e-11
+    x, it = hsmg.hmh_flex_cg(c, mg, g["b"], np.ones(n), np.zeros(n), g["pmask"], c.mult, tol, 100, ifvcor=True)
+    assert it == g["it_fcg"][0] and relmax(x, g["x_fcg"]) <= 1e-10
