@@ -20,3 +20,7 @@ if __name__ == "__main__":
     flat = refcases.reference_all()
     np.savez_compressed(refcases.GOLDEN, **flat)
     print(f"wrote {refcases.GOLDEN}: {len(flat)} arrays, {os.path.getsize(refcases.GOLDEN) / 1e6:.2f} MB")
+    if "--full" in sys.argv:         # the 1536-element turbChannel mesh: needs `python oracle/ref_build.py --lelt 1536`
+        full = refcases.ref_channel_full()
+        np.savez_compressed(refcases.GOLDEN_CHANNEL_FULL, **full)
+        print(f"wrote {refcases.GOLDEN_CHANNEL_FULL}: {len(full)} arrays, {os.path.getsize(refcases.GOLDEN_CHANNEL_FULL) / 1e6:.2f} MB")

@@ -160,7 +160,22 @@ def geometry_of(rc):
     return out
 
 
-def _pressure_case(case, with_geometry=False):
+def pressure_inputs(case, pmask):
+    """Right-hand sides in the range of the operator (A times a continuous field): with the all-Neumann null space an
+    inconsistent coarse rhs has no meaningful answer -- XXT pins a different unknown for every rank count
+    (crs_xxt.c:893-899, 926-949) -- and the residuals the preconditioner sees in hmh_gmres are consistent.  Returns the
+    rhs of the h1mg_solve call and of the hmh_gmres / hmh_flex_cg calls."""
+    n = case.n
+    rng = np.random.default_rng(3)
+    h1, h2 = np.ones(n), np.zeros(n)
+    xr = case.dssum(rng.standard_normal(n)) * case.mult * pmask
+    rhs = case.dssum(case.axhelm(xr, h1, h2)) * pmask
+    xe = case.dssum(rng.standard_normal(n)) * case.mult * pmask
+    b = case.dssum(case.axhelm(xe, h1, h2)) * pmask
+    return rhs, b
+
+
+def _pressure_case(case, with_geometry=False, capped=0):
     """set_overlap -> hsmg_setup/h1mg_setup/set_up_h1_crs (navier6.f:29-101, hsmg.f:22-47,2234-2270, navier8.f:83-233),
     h1mg_solve (hsmg.f:1855-1949) and hmh_gmres (gmres.f:304-545) incl. chktcg1 and ortho."""
     rc = _ref(case)
@@ -169,17 +184,10 @@ def _pressure_case(case, with_geometry=False):
     R.var("param")[[39, 40, 41, 42, 43]] = 0.0
     R.call("set_overlap")
     pmask = rc.fld("pmask")
-    rng = np.random.default_rng(3)
     h1, h2 = np.ones(n), np.zeros(n)
-    # a right-hand side in the range of the operator (A times a continuous field): with the all-Neumann null space an
-    # inconsistent coarse rhs has no meaningful answer -- XXT pins a different unknown for every rank count
-    # (crs_xxt.c:893-899, 926-949) -- and the residuals the preconditioner sees in hmh_gmres are consistent
-    xr = case.dssum(rng.standard_normal(n)) * case.mult * pmask
-    rhs = case.dssum(case.axhelm(xr, h1, h2)) * pmask
+    rhs, b = pressure_inputs(case, pmask)
     z, r = np.zeros(n), rhs.copy()
     R.call("h1mg_solve", z, r, False)
-    xe = case.dssum(rng.standard_normal(n)) * case.mult * pmask
-    b = case.dssum(case.axhelm(xe, h1, h2)) * pmask
     tol = 1e-8
     R.var("param")[20] = tol
     R.set("tolps", tol), R.set("istep", 1)
@@ -190,6 +198,10 @@ def _pressure_case(case, with_geometry=False):
     out = dict(pmask=pmask, rhs=rhs, rhs_out=r, z=z, b=b, x=x, it=np.array([it.value]), tol=np.array([tol]),
                x_fcg=xf, it_fcg=np.array([itf.value]),
                ifvcor=np.array([int(R.get("ifvcor"))]), volvm1=np.array([R.get("volvm1")]))
+    if capped:                                                     # the same GMRES stopped after `capped` iterations
+        xc, itc = b.copy(), C.c_int(capped)
+        R.call("hmh_gmres", xc, h1, h2, case.mult, itc)
+        out.update(x_capped=xc, it_capped=np.array([itc.value]))
     if with_geometry:
         out.update(geometry_of(rc))
         out.update(_velocity_solve(rc, case))
@@ -214,6 +226,34 @@ def ref_channel():
     """BASELINE config 5 (turbChannel mesh, 4 x 4 x 4 elements): pressure multigrid / GMRES / flexible CG with the constant
     null space on a periodic, wall-stretched box, and one velocity Helmholtz solve."""
     return _pressure_case(channel_case(), with_geometry=True)
+
+
+GOLDEN_CHANNEL_FULL = os.path.join(os.path.dirname(GOLDEN), "ref_channel_full.npz")
+CHANNEL_FULL_DIMS = (16, 12, 8)          # examples/turbChannel/turbChannel.box
+CHANNEL_FULL_CAP = 8
+
+
+def channel_full_samples(n):
+    """4096 fixed sample positions of a field on the full mesh (the fields themselves are 6.3 MB each)."""
+    return np.sort(np.random.default_rng(123).choice(n, 4096, replace=False))
+
+
+def ref_channel_full():
+    """BASELINE config 5 at the size of the reference's own files: the 16 x 12 x 8 = 1536-element mesh of
+    examples/turbChannel/turbChannel.{box,re2} (tests/test_readers.py checks the generated vertices and vertex ids against
+    those files), lx1 = 8, 786,432 grid points.  Needs the lelt = 1536 build of oracle/_ref (`python oracle/ref_build.py
+    --lelt 1536`).  Stored: iteration counts, norms, and the fields at 4096 fixed positions; the inputs are regenerated on
+    the test side (`pressure_inputs`) and identified by their norms and samples."""
+    case = channel_case(CHANNEL_FULL_DIMS)
+    g = _pressure_case(case, capped=CHANNEL_FULL_CAP)
+    idx = channel_full_samples(case.n)
+    out = dict(idx=idx.astype(np.int64), nel=np.array([case.nel]))
+    for k, v in g.items():
+        if v.size == case.n:
+            out[k + "_s"], out[k + "_l2"], out[k + "_max"] = v[idx].copy(), np.array([np.sqrt(np.sum(v * v))]), np.array([np.abs(v).max()])
+        else:
+            out[k] = v
+    return out
 
 
 def ref_ethier():

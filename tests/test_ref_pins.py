@@ -324,3 +324,39 @@ def test_baseline_config_meshes(name):
     assert it == g["it"][0] and relmax(x, g["x"]) <= 1e-11
     x, it = hsmg.hmh_flex_cg(c, mg, g["b"], np.ones(n), np.zeros(n), g["pmask"], c.mult, tol, 100, ifvcor=True)
     assert it == g["it_fcg"][0] and relmax(x, g["x_fcg"]) <= 1e-10
+
+
+def test_full_turbchannel_mesh_h1mg_and_gmres():
+    """BASELINE config 5 on the 1536-element mesh of examples/turbChannel (tests/golden/ref_channel_full.npz, from the
+    lelt = 1536 build of the reference): one h1mg_solve and GMRES stopped after 8 iterations -- the complete solves (56 GMRES
+    / 62 flexible-CG iterations in both the reference and the oracle, fields within 2e-13) take minutes in numpy and are
+    left to the GPU suite (tests/test_zz_gpu_configs.py)."""
+    g = dict(np.load(refcases.GOLDEN_CHANNEL_FULL))
+    c = refcases.channel_case(refcases.CHANNEL_FULL_DIMS)
+    idx = g["idx"]
+    assert c.nel == g["nel"][0] == 1536 and np.array_equal(idx, refcases.channel_full_samples(c.n))
+    assert np.isclose(c.bm1().sum(), g["volvm1"][0], rtol=1e-13) and np.isclose(g["volvm1"][0], 4 * np.pi ** 2, rtol=1e-13)
+    mg = hsmg.H1MG(c, refcases.channel_fbc(c), null_space=True)
+    rhs, b = refcases.pressure_inputs(c, mg.mask[-1])
+    for k, v in (("rhs", rhs), ("b", b)):                        # the regenerated inputs are the reference run's inputs
+        assert np.array_equal(v[idx], g[k + "_s"]) and np.sqrt(np.sum(v * v)) == g[k + "_l2"][0]
+    z = mg.solve(rhs)
+    assert np.array_equal(rhs[idx], g["rhs_out_s"])
+    assert np.abs(z[idx] - g["z_s"]).max() <= 1e-12 * g["z_max"][0]
+    assert abs(np.sqrt(np.sum(z * z)) - g["z_l2"][0]) <= 1e-12 * g["z_l2"][0]
+    n, cap = c.n, int(g["it_capped"][0])
+    assert cap == refcases.CHANNEL_FULL_CAP and g["it"][0] == 56 and g["it_fcg"][0] == 62
+    x, it = hsmg.hmh_gmres(c, mg, b, np.ones(n), np.zeros(n), mg.mask[-1], c.mult, float(g["tol"][0]), cap, ifvcor=True)
+    assert it == cap and np.abs(x[idx] - g["x_capped_s"]).max() <= 1e-11 * g["x_capped_max"][0]
+
+
+@pytest.mark.skipif(not _ref_available(), reason="oracle/_ref neither prebuilt nor buildable (no /root/reference)")
+def test_full_turbchannel_golden_is_what_the_reference_computes_now():
+    import os
+    from oracle import ref_build
+    if not os.path.exists(os.path.join(ref_build.OUT, "libnekref_lx8e1536.so")):
+        pytest.skip("lelt = 1536 build of oracle/_ref not present (python oracle/ref_build.py --lelt 1536)")
+    live, g = refcases.ref_channel_full(), dict(np.load(refcases.GOLDEN_CHANNEL_FULL))
+    assert set(live) == set(g)
+    for k, v in live.items():
+        assert np.array_equal(np.asarray(v), g[k]), k
