@@ -332,6 +332,77 @@ __global__ void __launch_bounds__(CG_THREADS)
     });
 }
 
+// EXPERIMENT, off by default -- measured slower than the gs + update pair at E = 262,144 (2.15 vs 0.61 + 0.66 ms per
+// iteration, profiles/r1o_gs_fuse_experiment_v*.json; bit-identical results): kept for an ncu look at where the extra
+// traffic of the scattered partner reads comes from.
+// The same update with the direct-stiffness summation folded in (one rank, NEKB_GS_FUSE_UPDATE=1): `ap` holds the
+// UN-assembled A p; every node gathers the members of its group on the fly (gs.cuh gs_gathered: the bits gs_op would
+// produce), so the assembled vector is never written back or re-read -- the scattered partner reads are served by L2
+// because the partners are streamed by neighbouring blocks of the same sweep.  Masked nodes skip the gather.
+__global__ void __launch_bounds__(CG_THREADS)
+    cggos_update2_gs_kernel(double *__restrict__ r, const double *__restrict__ ap, const unsigned char *__restrict__ code,
+                            const int32_t *__restrict__ link, const int32_t *__restrict__ goff,
+                            const int32_t *__restrict__ gidx, int64_t n, CgScalars *sc, double *partials)
+{
+    __shared__ double red[33];
+    __shared__ double wtab[128];
+    const double pap = sc->work[0], rz = sc->work[1];
+    const double alpha = rz / pap;
+    if (threadIdx.x < 128) wtab[threadIdx.x] = threadIdx.x ? 1.0 / (double)threadIdx.x : 0.0;
+    __syncthreads();
+    double s = 0.0;
+    const int64_t n4 = n >> 2;
+    double2 *r2 = reinterpret_cast<double2 *>(r);
+    const double2 *a2 = reinterpret_cast<const double2 *>(ap);
+    const uchar4 *c4 = reinterpret_cast<const uchar4 *>(code);
+    const int4 *l4 = reinterpret_cast<const int4 *>(link);
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n4; t += (int64_t)gridDim.x * blockDim.x) {
+        double2 ra = r2[2 * t], rb = r2[2 * t + 1];
+        const double2 aa = a2[2 * t], ab = a2[2 * t + 1];
+        const uchar4 c = c4[t];
+        const int4 l = l4[t];
+        // the four partner loads are issued together (a node without a partner re-reads itself: an L1 hit), the rare
+        // edge / corner groups take the loop afterwards
+        const int64_t t4 = t << 2;
+        const double q0 = ap[l.x >= 0 ? (int64_t)l.x : t4], q1 = ap[l.y >= 0 ? (int64_t)l.y : t4 + 1];
+        const double q2 = ap[l.z >= 0 ? (int64_t)l.z : t4 + 2], q3 = ap[l.w >= 0 ? (int64_t)l.w : t4 + 3];
+        double w0 = l.x >= 0 ? aa.x + q0 : aa.x, w1 = l.y >= 0 ? aa.y + q1 : aa.y;
+        double w2 = l.z >= 0 ? ab.x + q2 : ab.x, w3 = l.w >= 0 ? ab.y + q3 : ab.y;
+        if (l.x < -1) w0 = gs_gathered(ap, aa.x, l.x, goff, gidx);
+        if (l.y < -1) w1 = gs_gathered(ap, aa.y, l.y, goff, gidx);
+        if (l.z < -1) w2 = gs_gathered(ap, ab.x, l.z, goff, gidx);
+        if (l.w < -1) w3 = gs_gathered(ap, ab.y, l.w, goff, gidx);
+        if (c.x & 0x80) w0 = 0.0;
+        if (c.y & 0x80) w1 = 0.0;
+        if (c.z & 0x80) w2 = 0.0;
+        if (c.w & 0x80) w3 = 0.0;
+        ra.x = fma(-alpha, w0, ra.x);
+        ra.y = fma(-alpha, w1, ra.y);
+        rb.x = fma(-alpha, w2, rb.x);
+        rb.y = fma(-alpha, w3, rb.y);
+        r2[2 * t] = ra;
+        r2[2 * t + 1] = rb;
+        s = fma(wtab[c.x & 0x7f] * ra.x, ra.x, s);
+        s = fma(wtab[c.y & 0x7f] * ra.y, ra.y, s);
+        s = fma(wtab[c.z & 0x7f] * rb.x, rb.x, s);
+        s = fma(wtab[c.w & 0x7f] * rb.y, rb.y, s);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t t = n4 << 2; t < n; t++) {
+            const unsigned char c = code[t];
+            const double w = (c & 0x80) ? 0.0 : gs_gathered(ap, ap[t], link[t], goff, gidx);
+            r[t] = fma(-alpha, w, r[t]);
+            s = fma(wtab[c & 0x7f] * r[t], r[t], s);
+        }
+    double b = block_reduce(s, red);
+    grid_reduce(b, partials, &sc->counter[2], red, [=](double tot) {
+        sc->rtz1 = rz;
+        sc->work[1] = tot;
+        sc->alpha = alpha;
+        sc->it = sc->it + 1;
+    });
+}
+
 // u += alpha * p with the device-resident alpha (the u update of the final iteration)
 __global__ void __launch_bounds__(CG_THREADS)
     axpy_alpha_kernel(double *__restrict__ u, const double *__restrict__ p, int64_t n, const CgScalars *sc)
@@ -355,6 +426,11 @@ inline int axcg_variant()
         v = e ? atoi(e) : 0;
     }
     return v;
+}
+inline int gs_fuse_update_enabled()  // read per solve, so one process can time both forms
+{
+    const char *e = getenv("NEKB_GS_FUSE_UPDATE");
+    return e ? atoi(e) : 0;
 }
 inline int cg_fused_enabled()
 {
@@ -393,6 +469,9 @@ inline int cggos_run_fused(const CggosArgs &a, int maxit, double *hist_host, boo
     GsMap &h = gs_get(a.gs_handle);
     NEKB_REQUIRE(h.n == n, "cggos: gs handle was set up for a different vector length");
 
+    // gather form of dssum inside the update kernel: one rank only (no remote members to wait for)
+    const bool gather = gs_fuse_update_enabled() && c.nranks == 1 && h.nshared == 0;
+    if (gather) gs_ensure_link(h);
     cggos_init2_kernel<<<grid, CG_THREADS, 0, s>>>(a.u, r.p, a.rhs, a.mult, n, sc, c.partials.p + 1 * CG_PART_STRIDE);
     NEKB_LAUNCHED();
     comm_allreduce_sum(&sc->work[1], 1);
@@ -405,13 +484,21 @@ inline int cggos_run_fused(const CggosArgs &a, int maxit, double *hist_host, boo
         }
         prof_end(PROF_AX);
         comm_allreduce_sum(&sc->work[0], 1);
-        prof_begin(PROF_GS);
-        gs_op(a.gs_handle, ap.p, 1, nullptr);
-        prof_end(PROF_GS);
-        prof_begin(PROF_UPDATE);
-        cggos_update2_kernel<<<grid, CG_THREADS, 0, s>>>(r.p, ap.p, c.wcode.p, n, sc, c.partials.p + 2 * CG_PART_STRIDE);
-        NEKB_LAUNCHED();
-        prof_end(PROF_UPDATE);
+        if (gather) {
+            prof_begin(PROF_UPDATE);
+            cggos_update2_gs_kernel<<<grid, CG_THREADS, 0, s>>>(r.p, ap.p, c.wcode.p, h.link.p, h.goff.p, h.gidx.p, n, sc,
+                                                                c.partials.p + 2 * CG_PART_STRIDE);
+            NEKB_LAUNCHED();
+            prof_end(PROF_UPDATE);
+        } else {
+            prof_begin(PROF_GS);
+            gs_op(a.gs_handle, ap.p, 1, nullptr);
+            prof_end(PROF_GS);
+            prof_begin(PROF_UPDATE);
+            cggos_update2_kernel<<<grid, CG_THREADS, 0, s>>>(r.p, ap.p, c.wcode.p, n, sc, c.partials.p + 2 * CG_PART_STRIDE);
+            NEKB_LAUNCHED();
+            prof_end(PROF_UPDATE);
+        }
         comm_allreduce_sum(&sc->work[1], 1);
         if (hist_host) {
             cggos_hist_kernel<<<1, 1, 0, s>>>(sc, c.hist.p, iter - 1);

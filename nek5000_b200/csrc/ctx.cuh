@@ -56,6 +56,9 @@ struct GsMap {
     int64_t nmembers = 0;          // sum of group sizes
     DevBuf<int32_t> goff;          // [ngroups+1] CSR offsets, groups ordered by first member
     DevBuf<int32_t> gidx;          // [nmembers] member indices, ascending inside a group
+    DevBuf<int32_t> link;          // [n] node -> its group, for gather-style consumers (gs.cuh gs_ensure_link): -1 not in a
+                                   // group, >= 0 the other member of a pair, <= -2 group -2-g (three or more members)
+    bool link_built = false;
     // ---- remote part (np > 1): ids shared with other ranks --------------------------------------
     int64_t nshared = 0;           // local unique ids that also live on another rank
     std::vector<int> peers;        // neighbour ranks, ascending

@@ -99,6 +99,7 @@ inline void gs_build_local(GsMap &h, const int64_t *id_dev, int64_t n)
     NEKB_REQUIRE(n < (int64_t)2147483647, "gs_setup: local vector too long for int32 indexing");
     h.n = n;
     h.ngroups = h.nmembers = 0;
+    h.link_built = false;
     if (n == 0) return;
 
     DevBuf<int32_t> idx_nz, idx_sorted, num;
@@ -236,6 +237,51 @@ inline void gs_local(GsMap &h, double *u, int op)
         default: NEKB_REQUIRE(false, "gs_op: unsupported op (1 +, 2 *, 3 min, 4 max)");
     }
     NEKB_LAUNCHED();
+}
+
+// Node -> group view of the same map, for kernels that GATHER the assembled value of a node while streaming over the
+// vector (cg.cuh cggos_update2_gs_kernel) instead of scattering sums back: face nodes (pairs) hold the partner's index,
+// edge / corner nodes the group number.  Built on first use, 4 bytes per node.
+__global__ void __launch_bounds__(256)
+    gs_build_link_kernel(int32_t *__restrict__ link, const int32_t *__restrict__ goff, const int32_t *__restrict__ gidx,
+                         int ngroups)
+{
+    for (int gI = blockIdx.x * blockDim.x + threadIdx.x; gI < ngroups; gI += gridDim.x * blockDim.x) {
+        const int b = goff[gI], e = goff[gI + 1];
+        if (e - b == 2) {
+            link[gidx[b]] = gidx[b + 1];
+            link[gidx[b + 1]] = gidx[b];
+        } else {
+            for (int q = b; q < e; q++) link[gidx[q]] = -2 - gI;
+        }
+    }
+}
+
+inline void gs_ensure_link(GsMap &h)
+{
+    if (h.link_built) return;
+    Ctx &c = ctx();
+    h.link.alloc((size_t)(h.n > 0 ? h.n : 1));
+    NEKB_CUDA(cudaMemsetAsync(h.link.p, 0xFF, sizeof(int32_t) * (size_t)(h.n > 0 ? h.n : 1), c.stream));
+    if (h.ngroups > 0) {
+        gs_build_link_kernel<<<blocks_for(h.ngroups), 256, 0, c.stream>>>(h.link.p, h.goff.p, h.gidx.p, (int)h.ngroups);
+        NEKB_LAUNCHED();
+    }
+    h.link_built = true;
+}
+
+// The value gs_op(+) would leave at a node, read from the un-assembled vector: same members, same (ascending) order as
+// gs_local_kernel<1>, hence the same bits.
+__device__ __forceinline__ double gs_gathered(const double *__restrict__ u, double own, int l,
+                                              const int32_t *__restrict__ goff, const int32_t *__restrict__ gidx)
+{
+    if (l == -1) return own;
+    if (l >= 0) return own + u[l];          // a pair: IEEE addition commutes, so member order does not matter
+    const int g = -2 - l;
+    const int b = goff[g], e = goff[g + 1];
+    double v = u[gidx[b]];
+    for (int q = b + 1; q < e; q++) v += u[gidx[q]];
+    return v;
 }
 
 // u <- gs_op(u) [* mask]
