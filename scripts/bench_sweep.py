@@ -1,0 +1,41 @@
+"""BASELINE config 3 (SURVEY.md 8d "E sweep"): BP5 CG iteration rate against the element count on one GPU.
+    python scripts/bench_sweep.py [--dims 8,16,32,64,128] [--its 100]
+A dims entry is m (an m^3 box) or axbxc.  Prints one JSON line: per size E, ms per iteration, GDOF/s and the fraction of
+the HBM roofline by SURVEY 8(d)'s 79,648 algorithmic bytes per element-iteration (peak from MEASURED_PEAKS.json)."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--dims", default="8,16,32,64,128")
+    ap.add_argument("--its", type=int, default=100)
+    a = ap.parse_args()
+    from nek5000_b200 import nek
+    from nek5000_b200.bp5 import BP5
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        peak = None
+    rows = []
+    for d in a.dims.split(","):
+        dims = tuple(int(v) for v in d.split("x")) if "x" in d else (int(d),) * 3
+        nek.finalize()
+        nek.init(0, 8, 3)
+        b = BP5(*dims, lx1=8)
+        b.solve(-1e-8, 5)
+        it, sec = b.solve(-1e-8, a.its)
+        gbs = 79648.0 * b.nel * it / sec / 1e9
+        rows.append({"dims": dims, "E": b.nel, "ms_per_iteration": sec / it * 1e3, "gdofs": it * b.nel * 343 / sec / 1e9,
+                     "alg_GBs": gbs, "frac_of_hbm_peak": gbs / peak if peak else None})
+    nek.finalize()
+    print(json.dumps({"workload": "BP5 cggos, N=7, FP64, one GPU", "its": a.its, "hbm_peak_GBs": peak, "sweep": rows}))
+
+
+if __name__ == "__main__":
+    main()
