@@ -86,6 +86,10 @@ def ref_core(nx=8):
         R.set("kfldfdm", -1), R.set("ifsolv", 0), R.set("istep", 1)
         R.call("cggo", x, f.copy(), h1, h2, case.mask, case.mult, 1, tin, maxit, 1, rc.fld("binvm1"), "VELX")
         out[key + "_x"], out[key + "_it"] = x, np.array([R.get("niterhm")])
+    # the Lanczos tridiagonal cggo leaves in common /tdarray/ (hmholtz.f:808-815): diag_k = (beta_k^2 rho_{k-1} + rho_k) /
+    # rtz1_k, upper_{k-1} = -beta_k rho_{k-1} / sqrt(rtz2 rtz1) -- the whole alpha / beta history of the converged solve
+    nit = int(out["cggo_it"][0])
+    out["cggo_diagt"], out["cggo_upper"] = R.var("diagt")[:nit].copy(), R.var("upper")[:nit - 1].copy()
     # hmholtz wrapper on an un-assembled right-hand side
     rhs = case.bm1() * rng.standard_normal(n)
     out["hmh_rhs"] = rhs
@@ -106,7 +110,7 @@ def ref_core_lx6():
     """The same routines at lx1 = 6 (the library's generic, non-TMA kernels; a second polynomial order for the oracle)."""
     keep = ("glo_num", "vmult", "bm1", "binvm1", "v1mask", "volvm1", "zgm1", "wxm1", "dxm1", "g1m1", "g2m1", "g3m1", "g4m1", "g5m1",
             "g6m1", "u", "h1", "h2", "axhelm", "axhelm_poisson", "setprec", "dsop_add", "cggo_f", "cggo20_x", "cggo20_it", "cggo_x",
-            "cggo_it", "bp5_gf", "bp5_e1", "bp5_r1", "bp5_u1")
+            "cggo_it", "cggo_diagt", "cggo_upper", "bp5_gf", "bp5_e1", "bp5_r1", "bp5_u1")
     full = ref_core(6)
     return {k: full[k] for k in keep}
 
@@ -193,10 +197,15 @@ def _pressure_case(case, with_geometry=False, capped=0):
     R.set("tolps", tol), R.set("istep", 1)
     x, it = b.copy(), C.c_int(100)
     R.call("hmh_gmres", x, h1, h2, case.mult, it)
+    # residual history of the last GMRES cycle as the reference's own Givens data holds it (gmres.f:486-493): after step k
+    # rnorm_k = |s_k| rnorm_{k-1}, and the final rnorm = |gamma(j+1)| norm_fac
+    j = it.value - 30 * ((it.value - 1) // 30)
+    gm_s = np.abs(R.var("s_gmres")[:j]).copy()
+    gm_last = np.array([abs(R.var("gamma_gmres")[j]) / np.sqrt(R.get("volvm1"))])
     xf, itf = b.copy(), C.c_int(100)
     R.call("hmh_flex_cg", xf, h1, h2, case.mult, itf)            # core/hmholtz.f:2164 (param(42) = 2)
     out = dict(pmask=pmask, rhs=rhs, rhs_out=r, z=z, b=b, x=x, it=np.array([it.value]), tol=np.array([tol]),
-               x_fcg=xf, it_fcg=np.array([itf.value]),
+               x_fcg=xf, it_fcg=np.array([itf.value]), gmres_s=gm_s, gmres_rnorm_last=gm_last,
                ifvcor=np.array([int(R.get("ifvcor"))]), volvm1=np.array([R.get("volvm1")]))
     if capped:                                                     # the same GMRES stopped after `capped` iterations
         xc, itc = b.copy(), C.c_int(capped)

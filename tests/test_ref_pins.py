@@ -360,3 +360,51 @@ def test_full_turbchannel_golden_is_what_the_reference_computes_now():
     assert set(live) == set(g)
     for k, v in live.items():
         assert np.array_equal(np.asarray(v), g[k]), k
+
+
+def test_cggo_alpha_beta_history_is_the_reference_lanczos_tridiagonal():
+    """Residual-history pin against the reference itself: cggo leaves the Lanczos tridiagonal of the solve in common
+    /tdarray/ (hmholtz.f:808-815) -- diag_k = (beta_k^2 rho_{k-1} + rho_k)/rtz1_k, upper_{k-1} = -beta_k rho_{k-1}/sqrt(rtz2
+    rtz1) -- i.e. every alpha and beta of the 101 iterations.  The oracle's (rtz1, rho) history reproduces it bit for bit."""
+    for name, nx in (("core", 8), ("core_lx6", 6)):
+        g, c = G[name], refcases.case_of("core", nx)
+        _, it, h = c.cggo(g["cggo_f"], g["h1"], g["h2"], tin=1e-6, maxit=500, istep=1, history=True)
+        k = int(g["cggo_it"][0])
+        assert it == k and len(g["cggo_diagt"]) == k and len(g["cggo_upper"]) == k - 1
+        rtz, rho = h[:, 0], h[:, 2]
+        beta = np.zeros(k)
+        beta[1:] = rtz[1:k] / rtz[:k - 1]
+        diag = np.array([rho[0] / rtz[0]] + [(beta[i] ** 2 * rho[i - 1] + rho[i]) / rtz[i] for i in range(1, k)])
+        upper = np.array([-beta[i] * rho[i - 1] / np.sqrt(rtz[i - 1] * rtz[i]) for i in range(1, k)])
+        assert np.array_equal(diag, g["cggo_diagt"]) and np.array_equal(upper, g["cggo_upper"]), name
+
+
+@pytest.mark.parametrize("name", ["h1mg", "h1mg_neumann", "channel", "ethier"])
+def test_gmres_residual_history_against_the_reference_givens_data(name):
+    """hmh_gmres keeps the Givens sines and the rotated right-hand side of its last cycle (gmres.f:486-493): rnorm_k = |s_k|
+    rnorm_{k-1}, final rnorm = |gamma(j+1)| norm_fac.  The oracle's residual history agrees with that to 1e-10 of the
+    initial residual at every step, and entry by entry to 1e-10 while the residual is above 1e-5 of the initial one (below,
+    the recurrence carries the 1e-16 rounding floor of the initial residual: 5e-8 relative at the 1e-8 exit)."""
+    g = G[name]
+    if name in ("h1mg", "h1mg_neumann"):
+        mesh = "core" if name == "h1mg" else "neumann"
+        c = refcases.case_of(mesh)
+        fbc = refcases.fbc_of(mesh, c)
+    else:
+        c = refcases.channel_case() if name == "channel" else refcases.ethier_case()
+        fbc = refcases.channel_fbc(c) if name == "channel" else hsmg.box_fbc(c, (2,) * 6)
+    null = bool(g["ifvcor"][0])
+    mg = hsmg.H1MG(c, fbc, null_space=null)
+    n = c.n
+    _, it, h, _ = hsmg.hmh_gmres(c, mg, g["b"], np.ones(n), np.zeros(n), g["pmask"], c.mult, float(g["tol"][0]), 100,
+                                 ifvcor=null, history=True)
+    j = len(g["gmres_s"])
+    assert it == g["it"][0] == j < 30                        # one cycle
+    ref = np.zeros(j)
+    ref[-1] = g["gmres_rnorm_last"][0]
+    for k in range(j - 1, 0, -1):
+        ref[k - 1] = ref[k] / g["gmres_s"][k]
+    assert np.abs(ref - h).max() <= 1e-10 * h[0]
+    big = h > 1e-5 * h[0]
+    assert big.sum() >= 8 and np.all(np.abs(ref - h)[big] <= 1e-10 * h[big])
+    assert abs(ref[-1] - h[-1]) <= 1e-6 * h[-1] and h[-1] < float(g["tol"][0]) <= h[-2]
