@@ -105,3 +105,30 @@ def test_full_turbchannel_mesh_pressure_solve_against_the_reference(nek):
         assert it == g[itkey][0], (key, it, g[itkey])
         assert np.abs(res[idx] - g[key + "_s"]).max() <= ftol * g[key + "_max"][0], key
         assert abs(np.sqrt(np.sum(res * res)) - g[key + "_l2"][0]) <= ftol * g[key + "_l2"][0], key
+
+
+def test_cggo_history_against_the_reference_lanczos_tridiagonal(nek):
+    """The reference's own record of a cggo solve -- the Lanczos tridiagonal in common /tdarray/ (hmholtz.f:808-815), i.e.
+    every alpha and beta -- against the device's (rtz1, rho) history, over the window in which CG has not yet amplified
+    last-bit differences past 1e-9 (tests/test_gpu_parity.py explains the window); the count (101) must be identical."""
+    import ctypes as C
+    from nek5000_b200 import lib
+    from nek5000_b200._lib import check
+    from nek5000_b200.nek import DevArray
+    g, case = G["core"], refcases.case_of("core")
+    n = case.n
+    _register(nek, case, [g[f"g{i}m1"] for i in range(1, 7)], g["bm1"], g["binvm1"], g["volvm1"][0], g["zgm1"], g["wxm1"], g["dxm1"])
+    d = [DevArray.from_host(a) for a in (np.zeros(n), g["cggo_f"], g["h1"], g["h2"], g["v1mask"], g["vmult"], g["binvm1"])]
+    k = int(g["cggo_it"][0])
+    hist, it = np.zeros(3 * (500 + 2)), C.c_int(0)              # 3 * (maxit + 2) doubles (include/nekb200.h)
+    check(lib().nekb_cggo_dev(*[a.ptr for a in d], 1, 1e-6, 500, C.byref(it), hist.ctypes.data))
+    assert it.value == k
+    h = hist.reshape(-1, 3)
+    rtz, rho = h[:, 0], h[:, 2]
+    win = 40
+    beta = np.zeros(win)
+    beta[1:] = rtz[1:win] / rtz[:win - 1]
+    diag = np.array([rho[0] / rtz[0]] + [(beta[i] ** 2 * rho[i - 1] + rho[i]) / rtz[i] for i in range(1, win)])
+    upper = np.array([-beta[i] * rho[i - 1] / np.sqrt(rtz[i - 1] * rtz[i]) for i in range(1, win)])
+    assert np.all(np.abs(diag - g["cggo_diagt"][:win]) <= 1e-9 * np.abs(g["cggo_diagt"][:win]))
+    assert np.all(np.abs(upper - g["cggo_upper"][:win - 1]) <= 1e-9 * np.abs(g["cggo_upper"][:win - 1]))
