@@ -293,6 +293,9 @@ int nekb_re2_info(const char *path, int64_t *nelgt, int *ldim, int64_t *nelgv, i
                   int64_t *nbc, int nbc_cap);
 int nekb_re2_read_mesh(const char *path, int64_t e0, int64_t nel, double *xc, double *yc, double *zc, int *igroup);
 int nekb_re2_read_bc(const char *path, int section, char *cbc, double *bc);
+/* nekb_re2_read_curves: the curved-side records -> ccurve(12,nelgt) (one character) and curve(5,12,nelgt) of core/INPUT
+ *   (reader_re2.f:160-290 + buf_to_curve :473-497), global arrays pre-filled by the caller (blank / zero). */
+int nekb_re2_read_curves(const char *path, char *ccurve, double *curve);
 /* .ma2: core/map2.f:712-941 read_map -- 132-byte '#v001' header (7 integers: nel, nactive, depth, d2, npts, nrank,
  * noutflow), endian tag, then 1 + nlv int32 per element: RSB leaf and the vertex ids in SYMMETRIC corner order
  * (-> vertex(nlv,nel) int64 as setupds takes them).  nekb_assign_gllnid: core/map2.f:943-1026 assign_gllnid, in place:

@@ -1905,6 +1905,16 @@ int nekb_re2_read_bc(const char *path, int section, char *cbc, double *bc)
         re2_read_bc(fh, h, s, section, cbc, bc);
     });
 }
+int nekb_re2_read_curves(const char *path, char *ccurve, double *curve)
+{
+    return guard([&] {
+        FileHandle fh(path);
+        NEKB_REQUIRE(fh.f != nullptr, std::string("Cannot open .re2 file! ") + path);
+        const Re2Header h = re2_header(fh);
+        const Re2Sections s = re2_sections(fh, h);
+        re2_read_curves(fh, h, s, ccurve, curve);
+    });
+}
 int nekb_ma2_info(const char *path, int64_t *nel, int64_t *hdr7)
 {
     return guard([&] {

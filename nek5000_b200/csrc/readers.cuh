@@ -191,6 +191,34 @@ inline void re2_read_bc(FileHandle &fh, const Re2Header &h, const Re2Sections &s
     }
 }
 
+// Curved sides (readp_re2_curve + buf_to_curve, reader_re2.f:160-290,473-497): record = element, side (edge 1..12 or face
+// 1..6 depending on the curve type), curve(5), ccurve (one character in the last word, never byte-swapped).  Outputs are
+// the global arrays curve[5*12*nelgt] and ccurve[12*nelgt] of core/INPUT (slots without a record are left untouched).
+inline void re2_read_curves(FileHandle &fh, const Re2Header &h, const Re2Sections &s, char *ccurve, double *curve)
+{
+    const int64_t n = s.ncurve, rec = 8 * (int64_t)h.wdsize;
+    std::vector<unsigned char> buf((size_t)(n * rec));
+    if (n) fh.read_at(s.curve_off, buf.data(), buf.size(), ".re2 curved-side records");
+    for (int64_t r = 0; r < n; r++) {
+        const unsigned char *p = buf.data() + r * rec;
+        int64_t eg, f;
+        if (h.wdsize == 8) {
+            eg = (int64_t)re2_word(p, 8, h.swap);
+            f = (int64_t)re2_word(p + 8, 8, h.swap);
+        } else {
+            uint32_t a, b;
+            memcpy(&a, p, 4), memcpy(&b, p + 4, 4);
+            if (h.swap) a = bswap32(a), b = bswap32(b);
+            eg = (int32_t)a, f = (int32_t)b;
+        }
+        NEKB_REQUIRE(eg >= 1 && eg <= h.nelgt && f >= 1 && f <= 12, ".re2: bad curved-side record");
+        const int64_t slot = (eg - 1) * 12 + (f - 1);
+        if (curve)
+            for (int k = 0; k < 5; k++) curve[slot * 5 + k] = re2_word(p + (size_t)(2 + k) * h.wdsize, h.wdsize, h.swap);
+        if (ccurve) ccurve[slot] = (char)p[(size_t)7 * h.wdsize];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------- .ma2
 struct Ma2Header {
     int64_t nel = 0, nactive = 0, depth = 0, d2 = 0, npts = 0, nrank = 0, noutflow = 0;

@@ -167,6 +167,16 @@ def re2_read_bc(path: str, section: int = 0):
     return cbc, bc
 
 
+def re2_read_curves(path: str):
+    """The curved-side section -> ccurve (nelgt, 12) of 1-character codes (blank where the file has no record),
+    curve (nelgt, 12, 5)  (core/reader_re2.f:160-290, buf_to_curve)."""
+    info = re2_info(path)
+    ccurve = np.full((info["nelgt"], 12), b" ", dtype="S1")
+    curve = np.zeros((info["nelgt"], 12, 5))
+    check(lib().nekb_re2_read_curves(path.encode(), C.c_void_p(ccurve.ctypes.data), _ptr(curve)))
+    return ccurve, curve
+
+
 def ma2_read(path: str, nlv: int = 8, e0: int = 0, nel: int | None = None):
     """core/map2.f:712-941: (header[7], leaf[nel], vertex[nel, nlv]) of a .ma2 file."""
     n = C.c_int64(0)

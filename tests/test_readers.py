@@ -24,7 +24,7 @@ def nek():
     return N
 
 
-def write_re2(path, xc, yc, zc, bc_elem, bc_face, bc_type, version=2, big_endian=False):
+def write_re2(path, xc, yc, zc, bc_elem, bc_face, bc_type, version=2, big_endian=False, curves=()):
     """The on-disk layout of core/reader_re2.f: 80-byte header, endian tag, mesh records, curve count, one BC section."""
     nel = len(xc)
     e = ">" if big_endian else "<"
@@ -37,7 +37,15 @@ def write_re2(path, xc, yc, zc, bc_elem, bc_face, bc_type, version=2, big_endian
         rec[:, 1:9], rec[:, 9:17], rec[:, 17:25] = xc, yc, zc
         f.write(rec.tobytes())
         cnt = (lambda n: struct.pack(e + "i", n)) if version == 1 else (lambda n: np.array([n], dtype=e + "f8").tobytes())
-        f.write(cnt(0))                        # no curved sides
+        f.write(cnt(len(curves)))              # curved sides: element, side, curve(5), ccurve
+        for (ce, cs, cv, cc) in curves:
+            if version == 1:
+                f.write(struct.pack(e + "ii", int(ce), int(cs)))
+                f.write(np.asarray(cv, dtype=e + "f4").tobytes())
+                f.write(cc.ljust(4).encode())
+            else:
+                f.write(np.array([ce, cs, *cv], dtype=e + "f8").tobytes())
+                f.write(cc.ljust(8).encode())
         f.write(cnt(len(bc_elem)))
         for k in range(len(bc_elem)):
             if version == 1:
@@ -84,6 +92,31 @@ def test_re2_round_trip_of_the_bp5_fixture(nek, tmp_path, version, big):
     k = 17
     ref_bl = np.arange(5.0) if version == 1 else np.array([0.5, 1.5, 2.5, 3.5, 4.5])
     assert np.array_equal(bc[FIX["bc_elem"][k] - 1, FIX["bc_face"][k] - 1], ref_bl)
+
+
+@pytest.mark.parametrize("version,big", [(2, False), (2, True), (1, False), (1, True)])
+def test_re2_curved_sides(nek, tmp_path, version, big):
+    """readp_re2_curve / buf_to_curve (reader_re2.f:160-290,473-497): curve(5,12,nelgt), ccurve(12,nelgt); the sections after
+    the curve records (boundary conditions) are still found."""
+    p = str(tmp_path / "c.re2")
+    curves = [(3, 1, (0.5, 0.25, 0.0, 0.0, 0.0), "C"), (3, 12, (1.0, 2.0, 3.0, 0.0, 0.0), "m"), (1000, 5, (0.0, 0.0, 0.0, 1.5, 0.0), "s"),
+              (412, 7, (-0.75, 0.0, 0.0, 0.0, 0.0), "C")]
+    write_re2(p, FIX["xc"], FIX["yc"], FIX["zc"], FIX["bc_elem"], FIX["bc_face"], FIX["bc_type"], version, big, curves)
+    info = nek.re2_info(p)
+    assert info["ncurve"] == 4 and info["nbc"] == [600]
+    cc, cv = nek.re2_read_curves(p)
+    assert cc.shape == (1000, 12) and cv.shape == (1000, 12, 5)
+    assert (cc != b" ").sum() == 4
+    for (ce, cs, v, t) in curves:
+        assert cc[ce - 1, cs - 1] == t.encode() and np.array_equal(cv[ce - 1, cs - 1], np.asarray(v))   # exact in f4 too
+    assert not cv[cc == b" "].any()
+    cbc, _ = nek.re2_read_bc(p, 0)
+    assert (cbc == b"v  ").sum() == 600
+    # a record naming a side outside 1..12 is refused
+    from nek5000_b200.nek import NekbError
+    write_re2(p, FIX["xc"], FIX["yc"], FIX["zc"], FIX["bc_elem"], FIX["bc_face"], FIX["bc_type"], version, big, [(3, 13, (0,) * 5, "C")])
+    with pytest.raises(NekbError):
+        nek.re2_read_curves(p)
 
 
 @pytest.mark.parametrize("big", [False, True])
@@ -137,6 +170,35 @@ def test_the_reference_files_themselves(nek):
     assert (cbc == b"v  ").sum() == 600
     hdr, leaf, vertex = nek.ma2_read(os.path.join(REF_BP5, "bp5.ma2"))
     assert np.array_equal(leaf, FIX["leaf"]) and np.array_equal(vertex, FIX["vertex"]) and np.array_equal(hdr, FIX["ma2_header"])
+    # examples/turbChannel (BASELINE config 5): the box the oracle generates for tests/refcases.channel_case IS the file's mesh
+    # before usrdat -- same vertices, and the same identification of corners as the genmap vertex ids in turbChannel.ma2
+    import oracle
+    tc = "/root/reference/examples/turbChannel/turbChannel"
+    if os.path.exists(tc + ".re2"):
+        x, y, z, _ = nek.re2_read_mesh(tc + ".re2")
+        c = oracle.Case(16, 12, 8, nx=4, periodic=(1, 0, 1), rescale=False)
+        E = c.nel
+        for a, b in ((c.xc, x), (c.yc, y), (c.zc, z)):
+            assert np.abs(a.reshape(8, E, order="F").T - b).max() <= 2e-16
+        cbc, _ = nek.re2_read_bc(tc + ".re2", 0)
+        assert (cbc == b"W  ").sum() == 2 * 16 * 8 and (cbc == b"P  ").sum() == 2 * (12 * 8 + 16 * 12)
+        _, _, vertex = nek.ma2_read(tc + ".ma2")
+        mine = c.vertex.reshape(E, 8)
+        assert len(np.unique(vertex)) == len(np.unique(mine)) == 16 * 13 * 8
+        fwd = dict(zip(vertex.ravel().tolist(), mine.ravel().tolist()))
+        assert all(fwd[a] == b for a, b in zip(vertex.ravel().tolist(), mine.ravel().tolist()))
+    # short_tests/ethier (a curved ball mesh from exo2nek): 32 elements, 96 curved-side records
+    et = "/root/reference/short_tests/ethier/ethier.re2"
+    if os.path.exists(et):
+        cc, cv = nek.re2_read_curves(et)
+        info = nek.re2_info(et)
+        assert info["ncurve"] == (cc != b" ").sum() == 96
+        raw = open(et, "rb").read()
+        off = 84 + 32 * 25 * 8 + 8                                      # header, endian tag, mesh records, curve count
+        rec = np.frombuffer(raw[off:off + 96 * 64], dtype="<f8").reshape(96, 8)
+        for r, row in enumerate(rec):
+            e_, s_ = int(row[0]), int(row[1])
+            assert cc[e_ - 1, s_ - 1] == raw[off + r * 64 + 56:off + r * 64 + 57] and np.array_equal(cv[e_ - 1, s_ - 1], row[2:7])
     for name in ("short_tests/ethier/ethier", "examples/turbChannel/turbChannel"):
         p = os.path.join("/root/reference", name + ".re2")
         if os.path.exists(p):
