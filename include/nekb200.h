@@ -302,6 +302,11 @@ int nekb_re2_read_curves(const char *path, char *ccurve, double *curve);
  * leaf -> 0-based rank for np ranks (power-of-two shortcut; otherwise the reference's isort-based contiguous split). */
 int nekb_ma2_info(const char *path, int64_t *nel, int64_t *hdr7);
 int nekb_ma2_read(const char *path, int nlv, int64_t e0, int64_t nel, int32_t *leaf, int64_t *vertex);
+/* .co2: core/map2.f:338-473 read_con -- the connectivity file of a parRSB build: 132-byte '#v001'/'#v002' header (nelgt,
+ * nelgv, nv), endian tag, then 1 + nv int32 per element: global element id and vertex ids (-> eid(nel), vertex(nv,nel)
+ * int64, the arrays map2.f:206-232 hands to the partitioner and then to setupds).  nlv must equal the file's nv. */
+int nekb_co2_info(const char *path, int64_t *nelgt, int64_t *nelgv, int *nv);
+int nekb_co2_read(const char *path, int nlv, int64_t e0, int64_t nel, int64_t *eid, int64_t *vertex);
 int nekb_assign_gllnid(int *gllnid, int64_t nelgt, int64_t nelgv, int np);
 
 /* core/navier8.f:2004-2360 setvert3d with ifcenter=.false.: glo_num(nx^3,nel) from

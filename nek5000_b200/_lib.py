@@ -114,6 +114,8 @@ def lib() -> C.CDLL:
     L.nekb_re2_read_curves.argtypes = [C.c_char_p, vp, vp]
     L.nekb_ma2_info.argtypes = [C.c_char_p, C.POINTER(C.c_int64), vp]
     L.nekb_ma2_read.argtypes = [C.c_char_p, C.c_int, C.c_int64, C.c_int64, vp, vp]
+    L.nekb_co2_info.argtypes = [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), ip]
+    L.nekb_co2_read.argtypes = [C.c_char_p, C.c_int, C.c_int64, C.c_int64, vp, vp]
     L.nekb_assign_gllnid.argtypes = [vp, C.c_int64, C.c_int64, C.c_int]
     L.nekb_gs_discover.argtypes = [i64p, C.c_int64, ip, C.POINTER(C.c_int64), vp, vp, vp]
     L.nekb_bp5_setup.argtypes = [C.c_int] * 6 + [C.c_double]

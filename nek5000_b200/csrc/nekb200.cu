@@ -1938,6 +1938,27 @@ int nekb_ma2_read(const char *path, int nlv, int64_t e0, int64_t nel, int32_t *l
         ma2_read(fh, h, nlv, e0, nel, leaf, vertex);
     });
 }
+int nekb_co2_info(const char *path, int64_t *nelgt, int64_t *nelgv, int *nv)
+{
+    return guard([&] {
+        FileHandle fh(path);
+        NEKB_REQUIRE(fh.f != nullptr, std::string("Cannot find con file! ") + path);
+        const Co2Header h = co2_header(fh);
+        if (nelgt) *nelgt = h.nelgt;
+        if (nelgv) *nelgv = h.nelgv;
+        if (nv) *nv = h.nv;
+    });
+}
+int nekb_co2_read(const char *path, int nlv, int64_t e0, int64_t nel, int64_t *eid, int64_t *vertex)
+{
+    return guard([&] {
+        FileHandle fh(path);
+        NEKB_REQUIRE(fh.f != nullptr, std::string("Cannot find con file! ") + path);
+        const Co2Header h = co2_header(fh);
+        NEKB_REQUIRE(nlv == h.nv, "Number of vertices do not match!");          // map2.f:443-444
+        co2_read(fh, h, e0, nel, eid, vertex);
+    });
+}
 int nekb_assign_gllnid(int *gllnid, int64_t nelgt, int64_t nelgv, int np)
 {
     return guard([&] {

@@ -259,6 +259,49 @@ inline void ma2_read(FileHandle &fh, const Ma2Header &h, int nlv, int64_t e0, in
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------- .co2
+// core/map2.f:338-473 read_con: the connectivity file a parRSB build reads instead of .ma2 -- 132-byte header
+// ('#v001' + 3 x i12, or '#v002' list-directed: nelgt, nelgv, nv), endian tag, then per element 1 + nv int32: the global
+// element id and its vertex ids (consumed at map2.f:206-232: eid8 = wk4(ii+1), vtx8 = icopy48(wk4(ii+2..))).
+struct Co2Header {
+    int64_t nelgt = 0, nelgv = 0;
+    int nv = 0;
+    bool swap = false;
+};
+
+inline Co2Header co2_header(FileHandle &fh)
+{
+    char hdr[133] = {0};
+    fh.read_at(0, hdr, 132, ".co2 header");
+    NEKB_REQUIRE(!strncmp(hdr, "#v001", 5) || !strncmp(hdr, "#v002", 5), ".co2: unknown header version");
+    Co2Header h;
+    long long a = 0, b = 0, c = 0;
+    const int got = sscanf(hdr + 5, "%lld %lld %lld", &a, &b, &c);
+    NEKB_REQUIRE(got == 3, ".co2: cannot parse the header");
+    h.nelgt = a, h.nelgv = b, h.nv = (int)c;
+    NEKB_REQUIRE(h.nelgt >= 0 && h.nelgv >= 0 && h.nelgv <= h.nelgt && (h.nv == 4 || h.nv == 8), ".co2: bad header values");
+    float test;
+    fh.read_at(132, &test, 4, ".co2 endian tag");
+    h.swap = endian_tag_swapped(test, ".co2");
+    return h;
+}
+
+inline void co2_read(FileHandle &fh, const Co2Header &h, int64_t e0, int64_t nel, int64_t *eid, int64_t *vertex)
+{
+    NEKB_REQUIRE(e0 >= 0 && nel >= 0 && e0 + nel <= h.nelgt, ".co2: element range outside the file");
+    const int nv = h.nv;
+    const int64_t rec = (int64_t)(1 + nv) * 4;
+    std::vector<uint32_t> buf((size_t)(nel * (1 + nv)));
+    if (nel) fh.read_at(136 + e0 * rec, buf.data(), buf.size() * 4, ".co2 records");
+    for (int64_t e = 0; e < nel; e++) {
+        const uint32_t *p = buf.data() + e * (1 + nv);
+        auto w = [&](int k) { return (int32_t)(h.swap ? bswap32(p[k]) : p[k]); };
+        if (eid) eid[e] = (int64_t)w(0);
+        if (vertex)
+            for (int k = 0; k < nv; k++) vertex[e * nv + k] = (int64_t)w(1 + k);
+    }
+}
+
 // core/math.f isort(a,ind,n): the reference's index heap sort (ascending, NOT stable -- the order of equal keys decides
 // which elements land on either side of a partition boundary, so it is restated exactly).  1-based logic on 0-based storage.
 inline void nek_isort(std::vector<int> &a, std::vector<int> &ind)

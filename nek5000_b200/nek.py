@@ -189,6 +189,17 @@ def ma2_read(path: str, nlv: int = 8, e0: int = 0, nel: int | None = None):
     return hdr, leaf, vertex
 
 
+def co2_read(path: str, nlv: int = 8, e0: int = 0, nel: int | None = None):
+    """core/map2.f:338-473 read_con: (nelgt, nelgv, eid[nel], vertex[nel, nlv]) of a .co2 connectivity file."""
+    ngt, ngv, nv = C.c_int64(0), C.c_int64(0), C.c_int(0)
+    check(lib().nekb_co2_info(path.encode(), C.byref(ngt), C.byref(ngv), C.byref(nv)))
+    nel = int(ngt.value) - e0 if nel is None else nel
+    eid = np.zeros(nel, dtype=np.int64)
+    vertex = np.zeros((nel, nlv), dtype=np.int64)
+    check(lib().nekb_co2_read(path.encode(), nlv, e0, nel, _ptr(eid), _ptr(vertex)))
+    return int(ngt.value), int(ngv.value), eid, vertex
+
+
 def assign_gllnid(leaf, nelgv: int | None = None, np_ranks: int = 1) -> np.ndarray:
     """core/map2.f:943-1026 assign_gllnid: RSB leaves -> 0-based rank of every global element."""
     g = np.ascontiguousarray(leaf, dtype=np.int32).copy()

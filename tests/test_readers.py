@@ -134,6 +134,32 @@ def test_ma2_round_trip_and_numbering(nek, tmp_path, big):
     assert len(np.unique(vertex)) == 1331 and len(np.unique(glo)) == 71 ** 3 - 1000 * 6 ** 3 + 1
 
 
+@pytest.mark.parametrize("version,big", [(1, False), (1, True), (2, False)])
+def test_co2_round_trip(nek, tmp_path, version, big):
+    """read_con (map2.f:338-473): header '#v001' + 3 x i12 or '#v002' list-directed, endian tag, (element id, vertex ids)
+    int32 records; the vertex ids feed setvert3d exactly like those of a .ma2."""
+    e = ">" if big else "<"
+    p = str(tmp_path / "a.co2")
+    nel, vertex = 1000, FIX["vertex"]
+    with open(p, "wb") as f:
+        hdr = f"#v001{nel:12d}{nel:12d}{8:12d}" if version == 1 else f"#v002 {nel} {nel} 8"
+        f.write(hdr.ljust(132).encode())
+        f.write(struct.pack(e + "f", 6.54321))
+        f.write(np.concatenate([np.arange(1, nel + 1)[:, None], vertex], axis=1).astype(e + "i4").tobytes())
+    ngt, ngv, eid, v = nek.co2_read(p)
+    assert (ngt, ngv) == (1000, 1000) and np.array_equal(eid, np.arange(1, 1001)) and np.array_equal(v, vertex) and v.dtype == np.int64
+    _, _, e2, v2 = nek.co2_read(p, 8, 411, 37)
+    assert np.array_equal(e2, eid[411:448]) and np.array_equal(v2, vertex[411:448])
+    glo, _ = nek.setvert3d(8, 1000, v)
+    glo_ma2, _ = nek.setvert3d(8, 1000, FIX["vertex"])
+    assert np.array_equal(glo, glo_ma2)
+    from nek5000_b200.nek import NekbError
+    with pytest.raises(NekbError):
+        nek.co2_read(p, 4)                      # 'Number of vertices do not match!' (map2.f:443)
+    with pytest.raises(NekbError):
+        nek.co2_read(p, 8, 990, 20)
+
+
 def test_reader_errors_are_loud(nek, tmp_path):
     from nek5000_b200.nek import NekbError
     with pytest.raises(NekbError):
