@@ -368,6 +368,19 @@ int nekb_crs_solve_dev(double *e_dev, const double *r_dev);
 /* Sizes: number of levels, points per direction of every level (coarse first), distinct 1-D eigen-systems per
  * level, iterations of the last coarse solve. */
 int nekb_h1mg_info(int *lmax, int *nh3, int *ntab3, int *crs_iters);
+/* The reference's coarse-solver facade, core/fcrs.c:45-96 (crs_setup / crs_solve / crs_free over core/crs_xxt.c:860-965), as
+ * called from core/navier8.f:217 (set_up_h1_crs) and core/hsmg.f:1349, navier8.f:53,1528: n local dofs with global ids id[]
+ * (0 = ignored: Dirichlet, set_jl_crs_mask), the local operator as nz COO entries over 0-based local dofs (set_mat_ij),
+ * null_space flag.  Only sid = 0 (XXT, param(40) = 0) is provided -- a direct solve: the assembled matrix of all ranks is
+ * inverted on the device once, a solve is gather + GEMV + scatter; with a null space the result is mean-free over the
+ * distinct dofs like crs_xxt.c:951-960.  comm / np / param / datafname are ignored (the library's own transport).
+ * Limited to NEKB_CRS_DENSE_MAX (12288) distinct dofs.  Status: compiled, parity test written, NOT YET RUN ON A GPU. */
+void crs_setup_(int *handle, const int *sid, const int *comm, const int *np, const int *n, const int64_t *id, const int *nz,
+                const int *Ai, const int *Aj, const double *A, const int *null_space, const double *param,
+                const char *datafname, int *ierr);
+void crs_solve_(const int *handle, double *x, const double *b);
+void crs_free_(const int *handle);
+int nekb_fcrs_solve_dev(int handle, double *x_dev, const double *b_dev);
 /* Host copies of setup products for parity tests.  which: "mask","rstr_wt","swt" (level-sized, level 1-based),
  * "J" (interpolation level -> level+1, row-major nf x nc), "lm","ll","lr" (3*nelv, direction-major; level ignored),
  * "crs_a" (64*nelv, a(i,j,e) as a[e][i][j]). */

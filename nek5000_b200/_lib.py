@@ -114,6 +114,13 @@ def lib() -> C.CDLL:
     L.nekb_re2_read_curves.argtypes = [C.c_char_p, vp, vp]
     L.nekb_ma2_info.argtypes = [C.c_char_p, C.POINTER(C.c_int64), vp]
     L.nekb_ma2_read.argtypes = [C.c_char_p, C.c_int, C.c_int64, C.c_int64, vp, vp]
+    L.crs_setup_.argtypes = [ip, ip, ip, ip, ip, vp, ip, vp, vp, vp, ip, vp, C.c_char_p, ip]
+    L.crs_setup_.restype = None
+    L.crs_solve_.argtypes = [ip, vp, vp]
+    L.crs_solve_.restype = None
+    L.crs_free_.argtypes = [ip]
+    L.crs_free_.restype = None
+    L.nekb_fcrs_solve_dev.argtypes = [C.c_int, vp, vp]
     L.nekb_co2_info.argtypes = [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), ip]
     L.nekb_co2_read.argtypes = [C.c_char_p, C.c_int, C.c_int64, C.c_int64, vp, vp]
     L.nekb_assign_gllnid.argtypes = [vp, C.c_int64, C.c_int64, C.c_int]

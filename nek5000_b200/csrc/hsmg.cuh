@@ -24,6 +24,7 @@
 #pragma once
 #include <cmath>
 #include <map>
+#include <memory>
 #include <tuple>
 
 #include <cooperative_groups.h>
@@ -1290,6 +1291,169 @@ inline void crs_dense_setup(CrsSolver &k, int nel, const int64_t *vertex)
     k.nc = nc;
     NEKB_CUDA(cudaStreamSynchronize(s));
     k.dense = true;
+}
+
+// ------------------------------------------------------------------------------------------------ crs_* facade
+// The reference's coarse-solver facade (core/fcrs.c:45-96: crs_setup / crs_solve / crs_free over crs_xxt.c) for callers that
+// keep the reference's own set-up (core/navier8.f:83-233 set_up_h1_crs): n local dofs with global ids `id` (0 = Dirichlet,
+// ignored -- set_jl_crs_mask), the local operator as nz COO entries over 0-based local dofs (set_mat_ij), the null-space flag.
+// Served by the same direct solver as h1mg's level 1 (explicit inverse on the device, one GEMV per solve).  NOT YET RUN ON A
+// GPU (written after the round's GPU budget was spent): tests/test_zz_gpu_configs.py holds its parity test behind
+// NEKB_TEST_UNVALIDATED=1.  COLLECTIVE set-up and solve.
+struct FcrsHandle {
+    CrsSolver k;
+    int64_t n = 0;
+    DevBuf<double> b, x;
+};
+inline std::vector<std::unique_ptr<FcrsHandle>> &fcrs_table()
+{
+    static std::vector<std::unique_ptr<FcrsHandle>> t;
+    return t;
+}
+
+__global__ void __launch_bounds__(256)
+    crsd_scatter_ignored_kernel(double *__restrict__ x, const double *__restrict__ y, const int32_t *__restrict__ vid, int64_t n)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+        x[t] = vid[t] >= 0 ? y[vid[t]] : 0.0;     // crs_xxt.c:961-964: dofs with id 0 come back as 0
+}
+
+inline int fcrs_setup(int sid, int64_t n, const int64_t *id, int64_t nz, const int *Ai, const int *Aj, const double *A, int null_space)
+{
+    Ctx &c = ctx();
+    cudaStream_t s = c.stream;
+    NEKB_REQUIRE(sid == 0, "crs_setup: only the XXT slot (param(40) = 0) is provided; AMG / hypre are not");
+    NEKB_REQUIRE(n >= 0 && nz >= 0 && (n == 0 || id) && (nz == 0 || (Ai && Aj && A)), "crs_setup: bad arguments");
+    // distinct non-zero ids of all ranks, ascending -> dense dof numbers
+    std::vector<int64_t> mine;
+    for (int64_t t = 0; t < n; t++)
+        if (id[t] != 0) mine.push_back(id[t]);
+    std::sort(mine.begin(), mine.end());
+    mine.erase(std::unique(mine.begin(), mine.end()), mine.end());
+    int64_t cnt[2] = {(int64_t)mine.size(), 0};
+    for (int64_t q = 0; q < nz; q++) {
+        NEKB_REQUIRE(Ai[q] >= 0 && Ai[q] < n && Aj[q] >= 0 && Aj[q] < n, "crs_setup: matrix index outside the local dofs");
+        if (id[Ai[q]] != 0 && id[Aj[q]] != 0) cnt[1]++;
+    }
+    std::vector<int64_t> cnts((size_t)2 * c.nranks);
+    host_allgather(cnt, cnts.data(), sizeof cnt);
+    int64_t idmax = 1, nzmax = 1;
+    for (int r = 0; r < c.nranks; r++) idmax = std::max(idmax, cnts[2 * r]), nzmax = std::max(nzmax, cnts[2 * r + 1]);
+    std::vector<int64_t> id_loc((size_t)idmax, 0), id_all((size_t)idmax * c.nranks);
+    std::copy(mine.begin(), mine.end(), id_loc.begin());
+    host_allgather(id_loc.data(), id_all.data(), sizeof(int64_t) * id_loc.size());
+    std::vector<int64_t> gids;
+    for (int r = 0; r < c.nranks; r++) gids.insert(gids.end(), id_all.begin() + (size_t)r * idmax, id_all.begin() + (size_t)r * idmax + cnts[2 * r]);
+    std::sort(gids.begin(), gids.end());
+    gids.erase(std::unique(gids.begin(), gids.end()), gids.end());
+    const int64_t nc = (int64_t)gids.size();
+    NEKB_REQUIRE(nc >= 1, "crs_setup: no unmasked coarse dof");
+    NEKB_REQUIRE(nc <= crs_dense_max(), "crs_setup: coarse problem larger than NEKB_CRS_DENSE_MAX (direct solver only)");
+    auto dof = [&](int64_t g) { return (int64_t)(std::lower_bound(gids.begin(), gids.end(), g) - gids.begin()); };
+    // every rank's entries in dense numbering, gathered and summed in rank-major / entry order (same bits everywhere)
+    std::vector<int64_t> ij_loc((size_t)2 * nzmax, 0), ij_all((size_t)2 * nzmax * c.nranks);
+    std::vector<double> a_loc((size_t)nzmax, 0.0), a_all((size_t)nzmax * c.nranks);
+    int64_t m = 0;
+    for (int64_t q = 0; q < nz; q++)
+        if (id[Ai[q]] != 0 && id[Aj[q]] != 0) ij_loc[2 * m] = dof(id[Ai[q]]), ij_loc[2 * m + 1] = dof(id[Aj[q]]), a_loc[m] = A[q], m++;
+    host_allgather(ij_loc.data(), ij_all.data(), sizeof(int64_t) * ij_loc.size());
+    host_allgather(a_loc.data(), a_all.data(), sizeof(double) * a_loc.size());
+    const int64_t ld = crsd_ld(nc);
+    std::vector<double> M((size_t)ld * ld, 0.0), gmask((size_t)ld, 0.0);
+    for (int r = 0; r < c.nranks; r++)
+        for (int64_t q = 0; q < cnts[2 * r + 1]; q++) {
+            const int64_t *ij = ij_all.data() + ((size_t)r * nzmax + q) * 2;
+            M[(size_t)ij[0] * ld + ij[1]] += a_all[(size_t)r * nzmax + q];
+        }
+    double trace = 0.0;
+    for (int64_t v = 0; v < nc; v++) trace += M[(size_t)v * ld + v], gmask[v] = 1.0;
+    for (int64_t v = nc; v < ld; v++) M[(size_t)v * ld + v] = 1.0;          // padding: identity
+    if (null_space) {   // (trace/nc^2) 1 1^T: the regularised solve of a consistent rhs is the mean-free solution
+        const double gam = trace / ((double)nc * (double)nc);
+        for (int64_t i = 0; i < nc; i++)
+            for (int64_t j = 0; j < nc; j++) M[(size_t)i * ld + j] += gam;
+    }
+    std::unique_ptr<FcrsHandle> H(new FcrsHandle());
+    CrsSolver &k = H->k;
+    k.null_space = null_space ? 1 : 0;
+    k.ndof = (double)nc;
+    k.ainv.upload(M.data(), M.size(), s);
+    const int nb = (int)(ld / CRS_NB);
+    for (int kb = 0; kb < nb; kb++) {
+        crsd_pivot_kernel<<<1, 256, 0, s>>>(k.ainv.p, ld, kb);
+        NEKB_LAUNCHED();
+        if (nb > 1) {
+            crsd_row_kernel<<<nb, 256, 0, s>>>(k.ainv.p, ld, kb);
+            NEKB_LAUNCHED();
+            crsd_trail_kernel<<<dim3(nb, nb), 256, 0, s>>>(k.ainv.p, ld, kb);
+            NEKB_LAUNCHED();
+            crsd_col_kernel<<<nb, 256, 0, s>>>(k.ainv.p, ld, kb);
+            NEKB_LAUNCHED();
+        }
+    }
+    const size_t nn = (size_t)std::max<int64_t>(n, 1);
+    std::vector<int32_t> vid(nn, -1), voff((size_t)nc + 1, 0), vmem(nn, 0);
+    for (int64_t t = 0; t < n; t++)
+        if (id[t] != 0) vid[t] = (int32_t)dof(id[t]), voff[(size_t)vid[t] + 1]++;
+    for (int64_t v = 0; v < nc; v++) voff[v + 1] += voff[v];
+    std::vector<int32_t> cur(voff.begin(), voff.end() - 1);
+    for (int64_t t = 0; t < n; t++)
+        if (vid[t] >= 0) vmem[cur[vid[t]]++] = (int32_t)t;
+    k.vid.upload(vid.data(), vid.size(), s), k.voff.upload(voff.data(), voff.size(), s), k.vmem.upload(vmem.data(), vmem.size(), s);
+    k.gmask.upload(gmask.data(), (size_t)ld, s);
+    k.g.alloc((size_t)ld), k.y.alloc((size_t)ld);
+    k.g.zero(s), k.y.zero(s);
+    k.nc = nc;
+    k.n = 0;                      // crs_dense_solve's own scatter is skipped: ignored dofs need the variant above
+    k.dense = true;
+    H->n = n;
+    H->b.alloc(nn), H->x.alloc(nn);
+    NEKB_CUDA(cudaStreamSynchronize(s));
+    auto &tab = fcrs_table();
+    for (size_t h = 0; h < tab.size(); h++)
+        if (!tab[h]) {
+            tab[h] = std::move(H);
+            return (int)h;
+        }
+    tab.push_back(std::move(H));
+    return (int)tab.size() - 1;
+}
+
+inline FcrsHandle &fcrs_get(int handle)
+{
+    auto &tab = fcrs_table();
+    NEKB_REQUIRE(handle >= 0 && handle < (int)tab.size() && tab[handle], "crs_solve: invalid handle");   // fcrs.c CHECK_HANDLE
+    return *tab[handle];
+}
+
+// x = Q A^-1 Q^T b on device arrays of the handle's n local dofs
+inline void fcrs_solve_dev(int handle, double *x_dev, const double *b_dev)
+{
+    Ctx &c = ctx();
+    FcrsHandle &H = fcrs_get(handle);
+    crs_dense_solve(H.k, nullptr, b_dev);
+    if (H.n > 0) {
+        const int gx = (int)std::max<int64_t>(1, std::min<int64_t>((H.n + 255) / 256, (int64_t)c.num_sms * 4));
+        crsd_scatter_ignored_kernel<<<gx, 256, 0, c.stream>>>(x_dev, H.k.y.p, H.k.vid.p, H.n);
+        NEKB_LAUNCHED();
+    }
+}
+
+inline void fcrs_solve_host(int handle, double *x, const double *b)
+{
+    Ctx &c = ctx();
+    FcrsHandle &H = fcrs_get(handle);
+    if (H.n > 0) H.b.upload(b, (size_t)H.n, c.stream);
+    fcrs_solve_dev(handle, H.x.p, H.b.p);
+    if (H.n > 0) H.x.download(x, (size_t)H.n, c.stream);
+    NEKB_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+inline void fcrs_free(int handle)
+{
+    fcrs_get(handle);
+    NEKB_CUDA(cudaStreamSynchronize(ctx().stream));
+    fcrs_table()[handle].reset();
 }
 
 inline int vec_grid(int64_t n)

@@ -177,6 +177,7 @@ void nekb_finalize(void)
     crs_release_graph();
     h1mg() = H1mg();
     hsmg2() = H1mg();
+    fcrs_table().clear();
     fdm_h1_state() = FdmH1State();
     gmres_state() = GmresState();
     crs_scalars().release();
@@ -1050,6 +1051,30 @@ int nekb_crs_solve_dev(double *e_dev, const double *r_dev)
         NEKB_REQUIRE(h1mg().ready, "nekb_h1mg_setup has not been called");
         crs_solve_dev(h1mg(), e_dev, r_dev);
     });
+}
+// ---- the reference's coarse-solver facade (core/fcrs.c:45-96), Fortran names and by-reference arguments
+void crs_setup_(int *handle, const int *sid, const int *comm, const int *np, const int *n, const int64_t *id, const int *nz,
+                const int *Ai, const int *Aj, const double *A, const int *null_space, const double *param,
+                const char *datafname, int *ierr)
+{
+    (void)comm, (void)np, (void)param, (void)datafname;   // the library's own transport; XXT takes no parameters / data file
+    guard_fortran("crs_setup", [&] {
+        require_init();
+        *handle = fcrs_setup(*sid, *n, id, *nz, Ai, Aj, A, *null_space);
+        if (ierr) *ierr = 0;
+    });
+}
+void crs_solve_(const int *handle, double *x, const double *b)
+{
+    guard_fortran("crs_solve", [&] { fcrs_solve_host(*handle, x, b); });
+}
+void crs_free_(const int *handle)
+{
+    guard_fortran("crs_free", [&] { fcrs_free(*handle); });
+}
+int nekb_fcrs_solve_dev(int handle, double *x_dev, const double *b_dev)
+{
+    return guard([&] { fcrs_solve_dev(handle, x_dev, b_dev); });
 }
 int nekb_h1mg_info(int *lmax, int *nh3, int *ntab3, int *crs_iters)
 {

@@ -555,6 +555,33 @@ def hmh_flex_cg(res: np.ndarray, h1: np.ndarray, h2: np.ndarray, wt: np.ndarray,
     return int(it.value)
 
 
+# --------------------------------------------------------------------------------------------- coarse-solver facade
+def crs_setup(ids, Ai, Aj, A, null_space: bool, sid: int = 0) -> int:
+    """core/fcrs.c:45 crs_setup(handle,sid,comm,np,n,id,nz,Ai,Aj,A,null_space,param,datafname,ierr) as called at
+    core/navier8.f:217; returns the handle."""
+    ids = np.ascontiguousarray(ids, dtype=np.int64).reshape(-1)
+    Ai, Aj = (np.ascontiguousarray(a, dtype=np.int32).reshape(-1) for a in (Ai, Aj))
+    A = np.ascontiguousarray(A, dtype=np.float64).reshape(-1)
+    h, ierr, zero = C.c_int(-1), C.c_int(0), C.c_int(0)
+    lib().crs_setup_(C.byref(h), _i(sid), C.byref(zero), _i(1), _i(ids.size), _ptr(ids), _i(A.size), _ptr(Ai), _ptr(Aj), _ptr(A),
+                     _i(int(bool(null_space))), None, b"", C.byref(ierr))
+    if ierr.value != 0 or h.value < 0:
+        raise NekbError(lib().nekb_last_error().decode())
+    return int(h.value)
+
+
+def crs_solve(handle: int, b) -> np.ndarray:
+    """core/fcrs.c:80 crs_solve(handle,x,b): x = Q A^-1 Q^T b on the handle's local dofs."""
+    b = np.ascontiguousarray(b, dtype=np.float64).reshape(-1)
+    x = np.zeros_like(b)
+    lib().crs_solve_(_i(handle), _ptr(x), _ptr(b))
+    return x
+
+
+def crs_free(handle: int) -> None:
+    lib().crs_free_(_i(handle))
+
+
 # --------------------------------------------------------------------------------------------- device arrays
 class DevArray:
     """A device buffer owned through the C-ABI helpers (section E of the header)."""

@@ -8,6 +8,8 @@ Tolerances are the north star's: identical CG / GMRES iteration counts, fields <
 convergence is compared at the accuracy it was asked for, as in tests/test_gpu_golden.py).  The file sorts after the other
 GPU suites on purpose: these are the largest cases.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -132,3 +134,52 @@ def test_cggo_history_against_the_reference_lanczos_tridiagonal(nek):
     upper = np.array([-beta[i] * rho[i - 1] / np.sqrt(rtz[i - 1] * rtz[i]) for i in range(1, win)])
     assert np.all(np.abs(diag - g["cggo_diagt"][:win]) <= 1e-9 * np.abs(g["cggo_diagt"][:win]))
     assert np.all(np.abs(upper - g["cggo_upper"][:win - 1]) <= 1e-9 * np.abs(g["cggo_upper"][:win - 1]))
+
+
+@pytest.mark.skipif(os.environ.get("NEKB_TEST_UNVALIDATED") != "1",
+                    reason="crs_setup_/crs_solve_ facade was written after the round's GPU budget was spent: not yet run on a GPU "
+                           "(set NEKB_TEST_UNVALIDATED=1)")
+@pytest.mark.parametrize("null_space", [False, True])
+def test_crs_facade_against_a_dense_solve(nek, null_space):
+    """core/fcrs.c crs_setup / crs_solve (XXT slot) on the vertex mesh of a 4 x 3 x 2 box: ids = vertex numbers (0 on a
+    Dirichlet side unless the null space is kept), element matrices with the constant in their kernel, COO indices as
+    set_mat_ij builds them.  Against numpy: x = Q A^-1 Q^T b on the distinct dofs, 0 on ignored ones; with the null space the
+    mean-free solution of a consistent right-hand side (crs_xxt.c:951-960)."""
+    import oracle
+    case = oracle.Case(4, 3, 2, nx=2)
+    E = case.nel
+    ids = case.vertex.reshape(E, 8).copy()
+    rng = np.random.default_rng(5)
+    if not null_space:
+        ids[np.isin(ids, np.unique(ids)[:12])] = 0                # twelve vertices play the Dirichlet side
+    B = rng.standard_normal((E, 8, 8))
+    Ae = np.einsum("eik,ejk->eij", B, B)
+    P = np.eye(8) - np.full((8, 8), 1.0 / 8)
+    Ae = np.einsum("ik,ekl,lj->eij", P, Ae, P)                    # A_e 1 = 0: the assembled operator keeps the constant null space
+    loc = np.arange(8 * E).reshape(E, 8)
+    Ai = np.repeat(loc[:, :, None], 8, axis=2)                    # ia(i,j,e) = (e-1) n + i - 1, ja(i,j,e) = (e-1) n + j - 1
+    Aj = np.repeat(loc[:, None, :], 8, axis=1)
+    h = nek.crs_setup(ids.ravel(), Ai.ravel(), Aj.ravel(), Ae.ravel(), null_space)
+    gids = np.unique(ids[ids != 0])
+    dof = np.searchsorted(gids, ids.ravel())
+    keep = ids.ravel() != 0
+    nc = len(gids)
+    A = np.zeros((nc, nc))
+    np.add.at(A, (dof[Ai.ravel()][keep[Ai.ravel()] & keep[Aj.ravel()]], dof[Aj.ravel()][keep[Ai.ravel()] & keep[Aj.ravel()]]),
+              Ae.ravel()[keep[Ai.ravel()] & keep[Aj.ravel()]])
+    b = rng.standard_normal(8 * E)
+    g = np.zeros(nc)
+    np.add.at(g, dof[keep], b[keep])
+    if null_space:
+        b[keep] -= g.sum() / keep.sum()                           # consistent: the assembled right-hand side sums to zero
+        g = np.zeros(nc)
+        np.add.at(g, dof[keep], b[keep])
+        y = np.linalg.lstsq(A, g, rcond=None)[0]
+        y -= y.mean()
+    else:
+        y = np.linalg.solve(A, g)
+    want = np.where(keep, y[np.minimum(dof, nc - 1)], 0.0)
+    got = nek.crs_solve(h, b)
+    assert np.array_equal(got[~keep], np.zeros((~keep).sum()))
+    assert relmax(got, want) <= 1e-9
+    nek.crs_free(h)
