@@ -283,6 +283,16 @@ def ref_h1mg_lx6():
     return _pressure("core", 6)
 
 
+def ref_h1mg_lx4():
+    """lx1 = 4: the two-level form (mg_h1_lmax = 2, orders 1, 3; core/hsmg.f:2293)."""
+    return _pressure("core", 4)
+
+
+def ref_h1mg_lx10():
+    """lx1 = 10: orders 1, 3, 9."""
+    return _pressure("core", 10)
+
+
 def ref_periodic():
     """setupds / setvert3d (core/navier8.f:2004-2360) and the multiplicity on a box that is periodic in x and z: the vertex
     ids identify opposite sides, so faces, edges and corners wrap around."""
@@ -520,7 +530,7 @@ def ref_map():
     return out
 
 
-REFERENCE = dict(channel=ref_channel, ethier=ref_ethier, core=ref_core, core_lx6=ref_core_lx6, h1mg_lx6=ref_h1mg_lx6, periodic=ref_periodic, map=ref_map, eop=ref_eop, uzawa=ref_uzawa, hsolve=ref_hsolve, hsolve_pres=ref_hsolve_pres, ophinv=ref_ophinv, bp5=ref_bp5, h1mg=ref_h1mg, h1mg_neumann=ref_h1mg_neumann, fdm=ref_fdm, pnpn2=ref_pnpn2)
+REFERENCE = dict(channel=ref_channel, ethier=ref_ethier, core=ref_core, core_lx6=ref_core_lx6, h1mg_lx6=ref_h1mg_lx6, h1mg_lx4=ref_h1mg_lx4, h1mg_lx10=ref_h1mg_lx10, periodic=ref_periodic, map=ref_map, eop=ref_eop, uzawa=ref_uzawa, hsolve=ref_hsolve, hsolve_pres=ref_hsolve_pres, ophinv=ref_ophinv, bp5=ref_bp5, h1mg=ref_h1mg, h1mg_neumann=ref_h1mg_neumann, fdm=ref_fdm, pnpn2=ref_pnpn2)
 
 
 def reference_all():

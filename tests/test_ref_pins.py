@@ -42,6 +42,9 @@ def test_golden_file_is_what_the_reference_computes_now(name):
         pytest.skip("Pn-Pn-2 build of oracle/_ref not available")
     if name in ("core_lx6", "h1mg_lx6") and not ref.available(6, 6, 64):
         pytest.skip("lx1 = 6 build of oracle/_ref not available")
+    for nx in (4, 10):
+        if name == f"h1mg_lx{nx}" and not ref.available(nx, nx, 64):
+            pytest.skip(f"lx1 = {nx} build of oracle/_ref not available")
     live = refcases.REFERENCE[name]()
     assert set(live) == set(G[name])
     for k, v in live.items():
@@ -267,11 +270,13 @@ def test_uzawa_gmres_on_the_pnpn2_pressure_operator():
     assert relmax(x, g["x"]) <= 1e-9 and relmax(x, g["pe"]) <= 1e-6
 
 
-def test_h1mg_and_gmres_at_lx1_6():
-    """Multigrid orders (1, 3, 5) at lx1 = 6: the restatement against the reference's own h1mg_solve / hmh_gmres / hmh_flex_cg."""
-    g, c = G["h1mg_lx6"], refcases.case_of("core", 6)
+@pytest.mark.parametrize("nx,orders", [(6, [1, 3, 5]), (4, [1, 3]), (10, [1, 3, 9])])
+def test_h1mg_and_gmres_at_other_orders(nx, orders):
+    """Multigrid orders at lx1 = 6, 4 (two levels only, hsmg.f:2293) and 10: the restatement against the reference's own
+    h1mg_solve / hmh_gmres / hmh_flex_cg."""
+    g, c = G[f"h1mg_lx{nx}"], refcases.case_of("core", nx)
     mg = hsmg.H1MG(c, refcases.fbc_of("core", c), null_space=False)
-    assert mg.mg_nx == [1, 3, 5]
+    assert mg.mg_nx == orders
     r = g["rhs"].copy()
     assert relmax(mg.solve(r), g["z"]) <= 1e-12 and np.array_equal(r, g["rhs_out"])
     n = c.n
