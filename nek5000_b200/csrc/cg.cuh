@@ -332,9 +332,11 @@ __global__ void __launch_bounds__(CG_THREADS)
     });
 }
 
-// EXPERIMENT, off by default -- measured slower than the gs + update pair at E = 262,144 (2.15 vs 0.61 + 0.66 ms per
-// iteration, profiles/r1o_gs_fuse_experiment_v*.json; bit-identical results): kept for an ncu look at where the extra
-// traffic of the scattered partner reads comes from.
+// EXPERIMENT, off by default.  Mode 1 (every group gathered here) measured slower than the gs + update pair at E = 262,144
+// (2.15 vs 0.61 + 0.66 ms per iteration, profiles/r1o_gs_fuse_experiment_v*.json; bit-identical results) -- the suspected
+// cost is the edge / corner nodes (80 of 512 per element), each walking its group's CSR through three dependent, divergent
+// loads.  Mode 2 therefore assembles those groups in place first (gs_local_kernel on goff3 / gidx3) and gathers only the
+// face pairs here; it was written after the GPU budget was spent and has NOT been run yet.
 // The same update with the direct-stiffness summation folded in (one rank, NEKB_GS_FUSE_UPDATE=1): `ap` holds the
 // UN-assembled A p; every node gathers the members of its group on the fly (gs.cuh gs_gathered: the bits gs_op would
 // produce), so the assembled vector is never written back or re-read -- the scattered partner reads are served by L2
@@ -470,8 +472,10 @@ inline int cggos_run_fused(const CggosArgs &a, int maxit, double *hist_host, boo
     NEKB_REQUIRE(h.n == n, "cggos: gs handle was set up for a different vector length");
 
     // gather form of dssum inside the update kernel: one rank only (no remote members to wait for)
-    const bool gather = gs_fuse_update_enabled() && c.nranks == 1 && h.nshared == 0;
-    if (gather) gs_ensure_link(h);
+    // (1 = every group gathered by the update kernel; 2 = pairs gathered, edge / corner groups assembled in place first)
+    const int gmode = gs_fuse_update_enabled();
+    const bool gather = (gmode == 1 || gmode == 2) && c.nranks == 1 && h.nshared == 0;
+    if (gather) gs_ensure_link(h, gmode);
     cggos_init2_kernel<<<grid, CG_THREADS, 0, s>>>(a.u, r.p, a.rhs, a.mult, n, sc, c.partials.p + 1 * CG_PART_STRIDE);
     NEKB_LAUNCHED();
     comm_allreduce_sum(&sc->work[1], 1);
@@ -485,6 +489,12 @@ inline int cggos_run_fused(const CggosArgs &a, int maxit, double *hist_host, boo
         prof_end(PROF_AX);
         comm_allreduce_sum(&sc->work[0], 1);
         if (gather) {
+            if (gmode == 2 && h.ngroups3 > 0) {
+                prof_begin(PROF_GS);
+                gs_local_kernel<1><<<blocks_for(h.ngroups3), 256, 0, s>>>(ap.p, h.goff3.p, h.gidx3.p, (int)h.ngroups3);
+                NEKB_LAUNCHED();
+                prof_end(PROF_GS);
+            }
             prof_begin(PROF_UPDATE);
             cggos_update2_gs_kernel<<<grid, CG_THREADS, 0, s>>>(r.p, ap.p, c.wcode.p, h.link.p, h.goff.p, h.gidx.p, n, sc,
                                                                 c.partials.p + 2 * CG_PART_STRIDE);

@@ -58,7 +58,9 @@ struct GsMap {
     DevBuf<int32_t> gidx;          // [nmembers] member indices, ascending inside a group
     DevBuf<int32_t> link;          // [n] node -> its group, for gather-style consumers (gs.cuh gs_ensure_link): -1 not in a
                                    // group, >= 0 the other member of a pair, <= -2 group -2-g (three or more members)
-    bool link_built = false;
+    int link_mode = 0;             // 0 not built, 1 every group through `link`, 2 pairs through `link` + goff3/gidx3
+    DevBuf<int32_t> goff3, gidx3;  // CSR of the groups with three or more members (edges, corners), link_mode 2
+    int64_t ngroups3 = 0;
     // ---- remote part (np > 1): ids shared with other ranks --------------------------------------
     int64_t nshared = 0;           // local unique ids that also live on another rank
     std::vector<int> peers;        // neighbour ranks, ascending

@@ -99,7 +99,7 @@ inline void gs_build_local(GsMap &h, const int64_t *id_dev, int64_t n)
     NEKB_REQUIRE(n < (int64_t)2147483647, "gs_setup: local vector too long for int32 indexing");
     h.n = n;
     h.ngroups = h.nmembers = 0;
-    h.link_built = false;
+    h.link_mode = 0;
     if (n == 0) return;
 
     DevBuf<int32_t> idx_nz, idx_sorted, num;
@@ -244,30 +244,50 @@ inline void gs_local(GsMap &h, double *u, int op)
 // edge / corner nodes the group number.  Built on first use, 4 bytes per node.
 __global__ void __launch_bounds__(256)
     gs_build_link_kernel(int32_t *__restrict__ link, const int32_t *__restrict__ goff, const int32_t *__restrict__ gidx,
-                         int ngroups)
+                         int ngroups, int pairs_only)
 {
     for (int gI = blockIdx.x * blockDim.x + threadIdx.x; gI < ngroups; gI += gridDim.x * blockDim.x) {
         const int b = goff[gI], e = goff[gI + 1];
         if (e - b == 2) {
             link[gidx[b]] = gidx[b + 1];
             link[gidx[b + 1]] = gidx[b];
-        } else {
+        } else if (!pairs_only) {
             for (int q = b; q < e; q++) link[gidx[q]] = -2 - gI;
         }
     }
 }
 
-inline void gs_ensure_link(GsMap &h)
+// mode 1: every group is reachable from `link`; mode 2: only pairs are, and the groups with three or more members (edge and
+// corner nodes: 19 of an interior element's 127 groups) get their own CSR so that gs_local_kernel can assemble them in place
+// before the gathering kernel runs (their members then read their own, already assembled, value).
+inline void gs_ensure_link(GsMap &h, int mode)
 {
-    if (h.link_built) return;
+    if (h.link_mode == mode) return;
     Ctx &c = ctx();
+    cudaStream_t s = c.stream;
     h.link.alloc((size_t)(h.n > 0 ? h.n : 1));
-    NEKB_CUDA(cudaMemsetAsync(h.link.p, 0xFF, sizeof(int32_t) * (size_t)(h.n > 0 ? h.n : 1), c.stream));
+    NEKB_CUDA(cudaMemsetAsync(h.link.p, 0xFF, sizeof(int32_t) * (size_t)(h.n > 0 ? h.n : 1), s));
     if (h.ngroups > 0) {
-        gs_build_link_kernel<<<blocks_for(h.ngroups), 256, 0, c.stream>>>(h.link.p, h.goff.p, h.gidx.p, (int)h.ngroups);
+        gs_build_link_kernel<<<blocks_for(h.ngroups), 256, 0, s>>>(h.link.p, h.goff.p, h.gidx.p, (int)h.ngroups, mode == 2);
         NEKB_LAUNCHED();
     }
-    h.link_built = true;
+    h.ngroups3 = 0;
+    if (mode == 2 && h.ngroups > 0) {   // set-up only: filtered on the host
+        std::vector<int32_t> off((size_t)h.ngroups + 1), idx((size_t)h.nmembers), off3(1, 0), idx3;
+        h.goff.download(off.data(), off.size(), s);
+        h.gidx.download(idx.data(), idx.size(), s);
+        for (int64_t g = 0; g < h.ngroups; g++)
+            if (off[g + 1] - off[g] >= 3) {
+                idx3.insert(idx3.end(), idx.begin() + off[g], idx.begin() + off[g + 1]);
+                off3.push_back((int32_t)idx3.size());
+            }
+        h.ngroups3 = (int64_t)off3.size() - 1;
+        if (idx3.empty()) idx3.push_back(0);
+        h.goff3.upload(off3.data(), off3.size(), s);
+        h.gidx3.upload(idx3.data(), idx3.size(), s);
+        NEKB_CUDA(cudaStreamSynchronize(s));
+    }
+    h.link_mode = mode;
 }
 
 // The value gs_op(+) would leave at a node, read from the un-assembled vector: same members, same (ascending) order as
