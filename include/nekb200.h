@@ -381,6 +381,15 @@ void crs_setup_(int *handle, const int *sid, const int *comm, const int *np, con
 void crs_solve_(const int *handle, double *x, const double *b);
 void crs_free_(const int *handle);
 int nekb_fcrs_solve_dev(int handle, double *x_dev, const double *b_dev);
+/* HOST set-up only (nek5000_b200/csrc/crs_amg.cuh; no device work, nothing in the solve path uses it yet): an aggregation
+ * hierarchy for coarse problems beyond the dense limit -- the role of crs_xxt.c / crs_amg.c's set-up.  Input: the assembled
+ * operator as COO triplets over 0-based dofs (duplicates are summed in input order); levels are built until <= nmax rows
+ * (greedy aggregation with strength threshold theta, piecewise-constant prolongation, Galerkin products).  level_get copies
+ * a level's CSR (rowptr[n+1], col[nnz], val[nnz]) and, for every level but the coarsest, its aggregate map agg[n]. */
+int nekb_crs_amg_build_host(int64_t n, int64_t nz, const int64_t *I, const int64_t *J, const double *V, int64_t nmax, double theta,
+                            int *nlevels);
+int nekb_crs_amg_level_info(int level, int64_t *n, int64_t *nnz);
+int nekb_crs_amg_level_get(int level, int64_t *rowptr, int32_t *col, double *val, int32_t *agg);
 /* Host copies of setup products for parity tests.  which: "mask","rstr_wt","swt" (level-sized, level 1-based),
  * "J" (interpolation level -> level+1, row-major nf x nc), "lm","ll","lr" (3*nelv, direction-major; level ignored),
  * "crs_a" (64*nelv, a(i,j,e) as a[e][i][j]). */

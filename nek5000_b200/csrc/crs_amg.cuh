@@ -1,0 +1,137 @@
+// crs_amg.cuh -- HOST set-up of an aggregation hierarchy for coarse (vertex-mesh) problems that are too large for the dense
+// inverse of hsmg.cuh (> NEKB_CRS_DENSE_MAX distinct vertices).
+//
+// Role in the reference: crs_solve (core/fcrs.c:80 -> core/crs_xxt.c:926-965, or core/crs_amg.c with param(40) = 1) solves
+// the assembled vertex-mesh system directly.  Plan here (prototype scripts/proto_coarse_amg.py): CG to
+// rounding level preconditioned by one cycle over this hierarchy -- greedy aggregation on the strength graph, piecewise-
+// constant prolongation, Galerkin coarse matrices, damped Jacobi, the dense inverse at the coarsest level.
+//
+// STATUS: this file is set-up only and runs on the host (like setvert3d_host and gen_fast); it is exercised on the CPU by
+// tests/test_crs_amg_host.py through nekb_crs_amg_*.  The device cycle (CSR mat-vec, gather / scatter by aggregate) that
+// consumes it is NOT written yet, and nothing in the solve path uses this file.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <numeric>
+#include <vector>
+
+#include "common.cuh"
+
+namespace nekb {
+
+struct CsrHost {
+    int64_t n = 0;
+    std::vector<int64_t> rowptr;   // [n+1]
+    std::vector<int32_t> col;      // ascending inside a row
+    std::vector<double> val;
+    int64_t nnz() const { return (int64_t)col.size(); }
+};
+
+// Sums duplicate (i,j) entries in INPUT order (stable sort), drops nothing: explicit zeros of the element matrices stay in
+// the pattern, exactly as an assembled element-by-element operator has them.
+inline CsrHost csr_from_triplets(int64_t n, const std::vector<int64_t> &I, const std::vector<int64_t> &J, const std::vector<double> &V)
+{
+    NEKB_REQUIRE(I.size() == J.size() && I.size() == V.size(), "csr_from_triplets: ragged input");
+    std::vector<int64_t> ord(I.size());
+    std::iota(ord.begin(), ord.end(), (int64_t)0);
+    std::stable_sort(ord.begin(), ord.end(), [&](int64_t a, int64_t b) { return I[a] != I[b] ? I[a] < I[b] : J[a] < J[b]; });
+    CsrHost A;
+    A.n = n;
+    A.rowptr.assign((size_t)n + 1, 0);
+    int64_t pi = -1, pj = -1;
+    for (int64_t q : ord) {
+        NEKB_REQUIRE(I[q] >= 0 && I[q] < n && J[q] >= 0 && J[q] < n, "csr_from_triplets: index outside the matrix");
+        if (I[q] == pi && J[q] == pj) {
+            A.val.back() += V[q];
+        } else {
+            A.col.push_back((int32_t)J[q]);
+            A.val.push_back(V[q]);
+            A.rowptr[(size_t)I[q] + 1]++;
+            pi = I[q], pj = J[q];
+        }
+    }
+    for (int64_t i = 0; i < n; i++) A.rowptr[i + 1] += A.rowptr[i];
+    return A;
+}
+
+// Greedy aggregation on the strength graph |a_ij| >= theta sqrt(a_ii a_jj), i != j: in index order, a free vertex whose
+// strong neighbours are all free becomes a root and takes them; the leftovers then, again in index order, join the aggregate
+// of their strongest aggregated strong neighbour (first one on ties, column order; leftovers placed earlier count), or start
+// their own.
+inline std::vector<int32_t> amg_aggregate(const CsrHost &A, double theta, int32_t &na)
+{
+    const int64_t n = A.n;
+    std::vector<double> d((size_t)n, 0.0);
+    for (int64_t i = 0; i < n; i++)
+        for (int64_t q = A.rowptr[i]; q < A.rowptr[i + 1]; q++)
+            if (A.col[q] == i) d[i] = A.val[q];
+    auto strong = [&](int64_t i, int64_t q) {
+        const int32_t j = A.col[q];
+        return j != i && std::fabs(A.val[q]) >= theta * std::sqrt(d[i] * d[j]);
+    };
+    std::vector<int32_t> agg((size_t)n, -1);
+    na = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if (agg[i] >= 0) continue;
+        bool all_free = true;
+        for (int64_t q = A.rowptr[i]; q < A.rowptr[i + 1] && all_free; q++)
+            if (strong(i, q) && agg[A.col[q]] >= 0) all_free = false;
+        if (!all_free) continue;
+        agg[i] = na;
+        for (int64_t q = A.rowptr[i]; q < A.rowptr[i + 1]; q++)
+            if (strong(i, q)) agg[A.col[q]] = na;
+        na++;
+    }
+    for (int64_t i = 0; i < n; i++) {
+        if (agg[i] >= 0) continue;
+        double best = -1.0;
+        int32_t to = -1;
+        for (int64_t q = A.rowptr[i]; q < A.rowptr[i + 1]; q++)
+            if (strong(i, q) && agg[A.col[q]] >= 0 && std::fabs(A.val[q]) > best) best = std::fabs(A.val[q]), to = agg[A.col[q]];
+        if (to < 0) to = na++;
+        agg[i] = to;
+    }
+    return agg;
+}
+
+// A_c = P^T A P for the piecewise-constant P of `agg` (A_c[I][J] = sum of a_ij over i in I, j in J), summed in row-major
+// order of the fine matrix.
+inline CsrHost amg_galerkin(const CsrHost &A, const std::vector<int32_t> &agg, int32_t na)
+{
+    std::vector<int64_t> I, J;
+    std::vector<double> V;
+    I.reserve((size_t)A.nnz()), J.reserve((size_t)A.nnz()), V.reserve((size_t)A.nnz());
+    for (int64_t i = 0; i < A.n; i++)
+        for (int64_t q = A.rowptr[i]; q < A.rowptr[i + 1]; q++) I.push_back(agg[i]), J.push_back(agg[A.col[q]]), V.push_back(A.val[q]);
+    return csr_from_triplets(na, I, J, V);
+}
+
+struct AmgHierarchy {
+    std::vector<CsrHost> A;                   // A[0] = the fine operator ... A.back() = the coarsest (dense inverse)
+    std::vector<std::vector<int32_t>> agg;    // agg[l][i] = aggregate (row of A[l+1]) of row i of A[l]
+};
+
+inline AmgHierarchy amg_build(CsrHost A0, int64_t nmax, double theta)
+{
+    NEKB_REQUIRE(nmax >= 1 && theta > 0.0, "amg_build: bad parameters");
+    AmgHierarchy H;
+    H.A.push_back(std::move(A0));
+    while (H.A.back().n > nmax) {
+        int32_t na = 0;
+        std::vector<int32_t> g = amg_aggregate(H.A.back(), theta, na);
+        NEKB_REQUIRE((double)na < 0.7 * (double)H.A.back().n, "amg_build: aggregation stalled (no strong connections at this theta)");
+        CsrHost Ac = amg_galerkin(H.A.back(), g, na);
+        H.agg.push_back(std::move(g));
+        H.A.push_back(std::move(Ac));
+    }
+    return H;
+}
+
+inline AmgHierarchy &amg_host_hierarchy()
+{
+    static AmgHierarchy h;
+    return h;
+}
+
+}  // namespace nekb

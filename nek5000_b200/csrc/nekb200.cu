@@ -7,6 +7,7 @@
 #include "proj.cuh"
 #include "pnpn2.cuh"
 #include "readers.cuh"
+#include "crs_amg.cuh"
 
 using namespace nekb;
 
@@ -1982,6 +1983,42 @@ int nekb_co2_read(const char *path, int nlv, int64_t e0, int64_t nel, int64_t *e
         const Co2Header h = co2_header(fh);
         NEKB_REQUIRE(nlv == h.nv, "Number of vertices do not match!");          // map2.f:443-444
         co2_read(fh, h, e0, nel, eid, vertex);
+    });
+}
+// ---- host set-up of the aggregation hierarchy for large coarse problems (crs_amg.cuh; no device work)
+int nekb_crs_amg_build_host(int64_t n, int64_t nz, const int64_t *I, const int64_t *J, const double *V, int64_t nmax, double theta,
+                            int *nlevels)
+{
+    return guard([&] {
+        NEKB_REQUIRE(n >= 1 && nz >= 1 && I && J && V, "crs_amg_build_host: bad arguments");
+        std::vector<int64_t> vi(I, I + nz), vj(J, J + nz);
+        std::vector<double> vv(V, V + nz);
+        amg_host_hierarchy() = amg_build(csr_from_triplets(n, vi, vj, vv), nmax, theta);
+        if (nlevels) *nlevels = (int)amg_host_hierarchy().A.size();
+    });
+}
+int nekb_crs_amg_level_info(int level, int64_t *n, int64_t *nnz)
+{
+    return guard([&] {
+        AmgHierarchy &H = amg_host_hierarchy();
+        NEKB_REQUIRE(level >= 0 && level < (int)H.A.size(), "crs_amg_level_info: no such level");
+        if (n) *n = H.A[level].n;
+        if (nnz) *nnz = H.A[level].nnz();
+    });
+}
+int nekb_crs_amg_level_get(int level, int64_t *rowptr, int32_t *col, double *val, int32_t *agg)
+{
+    return guard([&] {
+        AmgHierarchy &H = amg_host_hierarchy();
+        NEKB_REQUIRE(level >= 0 && level < (int)H.A.size(), "crs_amg_level_get: no such level");
+        const CsrHost &A = H.A[level];
+        if (rowptr) std::copy(A.rowptr.begin(), A.rowptr.end(), rowptr);
+        if (col) std::copy(A.col.begin(), A.col.end(), col);
+        if (val) std::copy(A.val.begin(), A.val.end(), val);
+        if (agg) {
+            NEKB_REQUIRE(level < (int)H.agg.size(), "crs_amg_level_get: the coarsest level has no aggregates");
+            std::copy(H.agg[level].begin(), H.agg[level].end(), agg);
+        }
     });
 }
 int nekb_assign_gllnid(int *gllnid, int64_t nelgt, int64_t nelgv, int np)

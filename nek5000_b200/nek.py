@@ -582,6 +582,27 @@ def crs_free(handle: int) -> None:
     lib().crs_free_(_i(handle))
 
 
+def crs_amg_build_host(n: int, I, J, V, nmax: int = 4096, theta: float = 0.02):
+    """Host set-up of the aggregation hierarchy (csrc/crs_amg.cuh).  Returns a list of levels, each a dict with `rowptr`, `col`,
+    `val` (CSR) and, except for the coarsest, `agg` (row -> aggregate = row of the next level)."""
+    I, J = (np.ascontiguousarray(a, dtype=np.int64).reshape(-1) for a in (I, J))
+    V = np.ascontiguousarray(V, dtype=np.float64).reshape(-1)
+    nl = C.c_int(0)
+    check(lib().nekb_crs_amg_build_host(int(n), V.size, _ptr(I), _ptr(J), _ptr(V), int(nmax), float(theta), C.byref(nl)))
+    levels = []
+    for l in range(nl.value):
+        nn, nz = C.c_int64(0), C.c_int64(0)
+        check(lib().nekb_crs_amg_level_info(l, C.byref(nn), C.byref(nz)))
+        lv = dict(n=int(nn.value), rowptr=np.zeros(nn.value + 1, dtype=np.int64), col=np.zeros(nz.value, dtype=np.int32),
+                  val=np.zeros(nz.value))
+        agg = np.zeros(nn.value, dtype=np.int32) if l + 1 < nl.value else None
+        check(lib().nekb_crs_amg_level_get(l, _ptr(lv["rowptr"]), _ptr(lv["col"]), _ptr(lv["val"]), None if agg is None else _ptr(agg)))
+        if agg is not None:
+            lv["agg"] = agg
+        levels.append(lv)
+    return levels
+
+
 # --------------------------------------------------------------------------------------------- device arrays
 class DevArray:
     """A device buffer owned through the C-ABI helpers (section E of the header)."""
