@@ -390,6 +390,11 @@ int nekb_crs_amg_build_host(int64_t n, int64_t nz, const int64_t *I, const int64
                             int *nlevels);
 int nekb_crs_amg_level_info(int level, int64_t *n, int64_t *nnz);
 int nekb_crs_amg_level_get(int level, int64_t *rowptr, int32_t *col, double *val, int32_t *agg);
+/* Device side of the same (csrc/crs_amg_dev.cuh; compiled, NOT YET RUN ON A GPU, not used by h1mg_solve): upload moves the
+ * host hierarchy to the device (damped-Jacobi weight omega) and inverts the coarsest operator; solve_dev runs CG on the
+ * finest operator, preconditioned by one V(1,1) cycle, to a relative 2-norm residual tol (SPD systems). */
+int nekb_crs_amg_upload(double omega);
+int nekb_crs_amg_solve_dev(double *x_dev, const double *b_dev, double tol, int maxit, int *iters);
 /* Host copies of setup products for parity tests.  which: "mask","rstr_wt","swt" (level-sized, level 1-based),
  * "J" (interpolation level -> level+1, row-major nf x nc), "lm","ll","lr" (3*nelv, direction-major; level ignored),
  * "crs_a" (64*nelv, a(i,j,e) as a[e][i][j]). */

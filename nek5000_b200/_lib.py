@@ -124,6 +124,8 @@ def lib() -> C.CDLL:
     L.nekb_crs_amg_build_host.argtypes = [C.c_int64, C.c_int64, vp, vp, vp, C.c_int64, C.c_double, ip]
     L.nekb_crs_amg_level_info.argtypes = [C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.nekb_crs_amg_level_get.argtypes = [C.c_int, vp, vp, vp, vp]
+    L.nekb_crs_amg_upload.argtypes = [C.c_double]
+    L.nekb_crs_amg_solve_dev.argtypes = [vp, vp, C.c_double, C.c_int, ip]
     L.nekb_co2_info.argtypes = [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), ip]
     L.nekb_co2_read.argtypes = [C.c_char_p, C.c_int, C.c_int64, C.c_int64, vp, vp]
     L.nekb_assign_gllnid.argtypes = [vp, C.c_int64, C.c_int64, C.c_int]

@@ -1,0 +1,265 @@
+// crs_amg_dev.cuh -- device cycle over the host-built aggregation hierarchy of crs_amg.cuh: CG on the assembled coarse
+// operator, preconditioned by one V(1,1) cycle (damped Jacobi, piecewise-constant transfer, dense inverse at the coarsest
+// level through the crsd_* kernels of hsmg.cuh).  Plan and iteration counts: DESIGN.md section 8, scripts/proto_coarse_amg.py.
+//
+// STATUS: written after round 1's GPU budget was spent -- compiled, NOT YET RUN ON A GPU, not wired into h1mg_solve.  Entry
+// points nekb_crs_amg_upload / nekb_crs_amg_solve_dev; parity test (against numpy on the same levels) in
+// tests/test_zz_gpu_configs.py behind NEKB_TEST_UNVALIDATED=1.  SPD systems only (no null-space handling at this layer yet);
+// the CG loop reads its scalars back every iteration (to be replaced by device-side control + a captured graph once correct).
+#pragma once
+#include "crs_amg.cuh"
+#include "hsmg.cuh"
+
+namespace nekb {
+
+struct AmgLevelDev {
+    int64_t n = 0, nnz = 0;
+    DevBuf<int32_t> rowptr, col;       // CSR (nnz < 2^31)
+    DevBuf<double> val, dj;            // dj = omega / diag
+    DevBuf<int32_t> agg;               // row -> row of the next level
+    DevBuf<int32_t> moff, mem;         // CSR of the next level's rows -> their members here, ascending
+    DevBuf<double> b, x, x2, r;        // cycle work vectors of this level
+};
+struct AmgDev {
+    bool ready = false;
+    std::vector<AmgLevelDev> L;        // every level but the coarsest
+    int64_t nc = 0, ld = 0;            // coarsest size, padded leading dimension
+    DevBuf<double> ainv, cb, cy;       // explicit inverse, rhs / solution of the coarsest level
+    DevBuf<double> r, z, p, w, partial, scal;
+};
+inline AmgDev &amg_dev()
+{
+    static AmgDev a;
+    return a;
+}
+
+constexpr int AMG_T = 256;
+inline int amg_grid(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + AMG_T - 1) / AMG_T, (int64_t)ctx().num_sms * 8)); }
+
+// x = dj b (first Jacobi sweep from a zero guess) and r = b - A x, one thread per row
+__global__ void __launch_bounds__(AMG_T)
+    amg_presmooth_kernel(double *__restrict__ x, double *__restrict__ r, const double *__restrict__ b, const double *__restrict__ dj,
+                         const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, const double *__restrict__ val, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int q = rowptr[i]; q < rowptr[i + 1]; q++) s = fma(val[q], dj[col[q]] * b[col[q]], s);
+        x[i] = dj[i] * b[i];
+        r[i] = b[i] - s;
+    }
+}
+// y = A x
+__global__ void __launch_bounds__(AMG_T)
+    amg_spmv_kernel(double *__restrict__ y, const double *__restrict__ x, const int32_t *__restrict__ rowptr,
+                    const int32_t *__restrict__ col, const double *__restrict__ val, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int q = rowptr[i]; q < rowptr[i + 1]; q++) s = fma(val[q], x[col[q]], s);
+        y[i] = s;
+    }
+}
+// xo = x + dj (b - A x)
+__global__ void __launch_bounds__(AMG_T)
+    amg_postsmooth_kernel(double *__restrict__ xo, const double *__restrict__ x, const double *__restrict__ b,
+                          const double *__restrict__ dj, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                          const double *__restrict__ val, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int q = rowptr[i]; q < rowptr[i + 1]; q++) s = fma(val[q], x[col[q]], s);
+        xo[i] = x[i] + dj[i] * (b[i] - s);
+    }
+}
+// bc = P^T r: members summed in ascending order
+__global__ void __launch_bounds__(AMG_T)
+    amg_restrict_kernel(double *__restrict__ bc, const double *__restrict__ r, const int32_t *__restrict__ moff,
+                        const int32_t *__restrict__ mem, int64_t nc)
+{
+    for (int64_t I = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; I < nc; I += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int q = moff[I]; q < moff[I + 1]; q++) s += r[mem[q]];
+        bc[I] = s;
+    }
+}
+// x += P e
+__global__ void __launch_bounds__(AMG_T)
+    amg_prolong_add_kernel(double *__restrict__ x, const double *__restrict__ e, const int32_t *__restrict__ agg, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] += e[agg[i]];
+}
+// partial[block] = sum a b over the block's rows; amg_dot_final sums the partials in order into out[slot]
+__global__ void __launch_bounds__(AMG_T)
+    amg_dot_kernel(double *__restrict__ partial, const double *__restrict__ a, const double *__restrict__ b, int64_t n)
+{
+    __shared__ double red[33];
+    double s = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s = fma(a[i], b[i], s);
+    const double t = block_reduce(s, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+__global__ void __launch_bounds__(AMG_T) amg_dot_final_kernel(double *__restrict__ out, const double *__restrict__ partial, int nb)
+{
+    __shared__ double red[33];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) s += partial[i];
+    const double t = block_reduce(s, red);
+    if (threadIdx.x == 0) *out = t;
+}
+// y += a x ; y = x + a y
+__global__ void __launch_bounds__(AMG_T) amg_axpy_kernel(double *__restrict__ y, const double *__restrict__ x, double a, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = fma(a, x[i], y[i]);
+}
+__global__ void __launch_bounds__(AMG_T) amg_xpay_kernel(double *__restrict__ y, const double *__restrict__ x, double a, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = fma(a, y[i], x[i]);
+}
+
+// Moves the host hierarchy to the device and inverts the coarsest operator (blocked Gauss-Jordan of hsmg.cuh).
+inline void amg_upload(double omega)
+{
+    Ctx &c = ctx();
+    cudaStream_t s = c.stream;
+    const AmgHierarchy &H = amg_host_hierarchy();
+    NEKB_REQUIRE(!H.A.empty(), "crs_amg_upload: nekb_crs_amg_build_host has not been called");
+    AmgDev &D = amg_dev();
+    D = AmgDev();
+    const size_t nl = H.A.size() - 1;
+    D.L.resize(nl);
+    for (size_t l = 0; l < nl; l++) {
+        const CsrHost &A = H.A[l];
+        AmgLevelDev &L = D.L[l];
+        NEKB_REQUIRE(A.nnz() < (int64_t)2147483647, "crs_amg_upload: level too large for int32 offsets");
+        L.n = A.n, L.nnz = A.nnz();
+        std::vector<int32_t> rp(A.rowptr.begin(), A.rowptr.end());
+        std::vector<double> dj((size_t)A.n, 0.0);
+        for (int64_t i = 0; i < A.n; i++)
+            for (int64_t q = A.rowptr[i]; q < A.rowptr[i + 1]; q++)
+                if (A.col[q] == i) dj[i] = omega / A.val[q];
+        const int64_t ncn = H.A[l + 1].n;
+        std::vector<int32_t> moff((size_t)ncn + 1, 0), mem((size_t)A.n);
+        for (int64_t i = 0; i < A.n; i++) moff[(size_t)H.agg[l][i] + 1]++;
+        for (int64_t I = 0; I < ncn; I++) moff[I + 1] += moff[I];
+        std::vector<int32_t> cur(moff.begin(), moff.end() - 1);
+        for (int64_t i = 0; i < A.n; i++) mem[cur[H.agg[l][i]]++] = (int32_t)i;
+        L.rowptr.upload(rp.data(), rp.size(), s), L.col.upload(A.col.data(), A.col.size(), s), L.val.upload(A.val.data(), A.val.size(), s);
+        L.dj.upload(dj.data(), dj.size(), s), L.agg.upload(H.agg[l].data(), H.agg[l].size(), s);
+        L.moff.upload(moff.data(), moff.size(), s), L.mem.upload(mem.data(), mem.size(), s);
+        L.x.alloc((size_t)A.n), L.x2.alloc((size_t)A.n), L.r.alloc((size_t)A.n);
+        if (l > 0) L.b.alloc((size_t)A.n);
+        NEKB_CUDA(cudaStreamSynchronize(s));   // the host vectors above go out of scope
+    }
+    const CsrHost &Ac = H.A.back();
+    D.nc = Ac.n, D.ld = crsd_ld(Ac.n);
+    std::vector<double> M((size_t)D.ld * D.ld, 0.0);
+    for (int64_t i = 0; i < Ac.n; i++)
+        for (int64_t q = Ac.rowptr[i]; q < Ac.rowptr[i + 1]; q++) M[(size_t)i * D.ld + Ac.col[q]] = Ac.val[q];
+    for (int64_t v = Ac.n; v < D.ld; v++) M[(size_t)v * D.ld + v] = 1.0;
+    D.ainv.upload(M.data(), M.size(), s);
+    const int nb = (int)(D.ld / CRS_NB);
+    for (int kb = 0; kb < nb; kb++) {
+        crsd_pivot_kernel<<<1, 256, 0, s>>>(D.ainv.p, D.ld, kb);
+        NEKB_LAUNCHED();
+        if (nb > 1) {
+            crsd_row_kernel<<<nb, 256, 0, s>>>(D.ainv.p, D.ld, kb);
+            NEKB_LAUNCHED();
+            crsd_trail_kernel<<<dim3(nb, nb), 256, 0, s>>>(D.ainv.p, D.ld, kb);
+            NEKB_LAUNCHED();
+            crsd_col_kernel<<<nb, 256, 0, s>>>(D.ainv.p, D.ld, kb);
+            NEKB_LAUNCHED();
+        }
+    }
+    D.cb.alloc((size_t)D.ld), D.cy.alloc((size_t)D.ld);
+    D.cb.zero(s), D.cy.zero(s);
+    const int64_t n0 = H.A[0].n;
+    D.r.alloc((size_t)n0), D.z.alloc((size_t)n0), D.p.alloc((size_t)n0), D.w.alloc((size_t)n0);
+    D.partial.alloc((size_t)c.num_sms * 8), D.scal.alloc(4);
+    NEKB_CUDA(cudaStreamSynchronize(s));
+    D.ready = true;
+}
+
+// z = M^-1 b: one V(1,1) cycle from level l down; b_dev of level 0 is the caller's, deeper levels use their own buffers
+inline void amg_cycle(size_t l, const double *b_dev, double *z_dev)
+{
+    Ctx &c = ctx();
+    cudaStream_t s = c.stream;
+    AmgDev &D = amg_dev();
+    if (l == D.L.size()) {   // coarsest: z = Ainv b
+        const int gw = (int)std::max<int64_t>(1, std::min<int64_t>((D.nc * 32 + 255) / 256, (int64_t)c.num_sms * 8));
+        crsd_gemv_kernel<<<gw, 256, 0, s>>>(z_dev, D.ainv.p, b_dev, D.nc, D.ld);
+        NEKB_LAUNCHED();
+        return;
+    }
+    AmgLevelDev &L = D.L[l];
+    const bool last = l + 1 == D.L.size();
+    const int64_t ncn = last ? D.nc : D.L[l + 1].n;
+    double *bc = last ? D.cb.p : D.L[l + 1].b.p;
+    double *ec = last ? D.cy.p : D.L[l + 1].x2.p;   // the next level leaves its result in its x2 (see the final smoother)
+    amg_presmooth_kernel<<<amg_grid(L.n), AMG_T, 0, s>>>(L.x.p, L.r.p, b_dev, L.dj.p, L.rowptr.p, L.col.p, L.val.p, L.n);
+    NEKB_LAUNCHED();
+    amg_restrict_kernel<<<amg_grid(ncn), AMG_T, 0, s>>>(bc, L.r.p, L.moff.p, L.mem.p, ncn);
+    NEKB_LAUNCHED();
+    amg_cycle(l + 1, bc, ec);
+    amg_prolong_add_kernel<<<amg_grid(L.n), AMG_T, 0, s>>>(L.x.p, ec, L.agg.p, L.n);
+    NEKB_LAUNCHED();
+    amg_postsmooth_kernel<<<amg_grid(L.n), AMG_T, 0, s>>>(z_dev, L.x.p, b_dev, L.dj.p, L.rowptr.p, L.col.p, L.val.p, L.n);
+    NEKB_LAUNCHED();
+}
+
+inline double amg_dot(const double *a, const double *b, int64_t n)
+{
+    Ctx &c = ctx();
+    AmgDev &D = amg_dev();
+    const int nb = std::min(amg_grid(n), (int)D.partial.n);
+    amg_dot_kernel<<<nb, AMG_T, 0, c.stream>>>(D.partial.p, a, b, n);
+    NEKB_LAUNCHED();
+    amg_dot_final_kernel<<<1, AMG_T, 0, c.stream>>>(D.scal.p, D.partial.p, nb);
+    NEKB_LAUNCHED();
+    double v = 0.0;
+    NEKB_CUDA(cudaMemcpyAsync(&v, D.scal.p, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    NEKB_CUDA(cudaStreamSynchronize(c.stream));
+    return v;
+}
+
+// CG on A[0] x = b to a relative residual `tol` (2-norm), preconditioned by amg_cycle.  Returns the iteration count.
+inline int amg_pcg_solve(double *x_dev, const double *b_dev, double tol, int maxit)
+{
+    Ctx &c = ctx();
+    cudaStream_t s = c.stream;
+    AmgDev &D = amg_dev();
+    NEKB_REQUIRE(D.ready, "crs_amg_solve: nekb_crs_amg_upload has not been called");
+    const bool flat = D.L.empty();   // the whole problem fits the dense inverse
+    const int64_t n = flat ? D.nc : D.L[0].n;
+    NEKB_CUDA(cudaMemsetAsync(x_dev, 0, sizeof(double) * (size_t)n, s));
+    if (flat) {
+        amg_cycle(0, b_dev, x_dev);
+        return 1;
+    }
+    AmgLevelDev &L = D.L[0];
+    const int g = amg_grid(n);
+    NEKB_CUDA(cudaMemcpyAsync(D.r.p, b_dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+    const double n0 = std::sqrt(amg_dot(b_dev, b_dev, n));
+    if (n0 == 0.0) return 0;
+    amg_cycle(0, D.r.p, D.z.p);
+    NEKB_CUDA(cudaMemcpyAsync(D.p.p, D.z.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+    double rz = amg_dot(D.r.p, D.z.p, n);
+    for (int it = 1; it <= maxit; it++) {
+        amg_spmv_kernel<<<g, AMG_T, 0, s>>>(D.w.p, D.p.p, L.rowptr.p, L.col.p, L.val.p, n);
+        NEKB_LAUNCHED();
+        const double a = rz / amg_dot(D.p.p, D.w.p, n);
+        amg_axpy_kernel<<<g, AMG_T, 0, s>>>(x_dev, D.p.p, a, n);
+        NEKB_LAUNCHED();
+        amg_axpy_kernel<<<g, AMG_T, 0, s>>>(D.r.p, D.w.p, -a, n);
+        NEKB_LAUNCHED();
+        if (std::sqrt(amg_dot(D.r.p, D.r.p, n)) <= tol * n0) return it;
+        amg_cycle(0, D.r.p, D.z.p);
+        const double rz_new = amg_dot(D.r.p, D.z.p, n);
+        amg_xpay_kernel<<<g, AMG_T, 0, s>>>(D.p.p, D.z.p, rz_new / rz, n);   // p = z + beta p
+        NEKB_LAUNCHED();
+        rz = rz_new;
+    }
+    return maxit;
+}
+
+}  // namespace nekb

@@ -7,7 +7,7 @@
 #include "proj.cuh"
 #include "pnpn2.cuh"
 #include "readers.cuh"
-#include "crs_amg.cuh"
+#include "crs_amg_dev.cuh"
 
 using namespace nekb;
 
@@ -179,6 +179,7 @@ void nekb_finalize(void)
     h1mg() = H1mg();
     hsmg2() = H1mg();
     fcrs_table().clear();
+    amg_dev() = AmgDev();
     fdm_h1_state() = FdmH1State();
     gmres_state() = GmresState();
     crs_scalars().release();
@@ -2019,6 +2020,22 @@ int nekb_crs_amg_level_get(int level, int64_t *rowptr, int32_t *col, double *val
             NEKB_REQUIRE(level < (int)H.agg.size(), "crs_amg_level_get: the coarsest level has no aggregates");
             std::copy(H.agg[level].begin(), H.agg[level].end(), agg);
         }
+    });
+}
+int nekb_crs_amg_upload(double omega)
+{
+    return guard([&] {
+        require_init();
+        NEKB_REQUIRE(omega > 0.0 && omega <= 1.0, "crs_amg_upload: damping outside (0, 1]");
+        amg_upload(omega);
+    });
+}
+int nekb_crs_amg_solve_dev(double *x_dev, const double *b_dev, double tol, int maxit, int *iters)
+{
+    return guard([&] {
+        require_init();
+        const int it = amg_pcg_solve(x_dev, b_dev, tol, maxit);
+        if (iters) *iters = it;
     });
 }
 int nekb_assign_gllnid(int *gllnid, int64_t nelgt, int64_t nelgv, int np)
