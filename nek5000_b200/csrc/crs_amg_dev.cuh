@@ -157,19 +157,7 @@ inline void amg_upload(double omega)
         for (int64_t q = Ac.rowptr[i]; q < Ac.rowptr[i + 1]; q++) M[(size_t)i * D.ld + Ac.col[q]] = Ac.val[q];
     for (int64_t v = Ac.n; v < D.ld; v++) M[(size_t)v * D.ld + v] = 1.0;
     D.ainv.upload(M.data(), M.size(), s);
-    const int nb = (int)(D.ld / CRS_NB);
-    for (int kb = 0; kb < nb; kb++) {
-        crsd_pivot_kernel<<<1, 256, 0, s>>>(D.ainv.p, D.ld, kb);
-        NEKB_LAUNCHED();
-        if (nb > 1) {
-            crsd_row_kernel<<<nb, 256, 0, s>>>(D.ainv.p, D.ld, kb);
-            NEKB_LAUNCHED();
-            crsd_trail_kernel<<<dim3(nb, nb), 256, 0, s>>>(D.ainv.p, D.ld, kb);
-            NEKB_LAUNCHED();
-            crsd_col_kernel<<<nb, 256, 0, s>>>(D.ainv.p, D.ld, kb);
-            NEKB_LAUNCHED();
-        }
-    }
+    crsd_invert(D.ainv.p, D.ld);
     D.cb.alloc((size_t)D.ld), D.cy.alloc((size_t)D.ld);
     D.cb.zero(s), D.cy.zero(s);
     const int64_t n0 = H.A[0].n;

@@ -1195,6 +1195,25 @@ inline void crs_dense_solve(CrsSolver &k, double *x_out, const double *b_in)
     }
 }
 
+// In-place inverse of the ld x ld matrix M (ld a multiple of CRS_NB) by blocked Gauss-Jordan without pivoting (SPD input)
+inline void crsd_invert(double *M, int64_t ld)
+{
+    cudaStream_t s = ctx().stream;
+    const int nb = (int)(ld / CRS_NB);
+    for (int kb = 0; kb < nb; kb++) {
+        crsd_pivot_kernel<<<1, 256, 0, s>>>(M, ld, kb);
+        NEKB_LAUNCHED();
+        if (nb > 1) {
+            crsd_row_kernel<<<nb, 256, 0, s>>>(M, ld, kb);
+            NEKB_LAUNCHED();
+            crsd_trail_kernel<<<dim3(nb, nb), 256, 0, s>>>(M, ld, kb);
+            NEKB_LAUNCHED();
+            crsd_col_kernel<<<nb, 256, 0, s>>>(M, ld, kb);
+            NEKB_LAUNCHED();
+        }
+    }
+}
+
 // Assembles the global vertex-mesh matrix from the element matrices of ALL ranks (host transport, setup only; fixed
 // summation order so that every rank holds the same bits), imposes the masked dofs as identity rows, regularises the
 // all-Neumann null space with (trace/ndof^2) m m^T (m = unmasked dofs: for a consistent right-hand side the solution of the
@@ -1378,19 +1397,7 @@ inline int fcrs_setup(int sid, int64_t n, const int64_t *id, int64_t nz, const i
     k.null_space = null_space ? 1 : 0;
     k.ndof = (double)nc;
     k.ainv.upload(M.data(), M.size(), s);
-    const int nb = (int)(ld / CRS_NB);
-    for (int kb = 0; kb < nb; kb++) {
-        crsd_pivot_kernel<<<1, 256, 0, s>>>(k.ainv.p, ld, kb);
-        NEKB_LAUNCHED();
-        if (nb > 1) {
-            crsd_row_kernel<<<nb, 256, 0, s>>>(k.ainv.p, ld, kb);
-            NEKB_LAUNCHED();
-            crsd_trail_kernel<<<dim3(nb, nb), 256, 0, s>>>(k.ainv.p, ld, kb);
-            NEKB_LAUNCHED();
-            crsd_col_kernel<<<nb, 256, 0, s>>>(k.ainv.p, ld, kb);
-            NEKB_LAUNCHED();
-        }
-    }
+    crsd_invert(k.ainv.p, ld);
     const size_t nn = (size_t)std::max<int64_t>(n, 1);
     std::vector<int32_t> vid(nn, -1), voff((size_t)nc + 1, 0), vmem(nn, 0);
     for (int64_t t = 0; t < n; t++)
