@@ -2,9 +2,9 @@
 // operator, preconditioned by one V(1,1) cycle (damped Jacobi, piecewise-constant transfer, dense inverse at the coarsest
 // level through the crsd_* kernels of hsmg.cuh).  Plan and iteration counts: DESIGN.md section 8, scripts/proto_coarse_amg.py.
 //
-// STATUS: written after round 1's GPU budget was spent -- compiled, NOT YET RUN ON A GPU, not wired into h1mg_solve.  Entry
+// STATUS: written after round 1's GPU budget was spent -- compiled, NOT YET RUN ON A GPU; h1mg's coarse solve uses it only with NEKB_CRS_AMG=1.  Entry
 // points nekb_crs_amg_upload / nekb_crs_amg_solve_dev; parity test (against numpy on the same levels) in
-// tests/test_zz_gpu_configs.py behind NEKB_TEST_UNVALIDATED=1.  SPD systems only (no null-space handling at this layer yet);
+// tests/test_zz_gpu_configs.py behind NEKB_TEST_UNVALIDATED=1;
 // the CG loop reads its scalars back every iteration (to be replaced by device-side control + a captured graph once correct).
 #pragma once
 #include "crs_amg.cuh"
@@ -117,7 +117,10 @@ __global__ void __launch_bounds__(AMG_T) amg_xpay_kernel(double *__restrict__ y,
 }
 
 // Moves the host hierarchy to the device and inverts the coarsest operator (blocked Gauss-Jordan of hsmg.cuh).
-inline void amg_upload(double omega)
+// fine_mask (may be null): 1 = unmasked dof of the finest level; with null_space the coarsest operator gets gamma m m^T, m = the
+// aggregates that hold unmasked dofs (the constant survives every piecewise-constant Galerkin product), exactly as the dense
+// path regularises its matrix.
+inline void amg_upload(double omega, const std::vector<double> *fine_mask = nullptr, bool null_space = false)
 {
     Ctx &c = ctx();
     cudaStream_t s = c.stream;
@@ -156,6 +159,24 @@ inline void amg_upload(double omega)
     for (int64_t i = 0; i < Ac.n; i++)
         for (int64_t q = Ac.rowptr[i]; q < Ac.rowptr[i + 1]; q++) M[(size_t)i * D.ld + Ac.col[q]] = Ac.val[q];
     for (int64_t v = Ac.n; v < D.ld; v++) M[(size_t)v * D.ld + v] = 1.0;
+    if (null_space) {
+        std::vector<double> m = fine_mask ? *fine_mask : std::vector<double>((size_t)H.A[0].n, 1.0);
+        NEKB_REQUIRE((int64_t)m.size() == H.A[0].n, "crs_amg_upload: mask length differs from the finest level");
+        for (size_t l = 0; l < nl; l++) {
+            std::vector<double> mc((size_t)H.A[l + 1].n, 0.0);
+            for (int64_t i = 0; i < H.A[l].n; i++)
+                if (m[i] != 0.0) mc[H.agg[l][i]] = 1.0;
+            m.swap(mc);
+        }
+        double trace = 0.0, cnt = 0.0;
+        for (int64_t v = 0; v < Ac.n; v++)
+            if (m[v] != 0.0) trace += M[(size_t)v * D.ld + v], cnt += 1.0;
+        const double gam = cnt > 0.0 ? trace / (cnt * cnt) : 0.0;
+        for (int64_t i = 0; i < Ac.n; i++)
+            if (m[i] != 0.0)
+                for (int64_t j = 0; j < Ac.n; j++)
+                    if (m[j] != 0.0) M[(size_t)i * D.ld + j] += gam;
+    }
     D.ainv.upload(M.data(), M.size(), s);
     crsd_invert(D.ainv.p, D.ld);
     D.cb.alloc((size_t)D.ld), D.cy.alloc((size_t)D.ld);
@@ -249,5 +270,109 @@ inline int amg_pcg_solve(double *x_dev, const double *b_dev, double tol, int max
     }
     return maxit;
 }
+
+// ------------------------------------------------------------------------------------------------ h1mg wiring
+// crs_solve semantics (see crs_dense_solve) with the explicit inverse replaced by amg_pcg_solve on the assembled operator:
+// gather to the distinct dofs, all-reduce, mask / mean removal, CG to k.tol, mean removal, scatter.  Every rank holds the
+// whole hierarchy and solves redundantly, so the CG itself needs no communication.
+inline void crs_amg_solve(CrsSolver &k, double *x_out, const double *b_in)
+{
+    Ctx &c = ctx();
+    cudaStream_t s = c.stream;
+    const int64_t nc = k.nc;
+    const int gv = (int)std::max<int64_t>(1, std::min<int64_t>((nc + 255) / 256, (int64_t)c.num_sms * 4));
+    crsd_gather_kernel<<<gv, 256, 0, s>>>(k.g.p, b_in, k.voff.p, k.vmem.p, nc);
+    NEKB_LAUNCHED();
+    if (c.nranks > 1) comm_allreduce_sum(k.g.p, (int)nc);
+    crsd_prep_kernel<<<1, 1024, 0, s>>>(k.g.p, k.gmask.p, nc, k.null_space, k.ndof);
+    NEKB_LAUNCHED();
+    k.last_iters = amg_pcg_solve(k.y.p, k.g.p, k.tol, k.maxit);
+    k.iters_on_device = false;
+    crsd_mean_kernel<<<1, 1024, 0, s>>>(k.y.p, k.gmask.p, nc, k.null_space, k.ndof);
+    NEKB_LAUNCHED();
+    if (k.n > 0) {
+        const int gx = (int)std::max<int64_t>(1, std::min<int64_t>((k.n + 255) / 256, (int64_t)c.num_sms * 4));
+        crsd_scatter_kernel<<<gx, 256, 0, s>>>(x_out, k.y.p, k.vid.p, k.n);
+        NEKB_LAUNCHED();
+    }
+}
+
+// Same gathering of every rank's ids / element matrices / masks as crs_dense_setup, assembled into COO triplets (masked dofs:
+// identity rows) instead of a dense matrix.  COLLECTIVE.  Only with NEKB_CRS_AMG=1.
+inline void crs_amg_setup(CrsSolver &k, int nel, const int64_t *vertex)
+{
+    const char *env = getenv("NEKB_CRS_AMG");
+    if (!env || atoi(env) == 0) return;
+    Ctx &c = ctx();
+    cudaStream_t s = c.stream;
+    std::vector<int64_t> glo((size_t)8 * std::max(nel, 1));
+    setvert3d_host(glo.data(), 2, nel, vertex, c.nranks);
+    int64_t mx = 0;
+    for (int t = 0; t < 8 * nel; t++) mx = std::max(mx, glo[t]);
+    std::vector<int64_t> all((size_t)c.nranks);
+    host_allgather(&mx, all.data(), sizeof(int64_t));
+    int64_t nc = 0;
+    for (int64_t v : all) nc = std::max(nc, v);
+    if (nc <= 0) return;
+    int64_t nel_loc = nel;
+    std::vector<int64_t> nels((size_t)c.nranks);
+    host_allgather(&nel_loc, nels.data(), sizeof(int64_t));
+    int64_t nelmax = 1;
+    for (int64_t v : nels) nelmax = std::max(nelmax, v);
+    std::vector<double> a_loc((size_t)64 * nelmax, 0.0), m_loc((size_t)8 * nelmax, 0.0);
+    std::vector<int64_t> id_loc((size_t)8 * nelmax, 0);
+    if (nel > 0) {
+        k.a.download(a_loc.data(), (size_t)64 * nel, s);
+        k.mask.download(m_loc.data(), (size_t)8 * nel, s);
+        memcpy(id_loc.data(), glo.data(), sizeof(int64_t) * 8 * (size_t)nel);
+    }
+    std::vector<double> a_all((size_t)64 * nelmax * c.nranks), m_all((size_t)8 * nelmax * c.nranks);
+    std::vector<int64_t> id_all((size_t)8 * nelmax * c.nranks);
+    host_allgather(a_loc.data(), a_all.data(), sizeof(double) * a_loc.size());
+    host_allgather(m_loc.data(), m_all.data(), sizeof(double) * m_loc.size());
+    host_allgather(id_loc.data(), id_all.data(), sizeof(int64_t) * id_loc.size());
+    std::vector<double> gmask((size_t)nc, 1.0);
+    for (int r = 0; r < c.nranks; r++)
+        for (int64_t e = 0; e < nels[r]; e++)
+            for (int i = 0; i < 8; i++) {
+                const int64_t g = id_all[((size_t)r * nelmax + e) * 8 + i];
+                NEKB_REQUIRE(g >= 1 && g <= nc, "coarse numbering out of range");
+                if (m_all[((size_t)r * nelmax + e) * 8 + i] == 0.0) gmask[g - 1] = 0.0;
+            }
+    std::vector<int64_t> I, J;
+    std::vector<double> V;
+    for (int r = 0; r < c.nranks; r++)
+        for (int64_t e = 0; e < nels[r]; e++) {
+            const double *ae = a_all.data() + ((size_t)r * nelmax + e) * 64;
+            const int64_t *ie = id_all.data() + ((size_t)r * nelmax + e) * 8;
+            for (int i = 0; i < 8; i++)
+                for (int j = 0; j < 8; j++)
+                    if (gmask[ie[i] - 1] != 0.0 && gmask[ie[j] - 1] != 0.0) I.push_back(ie[i] - 1), J.push_back(ie[j] - 1), V.push_back(ae[i * 8 + j]);
+        }
+    for (int64_t v = 0; v < nc; v++)
+        if (gmask[v] == 0.0) I.push_back(v), J.push_back(v), V.push_back(1.0);
+    const char *en = getenv("NEKB_CRS_AMG_NMAX");
+    const int64_t nmax = en ? atoll(en) : 2048;
+    amg_host_hierarchy() = amg_build(csr_from_triplets(nc, I, J, V), nmax, 0.02);
+    amg_upload(0.7, &gmask, k.null_space != 0);
+    // local members of every global dof, as in crs_dense_setup
+    std::vector<int32_t> vid((size_t)8 * std::max(nel, 1), 0), voff((size_t)nc + 1, 0), vmem((size_t)8 * std::max(nel, 1), 0);
+    for (int t = 0; t < 8 * nel; t++) vid[t] = (int32_t)(glo[t] - 1), voff[(size_t)vid[t] + 1]++;
+    for (int64_t v = 0; v < nc; v++) voff[v + 1] += voff[v];
+    std::vector<int32_t> cur(voff.begin(), voff.end() - 1);
+    for (int t = 0; t < 8 * nel; t++) vmem[cur[vid[t]]++] = t;
+    k.vid.upload(vid.data(), vid.size(), s), k.voff.upload(voff.data(), voff.size(), s), k.vmem.upload(vmem.data(), vmem.size(), s);
+    k.gmask.upload(gmask.data(), (size_t)nc, s);
+    k.g.alloc((size_t)nc), k.y.alloc((size_t)nc);
+    k.g.zero(s), k.y.zero(s);
+    k.nc = nc;
+    NEKB_CUDA(cudaStreamSynchronize(s));
+    k.amg_solve = crs_amg_solve;
+}
+
+struct CrsAmgHookInstaller {
+    CrsAmgHookInstaller() { crs_amg_setup_hook() = crs_amg_setup; }
+};
+static CrsAmgHookInstaller crs_amg_hook_installer;
 
 }  // namespace nekb

@@ -281,7 +281,15 @@ struct CrsSolver {
     DevBuf<double> g, y;             // [nc] assembled right-hand side / solution
     DevBuf<int32_t> vid;             // [8 nel] global dof of every local vertex (0-based)
     DevBuf<int32_t> voff, vmem;      // CSR: local members of every global dof (empty rows for dofs of other ranks)
+    // ---- aggregation-hierarchy CG for problems beyond the dense limit (crs_amg_dev.cuh; NEKB_CRS_AMG=1, unvalidated) ----
+    void (*amg_solve)(CrsSolver &, double *, const double *) = nullptr;
 };
+// set by crs_amg_dev.cuh (included after this file): builds the hierarchy when the dense solver declined the problem
+inline void (*&crs_amg_setup_hook())(CrsSolver &, int, const int64_t *)
+{
+    static void (*f)(CrsSolver &, int, const int64_t *) = nullptr;
+    return f;
+}
 
 struct H1mg {
     bool ready = false;
@@ -1486,6 +1494,10 @@ inline void crs_solve_dev(H1mg &MM, double *x_out, const double *b_in)
         k.last_iters = 1, k.iters_on_device = false;
         return;
     }
+    if (k.amg_solve) {
+        k.amg_solve(k, x_out, b_in);
+        return;
+    }
     if (n == 0 && c.nranks <= 1) return;
     const int grid = vec_grid(n);
     DevBuf<CrsScalars> &scb = crs_scalars();
@@ -2040,6 +2052,8 @@ inline void h1mg_setup_run(H1mg &M, const int *fbc, const double *xm1, const dou
         NEKB_CUDA(cudaMemcpyAsync(&k.ndof, &scb.p->shift, sizeof(double), cudaMemcpyDeviceToHost, s));
         NEKB_CUDA(cudaStreamSynchronize(s));
         crs_dense_setup(k, nel, vertex);
+        k.amg_solve = nullptr;
+        if (!k.dense && crs_amg_setup_hook()) crs_amg_setup_hook()(k, nel, vertex);
     }
     NEKB_CUDA(cudaStreamSynchronize(s));
     M.ready = true;

@@ -228,3 +228,30 @@ def test_crs_amg_device_cycle_against_numpy(nek, m, nmax, iters):
     assert abs(it.value - itref) <= 2 and (iters is None or itref == iters)
     assert relmax(x, xref) <= 1e-10 and relmax(x, xe) <= 1e-9
     assert np.linalg.norm(A @ x - b) <= 5e-13 * np.linalg.norm(b)
+
+
+@pytest.mark.skipif(os.environ.get("NEKB_TEST_UNVALIDATED") != "1",
+                    reason="h1mg coarse solve through the aggregation hierarchy (NEKB_CRS_AMG=1) was written after the round's GPU "
+                           "budget was spent: not yet run on a GPU (set NEKB_TEST_UNVALIDATED=1)")
+@pytest.mark.parametrize("name", ["ethier", "channel"])
+def test_h1mg_solve_with_the_aggregation_coarse_solver(nek, name, monkeypatch):
+    """h1mg_solve / hmh_gmres with the coarse problem solved by CG over the aggregation hierarchy instead of the dense inverse
+    (forced on these small meshes: dense path off, coarsest level <= 8 unknowns): same golden fields and iteration counts."""
+    monkeypatch.setenv("NEKB_CRS_DENSE", "0")
+    monkeypatch.setenv("NEKB_CRS_AMG", "1")
+    monkeypatch.setenv("NEKB_CRS_AMG_NMAX", "8")
+    g = G[name]
+    case = refcases.channel_case() if name == "channel" else refcases.ethier_case()
+    fbc = refcases.channel_fbc(case) if name == "channel" else hsmg.box_fbc(case, (2,) * 6)
+    E, n = case.nel, case.n
+    _register(nek, case, [g[f"g{i}m1"] for i in range(1, 7)], g["bm1"], g["binvm1"], g["volvm1"][0], g["zgm1"], g["wxm1"], g["dxm1"])
+    nek.h1mg_setup(fbc, case.xm1, case.ym1, case.zm1, case.vertex, E, True)
+    z, r = np.zeros(n), g["rhs"].copy()
+    nek.h1mg_solve(z, r, False)
+    assert relmax(z, g["z"]) <= TOL_FIELD
+    assert 2 <= nek.h1mg_info()["crs_iters"] <= 40
+    tol = float(g["tol"][0])
+    nek.set_pressure_state(g["pmask"], g["binvm1"], tol, tol, True, E)
+    res = g["b"].copy()
+    it = nek.hmh_gmres(res, np.ones(n), np.zeros(n), g["vmult"], 100)
+    assert it == g["it"][0] and relmax(res, g["x"]) <= TOL_FIELD
