@@ -255,3 +255,42 @@ def test_h1mg_solve_with_the_aggregation_coarse_solver(nek, name, monkeypatch):
     res = g["b"].copy()
     it = nek.hmh_gmres(res, np.ones(n), np.zeros(n), g["vmult"], 100)
     assert it == g["it"][0] and relmax(res, g["x"]) <= TOL_FIELD
+
+
+@pytest.mark.skipif(os.environ.get("NEKB_TEST_UNVALIDATED") != "1",
+                    reason="added after the round's GPU budget was spent: not yet run on a GPU (set NEKB_TEST_UNVALIDATED=1); "
+                           "tests/test_gpu_hsmg.py already holds these orders to the oracle, which tests/test_ref_pins.py pins to the "
+                           "reference")
+@pytest.mark.parametrize("nx", [4, 6, 10])
+def test_h1mg_and_gmres_at_other_orders_against_the_reference(nx):
+    """lx1 = 4 (two multigrid levels), 6 and 10: h1mg_solve, hmh_gmres and hmh_flex_cg directly against the reference's output
+    (golden h1mg_lx{nx}); geometry from the oracle, which is the reference's bit for bit."""
+    from nek5000_b200 import nek
+    g, case = G[f"h1mg_lx{nx}"], refcases.case_of("core", nx)
+    E, n = case.nel, case.n
+    nek.finalize()
+    nek.init(0, nx, 3)
+    try:
+        geo = case.geom()
+        nek.set_nel(E, E)
+        nek.set_gll(case.z, case.w)
+        nek.set_dxyz(case.D, np.ascontiguousarray(case.D.T))
+        nek.set_geom(*geo[:6], geo[6])
+        nek.set_ifdfrm(None)
+        h, _ = nek.setupds(nx, E, case.vertex)
+        nek.set_ifield(1)
+        nek.set_field_handle(1, h)
+        nek.set_step_info(1, float(g["volvm1"][0]))
+        nek.set_binv(case.binv())
+        nek.h1mg_setup(refcases.fbc_of("core", case), case.xm1, case.ym1, case.zm1, case.vertex, E, False)
+        z, r = np.zeros(n), g["rhs"].copy()
+        nek.h1mg_solve(z, r, False)
+        assert np.array_equal(r, g["rhs_out"]) and relmax(z, g["z"]) <= TOL_FIELD
+        tol = float(g["tol"][0])
+        nek.set_pressure_state(g["pmask"], case.binv(), tol, tol, False, E)
+        res = g["b"].copy()
+        assert nek.hmh_gmres(res, np.ones(n), np.zeros(n), case.mult, 100) == g["it"][0] and relmax(res, g["x"]) <= TOL_FIELD
+        res = g["b"].copy()
+        assert nek.hmh_flex_cg(res, np.ones(n), np.zeros(n), case.mult, 100) == g["it_fcg"][0] and relmax(res, g["x_fcg"]) <= 1e-9
+    finally:
+        nek.finalize()
