@@ -8,7 +8,8 @@ residual) -- the question is how many sweeps over the sparse matrix that takes.
   * agg-V    : CG preconditioned by one V(1,1) cycle of a plain-aggregation hierarchy (piecewise-constant prolongation built
                by greedy aggregation on the matrix graph, Galerkin coarse matrices, damped-Jacobi smoothing, the existing
                dense inverse at the coarsest level of <= 4096 unknowns);
-  * agg-K    : the same with a two-step Krylov (K-)cycle on the second level.
+  * agg-K    : the same with a two-step Krylov (K-)cycle on the second level;
+  * smoothed : the same aggregates with the prolongation smoothed by one damped-Jacobi step (smoothed aggregation).
 
 Operator: Q1 stiffness matrix on an m^3 box (the Galerkin projection of the SEM operator onto the element-corner basis is
 spectrally equivalent), Neumann walls, one Dirichlet (outflow) side.      python scripts/proto_coarse_amg.py 16 32 48
@@ -112,6 +113,32 @@ class Hierarchy:
         return x + dj * (b - A @ x)
 
 
+def smoothed_hierarchy_cycle(A, nmax=2048, omega_p=0.66, omega=0.7):
+    """The same aggregates with a SMOOTHED prolongation P = (I - omega_p D^-1 A) P_tentative (classical smoothed aggregation):
+    returns (cycle function, level sizes, operator complexity, nnz per row of the finest P)."""
+    lev = []
+    A0 = A
+    while A.shape[0] > nmax:
+        agg, na = aggregate(A)
+        T = sp.csr_matrix((np.ones(A.shape[0]), (np.arange(A.shape[0]), agg)), shape=(A.shape[0], na))
+        Pm = (T - omega_p * (sp.diags(1.0 / A.diagonal()) @ (A @ T))).tocsr()
+        lev.append((A, Pm))
+        A = (Pm.T @ A @ Pm).tocsr()
+    Ainv = np.linalg.inv(A.toarray())
+
+    def cycle(b, l=0):
+        if l == len(lev):
+            return Ainv @ b
+        Al, Pm = lev[l]
+        dj = omega / Al.diagonal()
+        x = dj * b
+        x = x + Pm @ cycle(Pm.T @ (b - Al @ x), l + 1)
+        return x + dj * (b - Al @ x)
+
+    sizes = [l[0].shape[0] for l in lev] + [A.shape[0]]
+    return cycle, sizes, sum(l[0].nnz for l in lev) / max(A0.nnz, 1), (lev[0][1].nnz / A0.shape[0]) if lev else 0.0
+
+
 def pcg(A, b, prec, tol=1e-13, maxit=3000):
     x = np.zeros_like(b)
     r = b.copy()
@@ -149,6 +176,9 @@ def main():
         # one V(1,1) cycle sweeps every level's matrix twice (residual + post-smoothing residual); CG adds one fine sweep
         wv = itv * (1 + 2 * sum(H.nnz) / A.nnz)
         print(f"{m:4d} {n:9d} | {itj:7d} | {str(H.sizes):>24} {itv:6d} {itk:6d} | {itj:.0f}, {wv:.0f}   (setup {ts:.1f} s)")
+        cyc, sizes, cx, pn = smoothed_hierarchy_cycle(A)
+        _, its = pcg(A, b, cyc)
+        print(f"{'':>14} | smoothed aggregation {sizes}: {its} iterations, operator complexity {cx:.2f}, {pn:.1f} nnz per row of P")
 
 
 if __name__ == "__main__":
