@@ -387,7 +387,10 @@ int nekb_fcrs_solve_dev(int handle, double *x_dev, const double *b_dev);
  * (greedy aggregation with strength threshold theta, piecewise-constant prolongation, Galerkin products).  level_get copies
  * a level's CSR (rowptr[n+1], col[nnz], val[nnz]) and, for every level but the coarsest, its aggregate map agg[n]. */
 int nekb_crs_amg_build_host(int64_t n, int64_t nz, const int64_t *I, const int64_t *J, const double *V, int64_t nmax, double theta,
-                            int *nlevels);
+                            double omega_p, int *nlevels);
+/* omega_p = 0: piecewise-constant prolongation; > 0: smoothed aggregation, P = (I - omega_p D^-1 A) P_tentative.
+ * level_p: the prolongation of a level (n_level rows, n_{level+1} columns) in CSR; pass NULL arrays to query nnz first. */
+int nekb_crs_amg_level_p(int level, int64_t *nnz, int64_t *rowptr, int32_t *col, double *val);
 int nekb_crs_amg_level_info(int level, int64_t *n, int64_t *nnz);
 int nekb_crs_amg_level_get(int level, int64_t *rowptr, int32_t *col, double *val, int32_t *agg);
 /* Device side of the same (csrc/crs_amg_dev.cuh; compiled, NOT YET RUN ON A GPU, not used by h1mg_solve): upload moves the

@@ -121,7 +121,8 @@ def lib() -> C.CDLL:
     L.crs_free_.argtypes = [ip]
     L.crs_free_.restype = None
     L.nekb_fcrs_solve_dev.argtypes = [C.c_int, vp, vp]
-    L.nekb_crs_amg_build_host.argtypes = [C.c_int64, C.c_int64, vp, vp, vp, C.c_int64, C.c_double, ip]
+    L.nekb_crs_amg_build_host.argtypes = [C.c_int64, C.c_int64, vp, vp, vp, C.c_int64, C.c_double, C.c_double, ip]
+    L.nekb_crs_amg_level_p.argtypes = [C.c_int, C.POINTER(C.c_int64), vp, vp, vp]
     L.nekb_crs_amg_level_info.argtypes = [C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.nekb_crs_amg_level_get.argtypes = [C.c_int, vp, vp, vp, vp]
     L.nekb_crs_amg_upload.argtypes = [C.c_double]

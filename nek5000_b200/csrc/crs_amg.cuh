@@ -4,7 +4,8 @@
 // Role in the reference: crs_solve (core/fcrs.c:80 -> core/crs_xxt.c:926-965, or core/crs_amg.c with param(40) = 1) solves
 // the assembled vertex-mesh system directly.  Plan here (prototype scripts/proto_coarse_amg.py): CG to
 // rounding level preconditioned by one cycle over this hierarchy -- greedy aggregation on the strength graph, piecewise-
-// constant prolongation, Galerkin coarse matrices, damped Jacobi, the dense inverse at the coarsest level.
+// constant prolongation (optionally smoothed by one damped-Jacobi step: smoothed aggregation), Galerkin coarse matrices,
+// damped Jacobi, the dense inverse at the coarsest level.
 //
 // STATUS: this file is set-up only and runs on the host (like setvert3d_host and gen_fast); it is exercised on the CPU by
 // tests/test_crs_amg_host.py through nekb_crs_amg_*.  The device cycle (CSR mat-vec, gather / scatter by aggregate) that
@@ -22,6 +23,7 @@ namespace nekb {
 
 struct CsrHost {
     int64_t n = 0;
+    int64_t ncols = 0;             // 0 = square
     std::vector<int64_t> rowptr;   // [n+1]
     std::vector<int32_t> col;      // ascending inside a row
     std::vector<double> val;
@@ -107,22 +109,108 @@ inline CsrHost amg_galerkin(const CsrHost &A, const std::vector<int32_t> &agg, i
     return csr_from_triplets(na, I, J, V);
 }
 
+// C = A B (Gustavson: one dense accumulator row, columns of a result row emitted in ascending order; products are added in
+// the traversal order of A's and B's rows, so the result is reproducible).
+inline CsrHost spgemm(const CsrHost &A, const CsrHost &B)
+{
+    const int64_t bc = B.ncols ? B.ncols : B.n;
+    NEKB_REQUIRE((A.ncols ? A.ncols : A.n) == B.n, "spgemm: inner dimensions differ");
+    CsrHost C;
+    C.n = A.n, C.ncols = bc;
+    C.rowptr.assign((size_t)A.n + 1, 0);
+    std::vector<double> acc((size_t)bc, 0.0);
+    std::vector<int64_t> mark((size_t)bc, -1);
+    std::vector<int32_t> cols;
+    for (int64_t i = 0; i < A.n; i++) {
+        cols.clear();
+        for (int64_t q = A.rowptr[i]; q < A.rowptr[i + 1]; q++) {
+            const int32_t k = A.col[q];
+            const double a = A.val[q];
+            for (int64_t t = B.rowptr[k]; t < B.rowptr[k + 1]; t++) {
+                const int32_t j = B.col[t];
+                if (mark[j] != i) mark[j] = i, acc[j] = 0.0, cols.push_back(j);
+                acc[j] += a * B.val[t];
+            }
+        }
+        std::sort(cols.begin(), cols.end());
+        for (int32_t j : cols) C.col.push_back(j), C.val.push_back(acc[j]);
+        C.rowptr[i + 1] = (int64_t)C.col.size();
+    }
+    return C;
+}
+
+inline CsrHost csr_transpose(const CsrHost &A)
+{
+    const int64_t nc = A.ncols ? A.ncols : A.n;
+    CsrHost T;
+    T.n = nc, T.ncols = A.n;
+    T.rowptr.assign((size_t)nc + 1, 0);
+    for (int32_t j : A.col) T.rowptr[(size_t)j + 1]++;
+    for (int64_t j = 0; j < nc; j++) T.rowptr[j + 1] += T.rowptr[j];
+    T.col.resize(A.col.size()), T.val.resize(A.val.size());
+    std::vector<int64_t> cur(T.rowptr.begin(), T.rowptr.end() - 1);
+    for (int64_t i = 0; i < A.n; i++)
+        for (int64_t q = A.rowptr[i]; q < A.rowptr[i + 1]; q++) {
+            const int64_t d = cur[A.col[q]]++;
+            T.col[d] = (int32_t)i, T.val[d] = A.val[q];
+        }
+    return T;
+}
+
+// Prolongation of a level: the tentative (piecewise-constant) one, or with omega_p > 0 its smoothed form
+// P = (I - omega_p D^-1 A) P_tent (smoothed aggregation).
+inline CsrHost amg_prolongator(const CsrHost &A, const std::vector<int32_t> &agg, int32_t na, double omega_p)
+{
+    CsrHost T;
+    T.n = A.n, T.ncols = na;
+    T.rowptr.resize((size_t)A.n + 1);
+    T.col.assign(agg.begin(), agg.end());
+    T.val.assign((size_t)A.n, 1.0);
+    std::iota(T.rowptr.begin(), T.rowptr.end(), (int64_t)0);
+    if (!(omega_p > 0.0)) return T;
+    CsrHost AT = spgemm(A, T);
+    CsrHost P;
+    P.n = A.n, P.ncols = na;
+    P.rowptr.assign((size_t)A.n + 1, 0);
+    for (int64_t i = 0; i < A.n; i++) {
+        double d = 0.0;
+        for (int64_t q = A.rowptr[i]; q < A.rowptr[i + 1]; q++)
+            if (A.col[q] == i) d = A.val[q];
+        NEKB_REQUIRE(d != 0.0, "amg_prolongator: zero diagonal");
+        bool own = false;
+        for (int64_t q = AT.rowptr[i]; q < AT.rowptr[i + 1]; q++) {   // ascending columns; the tentative entry merges in
+            double v = -omega_p * AT.val[q] / d;
+            if (AT.col[q] == agg[i]) v += 1.0, own = true;
+            P.col.push_back(AT.col[q]), P.val.push_back(v);
+        }
+        NEKB_REQUIRE(own, "amg_prolongator: a row of A T misses its own aggregate");   // a_ii != 0 guarantees the entry
+        P.rowptr[i + 1] = (int64_t)P.col.size();
+    }
+    return P;
+}
+
 struct AmgHierarchy {
     std::vector<CsrHost> A;                   // A[0] = the fine operator ... A.back() = the coarsest (dense inverse)
     std::vector<std::vector<int32_t>> agg;    // agg[l][i] = aggregate (row of A[l+1]) of row i of A[l]
+    std::vector<CsrHost> P, PT;               // prolongation of level l (n_l x n_{l+1}) and its transpose
 };
 
-inline AmgHierarchy amg_build(CsrHost A0, int64_t nmax, double theta)
+inline AmgHierarchy amg_build(CsrHost A0, int64_t nmax, double theta, double omega_p = 0.0)
 {
-    NEKB_REQUIRE(nmax >= 1 && theta > 0.0, "amg_build: bad parameters");
+    NEKB_REQUIRE(nmax >= 1 && theta > 0.0 && omega_p >= 0.0, "amg_build: bad parameters");
     AmgHierarchy H;
     H.A.push_back(std::move(A0));
     while (H.A.back().n > nmax) {
         int32_t na = 0;
         std::vector<int32_t> g = amg_aggregate(H.A.back(), theta, na);
         NEKB_REQUIRE((double)na < 0.7 * (double)H.A.back().n, "amg_build: aggregation stalled (no strong connections at this theta)");
-        CsrHost Ac = amg_galerkin(H.A.back(), g, na);
+        CsrHost P = amg_prolongator(H.A.back(), g, na, omega_p);
+        CsrHost PT = csr_transpose(P);
+        CsrHost Ac = omega_p > 0.0 ? spgemm(PT, spgemm(H.A.back(), P)) : amg_galerkin(H.A.back(), g, na);
+        Ac.ncols = 0;
         H.agg.push_back(std::move(g));
+        H.P.push_back(std::move(P));
+        H.PT.push_back(std::move(PT));
         H.A.push_back(std::move(Ac));
     }
     return H;

@@ -1,5 +1,5 @@
 // crs_amg_dev.cuh -- device cycle over the host-built aggregation hierarchy of crs_amg.cuh: CG on the assembled coarse
-// operator, preconditioned by one V(1,1) cycle (damped Jacobi, piecewise-constant transfer, dense inverse at the coarsest
+// operator, preconditioned by one V(1,1) cycle (damped Jacobi, CSR transfer operators, dense inverse at the coarsest
 // level through the crsd_* kernels of hsmg.cuh).  Plan and iteration counts: DESIGN.md section 8, scripts/proto_coarse_amg.py.
 //
 // STATUS: written after round 1's GPU budget was spent -- compiled, NOT YET RUN ON A GPU; h1mg's coarse solve uses it only with NEKB_CRS_AMG=1.  Entry
@@ -16,8 +16,10 @@ struct AmgLevelDev {
     int64_t n = 0, nnz = 0;
     DevBuf<int32_t> rowptr, col;       // CSR (nnz < 2^31)
     DevBuf<double> val, dj;            // dj = omega / diag
-    DevBuf<int32_t> agg;               // row -> row of the next level
-    DevBuf<int32_t> moff, mem;         // CSR of the next level's rows -> their members here, ascending
+    DevBuf<int32_t> prow, pcol;        // prolongation P (n x n_next) in CSR: one entry per row (plain aggregation) or the
+    DevBuf<double> pval;               // smoothed form
+    DevBuf<int32_t> trow, tcol;        // its transpose (n_next x n): restriction
+    DevBuf<double> tval;
     DevBuf<double> b, x, x2, r;        // cycle work vectors of this level
 };
 struct AmgDev {
@@ -71,22 +73,16 @@ __global__ void __launch_bounds__(AMG_T)
         xo[i] = x[i] + dj[i] * (b[i] - s);
     }
 }
-// bc = P^T r: members summed in ascending order
-__global__ void __launch_bounds__(AMG_T)
-    amg_restrict_kernel(double *__restrict__ bc, const double *__restrict__ r, const int32_t *__restrict__ moff,
-                        const int32_t *__restrict__ mem, int64_t nc)
-{
-    for (int64_t I = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; I < nc; I += (int64_t)gridDim.x * blockDim.x) {
-        double s = 0.0;
-        for (int q = moff[I]; q < moff[I + 1]; q++) s += r[mem[q]];
-        bc[I] = s;
-    }
-}
 // x += P e
 __global__ void __launch_bounds__(AMG_T)
-    amg_prolong_add_kernel(double *__restrict__ x, const double *__restrict__ e, const int32_t *__restrict__ agg, int64_t n)
+    amg_spmv_add_kernel(double *__restrict__ x, const double *__restrict__ e, const int32_t *__restrict__ rowptr,
+                        const int32_t *__restrict__ col, const double *__restrict__ val, int64_t n)
 {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] += e[agg[i]];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int q = rowptr[i]; q < rowptr[i + 1]; q++) s = fma(val[q], e[col[q]], s);
+        x[i] += s;
+    }
 }
 // partial[block] = sum a b over the block's rows; amg_dot_final sums the partials in order into out[slot]
 __global__ void __launch_bounds__(AMG_T)
@@ -140,15 +136,13 @@ inline void amg_upload(double omega, const std::vector<double> *fine_mask = null
         for (int64_t i = 0; i < A.n; i++)
             for (int64_t q = A.rowptr[i]; q < A.rowptr[i + 1]; q++)
                 if (A.col[q] == i) dj[i] = omega / A.val[q];
-        const int64_t ncn = H.A[l + 1].n;
-        std::vector<int32_t> moff((size_t)ncn + 1, 0), mem((size_t)A.n);
-        for (int64_t i = 0; i < A.n; i++) moff[(size_t)H.agg[l][i] + 1]++;
-        for (int64_t I = 0; I < ncn; I++) moff[I + 1] += moff[I];
-        std::vector<int32_t> cur(moff.begin(), moff.end() - 1);
-        for (int64_t i = 0; i < A.n; i++) mem[cur[H.agg[l][i]]++] = (int32_t)i;
+        const CsrHost &P = H.P[l], &PT = H.PT[l];
+        NEKB_REQUIRE(P.nnz() < (int64_t)2147483647, "crs_amg_upload: prolongation too large for int32 offsets");
+        std::vector<int32_t> pr(P.rowptr.begin(), P.rowptr.end()), tr(PT.rowptr.begin(), PT.rowptr.end());
         L.rowptr.upload(rp.data(), rp.size(), s), L.col.upload(A.col.data(), A.col.size(), s), L.val.upload(A.val.data(), A.val.size(), s);
-        L.dj.upload(dj.data(), dj.size(), s), L.agg.upload(H.agg[l].data(), H.agg[l].size(), s);
-        L.moff.upload(moff.data(), moff.size(), s), L.mem.upload(mem.data(), mem.size(), s);
+        L.dj.upload(dj.data(), dj.size(), s);
+        L.prow.upload(pr.data(), pr.size(), s), L.pcol.upload(P.col.data(), P.col.size(), s), L.pval.upload(P.val.data(), P.val.size(), s);
+        L.trow.upload(tr.data(), tr.size(), s), L.tcol.upload(PT.col.data(), PT.col.size(), s), L.tval.upload(PT.val.data(), PT.val.size(), s);
         L.x.alloc((size_t)A.n), L.x2.alloc((size_t)A.n), L.r.alloc((size_t)A.n);
         if (l > 0) L.b.alloc((size_t)A.n);
         NEKB_CUDA(cudaStreamSynchronize(s));   // the host vectors above go out of scope
@@ -207,10 +201,10 @@ inline void amg_cycle(size_t l, const double *b_dev, double *z_dev)
     double *ec = last ? D.cy.p : D.L[l + 1].x2.p;   // the next level leaves its result in its x2 (see the final smoother)
     amg_presmooth_kernel<<<amg_grid(L.n), AMG_T, 0, s>>>(L.x.p, L.r.p, b_dev, L.dj.p, L.rowptr.p, L.col.p, L.val.p, L.n);
     NEKB_LAUNCHED();
-    amg_restrict_kernel<<<amg_grid(ncn), AMG_T, 0, s>>>(bc, L.r.p, L.moff.p, L.mem.p, ncn);
+    amg_spmv_kernel<<<amg_grid(ncn), AMG_T, 0, s>>>(bc, L.r.p, L.trow.p, L.tcol.p, L.tval.p, ncn);       // bc = P^T r
     NEKB_LAUNCHED();
     amg_cycle(l + 1, bc, ec);
-    amg_prolong_add_kernel<<<amg_grid(L.n), AMG_T, 0, s>>>(L.x.p, ec, L.agg.p, L.n);
+    amg_spmv_add_kernel<<<amg_grid(L.n), AMG_T, 0, s>>>(L.x.p, ec, L.prow.p, L.pcol.p, L.pval.p, L.n);   // x += P e
     NEKB_LAUNCHED();
     amg_postsmooth_kernel<<<amg_grid(L.n), AMG_T, 0, s>>>(z_dev, L.x.p, b_dev, L.dj.p, L.rowptr.p, L.col.p, L.val.p, L.n);
     NEKB_LAUNCHED();
@@ -353,7 +347,9 @@ inline void crs_amg_setup(CrsSolver &k, int nel, const int64_t *vertex)
         if (gmask[v] == 0.0) I.push_back(v), J.push_back(v), V.push_back(1.0);
     const char *en = getenv("NEKB_CRS_AMG_NMAX");
     const int64_t nmax = en ? atoll(en) : 2048;
-    amg_host_hierarchy() = amg_build(csr_from_triplets(nc, I, J, V), nmax, 0.02);
+    const char *es = getenv("NEKB_CRS_AMG_SMOOTH");   // prolongation smoothing weight; 0 = plain aggregation
+    const double omega_p = es ? atof(es) : 0.66;
+    amg_host_hierarchy() = amg_build(csr_from_triplets(nc, I, J, V), nmax, 0.02, omega_p);
     amg_upload(0.7, &gmask, k.null_space != 0);
     // local members of every global dof, as in crs_dense_setup
     std::vector<int32_t> vid((size_t)8 * std::max(nel, 1), 0), voff((size_t)nc + 1, 0), vmem((size_t)8 * std::max(nel, 1), 0);

@@ -1988,13 +1988,13 @@ int nekb_co2_read(const char *path, int nlv, int64_t e0, int64_t nel, int64_t *e
 }
 // ---- host set-up of the aggregation hierarchy for large coarse problems (crs_amg.cuh; no device work)
 int nekb_crs_amg_build_host(int64_t n, int64_t nz, const int64_t *I, const int64_t *J, const double *V, int64_t nmax, double theta,
-                            int *nlevels)
+                            double omega_p, int *nlevels)
 {
     return guard([&] {
         NEKB_REQUIRE(n >= 1 && nz >= 1 && I && J && V, "crs_amg_build_host: bad arguments");
         std::vector<int64_t> vi(I, I + nz), vj(J, J + nz);
         std::vector<double> vv(V, V + nz);
-        amg_host_hierarchy() = amg_build(csr_from_triplets(n, vi, vj, vv), nmax, theta);
+        amg_host_hierarchy() = amg_build(csr_from_triplets(n, vi, vj, vv), nmax, theta, omega_p);
         if (nlevels) *nlevels = (int)amg_host_hierarchy().A.size();
     });
 }
@@ -2020,6 +2020,18 @@ int nekb_crs_amg_level_get(int level, int64_t *rowptr, int32_t *col, double *val
             NEKB_REQUIRE(level < (int)H.agg.size(), "crs_amg_level_get: the coarsest level has no aggregates");
             std::copy(H.agg[level].begin(), H.agg[level].end(), agg);
         }
+    });
+}
+int nekb_crs_amg_level_p(int level, int64_t *nnz, int64_t *rowptr, int32_t *col, double *val)
+{
+    return guard([&] {
+        AmgHierarchy &H = amg_host_hierarchy();
+        NEKB_REQUIRE(level >= 0 && level < (int)H.P.size(), "crs_amg_level_p: no prolongation at this level");
+        const CsrHost &P = H.P[level];
+        if (nnz) *nnz = P.nnz();
+        if (rowptr) std::copy(P.rowptr.begin(), P.rowptr.end(), rowptr);
+        if (col) std::copy(P.col.begin(), P.col.end(), col);
+        if (val) std::copy(P.val.begin(), P.val.end(), val);
     });
 }
 int nekb_crs_amg_upload(double omega)

@@ -582,13 +582,14 @@ def crs_free(handle: int) -> None:
     lib().crs_free_(_i(handle))
 
 
-def crs_amg_build_host(n: int, I, J, V, nmax: int = 4096, theta: float = 0.02):
+def crs_amg_build_host(n: int, I, J, V, nmax: int = 4096, theta: float = 0.02, omega_p: float = 0.0):
     """Host set-up of the aggregation hierarchy (csrc/crs_amg.cuh).  Returns a list of levels, each a dict with `rowptr`, `col`,
-    `val` (CSR) and, except for the coarsest, `agg` (row -> aggregate = row of the next level)."""
+    `val` (CSR) and, except for the coarsest, `agg` (row -> aggregate = row of the next level) and the prolongation `p_rowptr`,
+    `p_col`, `p_val` (CSR, n_level x n_next; omega_p > 0: smoothed aggregation)."""
     I, J = (np.ascontiguousarray(a, dtype=np.int64).reshape(-1) for a in (I, J))
     V = np.ascontiguousarray(V, dtype=np.float64).reshape(-1)
     nl = C.c_int(0)
-    check(lib().nekb_crs_amg_build_host(int(n), V.size, _ptr(I), _ptr(J), _ptr(V), int(nmax), float(theta), C.byref(nl)))
+    check(lib().nekb_crs_amg_build_host(int(n), V.size, _ptr(I), _ptr(J), _ptr(V), int(nmax), float(theta), float(omega_p), C.byref(nl)))
     levels = []
     for l in range(nl.value):
         nn, nz = C.c_int64(0), C.c_int64(0)
@@ -599,6 +600,10 @@ def crs_amg_build_host(n: int, I, J, V, nmax: int = 4096, theta: float = 0.02):
         check(lib().nekb_crs_amg_level_get(l, _ptr(lv["rowptr"]), _ptr(lv["col"]), _ptr(lv["val"]), None if agg is None else _ptr(agg)))
         if agg is not None:
             lv["agg"] = agg
+            pz = C.c_int64(0)
+            check(lib().nekb_crs_amg_level_p(l, C.byref(pz), None, None, None))
+            lv["p_rowptr"], lv["p_col"], lv["p_val"] = np.zeros(nn.value + 1, dtype=np.int64), np.zeros(pz.value, dtype=np.int32), np.zeros(pz.value)
+            check(lib().nekb_crs_amg_level_p(l, None, _ptr(lv["p_rowptr"]), _ptr(lv["p_col"]), _ptr(lv["p_val"])))
         levels.append(lv)
     return levels
 

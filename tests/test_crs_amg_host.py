@@ -79,3 +79,37 @@ def test_cycle_over_the_exported_levels_converges_like_the_prototype(nek):
     _, itj = proto.pcg(A, b, lambda r: r / A.diagonal())
     assert it == 27 and itj == 110
     assert np.linalg.norm(A @ x - b) <= 2e-13 * np.linalg.norm(b)
+
+
+def test_smoothed_aggregation_hierarchy(nek):
+    """omega_p > 0: P = (I - omega_p D^-1 A) P_tentative, A_c = P^T A P by the library's sparse products, against scipy; CG over
+    the exported levels needs the prototype's 20 iterations (27 with the plain prolongation, 110 for Jacobi-PCG)."""
+    A = proto.q1_stiffness(20)
+    C = A.tocoo()
+    lv = nek.crs_amg_build_host(A.shape[0], C.row, C.col, C.data, nmax=2048, theta=0.02, omega_p=0.66)
+    assert [l["n"] for l in lv] == [8820, 343]
+    n, na = lv[0]["n"], lv[1]["n"]
+    T = sp.csr_matrix((np.ones(n), (np.arange(n), lv[0]["agg"])), shape=(n, na))
+    Pref = (T - 0.66 * (sp.diags(1.0 / A.diagonal()) @ (A @ T))).tocsr()
+    P = sp.csr_matrix((lv[0]["p_val"], lv[0]["p_col"], lv[0]["p_rowptr"]), shape=(n, na))
+    assert np.abs(P - Pref).max() <= 1e-15 and 5.0 < P.nnz / n < 6.0
+    assert np.abs(P @ np.ones(na) - 1.0)[np.abs(A @ np.ones(n)) < 1e-12].max() <= 1e-14      # constants are reproduced where A 1 = 0
+    Ac = (Pref.T @ A @ Pref).tocsr()
+    assert np.abs(_csr(lv[1]) - Ac).max() <= 1e-13 * np.abs(Ac).max()
+    Ainv = np.linalg.inv(_csr(lv[1]).toarray())
+    dj = 0.7 / A.diagonal()
+
+    def cycle(b):
+        x = dj * b
+        x = x + P @ (Ainv @ (P.T @ (b - A @ x)))
+        return x + dj * (b - A @ x)
+
+    b = A @ np.random.default_rng(0).standard_normal(n)
+    x, it = proto.pcg(A, b, cycle)
+    cyc, sizes, _, _ = proto.smoothed_hierarchy_cycle(A)
+    _, itp = proto.pcg(A, b, cyc)
+    assert it == itp == 20 and sizes == [8820, 343]
+    assert np.linalg.norm(A @ x - b) <= 2e-13 * np.linalg.norm(b)
+    # the plain form still exports its (one entry per row) prolongation
+    lv0 = _levels(nek, A, 2048)
+    assert np.array_equal(lv0[0]["p_col"], lv0[0]["agg"]) and np.array_equal(lv0[0]["p_val"], np.ones(n))

@@ -188,10 +188,11 @@ def test_crs_facade_against_a_dense_solve(nek, null_space):
 @pytest.mark.skipif(os.environ.get("NEKB_TEST_UNVALIDATED") != "1",
                     reason="device cycle over the aggregation hierarchy (csrc/crs_amg_dev.cuh) was written after the round's GPU "
                            "budget was spent: not yet run on a GPU (set NEKB_TEST_UNVALIDATED=1)")
-@pytest.mark.parametrize("m,nmax,iters", [(20, 4096, 27), (8, 4096, 1), (32, 800, None)])
-def test_crs_amg_device_cycle_against_numpy(nek, m, nmax, iters):
+@pytest.mark.parametrize("m,nmax,omega_p,iters", [(20, 4096, 0.0, 27), (20, 4096, 0.66, 20), (8, 4096, 0.0, 1), (32, 800, 0.0, None),
+                                                  (32, 800, 0.66, None)])
+def test_crs_amg_device_cycle_against_numpy(nek, m, nmax, omega_p, iters):
     """CG + V(1,1) aggregation cycle on the device against the same algorithm in numpy on the same (library-built) levels:
-    same iteration count (27 at 8820 vertices, the prototype's number), solution to 1e-10, residual at the requested 1e-13."""
+    same iteration count (27 at 8820 vertices, 20 with the smoothed prolongation: the prototype's numbers), solution to 1e-10, residual at the requested 1e-13."""
     import ctypes as C
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
@@ -203,10 +204,10 @@ def test_crs_amg_device_cycle_against_numpy(nek, m, nmax, iters):
     A = proto.q1_stiffness(m)
     n = A.shape[0]
     co = A.tocoo()
-    lv = nek.crs_amg_build_host(n, co.row, co.col, co.data, nmax=nmax, theta=0.02)
+    lv = nek.crs_amg_build_host(n, co.row, co.col, co.data, nmax=nmax, theta=0.02, omega_p=omega_p)
     check(lib().nekb_crs_amg_upload(0.7))
     mats = [sp.csr_matrix((l["val"], l["col"], l["rowptr"]), shape=(l["n"], l["n"])) for l in lv]
-    Ps = [sp.csr_matrix((np.ones(l["n"]), (np.arange(l["n"]), l["agg"])), shape=(l["n"], lv[k + 1]["n"])) for k, l in enumerate(lv[:-1])]
+    Ps = [sp.csr_matrix((l["p_val"], l["p_col"], l["p_rowptr"]), shape=(l["n"], lv[k + 1]["n"])) for k, l in enumerate(lv[:-1])]
     Ainv = np.linalg.inv(mats[-1].toarray())
 
     def cycle(b, l=0):
