@@ -385,7 +385,7 @@ def ref_ophinv():
     return out
 
 
-def hsolve_inputs(case, pres=False):
+def hsolve_inputs(case, pres=False, consistent=False):
     """A slowly varying sequence of right-hand sides (what successive time steps hand to hsolve) and the h1/h2 of each call;
     h2 changes at call 4, which makes project1 rebuild B = A X and re-orthogonalise (iproj_chk)."""
     n = case.n
@@ -396,20 +396,22 @@ def hsolve_inputs(case, pres=False):
     calls = []
     for k in range(4 if pres else 11):     # 11 > mmx + 1: the space saturates at mmx = 8 and the oldest vector is rotated out
         rhs = f[0] + np.sin(0.3 * k) * f[1] + 0.05 * k * k * f[2]
+        if consistent:       # all-Neumann pressure problem: the right-hand side integrates to zero, as crespsp's does after ortho
+            rhs = rhs - case.bm1() * (rhs.sum() / case.bm1().sum())
         calls.append((rhs, h1, h2 * (1.1 if (k >= 4 and not pres) else 1.0), 10 + k))
     return calls
 
 
-def _ref_hsolve(name, pres):
-    case = case_of("core")
+def _ref_hsolve(name, pres, case=None, tol=1e-7):
+    case = case or case_of("core")
     rc = _ref(case)
     R, n = rc.R, case.n
     if pres:
         R.set("ifmgrid", 1)
         R.var("param")[[39, 40, 41, 42, 43]] = 0.0
         R.call("set_overlap")
-        R.var("param")[20] = 1e-7       # param(21)
-        R.set("tolps", 1e-7)
+        R.var("param")[20] = tol        # param(21)
+        R.set("tolps", tol)
     mask = rc.fld("pmask" if pres else "v1mask")
     R.var("param")[21] = 0.0            # param(22)
     R.var("param")[92] = 20.0           # param(93): projection on, mxprev vectors
@@ -420,10 +422,10 @@ def _ref_hsolve(name, pres):
     approx, napprox = np.zeros(24 * n), np.zeros(10, dtype=np.int32)
     out = dict(mask=mask, vmult=rc.fld("vmult"), binvm1=rc.fld("binvm1"), volvm1=np.array([R.get("volvm1")]))
     its, ms = [], []
-    for k, (rhs, h1, h2, istep) in enumerate(hsolve_inputs(case, pres)):
+    for k, (rhs, h1, h2, istep) in enumerate(hsolve_inputs(case, pres, consistent=bool(R.get("ifvcor")) and pres)):
         R.set("istep", istep)
         u, r = np.zeros(n), rhs.copy()
-        R.call("hsolve", name, u, r, h1, h2, mask, out["vmult"], 1, 1e-7, 200, 1, approx, napprox, out["binvm1"])
+        R.call("hsolve", name, u, r, h1, h2, mask, out["vmult"], 1, tol, 200, 1, approx, napprox, out["binvm1"])
         its.append(int(R.get("niterhm"))), ms.append(int(napprox[1]))
         out[f"u{k}"], out[f"r{k}"] = u, r
     out["its"], out["m"] = np.array(its), np.array(ms)
@@ -441,6 +443,15 @@ def ref_hsolve_pres():
     """The same around the pressure solver of the Pn-Pn formulation: hsolve('PRES') -> project1 -> hmhzpf -> cggo('PRES') ->
     hmh_gmres (gmres.f:304-545) with h1mg_solve as preconditioner -> project2; four successive solves."""
     return _ref_hsolve("PRES", True)
+
+
+def ref_hsolve_pres_channel():
+    """BASELINE config 5 as examples/turbChannel/turbChannel.par runs it: Pn-Pn, [PRESSURE] residualTol = 1e-4 with
+    residualProj = yes -- hsolve('PRES') with the residual projection around hmh_gmres / h1mg_solve, on the turbChannel mesh
+    (4^3 cut: periodic x/z, stretched walls, constant null space); four successive solves."""
+    out = _ref_hsolve("PRES", True, channel_case(), 1e-4)
+    out["ifvcor"] = np.array([1])
+    return out
 
 
 MET9 = ("rxm2", "sxm2", "txm2", "rym2", "sym2", "tym2", "rzm2", "szm2", "tzm2")
@@ -530,7 +541,7 @@ def ref_map():
     return out
 
 
-REFERENCE = dict(channel=ref_channel, ethier=ref_ethier, core=ref_core, core_lx6=ref_core_lx6, h1mg_lx6=ref_h1mg_lx6, h1mg_lx4=ref_h1mg_lx4, h1mg_lx10=ref_h1mg_lx10, periodic=ref_periodic, map=ref_map, eop=ref_eop, uzawa=ref_uzawa, hsolve=ref_hsolve, hsolve_pres=ref_hsolve_pres, ophinv=ref_ophinv, bp5=ref_bp5, h1mg=ref_h1mg, h1mg_neumann=ref_h1mg_neumann, fdm=ref_fdm, pnpn2=ref_pnpn2)
+REFERENCE = dict(channel=ref_channel, ethier=ref_ethier, core=ref_core, core_lx6=ref_core_lx6, h1mg_lx6=ref_h1mg_lx6, h1mg_lx4=ref_h1mg_lx4, h1mg_lx10=ref_h1mg_lx10, periodic=ref_periodic, map=ref_map, eop=ref_eop, uzawa=ref_uzawa, hsolve=ref_hsolve, hsolve_pres=ref_hsolve_pres, hsolve_pres_channel=ref_hsolve_pres_channel, ophinv=ref_ophinv, bp5=ref_bp5, h1mg=ref_h1mg, h1mg_neumann=ref_h1mg_neumann, fdm=ref_fdm, pnpn2=ref_pnpn2)
 
 
 def reference_all():

@@ -413,3 +413,22 @@ def test_gmres_residual_history_against_the_reference_givens_data(name):
     big = h > 1e-5 * h[0]
     assert big.sum() >= 8 and np.all(np.abs(ref - h)[big] <= 1e-10 * h[big])
     assert abs(ref[-1] - h[-1]) <= 1e-6 * h[-1] and h[-1] < float(g["tol"][0]) <= h[-2]
+
+
+def test_hsolve_pres_on_the_channel_mesh_as_turbchannel_par_runs_it():
+    """BASELINE config 5 with the settings of examples/turbChannel/turbChannel.par: residualTol 1e-4, residualProj = yes --
+    hsolve('PRES') + project1/2 around hmh_gmres / h1mg_solve with the constant null space; four successive solves need 10, 8,
+    7, 2 iterations in the reference and in the restatement (fields to 1e-10)."""
+    from oracle import proj
+    g, c = G["hsolve_pres_channel"], refcases.channel_case()
+    assert g["its"].tolist() == [10, 8, 7, 2] and g["m"].tolist() == [1, 2, 3, 4]
+    mg = hsmg.H1MG(c, refcases.channel_fbc(c), null_space=True)
+    P = proj.Projection(c, g["mask"], g["vmult"])
+    vol = float(g["volvm1"][0])
+    for k, (rhs, h1, h2, istep) in enumerate(refcases.hsolve_inputs(c, pres=True, consistent=True)):
+        def solver(f, t):
+            tolps = min(proj.chktcg1(c, 1e-4, f, h1, h2, g["mask"], g["vmult"], g["binvm1"], vol), 1e-4)
+            return hsmg.hmh_gmres(c, mg, f, h1, h2, g["mask"], g["vmult"], tolps, 200, ifvcor=True)
+        u, r, it = proj.hsolve_projected(c, P, rhs, h1, h2, 1e-4, 200, istep, g["binvm1"], vol, solver)
+        assert P.m == g["m"][k] and it == g["its"][k]
+        assert relmax(u, g[f"u{k}"]) <= 1e-10, k
