@@ -219,7 +219,8 @@ def _pressure_case(case, with_geometry=False, capped=0):
 
 def _velocity_solve(rc, case):
     """One velocity Helmholtz solve of a time step on the same mesh: hmholtz('VELX') (hmholtz.f:2-69 -> cggo :611-846) with
-    h1 = 1/Re, h2 = bd(1)/dt (the constants of ethier.par: viscosity 0.01, dt 2e-3) on an un-assembled right-hand side."""
+    constant h1 = 0.01 (viscosity) and h2 = 500 (bd/dt) -- a mass-dominated balance of the kind a time step produces, not the
+    literal values of ethier.par (viscosity 0.1, dt 1e-4, bdf3) -- on an un-assembled right-hand side, tolerance 1e-9."""
     R, n = rc.R, case.n
     rng = np.random.default_rng(11)
     h1, h2 = np.full(n, 0.01), np.full(n, 1.0 / 2e-3)
