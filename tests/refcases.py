@@ -267,8 +267,22 @@ def ref_channel_full():
 
 
 def ref_ethier():
-    """BASELINE config 2 (ethier box, 27 elements on [-1,1]^3, all sides 'v  '): the same set."""
-    return _pressure_case(ethier_case(), with_geometry=True)
+    """BASELINE config 2 (ethier box, 27 elements on [-1,1]^3, all sides 'v  '): the same set, plus the velocity solve with the
+    literal constants of short_tests/ethier/ethier.par: viscosity = -10 (h1 = 0.1), dt = 1e-4 with bdf3 (h2 = (11/6)/dt),
+    [VELOCITY] residualTol = 1e-12."""
+    case = ethier_case()
+    out = _pressure_case(case, with_geometry=True)
+    rc = _ref(case)
+    R, n = rc.R, case.n
+    rng = np.random.default_rng(12)
+    h1, h2 = np.full(n, 0.1), np.full(n, (11.0 / 6.0) / 1e-4)
+    rhs = rc.fld("bm1") * rng.standard_normal(n) * h2[0]              # the size of bd/dt * B u
+    x, r = np.zeros(n), rhs.copy()
+    R.var("param")[21] = 0.0
+    R.set("ifsolv", 0), R.set("kfldfdm", -1), R.set("istep", 10), R.set("ifield", 1)
+    R.call("hmholtz", "VELX", x, r, h1, h2, rc.fld("v1mask"), rc.fld("vmult"), 1, 1e-12, 200, 1)
+    out.update(par_h1=h1[:1].copy(), par_h2=h2[:1].copy(), par_rhs=rhs, par_x=x, par_it=np.array([R.get("niterhm")]))
+    return out
 
 
 def ref_h1mg():

@@ -432,3 +432,20 @@ def test_hsolve_pres_on_the_channel_mesh_as_turbchannel_par_runs_it():
         u, r, it = proj.hsolve_projected(c, P, rhs, h1, h2, 1e-4, 200, istep, g["binvm1"], vol, solver)
         assert P.m == g["m"][k] and it == g["its"][k]
         assert relmax(u, g[f"u{k}"]) <= 1e-10, k
+
+
+def test_ethier_par_velocity_solve_where_chktcg1_bites():
+    """short_tests/ethier/ethier.par literally: viscosity 0.1, dt 1e-4 with bdf3, [VELOCITY] residualTol = 1e-12.  That tolerance
+    is below what double precision can deliver for this operator, so hmholtz's chktcg1 (hmholtz.f:527-609) raises it to 1.8e-9
+    and the reference stops after 7 iterations; the restatement reproduces tolerance, count and field bit for bit."""
+    from oracle import proj
+    g, c = G["ethier"], refcases.ethier_case()
+    n = c.n
+    rhs = c.dssum(g["par_rhs"]) * c.mask
+    h1, h2 = np.full(n, g["par_h1"][0]), np.full(n, g["par_h2"][0])
+    tol = proj.chktcg1(c, 1e-12, rhs, h1, h2, c.mask, c.mult, c.binv(), float(g["volvm1"][0]))
+    assert 1e-9 < tol < 3e-9
+    x, it = c.cggo(rhs, h1, h2, tin=tol, maxit=200, istep=10)
+    assert it == g["par_it"][0] == 7 and np.array_equal(x, g["par_x"])
+    _, it_unchecked = c.cggo(rhs, h1, h2, tin=1e-12, maxit=200, istep=10)
+    assert it_unchecked > it                                      # without chktcg1 the loop would run on

@@ -319,3 +319,18 @@ def test_hsolve_pres_on_the_channel_mesh_as_turbchannel_par_runs_it(nek):
         assert napprox[1] == g["m"][k]
         assert abs(it - g["its"][k]) <= 1, (k, it, g["its"])
         assert relmax(u, g[f"u{k}"]) <= 1e-5, k
+
+
+@pytest.mark.skipif(os.environ.get("NEKB_TEST_UNVALIDATED") != "1",
+                    reason="added after the round's GPU budget was spent: not yet run on a GPU (set NEKB_TEST_UNVALIDATED=1)")
+def test_ethier_par_velocity_solve_where_chktcg1_bites(nek):
+    """ethier.par's literal velocity solve (viscosity 0.1, dt 1e-4 / bdf3, residualTol 1e-12): hmholtz's chktcg1 raises the
+    tolerance to 1.8e-9; the reference stops after 7 iterations."""
+    g, case = G["ethier"], refcases.ethier_case()
+    n = case.n
+    _register(nek, case, [g[f"g{i}m1"] for i in range(1, 7)], g["bm1"], g["binvm1"], g["volvm1"][0], g["zgm1"], g["wxm1"], g["dxm1"])
+    nek.set_step_info(10, float(g["volvm1"][0]))
+    nek.set_param(22, 0.0)
+    x, rhs = np.zeros(n), g["par_rhs"].copy()
+    it = nek.hmholtz("VELX", x, rhs, np.full(n, g["par_h1"][0]), np.full(n, g["par_h2"][0]), g["v1mask"], g["vmult"], 1, 1e-12, 200, 1)
+    assert it == g["par_it"][0] == 7 and relmax(x, g["par_x"]) <= TOL_CONVERGED
