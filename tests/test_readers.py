@@ -208,7 +208,10 @@ def test_the_reference_files_themselves(nek):
             assert np.abs(a.reshape(8, E, order="F").T - b).max() <= 2e-16
         cbc, _ = nek.re2_read_bc(tc + ".re2", 0)
         assert (cbc == b"W  ").sum() == 2 * 16 * 8 and (cbc == b"P  ").sum() == 2 * (12 * 8 + 16 * 12)
-        _, _, vertex = nek.ma2_read(tc + ".ma2")
+        _, leaf, vertex = nek.ma2_read(tc + ".ma2")
+        for npr in (4, 8):                          # turbChannel.par: minNumProcesses = 4; the 8-GPU box of BASELINE config 5
+            part = nek.assign_gllnid(leaf, None, npr)
+            assert np.bincount(part, minlength=npr).tolist() == [1536 // npr] * npr
         mine = c.vertex.reshape(E, 8)
         assert len(np.unique(vertex)) == len(np.unique(mine)) == 16 * 13 * 8
         fwd = dict(zip(vertex.ravel().tolist(), mine.ravel().tolist()))
