@@ -43,6 +43,7 @@ NXYZ = LX1 ** 3
 WORDS_AX = 8.0                   # read p, 6 geometric factors, write w
 WORDS_AX_CG = 12.0               # fused kernel: + read/write u (x += alpha p) + read r, write p (p = r + beta p); the p read is shared
 WORDS_ITER = 19.445              # + gs/mask 1.445 + x,r update 6 + weight 1 + p update 3
+WORDS_ITER_EXECUTED = 12.0 + 1.445 + 3.125   # what the fused path moves: ax_cg 12 + gs 1.445 + (r, w read; r write; 1-byte code) 3.125
 
 
 def peaks():
@@ -129,6 +130,33 @@ def ref_leg(steps: int, warmup: int, target_s: float):
         return None
 
 
+def parity_check(rank, world, local, layout):
+    """N > 1: before anything is timed, a small brick-partitioned BP5 problem (2x2x1 deformed elements per rank, 40 CG
+    iterations) is solved on the same ranks, through the same exchange path, and every rank's part is compared with the
+    oracle's UNDIVIDED solve (the checker, not the thing measured; tests/_mgpu_worker.py runs the same comparison).
+    Returns {"max_rel_vs_oracle", "its", ...} (max over ranks) for the JSON line."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import oracle
+    from nek5000_b200 import nek
+    from nek5000_b200.bp5 import BP5
+    px, py, pz = layout
+    nelx, nely, nelz, maxit = 2 * px, 2 * py, 1 * pz, 40
+    b = BP5(nelx, nely, nelz, lx1=LX1, device=local, rank=rank, nranks=world, layout=layout, deform=0.04)
+    it, _, hist = b.solve(-1e-8, maxit, history=True)
+    ref = oracle.bp5_partitioned_reference(nelx, nely, nelz, layout, rank, maxit=maxit, deform=0.04)
+    rel = lambda x, y: float(np.abs(x - y).max() / max(np.abs(y).max(), 1e-300))
+    d = {"u": rel(b.get("u1"), ref["u"]), "r1": rel(b.get("r1"), ref["r1"]), "pap_history": rel(hist[:, 0], ref["hist"][:, 0])}
+    ok = int(np.array_equal(b.get("mult"), ref["mult"]) and it == ref["it"])
+    t = torch.tensor([d["u"], d["r1"], d["pap_history"], float(1 - ok)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    u, r1, pap, bad = (float(v) for v in t.tolist())
+    return {"max_rel_vs_oracle": max(u, r1, pap), "its": int(it), "its_oracle": int(ref["it"]), "solution": u, "rhs": r1,
+            "pap_history": pap, "multiplicity_and_count_identical": bad == 0.0,
+            "problem": f"{nelx}x{nely}x{nelz} deformed elements in bricks {px}x{py}x{pz}, {maxit} CG iterations, every rank against the undivided oracle solve"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -139,6 +167,10 @@ def main():
     ap.add_argument("--maxit", type=int, default=500, help="CG iterations per solve (bp5.par:13-15)")
     ap.add_argument("--m-cpu", type=int, default=32, help="CPU-baseline sample: elements per direction")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --m^3 elements PER GPU (the driver's contract); strong: --m^3 elements in TOTAL, split into bricks "
+                         "(BASELINE configs[3] / SURVEY 8d: E = 262,144 on 1/2/4/8 GPUs)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the small multi-rank parity problem run before the timed region")
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -148,11 +180,19 @@ def main():
 
     from nek5000_b200.bp5 import brick_layout
     px, py, pz = brick_layout(max(a.gpus, 1))
-    config = {"workload": f"BP5 box mesh, N=7 (lx1=8), FP64, E={a.m}^3={a.m ** 3} elements per GPU "
-                          f"({a.m * px}x{a.m * py}x{a.m * pz} global, bricks {px}x{py}x{pz}), cggos {a.maxit} fixed CG "
+    if a.scaling == "strong":
+        gx = gy = gz = a.m                                         # the whole job is m^3 elements
+        assert a.m % px == 0 and a.m % py == 0 and a.m % pz == 0, "strong scaling: --m must be divisible by the brick counts"
+        per = f"E={a.m}^3={a.m ** 3} elements in total, {a.m ** 3 // max(a.gpus, 1)} per GPU"
+    else:
+        gx, gy, gz = a.m * px, a.m * py, a.m * pz
+        per = f"E={a.m}^3={a.m ** 3} elements per GPU"
+    E_per = gx * gy * gz // max(a.gpus, 1)
+    config = {"workload": f"BP5 box mesh, N=7 (lx1=8), FP64, {per} "
+                          f"({gx}x{gy}x{gz} global, bricks {px}x{py}x{pz}), cggos {a.maxit} fixed CG "
                           f"iterations per step (bp5.par), identity preconditioner, all-Dirichlet box [0,1]^3",
-              "elements_global": a.m ** 3 * max(a.gpus, 1), "iterations_per_step": a.maxit,
-              "l2": "inputs larger than L2 (each n-vector 1.07 GB, factors 6.4 GB per GPU at E=262,144)"}
+              "elements_global": gx * gy * gz, "iterations_per_step": a.maxit,
+              "l2": f"inputs larger than L2 (each n-vector {E_per * 512 * 8 / 1e9:.2f} GB, factors {E_per * 512 * 48 / 1e9:.2f} GB per GPU)"}
 
     if a.impl == "reference":
         if rank != 0:
@@ -161,9 +201,15 @@ def main():
         if leg is None:
             leg, kind = cpu_leg(max(a.steps, 1), a.warmup, a.m_cpu, target_s=4.0), "port"
         gd, nt, sample, ms = leg
+        # the CPU arm runs a BOUNDED SAMPLE of the workload, not the 64^3-per-GPU mesh: say so where the config is read
+        config = dict(config, workload_of_the_gpu_arm=config["workload"],
+                      workload="CPU arm, bounded sample of the same BP5 case (N=7, FP64, cggos, same iteration body): " + sample,
+                      same_config_as_gpu_arm=False,
+                      note="the value is a host-CPU throughput on this box and does not depend on --gpus")
+        config.pop("elements_global", None)
         emit(({"impl": "reference", "metric": "BP5 Poisson GDOF/s (N=7, FP64)", "value": gd, "unit": "GDOF/s",
                           "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                          "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f64",
                           "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": gd, "unit": "GDOF/s", "cores": nt, "kind": kind, "sample": sample},
                           "e2e": {"value": gd, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -186,7 +232,10 @@ def main():
     if world > 1:
         nek.comm_init_torch()
     assert world == max(a.gpus, 1), f"--gpus {a.gpus} but WORLD_SIZE={world}"
-    case = BP5(a.m * px, a.m * py, a.m * pz, lx1=LX1, device=local, rank=rank, nranks=world, layout=(px, py, pz))
+    parity = None
+    if world > 1 and not a.no_parity:
+        parity = parity_check(rank, world, local, (px, py, pz))
+    case = BP5(gx, gy, gz, lx1=LX1, device=local, rank=rank, nranks=world, layout=(px, py, pz))
     n, E_glob = case.n, case.nel_global
     L = lib()
     try:  # how the inter-rank part of gs_op runs (0 single rank, 1 NCCL send/recv, 2 peer memory over NVLink)
@@ -278,17 +327,22 @@ def main():
     tot_prof = sum(v[0] for v in prof.values())
     out = {
         "metric": "BP5 Poisson GDOF/s (N=7, FP64)", "value": value, "unit": "GDOF/s", "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": warmup, "ms_per_step": dev_s / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": warmup, "ms_per_step": dev_s / a.steps * 1e3, "higher_is_better": True, "scaling": a.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
         "relerr": relerr, "wall_ms_per_step": wall_s / a.steps * 1e3, "gpu_launches": launches, "clocks": clocks,
-        "e2e": e2e,
+        "e2e": e2e, "parity": parity,
         "roofline": {"bound": "hbm", "kernel": ax_name, "achieved": ax_gbs, "peak": peak,
                      "unit": "GB/s", "frac": (ax_gbs / peak) if ax_gbs else None, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ax_bytes, "mean_launch_ms": ax_s / max(ax_n, 1) * 1e3,
                      "share_of_step": ax_s / tot_prof if tot_prof > 0 else None,
                      "kernel_ms_per_iteration": {k: v[0] / max(v[1], 1) * 1e3 for k, v in prof.items()},
                      "whole_iteration": {"achieved": iter_gbs, "frac": iter_gbs / peak,
-                                         "algorithmic_bytes_per_element_iteration": WORDS_ITER * 8 * NXYZ}},
+                                         "algorithmic_bytes_per_element_iteration": WORDS_ITER * 8 * NXYZ,
+                                         "accounting": "SURVEY 8(d): 19.445 words per point (unfused kernel sequence)",
+                                         "executed": {"achieved": iter_gbs * WORDS_ITER_EXECUTED / WORDS_ITER,
+                                                      "frac": iter_gbs * WORDS_ITER_EXECUTED / WORDS_ITER / peak,
+                                                      "bytes_per_element_iteration": WORDS_ITER_EXECUTED * 8 * NXYZ,
+                                                      "accounting": "bytes the fused path needs: 16.57 words per point"}}},
     }
     # dram__bytes_read+write per launch of the same kernel from the committed ncu --set full captures (E = 262,144)
     if case.nel == 262144:

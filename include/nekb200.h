@@ -171,6 +171,9 @@ int nekb_set_v1mask(const double *v1mask);
  * scalars cggo reads: volvm1, voltm1 (core/MASS), param(18,22) stay at their defaults. */
 int nekb_set_ifield(int ifield);
 int nekb_set_field_handle(int ifield, int gs_handle);
+/* TSTEP restol(0:ldimt1) (set by core/reader_par.f from residualTol / param(22)): a non-zero restol(ifield) overrules the
+ * tolerance cggo receives unless that one is negative (core/hmholtz.f:673-679).  0 (default) = use the caller's. */
+int nekb_set_restol(int ifield, double restol);
 int nekb_set_step_info(int istep, double volvm1, double voltm1);
 /* core/induct.f:1022-1090 ophinv(o1,o2,o3,i1,i2,i3,h1,h2,tolh,nmxhi): o_k = (h1 A + h2 B)^-1 i_k for the three velocity
  * components -- in the reference three hsolve -> hmholtz -> cggo calls in a row (standard branch: ifstrs = .false., no

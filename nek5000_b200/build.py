@@ -6,6 +6,7 @@ The library is the product: nothing here falls back to a CPU path when it is mis
 """
 from __future__ import annotations
 
+import glob
 import os
 import shutil
 import subprocess
@@ -15,8 +16,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnekb200.so")
 SOURCES = ["nekb200.cu"]
-HEADERS = ["common.cuh", "ctx.cuh", "ax.cuh", "gs.cuh", "cg.cuh", "comm.cuh", "setup.cuh", "hsmg.cuh", "fdm_h1.cuh", "gmres.cuh", "hcg.cuh",
-           "readers.cuh", "proj.cuh", "pnpn2.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -32,7 +31,9 @@ def is_stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(HERE, "..", "include", "nekb200.h")]
+    # every header of csrc/ is a dependency of the single translation unit (no hand-kept list to go stale)
+    deps = [os.path.join(CSRC, f) for f in SOURCES] + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + \
+           [os.path.join(HERE, "..", "include", "nekb200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -533,6 +533,14 @@ inline int cggos_run_fused(const CggosArgs &a, int maxit, double *hist_host, boo
 }
 
 // ---------------------------------------------------------------------------------------------- cggo
+// core/hmholtz.f:673-679: tol = abs(tin); a non-zero restol(ifield) overrules it; a negative tin (relative tolerance)
+// overrules both.  The kernels take "tin" and apply abs() / the relative rule, so the override is folded in here.
+inline double cggo_tin(double tin)
+{
+    Ctx &c = ctx();
+    const double rt = (c.ifield >= 0 && c.ifield < 32) ? c.restol[c.ifield] : 0.0;
+    return (tin >= 0.0 && rt != 0.0) ? rt : tin;
+}
 struct CggoArgs {
     double *x;
     const double *f, *h1, *h2, *mask, *mult, *binv;

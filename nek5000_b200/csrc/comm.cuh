@@ -294,11 +294,12 @@ inline void gs_p2p_setup(GsMap &h)
     host_allgather(&mine, all.data(), sizeof mine);
     bool ok = true;
     for (const GsP2pRecord &r : all) ok = ok && r.ok;   // the same decision on every rank
-    if (!ok || np == 0) {
-        if (!ok) h.xmem.release();
-        h.p2p = ok;     // a rank without peers has nothing to exchange but stays in step
+    if (!ok) {          // the same verdict on every rank (all see the same records): nobody goes on to the second collective
+        h.xmem.release();
         return;
     }
+    // A rank without peers (np == 0) has nothing to open, but it MUST still join the verdict all-gather below: the ranks
+    // that do have peers call it, and a collective that some ranks skip pairs with whatever those ranks call next.
     std::vector<double *> precv(np);
     std::vector<int64_t> pstride(np), myoff(np);
     std::vector<unsigned long long *> parr(np), pdone(np);
@@ -337,6 +338,10 @@ inline void gs_p2p_setup(GsMap &h)
     if (!ok) {
         gs_p2p_release(h);
         h.xmem.release();
+        return;
+    }
+    if (np == 0) {      // nothing to exchange, but in step with the others
+        h.p2p = true;
         return;
     }
     std::vector<unsigned char> ip((size_t)nitems);

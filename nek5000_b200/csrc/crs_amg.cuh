@@ -7,9 +7,8 @@
 // constant prolongation (optionally smoothed by one damped-Jacobi step: smoothed aggregation), Galerkin coarse matrices,
 // damped Jacobi, the dense inverse at the coarsest level.
 //
-// STATUS: this file is set-up only and runs on the host (like setvert3d_host and gen_fast); it is exercised on the CPU by
-// tests/test_crs_amg_host.py through nekb_crs_amg_*.  The device cycle (CSR mat-vec, gather / scatter by aggregate) that
-// consumes it is NOT written yet, and nothing in the solve path uses this file.
+// This file is the set-up and runs on the host (like setvert3d_host and gen_fast); it is exercised on the CPU by
+// tests/test_crs_amg_host.py through nekb_crs_amg_*.  The device cycle that consumes it is crs_amg_dev.cuh.
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -74,6 +73,19 @@ inline std::vector<int32_t> amg_aggregate(const CsrHost &A, double theta, int32_
     };
     std::vector<int32_t> agg((size_t)n, -1);
     na = 0;
+    // Decoupled unknowns (a row with no off-diagonal non-zero: the identity rows of masked / Dirichlet vertices) would each
+    // stay an aggregate of their own on every level and keep the hierarchy from ever reaching `nmax` (a box side of
+    // Dirichlet vertices: 49^2 singletons at 48^3 elements).  They all share ONE aggregate: its coarse row is the sum of
+    // their diagonals (still SPD), and their right-hand side is zero wherever the solver is used (masked dofs).
+    int32_t iso = -1;
+    for (int64_t i = 0; i < n; i++) {
+        bool coupled = false;
+        for (int64_t q = A.rowptr[i]; q < A.rowptr[i + 1] && !coupled; q++) coupled = A.col[q] != i && A.val[q] != 0.0;
+        if (!coupled) {
+            if (iso < 0) iso = na++;
+            agg[i] = iso;
+        }
+    }
     for (int64_t i = 0; i < n; i++) {
         if (agg[i] >= 0) continue;
         bool all_free = true;
@@ -203,7 +215,13 @@ inline AmgHierarchy amg_build(CsrHost A0, int64_t nmax, double theta, double ome
     while (H.A.back().n > nmax) {
         int32_t na = 0;
         std::vector<int32_t> g = amg_aggregate(H.A.back(), theta, na);
-        NEKB_REQUIRE((double)na < 0.7 * (double)H.A.back().n, "amg_build: aggregation stalled (no strong connections at this theta)");
+        if (!((double)na < 0.7 * (double)H.A.back().n)) {
+            // no further coarsening at this strength threshold: this level becomes the coarsest one if the dense inverse that
+            // serves it can hold it, otherwise the set-up fails loudly
+            NEKB_REQUIRE(H.A.back().n <= 16384 && H.A.size() > 1,
+                         "amg_build: aggregation stalled (no strong connections at this theta) above the dense-solver size");
+            break;
+        }
         CsrHost P = amg_prolongator(H.A.back(), g, na, omega_p);
         CsrHost PT = csr_transpose(P);
         CsrHost Ac = omega_p > 0.0 ? spgemm(PT, spgemm(H.A.back(), P)) : amg_galerkin(H.A.back(), g, na);

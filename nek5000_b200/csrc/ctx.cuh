@@ -113,6 +113,7 @@ struct Ctx {
     double volvm1 = 0.0, voltm1 = 0.0;
     int niterhm = 0;
     double param[201] = {0};       // INPUT param(1:200) entries the path reads (18, 21, 22); 1-based
+    double restol[32] = {0};       // TSTEP restol(0:ldimt1): per-field residual tolerance that overrules cggo's tin (hmholtz.f:676)
     DevBuf<double> binvm1, bintm1; // MASS binvm1 / bintm1 for hmholtz
     DevBuf<double> vmask[3], vmult; // SOLN v1mask,v2mask,v3mask and vmult for ophinv
     int niter3[3] = {0, 0, 0};     // niterhm of the three component solves of the last ophinv

@@ -452,6 +452,8 @@ inline bool hcg_run(int nrhs, double *const *x, const double *const *f, const do
         }
     }
     const bool has_h2 = h2max > 0.0;
+    // before hcg_prep_kernel reads bm1[t]: an unregistered bm1 must give this message, not a device fault
+    if (has_h2) NEKB_REQUIRE(c.bm1.p != nullptr && c.bm1.n >= (size_t)n, "hcg: bm1 must be registered (h2 != 0)");
     if (has_h2) S.h2b.ensure((size_t)n);
     NEKB_CUDA(cudaMemsetAsync(S.flag.p, 0, sizeof(int), s));
     hcg_prep_kernel<<<grid, CG_THREADS, 0, s>>>(S.mcode.p, has_h2 ? S.h2b.p : nullptr, mask[0], nrhs > 1 ? mask[1] : nullptr,
@@ -461,7 +463,6 @@ inline bool hcg_run(int nrhs, double *const *x, const double *const *f, const do
     NEKB_CUDA(cudaMemcpyAsync(&notbinary, S.flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     NEKB_CUDA(cudaStreamSynchronize(s));
     if (notbinary) return false;
-    if (has_h2) NEKB_REQUIRE(c.bm1.n >= (size_t)n, "hcg: bm1 must be registered (h2 != 0)");
 
     setprec_run(S.d.p, h1, h2, nel, gs_handle);  // :690 (depends on h1, h2 only: shared by the components)
 
@@ -559,6 +560,7 @@ inline bool hcg_run(int nrhs, double *const *x, const double *const *f, const do
 // branches hcg does not provide (Schwarz preconditioner, null-space correction, lx1 != 8, non-binary masks).
 inline int cggo_solve(const CggoArgs &a, double tin, int maxit, double *hist_host)
 {
+    tin = cggo_tin(tin);  // restol(ifield), hmholtz.f:676
     if (hcg_applicable(1)) {
         double *xs[1] = {a.x};
         const double *fs[1] = {a.f}, *ms[1] = {a.mask};

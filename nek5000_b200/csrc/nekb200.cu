@@ -407,6 +407,14 @@ int nekb_set_ifield(int ifield)
         ctx().ifield = ifield;
     });
 }
+int nekb_set_restol(int ifield, double restol)
+{
+    return guard([&] {
+        NEKB_REQUIRE(ifield >= 0 && ifield < 32, "ifield out of range");
+        NEKB_REQUIRE(restol >= 0.0, "restol must be >= 0 (0 = cggo uses the caller's tolerance)");
+        ctx().restol[ifield] = restol;
+    });
+}
 int nekb_set_field_handle(int ifield, int gs_handle)
 {
     return guard([&] {
@@ -482,6 +490,7 @@ static void ophinv_dev(double *const *o, double *const *rhs, const double *h1, c
         if (c.param[22] == 0.0 || c.istep <= 10)                                     // :59-60
             tol[k] = chktcg1_dev(tol[k], rhs[k], h1, h2max > 0.0 ? h2 : nullptr, mask[k], mult, binv, nel, c.volvm1);
         if (tolh < 0) tol[k] = tolh;                                                 // :62
+        tol[k] = cggo_tin(tol[k]);                                                   // :676 restol(ifield)
     }
     const double *f[3] = {rhs[0], rhs[1], rhs[2]};
     if (hcg_applicable(3) &&
@@ -909,6 +918,7 @@ void hmholtz_(const char *name, double *u, double *rhs, const double *h1, const 
         require_init();
         Ctx &c = ctx();
         const bool pres = name_len >= 4 && !strncmp(name, "PRES", 4);
+        fdm_h1_state().kfldfdm = pres ? 4 : -1;  // hmholtz.f:44-50: every call resets it (ldim+1 for 'PRES', else Jacobi)
         const int nel = *imsh == 1 ? c.nelv : c.nelt;
         const size_t n = (size_t)nel * c.nxyz;
         const DevBuf<double> &binv = *imsh == 1 ? c.binvm1 : (c.bintm1.n ? c.bintm1 : c.binvm1);
@@ -2162,6 +2172,12 @@ static void *bp5_ptr(const char *which, size_t *bytes)
     NEKB_REQUIRE(false, "unknown array name '" + w + "'");
     return nullptr;
 }
+static void *bp5_ptr_checked(const char *which, size_t *bytes)
+{
+    void *p = bp5_ptr(which, bytes);
+    NEKB_REQUIRE(p != nullptr, std::string("array '") + which + "' was released (lean BP5 set-up above 10^6 elements, NEKB_BP5_LEAN)");
+    return p;
+}
 int nekb_bp5_get(const char *which, void *host_out, size_t n_bytes)
 {
     return guard([&] {
@@ -2178,7 +2194,7 @@ int nekb_bp5_get(const char *which, void *host_out, size_t n_bytes)
             return;
         }
         size_t bytes = 0;
-        void *p = bp5_ptr(which, &bytes);
+        void *p = bp5_ptr_checked(which, &bytes);
         NEKB_REQUIRE(n_bytes >= bytes, "output buffer too small");
         NEKB_CUDA(cudaMemcpyAsync(host_out, p, bytes, cudaMemcpyDeviceToHost, c.stream));
         NEKB_CUDA(cudaStreamSynchronize(c.stream));
@@ -2191,7 +2207,7 @@ void *nekb_bp5_devptr(const char *which)
     void *p = nullptr;
     guard([&] {
         size_t bytes;
-        p = bp5_ptr(which, &bytes);
+        p = bp5_ptr_checked(which, &bytes);
     });
     return p;
 }

@@ -610,7 +610,13 @@ inline void bp5_setup(int nelx, int nely, int nelz, int px, int py, int pz, doub
     }
     std::vector<int64_t> glo((size_t)n);
     b.ngv = setvert3d_host(glo.data(), nx, nel, b.vertex.data(), c.nranks);
-    b.glo_num.upload(glo.data(), (size_t)n, s);
+    // BASELINE config 3 (E swept until HBM is full): above a million elements (or with NEKB_BP5_LEAN=1) everything the solve
+    // itself does not read is released or never uploaded -- coordinates, the int64 numbering, the mass matrix: 5 of 15
+    // field-sized arrays.  nekb_bp5_get / nekb_bp5_devptr on a released array fail loudly.
+    const char *lean_env = getenv("NEKB_BP5_LEAN");
+    const bool lean = lean_env ? atoi(lean_env) != 0 : nel > 1000000;
+    if (!lean) b.glo_num.upload(glo.data(), (size_t)n, s);
+    else b.xm1.release(), b.ym1.release(), b.zm1.release();      // before the gs set-up's temporaries are allocated
     // candidates for sharing with other ranks: nodes on brick faces that have a neighbouring brick
     std::vector<int32_t> cand;
     if (c.nranks > 1) {
@@ -656,6 +662,7 @@ inline void bp5_setup(int nelx, int nely, int nelz, int px, int py, int pz, doub
     b.u1.alloc(n);
     b.u1.zero(s);
     NEKB_CUDA(cudaStreamSynchronize(s));
+    if (lean) c.bm1.release();
     b.built = true;
 }
 

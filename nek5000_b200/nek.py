@@ -126,6 +126,11 @@ def set_field_handle(ifield: int, gs_handle: int) -> None:
     check(lib().nekb_set_field_handle(ifield, gs_handle))
 
 
+def set_restol(ifield: int, restol: float) -> None:
+    """TSTEP restol(ifield): overrules cggo's tolerance when non-zero (core/hmholtz.f:676)."""
+    check(lib().nekb_set_restol(ifield, restol))
+
+
 def set_step_info(istep: int, volvm1: float, voltm1: float | None = None) -> None:
     check(lib().nekb_set_step_info(istep, volvm1, volvm1 if voltm1 is None else voltm1))
 

@@ -319,3 +319,33 @@ def cpu_cggos(case: "Case", rhs, maxit: int, nthreads: int = 0):
     sec = L.nkb_cpu_cggos(u, np.ascontiguousarray(rhs), case.mult, case.mask, off, idx, len(off) - 1, case.gf(),
                           case.nx, case.nel, case.d, case.dt, maxit, nt)
     return u, sec, nt
+
+
+def bp5_partitioned_reference(nelx, nely, nelz, layout, rank, maxit=40, deform=0.04, nx=8):
+    """The undivided BP5 solve a brick-partitioned run must reproduce on rank `rank` (checker for the multi-GPU tests and
+    for bench.py's `parity` field at N > 1).  Every rank draws the seed-1 ran1 stream over its LOCAL nodes in local element
+    order (core/navier5.f:2665-2698), so the exact solution of the undivided mesh is that stream placed brick by
+    brick; e1 = dsavg(.)*mask, r1 = mask*dssum(A e1) (bp5.usr:352-360), then cggos on the whole mesh.
+    Returns dict(take=<global node indices of this rank's nodes in its local order>, e1, r1, u, hist, it, mult, glo_num)
+    with the fields already restricted to the rank."""
+    px, py, pz = layout
+    case = Case(nelx, nely, nelz, nx=nx, deform=deform)
+    nxyz = nx ** 3
+    lx, ly, lz = nelx // px, nely // py, nelz // pz
+    eg = np.arange(case.nel)
+    ex, ey, ez = eg % nelx, (eg // nelx) % nely, eg // (nelx * nely)
+    owner = (ex // lx) + px * ((ey // ly) + py * (ez // lz))
+    local_of = (ex % lx) + lx * ((ey % ly) + ly * (ez % lz))
+    nloc = lx * ly * lz * nxyz
+    stream = np.zeros(nloc)
+    lib().nko_rand_fld(stream, nloc)
+    rnd = stream.reshape(-1, nxyz)[local_of].reshape(-1)
+    e1 = case.dssum(rnd) * case.mult * case.mask
+    ap, _ = case.ax_bp5(e1)
+    r1 = case.dssum(ap) * case.mask
+    uref, itref, href = case.cggos(r1, e1, maxit=maxit, history=True)
+    mine = np.flatnonzero(owner == rank)
+    order = mine[np.argsort(local_of[mine])]
+    take = (order[:, None] * nxyz + np.arange(nxyz)[None, :]).reshape(-1)
+    return dict(case=case, take=take, e1=e1[take], r1=r1[take], u=uref[take], hist=href, it=itref, mult=case.mult[take],
+                glo_num=case.glo_num[take])

@@ -27,12 +27,23 @@ def main():
         dims = tuple(int(v) for v in d.split("x")) if "x" in d else (int(d),) * 3
         nek.finalize()
         nek.init(0, 8, 3)
-        b = BP5(*dims, lx1=8)
-        b.solve(-1e-8, 5)
-        it, sec = b.solve(-1e-8, a.its)
+        try:
+            import torch
+            free0 = torch.cuda.mem_get_info(0)
+            b = BP5(*dims, lx1=8)
+            b.solve(-1e-8, 5)
+            it, sec = b.solve(-1e-8, a.its)
+            free1 = torch.cuda.mem_get_info(0)
+        except Exception as ex:            # a size that does not fit fails loudly inside the library; the sweep records it
+            rows.append({"dims": dims, "E": dims[0] * dims[1] * dims[2], "error": str(ex)[-200:]})
+            print(json.dumps(rows[-1]), file=sys.stderr, flush=True)
+            continue
         gbs = 79648.0 * b.nel * it / sec / 1e9
         rows.append({"dims": dims, "E": b.nel, "ms_per_iteration": sec / it * 1e3, "gdofs": it * b.nel * 343 / sec / 1e9,
-                     "alg_GBs": gbs, "frac_of_hbm_peak": gbs / peak if peak else None})
+                     "alg_GBs": gbs, "frac_of_hbm_peak": gbs / peak if peak else None, "relerr": b.relerr(),
+                     "hbm_used_GB": (free1[1] - free1[0]) / 1e9, "hbm_total_GB": free1[1] / 1e9})
+        print(json.dumps(rows[-1]), file=sys.stderr, flush=True)
+        del b
     nek.finalize()
     print(json.dumps({"workload": "BP5 cggos, N=7, FP64, one GPU", "its": a.its, "hbm_peak_GBs": peak, "sweep": rows}))
 

@@ -56,6 +56,12 @@ def aggregate(A, theta=0.02):
     S = sp.csr_matrix((np.abs(C.data[strong]), (C.row[strong], C.col[strong])), shape=(n, n))
     agg = -np.ones(n, dtype=np.int64)
     na = 0
+    # decoupled unknowns (no off-diagonal non-zero: identity rows of masked vertices) share one aggregate
+    offd = sp.csr_matrix(((C.data != 0) & (C.row != C.col), (C.row, C.col)), shape=(n, n))
+    iso = np.asarray(offd.sum(axis=1)).ravel() == 0
+    if iso.any():
+        agg[iso] = 0
+        na = 1
     ip, ix = S.indptr, S.indices
     for i in range(n):
         if agg[i] >= 0:

@@ -1,0 +1,160 @@
+"""torchrun worker -- BASELINE config 5 on N GPUs: the pressure solve (h1mg_solve preconditioner + hmh_gmres) on the complete
+mesh of examples/turbChannel (16 x 12 x 8 = 1536 elements, periodic x/z, stretched walls, lx1 = 8, constant null space),
+elements distributed as the reference distributes them: rank of a global element = assign_gllnid (core/map2.f:943-1026) of
+the RSB leaves in examples/turbChannel/turbChannel.ma2, local order = ascending global element id (core/map2.f:233-236),
+vertex ids = the .ma2's genmap numbering (fixture tests/golden/channel_partition.npz, made from the reference's files by
+tests/golden/gen_channel_partition.py -- /root/reference does not exist on the GPU box).
+
+Parity: every rank's part of h1mg_solve's output and of the GMRES solution against the reference's own single-rank run
+(tests/golden/ref_channel_full.npz: iteration count 56 incl. one GMRES(30) restart, fields at 4096 sampled positions).
+Timing (device-resident, CUDA events through the library's stream, max over ranks): ms per h1mg_solve call and per GMRES solve.
+Prints 'MGPU-CHANNEL-OK rank r ...' per rank and one JSON line (rank 0) starting with 'CHANNEL-JSON '."""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import refcases
+    from nek5000_b200 import nek
+    from nek5000_b200._lib import check, lib
+
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    calls = int(os.environ.get("NEKB_CHANNEL_CALLS", "20"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nek.init(local, 8, 3)
+    if world > 1:
+        nek.comm_init_torch()
+    L = lib()
+
+    g = dict(np.load(refcases.GOLDEN_CHANNEL_FULL))
+    part = np.load(os.path.join(HERE, "golden", "channel_partition.npz"))
+    case = refcases.channel_case(refcases.CHANNEL_FULL_DIMS)
+    Eg, nxyz = case.nel, 512
+    gllnid = part[f"gllnid_np{world}"] if world > 1 else np.zeros(Eg, dtype=np.int32)
+    order = np.flatnonzero(gllnid == rank)                     # ascending global element id
+    nel = len(order)
+    take = (order[:, None] * nxyz + np.arange(nxyz)[None, :]).reshape(-1)
+    loc = lambda a: np.ascontiguousarray(a[take])
+    geo = case.geom()
+    nek.set_nel(nel, nel)
+    nek.set_gll(case.z, case.w)
+    nek.set_dxyz(case.D, np.ascontiguousarray(case.D.T))
+    nek.set_geom(*[loc(a) for a in geo[:7]])
+    nek.set_ifdfrm(None)
+    vertex = np.ascontiguousarray(part["vertex"][order].reshape(-1))           # the .ma2's own vertex ids
+    h, _ = nek.setupds(8, nel, vertex, Eg)
+    nek.set_ifield(1)
+    nek.set_field_handle(1, h)
+    vol = float(g["volvm1"][0])
+    nek.set_step_info(1, vol)
+    nek.set_binv(loc(case.binv()))
+    t0 = time.perf_counter()
+    nek.h1mg_setup(np.ascontiguousarray(refcases.channel_fbc(case)[order]), loc(case.xm1), loc(case.ym1), loc(case.zm1), vertex, nel, True)
+    setup_s = time.perf_counter() - t0
+    pmask = np.ones(case.n)
+    rhs, b = refcases.pressure_inputs(case, pmask)
+    tol = float(g["tol"][0])
+    nek.set_pressure_state(loc(pmask), loc(case.binv()), tol, tol, True, Eg)
+
+    # ---- parity against the reference's single-rank run -------------------------------------------------------------
+    idx = g["idx"]
+    pos = np.searchsorted(take, idx)
+    pos[pos >= len(take)] = 0
+    here = take[pos] == idx                                     # sampled positions this rank owns
+    lpos = pos[here]
+    D = nek.DevArray
+    zd, rd = D(nel * nxyz), D.from_host(loc(rhs))
+    check(L.nekb_h1mg_solve_dev(zd.ptr, rd.ptr))
+    z = zd.to_host()
+    dz = np.abs(z[lpos] - g["z_s"][here]).max() / g["z_max"][0] if here.any() else 0.0
+    assert dz <= 1e-9, ("h1mg_solve", dz)
+    h1d, wtd = D.from_host(np.ones(nel * nxyz)), D.from_host(loc(case.mult))
+    pmd = D.from_host(loc(pmask))
+    it = C.c_int(0)
+    hist = np.zeros(101)
+    xd = D.from_host(loc(b))
+    check(L.nekb_hmh_gmres_dev(xd.ptr, h1d.ptr, None, wtd.ptr, pmd.ptr, tol, 100, C.byref(it), hist.ctypes.data, None))
+    x = xd.to_host()
+    dx = np.abs(x[lpos] - g["x_s"][here]).max() / g["x_max"][0] if here.any() else 0.0
+    assert it.value == int(g["it"][0]), ("GMRES iteration count", it.value, int(g["it"][0]))
+    assert dx <= 1e-8, ("GMRES solution", dx)
+    # the reference's own record of the last GMRES cycle: |s_k| = rnorm_k / rnorm_{k-1} (gmres.f:486-493)
+    j = it.value - 30 * ((it.value - 1) // 30)
+    ratios = hist[it.value - j + 1:it.value + 1] / hist[it.value - j:it.value]
+    dr = np.abs(ratios[1:] - g["gmres_s"][1:j]).max() if j > 1 else 0.0
+    l2 = torch.tensor([float(np.sum(x * x * loc(case.mult)))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(l2)
+
+    # ---- timing ---------------------------------------------------------------------------------------------------------
+    def sync():
+        check(L.nekb_sync())
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    stream = torch.cuda.ExternalStream(int(L.nekb_stream()))
+    for _ in range(3):
+        check(L.nekb_h1mg_solve_dev(zd.ptr, rd.ptr))
+    sync()
+    nek.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(calls):
+        check(L.nekb_h1mg_solve_dev(zd.ptr, rd.ptr))
+    e1.record(stream)
+    sync()
+    mg_ms = maxr(e0.elapsed_time(e1) / calls)
+    mg_launches = nek.launch_count() / calls
+    best = 1e30
+    bloc = loc(b)
+    for _ in range(3):
+        xd = D.from_host(bloc)
+        sync()
+        e0.record(stream)
+        check(L.nekb_hmh_gmres_dev(xd.ptr, h1d.ptr, None, wtd.ptr, pmd.ptr, tol, 100, C.byref(it), None, None))
+        e1.record(stream)
+        sync()
+        best = min(best, maxr(e0.elapsed_time(e1)))
+    print(f"MGPU-CHANNEL-OK rank {rank} of {world}: nel={nel} gmres its={it.value} rel(z)={dz:.2e} rel(x)={dx:.2e} "
+          f"max|s_k - ref|={dr:.1e}", flush=True)
+    if rank == 0:
+        info = nek.h1mg_info()
+        print("CHANNEL-JSON " + json.dumps({
+            "workload": "examples/turbChannel mesh 16x12x8 = 1536 elements, lx1=8, 786,432 points, periodic x/z, null space; "
+                        "partition = assign_gllnid of turbChannel.ma2's RSB leaves; tol 1e-8",
+            "n_gpus": world, "elements_per_gpu": nel, "h1mg_setup_s": setup_s, "h1mg_solve_ms": mg_ms,
+            "h1mg_solve_launches": mg_launches, "gmres_iterations": it.value, "gmres_ms": best,
+            "gmres_ms_per_iteration": best / max(it.value, 1), "reference_iterations": int(g["it"][0]),
+            "parity": {"h1mg_solve_max_rel": dz, "gmres_solution_max_rel": dx, "gmres_givens_max_abs": dr,
+                       "x_weighted_l2": float(np.sqrt(l2.item())), "reference_x_l2_unweighted": float(g["x_l2"][0])},
+            "h1mg_info": info}),
+            flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    nek.finalize()
+
+
+if __name__ == "__main__":
+    main()

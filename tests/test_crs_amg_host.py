@@ -53,8 +53,14 @@ def test_duplicates_and_errors(nek):
     assert np.array_equal(lv[0]["val"], [3.0, -1.0, -1.0, 4.0, 5.0])
     with pytest.raises(NekbError):                          # index outside the matrix
         nek.crs_amg_build_host(3, [0, 3], [0, 0], [1.0, 1.0], nmax=8)
-    with pytest.raises(NekbError):                          # diagonal matrix above nmax: no strong connection, aggregation stalls
-        nek.crs_amg_build_host(64, np.arange(64), np.arange(64), np.ones(64), nmax=8)
+    # decoupled unknowns (identity rows of masked vertices) share ONE aggregate, so they cannot keep a hierarchy above nmax
+    lv = nek.crs_amg_build_host(64, np.arange(64), np.arange(64), np.ones(64), nmax=8)
+    assert [l["n"] for l in lv] == [64, 1] and lv[1]["val"].tolist() == [64.0] and not lv[0]["agg"].any()
+    with pytest.raises(NekbError):                          # coupled, but nothing is strong at this theta: aggregation stalls
+        n = 40000
+        i = np.arange(n - 1)
+        nek.crs_amg_build_host(n, np.concatenate([np.arange(n), i, i + 1]), np.concatenate([np.arange(n), i + 1, i]),
+                               np.concatenate([np.ones(n), np.full(2 * (n - 1), -1e-3)]), nmax=8)
 
 
 def test_cycle_over_the_exported_levels_converges_like_the_prototype(nek):

@@ -459,3 +459,22 @@ def test_multi_gpu_h1mg_and_gmres_match_single_domain_oracle(world):
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("MGPU-HSMG-OK") == world
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_multi_gpu_channel_pressure_solve_matches_the_reference(world):
+    """BASELINE config 5: the turbChannel pressure solve with the elements distributed by the reference's own partition of
+    turbChannel.ma2 (tests/_mgpu_channel_worker.py) -- GMRES count 56 and fields against the reference's single-rank run."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, NEKB_CHANNEL_CALLS="5")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(29560 + world), os.path.join(here, "_mgpu_channel_worker.py")],
+                       capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("MGPU-CHANNEL-OK") == world

@@ -136,9 +136,6 @@ def test_cggo_history_against_the_reference_lanczos_tridiagonal(nek):
     assert np.all(np.abs(upper - g["cggo_upper"][:win - 1]) <= 1e-9 * np.abs(g["cggo_upper"][:win - 1]))
 
 
-@pytest.mark.skipif(os.environ.get("NEKB_TEST_UNVALIDATED") != "1",
-                    reason="crs_setup_/crs_solve_ facade was written after the round's GPU budget was spent: not yet run on a GPU "
-                           "(set NEKB_TEST_UNVALIDATED=1)")
 @pytest.mark.parametrize("null_space", [False, True])
 def test_crs_facade_against_a_dense_solve(nek, null_space):
     """core/fcrs.c crs_setup / crs_solve (XXT slot) on the vertex mesh of a 4 x 3 x 2 box: ids = vertex numbers (0 on a
@@ -185,9 +182,6 @@ def test_crs_facade_against_a_dense_solve(nek, null_space):
     nek.crs_free(h)
 
 
-@pytest.mark.skipif(os.environ.get("NEKB_TEST_UNVALIDATED") != "1",
-                    reason="device cycle over the aggregation hierarchy (csrc/crs_amg_dev.cuh) was written after the round's GPU "
-                           "budget was spent: not yet run on a GPU (set NEKB_TEST_UNVALIDATED=1)")
 @pytest.mark.parametrize("m,nmax,omega_p,iters", [(20, 4096, 0.0, 27), (20, 4096, 0.66, 20), (8, 4096, 0.0, 1), (32, 800, 0.0, None),
                                                   (32, 800, 0.66, None)])
 def test_crs_amg_device_cycle_against_numpy(nek, m, nmax, omega_p, iters):
@@ -231,9 +225,6 @@ def test_crs_amg_device_cycle_against_numpy(nek, m, nmax, omega_p, iters):
     assert np.linalg.norm(A @ x - b) <= 5e-13 * np.linalg.norm(b)
 
 
-@pytest.mark.skipif(os.environ.get("NEKB_TEST_UNVALIDATED") != "1",
-                    reason="h1mg coarse solve through the aggregation hierarchy (NEKB_CRS_AMG=1) was written after the round's GPU "
-                           "budget was spent: not yet run on a GPU (set NEKB_TEST_UNVALIDATED=1)")
 @pytest.mark.parametrize("name", ["ethier", "channel"])
 def test_h1mg_solve_with_the_aggregation_coarse_solver(nek, name, monkeypatch):
     """h1mg_solve / hmh_gmres with the coarse problem solved by CG over the aggregation hierarchy instead of the dense inverse
@@ -258,10 +249,6 @@ def test_h1mg_solve_with_the_aggregation_coarse_solver(nek, name, monkeypatch):
     assert it == g["it"][0] and relmax(res, g["x"]) <= TOL_FIELD
 
 
-@pytest.mark.skipif(os.environ.get("NEKB_TEST_UNVALIDATED") != "1",
-                    reason="added after the round's GPU budget was spent: not yet run on a GPU (set NEKB_TEST_UNVALIDATED=1); "
-                           "tests/test_gpu_hsmg.py already holds these orders to the oracle, which tests/test_ref_pins.py pins to the "
-                           "reference")
 @pytest.mark.parametrize("nx", [4, 6, 10])
 def test_h1mg_and_gmres_at_other_orders_against_the_reference(nx):
     """lx1 = 4 (two multigrid levels), 6 and 10: h1mg_solve, hmh_gmres and hmh_flex_cg directly against the reference's output
@@ -297,8 +284,6 @@ def test_h1mg_and_gmres_at_other_orders_against_the_reference(nx):
         nek.finalize()
 
 
-@pytest.mark.skipif(os.environ.get("NEKB_TEST_UNVALIDATED") != "1",
-                    reason="added after the round's GPU budget was spent: not yet run on a GPU (set NEKB_TEST_UNVALIDATED=1)")
 def test_hsolve_pres_on_the_channel_mesh_as_turbchannel_par_runs_it(nek):
     """BASELINE config 5 with turbChannel.par's settings (residualTol 1e-4, residualProj = yes): hsolve('PRES') -> project1 ->
     hmhzpf -> cggo('PRES') -> hmh_gmres with h1mg_solve -> project2 on the channel mesh with the constant null space; the
@@ -321,8 +306,6 @@ def test_hsolve_pres_on_the_channel_mesh_as_turbchannel_par_runs_it(nek):
         assert relmax(u, g[f"u{k}"]) <= 1e-5, k
 
 
-@pytest.mark.skipif(os.environ.get("NEKB_TEST_UNVALIDATED") != "1",
-                    reason="added after the round's GPU budget was spent: not yet run on a GPU (set NEKB_TEST_UNVALIDATED=1)")
 def test_ethier_par_velocity_solve_where_chktcg1_bites(nek):
     """ethier.par's literal velocity solve (viscosity 0.1, dt 1e-4 / bdf3, residualTol 1e-12): hmholtz's chktcg1 raises the
     tolerance to 1.8e-9; the reference stops after 7 iterations."""
