@@ -171,6 +171,10 @@ int nekb_set_v1mask(const double *v1mask);
  * scalars cggo reads: volvm1, voltm1 (core/MASS), param(18,22) stay at their defaults. */
 int nekb_set_ifield(int ifield);
 int nekb_set_field_handle(int ifield, int gs_handle);
+/* Residual history of the most recent cggo (rows of 3: rtz1, rbn2, rho per executed check, core/hmholtz.f:754-802) or
+ * hmh_gmres (rows of 1: rnorm per iteration, core/gmres.f:486-498) solve, whichever entry point ran it -- the
+ * numbers the reference prints per iteration and keeps nowhere.  out may be NULL to query the shape. */
+int nekb_last_history(double *out, int64_t capacity, int *rows, int *cols);
 /* TSTEP restol(0:ldimt1) (set by core/reader_par.f from residualTol / param(22)): a non-zero restol(ifield) overrules the
  * tolerance cggo receives unless that one is negative (core/hmholtz.f:673-679).  0 (default) = use the caller's. */
 int nekb_set_restol(int ifield, double restol);

@@ -405,6 +405,83 @@ __global__ void __launch_bounds__(CG_THREADS)
     });
 }
 
+// Default form of the update with the direct-stiffness summation folded in (structured gather, gs.cuh gs_ensure_struct):
+// `ap` holds A p with only the "S" groups assembled in place; face-interior nodes add their partner through the 8-byte
+// affine link of their face, edge / corner nodes read their group's value from gval, interior nodes are final as they are.
+// Same members, same order as gs_local_kernel<1>, hence the same bits as the stock pair gs_op + cggos_update2_kernel.
+// One thread = 4 consecutive nodes (half a row of an 8^3 tile: same j, k; i = 0..3 or 4..7).
+__global__ void __launch_bounds__(CG_THREADS)
+    cggos_update3_kernel(double *__restrict__ r, const double *__restrict__ ap, const unsigned char *__restrict__ code,
+                         const FaceLink *__restrict__ ftab, const int32_t *__restrict__ etab, const double *__restrict__ gval,
+                         int64_t n, CgScalars *sc, double *partials)
+{
+    __shared__ double red[33];
+    __shared__ double wtab[128];
+    const double pap = sc->work[0], rz = sc->work[1];
+    const double alpha = rz / pap;
+    if (threadIdx.x < 128) wtab[threadIdx.x] = threadIdx.x ? 1.0 / (double)threadIdx.x : 0.0;
+    __syncthreads();
+    double s = 0.0;
+    const int64_t n4 = n >> 2;   // n is a multiple of 512
+    double2 *r2 = reinterpret_cast<double2 *>(r);
+    const double2 *a2 = reinterpret_cast<const double2 *>(ap);
+    const uchar4 *c4 = reinterpret_cast<const uchar4 *>(code);
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n4; t += (int64_t)gridDim.x * blockDim.x) {
+        double2 ra = r2[2 * t], rb = r2[2 * t + 1];
+        const double2 aa = a2[2 * t], ab = a2[2 * t + 1];
+        const uchar4 c = c4[t];
+        double w[4] = {aa.x, aa.y, ab.x, ab.y};
+        const int l4 = (int)(t & 127);                 // position of the quad in its tile
+        const int64_t el = t >> 7;
+        const int i0 = (l4 & 1) << 2, j = (l4 >> 1) & 7, k = l4 >> 4;
+        const int bj = (j == 0 || j == 7), bk = (k == 0 || k == 7);
+        if (bj + bk == 0) {
+            // only the row end (i = 0 or 7) is on the surface: a node of an x-face
+            const int ie = i0 ? 3 : 0;                 // index in the quad of the surface node
+            const FaceLink L = ftab[el * 6 + (i0 ? 1 : 0)];
+            if (L.base >= 0 && !(((const unsigned char *)&c)[ie] & 0x80)) w[ie] += ap[(int64_t)L.base + j * L.sa + k * L.sb];
+        } else if (bj + bk == 1) {
+            // a y- or z-face row: the three inner nodes of the quad are face-interior, the row end is an edge node
+            const int f = bj ? 2 + (j == 7) : 4 + (k == 7);
+            const int bco = bj ? k : j;                // second in-face coordinate (first is i)
+            const FaceLink L = ftab[el * 6 + f];
+            const int ie = i0 ? 3 : 0;
+            if (L.base >= 0) {
+                const int64_t pb = (int64_t)L.base + bco * L.sb;
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (q != ie) w[q] += ap[pb + (i0 + q) * L.sa];
+            }
+            const int g = etab[el * GS_ST_EDGE_SLOTS + gs_st_slot(i0 ? 7 : 0, j, k)];
+            if (g >= 0) w[ie] = gval[g];
+        } else {
+            // an x-edge row (j and k on the surface): every node is an edge node, the row end a corner
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int g = etab[el * GS_ST_EDGE_SLOTS + gs_st_slot(i0 + q, j, k)];
+                if (g >= 0) w[q] = gval[g];
+            }
+        }
+        ra.x = fma(-alpha, (c.x & 0x80) ? 0.0 : w[0], ra.x);
+        ra.y = fma(-alpha, (c.y & 0x80) ? 0.0 : w[1], ra.y);
+        rb.x = fma(-alpha, (c.z & 0x80) ? 0.0 : w[2], rb.x);
+        rb.y = fma(-alpha, (c.w & 0x80) ? 0.0 : w[3], rb.y);
+        r2[2 * t] = ra;
+        r2[2 * t + 1] = rb;
+        s = fma(wtab[c.x & 0x7f] * ra.x, ra.x, s);
+        s = fma(wtab[c.y & 0x7f] * ra.y, ra.y, s);
+        s = fma(wtab[c.z & 0x7f] * rb.x, rb.x, s);
+        s = fma(wtab[c.w & 0x7f] * rb.y, rb.y, s);
+    }
+    double b = block_reduce(s, red);
+    grid_reduce(b, partials, &sc->counter[2], red, [=](double tot) {
+        sc->rtz1 = rz;
+        sc->work[1] = tot;
+        sc->alpha = alpha;
+        sc->it = sc->it + 1;
+    });
+}
+
 // u += alpha * p with the device-resident alpha (the u update of the final iteration)
 __global__ void __launch_bounds__(CG_THREADS)
     axpy_alpha_kernel(double *__restrict__ u, const double *__restrict__ p, int64_t n, const CgScalars *sc)
@@ -432,7 +509,7 @@ inline int axcg_variant()
 inline int gs_fuse_update_enabled()  // read per solve, so one process can time both forms
 {
     const char *e = getenv("NEKB_GS_FUSE_UPDATE");
-    return e ? atoi(e) : 0;
+    return e ? atoi(e) : 3;
 }
 inline int cg_fused_enabled()
 {
@@ -473,9 +550,12 @@ inline int cggos_run_fused(const CggosArgs &a, int maxit, double *hist_host, boo
 
     // gather form of dssum inside the update kernel: one rank only (no remote members to wait for)
     // (1 = every group gathered by the update kernel; 2 = pairs gathered, edge / corner groups assembled in place first)
+    // 3 (default) = structured gather: face pairs through per-face affine links, edge / corner groups through gval, groups
+    // with remote members in place + the inter-rank exchange; 0 = the stock pair gs_op + update2
     const int gmode = gs_fuse_update_enabled();
     const bool gather = (gmode == 1 || gmode == 2) && c.nranks == 1 && h.nshared == 0;
     if (gather) gs_ensure_link(h, gmode);
+    const bool structured = gmode == 3 && gs_ensure_struct(h);
     cggos_init2_kernel<<<grid, CG_THREADS, 0, s>>>(a.u, r.p, a.rhs, a.mult, n, sc, c.partials.p + 1 * CG_PART_STRIDE);
     NEKB_LAUNCHED();
     comm_allreduce_sum(&sc->work[1], 1);
@@ -488,7 +568,24 @@ inline int cggos_run_fused(const CggosArgs &a, int maxit, double *hist_host, boo
         }
         prof_end(PROF_AX);
         comm_allreduce_sum(&sc->work[0], 1);
-        if (gather) {
+        if (structured) {
+            prof_begin(PROF_GS);
+            if (h.ngroupsE > 0) {
+                gs_gval_kernel<<<blocks_for(h.ngroupsE), 256, 0, s>>>(h.gval.p, ap.p, h.goffE.p, h.gidxE.p, (int)h.ngroupsE);
+                NEKB_LAUNCHED();
+            }
+            if (h.ngroupsS > 0) {
+                gs_local_kernel<1><<<blocks_for(h.ngroupsS), 256, 0, s>>>(ap.p, h.goffS.p, h.gidxS.p, (int)h.ngroupsS);
+                NEKB_LAUNCHED();
+            }
+            if (h.nshared > 0 || c.nranks > 1) gs_remote_exchange(h, ap.p, 1);
+            prof_end(PROF_GS);
+            prof_begin(PROF_UPDATE);
+            cggos_update3_kernel<<<grid, CG_THREADS, 0, s>>>(r.p, ap.p, c.wcode.p, h.ftab.p, h.etab.p, h.gval.p, n, sc,
+                                                             c.partials.p + 2 * CG_PART_STRIDE);
+            NEKB_LAUNCHED();
+            prof_end(PROF_UPDATE);
+        } else if (gather) {
             if (gmode == 2 && h.ngroups3 > 0) {
                 prof_begin(PROF_GS);
                 gs_local_kernel<1><<<blocks_for(h.ngroups3), 256, 0, s>>>(ap.p, h.goff3.p, h.gidx3.p, (int)h.ngroups3);

@@ -2,10 +2,9 @@
 // operator, preconditioned by one V(1,1) cycle (damped Jacobi, CSR transfer operators, dense inverse at the coarsest
 // level through the crsd_* kernels of hsmg.cuh).  Plan and iteration counts: DESIGN.md section 8, scripts/proto_coarse_amg.py.
 //
-// STATUS: written after round 1's GPU budget was spent -- compiled, NOT YET RUN ON A GPU; h1mg's coarse solve uses it only with NEKB_CRS_AMG=1.  Entry
-// points nekb_crs_amg_upload / nekb_crs_amg_solve_dev; parity test (against numpy on the same levels) in
-// tests/test_zz_gpu_configs.py behind NEKB_TEST_UNVALIDATED=1;
-// the CG loop reads its scalars back every iteration (to be replaced by device-side control + a captured graph once correct).
+// Entry points nekb_crs_amg_upload / nekb_crs_amg_solve_dev; parity test (against numpy on the same levels) in
+// tests/test_zz_gpu_configs.py.  Two drivers of the same arithmetic: amg_pcg_solve (one launch per operation, scalars read
+// back every iteration: the readable form, NEKB_CRS_AMG_COOP=0) and amg_pcg_coop_kernel (one cooperative launch, default).
 #pragma once
 #include "crs_amg.cuh"
 #include "hsmg.cuh"
@@ -27,7 +26,8 @@ struct AmgDev {
     std::vector<AmgLevelDev> L;        // every level but the coarsest
     int64_t nc = 0, ld = 0;            // coarsest size, padded leading dimension
     DevBuf<double> ainv, cb, cy;       // explicit inverse, rhs / solution of the coarsest level
-    DevBuf<double> r, z, p, w, partial, scal;
+    DevBuf<double> r, z, p, p2, w, partial, scal, coop_part;
+    DevBuf<int> iters;
 };
 inline AmgDev &amg_dev()
 {
@@ -176,7 +176,7 @@ inline void amg_upload(double omega, const std::vector<double> *fine_mask = null
     D.cb.alloc((size_t)D.ld), D.cy.alloc((size_t)D.ld);
     D.cb.zero(s), D.cy.zero(s);
     const int64_t n0 = H.A[0].n;
-    D.r.alloc((size_t)n0), D.z.alloc((size_t)n0), D.p.alloc((size_t)n0), D.w.alloc((size_t)n0);
+    D.r.alloc((size_t)n0), D.z.alloc((size_t)n0), D.p.alloc((size_t)n0), D.p2.alloc((size_t)n0), D.w.alloc((size_t)n0);
     D.partial.alloc((size_t)c.num_sms * 8), D.scal.alloc(4);
     NEKB_CUDA(cudaStreamSynchronize(s));
     D.ready = true;
@@ -265,6 +265,232 @@ inline int amg_pcg_solve(double *x_dev, const double *b_dev, double tol, int max
     return maxit;
 }
 
+// ------------------------------------------------------------------------------------------------ one-launch form
+// The same CG + V(1,1) cycle as amg_pcg_solve in ONE cooperative launch: the whole hierarchy (<= 10^6 rows) lives in L2, so
+// the solve is bound by the number of grid-wide synchronisations, not by bandwidth; the host-driven form above costs ~19
+// launches and three scalar read-backs per iteration.  Phases of one iteration (3 levels: 10 grid syncs):
+//   w = A (z + beta p) [p rebuilt on the fly, double-buffered]; (p,w)              | sync
+//   x += a p; r -= a w; (r,r); level-0 pre-smoothing x0 = dj r, res0 = r - A x0 with the neighbours' new r rebuilt on the fly | sync
+//   per level below: restriction | sync | pre-smoothing | sync ... coarsest: y = Ainv b | sync
+//   per level upwards: x += P e | sync | post-smoothing (level 0: z, (r,z))        | sync
+// Scalars are combined from per-block partials in a fixed order by every block (coop_total), so all blocks take the same
+// branch and the result is run-to-run reproducible.
+constexpr int AMG_MAXLEV = 6;
+struct AmgCoopLevel {
+    int n;
+    const int32_t *rowptr, *col, *prow, *pcol, *trow, *tcol;
+    const double *val, *dj, *pval, *tval;
+    double *b, *x, *r, *e;      // rhs (level 0: the CG residual), iterate, residual, result of the level (level 0: z)
+};
+struct AmgCoopArgs {
+    int nlev;                   // levels above the coarsest
+    AmgCoopLevel L[AMG_MAXLEV];
+    int nc;
+    int64_t ld;
+    const double *ainv;
+    double *cb, *cy;
+    double *x, *r, *z, *p0, *p1, *w;
+    const double *b;
+    double tol;
+    int maxit;
+    double *partials;           // >= 4 * gridDim doubles
+    int *iters_out;
+};
+__global__ void __launch_bounds__(512) amg_pcg_coop_kernel(AmgCoopArgs A)
+{
+    namespace cgr = cooperative_groups;
+    cgr::grid_group grid = cgr::this_grid();
+    __shared__ double red[33];
+    __shared__ double s_b;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x, G = gridDim.x;
+    double *P0 = A.partials, *P1 = A.partials + G, *P2 = A.partials + 2 * G, *P3 = A.partials + 3 * G;
+    const AmgCoopLevel &F = A.L[0];
+    const int n = F.n;
+    // x = 0, r = b, (b,b)
+    {
+        double s = 0.0;
+        for (int i = tid; i < n; i += nth) {
+            const double bv = A.b[i];
+            A.x[i] = 0.0, A.r[i] = bv, A.p0[i] = 0.0;
+            s = fma(bv, bv, s);
+        }
+        const double t = block_reduce(s, red);
+        if (threadIdx.x == 0) P0[blockIdx.x] = t;
+    }
+    grid.sync();
+    const double bb = coop_total(P0, G, red, &s_b);
+    int it = 0;
+    if (bb > 0.0) {
+        const double stop2 = A.tol * A.tol * bb;
+        // one V(1,1) cycle on the current r -> z, with (r,z) partials in P1.  `fresh` = the level-0 pre-smoothing has already
+        // been done by the caller phase (fused with the r update).
+        auto cycle = [&](bool fresh) {
+            for (int l = 0; l < A.nlev; l++) {
+                const AmgCoopLevel &L = A.L[l];
+                if (!(l == 0 && fresh)) {
+                    const double *bl = l == 0 ? A.r : L.b;
+                    for (int i = tid; i < L.n; i += nth) {   // x = dj b ; r = b - A x
+                        double s = 0.0;
+                        for (int q = L.rowptr[i]; q < L.rowptr[i + 1]; q++) s = fma(L.val[q], L.dj[L.col[q]] * bl[L.col[q]], s);
+                        L.x[i] = L.dj[i] * bl[i];
+                        L.r[i] = bl[i] - s;
+                    }
+                    grid.sync();
+                }
+                const bool last = l + 1 == A.nlev;
+                double *bc = last ? A.cb : A.L[l + 1].b;
+                const int ncn = last ? A.nc : A.L[l + 1].n;
+                for (int i = tid; i < ncn; i += nth) {       // bc = P^T r
+                    double s = 0.0;
+                    for (int q = L.trow[i]; q < L.trow[i + 1]; q++) s = fma(L.tval[q], L.r[L.tcol[q]], s);
+                    bc[i] = s;
+                }
+                grid.sync();
+            }
+            {   // coarsest: y = Ainv b, one warp per row
+                const int lane = threadIdx.x & 31, w0 = tid >> 5, nw = nth >> 5;
+                for (int r = w0; r < A.nc; r += nw) {
+                    const double *row = A.ainv + (size_t)r * A.ld;
+                    double s = 0.0;
+                    for (int j = lane; j < A.nc; j += 32) s = fma(row[j], A.cb[j], s);
+                    s = warp_sum(s);
+                    if (lane == 0) A.cy[r] = s;
+                }
+            }
+            grid.sync();
+            for (int l = A.nlev - 1; l >= 0; l--) {
+                const AmgCoopLevel &L = A.L[l];
+                const bool last = l + 1 == A.nlev;
+                const double *ec = last ? A.cy : A.L[l + 1].e;
+                for (int i = tid; i < L.n; i += nth) {       // x += P e
+                    double s = 0.0;
+                    for (int q = L.prow[i]; q < L.prow[i + 1]; q++) s = fma(L.pval[q], ec[L.pcol[q]], s);
+                    L.x[i] += s;
+                }
+                grid.sync();
+                const double *bl = l == 0 ? A.r : L.b;
+                double *out = l == 0 ? A.z : L.e;
+                double rzp = 0.0;
+                for (int i = tid; i < L.n; i += nth) {       // out = x + dj (b - A x)
+                    double s = 0.0;
+                    for (int q = L.rowptr[i]; q < L.rowptr[i + 1]; q++) s = fma(L.val[q], L.x[L.col[q]], s);
+                    const double v = L.x[i] + L.dj[i] * (bl[i] - s);
+                    out[i] = v;
+                    if (l == 0) rzp = fma(bl[i], v, rzp);
+                }
+                if (l == 0) {
+                    const double t = block_reduce(rzp, red);
+                    if (threadIdx.x == 0) P1[blockIdx.x] = t;
+                }
+                grid.sync();
+            }
+        };
+        cycle(false);
+        double rz = coop_total(P1, G, red, &s_b);
+        double beta = 0.0;
+        double *pin = A.p0, *pout = A.p1;
+        for (; it < A.maxit;) {
+            {   // p = z + beta p (own entry stored, neighbours rebuilt) ; w = A p ; (p,w)
+                double s = 0.0;
+                for (int i = tid; i < n; i += nth) {
+                    double acc = 0.0;
+                    for (int q = F.rowptr[i]; q < F.rowptr[i + 1]; q++) {
+                        const int j = F.col[q];
+                        acc = fma(F.val[q], fma(beta, pin[j], A.z[j]), acc);
+                    }
+                    const double pi = fma(beta, pin[i], A.z[i]);
+                    pout[i] = pi;
+                    A.w[i] = acc;
+                    s = fma(pi, acc, s);
+                }
+                const double t = block_reduce(s, red);
+                if (threadIdx.x == 0) P2[blockIdx.x] = t;
+            }
+            grid.sync();
+            const double pw = coop_total(P2, G, red, &s_b);
+            const double alpha = rz / pw;
+            {   // x += a p ; r -= a w ; (r,r) ; level-0 pre-smoothing on the new r (neighbours' r rebuilt: r_j - a w_j)
+                double s = 0.0;
+                for (int i = tid; i < n; i += nth) {
+                    A.x[i] = fma(alpha, pout[i], A.x[i]);
+                    const double ri = fma(-alpha, A.w[i], A.r[i]);
+                    double acc = 0.0;
+                    for (int q = F.rowptr[i]; q < F.rowptr[i + 1]; q++) {
+                        const int j = F.col[q];
+                        acc = fma(F.val[q], F.dj[j] * fma(-alpha, A.w[j], A.r[j]), acc);
+                    }
+                    F.x[i] = F.dj[i] * ri;
+                    F.r[i] = ri - acc;
+                    A.z[i] = ri;             // parked: A.r is still being read by other threads' neighbour sums
+                    s = fma(ri, ri, s);
+                }
+                const double t = block_reduce(s, red);
+                if (threadIdx.x == 0) P3[blockIdx.x] = t;
+            }
+            grid.sync();
+            for (int i = tid; i < n; i += nth) A.r[i] = A.z[i];   // own entries only: no other thread reads r before the next sync
+            const double rr = coop_total(P3, G, red, &s_b);
+            it++;
+            if (rr <= stop2) break;
+            cycle(true);
+            const double rz_new = coop_total(P1, G, red, &s_b);
+            beta = rz_new / rz;
+            rz = rz_new;
+            double *tmp = pin;
+            pin = pout, pout = tmp;
+        }
+    }
+    if (tid == 0) *A.iters_out = it;
+}
+
+inline int amg_coop_enabled()
+{
+    const char *e = getenv("NEKB_CRS_AMG_COOP");
+    return e ? atoi(e) : 1;
+}
+
+// Launches the one-kernel solve; the iteration count stays on the device (D.iters) unless `want_iters`.
+inline int amg_pcg_solve_coop(double *x_dev, const double *b_dev, double tol, int maxit, bool want_iters)
+{
+    Ctx &c = ctx();
+    cudaStream_t s = c.stream;
+    AmgDev &D = amg_dev();
+    NEKB_REQUIRE(D.ready && !D.L.empty() && D.L.size() <= (size_t)AMG_MAXLEV, "amg_pcg_solve_coop: hierarchy not uploaded / too deep");
+    AmgCoopArgs A;
+    memset(&A, 0, sizeof A);
+    A.nlev = (int)D.L.size();
+    for (int l = 0; l < A.nlev; l++) {
+        AmgLevelDev &L = D.L[l];
+        AmgCoopLevel &o = A.L[l];
+        o.n = (int)L.n;
+        o.rowptr = L.rowptr.p, o.col = L.col.p, o.val = L.val.p, o.dj = L.dj.p;
+        o.prow = L.prow.p, o.pcol = L.pcol.p, o.pval = L.pval.p, o.trow = L.trow.p, o.tcol = L.tcol.p, o.tval = L.tval.p;
+        o.b = l > 0 ? L.b.p : nullptr, o.x = L.x.p, o.r = L.r.p, o.e = L.x2.p;
+    }
+    A.nc = (int)D.nc, A.ld = D.ld, A.ainv = D.ainv.p, A.cb = D.cb.p, A.cy = D.cy.p;
+    A.x = x_dev, A.r = D.r.p, A.z = D.z.p, A.p0 = D.p.p, A.p1 = D.p2.p, A.w = D.w.p, A.b = b_dev;
+    A.tol = tol, A.maxit = maxit;
+    static int per_sm = 0;
+    if (!per_sm) {
+        NEKB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, amg_pcg_coop_kernel, 512, 0));
+        NEKB_REQUIRE(per_sm >= 1, "amg_pcg_coop_kernel cannot be made resident");
+        per_sm = 1;   // one CTA per SM: the phases are synchronisation-bound, fewer arrivals make a cheaper grid sync
+    }
+    int gridc = (int)((D.L[0].n + 511) / 512);
+    if (gridc > c.num_sms * per_sm) gridc = c.num_sms * per_sm;
+    D.coop_part.ensure((size_t)4 * c.num_sms * per_sm);
+    D.iters.ensure(1);
+    A.partials = D.coop_part.p, A.iters_out = D.iters.p;
+    void *args[] = {&A};
+    NEKB_CUDA(cudaLaunchCooperativeKernel((void *)amg_pcg_coop_kernel, dim3(gridc), dim3(512), args, 0, s));
+    NEKB_LAUNCHED();
+    if (!want_iters) return -1;
+    int it = 0;
+    NEKB_CUDA(cudaMemcpyAsync(&it, D.iters.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    NEKB_CUDA(cudaStreamSynchronize(s));
+    return it;
+}
+
 // ------------------------------------------------------------------------------------------------ h1mg wiring
 // crs_solve semantics (see crs_dense_solve) with the explicit inverse replaced by amg_pcg_solve on the assembled operator:
 // gather to the distinct dofs, all-reduce, mask / mean removal, CG to k.tol, mean removal, scatter.  Every rank holds the
@@ -280,8 +506,13 @@ inline void crs_amg_solve(CrsSolver &k, double *x_out, const double *b_in)
     if (c.nranks > 1) comm_allreduce_sum(k.g.p, (int)nc);
     crsd_prep_kernel<<<1, 1024, 0, s>>>(k.g.p, k.gmask.p, nc, k.null_space, k.ndof);
     NEKB_LAUNCHED();
-    k.last_iters = amg_pcg_solve(k.y.p, k.g.p, k.tol, k.maxit);
-    k.iters_on_device = false;
+    if (amg_coop_enabled() && !amg_dev().L.empty()) {
+        amg_pcg_solve_coop(k.y.p, k.g.p, k.tol, k.maxit, false);      // no host round trip inside h1mg_solve
+        k.last_iters = -1, k.iters_on_device = false;
+    } else {
+        k.last_iters = amg_pcg_solve(k.y.p, k.g.p, k.tol, k.maxit);
+        k.iters_on_device = false;
+    }
     crsd_mean_kernel<<<1, 1024, 0, s>>>(k.y.p, k.gmask.p, nc, k.null_space, k.ndof);
     NEKB_LAUNCHED();
     if (k.n > 0) {

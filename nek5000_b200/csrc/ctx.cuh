@@ -48,6 +48,12 @@ struct IpcMaps {
     }
 };
 
+// partner(a, b) = base + a * sa + b * sb for the node with in-face coordinates (a, b) (the two free local indices, lower axis first)
+struct FaceLink {
+    int32_t base;
+    int16_t sa, sb;
+};
+
 // Local gather-scatter map (gslib gs_setup result restated for the device).
 struct GsMap {
     bool used = false;
@@ -61,6 +67,18 @@ struct GsMap {
     int link_mode = 0;             // 0 not built, 1 every group through `link`, 2 pairs through `link` + goff3/gidx3
     DevBuf<int32_t> goff3, gidx3;  // CSR of the groups with three or more members (edges, corners), link_mode 2
     int64_t ngroups3 = 0;
+    // ---- structured gather view of the same map for the fused cggos update (gs.cuh gs_ensure_struct, lx1 = 8) ----------
+    // Face-interior nodes of a conforming hex mesh pair face to face by an affine index map, so a face needs 8 bytes
+    // (base, two strides) instead of a 4-byte partner per node; edge / corner nodes read the assembled value of their group
+    // from `gval` through an 80-entry table per element; everything else (groups with remote members, non-conforming
+    // leftovers) is assembled in place by the stock kernel on the (goffS, gidxS) subset.
+    int struct_state = 0;          // 0 not built, 1 built, -1 not available for this handle (vector is not nel * 8^3 nodes)
+    DevBuf<FaceLink> ftab;         // [nel][6]  faces -x,+x,-y,+y,-z,+z; base < 0: no gathered partner on that face
+    DevBuf<int32_t> etab;          // [nel][80] edge / corner node -> slot in gval, or -1 (own value is final)
+    DevBuf<int32_t> goffE, gidxE;  // CSR of the groups assembled into gval (all members are edge / corner nodes, no remote member)
+    DevBuf<int32_t> goffS, gidxS;  // CSR of the groups assembled in place
+    DevBuf<double> gval;           // [ngroupsE]
+    int64_t ngroupsE = 0, ngroupsS = 0;
     // ---- remote part (np > 1): ids shared with other ranks --------------------------------------
     int64_t nshared = 0;           // local unique ids that also live on another rank
     std::vector<int> peers;        // neighbour ranks, ascending
@@ -112,6 +130,10 @@ struct Ctx {
     int istep = 0;
     double volvm1 = 0.0, voltm1 = 0.0;
     int niterhm = 0;
+    // residual history of the most recent cggo / hmh_gmres / hmh_flex_cg solve, whoever called it (hmholtz_, hsolve_, ...):
+    // what the reference only prints (hmholtz.f:770-773, gmres.f:496-498); read back with nekb_last_history
+    std::vector<double> last_hist;
+    int last_hist_rows = 0, last_hist_cols = 0;
     double param[201] = {0};       // INPUT param(1:200) entries the path reads (18, 21, 22); 1-based
     double restol[32] = {0};       // TSTEP restol(0:ldimt1): per-field residual tolerance that overrules cggo's tin (hmholtz.f:676)
     DevBuf<double> binvm1, bintm1; // MASS binvm1 / bintm1 for hmholtz

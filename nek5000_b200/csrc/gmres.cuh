@@ -236,6 +236,8 @@ inline int hmh_gmres_run(double *res, const double *h1, const double *h2, const 
     bool conv = false;
     double div0 = 0.0, tolpss = tol, rnorm = 0.0;
     unsigned *counter = &c.sc.p->counter[0];
+    c.last_hist.assign((size_t)(maxit > 0 ? maxit : 0) + 1, 0.0);   // rnorm per iteration, for nekb_last_history
+    c.last_hist_rows = 0, c.last_hist_cols = 1;
     while (!conv) {
         if (iter == 0) {
             NEKB_CUDA(cudaMemcpyAsync(G.r.p, res, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s));  // :352
@@ -301,6 +303,7 @@ inline int hmh_gmres_run(double *res, const double *h1, const double *h2, const 
             gam[j] = cg[j] * gam[j];
             rnorm = fabs(gam[j + 1]) * norm_fac;
             if (hist_host) hist_host[iter - 1] = rnorm;
+            if ((int)c.last_hist.size() >= iter) c.last_hist[iter - 1] = rnorm, c.last_hist_rows = iter;
             if (iter + 1 > maxit || rnorm < tolpss) {  // :466-467
                 conv = true;
                 break;

@@ -304,6 +304,181 @@ __device__ __forceinline__ double gs_gathered(const double *__restrict__ u, doub
     return v;
 }
 
+// ---------------------------------------------------------------------------------------------- structured gather view
+// Node classes of an 8^3 tile by the number of local indices on the tile surface: 0 interior, 1 face-interior, >= 2 edge /
+// corner.  Slots of the edge / corner nodes in the per-element table: x-edges 0..23 (edge (j,k in {0,7}) * 6 + i-1), y-edges
+// 24..47, z-edges 48..71, corners 72..79.
+constexpr int GS_ST_NX = 8, GS_ST_N3 = 512, GS_ST_EDGE_SLOTS = 80;
+__host__ __device__ __forceinline__ int gs_st_nb(int i, int j, int k)
+{
+    return (i == 0 || i == 7) + (j == 0 || j == 7) + (k == 0 || k == 7);
+}
+__host__ __device__ __forceinline__ int gs_st_slot(int i, int j, int k)   // nb >= 2 only
+{
+    const int bi = (i == 0 || i == 7), bj = (j == 0 || j == 7), bk = (k == 0 || k == 7);
+    const int hi = i == 7, hj = j == 7, hk = k == 7;
+    if (bi + bj + bk == 3) return 72 + hi + 2 * hj + 4 * hk;
+    if (!bi) return (hj + 2 * hk) * 6 + (i - 1);
+    if (!bj) return 24 + (hi + 2 * hk) * 6 + (j - 1);
+    return 48 + (hi + 2 * hj) * 6 + (k - 1);
+}
+// nb == 1 only: face (0..5 = -x,+x,-y,+y,-z,+z) and the in-face coordinates (lower axis first)
+__host__ __device__ __forceinline__ int gs_st_face(int i, int j, int k, int &a, int &b)
+{
+    if (i == 0 || i == 7) {
+        a = j, b = k;
+        return i == 7;
+    }
+    if (j == 0 || j == 7) {
+        a = i, b = k;
+        return 2 + (j == 7);
+    }
+    a = i, b = j;
+    return 4 + (k == 7);
+}
+
+// Builds the structured view (host, set-up only).  Classification of a group of the local map:
+//   S  (assembled in place)   : a member is shared with another rank, or the group mixes node classes / is not a clean pair
+//   P  (gathered through ftab): exactly two face-interior members, and all 36 pairs of both faces follow one affine map
+//   E  (assembled into gval)  : every member is an edge / corner node
+inline bool gs_ensure_struct(GsMap &h)
+{
+    if (h.struct_state != 0) return h.struct_state > 0;
+    h.struct_state = -1;
+    if (h.n <= 0 || h.n % GS_ST_N3 != 0) return false;
+    Ctx &c = ctx();
+    cudaStream_t s = c.stream;
+    const int64_t nel = h.n / GS_ST_N3, ng = h.ngroups;
+    std::vector<int32_t> off((size_t)ng + 1, 0), idx((size_t)(h.nmembers > 0 ? h.nmembers : 1));
+    if (ng > 0) {
+        h.goff.download(off.data(), off.size(), s);
+        h.gidx.download(idx.data(), (size_t)h.nmembers, s);
+    }
+    std::vector<unsigned char> shared((size_t)h.n, 0);
+    if (h.nshared > 0 && h.nx_members > 0) {
+        std::vector<int32_t> xg((size_t)h.nx_members);
+        h.x_gidx.download(xg.data(), xg.size(), s);
+        for (int32_t q : xg) shared[q] = 1;
+    }
+    auto cls = [](int32_t node) {
+        const int q = node & (GS_ST_N3 - 1);
+        return gs_st_nb(q & 7, (q >> 3) & 7, q >> 6);
+    };
+    // pass 1: classify; partner[] of the candidate pairs
+    enum : unsigned char { GS_S = 0, GS_P = 1, GS_E = 2 };
+    std::vector<unsigned char> gclass((size_t)(ng > 0 ? ng : 1), GS_S);
+    std::vector<int32_t> partner((size_t)h.n, -1), gof((size_t)h.n, -1);
+    for (int64_t g = 0; g < ng; g++) {
+        const int b = off[g], e = off[g + 1];
+        bool sh = false, all_face = true, all_edge = true;
+        for (int q = b; q < e; q++) {
+            const int nb = cls(idx[q]);
+            sh = sh || shared[idx[q]];
+            all_face = all_face && nb == 1;
+            all_edge = all_edge && nb >= 2;
+            gof[idx[q]] = (int32_t)g;
+        }
+        if (sh) continue;
+        if (e - b == 2 && all_face) {
+            gclass[g] = GS_P;
+            partner[idx[b]] = idx[b + 1], partner[idx[b + 1]] = idx[b];
+        } else if (all_edge)
+            gclass[g] = GS_E;
+    }
+    // pass 2: affine fit per face; a face that is only partly paired or not affine sends its groups to S
+    std::vector<FaceLink> ftab((size_t)nel * 6);
+    auto node_of = [](int f, int a, int b) {   // local index of in-face (a, b) on face f
+        const int fixed = (f & 1) ? 7 : 0;
+        if (f < 2) return fixed + 8 * a + 64 * b;
+        if (f < 4) return a + 8 * fixed + 64 * b;
+        return a + 8 * b + 64 * fixed;
+    };
+    for (int64_t el = 0; el < nel; el++)
+        for (int f = 0; f < 6; f++) {
+            FaceLink L{-1, 0, 0};
+            const int32_t base_node = (int32_t)(el * GS_ST_N3);
+            int npair = 0;
+            for (int b = 1; b <= 6; b++)
+                for (int a = 1; a <= 6; a++) npair += partner[base_node + node_of(f, a, b)] >= 0;
+            bool ok = npair == 36;
+            if (ok) {
+                const int64_t p11 = partner[base_node + node_of(f, 1, 1)], p21 = partner[base_node + node_of(f, 2, 1)],
+                              p12 = partner[base_node + node_of(f, 1, 2)];
+                const int64_t sa = p21 - p11, sb = p12 - p11, base = p11 - sa - sb;
+                ok = sa >= -32768 && sa <= 32767 && sb >= -32768 && sb <= 32767 && base >= 0 && base <= 2147483647;
+                for (int b = 1; b <= 6 && ok; b++)
+                    for (int a = 1; a <= 6 && ok; a++) ok = partner[base_node + node_of(f, a, b)] == base + a * sa + b * sb;
+                if (ok) L = FaceLink{(int32_t)base, (int16_t)sa, (int16_t)sb};
+            }
+            if (!ok && npair > 0)
+                for (int b = 1; b <= 6; b++)
+                    for (int a = 1; a <= 6; a++) {
+                        const int32_t nd = base_node + node_of(f, a, b);
+                        if (partner[nd] >= 0) gclass[gof[nd]] = GS_S;
+                    }
+            ftab[(size_t)el * 6 + f] = L;
+        }
+    // a demoted group takes the face(s) of its other member down with it: sweep until every linked face has all 36 of its
+    // groups in P (one sweep on a conforming mesh)
+    for (bool changed = true; changed;) {
+        changed = false;
+        for (int64_t el = 0; el < nel; el++)
+            for (int f = 0; f < 6; f++) {
+                FaceLink &L = ftab[(size_t)el * 6 + f];
+                if (L.base < 0) continue;
+                bool ok = true;
+                for (int b = 1; b <= 6 && ok; b++)
+                    for (int a = 1; a <= 6 && ok; a++) ok = gclass[gof[(int32_t)(el * GS_ST_N3) + node_of(f, a, b)]] == GS_P;
+                if (ok) continue;
+                for (int b = 1; b <= 6; b++)
+                    for (int a = 1; a <= 6; a++) gclass[gof[(int32_t)(el * GS_ST_N3) + node_of(f, a, b)]] = GS_S;
+                L = FaceLink{-1, 0, 0};
+                changed = true;
+            }
+    }
+    // pass 3: the two CSR subsets and the edge table
+    std::vector<int32_t> offE(1, 0), idxE, offS(1, 0), idxS, etab((size_t)nel * GS_ST_EDGE_SLOTS, -1);
+    for (int64_t g = 0; g < ng; g++) {
+        const int b = off[g], e = off[g + 1];
+        if (gclass[g] == GS_E) {
+            const int32_t slot = (int32_t)offE.size() - 1;
+            for (int q = b; q < e; q++) {
+                const int nd = idx[q], l = nd & (GS_ST_N3 - 1);
+                etab[(size_t)(nd >> 9) * GS_ST_EDGE_SLOTS + gs_st_slot(l & 7, (l >> 3) & 7, l >> 6)] = slot;
+                idxE.push_back(nd);
+            }
+            offE.push_back((int32_t)idxE.size());
+        } else if (gclass[g] == GS_S) {
+            idxS.insert(idxS.end(), idx.begin() + b, idx.begin() + e);
+            offS.push_back((int32_t)idxS.size());
+        }
+    }
+    h.ngroupsE = (int64_t)offE.size() - 1, h.ngroupsS = (int64_t)offS.size() - 1;
+    if (idxE.empty()) idxE.push_back(0);
+    if (idxS.empty()) idxS.push_back(0);
+    h.ftab.upload(ftab.data(), ftab.size(), s);
+    h.etab.upload(etab.data(), etab.size(), s);
+    h.goffE.upload(offE.data(), offE.size(), s), h.gidxE.upload(idxE.data(), idxE.size(), s);
+    h.goffS.upload(offS.data(), offS.size(), s), h.gidxS.upload(idxS.data(), idxS.size(), s);
+    h.gval.alloc((size_t)(h.ngroupsE > 0 ? h.ngroupsE : 1));
+    NEKB_CUDA(cudaStreamSynchronize(s));
+    h.struct_state = 1;
+    return true;
+}
+
+// gval[g] = combined value of group g of the E subset (members in ascending order: the bits gs_local_kernel would write)
+__global__ void __launch_bounds__(256)
+    gs_gval_kernel(double *__restrict__ gval, const double *__restrict__ u, const int32_t *__restrict__ goff,
+                   const int32_t *__restrict__ gidx, int ngroups)
+{
+    for (int gI = blockIdx.x * blockDim.x + threadIdx.x; gI < ngroups; gI += gridDim.x * blockDim.x) {
+        const int b = goff[gI], e = goff[gI + 1];
+        double v = u[gidx[b]];
+        for (int q = b + 1; q < e; q++) v += u[gidx[q]];
+        gval[gI] = v;
+    }
+}
+
 // u <- gs_op(u) [* mask]
 inline void gs_op(int handle, double *u, int op, const double *mask)
 {

@@ -558,7 +558,19 @@ inline bool hcg_run(int nrhs, double *const *x, const double *const *f, const do
 
 // cggo with the fused path tried first (one right-hand side); falls back to the kernel-per-statement cggo_run for the
 // branches hcg does not provide (Schwarz preconditioner, null-space correction, lx1 != 8, non-binary masks).
+inline int cggo_solve_impl(const CggoArgs &a, double tin, int maxit, double *hist_host);
 inline int cggo_solve(const CggoArgs &a, double tin, int maxit, double *hist_host)
+{
+    // the history always lands in ctx().last_hist as well (3 doubles per executed check: rtz1, rbn2, rho)
+    Ctx &c = ctx();
+    const int niter = maxit < 900 ? maxit : 900;
+    c.last_hist.assign((size_t)3 * (niter + 2), 0.0);
+    const int it = cggo_solve_impl(a, tin, maxit, c.last_hist.data());
+    c.last_hist_rows = it + 1 <= niter + 1 ? it + 1 : niter + 1, c.last_hist_cols = 3;
+    if (hist_host) memcpy(hist_host, c.last_hist.data(), sizeof(double) * 3 * (size_t)c.last_hist_rows);
+    return it;
+}
+inline int cggo_solve_impl(const CggoArgs &a, double tin, int maxit, double *hist_host)
 {
     tin = cggo_tin(tin);  // restol(ifield), hmholtz.f:676
     if (hcg_applicable(1)) {

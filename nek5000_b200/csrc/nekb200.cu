@@ -407,6 +407,19 @@ int nekb_set_ifield(int ifield)
         ctx().ifield = ifield;
     });
 }
+int nekb_last_history(double *out, int64_t capacity, int *rows, int *cols)
+{
+    return guard([&] {
+        Ctx &c = ctx();
+        if (rows) *rows = c.last_hist_rows;
+        if (cols) *cols = c.last_hist_cols;
+        const int64_t want = (int64_t)c.last_hist_rows * c.last_hist_cols;
+        if (out) {
+            NEKB_REQUIRE(capacity >= want, "nekb_last_history: output buffer too small");
+            memcpy(out, c.last_hist.data(), sizeof(double) * (size_t)want);
+        }
+    });
+}
 int nekb_set_restol(int ifield, double restol)
 {
     return guard([&] {
@@ -1104,6 +1117,10 @@ int nekb_h1mg_info(int *lmax, int *nh3, int *ntab3, int *crs_iters)
                 NEKB_CUDA(cudaMemcpyAsync(&hs, crs_scalars().p, sizeof(CrsScalars), cudaMemcpyDeviceToHost, ctx().stream));
                 NEKB_CUDA(cudaStreamSynchronize(ctx().stream));
                 M.crs.last_iters = hs.it;
+            }
+            if (M.crs.last_iters < 0 && amg_dev().iters.p) {   // the one-launch aggregation-hierarchy CG keeps its count on the device
+                NEKB_CUDA(cudaMemcpyAsync(&M.crs.last_iters, amg_dev().iters.p, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+                NEKB_CUDA(cudaStreamSynchronize(ctx().stream));
             }
             *crs_iters = M.crs.last_iters;
         }
@@ -2056,7 +2073,8 @@ int nekb_crs_amg_solve_dev(double *x_dev, const double *b_dev, double tol, int m
 {
     return guard([&] {
         require_init();
-        const int it = amg_pcg_solve(x_dev, b_dev, tol, maxit);
+        const int it = (amg_coop_enabled() && !amg_dev().L.empty()) ? amg_pcg_solve_coop(x_dev, b_dev, tol, maxit, true)
+                                                                      : amg_pcg_solve(x_dev, b_dev, tol, maxit);
         if (iters) *iters = it;
     });
 }

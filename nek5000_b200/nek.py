@@ -126,6 +126,17 @@ def set_field_handle(ifield: int, gs_handle: int) -> None:
     check(lib().nekb_set_field_handle(ifield, gs_handle))
 
 
+def last_history() -> np.ndarray:
+    """History of the most recent cggo solve, shape (checks, 3): rtz1, rbn2, rho; or of the most recent hmh_gmres /
+    hmh_flex_cg solve, shape (iterations, 1): rnorm."""
+    rows, cols = C.c_int(0), C.c_int(0)
+    check(lib().nekb_last_history(None, 0, C.byref(rows), C.byref(cols)))
+    out = np.zeros((rows.value, max(cols.value, 1)))
+    if out.size:
+        check(lib().nekb_last_history(out.ctypes.data, out.size, C.byref(rows), C.byref(cols)))
+    return out
+
+
 def set_restol(ifield: int, restol: float) -> None:
     """TSTEP restol(ifield): overrules cggo's tolerance when non-zero (core/hmholtz.f:676)."""
     check(lib().nekb_set_restol(ifield, restol))

@@ -1474,7 +1474,8 @@ class Unit:
            re.match(r"^(open|close|rewind|backspace|endfile|inquire|flush)\s*\(", low) or re.match(r"^format\s*\(", low):
             if low.startswith("read"):
                 return ['f77_unsupported("read statement");']
-            return ["/* i/o dropped */;"]
+            tr = self.trace_write(txt, low)
+            return [tr] if tr else ["/* i/o dropped */;"]
         m = re.match(r"^call\s+([a-z_$][\w$]*)\s*(\(.*\))?\s*$", txt, re.I)
         if m:
             name = m.group(1).lower()
@@ -1500,6 +1501,48 @@ class Unit:
             self.stfuncs[lhs[1]] = ([a[1] for a in lhs[2]], rhs)
             return [f"/* statement function {lhs[1]} */;"]
         return [self.gen_assign(lhs, rhs)]
+
+    def trace_write(self, txt, low):
+        """write(6,...) / write(*,...) in a routine named in Translator.trace_units: instead of being dropped, the NUMERIC scalar
+        items of the output list are handed to f77_trace(unit, n, values...) (oracle/ref_stubs.c keeps them in a ring buffer
+        when tracing is switched on).  This is how the tests read what the reference LOGS -- e.g. cggo's per-iteration residual
+        (core/hmholtz.f:770-773), which it keeps in no COMMON variable.  Strings, implied-do lists and anything that does not
+        parse are skipped; the arithmetic of the routine is untouched."""
+        if self.name not in getattr(self.tr, "trace_units", ()) or not low.startswith("write"):
+            return None
+        i = low.index("(")
+        j = match_paren(txt, i)
+        if j < 0:
+            return None
+        ctl = re.sub(r"\s+", "", low[i + 1:j])
+        if not (ctl.startswith("6,") or ctl.startswith("*,") or ctl in ("6", "*")):
+            return None
+        rest = txt[j + 1:].strip()
+        if not rest:
+            return None
+        try:
+            p = Parser(tokenize("(" + rest + ")"), "")
+            p.expect("op", "(")
+            items = p.arglist()
+            if not p.done():
+                return None
+            vals = []
+            for e in items:
+                if e[0] in ("range", "star"):
+                    return None
+                t = self.typeof(e)
+                if t == "ch":
+                    continue
+                if e[0] == "app" and not self.is_arrayref(e) and e[1] not in self.stfuncs and e[1] not in INTRINSICS:
+                    return None                     # a function call in an output list: leave it alone
+                if e[0] == "name" and self.sym(e[1]).is_array:
+                    return None                     # whole-array output
+                vals.append(f"(double)({self.cx(e)})")
+            if not vals or len(vals) > 12:
+                return None
+            return f'if (f77_trace_on) f77_trace("{self.name}", {len(vals)}, {", ".join(vals)});'
+        except (TranslationError, SyntaxError, KeyError, IndexError):
+            return None
 
     def has_top_comma(self, s):
         depth, q = 0, None
@@ -1726,6 +1769,8 @@ static int f77_index(const char *a, long la, const char *b, long lb) {
 }
 static void f77_unsupported(const char *what) { fprintf(stderr, "f77c: unsupported construct executed: %s\n", what); abort(); }
 static void f77_stop(void) { fprintf(stderr, "f77c: STOP\n"); exit(1); }
+extern int f77_trace_on;                                       /* oracle/ref_stubs.c */
+extern void f77_trace(const char *unit, int n, ...);
 """
 
 
@@ -1741,6 +1786,7 @@ class Translator:
         self.defined = {}
         self.known_units = set()
         self.failed = {}
+        self.trace_units = set()  # routines whose write(6,...) statements report their numeric items to f77_trace
 
     def add_file(self, path, only=None, skip=()):
         for u in split_units(self.reader.read(path)):

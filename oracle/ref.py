@@ -29,10 +29,14 @@ def available(lx1=8, lx2=None, lelt=64) -> bool:
 class Ref:
     _cache = {}
 
-    def __new__(cls, lx1=8, lx2=None, lelt=64, lgmres=30, fresh=False):
+    def __new__(cls, lx1=8, lx2=None, lelt=64, lgmres=30, fresh=False, hybrid=False):
         """fresh=True loads a private copy of the library: the reference keeps state in SAVE variables (icalld counters,
         hmh_gmres' norm_fac, ...) and in the stand-ins' handle tables, which must not leak from one test case to the next."""
         key = (lx1, lx2 or lx1, lelt, lgmres)
+        if hybrid:        # the drop-in variant (ref_build.HYB_STOP routines come from libnekb200.so): always a private copy
+            self = super().__new__(cls)
+            self._init(*key, fresh=True, hybrid=True)
+            return self
         if fresh:
             self = super().__new__(cls)
             self._init(*key, fresh=True)
@@ -43,8 +47,14 @@ class Ref:
             cls._cache[key] = self
         return cls._cache[key]
 
-    def _init(self, lx1, lx2, lelt, lgmres, fresh=False):
-        so = ref_build.build(lx1, lx2, lelt, lgmres)
+    def _init(self, lx1, lx2, lelt, lgmres, fresh=False, hybrid=False):
+        so = ref_build.build(lx1, lx2, lelt, lgmres, hybrid=hybrid)
+        self.hybrid = hybrid
+        if hybrid:
+            # libnekb200.so first, globally (it carries the soname the hybrid's DT_NEEDED entry asks for, so the private copy
+            # made below binds to this very instance)
+            from nek5000_b200 import lib as _product
+            _product()
         self.meta = json.load(open(so.replace("libnekref_", "nekref_").replace(".so", ".json")))
         if fresh:
             import shutil
@@ -92,6 +102,22 @@ class Ref:
         v = self.var(name)
         return v[0] if v.shape == (1,) and not self.meta["commons"][name.lower()]["dims"] else v
 
+    # ---- what the reference logs (write(6,...) in the routines of ref_build.TRACE_UNITS) -----------------------------------
+    def trace(self, on=True):
+        """Starts (and clears) or stops the recording of the numeric items of the traced routines' write(6,...) statements."""
+        self.lib.nekref_trace_enable(1 if on else 0)
+
+    def trace_records(self, unit=None, nvals=None):
+        """[(unit, values)] recorded since trace(True); optionally only those of routine `unit` with `nvals` numeric items."""
+        out = []
+        name, vals = C.create_string_buffer(24), (C.c_double * 12)()
+        for i in range(self.lib.nekref_trace_count()):
+            n = self.lib.nekref_trace_get(i, name, vals)
+            u = name.value.decode()
+            if (unit is None or u == unit) and (nvals is None or n == nvals):
+                out.append((u, np.array(vals[:n])))
+        return out
+
     # ---- calls ----------------------------------------------------------------------------------------------------------
     def call(self, name, *args, restype=None):
         """Calls `name_` Fortran-style.  numpy arrays pass their buffer, ints/floats/bools pass a temporary by reference
@@ -133,10 +159,13 @@ class RefCase:
     initds/dsset/setedge + setupds + multiplicity (connect1.f:43-135), genwz, geom1/geom2/volume/setinvm/setdef
     (gengeom, core/coef.f / drive2.f), bcmask."""
 
-    def __init__(self, case, lelt=None, lx2=None, ifsplit=True, nfield=1, fresh=True, lgmres=30):
+    def __init__(self, case, lelt=None, lx2=None, ifsplit=True, nfield=1, fresh=True, lgmres=30, hybrid=False, device=0):
+        """hybrid=True: the drop-in variant -- the same set-up sequence, with the glue calls of INTEGRATION.md
+        (oracle/hyb_glue.c) where a Nek5000 build would make them: nekb_init before the first gs_setup, the field handle
+        after setupds, the registration of COMMON state after the geometry is complete."""
         nx, E = case.nx, case.nel
         lelt = lelt or max(64, E)
-        R = self.R = Ref(nx, lx2 or nx, lelt, lgmres, fresh=fresh)
+        R = self.R = Ref(nx, lx2 or nx, lelt, lgmres, fresh=fresh, hybrid=hybrid)
         self.case, self.E, self.nx = case, E, nx
         R.call("initdim")
         R.call("initdat")
@@ -174,8 +203,12 @@ class RefCase:
         for n, a in (("xm1", case.xm1), ("ym1", case.ym1), ("zm1", case.zm1)):
             R.var(n)[..., :E] = a.reshape(sh, order="F")
         # numbering + gs handle + multiplicity (connect1.f:81-135)
+        if hybrid:
+            R.call("nekhyb_init", device)
         R.call("setupds", R.var("gsh_fld")[1:2], nx, nx, nx, E, E, R.var("vertex"), R.var("glo_num"))
         R.var("gsh_fld")[2] = R.var("gsh_fld")[1]
+        if hybrid:
+            R.call("nekhyb_set_field")
         n = nx ** 3 * E
         R.call("rone", R.var("vmult"), n)
         R.call("dssum", R.var("vmult"), nx, nx, nx)
@@ -189,6 +222,8 @@ class RefCase:
         R.call("sfastax")
         R.call("bcmask")
         R.set("ifield", 1)
+        if hybrid:
+            R.call("nekhyb_register")
 
     def fld(self, name):
         """Flat copy (Nek memory order) of the first E elements of a field in COMMON."""

@@ -53,6 +53,40 @@ mfo_open_files mfi fgslib_gs_unique plan4 plan3 fluid heat cvode_solve readat re
 full_restart_save restart hpts prepost lastep drgtrq""".split()
 
 
+# routines whose write(6,...) statements report their numeric items through f77_trace (oracle/f77c.py trace_write):
+# the residual histories the reference only logs
+TRACE_UNITS = """cggo hmh_gmres hmh_flex_cg uzawa_gmres""".split()
+
+
+# ---- the DROP-IN variant ("hyb"): the reference's own callers on top of libnekb200.so ------------------------------------
+# The routines below are NOT translated; the library is linked against nek5000_b200/libnekb200.so, so the transpiled
+# reference's calls to them (Fortran convention: by reference, hidden CHARACTER lengths) land in the CUDA entry points --
+# what a Nek5000 build gets when libnekb200.so precedes libnek5000.a on the link line (INTEGRATION.md).  The gslib and crs
+# stand-ins of ref_stubs.c are compiled out as well (fgslib_gs_* / crs_* come from the product), and oracle/hyb_glue.c
+# plays the Fortran glue of INTEGRATION.md: it registers the COMMON state (located through a generated header of COMMON
+# offsets, the "SIZE -> header generator" of SURVEY 8b) and overrides h1mg_setup.
+HYB_STOP = """axhelm dssum dsop cggo cggos axhm1 h1mg_solve h1mg_setup""".split()
+HYB_ROOTS = """get_fast_bc get_vert set_overlap""".split()
+# COMMON variables the glue reads
+HYB_VARS = """nelv nelt nelgv zgm1 wxm1 dxm1 dxtm1 g1m1 g2m1 g3m1 g4m1 g5m1 g6m1 bm1 binvm1 bintm1 ifdfrm istep volvm1 voltm1
+ifield gsh_fld param v1mask v2mask v3mask vmult pmask tolps ifvcor xm1 ym1 zm1 vertex niterhm""".split()
+
+
+def hyb_header(meta, lx1):
+    """C view of the COMMON variables in HYB_VARS: extern storage of the block + a typed pointer macro per variable."""
+    ct = {"r8": "double", "i4": "int", "l4": "int", "i8": "long long"}
+    blocks, lines = set(), []
+    for v in HYB_VARS:
+        m = meta["commons"][v]
+        blocks.add(m["block"])
+        lines.append(f"#define V_{v} (({ct[m['type']]} *)(cb_{m['block']} + {m['offset']}))")
+    lo = meta["commons"]["gsh_fld"]["lows"][0]
+    head = ["/* generated by oracle/ref_build.py from the same SIZE the reference was translated with */",
+            f"#define NEKHYB_LX1 {lx1}", f"#define NEKHYB_LELT {meta['lelt']}", f"#define NEKHYB_GSH_FLD_LOW {lo}"]
+    head += [f"extern char cb_{b}[];" for b in sorted(blocks)]
+    return "\n".join(head + lines) + "\n"
+
+
 def size_text(lx1, lx2, lelt, lgmres, ldimt=1):
     lxd = (3 * lx1 + 1) // 2
     return f"""c     generated by oracle/ref_build.py (keys of core/SIZE.template)
@@ -89,12 +123,13 @@ def size_text(lx1, lx2, lelt, lgmres, ldimt=1):
 """
 
 
-def build(lx1=8, lx2=None, lelt=64, lgmres=30, tag=None, force=False, verbose=False):
+def build(lx1=8, lx2=None, lelt=64, lgmres=30, tag=None, force=False, verbose=False, hybrid=False):
     import f77c
     lx2 = lx1 if lx2 is None else lx2
-    tag = tag or f"lx{lx1}" + ("" if lx2 == lx1 else f"p{lx2}") + f"e{lelt}" + ("" if lgmres == 30 else f"g{lgmres}")
+    tag = tag or f"lx{lx1}" + ("" if lx2 == lx1 else f"p{lx2}") + f"e{lelt}" + ("" if lgmres == 30 else f"g{lgmres}") + \
+        ("hyb" if hybrid else "")
     so = os.path.join(OUT, f"libnekref_{tag}.so")
-    deps = [os.path.join(HERE, f) for f in ("f77c.py", "ref_build.py", "ref_stubs.c")]
+    deps = [os.path.join(HERE, f) for f in ("f77c.py", "ref_build.py", "ref_stubs.c") + (("hyb_glue.c",) if hybrid else ())]
     if os.path.exists(so) and not force and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in deps):
         return so
     if not os.path.isdir(os.path.join(REF, "core")):
@@ -107,13 +142,15 @@ def build(lx1=8, lx2=None, lelt=64, lgmres=30, tag=None, force=False, verbose=Fa
         f.write(size_text(lx1, lx2, lelt, lgmres))
     tr = f77c.Translator(REF, [inc, os.path.join(REF, "core")],
                          {"PARALLEL": "PARALLEL.default", "mpif.h": "mpi_dummy.h"}, defines=["UNDERSCORE"])
+    tr.trace_units = set(TRACE_UNITS)
+    stop = STOP + (HYB_STOP if hybrid else [])
     for fn in CORE_FILES:
-        tr.add_file(os.path.join(REF, "core", fn), skip=STOP)
-    tr.add_file(os.path.join(REF, "examples", "bp5", "bp5.usr"), skip=STOP)
+        tr.add_file(os.path.join(REF, "core", fn), skip=stop)
+    tr.add_file(os.path.join(REF, "examples", "bp5", "bp5.usr"), skip=stop)
     for fn in sorted(glob.glob(os.path.join(REF, "3rd_party", "blasLapack", "*.f"))):
         tr.add_file(fn)
-    roots = [r for r in ROOTS if r in tr.units]
-    code, missing = tr.translate(roots, stop_at=set(STOP))
+    roots = [r for r in ROOTS + (HYB_ROOTS if hybrid else []) if r in tr.units]
+    code, missing = tr.translate(roots, stop_at=set(stop))
     csrc = os.path.join(OUT, f"nekref_{tag}.c")
     with open(csrc, "w") as f:
         f.write(code)
@@ -129,6 +166,14 @@ def build(lx1=8, lx2=None, lelt=64, lgmres=30, tag=None, force=False, verbose=Fa
     # product exports for the drop-in) must bind inside the library even when libnekb200.so is loaded in the same process
     cmd = [cc, "-O2", "-ffp-contract=off", "-w", "-fPIC", *big, "-shared", "-Wl,-Bsymbolic", "-o", so, csrc,
            os.path.join(HERE, "ref_stubs.c"), "-lm"]
+    if hybrid:
+        # -Bsymbolic stays: the routines this library DEFINES (hmholtz_, hmh_gmres_, bp5_, glsc3_, ...) keep calling each
+        # other, so exactly the HYB_STOP routines (undefined here) and the gslib / crs API resolve to libnekb200.so.
+        with open(os.path.join(inc, "nekhyb_commons.h"), "w") as f:
+            f.write(hyb_header(meta, lx1))
+        prod = os.path.normpath(os.path.join(HERE, "..", "nek5000_b200"))
+        cmd = cmd[:-1] + ["-DNEKHYB", os.path.join(HERE, "hyb_glue.c"), "-I", inc, "-I", os.path.join(HERE, "..", "include"),
+                          "-L", prod, "-lnekb200", "-Wl,-rpath,$ORIGIN/../../nek5000_b200", "-Wl,--no-undefined", "-lm"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("gcc failed on the transpiled reference:\n" + r.stderr[-4000:])
@@ -146,5 +191,6 @@ if __name__ == "__main__":
     ap.add_argument("--lgmres", type=int, default=30)
     ap.add_argument("--tag", default=None)
     ap.add_argument("--force", action="store_true")
+    ap.add_argument("--hybrid", action="store_true", help="the drop-in variant: reference callers on top of libnekb200.so")
     a = ap.parse_args()
-    print(build(a.lx1, a.lx2, a.lelt, a.lgmres, a.tag, a.force, verbose=True))
+    print(build(a.lx1, a.lx2, a.lelt, a.lgmres, a.tag, a.force, verbose=True, hybrid=a.hybrid))

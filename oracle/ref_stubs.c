@@ -19,6 +19,7 @@
 
 typedef long long i64;
 
+#ifndef NEKHYB   /* the drop-in variant takes gslib's and crs' Fortran API from libnekb200.so */
 /* ---------------------------------------------------------------- gather-scatter ---------------------------------- */
 typedef struct {
   int n;        /* length of the id vector */
@@ -210,6 +211,12 @@ void crs_solve_(const int *handle, double *x, const double *b)
 void crs_free_(const int *handle) {}
 
 /* ---------------------------------------------------------------- system / hooks ---------------------------------- */
+#else
+void fgslib_crystal_ituple_transfer_() {}
+void fgslib_crystal_tuple_transfer_() {}
+void fgslib_crystal_setup_(int *h) { *h = 0; }
+void fgslib_crystal_free_() {}
+#endif
 double etime_(float *t) { return 0.0; }
 #include <time.h>
 double dnekclock_(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec; }
@@ -240,3 +247,36 @@ void nekgsync_() {}
 DEAD(byte_open_) DEAD(byte_close_) DEAD(byte_write_) DEAD(byte_read_) DEAD(mpi_file_open_) DEAD(mpi_file_close_)
 DEAD(mpi_file_set_view_) DEAD(mpi_file_write_all_) DEAD(fem_amg_solve_) DEAD(fem_amg_setup_) DEAD(outpost_)
 DEAD(outpost2_) DEAD(fgslib_gs_unique_)
+
+/* ---------------------------------------------------------------- write(6,...) trace (oracle/f77c.py trace_write) ------------- */
+/* The reference logs some quantities and keeps them nowhere else (cggo's residual per iteration, core/hmholtz.f:770-773).
+ * In routines named in ref_build.TRACE_UNITS the translator turns write(6,...) into f77_trace(unit, n, numeric items...);
+ * records are kept here while tracing is on and read back by oracle/ref.py (Ref.trace). */
+#include <stdarg.h>
+int f77_trace_on = 0;
+#define TRACE_MAX 65536
+#define TRACE_VALS 12
+typedef struct { char unit[24]; int n; double v[TRACE_VALS]; } trace_rec_t;
+static trace_rec_t *trace_buf = 0;
+static int trace_n = 0;
+void f77_trace(const char *unit, int n, ...)
+{
+  if (!trace_buf) trace_buf = (trace_rec_t *)calloc(TRACE_MAX, sizeof(trace_rec_t));
+  if (trace_n >= TRACE_MAX || !trace_buf) return;
+  trace_rec_t *r = &trace_buf[trace_n++];
+  strncpy(r->unit, unit, sizeof r->unit - 1);
+  r->n = n > TRACE_VALS ? TRACE_VALS : n;
+  va_list ap;
+  va_start(ap, n);
+  for (int i = 0; i < r->n; i++) r->v[i] = va_arg(ap, double);
+  va_end(ap);
+}
+void nekref_trace_enable(int on) { f77_trace_on = on; trace_n = 0; }
+int nekref_trace_count(void) { return trace_n; }
+int nekref_trace_get(int i, char *unit24, double *vals12)
+{
+  if (i < 0 || i >= trace_n) return -1;
+  memcpy(unit24, trace_buf[i].unit, 24);
+  memcpy(vals12, trace_buf[i].v, sizeof(double) * TRACE_VALS);
+  return trace_buf[i].n;
+}

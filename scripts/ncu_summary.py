@@ -15,6 +15,7 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed.sum", "lts__t_sector_hit_rate.pct",
+        "l1tex__t_sector_hit_rate.pct", "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sectors_srcunit_tex_op_write.sum",
         "sm__cycles_elapsed.max"]
 
 
@@ -50,7 +51,10 @@ def main():
                     f"{', '.join(sorted({short(r[ki]) for r in data[:last]} - set(agg)))}", ""]
     traffic = {}
     for rep in reps:
-        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        if rep.endswith(".csv"):      # `ncu -i x.ncu-rep --page raw --csv > x.raw.csv` done on the GPU box (reports are 15 MB each)
+            txt = open(rep).read()
+        else:
+            txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(txt.splitlines()))
         hdr, units = rows[0], rows[1]
         out += [f"## `ncu --set full --clock-control none` : {os.path.basename(rep)}", ""]

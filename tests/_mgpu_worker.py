@@ -108,6 +108,21 @@ def main():
             d = rel(outs[k].to_host(), xo[take])
             worst = max(worst, d) if tol < 0 else worst
             assert d <= ftol, ("ophinv solution", k, d)
+    # ---- a user handle in which one rank shares NOTHING while the others do (gs_p2p_setup made a different number
+    # of collective calls on such a rank).  Ranks 0..world-2 share ids 1..32, the last rank holds ids of its own; two
+    # handles and two exchanges back to back so that a mismatched collective would pair up wrongly and hang / corrupt.
+    if world >= 3:
+        for rep in range(2):
+            q = np.arange(32, dtype=np.int64)
+            ids = np.concatenate([1 + q if rank < world - 1 else 10_000 + 100 * rank + q, 5_000_000 + 1000 * rank + q])
+            hu = nek.fgslib_gs_setup(ids)
+            v = np.full(64, float(rank + 1))
+            nek.fgslib_gs_op(hu, v, 1, 1, 0)
+            want = np.full(64, float(rank + 1))
+            if rank < world - 1:
+                want[:32] = sum(range(1, world))
+            assert np.array_equal(v, want), ("asymmetric gs handle", rank, v[:4], want[:4])
+            nek.fgslib_gs_free(hu)
     print(f"MGPU-OK rank {rank} of {world}: its={it} rel(u)={rel(u, uref[take]):.2e} ophinv its={itv.tolist()} rel={worst:.1e} gs-exchange-mode={mode}", flush=True)
     dist.barrier()
     dist.destroy_process_group()

@@ -46,6 +46,94 @@ def _ref(case, **kw):
     return RefCase(case, **kw)
 
 
+class _Logged:
+    """Runs reference calls with the reference's own per-iteration log lines switched on (nio = 0, ifprint, param(74); the
+    values are captured by oracle/ref_stubs.c f77_trace instead of being printed) and returns what was logged:
+    cggo (core/hmholtz.f:770-773): istep, iter, rbn2, h1(1), tol, h2(1), ifmcor per executed check;
+    hmh_gmres (core/gmres.f:496-498): iter, tolpss, rnorm, div0, ratio, istep per iteration."""
+
+    def __init__(self, R):
+        self.R = R
+
+    def __enter__(self):
+        R = self.R
+        self.saved = (int(R.get("nio")), int(R.get("ifprint")), float(R.var("param")[73]))
+        R.set("nio", 0), R.set("ifprint", 1)
+        R.var("param")[73] = 1.0
+        R.trace(True)
+        return self
+
+    def __exit__(self, *exc):
+        R = self.R
+        self.records = R.trace_records()
+        R.trace(False)
+        R.set("nio", self.saved[0]), R.set("ifprint", self.saved[1])
+        R.var("param")[73] = self.saved[2]
+
+    def cggo(self):
+        """(rbn2 per check, tol) of the cggo calls logged, one pair per call (a call starts at iter = 1)."""
+        calls = []
+        for u, v in self.records:
+            if u == "cggo" and len(v) == 7:
+                if int(v[1]) == 1:
+                    calls.append(([], v[4]))
+                calls[-1][0].append(v[2])
+                calls[-1] = (calls[-1][0], v[4])
+        return [(np.array(h), float(t)) for h, t in calls]
+
+    def gmres(self):
+        calls = []
+        for u, v in self.records:
+            if u == "hmh_gmres" and len(v) == 6:
+                if int(v[0]) == 1:
+                    calls.append(([], v[1]))
+                calls[-1][0].append(v[2])
+        return [(np.array(h), float(t)) for h, t in calls]
+
+
+def ulp_perturbed(a, seed=99):
+    """`a` with every entry moved by one unit of rounding (relative 2^-52, random sign): the smallest change of the input a
+    floating-point computation can see.  The reference run on such an input shows how far the reference's OWN iterates move
+    under rounding-level changes -- the yardstick for an iteration count that differs by one (tests: count_or_margin)."""
+    sgn = np.where(np.random.default_rng(seed).random(a.shape) < 0.5, -1.0, 1.0)
+    return a * (1.0 + 2.0 ** -52 * sgn)
+
+
+def count_or_margin(it, it_ref, res, res_ref, tol, res_ref_pert=None, slack=1000.0, cap=1e-6, what="", gmres=False):
+    """The north star asks for IDENTICAL iteration counts.  This passes when they are.  When they differ, it passes only for a
+    difference of one that is a proven rounding-margin event, and it says so in the assertion text otherwise:
+
+      * k = min(it, it_ref) is the exit check that went the other way (cggo: check k+1 leaves with niterhm = k,
+        core/hmholtz.f:778-779; gmres = True: the test after iteration k, core/gmres.f:502, i.e. entry k-1 of the histories);
+        `res` / `res_ref` are the residual norms that check compares with `tol` (what the reference logs per iteration,
+        core/hmholtz.f:770-773, core/gmres.f:496-498);
+      * with `res_ref_pert` (the reference run again on an input moved by ONE unit of rounding): the distance of the
+        reference's residual from tol at check k must be within `slack` x what the reference's own history moved under that
+        perturbation (envelope up to k) -- i.e. the reference itself flips under rounding-level changes of this size -- and
+        the device history must stay within `slack` x that envelope of the reference's at every earlier check;
+      * without it: the device history must agree with the reference's to `cap` (relative) at every check up to k, which
+        bounds the distance of the reference's residual from tol by the same number (the two residuals straddle tol)."""
+    if it == it_ref:
+        return
+    assert abs(it - it_ref) == 1, f"{what}: iteration count {it} vs the reference's {it_ref}"
+    k = min(it, it_ref) - (1 if gmres else 0)
+    assert len(res) > k and len(res_ref) > k, f"{what}: histories too short ({len(res)}, {len(res_ref)}) for check {k}"
+    rel = np.abs(np.asarray(res[:k + 1]) - res_ref[:k + 1]) / res_ref[:k + 1]
+    margin = abs(res_ref[k] - tol) / tol
+    assert (res[k] <= tol) != (res_ref[k] <= tol), f"{what}: counts {it}/{it_ref} differ but check {k} agrees: {res[k]}, {res_ref[k]}, tol {tol}"
+    if res_ref_pert is not None:
+        m = min(len(res_ref_pert), k + 1)
+        env = np.maximum.accumulate(np.abs(res_ref[:m] - res_ref_pert[:m]) / res_ref[:m])
+        env = np.concatenate([env, np.full(k + 1 - m, env[-1])])
+        assert margin <= slack * env[k], (f"{what}: count {it} vs {it_ref}: the reference's residual is {margin:.2e} (relative) away from "
+                                          f"tol at check {k}, its own rounding sensitivity there is {env[k]:.2e}")
+        bad = rel > slack * np.maximum(env, 1e-15)
+        assert not bad.any(), f"{what}: history departs from the reference's beyond its rounding sensitivity at checks {np.flatnonzero(bad)[:5]}: {rel[bad][:5]} vs {env[bad][:5]}"
+    else:
+        assert rel.max() <= cap, f"{what}: count {it} vs {it_ref} and the residual histories differ by {rel.max():.2e} > {cap:.0e}"
+        assert margin <= rel[k] * (1 + 1e-12)
+
+
 # --------------------------------------------------------------------------------------------------- reference runs
 def ref_core(nx=8):
     """setupds/setvert3d (navier8.f:2004-2360), geom1/geom2/setinvm (coef.f:555-784), bcmask (bdry.f:317+), axhelm
@@ -343,6 +431,15 @@ def ref_fdm():
         R.set("ifsolv", 0), R.set("istep", 1), R.set("kfldfdm", 1)
         R.call("cggo", x, f.copy(), h1, h2, case.mask, case.mult, 1, tin, maxit, 1, rc.fld("binvm1"), "VELX")
         out[key + "_x"], out[key + "_it"] = x, np.array([R.get("niterhm")])
+    # the converged solve once more with the reference's log captured, and on a right-hand side perturbed by one unit of
+    # rounding: the Schwarz-preconditioned CG amplifies such changes, and the second history says by how much
+    for key, rhs in (("cg_rbn2", f), ("cg_rbn2_pert", ulp_perturbed(f))):
+        with _Logged(R) as lg:
+            R.set("ifsolv", 0), R.set("istep", 1), R.set("kfldfdm", 1)
+            R.call("cggo", np.zeros(n), rhs.copy(), h1, h2, case.mask, case.mult, 1, 1e-8, 300, 1, rc.fld("binvm1"), "VELX")
+        (hist, tol), = lg.cggo()
+        out[key], out[key.replace("rbn2", "it")], out["cg_tol"] = hist, np.array([R.get("niterhm")]), np.array([tol])
+    R.set("kfldfdm", -1)
     return out
 
 
@@ -397,6 +494,23 @@ def ref_ophinv():
             assert np.array_equal(x, o[k]) and np.array_equal(r, ii[k])
             out[f"o{k + 1}{key}"], out[f"r{k + 1}{key}"] = o[k], ii[k]
         out["its" + key] = np.array(its)
+    # The same with h2 / 20 (the balance of a ten times larger time step): 133 / 128 / 153 iterations.  Over that many
+    # iterations CG amplifies rounding-level differences to ~1e-6 of the residual, so a re-ordered summation may leave the loop
+    # one iteration earlier or later; the reference's own log (residual per check) on the original and on a right-hand side
+    # perturbed by one unit of rounding is stored so that the tests can tell such a flip from an error (count_or_margin).
+    out["h2_long"] = h2 / 20.0
+    for key, rr in (("long", rhs), ("long_pert", [ulp_perturbed(a, 100 + k) for k, a in enumerate(rhs)])):
+        its = []
+        for k, nm in enumerate(("VELX", "VELY", "VELZ")):
+            x, r = np.zeros(n), rr[k].copy()
+            with _Logged(R) as lg:
+                R.call("hmholtz", nm, x, r, h1, out["h2_long"], masks[k], out["vmult"], 1, 1e-8, 300, k + 1)
+            (hist, tol), = lg.cggo()
+            its.append(int(R.get("niterhm")))
+            out[f"rbn2_{key}{k + 1}"], out[f"tol_{key}{k + 1}"] = hist, np.array([tol])
+            if key == "long":
+                out[f"o{k + 1}_long"] = x
+        out["its_" + key] = np.array(its)
     return out
 
 
@@ -440,9 +554,13 @@ def _ref_hsolve(name, pres, case=None, tol=1e-7):
     for k, (rhs, h1, h2, istep) in enumerate(hsolve_inputs(case, pres, consistent=bool(R.get("ifvcor")) and pres)):
         R.set("istep", istep)
         u, r = np.zeros(n), rhs.copy()
-        R.call("hsolve", name, u, r, h1, h2, mask, out["vmult"], 1, tol, 200, 1, approx, napprox, out["binvm1"])
+        with _Logged(R) as lg:
+            R.call("hsolve", name, u, r, h1, h2, mask, out["vmult"], 1, tol, 200, 1, approx, napprox, out["binvm1"])
         its.append(int(R.get("niterhm"))), ms.append(int(napprox[1]))
         out[f"u{k}"], out[f"r{k}"] = u, r
+        # the residual the exit test saw at every check / iteration of this solve, and the tolerance it was held against
+        (hist, tl), = (lg.gmres() if pres else lg.cggo())
+        out[f"res{k}"], out[f"restol{k}"] = hist, np.array([tl])
     out["its"], out["m"] = np.array(its), np.array(ms)
     return out
 

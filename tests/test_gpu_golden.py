@@ -193,10 +193,15 @@ def test_fdm_h1_and_schwarz_cggo_against_the_reference(nek):
     assert it == g["cg20_it"][0] and relmax(x, g["cg20_x"]) <= TOL_FIELD
     x = np.zeros(n)
     it = nek.cggo(x, g["f"], g["h1"], g["h2"], case.mask, case.mult, 1, 1e-8, 300, 1, case.binv(), "VELX")
+    hist = nek.last_history()
     nek.set_kfldfdm(-1)
-    # the non-symmetric Schwarz preconditioner makes CG amplify 1e-15 differences past iteration ~30 (the reference
-    # against the oracle shows the same): count within 1, solution to the solver tolerance
-    assert abs(it - g["cg_it"][0]) <= 1 and relmax(x, g["cg_x"]) <= 1e-6
+    # The non-symmetric Schwarz preconditioner makes CG amplify rounding-level differences: the reference's own residual
+    # history moves by 5e-2 (relative) at check 48 when its right-hand side is changed by one unit of rounding (golden
+    # cg_rbn2 / cg_rbn2_pert, logged by the reference itself).  Identical count, or a one-off flip proven to lie inside that
+    # sensitivity; solution to the solver tolerance.
+    refcases.count_or_margin(it, int(g["cg_it"][0]), hist[:, 1], g["cg_rbn2"], float(g["cg_tol"][0]), g["cg_rbn2_pert"],
+                             what="Schwarz-preconditioned cggo")
+    assert relmax(x, g["cg_x"]) <= 1e-6
 
 
 def test_pnpn2_hsmg_solve_against_the_reference(nek):
@@ -268,6 +273,37 @@ def test_ophinv_fused_three_rhs_against_the_reference(nek):
         for k in range(3):
             assert relmax(i[k], g[f"r{k + 1}{key}"]) <= TOL_APPLY                # rhs dssum'ed + masked in place
             assert relmax(o[k], g[f"o{k + 1}{key}"]) <= ftol, (key, k)
+
+
+def test_ophinv_long_runs_and_the_exit_margin(nek):
+    """The conditioning round 1's golden case started with (h2 / 20: the reference needs 133 / 128 / 153 iterations).  Over
+    that many iterations CG amplifies rounding-level differences, so the fused solve may leave a component's loop one
+    iteration away from the reference -- round 1 saw 152 against 153.  The golden file now holds the reference's own logged
+    residual histories of these solves, on the original right-hand sides and on ones perturbed by a single unit of rounding;
+    every count must be identical or a one-off flip inside the reference's own sensitivity (refcases.count_or_margin)."""
+    import ctypes as C
+    from nek5000_b200 import lib
+    from nek5000_b200._lib import check
+    from nek5000_b200.nek import DevArray
+    g, case = G["ophinv"], refcases.case_of("ophinv")
+    _register_ophinv(nek, g, case)
+    n = case.n
+    D = DevArray.from_host
+    outs = [DevArray(n) for _ in range(3)]
+    rh = [D(g[f"i{k + 1}"]) for k in range(3)]
+    h1, h2, mult, binv = D(g["h1"]), D(g["h2_long"]), D(g["vmult"]), D(g["binvm1"])
+    m = [D(g[f"v{k + 1}mask"]) for k in range(3)]
+    its = np.zeros(3, dtype=np.int32)
+    stride = 3 * (300 + 2)
+    hist = np.zeros(3 * stride)
+    check(lib().nekb_ophinv_dev(outs[0].ptr, outs[1].ptr, outs[2].ptr, rh[0].ptr, rh[1].ptr, rh[2].ptr, h1.ptr, h2.ptr,
+                                m[0].ptr, m[1].ptr, m[2].ptr, mult.ptr, binv.ptr, 1e-8, 300, its.ctypes.data, hist.ctypes.data))
+    assert g["its_long"].tolist() == [133, 128, 153]
+    for k in range(3):
+        hk = hist[k * stride:(k + 1) * stride].reshape(-1, 3)[:its[k] + 1, 1]
+        refcases.count_or_margin(int(its[k]), int(g["its_long"][k]), hk, g[f"rbn2_long{k + 1}"], float(g[f"tol_long{k + 1}"][0]),
+                                 g[f"rbn2_long_pert{k + 1}"], what=f"ophinv component {k + 1} (long run)")
+        assert relmax(outs[k].to_host(), g[f"o{k + 1}_long"]) <= TOL_CONVERGED, k
 
 
 def test_ophinv_with_a_zero_component(nek):
@@ -356,8 +392,10 @@ def test_lx1_6_generic_kernels_against_the_reference():
 def test_hsolve_with_residual_projection_against_the_reference(nek):
     """core/navier4.f:562-634 hsolve + project1/project2 (:636-1199), device-resident approximation space: eleven successive
     'VELX' solves (h2 changes at call 4; the space saturates at mmx = 8 and drops rank-deficient vectors afterwards: m = 1 2 3 4
-    5 6 7 8 7 8 7).  Iteration counts within 1 of the reference's 64 58 55 6 49 43 38 6 5 8 1 (the projected right-hand side is
-    a difference of nearly equal vectors, its sums run in another order), space size m identical."""
+    5 6 7 8 7 8 7).  Iteration counts equal to the reference's 64 58 55 6 49 43 38 6 5 8 1 -- or off by one ONLY where the
+    reference's own logged residual at the deciding check lies within 1e-7 of the tolerance and the device history agrees with
+    the reference's to that accuracy up to there (refcases.count_or_margin; the projected right-hand side is a difference of
+    nearly equal vectors, its sums run in another order) -- space size m identical."""
     g, case = G["hsolve"], refcases.case_of("core")
     gc = G["core"]
     register_core(nek, gc, case)
@@ -373,7 +411,8 @@ def test_hsolve_with_residual_projection_against_the_reference(nek):
         it = nek.hsolve("VELX", u, r, h1, h2, g["mask"], g["vmult"], 1, 1e-7, 200, 1, None, napprox, g["binvm1"])
         its.append(it)
         assert napprox[0] == 8 and napprox[1] == g["m"][k]
-        assert abs(it - g["its"][k]) <= 1, (k, its, g["its"])
+        refcases.count_or_margin(it, int(g["its"][k]), nek.last_history()[:, 1], g[f"res{k}"], float(g[f"restol{k}"][0]),
+                                 cap=1e-7, what=f"hsolve('VELX') call {k}")
         scale = np.abs(case.dssum(rhs * g["mask"])).max()
         assert np.abs(r - g[f"r{k}"]).max() <= 1e-9 * scale, k              # projected right-hand side
         assert relmax(u, g[f"u{k}"]) <= 1e-6, k
@@ -403,7 +442,8 @@ def test_hsolve_pres_with_residual_projection_against_the_reference(nek):
         u, r = np.zeros(n), rhs.copy()
         it = nek.hsolve("PRES", u, r, h1, h2, g["mask"], g["vmult"], 1, 1e-7, 200, 1, None, napprox, g["binvm1"])
         assert napprox[1] == g["m"][k]
-        assert abs(it - g["its"][k]) <= 1, (k, it, g["its"])
+        refcases.count_or_margin(it, int(g["its"][k]), nek.last_history()[:, 0], g[f"res{k}"], float(g[f"restol{k}"][0]),
+                                 cap=1e-7, what=f"hsolve('PRES') call {k}", gmres=True)
         assert relmax(u, g[f"u{k}"]) <= 1e-5, k
 
 

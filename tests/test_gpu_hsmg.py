@@ -181,8 +181,13 @@ def test_h1mg_all_neumann_null_space(nek):
     xref, itref, hist_ref, div0 = hsmg.hmh_gmres(case, mg, b, h1, h2, case.mask, case.mult, tol, maxit, ifvcor=True, history=True)
     bdv, h1d, wtd, pmd = (nek.DevArray.from_host(a) for a in (b, h1, case.mult, case.mask))
     it = C.c_int(0)
-    check(L.nekb_hmh_gmres_dev(bdv.ptr, h1d.ptr, None, wtd.ptr, pmd.ptr, tol, maxit, C.byref(it), None, None))
-    assert abs(it.value - itref) <= 1 and itref < maxit
+    hist = np.zeros(maxit + 1)
+    check(L.nekb_hmh_gmres_dev(bdv.ptr, h1d.ptr, None, wtd.ptr, pmd.ptr, tol, maxit, C.byref(it), hist.ctypes.data, None))
+    # identical count, or a one-off flip only where the two residual histories agree to 1e-8 and straddle tol
+    import refcases
+    refcases.count_or_margin(it.value, itref, hist[:it.value], np.asarray(hist_ref), tol, cap=1e-8, gmres=True,
+                             what="all-Neumann hmh_gmres against the numpy oracle")
+    assert itref < maxit
     x = bdv.to_host()
     assert relmax(x, xref) <= 1e-6
 

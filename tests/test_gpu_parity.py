@@ -205,6 +205,35 @@ def test_cggos_history_and_solution(nek):
     nek.fgslib_gs_free(h)
 
 
+@pytest.mark.parametrize("dims,per,dirichlet", [((3, 3, 2), (0, 0, 0), (1, 1, 1, 1, 1, 1)), ((4, 3, 2), (1, 0, 1), (1, 1, 1, 1, 1, 1)),
+                                                ((1, 1, 1), (0, 0, 0), (1, 1, 1, 1, 1, 1)), ((2, 1, 1), (1, 1, 1), (1, 1, 1, 1, 1, 1)),
+                                                ((1, 2, 3), (1, 0, 0), (0, 0, 1, 1, 0, 1))])
+def test_structured_gather_update_is_bit_identical_to_gs_op_plus_update(nek, dims, per, dirichlet, monkeypatch):
+    """The default fused cggos iteration folds the direct-stiffness summation into the update kernel (structured gather:
+    face pairs through per-face affine links, edge / corner groups through gval; gs.cuh gs_ensure_struct).  It must give the
+    bits of the stock pair gs_op + cggos_update2_kernel (NEKB_GS_FUSE_UPDATE=0) -- same members, same order -- on boxes with
+    periodic sides (an element paired with itself, two elements paired twice) and partial Dirichlet sides, and agree with the
+    oracle like the stock pair does."""
+    case = oracle.Case(*dims, nx=8, periodic=per, dirichlet=dirichlet, deform=0.04 if not any(per) else 0.0)
+    register(nek, case, bp5=True)
+    e1, r1 = case.bp5_problem()
+    maxit = 30
+    uref, itref, hist = case.cggos(r1, e1, tol=-1e-8, maxit=maxit, history=True)
+    us = []
+    for flag in ("0", "3"):
+        monkeypatch.setenv("NEKB_GS_FUSE_UPDATE", flag)
+        h, _ = nek.setupds(8, case.nel, case.vertex)
+        nek.set_field_handle(1, h)
+        nek.set_ifield(1)
+        u = np.zeros(case.n)
+        it = nek.cggos(u, r1, e1, case.mult, np.ones(case.n), -1e-8, maxit, "bp5")
+        assert it == maxit
+        us.append(u)
+        nek.fgslib_gs_free(h)
+    assert np.array_equal(us[0], us[1])
+    assert relmax(us[1], uref) <= TOL_HIST
+
+
 @pytest.mark.parametrize("ifh2", [False, True])
 def test_cggo_iterations_and_solution(nek, ifh2):
     """Stock cggo (hmholtz.f:611-846).  CG amplifies rounding differences exponentially with the iteration number

@@ -184,8 +184,10 @@ def test_crs_facade_against_a_dense_solve(nek, null_space):
 
 @pytest.mark.parametrize("m,nmax,omega_p,iters", [(20, 4096, 0.0, 27), (20, 4096, 0.66, 20), (8, 4096, 0.0, 1), (32, 800, 0.0, None),
                                                   (32, 800, 0.66, None)])
-def test_crs_amg_device_cycle_against_numpy(nek, m, nmax, omega_p, iters):
-    """CG + V(1,1) aggregation cycle on the device against the same algorithm in numpy on the same (library-built) levels:
+@pytest.mark.parametrize("coop", ["1", "0"])
+def test_crs_amg_device_cycle_against_numpy(nek, m, nmax, omega_p, iters, coop, monkeypatch):
+    """coop = "1": the whole solve in one cooperative launch (amg_pcg_coop_kernel, default); "0": one launch per operation.
+    CG + V(1,1) aggregation cycle on the device against the same algorithm in numpy on the same (library-built) levels:
     same iteration count (27 at 8820 vertices, 20 with the smoothed prolongation: the prototype's numbers), solution to 1e-10, residual at the requested 1e-13."""
     import ctypes as C
     import sys
@@ -195,6 +197,7 @@ def test_crs_amg_device_cycle_against_numpy(nek, m, nmax, omega_p, iters):
     from nek5000_b200 import lib
     from nek5000_b200._lib import check
     from nek5000_b200.nek import DevArray
+    monkeypatch.setenv("NEKB_CRS_AMG_COOP", coop)
     A = proto.q1_stiffness(m)
     n = A.shape[0]
     co = A.tocoo()
@@ -302,7 +305,8 @@ def test_hsolve_pres_on_the_channel_mesh_as_turbchannel_par_runs_it(nek):
         u, r = np.zeros(n), rhs.copy()
         it = nek.hsolve("PRES", u, r, h1, h2, g["mask"], g["vmult"], 1, 1e-4, 200, 1, None, napprox, g["binvm1"])
         assert napprox[1] == g["m"][k]
-        assert abs(it - g["its"][k]) <= 1, (k, it, g["its"])
+        refcases.count_or_margin(it, int(g["its"][k]), nek.last_history()[:, 0], g[f"res{k}"], float(g[f"restol{k}"][0]),
+                                 cap=1e-7, what=f"channel hsolve('PRES') call {k}", gmres=True)
         assert relmax(u, g[f"u{k}"]) <= 1e-5, k
 
 
