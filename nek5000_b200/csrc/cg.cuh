@@ -482,6 +482,107 @@ __global__ void __launch_bounds__(CG_THREADS)
     });
 }
 
+// The same update, organised by element instead of by node: 128 threads own one 8^3 tile (one quad of nodes each).  The
+// irregular part -- 216 face partners and 80 edge / corner values per element -- is fetched by ALL threads in one uniform,
+// fully independent sweep into shared memory (no divergent dependent loads in the streaming part), then every thread
+// patches its quad from shared memory.  Bits as cggos_update3_kernel / the stock pair.
+template <int EPB>
+__global__ void __launch_bounds__(128 * EPB, 4)
+    cggos_update4_kernel(double *__restrict__ r, const double *__restrict__ ap, const unsigned char *__restrict__ code,
+                         const FaceLink *__restrict__ ftab, const int32_t *__restrict__ etab, const double *__restrict__ gval,
+                         int nel, CgScalars *sc, double *partials)
+{
+    __shared__ double red[33];
+    __shared__ double wtab[128];
+    __shared__ double s_face[EPB][6 * 36];
+    __shared__ double s_edge[EPB][GS_ST_EDGE_SLOTS];
+    __shared__ int s_eg[EPB][GS_ST_EDGE_SLOTS];
+    __shared__ int s_fok[EPB][6];
+    const double pap = sc->work[0], rz = sc->work[1];
+    const double alpha = rz / pap;
+    if (threadIdx.x < 128) wtab[threadIdx.x] = threadIdx.x ? 1.0 / (double)threadIdx.x : 0.0;
+    const int es = threadIdx.x >> 7, lt = threadIdx.x & 127;
+    const int i0 = (lt & 1) << 2, j = (lt >> 1) & 7, k = lt >> 4;
+    const int bj = (j == 0 || j == 7), bk = (k == 0 || k == 7);
+    const int ie = i0 ? 3 : 0;
+    double s = 0.0;
+    double2 *r2 = reinterpret_cast<double2 *>(r);
+    const double2 *a2 = reinterpret_cast<const double2 *>(ap);
+    const uchar4 *c4 = reinterpret_cast<const uchar4 *>(code);
+    for (int e0 = blockIdx.x * EPB; e0 < nel; e0 += gridDim.x * EPB) {
+        const int e = e0 + es;
+        const bool act = e < nel;
+        const int64_t t = (int64_t)(act ? e : 0) * 128 + lt;
+        double2 ra, rb, aa, ab;
+        uchar4 c;
+        if (act) {
+            ra = r2[2 * t], rb = r2[2 * t + 1];
+            aa = a2[2 * t], ab = a2[2 * t + 1];
+            c = c4[t];
+            // the irregular part, uniform over the threads: items 0..215 = (face, in-face node), 216..295 = edge / corner slots
+#pragma unroll
+            for (int it = lt; it < 216 + GS_ST_EDGE_SLOTS; it += 128) {
+                if (it < 216) {
+                    const int f = it / 36, q = it - 36 * f;
+                    const int b = q / 6, a = q - 6 * b;
+                    const FaceLink L = ftab[(int64_t)e * 6 + f];
+                    double v = 0.0;
+                    if (L.base >= 0) v = ap[(int64_t)L.base + (a + 1) * L.sa + (b + 1) * L.sb];
+                    s_face[es][it] = v;
+                    if (q == 0) s_fok[es][f] = L.base >= 0;
+                } else {
+                    const int sl = it - 216;
+                    const int g = etab[(int64_t)e * GS_ST_EDGE_SLOTS + sl];
+                    s_eg[es][sl] = g;
+                    s_edge[es][sl] = g >= 0 ? gval[g] : 0.0;
+                }
+            }
+        }
+        __syncthreads();
+        if (act) {
+            double w[4] = {aa.x, aa.y, ab.x, ab.y};
+            if (bj + bk == 0) {
+                const int f = i0 ? 1 : 0;
+                if (s_fok[es][f]) w[ie] += s_face[es][f * 36 + (j - 1) + 6 * (k - 1)];
+            } else if (bj + bk == 1) {
+                const int f = bj ? 2 + (j == 7) : 4 + (k == 7);
+                const int bco = bj ? k : j;
+                if (s_fok[es][f]) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        if (q != ie) w[q] += s_face[es][f * 36 + (i0 + q - 1) + 6 * (bco - 1)];
+                }
+                const int sl = gs_st_slot(i0 ? 7 : 0, j, k);
+                if (s_eg[es][sl] >= 0) w[ie] = s_edge[es][sl];
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int sl = gs_st_slot(i0 + q, j, k);
+                    if (s_eg[es][sl] >= 0) w[q] = s_edge[es][sl];
+                }
+            }
+            ra.x = fma(-alpha, (c.x & 0x80) ? 0.0 : w[0], ra.x);
+            ra.y = fma(-alpha, (c.y & 0x80) ? 0.0 : w[1], ra.y);
+            rb.x = fma(-alpha, (c.z & 0x80) ? 0.0 : w[2], rb.x);
+            rb.y = fma(-alpha, (c.w & 0x80) ? 0.0 : w[3], rb.y);
+            r2[2 * t] = ra;
+            r2[2 * t + 1] = rb;
+            s = fma(wtab[c.x & 0x7f] * ra.x, ra.x, s);
+            s = fma(wtab[c.y & 0x7f] * ra.y, ra.y, s);
+            s = fma(wtab[c.z & 0x7f] * rb.x, rb.x, s);
+            s = fma(wtab[c.w & 0x7f] * rb.y, rb.y, s);
+        }
+        __syncthreads();   // the shared tables are rewritten by the next element
+    }
+    double b = block_reduce(s, red);
+    grid_reduce(b, partials, &sc->counter[2], red, [=](double tot) {
+        sc->rtz1 = rz;
+        sc->work[1] = tot;
+        sc->alpha = alpha;
+        sc->it = sc->it + 1;
+    });
+}
+
 // u += alpha * p with the device-resident alpha (the u update of the final iteration)
 __global__ void __launch_bounds__(CG_THREADS)
     axpy_alpha_kernel(double *__restrict__ u, const double *__restrict__ p, int64_t n, const CgScalars *sc)
@@ -555,7 +656,7 @@ inline int cggos_run_fused(const CggosArgs &a, int maxit, double *hist_host, boo
     const int gmode = gs_fuse_update_enabled();
     const bool gather = (gmode == 1 || gmode == 2) && c.nranks == 1 && h.nshared == 0;
     if (gather) gs_ensure_link(h, gmode);
-    const bool structured = gmode == 3 && gs_ensure_struct(h);
+    const bool structured = (gmode == 3 || gmode == 4) && gs_ensure_struct(h);
     cggos_init2_kernel<<<grid, CG_THREADS, 0, s>>>(a.u, r.p, a.rhs, a.mult, n, sc, c.partials.p + 1 * CG_PART_STRIDE);
     NEKB_LAUNCHED();
     comm_allreduce_sum(&sc->work[1], 1);
@@ -581,8 +682,13 @@ inline int cggos_run_fused(const CggosArgs &a, int maxit, double *hist_host, boo
             if (h.nshared > 0 || c.nranks > 1) gs_remote_exchange(h, ap.p, 1);
             prof_end(PROF_GS);
             prof_begin(PROF_UPDATE);
-            cggos_update3_kernel<<<grid, CG_THREADS, 0, s>>>(r.p, ap.p, c.wcode.p, h.ftab.p, h.etab.p, h.gval.p, n, sc,
-                                                             c.partials.p + 2 * CG_PART_STRIDE);
+            if (gmode == 4) {
+                const int g4 = grid_for((a.nel + 1) / 2, 4);   // 4 CTAs of 256 threads per SM (64 registers)
+                cggos_update4_kernel<2><<<g4, 256, 0, s>>>(r.p, ap.p, c.wcode.p, h.ftab.p, h.etab.p, h.gval.p, a.nel, sc,
+                                                           c.partials.p + 2 * CG_PART_STRIDE);
+            } else
+                cggos_update3_kernel<<<grid, CG_THREADS, 0, s>>>(r.p, ap.p, c.wcode.p, h.ftab.p, h.etab.p, h.gval.p, n, sc,
+                                                                 c.partials.p + 2 * CG_PART_STRIDE);
             NEKB_LAUNCHED();
             prof_end(PROF_UPDATE);
         } else if (gather) {

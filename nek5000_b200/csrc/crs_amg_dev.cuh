@@ -296,7 +296,34 @@ struct AmgCoopArgs {
     double *partials;           // >= 4 * gridDim doubles
     int *iters_out;
 };
-__global__ void __launch_bounds__(512) amg_pcg_coop_kernel(AmgCoopArgs A)
+// Row sweep of a CSR operator: out(i, sum_q val[q] * xf(col[q])).  Thread per row when there are at least as many rows as
+// an eighth of the threads (level 0: 27 entries per row), otherwise warp per row with coalesced row reads (the deeper levels
+// and the restrictions, whose rows hold 50-150 entries: a thread walking such a row alone is 150 dependent L2 round trips).
+template <class XF, class OUT>
+__device__ __forceinline__ void amg_rows(int n, const int32_t *__restrict__ rp, const int32_t *__restrict__ col,
+                                         const double *__restrict__ val, int tid, int nth, XF xf, OUT out)
+{
+    if (n * 8 >= nth) {
+        for (int i = tid; i < n; i += nth) {
+            double s = 0.0;
+            const int e = rp[i + 1];
+#pragma unroll 4
+            for (int q = rp[i]; q < e; q++) s = fma(val[q], xf(col[q]), s);
+            out(i, s);
+        }
+    } else {
+        const int lane = threadIdx.x & 31, nw = nth >> 5;
+        for (int i = tid >> 5; i < n; i += nw) {
+            double s = 0.0;
+            const int e = rp[i + 1];
+            for (int q = rp[i] + lane; q < e; q += 32) s = fma(val[q], xf(col[q]), s);
+            s = warp_sum(s);
+            if (lane == 0) out(i, s);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024) amg_pcg_coop_kernel(AmgCoopArgs A)
 {
     namespace cgr = cooperative_groups;
     cgr::grid_group grid = cgr::this_grid();
@@ -329,22 +356,18 @@ __global__ void __launch_bounds__(512) amg_pcg_coop_kernel(AmgCoopArgs A)
                 const AmgCoopLevel &L = A.L[l];
                 if (!(l == 0 && fresh)) {
                     const double *bl = l == 0 ? A.r : L.b;
-                    for (int i = tid; i < L.n; i += nth) {   // x = dj b ; r = b - A x
-                        double s = 0.0;
-                        for (int q = L.rowptr[i]; q < L.rowptr[i + 1]; q++) s = fma(L.val[q], L.dj[L.col[q]] * bl[L.col[q]], s);
-                        L.x[i] = L.dj[i] * bl[i];
-                        L.r[i] = bl[i] - s;
-                    }
+                    amg_rows(L.n, L.rowptr, L.col, L.val, tid, nth, [&](int jc) { return L.dj[jc] * bl[jc]; },
+                             [&](int i, double sm) {            // x = dj b ; r = b - A x
+                                 L.x[i] = L.dj[i] * bl[i];
+                                 L.r[i] = bl[i] - sm;
+                             });
                     grid.sync();
                 }
                 const bool last = l + 1 == A.nlev;
                 double *bc = last ? A.cb : A.L[l + 1].b;
                 const int ncn = last ? A.nc : A.L[l + 1].n;
-                for (int i = tid; i < ncn; i += nth) {       // bc = P^T r
-                    double s = 0.0;
-                    for (int q = L.trow[i]; q < L.trow[i + 1]; q++) s = fma(L.tval[q], L.r[L.tcol[q]], s);
-                    bc[i] = s;
-                }
+                amg_rows(ncn, L.trow, L.tcol, L.tval, tid, nth, [&](int jc) { return L.r[jc]; },
+                         [&](int i, double sm) { bc[i] = sm; });     // bc = P^T r
                 grid.sync();
             }
             {   // coarsest: y = Ainv b, one warp per row
@@ -362,22 +385,18 @@ __global__ void __launch_bounds__(512) amg_pcg_coop_kernel(AmgCoopArgs A)
                 const AmgCoopLevel &L = A.L[l];
                 const bool last = l + 1 == A.nlev;
                 const double *ec = last ? A.cy : A.L[l + 1].e;
-                for (int i = tid; i < L.n; i += nth) {       // x += P e
-                    double s = 0.0;
-                    for (int q = L.prow[i]; q < L.prow[i + 1]; q++) s = fma(L.pval[q], ec[L.pcol[q]], s);
-                    L.x[i] += s;
-                }
+                amg_rows(L.n, L.prow, L.pcol, L.pval, tid, nth, [&](int jc) { return ec[jc]; },
+                         [&](int i, double sm) { L.x[i] += sm; });   // x += P e
                 grid.sync();
                 const double *bl = l == 0 ? A.r : L.b;
                 double *out = l == 0 ? A.z : L.e;
                 double rzp = 0.0;
-                for (int i = tid; i < L.n; i += nth) {       // out = x + dj (b - A x)
-                    double s = 0.0;
-                    for (int q = L.rowptr[i]; q < L.rowptr[i + 1]; q++) s = fma(L.val[q], L.x[L.col[q]], s);
-                    const double v = L.x[i] + L.dj[i] * (bl[i] - s);
-                    out[i] = v;
-                    if (l == 0) rzp = fma(bl[i], v, rzp);
-                }
+                amg_rows(L.n, L.rowptr, L.col, L.val, tid, nth, [&](int jc) { return L.x[jc]; },
+                         [&](int i, double sm) {                  // out = x + dj (b - A x)
+                             const double v = L.x[i] + L.dj[i] * (bl[i] - sm);
+                             out[i] = v;
+                             rzp = fma(bl[i], v, rzp);
+                         });
                 if (l == 0) {
                     const double t = block_reduce(rzp, red);
                     if (threadIdx.x == 0) P1[blockIdx.x] = t;
@@ -392,17 +411,13 @@ __global__ void __launch_bounds__(512) amg_pcg_coop_kernel(AmgCoopArgs A)
         for (; it < A.maxit;) {
             {   // p = z + beta p (own entry stored, neighbours rebuilt) ; w = A p ; (p,w)
                 double s = 0.0;
-                for (int i = tid; i < n; i += nth) {
-                    double acc = 0.0;
-                    for (int q = F.rowptr[i]; q < F.rowptr[i + 1]; q++) {
-                        const int j = F.col[q];
-                        acc = fma(F.val[q], fma(beta, pin[j], A.z[j]), acc);
-                    }
-                    const double pi = fma(beta, pin[i], A.z[i]);
-                    pout[i] = pi;
-                    A.w[i] = acc;
-                    s = fma(pi, acc, s);
-                }
+                amg_rows(n, F.rowptr, F.col, F.val, tid, nth, [&](int jc) { return fma(beta, pin[jc], A.z[jc]); },
+                         [&](int i, double acc) {
+                             const double pi = fma(beta, pin[i], A.z[i]);
+                             pout[i] = pi;
+                             A.w[i] = acc;
+                             s = fma(pi, acc, s);
+                         });
                 const double t = block_reduce(s, red);
                 if (threadIdx.x == 0) P2[blockIdx.x] = t;
             }
@@ -411,28 +426,26 @@ __global__ void __launch_bounds__(512) amg_pcg_coop_kernel(AmgCoopArgs A)
             const double alpha = rz / pw;
             {   // x += a p ; r -= a w ; (r,r) ; level-0 pre-smoothing on the new r (neighbours' r rebuilt: r_j - a w_j)
                 double s = 0.0;
-                for (int i = tid; i < n; i += nth) {
-                    A.x[i] = fma(alpha, pout[i], A.x[i]);
-                    const double ri = fma(-alpha, A.w[i], A.r[i]);
-                    double acc = 0.0;
-                    for (int q = F.rowptr[i]; q < F.rowptr[i + 1]; q++) {
-                        const int j = F.col[q];
-                        acc = fma(F.val[q], F.dj[j] * fma(-alpha, A.w[j], A.r[j]), acc);
-                    }
-                    F.x[i] = F.dj[i] * ri;
-                    F.r[i] = ri - acc;
-                    A.z[i] = ri;             // parked: A.r is still being read by other threads' neighbour sums
-                    s = fma(ri, ri, s);
-                }
+                amg_rows(n, F.rowptr, F.col, F.val, tid, nth, [&](int jc) { return F.dj[jc] * fma(-alpha, A.w[jc], A.r[jc]); },
+                         [&](int i, double acc) {
+                             A.x[i] = fma(alpha, pout[i], A.x[i]);
+                             const double ri = fma(-alpha, A.w[i], A.r[i]);
+                             F.x[i] = F.dj[i] * ri;
+                             F.r[i] = ri - acc;
+                             A.z[i] = ri;          // parked: A.r is still being read by other threads' neighbour sums
+                             s = fma(ri, ri, s);
+                         });
                 const double t = block_reduce(s, red);
                 if (threadIdx.x == 0) P3[blockIdx.x] = t;
             }
             grid.sync();
-            for (int i = tid; i < n; i += nth) A.r[i] = A.z[i];   // own entries only: no other thread reads r before the next sync
+            // own entries only (the writer of z[i] in the sweep above is the thread that copies it here when rows are swept by
+            // threads; with the warp-per-row sweep lane 0 wrote it, so every thread copies a strided share after the sync)
+            for (int i = tid; i < n; i += nth) A.r[i] = A.z[i];
             const double rr = coop_total(P3, G, red, &s_b);
             it++;
             if (rr <= stop2) break;
-            cycle(true);
+            cycle(true);   // reads r at other rows only in its last phase (level-0 post-smoothing), several syncs from here
             const double rz_new = coop_total(P1, G, red, &s_b);
             beta = rz_new / rz;
             rz = rz_new;
@@ -472,17 +485,17 @@ inline int amg_pcg_solve_coop(double *x_dev, const double *b_dev, double tol, in
     A.tol = tol, A.maxit = maxit;
     static int per_sm = 0;
     if (!per_sm) {
-        NEKB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, amg_pcg_coop_kernel, 512, 0));
+        NEKB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, amg_pcg_coop_kernel, 1024, 0));
         NEKB_REQUIRE(per_sm >= 1, "amg_pcg_coop_kernel cannot be made resident");
         per_sm = 1;   // one CTA per SM: the phases are synchronisation-bound, fewer arrivals make a cheaper grid sync
     }
-    int gridc = (int)((D.L[0].n + 511) / 512);
+    int gridc = (int)((D.L[0].n + 1023) / 1024);
     if (gridc > c.num_sms * per_sm) gridc = c.num_sms * per_sm;
     D.coop_part.ensure((size_t)4 * c.num_sms * per_sm);
     D.iters.ensure(1);
     A.partials = D.coop_part.p, A.iters_out = D.iters.p;
     void *args[] = {&A};
-    NEKB_CUDA(cudaLaunchCooperativeKernel((void *)amg_pcg_coop_kernel, dim3(gridc), dim3(512), args, 0, s));
+    NEKB_CUDA(cudaLaunchCooperativeKernel((void *)amg_pcg_coop_kernel, dim3(gridc), dim3(1024), args, 0, s));
     NEKB_LAUNCHED();
     if (!want_iters) return -1;
     int it = 0;
@@ -506,7 +519,7 @@ inline void crs_amg_solve(CrsSolver &k, double *x_out, const double *b_in)
     if (c.nranks > 1) comm_allreduce_sum(k.g.p, (int)nc);
     crsd_prep_kernel<<<1, 1024, 0, s>>>(k.g.p, k.gmask.p, nc, k.null_space, k.ndof);
     NEKB_LAUNCHED();
-    if (amg_coop_enabled() && !amg_dev().L.empty()) {
+    if (k.amg_one_launch) {                                             // decided at set-up (NEKB_CRS_AMG_COOP)
         amg_pcg_solve_coop(k.y.p, k.g.p, k.tol, k.maxit, false);      // no host round trip inside h1mg_solve
         k.last_iters = -1, k.iters_on_device = false;
     } else {
@@ -595,6 +608,7 @@ inline void crs_amg_setup(CrsSolver &k, int nel, const int64_t *vertex)
     k.nc = nc;
     NEKB_CUDA(cudaStreamSynchronize(s));
     k.amg_solve = crs_amg_solve;
+    k.amg_one_launch = amg_coop_enabled() && !amg_dev().L.empty();
 }
 
 struct CrsAmgHookInstaller {

@@ -271,6 +271,7 @@ struct CrsSolver {
     int null_space = 0;
     int last_iters = 0;
     bool iters_on_device = false;  // the cooperative kernel leaves its count in the device scalars
+    bool amg_one_launch = false;   // the aggregation-hierarchy CG runs as one cooperative launch (no host round trip)
     double tol = 1e-13;
     int maxit = 2000;
     // ---- direct solver (the XXT role): explicit inverse of the assembled coarse matrix, applied as one GEMV --------
@@ -300,6 +301,15 @@ struct H1mg {
     CrsSolver crs;
     // setup products kept on the host for parity tests
     std::vector<double> lm_host, ll_host, lr_host;  // [3][nel]
+    // Captured V-cycles (single rank): h1mg_solve is ~28 launches of a fixed sequence with fixed arguments for a given pair
+    // of buffers -- the preconditioner step of hmh_gmres is called with the same (z_j, w) pairs in every cycle -- so the
+    // sequence is replayed from a CUDA graph (one launch instead of 28; the gaps between the small lower-level kernels go).
+    struct VGraph {
+        int seen = 0;                 // calls with this (z, rhs) pair so far: the first runs eagerly (it may allocate)
+        cudaGraphExec_t exec = nullptr;
+        int64_t launches = 0;
+    };
+    std::map<std::pair<const void *, const void *>, VGraph> vgraphs;
 };
 inline H1mg &h1mg()
 {
@@ -316,6 +326,9 @@ inline void crs_release_graph(H1mg &M)
     CrsSolver &k = M.crs;
     if (k.graph) cudaGraphExecDestroy(k.graph);
     k.graph = nullptr;
+    for (auto &kv : M.vgraphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    M.vgraphs.clear();
 }
 inline void crs_release_graph()
 {
@@ -2061,11 +2074,48 @@ inline void h1mg_setup_run(H1mg &M, const int *fbc, const double *xm1, const dou
 
 // ================================================================================================ h1mg_solve
 // z = M^-1 rhs ; rhs is masked in place (h1mg_schwarz_part1 does that to its input, hsmg.f:449).
+inline void h1mg_solve_body(double *z, double *rhs);
+inline int h1mg_graph_enabled()
+{
+    const char *e = getenv("NEKB_H1MG_GRAPH");
+    return e ? atoi(e) : 1;
+}
 inline void h1mg_solve_dev(double *z, double *rhs)
 {
     Ctx &c = ctx();
     H1mg &M = h1mg();
     NEKB_REQUIRE(M.ready && !M.pnpn2, "h1mg_solve: nekb_h1mg_setup has not been called");
+    // Graph replay: one rank (the inter-rank exchange passes a running epoch to its kernels), coarse solve without a host
+    // round trip (dense inverse, or the one-launch aggregation CG).
+    CrsSolver &k = M.crs;
+    const bool capturable = c.nranks == 1 && h1mg_graph_enabled() && (k.dense || (k.amg_solve != nullptr && k.amg_one_launch));
+    if (!capturable) {
+        h1mg_solve_body(z, rhs);
+        return;
+    }
+    H1mg::VGraph &g = M.vgraphs[std::make_pair((const void *)z, (const void *)rhs)];
+    if (g.exec == nullptr) {
+        if (g.seen++ == 0 || M.vgraphs.size() > 256) {   // first use of this pair: eager (buffers may still be allocated inside)
+            h1mg_solve_body(z, rhs);
+            return;
+        }
+        cudaGraph_t graph = nullptr;
+        const int64_t before = launch_counter();
+        NEKB_CUDA(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
+        h1mg_solve_body(z, rhs);
+        NEKB_CUDA(cudaStreamEndCapture(c.stream, &graph));
+        g.launches = launch_counter() - before;
+        launch_counter() = before;
+        NEKB_CUDA(cudaGraphInstantiate(&g.exec, graph, 0));
+        NEKB_CUDA(cudaGraphDestroy(graph));
+    }
+    NEKB_CUDA(cudaGraphLaunch(g.exec, c.stream));
+    launch_counter() += g.launches;
+}
+inline void h1mg_solve_body(double *z, double *rhs)
+{
+    Ctx &c = ctx();
+    H1mg &M = h1mg();
     cudaStream_t s = c.stream;
     const int nel = M.nel, top = M.lmax - 1;
     mg_schwarz(M.lev[top], rhs, z, nel);                                   // :1890

@@ -220,7 +220,7 @@ def test_structured_gather_update_is_bit_identical_to_gs_op_plus_update(nek, dim
     maxit = 30
     uref, itref, hist = case.cggos(r1, e1, tol=-1e-8, maxit=maxit, history=True)
     us = []
-    for flag in ("0", "3"):
+    for flag in ("0", "3", "4"):
         monkeypatch.setenv("NEKB_GS_FUSE_UPDATE", flag)
         h, _ = nek.setupds(8, case.nel, case.vertex)
         nek.set_field_handle(1, h)
@@ -230,7 +230,7 @@ def test_structured_gather_update_is_bit_identical_to_gs_op_plus_update(nek, dim
         assert it == maxit
         us.append(u)
         nek.fgslib_gs_free(h)
-    assert np.array_equal(us[0], us[1])
+    assert np.array_equal(us[0], us[1]) and np.array_equal(us[0], us[2])     # 3: node-organised kernel, 4: element-organised
     assert relmax(us[1], uref) <= TOL_HIST
 
 
