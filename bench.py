@@ -285,6 +285,34 @@ def main():
     wall_s = max_over_ranks(wall_s)
     iters = a.steps * a.maxit
     value = iters * E_glob * NDOF / dev_s / 1e9
+    # Which operator kernel ran: on a mesh of affine elements (this box) the library replaces the per-node factors by six
+    # constants per element (decided from the registered factors, ax.cuh ax_affine_ensure).  The same solve is timed once more
+    # with that switched off, so the line also carries the number for general (deformed) geometry.
+    affine = bool(L.nekb_ax_affine_active()) if hasattr(L, "nekb_ax_affine_active") else False
+    general = None
+    if affine:
+        os.environ["NEKB_AX_AFFINE"] = "0"
+        case.solve(-1e-8, a.maxit)
+        barrier()
+        check(L.nekb_prof_enable(1))
+        g_s = 0.0
+        for _ in range(max(1, min(a.steps, 2))):
+            it, sec = case.solve(-1e-8, a.maxit)
+            g_s += sec
+        barrier()
+        gprof = {}
+        for k in ("ax", "gs", "update", "pupdate"):
+            s_, c_ = C.c_double(0), C.c_int64(0)
+            check(L.nekb_prof_get(k.encode(), C.byref(s_), C.byref(c_)))
+            gprof[k] = s_.value / max(c_.value, 1) * 1e3
+        check(L.nekb_prof_enable(0))
+        del os.environ["NEKB_AX_AFFINE"]
+        g_s = max_over_ranks(g_s)
+        gi = max(1, min(a.steps, 2)) * a.maxit
+        general = {"value": gi * E_glob * NDOF / g_s / 1e9, "unit": "GDOF/s", "kernel_ms_per_iteration": gprof,
+                   "ax_roofline_frac": WORDS_AX_CG * 8 * NXYZ * case.nel / (gprof["ax"] * 1e-3) / 1e9 / peaks()[0] if gprof["ax"] > 0 else None,
+                   "what": "the same solve with NEKB_AX_AFFINE=0: six factors streamed per node (ax_cg_kernel, 12 words per point), "
+                           "as for deformed elements"}
 
     # ---- end to end through cggos_ with host buffers -----------------------------------------------------------------
     e2e = None
@@ -321,6 +349,10 @@ def main():
     ax_words = WORDS_AX_CG if fused else WORDS_AX
     ax_name = ("ax_cg_kernel<8,3,2> (u += alpha p; p = r + beta p; w = A p; pap -- 12 words/pt)" if fused
                else "ax_tma_kernel<8,3,2> (w = A p with fused pap -- 8 words/pt)")
+    if affine and fused:
+        ax_words = WORDS_AX_CG - 6.0
+        ax_name = ("ax_cg_affine_kernel<8,4,3> (u += alpha p; p = r + beta p; w = A p; pap; the six factors rebuilt from one "
+                   "64-byte record per element: 6 words/pt + 64 B/element)")
     ax_bytes = ax_words * 8 * NXYZ * case.nel                      # per launch (this rank's elements)
     ax_gbs = ax_bytes / (ax_s / max(ax_n, 1)) / 1e9 if ax_s > 0 else None
     iter_gbs = WORDS_ITER * 8 * NXYZ * case.nel * iters / dev_s / 1e9   # whole iteration, per GPU
@@ -330,7 +362,10 @@ def main():
         "warmup": warmup, "ms_per_step": dev_s / a.steps * 1e3, "higher_is_better": True, "scaling": a.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
         "relerr": relerr, "wall_ms_per_step": wall_s / a.steps * 1e3, "gpu_launches": launches, "clocks": clocks,
-        "e2e": e2e, "parity": parity,
+        "e2e": e2e, "parity": parity, "operator_kernel": "affine elements: per-element constants" if affine else "general: per-node factors",
+        "general_geometry": general,
+        "affine_check": {"max_relative_deviation_of_the_registered_factors": float(L.nekb_ax_affine_deviation()),
+                         "accepted_up_to": 3e-12} if hasattr(L, "nekb_ax_affine_deviation") else None,
         "roofline": {"bound": "hbm", "kernel": ax_name, "achieved": ax_gbs, "peak": peak,
                      "unit": "GB/s", "frac": (ax_gbs / peak) if ax_gbs else None, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ax_bytes, "mean_launch_ms": ax_s / max(ax_n, 1) * 1e3,
@@ -339,10 +374,11 @@ def main():
                      "whole_iteration": {"achieved": iter_gbs, "frac": iter_gbs / peak,
                                          "algorithmic_bytes_per_element_iteration": WORDS_ITER * 8 * NXYZ,
                                          "accounting": "SURVEY 8(d): 19.445 words per point (unfused kernel sequence)",
-                                         "executed": {"achieved": iter_gbs * WORDS_ITER_EXECUTED / WORDS_ITER,
-                                                      "frac": iter_gbs * WORDS_ITER_EXECUTED / WORDS_ITER / peak,
-                                                      "bytes_per_element_iteration": WORDS_ITER_EXECUTED * 8 * NXYZ,
-                                                      "accounting": "bytes the fused path needs: 16.57 words per point"}}},
+                                         "executed": {"achieved": iter_gbs * (WORDS_ITER_EXECUTED - (6.0 if affine else 0.0)) / WORDS_ITER,
+                                                      "frac": iter_gbs * (WORDS_ITER_EXECUTED - (6.0 if affine else 0.0)) / WORDS_ITER / peak,
+                                                      "bytes_per_element_iteration": (WORDS_ITER_EXECUTED - (6.0 if affine else 0.0)) * 8 * NXYZ,
+                                                      "accounting": "bytes the fused path needs: 16.57 words per point (10.57 when the "
+                                                                    "factors are rebuilt from per-element constants)"}}},
     }
     # dram__bytes_read+write per launch of the same kernel from the committed ncu --set full captures (E = 262,144)
     if case.nel == 262144:

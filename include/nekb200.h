@@ -171,6 +171,14 @@ int nekb_set_v1mask(const double *v1mask);
  * scalars cggo reads: volvm1, voltm1 (core/MASS), param(18,22) stay at their defaults. */
 int nekb_set_ifield(int ifield);
 int nekb_set_field_handle(int ifield, int gs_handle);
+/* 1 when the registered geometric factors are, on every element and to 1e-13, a per-element constant times w_i w_j w_k
+ * (affine elements: every genbox brick) and the fused BP5 operator kernel therefore reads six constants per element instead
+ * of six factors per node (csrc/ax.cuh ax_cg_affine_kernel); 0 otherwise or with NEKB_AX_AFFINE=0.  The arithmetic is that
+ * of core/hmholtz.f:191-217 / bp5.usr:1278-1341 with G_ab(i,j,k) written as c_ab * w3(i,j,k). */
+int nekb_ax_affine_active(void);
+/* Largest relative deviation of a registered factor from (element constant) * w3 found by the last check: the rounding noise
+ * of the numerical differentiation behind the factors (2e-12 on a 64^3 box) for affine elements, O(1) for deformed ones. */
+double nekb_ax_affine_deviation(void);
 /* Residual history of the most recent cggo (rows of 3: rtz1, rbn2, rho per executed check, core/hmholtz.f:754-802) or
  * hmh_gmres (rows of 1: rnorm per iteration, core/gmres.f:486-498) solve, whichever entry point ran it -- the
  * numbers the reference prints per iteration and keeps nowhere.  out may be NULL to query the shape. */

@@ -459,6 +459,263 @@ __global__ void __launch_bounds__(NX *NX *GROUPS, 1)
     }
 }
 
+// ---------------------------------------------------------------------------------------------- kernel v4 (affine elements)
+// On an affine element (a parallelepiped: every element of a genbox mesh, uniform or stretched) the Jacobian matrix is
+// constant, so each of the six factors is one number per element times the quadrature weight w_i w_j w_k of the node
+// (core/coef.f:633-784: G = (cofactor products) / J * w3m1 with constant cofactors and J).  The factors of such elements
+// need not be streamed per node: the kernel below is ax_cg_kernel with the 24 KB factor block of a stage replaced by one
+// 64-byte record of six constants (HBM traffic of the kernel: 6 instead of 12 words per node).  Whether a mesh qualifies is
+// DECIDED FROM THE REGISTERED FACTORS THEMSELVES (ax_affine_ensure: every node of every element within 1e-13 of
+// constant * w3), never assumed; anything else keeps the general kernel.
+constexpr int AFF_REC = 8;   // doubles per element record (6 used)
+
+template <int NX>
+__global__ void __launch_bounds__(NX *NX) ax_affine_check_kernel(const double *__restrict__ g, double *__restrict__ gc, int nel,
+                                                                unsigned long long *maxdev_bits)
+{
+    constexpr int N2 = NX * NX, N3 = NX * NX * NX;
+    __shared__ double s_part[6][N2];
+    __shared__ double s_ref[6];
+    __shared__ double s_max;
+    const int e = blockIdx.x, ij = threadIdx.x, i = ij % NX, j = ij / NX;
+    const double *ge = g + (size_t)e * 6 * N3;
+    // constants = mean over the tile of G_c / w3 (the registered factors carry the rounding noise of the numerical
+    // differentiation they come from -- up to 2e-12 relative on a 64^3 box; the mean halves what one node would carry)
+    for (int c = 0; c < 6; c++) {
+        double a = 0.0;
+        for (int k = 0; k < NX; k++) a += ge[c * N3 + k * N2 + ij] / (c_w[i] * c_w[j] * c_w[k]);
+        s_part[c][ij] = a;
+    }
+    __syncthreads();
+    if (ij < 6) {
+        double a = 0.0;
+        for (int t = 0; t < N2; t++) a += s_part[ij][t];
+        s_ref[ij] = a / (double)N3;
+    }
+    __syncthreads();
+    if (ij == 0) {
+        double m = 0.0;
+        for (int c = 0; c < 6; c++) m = fmax(m, fabs(s_ref[c]));
+        s_max = m;
+        for (int c = 0; c < 6; c++) gc[(size_t)e * AFF_REC + c] = s_ref[c];
+        gc[(size_t)e * AFF_REC + 6] = gc[(size_t)e * AFF_REC + 7] = 0.0;
+    }
+    __syncthreads();
+    double dev = s_max > 0.0 ? 0.0 : 1.0;
+    for (int k = 0; k < NX; k++) {
+        const double w3 = c_w[i] * c_w[j] * c_w[k];
+        for (int c = 0; c < 6; c++) {
+            const double d = fabs(ge[c * N3 + k * N2 + ij] - s_ref[c] * w3) / (s_max * w3);
+            dev = (d > dev || d != d) ? (d != d ? 1.0 : d) : dev;
+        }
+    }
+    atomicMax(maxdev_bits, (unsigned long long)__double_as_longlong(dev));   // non-negative doubles order like their bits
+}
+
+template <int NX, int GROUPS, int STAGES>
+struct AxCgAffSmem {
+    static constexpr int N2 = NX * NX, N3 = NX * NX * NX;
+    static constexpr size_t stage_doubles = 3 * (size_t)N3 + AFF_REC;          // r, p, u tiles + the element's constants
+    static constexpr size_t group_doubles = STAGES * stage_doubles;
+    static constexpr size_t bytes = GROUPS * group_doubles * sizeof(double) + GROUPS * STAGES * sizeof(uint64_t) + 64 * sizeof(double);
+};
+
+template <int NX, int GROUPS, int STAGES, bool FIRST>
+__global__ void __launch_bounds__(NX *NX *GROUPS, 1)
+    ax_cg_affine_kernel(const double *__restrict__ r, double *__restrict__ p, double *__restrict__ u,
+                        const double *__restrict__ gc, double *__restrict__ w, int nel, const CgScalars *__restrict__ sc,
+                        double *__restrict__ partials, unsigned *counter, double *pap_out)
+{
+    using L = AxCgAffSmem<NX, GROUPS, STAGES>;
+    constexpr int N2 = L::N2, N3 = L::N3;
+    constexpr uint32_t T_BYTES = N3 * sizeof(double), C_BYTES = AFF_REC * sizeof(double);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *smem = reinterpret_cast<double *>(smem_raw);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + GROUPS * L::group_doubles);
+    double *s_red = reinterpret_cast<double *>(bars + GROUPS * STAGES);
+
+    const int grp = threadIdx.x / N2, ij = threadIdx.x % N2, i = ij % NX, j = ij / NX;
+    double *gbase = smem + grp * L::group_doubles;
+    uint64_t *full = bars + grp * STAGES;
+    const bool leader = ij == 0;
+
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < GROUPS * STAGES; q++) mbar_init(&bars[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const double alpha = FIRST ? 0.0 : sc->alpha;
+    const double beta = FIRST ? 0.0 : sc->work[1] / sc->rtz1;
+    const double wij = c_w[i] * c_w[j];
+
+    double Di[NX], Dj[NX], DTi[NX], DTj[NX];
+#pragma unroll
+    for (int m = 0; m < NX; m++) {
+        Di[m] = c_D[i * NX + m];
+        Dj[m] = c_D[j * NX + m];
+        DTi[m] = c_D[m * NX + i];
+        DTj[m] = c_D[m * NX + j];
+    }
+
+    const int first = blockIdx.x * GROUPS + grp, stride = gridDim.x * GROUPS;
+    auto issue = [&](int stage, int e) {
+        double *st = gbase + stage * L::stage_doubles;
+        mbar_expect_tx(&full[stage], C_BYTES + (FIRST ? 1 : 3) * T_BYTES);
+        bulk_g2s(st + 3 * N3, gc + (size_t)e * AFF_REC, C_BYTES, &full[stage]);
+        bulk_g2s(st, r + (size_t)e * N3, T_BYTES, &full[stage]);
+        if (!FIRST) {
+            bulk_g2s(st + N3, p + (size_t)e * N3, T_BYTES, &full[stage]);
+            bulk_g2s(st + 2 * N3, u + (size_t)e * N3, T_BYTES, &full[stage]);
+        }
+    };
+    if (leader) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) {
+            const int e = first + s * stride;
+            if (e < nel) issue(s, e);
+        }
+    }
+
+    double pap = 0.0;
+    int it = 0;
+    for (int e = first; e < nel; e += stride, it++) {
+        const int stage = it % STAGES;
+        const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&full[stage], parity);
+        double *sr = gbase + stage * L::stage_doubles, *sp = sr + N3, *su = sr + 2 * N3;
+        const double *sgc = sr + 3 * N3;
+        const double *sf = FIRST ? sr : sp;  // the tile holding the search direction p of this iteration
+        // the six constants of the element, scaled by this thread's w_i w_j (w_k follows per plane)
+        const double c0 = sgc[0] * wij, c1 = sgc[1] * wij, c2 = sgc[2] * wij, c3 = sgc[3] * wij, c4 = sgc[4] * wij, c5 = sgc[5] * wij;
+
+        double ucol[NX], wcol[NX];
+        double *__restrict__ pe = p + (size_t)e * N3;
+        if (FIRST) {
+#pragma unroll
+            for (int k = 0; k < NX; k++) {
+                ucol[k] = sr[k * N2 + ij];
+                pe[k * N2 + ij] = ucol[k];
+                wcol[k] = 0.0;
+            }
+        } else {
+            double *__restrict__ ue = u + (size_t)e * N3;
+#pragma unroll
+            for (int k = 0; k < NX; k++) {
+                const double po = sp[k * N2 + ij];
+                const double pn = fma(beta, po, sr[k * N2 + ij]);
+                ue[k * N2 + ij] = fma(alpha, po, su[k * N2 + ij]);
+                sp[k * N2 + ij] = pn;
+                pe[k * N2 + ij] = pn;
+                ucol[k] = pn;
+                wcol[k] = 0.0;
+            }
+            group_barrier(1 + grp, N2);  // the p tile is complete
+        }
+        // r and u tiles are dead once p is built (FIRST: the unused p and u slots): they take the r- and s-fluxes
+        double *swr = FIRST ? sp : sr, *sws = su;
+#pragma unroll
+        for (int k = 0; k < NX; k++) {
+            const int q = k * N2 + ij;
+            const double wk = c_w[k];
+            double ur = 0.0, us = 0.0, ut = 0.0;
+#pragma unroll
+            for (int m = 0; m < NX; m++) {
+                ur = fma(Di[m], sf[k * N2 + j * NX + m], ur);
+                us = fma(Dj[m], sf[k * N2 + m * NX + i], us);
+                ut = fma(c_D[k * NX + m], ucol[m], ut);
+            }
+            // G_ab(i,j,k) = c_ab * w_i w_j w_k: the same three products as the general kernel, with the common weight last
+            const double wr = fma(c0, ur, fma(c1, us, c2 * ut)) * wk;
+            const double ws = fma(c1, ur, fma(c3, us, c4 * ut)) * wk;
+            const double wt = fma(c2, ur, fma(c4, us, c5 * ut)) * wk;
+            swr[q] = wr;
+            sws[q] = ws;
+#pragma unroll
+            for (int m = 0; m < NX; m++) wcol[m] = fma(c_D[k * NX + m], wt, wcol[m]);
+        }
+        group_barrier(1 + grp, N2);
+#pragma unroll
+        for (int k = 0; k < NX; k++) {
+            double acc = wcol[k];
+#pragma unroll
+            for (int m = 0; m < NX; m++) {
+                acc = fma(DTi[m], swr[k * N2 + j * NX + m], acc);
+                acc = fma(DTj[m], sws[k * N2 + m * NX + i], acc);
+            }
+            wcol[k] = acc;
+        }
+        double *__restrict__ we = w + (size_t)e * N3;
+#pragma unroll
+        for (int k = 0; k < NX; k++) {
+            we[k * N2 + ij] = wcol[k];
+            pap = fma(ucol[k], wcol[k], pap);
+        }
+        group_barrier(1 + grp, N2);
+        if (leader) {
+            const int en = e + STAGES * stride;
+            if (en < nel) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(stage, en);
+            }
+        }
+    }
+    if (pap_out != nullptr) {
+        double b = block_reduce(pap, s_red);
+        grid_reduce(b, partials, counter, s_red, [=](double t) { *pap_out = t; });
+    }
+}
+
+// Decides (once per registered geometry) whether every element is affine and, if so, extracts the per-element constants.
+inline bool ax_affine_ensure()
+{
+    Ctx &c = ctx();
+    const char *env = getenv("NEKB_AX_AFFINE");      // read per solve: 0 keeps the general (per-node factors) kernel
+    if (env && atoi(env) == 0) return false;
+    if (c.affine_gen == c.geom_gen) return c.affine;
+    c.affine_gen = c.geom_gen;
+    c.affine = false;
+    if (c.nx != 8 || !c.have_geom || !c.have_gll || c.nelt < 1) return false;
+    NEKB_CUDA(cudaMemcpyToSymbolAsync(c_w, c.w_host.data(), sizeof(double) * c.nx, 0, cudaMemcpyHostToDevice, c.stream));
+    c.gc.alloc((size_t)c.nelt * AFF_REC);
+    DevBuf<unsigned long long> md;
+    md.alloc(1);
+    md.zero(c.stream);
+    ax_affine_check_kernel<8><<<c.nelt, 64, 0, c.stream>>>(c.g.p, c.gc.p, c.nelt, md.p);
+    NEKB_LAUNCHED();
+    unsigned long long bits = 0;
+    md.download(&bits, 1, c.stream);
+    memcpy(&c.affine_maxdev, &bits, sizeof(double));
+    // Tolerance: a deviation d of the factors moves A u by about 0.3 d (measured); the parity budget of one
+    // application is 1e-12, so the affine kernel is used only while d <= 3e-12 (NEKB_AX_AFFINE_TOL overrides).
+    const char *te = getenv("NEKB_AX_AFFINE_TOL");
+    const double tol = te ? atof(te) : 3e-12;
+    c.affine = c.affine_maxdev <= tol;
+    if (!c.affine) c.gc.release();
+    return c.affine;
+}
+
+template <int NX, int GROUPS, int STAGES>
+inline void launch_ax_cg_affine(const double *r, double *p, double *u, double *w, int nel, bool first, double *pap_out)
+{
+    Ctx &c = ctx();
+    using L = AxCgAffSmem<NX, GROUPS, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        NEKB_CUDA(cudaFuncSetAttribute(ax_cg_affine_kernel<NX, GROUPS, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes));
+        NEKB_CUDA(cudaFuncSetAttribute(ax_cg_affine_kernel<NX, GROUPS, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes));
+        configured = true;
+    }
+    const int grid = grid_for((nel + GROUPS - 1) / GROUPS, 1);
+    if (first)
+        ax_cg_affine_kernel<NX, GROUPS, STAGES, true><<<grid, NX * NX * GROUPS, L::bytes, c.stream>>>(
+            r, p, u, c.gc.p, w, nel, c.sc.p, c.partials.p, &c.sc.p->counter[0], pap_out);
+    else
+        ax_cg_affine_kernel<NX, GROUPS, STAGES, false><<<grid, NX * NX * GROUPS, L::bytes, c.stream>>>(
+            r, p, u, c.gc.p, w, nel, c.sc.p, c.partials.p, &c.sc.p->counter[0], pap_out);
+    NEKB_LAUNCHED();
+}
+
 template <int NX, int GROUPS, int STAGES>
 inline void launch_ax_cg(const double *r, double *p, double *u, double *w, int nel, bool first, double *pap_out)
 {

@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(CG_THREADS)
 
 // bp5.usr:853-866 without the u update: alpha = rpp1/pap ; r -= alpha*(mask*ap) ; (r,z) = sum mult r r.
 // The last block stores alpha, rotates the (r,z) scalars and advances the iteration counter.
-__global__ void __launch_bounds__(CG_THREADS)
+__global__ void __launch_bounds__(CG_THREADS, 6)   // cg_grid launches 6 CTAs per SM: all of them must be resident at once
     cggos_update2_kernel(double *__restrict__ r, const double *__restrict__ ap, const unsigned char *__restrict__ code,
                          int64_t n, CgScalars *sc, double *partials)
 {
@@ -486,8 +486,8 @@ __global__ void __launch_bounds__(CG_THREADS)
 // irregular part -- 216 face partners and 80 edge / corner values per element -- is fetched by ALL threads in one uniform,
 // fully independent sweep into shared memory (no divergent dependent loads in the streaming part), then every thread
 // patches its quad from shared memory.  Bits as cggos_update3_kernel / the stock pair.
-template <int EPB>
-__global__ void __launch_bounds__(128 * EPB, 4)
+template <int EPB, int MINB>
+__global__ void __launch_bounds__(128 * EPB, MINB)
     cggos_update4_kernel(double *__restrict__ r, const double *__restrict__ ap, const unsigned char *__restrict__ code,
                          const FaceLink *__restrict__ ftab, const int32_t *__restrict__ etab, const double *__restrict__ gval,
                          int nel, CgScalars *sc, double *partials)
@@ -610,7 +610,7 @@ inline int axcg_variant()
 inline int gs_fuse_update_enabled()  // read per solve, so one process can time both forms
 {
     const char *e = getenv("NEKB_GS_FUSE_UPDATE");
-    return e ? atoi(e) : 3;
+    return e ? atoi(e) : 4;
 }
 inline int cg_fused_enabled()
 {
@@ -651,17 +651,28 @@ inline int cggos_run_fused(const CggosArgs &a, int maxit, double *hist_host, boo
 
     // gather form of dssum inside the update kernel: one rank only (no remote members to wait for)
     // (1 = every group gathered by the update kernel; 2 = pairs gathered, edge / corner groups assembled in place first)
-    // 3 (default) = structured gather: face pairs through per-face affine links, edge / corner groups through gval, groups
-    // with remote members in place + the inter-rank exchange; 0 = the stock pair gs_op + update2
+    // 3 / 4 (default 4) = structured gather: face pairs through per-face affine links, edge / corner groups through gval,
+    // groups with remote members in place + the inter-rank exchange (3: node-organised update kernel, 4: element-organised);
+    // 0 = the stock pair gs_op + update2
     const int gmode = gs_fuse_update_enabled();
     const bool gather = (gmode == 1 || gmode == 2) && c.nranks == 1 && h.nshared == 0;
     if (gather) gs_ensure_link(h, gmode);
     const bool structured = (gmode == 3 || gmode == 4) && gs_ensure_struct(h);
+    const bool affine = ax_affine_ensure();   // decided from the registered factors (all elements affine to 1e-13)
     cggos_init2_kernel<<<grid, CG_THREADS, 0, s>>>(a.u, r.p, a.rhs, a.mult, n, sc, c.partials.p + 1 * CG_PART_STRIDE);
     NEKB_LAUNCHED();
     comm_allreduce_sum(&sc->work[1], 1);
     for (int iter = 1; iter <= maxit; iter++) {
         prof_begin(PROF_AX);
+        if (affine) {   // per-element constants instead of per-node factors (ax.cuh kernel v4); stages are 12 KB
+            switch (axcg_variant()) {
+                case 1: launch_ax_cg_affine<8, 4, 4>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
+                case 2: launch_ax_cg_affine<8, 6, 3>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
+                case 3: launch_ax_cg_affine<8, 8, 2>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
+                case 4: launch_ax_cg_affine<8, 3, 4>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
+                default: launch_ax_cg_affine<8, 4, 3>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
+            }
+        } else
         switch (axcg_variant()) {  // element groups per CTA x ring stages (36 KB each): bytes in flight vs. threads per SM
             case 1: launch_ax_cg<8, 2, 3>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
             case 2: launch_ax_cg<8, 2, 2>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
@@ -683,9 +694,24 @@ inline int cggos_run_fused(const CggosArgs &a, int maxit, double *hist_host, boo
             prof_end(PROF_GS);
             prof_begin(PROF_UPDATE);
             if (gmode == 4) {
-                const int g4 = grid_for((a.nel + 1) / 2, 4);   // 4 CTAs of 256 threads per SM (64 registers)
-                cggos_update4_kernel<2><<<g4, 256, 0, s>>>(r.p, ap.p, c.wcode.p, h.ftab.p, h.etab.p, h.gval.p, a.nel, sc,
-                                                           c.partials.p + 2 * CG_PART_STRIDE);
+                // resident CTAs per SM x elements per CTA = elements in flight per SM (the kernel is latency-bound: ncu
+                // profiles/r2g: DRAM 51 % active at 3.49 GB moved, which is within 4 % of the minimum)
+                static int var = -1;
+                if (var < 0) {
+                    const char *e = getenv("NEKB_UPD4_VARIANT");
+                    var = e ? atoi(e) : 3;   // measured (profiles/r2i, r2k): one element per 128-thread CTA, 12 CTAs per SM
+                }
+#define NEKB_UPD4(EPBV, MINBV)                                                                                               \
+    cggos_update4_kernel<EPBV, MINBV><<<grid_for((a.nel + EPBV - 1) / EPBV, MINBV), 128 * EPBV, 0, s>>>(                      \
+        r.p, ap.p, c.wcode.p, h.ftab.p, h.etab.p, h.gval.p, a.nel, sc, c.partials.p + 2 * CG_PART_STRIDE)
+                switch (var) {
+                    case 0: NEKB_UPD4(2, 4); break;
+                    case 1: NEKB_UPD4(2, 6); break;
+                    case 2: NEKB_UPD4(1, 8); break;
+                    case 4: NEKB_UPD4(4, 3); break;
+                    default: NEKB_UPD4(1, 12); break;
+                }
+#undef NEKB_UPD4
             } else
                 cggos_update3_kernel<<<grid, CG_THREADS, 0, s>>>(r.p, ap.p, c.wcode.p, h.ftab.p, h.etab.p, h.gval.p, n, sc,
                                                                  c.partials.p + 2 * CG_PART_STRIDE);

@@ -8,6 +8,8 @@ constexpr int MAX_NX = 16;
 
 // Derivative matrix, row-major: c_D[a * nx + b] = D(a,b) = dxm1(a,b) (core/DXYZ:4).
 __constant__ double c_D[MAX_NX * MAX_NX];
+__constant__ double c_z[MAX_NX];   // GLL points  (uploaded by setup.cuh upload_gll_constants / ax.cuh ax_affine_ensure)
+__constant__ double c_w[MAX_NX];   // GLL weights
 
 // Device-side scalars of the CG drivers (one cache line region, zero-initialised).
 struct CgScalars {
@@ -125,6 +127,13 @@ struct Ctx {
     DevBuf<double> v1mask;         // bp5 mask
     std::vector<int> ifdfrm;       // empty = all deformed
     bool have_geom = false;
+    // Elements whose six factors are a per-element constant times w_i w_j w_k (affine elements: every genbox brick, stretched
+    // or not): the BP5 operator kernel then reads 6 doubles per ELEMENT instead of 6 per NODE (ax.cuh ax_cg_affine_kernel).
+    int geom_gen = 0;              // bumped whenever `g` changes
+    int affine_gen = -1;           // geom_gen the verdict below belongs to
+    bool affine = false;           // every element passed the test
+    double affine_maxdev = 0.0;    // largest relative deviation of a registered factor from constant * w3 (last check)
+    DevBuf<double> gc;             // [nelt][8]: rr,rs,rt,ss,st,tt constants (+2 pad: 64-byte records for bulk copies)
     int ifield = 1;
     int gsh_fld[32];
     int istep = 0;

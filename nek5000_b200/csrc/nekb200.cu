@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(CG_THREADS)
 
 void apply_ifdfrm()
 {
+    ctx().geom_gen++;   // every registration of factors ends here
     Ctx &c = ctx();
     if (!c.have_geom || c.ifdfrm.empty()) return;
     NEKB_REQUIRE((int)c.ifdfrm.size() >= c.nelt, "ifdfrm shorter than nelt");
@@ -336,6 +337,7 @@ int nekb_set_geom_bp5(const double *gf)
         NEKB_LAUNCHED();
         NEKB_CUDA(cudaStreamSynchronize(c.stream));
         c.have_geom = true;
+        c.geom_gen++;
     });
 }
 int nekb_set_geom_from_xyz(const double *xm1, const double *ym1, const double *zm1, int bp5_form)
@@ -407,6 +409,13 @@ int nekb_set_ifield(int ifield)
         ctx().ifield = ifield;
     });
 }
+int nekb_ax_affine_active(void)
+{
+    int v = 0;
+    guard([&] { v = ax_affine_ensure() ? 1 : 0; });
+    return v;
+}
+double nekb_ax_affine_deviation(void) { return ctx().affine_maxdev; }
 int nekb_last_history(double *out, int64_t capacity, int *rows, int *cols)
 {
     return guard([&] {

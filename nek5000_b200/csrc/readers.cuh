@@ -67,14 +67,30 @@ inline Re2Header re2_header(FileHandle &fh)
     char hdr[81] = {0};
     fh.read_at(0, hdr, 80, ".re2 header");
     Re2Header h;
-    NEKB_REQUIRE(!strncmp(hdr, "#v00", 4) && hdr[4] >= '1' && hdr[4] <= '3', ".re2: unknown header version");
+    NEKB_REQUIRE(!strncmp(hdr, "#v00", 4) && hdr[4] >= '1' && hdr[4] <= '4', ".re2: unknown header version");
     h.version = hdr[4] - '0';
     long long a = 0, c = 0;
     int b = 0;
-    // #v001: (a5,i9,i3,i9); #v002/#v003: (a5,i9,i3,i9) for nelgt < 10^9 files written by genbox/reatore2 (free-format read)
-    NEKB_REQUIRE(sscanf(hdr + 5, "%lld %d %lld", &a, &b, &c) == 3, ".re2: cannot parse the header");
+    if (h.version == 4) {
+        // '#v004': list-directed read of version, nelgt, ldimr, nelgv, nBCre2 (core/reader_re2.f:585-586)
+        long long nbc4 = 0;
+        NEKB_REQUIRE(sscanf(hdr + 5, "%lld %d %lld %lld", &a, &b, &c, &nbc4) >= 3, ".re2: cannot parse the #v004 header");
+    } else {
+        // format (a5,i9,i3,i9) (core/reader_re2.f:588-590): FIXED columns -- with nelgt >= 10^8 the i3 and i9 fields abut
+        // ('  3123456789'), so the fields are cut by position, not by white space
+        auto field = [&](int lo, int hi) -> long long {
+            char buf[16] = {0};
+            memcpy(buf, hdr + lo, (size_t)(hi - lo));
+            char *end = nullptr;
+            const long long v = strtoll(buf, &end, 10);
+            while (end && *end == ' ') end++;
+            NEKB_REQUIRE(end != buf && end && *end == 0, ".re2: cannot parse the header (format a5,i9,i3,i9)");
+            return v;
+        };
+        a = field(5, 14), b = (int)field(14, 17), c = field(17, 26);
+    }
     h.nelgt = a, h.ldim = b, h.nelgv = c;
-    h.wdsize = h.version == 1 ? 4 : 8;
+    h.wdsize = h.version == 1 ? 4 : 8;   // reader_re2.f:593-596
     NEKB_REQUIRE(h.ldim == 2 || h.ldim == 3, ".re2: ldim must be 2 or 3");
     float test;
     fh.read_at(80, &test, 4, ".re2 endian tag");
@@ -186,8 +202,16 @@ inline void re2_read_bc(FileHandle &fh, const Re2Header &h, const Re2Sections &s
         if (bc)
             for (int k = 0; k < 5; k++) bc[slot * 5 + k] = re2_word(p + (size_t)(2 + k) * h.wdsize, h.wdsize, h.swap);
         if (cbc) memcpy(cbc + slot * 3, p + (size_t)7 * h.wdsize, 3);
-        // (for element counts >= 10^6 in #v001 files the reference re-reads the element id from bl(1); 8-byte files carry it
-        // exactly, reader_re2.f:520-528)
+        // reader_re2.f:533-534: in a 4-byte file with nelgt >= 10^6 the first word of a periodic ('P  ') record is the
+        // partner element as an INTEGER (a real*4 cannot hold it exactly): bl(1) = buf(3) as int.  (8-byte files, :522-523, copy
+        // the same bits with copyi4, which the double read above reproduces only for the 4-byte case -- they carry the id as a
+        // double there.)
+        if (bc && h.wdsize == 4 && h.nelgt >= 1000000 && !memcmp(p + (size_t)7 * h.wdsize, "P  ", 3)) {
+            uint32_t w;
+            memcpy(&w, p + (size_t)2 * h.wdsize, 4);
+            if (h.swap) w = bswap32(w);
+            bc[slot * 5] = (double)(int32_t)w;
+        }
     }
 }
 

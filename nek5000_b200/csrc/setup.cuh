@@ -330,8 +330,7 @@ struct BoxDesc {
     double deform;
 };
 
-__constant__ double c_z[MAX_NX];   // GLL points
-__constant__ double c_w[MAX_NX];   // GLL weights
+// c_z / c_w (GLL points and weights in constant memory) are defined in ctx.cuh
 
 // Box [0,1]^3, elements x-fastest (tools/genbox; examples/bp5/genbox.in:16-20); nodes by the trilinear map of
 // core/genxyz.f:1269-1332 (tensr3 with the 2-point Lagrange weights (1-z)/2, (1+z)/2, contracted r, then s, then t).
@@ -486,6 +485,7 @@ inline void geom_from_xyz(const double *x, const double *y, const double *z, int
         NEKB_LAUNCHED();
     }
     c.have_geom = true;
+    c.geom_gen++;
     c.nelt = nel;
     if (c.nelv == 0 || c.nelv > nel) c.nelv = nel;
 }

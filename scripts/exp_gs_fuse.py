@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--m", type=int, default=64)
     ap.add_argument("--its", type=int, default=100)
     ap.add_argument("--skip-small", action="store_true", help="timing only (for an ncu capture of the large case)")
+    ap.add_argument("--modes", default="0,2,3,4", help="NEKB_GS_FUSE_UPDATE values to time (each twice)")
     a = ap.parse_args()
     from nek5000_b200 import lib, nek
     from nek5000_b200._lib import check
@@ -42,7 +43,7 @@ def main():
     m = a.m
     b = BP5(m, m, m, lx1=8)
     res = {}
-    for flag in ("0", "2", "3", "4", "0", "2", "3", "4"):
+    for flag in a.modes.split(",") * 2:
         os.environ["NEKB_GS_FUSE_UPDATE"] = flag
         b.solve(-1e-8, 5)
         check(L.nekb_prof_enable(1))

@@ -31,8 +31,12 @@ def main():
     if os.path.exists(launches):
         rows = [r for r in csv.reader(open(launches)) if len(r) > 10]
         hdr = rows[0]
-        ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
-        data = rows[1:]
+        if "Kernel Name" in hdr:
+            ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+            data = rows[1:]
+        else:                       # a tail of the file (the whole list is too large to bring back): ncu's fixed column order
+            ki, vi = 4, 14
+            data = rows
         # the last cggos solve = the timed step: everything after the last init kernel
         marker = os.environ.get("NCU_STEP_MARKER", "cggos_init")   # first kernel of a solve (ophinv: hcg_prep_kernel)
         last = max((i for i, r in enumerate(data) if marker in r[ki]), default=0)

@@ -93,9 +93,14 @@ def main():
     assert it.value == int(g["it"][0]), ("GMRES iteration count", it.value, int(g["it"][0]))
     assert dx <= 1e-8, ("GMRES solution", dx)
     # the reference's own record of the last GMRES cycle: |s_k| = rnorm_k / rnorm_{k-1} (gmres.f:486-493)
+    # (hist[i-1] = rnorm after iteration i; the first ratio of a cycle starts from the recomputed restart residual, skipped)
     j = it.value - 30 * ((it.value - 1) // 30)
-    ratios = hist[it.value - j + 1:it.value + 1] / hist[it.value - j:it.value]
-    dr = np.abs(ratios[1:] - g["gmres_s"][1:j]).max() if j > 1 else 0.0
+    refh = np.zeros(j)                                          # the reference's rnorm over its last cycle, rebuilt backwards
+    refh[-1] = g["gmres_rnorm_last"][0]
+    for k in range(j - 1, 0, -1):
+        refh[k - 1] = refh[k] / g["gmres_s"][k]
+    dr = np.abs(refh - hist[it.value - j:it.value]).max() / hist[0]
+    assert dr <= 1e-9, ("GMRES residual history against the reference's Givens data", dr)
     l2 = torch.tensor([float(np.sum(x * x * loc(case.mult)))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(l2)
@@ -137,7 +142,7 @@ def main():
         sync()
         best = min(best, maxr(e0.elapsed_time(e1)))
     print(f"MGPU-CHANNEL-OK rank {rank} of {world}: nel={nel} gmres its={it.value} rel(z)={dz:.2e} rel(x)={dx:.2e} "
-          f"max|s_k - ref|={dr:.1e}", flush=True)
+          f"max|rnorm - ref|/rnorm_1={dr:.1e}", flush=True)
     if rank == 0:
         info = nek.h1mg_info()
         print("CHANNEL-JSON " + json.dumps({
@@ -146,7 +151,7 @@ def main():
             "n_gpus": world, "elements_per_gpu": nel, "h1mg_setup_s": setup_s, "h1mg_solve_ms": mg_ms,
             "h1mg_solve_launches": mg_launches, "gmres_iterations": it.value, "gmres_ms": best,
             "gmres_ms_per_iteration": best / max(it.value, 1), "reference_iterations": int(g["it"][0]),
-            "parity": {"h1mg_solve_max_rel": dz, "gmres_solution_max_rel": dx, "gmres_givens_max_abs": dr,
+            "parity": {"h1mg_solve_max_rel": dz, "gmres_solution_max_rel": dx, "gmres_history_max_rel_to_first": dr,
                        "x_weighted_l2": float(np.sqrt(l2.item())), "reference_x_l2_unweighted": float(g["x_l2"][0])},
             "h1mg_info": info}),
             flush=True)

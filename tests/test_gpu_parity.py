@@ -234,6 +234,33 @@ def test_structured_gather_update_is_bit_identical_to_gs_op_plus_update(nek, dim
     assert relmax(us[1], uref) <= TOL_HIST
 
 
+def test_affine_operator_kernel_is_chosen_from_the_factors_and_agrees_with_the_general_one(nek, monkeypatch):
+    """ax_cg_affine_kernel (six constants per element instead of six factors per node) may only run when the REGISTERED
+    factors say so: uniform and stretched bricks qualify, a deformed mesh does not.  Where it runs, the solve agrees with the
+    general kernel to rounding (the factor c * w3 is formed in another order) and with the oracle as the general one does."""
+    from nek5000_b200 import lib
+    stretch = lambda xc, yc, zc: (xc, np.tanh(1.7 * (2 * yc - 1)) / np.tanh(1.7), 0.5 * zc * (1 + zc))
+    for kw, want in ((dict(), 1), (dict(vertex_map=stretch, rescale=False), 1), (dict(deform=0.05), 0)):
+        case = oracle.Case(3, 3, 2, nx=8, **kw)
+        register(nek, case, bp5=True)
+        h, _ = nek.setupds(8, case.nel, case.vertex)
+        nek.set_field_handle(1, h)
+        nek.set_ifield(1)
+        assert lib().nekb_ax_affine_active() == want, kw
+        e1, r1 = case.bp5_problem()
+        uref, itref, hist = case.cggos(r1, e1, tol=-1e-8, maxit=30, history=True)
+        us = []
+        for flag in ("1", "0"):
+            monkeypatch.setenv("NEKB_AX_AFFINE", flag)
+            u = np.zeros(case.n)
+            assert nek.cggos(u, r1, e1, case.mult, np.ones(case.n), -1e-8, 30, "bp5") == 30
+            us.append(u)
+        monkeypatch.delenv("NEKB_AX_AFFINE")
+        assert relmax(us[0], us[1]) <= (1e-12 if want else 0.0)
+        assert relmax(us[0], uref) <= TOL_HIST and relmax(us[1], uref) <= TOL_HIST
+        nek.fgslib_gs_free(h)
+
+
 @pytest.mark.parametrize("ifh2", [False, True])
 def test_cggo_iterations_and_solution(nek, ifh2):
     """Stock cggo (hmholtz.f:611-846).  CG amplifies rounding differences exponentially with the iteration number
