@@ -670,6 +670,8 @@ inline int cggos_run_fused(const CggosArgs &a, int maxit, double *hist_host, boo
                 case 2: launch_ax_cg_affine<8, 6, 3>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
                 case 3: launch_ax_cg_affine<8, 8, 2>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
                 case 4: launch_ax_cg_affine<8, 3, 4>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
+                case 5: launch_ax_cg_affine<8, 5, 3>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
+                case 6: launch_ax_cg_affine<8, 5, 2>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
                 default: launch_ax_cg_affine<8, 4, 3>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
             }
         } else

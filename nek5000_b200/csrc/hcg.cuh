@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(NX *NX *NRHS *PIPES, 1)
 
 // rho_c = (w_c, p_c)_{mask_c * mult}   (hmholtz.f:798-801; the mask is applied where w is consumed, w is not rewritten)
 template <int NRHS>
-__global__ void __launch_bounds__(CG_THREADS)
+__global__ void __launch_bounds__(CG_THREADS, 4)   // 4 CTAs per SM resident: the grid is sized for exactly that (hcg_run)
     hcg_rho_kernel(HcgPtrs P, const unsigned char *__restrict__ mcode, const double *__restrict__ mult, int64_t n, HcgScalars *sc,
                    double *partials)
 {
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(CG_THREADS)
 // (z,r)_mult with z = d r, and (r,r)_{mult binv}.  FIRST: r is the right-hand side, nothing to subtract.
 // Two nodes per thread and step (16-byte loads, all loads of a step independent of the mask byte).
 template <int NRHS, bool FIRST>
-__global__ void __launch_bounds__(CG_THREADS)
+__global__ void __launch_bounds__(CG_THREADS, 4)   // 4 CTAs per SM resident: the grid is sized for exactly that (hcg_run)
     hcg_update_kernel(HcgPtrs P, const unsigned char *__restrict__ mcode, const double *__restrict__ mult, const double *__restrict__ d,
                       const double *__restrict__ binv, int64_t n, HcgScalars *sc, double *partials, double *hist, int hist_stride)
 {
@@ -418,7 +418,11 @@ inline bool hcg_run(int nrhs, double *const *x, const double *const *f, const do
     HcgState &S = hcg_state();
     cudaStream_t s = c.stream;
     const int64_t n = (int64_t)nel * c.nxyz;
-    const int maxcg = 900, niter = maxit < maxcg ? maxit : maxcg, grid = cg_grid(n);
+    const int maxcg = 900, niter = maxit < maxcg ? maxit : maxcg;
+    // streaming kernels of this file: 4 resident CTAs per SM (<= 64 registers), one wave (round 1 launched 6 per SM of a
+    // 90-register kernel: two resident, three waves, 50 % of the DRAM bandwidth)
+    int grid = cg_grid(n);
+    if (grid > c.num_sms * 4) grid = c.num_sms * 4;
     NEKB_REQUIRE(nrhs == 1 || nrhs == 3, "hcg: 1 or 3 right-hand sides");
     GsMap &h = gs_get(gs_handle);
     NEKB_REQUIRE(h.n == n, "hcg: gs handle was set up for a different vector length");
