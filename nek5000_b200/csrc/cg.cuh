@@ -482,6 +482,86 @@ __global__ void __launch_bounds__(CG_THREADS)
     });
 }
 
+// Branch-free form of cggos_update3_kernel: every thread runs the SAME instruction stream over the four nodes of its quad --
+// two predicated table loads per node (face link / edge slot), then two predicated value loads (partner / gval) -- so the
+// 2 x 8 irregular loads of a thread are issued in two independent batches instead of inside divergent, serialised branches,
+// and no shared memory or barrier is involved.  Bits as the other forms.
+__global__ void __launch_bounds__(CG_THREADS, 4)
+    cggos_update5_kernel(double *__restrict__ r, const double *__restrict__ ap, const unsigned char *__restrict__ code,
+                         const FaceLink *__restrict__ ftab, const int32_t *__restrict__ etab, const double *__restrict__ gval,
+                         int64_t n, CgScalars *sc, double *partials)
+{
+    __shared__ double red[33];
+    __shared__ double wtab[128];
+    const double pap = sc->work[0], rz = sc->work[1];
+    const double alpha = rz / pap;
+    if (threadIdx.x < 128) wtab[threadIdx.x] = threadIdx.x ? 1.0 / (double)threadIdx.x : 0.0;
+    __syncthreads();
+    double s = 0.0;
+    const int64_t n4 = n >> 2;
+    double2 *r2 = reinterpret_cast<double2 *>(r);
+    const double2 *a2 = reinterpret_cast<const double2 *>(ap);
+    const uchar4 *c4 = reinterpret_cast<const uchar4 *>(code);
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n4; t += (int64_t)gridDim.x * blockDim.x) {
+        double2 ra = r2[2 * t], rb = r2[2 * t + 1];
+        const double2 aa = a2[2 * t], ab = a2[2 * t + 1];
+        const uchar4 c = c4[t];
+        double w[4] = {aa.x, aa.y, ab.x, ab.y};
+        const int l4 = (int)(t & 127);
+        const int64_t el = t >> 7;
+        const int i0 = (l4 & 1) << 2, j = (l4 >> 1) & 7, k = l4 >> 4;
+        const int bj = (j == 0 || j == 7), bk = (k == 0 || k == 7);
+        const int hj = j == 7, hk = k == 7;
+        FaceLink L[4];
+        int g[4];
+        int fa[4], fb[4];
+        // level 1: the tables
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = i0 + q;
+            const int bi = (i == 0 || i == 7), hi = i == 7;
+            const int nb = bi + bj + bk;
+            const int f = bi ? hi : (bj ? 2 + hj : 4 + hk);
+            fa[q] = bi ? j : i;                  // in-face coordinates, lower axis first: x-face (j,k), y-face (i,k), z-face (i,j)
+            fb[q] = (bi || bj) ? k : j;
+            L[q].base = -1, L[q].sa = 0, L[q].sb = 0;
+            if (nb == 1) L[q] = ftab[el * 6 + f];
+            g[q] = -1;
+            if (nb >= 2) g[q] = etab[el * GS_ST_EDGE_SLOTS + gs_st_slot(i, j, k)];
+        }
+        // level 2: the values
+        double pv[4], gv[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            pv[q] = 0.0, gv[q] = 0.0;
+            if (L[q].base >= 0) pv[q] = ap[(int64_t)L[q].base + fa[q] * L[q].sa + fb[q] * L[q].sb];
+            if (g[q] >= 0) gv[q] = gval[g[q]];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (L[q].base >= 0) w[q] += pv[q];
+            if (g[q] >= 0) w[q] = gv[q];
+        }
+        ra.x = fma(-alpha, (c.x & 0x80) ? 0.0 : w[0], ra.x);
+        ra.y = fma(-alpha, (c.y & 0x80) ? 0.0 : w[1], ra.y);
+        rb.x = fma(-alpha, (c.z & 0x80) ? 0.0 : w[2], rb.x);
+        rb.y = fma(-alpha, (c.w & 0x80) ? 0.0 : w[3], rb.y);
+        r2[2 * t] = ra;
+        r2[2 * t + 1] = rb;
+        s = fma(wtab[c.x & 0x7f] * ra.x, ra.x, s);
+        s = fma(wtab[c.y & 0x7f] * ra.y, ra.y, s);
+        s = fma(wtab[c.z & 0x7f] * rb.x, rb.x, s);
+        s = fma(wtab[c.w & 0x7f] * rb.y, rb.y, s);
+    }
+    double b = block_reduce(s, red);
+    grid_reduce(b, partials, &sc->counter[2], red, [=](double tot) {
+        sc->rtz1 = rz;
+        sc->work[1] = tot;
+        sc->alpha = alpha;
+        sc->it = sc->it + 1;
+    });
+}
+
 // The same update, organised by element instead of by node: 128 threads own one 8^3 tile (one quad of nodes each).  The
 // irregular part -- 216 face partners and 80 edge / corner values per element -- is fetched by ALL threads in one uniform,
 // fully independent sweep into shared memory (no divergent dependent loads in the streaming part), then every thread
@@ -657,7 +737,7 @@ inline int cggos_run_fused(const CggosArgs &a, int maxit, double *hist_host, boo
     const int gmode = gs_fuse_update_enabled();
     const bool gather = (gmode == 1 || gmode == 2) && c.nranks == 1 && h.nshared == 0;
     if (gather) gs_ensure_link(h, gmode);
-    const bool structured = (gmode == 3 || gmode == 4) && gs_ensure_struct(h);
+    const bool structured = (gmode == 3 || gmode == 4 || gmode == 5) && gs_ensure_struct(h);
     const bool affine = ax_affine_ensure();   // decided from the registered factors (all elements affine to 1e-13)
     cggos_init2_kernel<<<grid, CG_THREADS, 0, s>>>(a.u, r.p, a.rhs, a.mult, n, sc, c.partials.p + 1 * CG_PART_STRIDE);
     NEKB_LAUNCHED();
@@ -695,7 +775,12 @@ inline int cggos_run_fused(const CggosArgs &a, int maxit, double *hist_host, boo
             if (h.nshared > 0 || c.nranks > 1) gs_remote_exchange(h, ap.p, 1);
             prof_end(PROF_GS);
             prof_begin(PROF_UPDATE);
-            if (gmode == 4) {
+            if (gmode == 5) {
+                int g5 = grid;
+                if (g5 > c.num_sms * 4) g5 = c.num_sms * 4;
+                cggos_update5_kernel<<<g5, CG_THREADS, 0, s>>>(r.p, ap.p, c.wcode.p, h.ftab.p, h.etab.p, h.gval.p, n, sc,
+                                                               c.partials.p + 2 * CG_PART_STRIDE);
+            } else if (gmode == 4) {
                 // resident CTAs per SM x elements per CTA = elements in flight per SM (the kernel is latency-bound: ncu
                 // profiles/r2g: DRAM 51 % active at 3.49 GB moved, which is within 4 % of the minimum)
                 static int var = -1;
