@@ -172,6 +172,7 @@ def main():
                          "(BASELINE configs[3] / SURVEY 8d: E = 262,144 on 1/2/4/8 GPUs)")
     ap.add_argument("--no-parity", action="store_true", help="skip the small multi-rank parity problem run before the timed region")
     ap.add_argument("--no-general", action="store_true", help="skip the extra timing of the general-geometry operator kernel")
+    ap.add_argument("--no-check", action="store_true", help="skip the fused-vs-kernel-per-statement answer check at bench scale")
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -315,6 +316,31 @@ def main():
                    "what": "the same solve with NEKB_AX_AFFINE=0: six factors streamed per node (ax_cg_kernel, 12 words per point), "
                            "as for deformed elements"}
 
+    # ---- the answer at bench scale: two independent code paths must agree ------------------------------------------------
+    # ("bench.py asserts nothing about the answer at bench scale".)  The oracle cannot run 500 iterations on
+    # 64^3 elements in the time a bench has, so the check is internal but independent: the same solve through the
+    # kernel-per-statement path (NEKB_CG_FUSED=0: stand-alone Ax kernel with per-node factors, gs_op in place, separate
+    # update / direction kernels -- the path the per-apply parity tests pin to the reference) against the fused path's
+    # solution and relerr.
+    answer = None
+    if not a.no_check:
+        u_fused = torch.empty(n, dtype=torch.float64, device="cuda")
+        check(L.nekb_d2d(u_fused.data_ptr(), case.devptr("u1"), n * 8))
+        torch.cuda.synchronize()
+        os.environ["NEKB_CG_FUSED"] = "0"
+        case.solve(-1e-8, a.maxit)
+        del os.environ["NEKB_CG_FUSED"]
+        barrier()
+        u_stock = torch.empty(n, dtype=torch.float64, device="cuda")
+        check(L.nekb_d2d(u_stock.data_ptr(), case.devptr("u1"), n * 8))
+        torch.cuda.synchronize()
+        d = float((u_fused - u_stock).abs().max() / u_stock.abs().max())
+        relerr_stock = case.relerr()
+        d = max_over_ranks(d)
+        answer = {"max_rel_diff_fused_vs_kernel_per_statement_path": d, "relerr_fused": relerr, "relerr_kernel_per_statement": relerr_stock,
+                  "iterations": a.maxit, "ok": bool(d <= 1e-9 and abs(relerr - relerr_stock) <= 1e-9)}
+        assert answer["ok"], answer
+
     # ---- end to end through cggos_ with host buffers -----------------------------------------------------------------
     e2e = None
     if not a.no_e2e:
@@ -363,7 +389,7 @@ def main():
         "warmup": warmup, "ms_per_step": dev_s / a.steps * 1e3, "higher_is_better": True, "scaling": a.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
         "relerr": relerr, "wall_ms_per_step": wall_s / a.steps * 1e3, "gpu_launches": launches, "clocks": clocks,
-        "e2e": e2e, "parity": parity, "operator_kernel": "affine elements: per-element constants" if affine else "general: per-node factors",
+        "e2e": e2e, "parity": parity, "answer_check": answer, "operator_kernel": "affine elements: per-element constants" if affine else "general: per-node factors",
         "general_geometry": general,
         "affine_check": {"max_relative_deviation_of_the_registered_factors": float(L.nekb_ax_affine_deviation()),
                          "accepted_up_to": 3e-12} if hasattr(L, "nekb_ax_affine_deviation") else None,

@@ -487,6 +487,7 @@ void *nekb_dev_alloc(size_t bytes);
 void nekb_dev_free(void *dev);
 int nekb_h2d(void *dev, const void *host, size_t bytes);
 int nekb_d2h(void *host, const void *dev, size_t bytes);
+int nekb_d2d(void *dst_dev, const void *src_dev, size_t bytes);
 int nekb_sync(void);
 
 #ifdef __cplusplus

@@ -90,6 +90,7 @@ def lib() -> C.CDLL:
     L.nekb_set_restol.argtypes = [C.c_int, C.c_double]
     L.nekb_last_history.argtypes = [vp, C.c_int64, ip, ip]
     L.nekb_ax_affine_deviation.restype = C.c_double
+    L.nekb_d2d.argtypes = [vp, vp, C.c_size_t]
     L.nekb_set_step_info.argtypes = [C.c_int, C.c_double, C.c_double]
     L.nekb_gs_setup.argtypes = [ip, i64p, C.c_int64]
     L.nekb_gs_setup_dev.argtypes = [ip, vp, C.c_int64]

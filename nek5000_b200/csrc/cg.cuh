@@ -692,14 +692,10 @@ inline int gs_fuse_update_enabled()  // read per solve, so one process can time 
     const char *e = getenv("NEKB_GS_FUSE_UPDATE");
     return e ? atoi(e) : 4;
 }
-inline int cg_fused_enabled()
+inline int cg_fused_enabled()   // read per solve: bench.py times the kernel-per-statement path beside the fused one
 {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("NEKB_CG_FUSED");
-        v = e ? atoi(e) : 1;
-    }
-    return v;
+    const char *e = getenv("NEKB_CG_FUSED");
+    return e ? atoi(e) : 1;
 }
 
 inline int cggos_run_fused(const CggosArgs &a, int maxit, double *hist_host, bool &used)

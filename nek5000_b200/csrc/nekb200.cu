@@ -2261,6 +2261,13 @@ int nekb_d2h(void *host, const void *dev, size_t bytes)
         NEKB_CUDA(cudaStreamSynchronize(ctx().stream));
     });
 }
+int nekb_d2d(void *dst_dev, const void *src_dev, size_t bytes)
+{
+    return guard([&] {
+        NEKB_CUDA(cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, ctx().stream));
+        NEKB_CUDA(cudaStreamSynchronize(ctx().stream));
+    });
+}
 int nekb_sync(void)
 {
     return guard([&] { NEKB_CUDA(cudaStreamSynchronize(ctx().stream)); });
