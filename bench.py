@@ -313,7 +313,7 @@ def main():
         gi = max(1, min(a.steps, 2)) * a.maxit
         general = {"value": gi * E_glob * NDOF / g_s / 1e9, "unit": "GDOF/s", "kernel_ms_per_iteration": gprof,
                    "ax_roofline_frac": WORDS_AX_CG * 8 * NXYZ * case.nel / (gprof["ax"] * 1e-3) / 1e9 / peaks()[0] if gprof["ax"] > 0 else None,
-                   "what": "the same solve with NEKB_AX_AFFINE=0: six factors streamed per node (ax_cg_kernel, 12 words per point), "
+                   "what": "the same solve with NEKB_AX_AFFINE=0: six factors streamed per node (ax_cg_mma_kernel, 12 words per point), "
                            "as for deformed elements"}
 
     # ---- the answer at bench scale: two independent code paths must agree ------------------------------------------------
@@ -374,12 +374,14 @@ def main():
     ax_s, ax_n = prof["ax"]
     fused = os.environ.get("NEKB_CG_FUSED", "1") != "0"
     ax_words = WORDS_AX_CG if fused else WORDS_AX
-    ax_name = ("ax_cg_kernel<8,3,2> (u += alpha p; p = r + beta p; w = A p; pap -- 12 words/pt)" if fused
+    ax_name = ("ax_cg_mma_kernel<6,1> (u += alpha p; p = r + beta p; w = A p; pap -- 12 words/pt; one warp per element, the "
+               "in-plane contractions on DMMA)" if fused
                else "ax_tma_kernel<8,3,2> (w = A p with fused pap -- 8 words/pt)")
     if affine and fused:
         ax_words = WORDS_AX_CG - 6.0
-        ax_name = ("ax_cg_affine_kernel<8,4,3> (u += alpha p; p = r + beta p; w = A p; pap; the six factors rebuilt from one "
-                   "64-byte record per element: 6 words/pt + 64 B/element)")
+        ax_name = ("ax_cg_affine_mma_kernel<8,2> (u += alpha p; p = r + beta p; w = A p; pap; the six factors rebuilt from one "
+                   "64-byte record per element: 6 words/pt + 64 B/element; one warp per element, the in-plane contractions "
+                   "on mma.sync.m8n8k4.f64)")
     ax_bytes = ax_words * 8 * NXYZ * case.nel                      # per launch (this rank's elements)
     ax_gbs = ax_bytes / (ax_s / max(ax_n, 1)) / 1e9 if ax_s > 0 else None
     iter_gbs = WORDS_ITER * 8 * NXYZ * case.nel * iters / dev_s / 1e9   # whole iteration, per GPU
@@ -409,8 +411,8 @@ def main():
     }
     # dram__bytes_read+write per launch of the same kernel from the committed ncu --set full captures (E = 262,144)
     if case.nel == 262144 and fused:
-        fn, key = (("r2o_ncu_traffic.json", "ax_cg_affine_kernel<8, 4, 3, 0>") if affine
-                   else ("r2g_ncu_traffic.json", "ax_cg_kernel<8, 3, 2, 0>"))
+        fn, key = (("r2t_ncu_traffic.json", "ax_cg_affine_mma_kernel<8, 2, 0>") if affine
+                   else ("r2t_ncu_traffic.json", "ax_cg_mma_kernel<6, 1, 0>"))
         pj = os.path.join(ROOT, "profiles", fn)
         if os.path.exists(pj):
             try:
@@ -419,9 +421,9 @@ def main():
             except Exception:
                 pass
     if affine and fused:
-        out["roofline"]["note"] = ("with half the bytes of the general kernel this kernel is no longer DRAM-bound: ncu shows the "
-                                   "shared-memory pipe at 71 % and DRAM at 59 % (profiles/r2o_ncu_summary.md); the general-geometry "
-                                   "kernel (general_geometry.ax_roofline_frac) is the one that sits at the HBM roofline")
+        out["roofline"]["note"] = ("round 2 moved the two in-plane contractions of this kernel to FP64 tensor-core instructions "
+                                   "(DMMA.8x8x4) after ncu showed the previous form bound by the shared-memory pipe (71 %) and "
+                                   "not by DRAM (59 %): profiles/r2o_ncu_summary.md (before), profiles/r2t_ncu_summary.md (after)")
     if a.gpus == 1 and not a.no_cpu:
         leg, kind = ref_leg(2, 1, target_s=5.0), "reference"
         if leg is None:

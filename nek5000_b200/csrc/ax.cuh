@@ -716,6 +716,426 @@ inline void launch_ax_cg_affine(const double *r, double *p, double *u, double *w
     NEKB_LAUNCHED();
 }
 
+// ---------------------------------------------------------------------------------------------- kernel v5 (affine, warp per element, DMMA)
+// ncu of kernel v4 (profiles/r2o_ncu_summary.md): DRAM 59 % active, the shared-memory pipe and the FP64 pipe busy in turn
+// (858 + 514 of 1466 cycles per element and SM, profiles/r2p_ubench_dmma.txt: LDS.64 = 2 clk, LDS.128 = 1 clk per warp
+// instruction), two warps per scheduler: the contraction, not the bandwidth, bounds it -- the case for which the north star
+// allows FP64 tensor-core instructions.  Here ONE WARP owns an element and the two in-plane contractions of every k-plane
+// (D u and u D^T, and their transposes on the way back) are mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4; same flop rate as DFMA on
+// B200, but a fragment is ONE shared-memory word per lane instead of eight):
+//   lane = (g = lane / 4, t = lane % 4) owns the two k-columns (i = g, j = t) and (i = g, j = t + 4): the C-fragment layout
+//   (row g, columns 2t, 2t+1) with matrix column c standing for j = pi(c), pi(2q + s) = q + 4s.
+//   ur(i,j) = sum_m D(i,m) p(m,j,k):  A = D (registers), B = p[k][pi(g)][2t .. 2t+1]: ONE LDS.128 per plane (contraction index
+//             m = 2t + s in step s, so a lane's two B elements are adjacent; the 32 lanes read the plane's 512 bytes once)
+//   us(i,j) = sum_m p(i,m,k) D(j,m):  A(row g, col t, step s) = p(i = g, j = t + 4s, k) = the lane's OWN node: no load at all
+//   ut        from the lane's own k-columns in registers with D(k,m) from the constant bank, as in v4
+//   back:  D^T wr through shared memory (own-address STS.64, one LDS.128 fragment per plane), D^T ws from the lane's own values,
+//          D^T wt accumulated in registers; the DMMA accumulator starts from that register sum.
+// Per element a lane issues 80 LDS/STS.64 + 16 LDS.128 (v4: 2 x (154 + 67 + 27)), 64 DMMA and ~520 DFMA; no block or group
+// barrier (only __syncwarp), ~170 registers.
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int WARPS, int STAGES>
+struct AxCgAffMmaSmem {
+    static constexpr int N3 = 512;
+    static constexpr size_t stage_doubles = 3 * (size_t)N3 + AFF_REC;          // r, p, u tiles + the element's constants
+    static constexpr size_t warp_doubles = STAGES * stage_doubles;
+    static constexpr size_t bytes = WARPS * warp_doubles * sizeof(double) + WARPS * STAGES * sizeof(uint64_t) + 64 * sizeof(double);
+};
+
+template <int WARPS, int STAGES, bool FIRST>
+__global__ void __launch_bounds__(32 * WARPS, 1)
+    ax_cg_affine_mma_kernel(const double *__restrict__ r, double *__restrict__ p, double *__restrict__ u,
+                            const double *__restrict__ gc, double *__restrict__ w, int nel,
+                            const CgScalars *__restrict__ sc, double *__restrict__ partials, unsigned *counter, double *pap_out)
+{
+    using L = AxCgAffMmaSmem<WARPS, STAGES>;
+    constexpr int NX = 8, N2 = 64, N3 = 512;
+    constexpr uint32_t T_BYTES = N3 * sizeof(double), C_BYTES = AFF_REC * sizeof(double);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *smem = reinterpret_cast<double *>(smem_raw);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + WARPS * L::warp_doubles);
+    double *s_red = reinterpret_cast<double *>(bars + WARPS * STAGES);
+
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int pg = (g >> 1) + 4 * (g & 1);   // pi(g): the j a B-fragment column / C-fragment column g stands for
+    double *wbase = smem + wid * L::warp_doubles;
+    uint64_t *full = bars + wid * STAGES;
+
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < WARPS * STAGES; q++) mbar_init(&bars[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const double alpha = FIRST ? 0.0 : sc->alpha;
+    const double beta = FIRST ? 0.0 : sc->work[1] / sc->rtz1;
+    // operand fragments of D (step s of the two k = 4 steps of an 8-long contraction)
+    double dA[2], dB[2], dAt[2], dBt[2], wij[2];
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        dA[s] = c_D[g * NX + 2 * t + s];           // ur : A(i = g, m = 2t + s) = D(i, m)
+        dB[s] = c_D[pg * NX + t + 4 * s];          // us : B(m = t + 4s, j = pi(g)) = D(j, m)
+        dAt[s] = c_D[(2 * t + s) * NX + g];        // D^T wr : A(i = g, m = 2t + s) = D(m, i)
+        dBt[s] = c_D[(t + 4 * s) * NX + pg];       // D^T ws : B(m = t + 4s, j = pi(g)) = D(m, j)
+        wij[s] = c_w[g] * c_w[t + 4 * s];
+    }
+    const int own0 = t * NX + g, own1 = (t + 4) * NX + g;   // the lane's two nodes in a plane: 32 consecutive words per warp
+    const int frag = pg * NX + 2 * t;                      // B fragment (two adjacent words) in a plane
+
+    const int first = blockIdx.x * WARPS + wid, stride = gridDim.x * WARPS;
+    auto issue = [&](int stage, int e) {
+        double *st = wbase + stage * L::stage_doubles;
+        mbar_expect_tx(&full[stage], C_BYTES + (FIRST ? 1 : 3) * T_BYTES);
+        bulk_g2s(st + 3 * N3, gc + (size_t)e * AFF_REC, C_BYTES, &full[stage]);
+        bulk_g2s(st, r + (size_t)e * N3, T_BYTES, &full[stage]);
+        if (!FIRST) {
+            bulk_g2s(st + N3, p + (size_t)e * N3, T_BYTES, &full[stage]);
+            bulk_g2s(st + 2 * N3, u + (size_t)e * N3, T_BYTES, &full[stage]);
+        }
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) {
+            const int e = first + s * stride;
+            if (e < nel) issue(s, e);
+        }
+    }
+
+    double pap = 0.0;
+    int it = 0;
+    for (int e = first; e < nel; e += stride, it++) {
+        const int stage = it % STAGES;
+        const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&full[stage], parity);
+        double *sr = wbase + stage * L::stage_doubles, *sp = sr + N3, *su = sr + 2 * N3;
+        const double *sgc = sr + 3 * N3;
+        const double *sf = FIRST ? sr : sp;    // the tile holding the search direction p of this iteration
+        double *swr = FIRST ? sp : sr;         // dead tile that takes the r-fluxes
+        const double c0 = sgc[0], c1 = sgc[1], c2 = sgc[2], c3 = sgc[3], c4 = sgc[4], c5 = sgc[5];
+
+        // ---- phase 0: u += alpha p_old ; p = r + beta p_old at the lane's own nodes
+        double pc[2][NX];
+        double *__restrict__ pe = p + (size_t)e * N3;
+        if (FIRST) {
+#pragma unroll
+            for (int k = 0; k < NX; k++) {
+                pc[0][k] = sr[k * N2 + own0];
+                pc[1][k] = sr[k * N2 + own1];
+                pe[k * N2 + own0] = pc[0][k];
+                pe[k * N2 + own1] = pc[1][k];
+            }
+        } else {
+            double *__restrict__ ue = u + (size_t)e * N3;
+#pragma unroll
+            for (int k = 0; k < NX; k++) {
+                const double po0 = sp[k * N2 + own0], po1 = sp[k * N2 + own1];
+                const double pn0 = fma(beta, po0, sr[k * N2 + own0]), pn1 = fma(beta, po1, sr[k * N2 + own1]);
+                ue[k * N2 + own0] = fma(alpha, po0, su[k * N2 + own0]);
+                ue[k * N2 + own1] = fma(alpha, po1, su[k * N2 + own1]);
+                sp[k * N2 + own0] = pn0;
+                sp[k * N2 + own1] = pn1;
+                pe[k * N2 + own0] = pn0;
+                pe[k * N2 + own1] = pn1;
+                pc[0][k] = pn0;
+                pc[1][k] = pn1;
+            }
+            __syncwarp();   // the p tile is complete
+        }
+
+        // ---- phase 1: gradient, metric, t-part of the divergence; r- and s-fluxes to shared memory (dead tiles) at the
+        // lane's own nodes -- the s-fluxes come back as the lane's own A fragment, so only the r-fluxes change hands
+        double wc[2][NX];
+        double *sws = su;
+#pragma unroll
+        for (int m = 0; m < NX; m++) wc[0][m] = wc[1][m] = 0.0;
+#pragma unroll
+        for (int k = 0; k < NX; k++) {
+            const double2 b = *reinterpret_cast<const double2 *>(sf + k * N2 + frag);
+            double ur0 = 0.0, ur1 = 0.0, us0 = 0.0, us1 = 0.0, ut0 = 0.0, ut1 = 0.0;
+            dmma884(ur0, ur1, dA[0], b.x);
+            dmma884(ur0, ur1, dA[1], b.y);
+            dmma884(us0, us1, pc[0][k], dB[0]);
+            dmma884(us0, us1, pc[1][k], dB[1]);
+#pragma unroll
+            for (int m = 0; m < NX; m++) {
+                ut0 = fma(c_D[k * NX + m], pc[0][m], ut0);
+                ut1 = fma(c_D[k * NX + m], pc[1][m], ut1);
+            }
+            // G_ab(i,j,k) = c_ab * w_i w_j w_k
+            const double W0 = wij[0] * c_w[k], W1 = wij[1] * c_w[k];
+            const double wr0 = fma(c0, ur0, fma(c1, us0, c2 * ut0)) * W0, wr1 = fma(c0, ur1, fma(c1, us1, c2 * ut1)) * W1;
+            const double ws0 = fma(c1, ur0, fma(c3, us0, c4 * ut0)) * W0, ws1 = fma(c1, ur1, fma(c3, us1, c4 * ut1)) * W1;
+            const double wt0 = fma(c2, ur0, fma(c4, us0, c5 * ut0)) * W0, wt1 = fma(c2, ur1, fma(c4, us1, c5 * ut1)) * W1;
+            swr[k * N2 + own0] = wr0;
+            swr[k * N2 + own1] = wr1;
+            sws[k * N2 + own0] = ws0;
+            sws[k * N2 + own1] = ws1;
+#pragma unroll
+            for (int m = 0; m < NX; m++) {
+                wc[0][m] = fma(c_D[k * NX + m], wt0, wc[0][m]);
+                wc[1][m] = fma(c_D[k * NX + m], wt1, wc[1][m]);
+            }
+        }
+        __syncwarp();   // the r-flux tile is complete
+
+        // ---- phase 2: D^T wr + D^T ws on top of the register sum, store, p.w
+        double *__restrict__ we = w + (size_t)e * N3;
+#pragma unroll
+        for (int k = 0; k < NX; k++) {
+            const double2 b = *reinterpret_cast<const double2 *>(swr + k * N2 + frag);
+            double a0 = wc[0][k], a1 = wc[1][k];
+            dmma884(a0, a1, dAt[0], b.x);
+            dmma884(a0, a1, dAt[1], b.y);
+            dmma884(a0, a1, sws[k * N2 + own0], dBt[0]);
+            dmma884(a0, a1, sws[k * N2 + own1], dBt[1]);
+            we[k * N2 + own0] = a0;
+            we[k * N2 + own1] = a1;
+            pap = fma(sf[k * N2 + own0], a0, pap);
+            pap = fma(sf[k * N2 + own1], a1, pap);
+        }
+        __syncwarp();   // every lane is done with this stage
+        if (lane == 0) {
+            const int en = e + STAGES * stride;
+            if (en < nel) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(stage, en);
+            }
+        }
+    }
+    if (pap_out != nullptr) {
+        double b = block_reduce(pap, s_red);
+        grid_reduce(b, partials, counter, s_red, [=](double tt) { *pap_out = tt; });
+    }
+}
+
+template <int WARPS, int STAGES>
+inline void launch_ax_cg_affine_mma(const double *r, double *p, double *u, double *w, int nel, bool first, double *pap_out)
+{
+    Ctx &c = ctx();
+    using L = AxCgAffMmaSmem<WARPS, STAGES>;
+    static_assert(L::bytes <= 227 * 1024, "shared memory of one SM");
+    static bool configured = false;
+    if (!configured) {
+        NEKB_CUDA(cudaFuncSetAttribute(ax_cg_affine_mma_kernel<WARPS, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes));
+        NEKB_CUDA(cudaFuncSetAttribute(ax_cg_affine_mma_kernel<WARPS, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes));
+        configured = true;
+    }
+    const int grid = grid_for((nel + WARPS - 1) / WARPS, 1);
+    if (first)
+        ax_cg_affine_mma_kernel<WARPS, STAGES, true><<<grid, 32 * WARPS, L::bytes, c.stream>>>(
+            r, p, u, c.gc.p, w, nel, c.sc.p, c.partials.p, &c.sc.p->counter[0], pap_out);
+    else
+        ax_cg_affine_mma_kernel<WARPS, STAGES, false><<<grid, 32 * WARPS, L::bytes, c.stream>>>(
+            r, p, u, c.gc.p, w, nel, c.sc.p, c.partials.p, &c.sc.p->counter[0], pap_out);
+    NEKB_LAUNCHED();
+}
+
+// ---------------------------------------------------------------------------------------------- kernel v6 (general geometry, warp per element, DMMA)
+// Kernel v5's mapping with the six per-node factors streamed as in ax_cg_kernel (a stage is 9 tiles = 36 KB): each lane
+// reads the factors of its own nodes from the stage (12 conflict-free LDS.64 per plane).  Six warps with one stage each fill the
+// shared memory of an SM; the kernel is DRAM-bound (2130 cycles of HBM time per element and SM against ~1200 of FP64 +
+// shared-memory pipe time).  Measured at E = 262,144 (profiles/r2s_*): 6 x 1 stages 2.19-2.25 ms, 3 x 2 2.57 ms, 2 x 3 3.5 ms,
+// ax_cg_kernel<8,3,2> 2.25-2.34 ms.
+template <int WARPS, int STAGES>
+struct AxCgMmaSmem {
+    static constexpr int N3 = 512;
+    static constexpr size_t stage_doubles = 9 * (size_t)N3;                    // r, p, u tiles + the six factor tiles
+    static constexpr size_t warp_doubles = STAGES * stage_doubles;
+    static constexpr size_t bytes = WARPS * warp_doubles * sizeof(double) + WARPS * STAGES * sizeof(uint64_t) + 64 * sizeof(double);
+};
+
+template <int WARPS, int STAGES, bool FIRST>
+__global__ void __launch_bounds__(32 * WARPS, 1)
+    ax_cg_mma_kernel(const double *__restrict__ r, double *__restrict__ p, double *__restrict__ u,
+                            const double *__restrict__ gf, double *__restrict__ w, int nel,
+                            const CgScalars *__restrict__ sc, double *__restrict__ partials, unsigned *counter, double *pap_out)
+{
+    using L = AxCgMmaSmem<WARPS, STAGES>;
+    constexpr int NX = 8, N2 = 64, N3 = 512;
+    constexpr uint32_t T_BYTES = N3 * sizeof(double), G_BYTES = 6 * N3 * sizeof(double);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *smem = reinterpret_cast<double *>(smem_raw);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + WARPS * L::warp_doubles);
+    double *s_red = reinterpret_cast<double *>(bars + WARPS * STAGES);
+
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int pg = (g >> 1) + 4 * (g & 1);   // pi(g): the j a B-fragment column / C-fragment column g stands for
+    double *wbase = smem + wid * L::warp_doubles;
+    uint64_t *full = bars + wid * STAGES;
+
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < WARPS * STAGES; q++) mbar_init(&bars[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const double alpha = FIRST ? 0.0 : sc->alpha;
+    const double beta = FIRST ? 0.0 : sc->work[1] / sc->rtz1;
+    // operand fragments of D (step s of the two k = 4 steps of an 8-long contraction)
+    double dA[2], dB[2], dAt[2], dBt[2];
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        dA[s] = c_D[g * NX + 2 * t + s];           // ur : A(i = g, m = 2t + s) = D(i, m)
+        dB[s] = c_D[pg * NX + t + 4 * s];          // us : B(m = t + 4s, j = pi(g)) = D(j, m)
+        dAt[s] = c_D[(2 * t + s) * NX + g];        // D^T wr : A(i = g, m = 2t + s) = D(m, i)
+        dBt[s] = c_D[(t + 4 * s) * NX + pg];       // D^T ws : B(m = t + 4s, j = pi(g)) = D(m, j)
+    }
+    const int own0 = t * NX + g, own1 = (t + 4) * NX + g;   // the lane's two nodes in a plane: 32 consecutive words per warp
+    const int frag = pg * NX + 2 * t;                      // B fragment (two adjacent words) in a plane
+
+    const int first = blockIdx.x * WARPS + wid, stride = gridDim.x * WARPS;
+    auto issue = [&](int stage, int e) {
+        double *st = wbase + stage * L::stage_doubles;
+        mbar_expect_tx(&full[stage], G_BYTES + (FIRST ? 1 : 3) * T_BYTES);
+        bulk_g2s(st + 3 * N3, gf + (size_t)e * 6 * N3, G_BYTES, &full[stage]);
+        bulk_g2s(st, r + (size_t)e * N3, T_BYTES, &full[stage]);
+        if (!FIRST) {
+            bulk_g2s(st + N3, p + (size_t)e * N3, T_BYTES, &full[stage]);
+            bulk_g2s(st + 2 * N3, u + (size_t)e * N3, T_BYTES, &full[stage]);
+        }
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) {
+            const int e = first + s * stride;
+            if (e < nel) issue(s, e);
+        }
+    }
+
+    double pap = 0.0;
+    int it = 0;
+    for (int e = first; e < nel; e += stride, it++) {
+        const int stage = it % STAGES;
+        const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&full[stage], parity);
+        double *sr = wbase + stage * L::stage_doubles, *sp = sr + N3, *su = sr + 2 * N3;
+        const double *sg = sr + 3 * N3;    // g[c][k][j][i], c = rr, rs, rt, ss, st, tt
+        const double *sf = FIRST ? sr : sp;    // the tile holding the search direction p of this iteration
+        double *swr = FIRST ? sp : sr;         // dead tile that takes the r-fluxes
+
+        // ---- phase 0: u += alpha p_old ; p = r + beta p_old at the lane's own nodes
+        double pc[2][NX];
+        double *__restrict__ pe = p + (size_t)e * N3;
+        if (FIRST) {
+#pragma unroll
+            for (int k = 0; k < NX; k++) {
+                pc[0][k] = sr[k * N2 + own0];
+                pc[1][k] = sr[k * N2 + own1];
+                pe[k * N2 + own0] = pc[0][k];
+                pe[k * N2 + own1] = pc[1][k];
+            }
+        } else {
+            double *__restrict__ ue = u + (size_t)e * N3;
+#pragma unroll
+            for (int k = 0; k < NX; k++) {
+                const double po0 = sp[k * N2 + own0], po1 = sp[k * N2 + own1];
+                const double pn0 = fma(beta, po0, sr[k * N2 + own0]), pn1 = fma(beta, po1, sr[k * N2 + own1]);
+                ue[k * N2 + own0] = fma(alpha, po0, su[k * N2 + own0]);
+                ue[k * N2 + own1] = fma(alpha, po1, su[k * N2 + own1]);
+                sp[k * N2 + own0] = pn0;
+                sp[k * N2 + own1] = pn1;
+                pe[k * N2 + own0] = pn0;
+                pe[k * N2 + own1] = pn1;
+                pc[0][k] = pn0;
+                pc[1][k] = pn1;
+            }
+            __syncwarp();   // the p tile is complete
+        }
+
+        // ---- phase 1: gradient, metric, t-part of the divergence; r- and s-fluxes to shared memory (dead tiles) at the
+        // lane's own nodes -- the s-fluxes come back as the lane's own A fragment, so only the r-fluxes change hands
+        double wc[2][NX];
+        double *sws = su;
+#pragma unroll
+        for (int m = 0; m < NX; m++) wc[0][m] = wc[1][m] = 0.0;
+#pragma unroll
+        for (int k = 0; k < NX; k++) {
+            const double2 b = *reinterpret_cast<const double2 *>(sf + k * N2 + frag);
+            double ur0 = 0.0, ur1 = 0.0, us0 = 0.0, us1 = 0.0, ut0 = 0.0, ut1 = 0.0;
+            dmma884(ur0, ur1, dA[0], b.x);
+            dmma884(ur0, ur1, dA[1], b.y);
+            dmma884(us0, us1, pc[0][k], dB[0]);
+            dmma884(us0, us1, pc[1][k], dB[1]);
+#pragma unroll
+            for (int m = 0; m < NX; m++) {
+                ut0 = fma(c_D[k * NX + m], pc[0][m], ut0);
+                ut1 = fma(c_D[k * NX + m], pc[1][m], ut1);
+            }
+            // the six factors of the lane's two nodes of this plane (same products, same order as ax_cg_kernel)
+            const int q0 = k * N2 + own0, q1 = k * N2 + own1;
+            const double A0 = sg[q0], A1 = sg[N3 + q0], A2 = sg[2 * N3 + q0], A3 = sg[3 * N3 + q0], A4 = sg[4 * N3 + q0], A5 = sg[5 * N3 + q0];
+            const double B0 = sg[q1], B1 = sg[N3 + q1], B2 = sg[2 * N3 + q1], B3 = sg[3 * N3 + q1], B4 = sg[4 * N3 + q1], B5 = sg[5 * N3 + q1];
+            const double wr0 = fma(A0, ur0, fma(A1, us0, A2 * ut0)), wr1 = fma(B0, ur1, fma(B1, us1, B2 * ut1));
+            const double ws0 = fma(A1, ur0, fma(A3, us0, A4 * ut0)), ws1 = fma(B1, ur1, fma(B3, us1, B4 * ut1));
+            const double wt0 = fma(A2, ur0, fma(A4, us0, A5 * ut0)), wt1 = fma(B2, ur1, fma(B4, us1, B5 * ut1));
+            swr[k * N2 + own0] = wr0;
+            swr[k * N2 + own1] = wr1;
+            sws[k * N2 + own0] = ws0;
+            sws[k * N2 + own1] = ws1;
+#pragma unroll
+            for (int m = 0; m < NX; m++) {
+                wc[0][m] = fma(c_D[k * NX + m], wt0, wc[0][m]);
+                wc[1][m] = fma(c_D[k * NX + m], wt1, wc[1][m]);
+            }
+        }
+        __syncwarp();   // the r-flux tile is complete
+
+        // ---- phase 2: D^T wr + D^T ws on top of the register sum, store, p.w
+        double *__restrict__ we = w + (size_t)e * N3;
+#pragma unroll
+        for (int k = 0; k < NX; k++) {
+            const double2 b = *reinterpret_cast<const double2 *>(swr + k * N2 + frag);
+            double a0 = wc[0][k], a1 = wc[1][k];
+            dmma884(a0, a1, dAt[0], b.x);
+            dmma884(a0, a1, dAt[1], b.y);
+            dmma884(a0, a1, sws[k * N2 + own0], dBt[0]);
+            dmma884(a0, a1, sws[k * N2 + own1], dBt[1]);
+            we[k * N2 + own0] = a0;
+            we[k * N2 + own1] = a1;
+            pap = fma(sf[k * N2 + own0], a0, pap);
+            pap = fma(sf[k * N2 + own1], a1, pap);
+        }
+        __syncwarp();   // every lane is done with this stage
+        if (lane == 0) {
+            const int en = e + STAGES * stride;
+            if (en < nel) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(stage, en);
+            }
+        }
+    }
+    if (pap_out != nullptr) {
+        double b = block_reduce(pap, s_red);
+        grid_reduce(b, partials, counter, s_red, [=](double tt) { *pap_out = tt; });
+    }
+}
+
+template <int WARPS, int STAGES>
+inline void launch_ax_cg_mma(const double *r, double *p, double *u, double *w, int nel, bool first, double *pap_out)
+{
+    Ctx &c = ctx();
+    using L = AxCgMmaSmem<WARPS, STAGES>;
+    static_assert(L::bytes <= 227 * 1024, "shared memory of one SM");
+    static bool configured = false;
+    if (!configured) {
+        NEKB_CUDA(cudaFuncSetAttribute(ax_cg_mma_kernel<WARPS, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes));
+        NEKB_CUDA(cudaFuncSetAttribute(ax_cg_mma_kernel<WARPS, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes));
+        configured = true;
+    }
+    const int grid = grid_for((nel + WARPS - 1) / WARPS, 1);
+    if (first)
+        ax_cg_mma_kernel<WARPS, STAGES, true><<<grid, 32 * WARPS, L::bytes, c.stream>>>(
+            r, p, u, c.g.p, w, nel, c.sc.p, c.partials.p, &c.sc.p->counter[0], pap_out);
+    else
+        ax_cg_mma_kernel<WARPS, STAGES, false><<<grid, 32 * WARPS, L::bytes, c.stream>>>(
+            r, p, u, c.g.p, w, nel, c.sc.p, c.partials.p, &c.sc.p->counter[0], pap_out);
+    NEKB_LAUNCHED();
+}
+
 template <int NX, int GROUPS, int STAGES>
 inline void launch_ax_cg(const double *r, double *p, double *u, double *w, int nel, bool first, double *pap_out)
 {

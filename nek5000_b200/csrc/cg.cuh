@@ -663,6 +663,171 @@ __global__ void __launch_bounds__(128 * EPB, MINB)
     });
 }
 
+// The same update as a streaming pipeline: ONE WARP owns an element; the element's r and A p tiles, its byte codes and its two
+// gather tables (48 B of face links + 320 B of edge slots) arrive in a per-warp ring of shared-memory stages by TMA bulk copies
+// (one mbarrier per stage), so the bytes in flight do not depend on how many threads are stalled behind a barrier -- ncu of
+// cggos_update4_kernel showed DRAM 51-55 % active at near-minimal traffic: a latency chain (table -> partner -> barrier), not
+// bandwidth.  The irregular part is software-pipelined: as soon as the tables of element n+1 are in shared memory, every lane
+// issues the (<= 16, predicated) partner / gval loads of ITS OWN nodes of that element into registers, then computes element n
+// with the values fetched one trip earlier.  A lane owns the two k-columns (i0, i0+1; j): one double2 per plane, 512 contiguous
+// bytes per warp instruction for the shared-memory reads and the r stores.  No block barrier, no shared-memory staging of the
+// gathered values.  Same members and member order per node as gs_local_kernel<1> (pairs: own + partner; edge / corner groups:
+// gval), i.e. the bits of the other forms; (r,r) is summed in another grouping.
+constexpr int UPD6_STAGE_BYTES = 2 * 4096 + 512 + 48 + 320 + 16;   // r, ap, code, ftab[6], etab[80]; padded to 128 B
+static_assert(UPD6_STAGE_BYTES % 128 == 0, "stage alignment");
+
+template <int WARPS, int STAGES>
+__global__ void __launch_bounds__(32 * WARPS, 1)
+    cggos_update6_kernel(double *__restrict__ r, const double *__restrict__ ap, const unsigned char *__restrict__ code,
+                         const FaceLink *__restrict__ ftab, const int32_t *__restrict__ etab, const double *__restrict__ gval,
+                         int nel, CgScalars *sc, double *partials)
+{
+    static_assert(STAGES >= 2, "the next element's tables must be resident while this one is computed");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double red[33];
+    __shared__ double wtab[128];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WARPS * STAGES * UPD6_STAGE_BYTES);
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *wbase = smem_raw + (size_t)wid * STAGES * UPD6_STAGE_BYTES;
+    uint64_t *full = bars + wid * STAGES;
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < WARPS * STAGES; q++) mbar_init(&bars[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 128) wtab[threadIdx.x] = threadIdx.x ? 1.0 / (double)threadIdx.x : 0.0;
+    __syncthreads();
+    const double pap = sc->work[0], rz = sc->work[1];
+    const double alpha = rz / pap;
+
+    // the lane's 16 nodes: (i0 + q, j, k), q = 0, 1, k = 0..7; what each of them gathers (fixed per lane)
+    //   desc = -1: interior node; 0..5: face-interior node of face f, with in-face coordinates (fa, fb); 8 + slot: edge / corner
+    const int i0 = (lane & 3) * 2, j = lane >> 2;
+    int desc[16], fa[16], fb[16];
+#pragma unroll
+    for (int n = 0; n < 16; n++) {
+        const int k = n >> 1, i = i0 + (n & 1);
+        const int nb = gs_st_nb(i, j, k);
+        desc[n] = -1, fa[n] = 0, fb[n] = 0;
+        if (nb == 1) desc[n] = gs_st_face(i, j, k, fa[n], fb[n]);
+        if (nb >= 2) desc[n] = 8 + gs_st_slot(i, j, k);
+    }
+
+    const int first = blockIdx.x * WARPS + wid, stride = gridDim.x * WARPS;
+    auto issue = [&](int stage, int e) {
+        unsigned char *st = wbase + (size_t)stage * UPD6_STAGE_BYTES;
+        mbar_expect_tx(&full[stage], 2 * 4096 + 512 + 48 + 320);
+        bulk_g2s(st, r + (size_t)e * 512, 4096, &full[stage]);
+        bulk_g2s(st + 4096, ap + (size_t)e * 512, 4096, &full[stage]);
+        bulk_g2s(st + 8192, code + (size_t)e * 512, 512, &full[stage]);
+        bulk_g2s(st + 8704, ftab + (size_t)e * 6, 48, &full[stage]);
+        bulk_g2s(st + 8752, etab + (size_t)e * GS_ST_EDGE_SLOTS, 320, &full[stage]);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) {
+            const int e = first + s * stride;
+            if (e < nel) issue(s, e);
+        }
+    }
+    // gathers of the lane's own nodes of the element in `stage` (tables already in shared memory): values + validity mask
+    auto gather = [&](int stage, double (&gv)[16]) -> unsigned {
+        const unsigned char *st = wbase + (size_t)stage * UPD6_STAGE_BYTES;
+        const FaceLink *sf = reinterpret_cast<const FaceLink *>(st + 8704);
+        const int32_t *se = reinterpret_cast<const int32_t *>(st + 8752);
+        unsigned vm = 0;
+#pragma unroll
+        for (int n = 0; n < 16; n++) {
+            gv[n] = 0.0;
+            if (desc[n] >= 8) {
+                const int gI = se[desc[n] - 8];
+                if (gI >= 0) {
+                    gv[n] = gval[gI];
+                    vm |= 1u << n;
+                }
+            } else if (desc[n] >= 0) {
+                const FaceLink Lk = sf[desc[n]];
+                if (Lk.base >= 0) {
+                    gv[n] = ap[(int64_t)Lk.base + fa[n] * Lk.sa + fb[n] * Lk.sb];
+                    vm |= 1u << n;
+                }
+            }
+        }
+        return vm;
+    };
+
+    double s = 0.0;
+    double gcur[16];
+    unsigned vcur = 0;
+    if (first < nel) {
+        mbar_wait(&full[0], 0);
+        vcur = gather(0, gcur);
+    }
+    int it = 0;
+    for (int e = first; e < nel; e += stride, it++) {
+        const int stage = it % STAGES;
+        // the next element's tables -> its gathers go out before this element is touched
+        double gnext[16];
+        unsigned vnext = 0;
+        const int en1 = e + stride;
+        if (en1 < nel) {
+            const int st1 = (it + 1) % STAGES;
+            mbar_wait(&full[st1], (uint32_t)((it + 1) / STAGES) & 1u);
+            vnext = gather(st1, gnext);
+        }
+        const unsigned char *st = wbase + (size_t)stage * UPD6_STAGE_BYTES;
+        const double2 *sr2 = reinterpret_cast<const double2 *>(st);
+        const double2 *sa2 = reinterpret_cast<const double2 *>(st + 4096);
+        const uchar2 *sc2 = reinterpret_cast<const uchar2 *>(st + 8192);
+        double2 *r2 = reinterpret_cast<double2 *>(r + (size_t)e * 512);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int q = k * 32 + lane;
+            double2 rv = sr2[q];
+            const double2 av = sa2[q];
+            const uchar2 c = sc2[q];
+            double w0 = av.x, w1 = av.y;
+            if (vcur & (1u << (2 * k))) w0 = desc[2 * k] >= 8 ? gcur[2 * k] : w0 + gcur[2 * k];
+            if (vcur & (1u << (2 * k + 1))) w1 = desc[2 * k + 1] >= 8 ? gcur[2 * k + 1] : w1 + gcur[2 * k + 1];
+            rv.x = fma(-alpha, (c.x & 0x80) ? 0.0 : w0, rv.x);
+            rv.y = fma(-alpha, (c.y & 0x80) ? 0.0 : w1, rv.y);
+            r2[q] = rv;
+            s = fma(wtab[c.x & 0x7f] * rv.x, rv.x, s);
+            s = fma(wtab[c.y & 0x7f] * rv.y, rv.y, s);
+        }
+        __syncwarp();   // every lane is done with this stage
+        if (lane == 0) {
+            const int en = e + STAGES * stride;
+            if (en < nel) issue(stage, en);   // the stage was only read: no generic-proxy writes to order
+        }
+#pragma unroll
+        for (int n = 0; n < 16; n++) gcur[n] = gnext[n];
+        vcur = vnext;
+    }
+    double b = block_reduce(s, red);
+    grid_reduce(b, partials, &sc->counter[2], red, [=](double tot) {
+        sc->rtz1 = rz;
+        sc->work[1] = tot;
+        sc->alpha = alpha;
+        sc->it = sc->it + 1;
+    });
+}
+
+template <int WARPS, int STAGES>
+inline void launch_cggos_update6(double *r, const double *ap, const unsigned char *code, const GsMap &h, int nel, CgScalars *sc,
+                                 double *partials)
+{
+    Ctx &c = ctx();
+    constexpr size_t bytes = (size_t)WARPS * STAGES * UPD6_STAGE_BYTES + WARPS * STAGES * sizeof(uint64_t);
+    static_assert(bytes + 2048 <= 227 * 1024, "shared memory of one SM");
+    static bool configured = false;
+    if (!configured) {
+        NEKB_CUDA(cudaFuncSetAttribute(cggos_update6_kernel<WARPS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        configured = true;
+    }
+    cggos_update6_kernel<WARPS, STAGES><<<grid_for((nel + WARPS - 1) / WARPS, 1), 32 * WARPS, bytes, c.stream>>>(
+        r, ap, code, h.ftab.p, h.etab.p, h.gval.p, nel, sc, partials);
+}
+
 // u += alpha * p with the device-resident alpha (the u update of the final iteration)
 __global__ void __launch_bounds__(CG_THREADS)
     axpy_alpha_kernel(double *__restrict__ u, const double *__restrict__ p, int64_t n, const CgScalars *sc)
@@ -690,7 +855,7 @@ inline int axcg_variant()
 inline int gs_fuse_update_enabled()  // read per solve, so one process can time both forms
 {
     const char *e = getenv("NEKB_GS_FUSE_UPDATE");
-    return e ? atoi(e) : 4;
+    return e ? atoi(e) : 6;
 }
 inline int cg_fused_enabled()   // read per solve: bench.py times the kernel-per-statement path beside the fused one
 {
@@ -733,7 +898,7 @@ inline int cggos_run_fused(const CggosArgs &a, int maxit, double *hist_host, boo
     const int gmode = gs_fuse_update_enabled();
     const bool gather = (gmode == 1 || gmode == 2) && c.nranks == 1 && h.nshared == 0;
     if (gather) gs_ensure_link(h, gmode);
-    const bool structured = (gmode == 3 || gmode == 4 || gmode == 5) && gs_ensure_struct(h);
+    const bool structured = (gmode >= 3 && gmode <= 6) && gs_ensure_struct(h);
     const bool affine = ax_affine_ensure();   // decided from the registered factors (all elements affine to 1e-13)
     cggos_init2_kernel<<<grid, CG_THREADS, 0, s>>>(a.u, r.p, a.rhs, a.mult, n, sc, c.partials.p + 1 * CG_PART_STRIDE);
     NEKB_LAUNCHED();
@@ -748,13 +913,21 @@ inline int cggos_run_fused(const CggosArgs &a, int maxit, double *hist_host, boo
                 case 4: launch_ax_cg_affine<8, 3, 4>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
                 case 5: launch_ax_cg_affine<8, 5, 3>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
                 case 6: launch_ax_cg_affine<8, 5, 2>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
-                default: launch_ax_cg_affine<8, 4, 3>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
+                // warp per element, in-plane contractions on DMMA (ax.cuh kernel v5): warps per SM x ring stages per warp
+                case 11: launch_ax_cg_affine_mma<6, 3>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
+                case 14: launch_ax_cg_affine_mma<4, 4>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
+                case 7: launch_ax_cg_affine<8, 4, 3>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;   // round-2 default before v5
+                default: launch_ax_cg_affine_mma<8, 2>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
             }
         } else
         switch (axcg_variant()) {  // element groups per CTA x ring stages (36 KB each): bytes in flight vs. threads per SM
             case 1: launch_ax_cg<8, 2, 3>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
             case 2: launch_ax_cg<8, 2, 2>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
-            default: launch_ax_cg<8, 3, 2>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
+            case 3: launch_ax_cg<8, 3, 2>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;   // default before kernel v6
+            // warp per element, in-plane contractions on DMMA (ax.cuh kernel v6): warps per SM x 36 KB ring stages per warp
+            case 10: launch_ax_cg_mma<3, 2>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
+            case 11: launch_ax_cg_mma<2, 3>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
+            default: launch_ax_cg_mma<6, 1>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
         }
         prof_end(PROF_AX);
         comm_allreduce_sum(&sc->work[0], 1);
@@ -776,6 +949,20 @@ inline int cggos_run_fused(const CggosArgs &a, int maxit, double *hist_host, boo
                 if (g5 > c.num_sms * 4) g5 = c.num_sms * 4;
                 cggos_update5_kernel<<<g5, CG_THREADS, 0, s>>>(r.p, ap.p, c.wcode.p, h.ftab.p, h.etab.p, h.gval.p, n, sc,
                                                                c.partials.p + 2 * CG_PART_STRIDE);
+            } else if (gmode == 6) {
+                // warp-per-element TMA ring (cggos_update6_kernel): warps per SM x stages per warp
+                static int var6 = -1;
+                if (var6 < 0) {
+                    const char *e = getenv("NEKB_UPD6_VARIANT");
+                    var6 = e ? atoi(e) : 0;
+                }
+                double *part = c.partials.p + 2 * CG_PART_STRIDE;
+                switch (var6) {
+                    case 1: launch_cggos_update6<8, 3>(r.p, ap.p, c.wcode.p, h, a.nel, sc, part); break;
+                    case 2: launch_cggos_update6<10, 2>(r.p, ap.p, c.wcode.p, h, a.nel, sc, part); break;
+                    case 3: launch_cggos_update6<6, 4>(r.p, ap.p, c.wcode.p, h, a.nel, sc, part); break;
+                    default: launch_cggos_update6<12, 2>(r.p, ap.p, c.wcode.p, h, a.nel, sc, part); break;
+                }
             } else if (gmode == 4) {
                 // resident CTAs per SM x elements per CTA = elements in flight per SM (the kernel is latency-bound: ncu
                 // profiles/r2g: DRAM 51 % active at 3.49 GB moved, which is within 4 % of the minimum)

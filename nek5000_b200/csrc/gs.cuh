@@ -305,38 +305,7 @@ __device__ __forceinline__ double gs_gathered(const double *__restrict__ u, doub
 }
 
 // ---------------------------------------------------------------------------------------------- structured gather view
-// Node classes of an 8^3 tile by the number of local indices on the tile surface: 0 interior, 1 face-interior, >= 2 edge /
-// corner.  Slots of the edge / corner nodes in the per-element table: x-edges 0..23 (edge (j,k in {0,7}) * 6 + i-1), y-edges
-// 24..47, z-edges 48..71, corners 72..79.
-constexpr int GS_ST_NX = 8, GS_ST_N3 = 512, GS_ST_EDGE_SLOTS = 80;
-__host__ __device__ __forceinline__ int gs_st_nb(int i, int j, int k)
-{
-    return (i == 0 || i == 7) + (j == 0 || j == 7) + (k == 0 || k == 7);
-}
-__host__ __device__ __forceinline__ int gs_st_slot(int i, int j, int k)   // nb >= 2 only
-{
-    const int bi = (i == 0 || i == 7), bj = (j == 0 || j == 7), bk = (k == 0 || k == 7);
-    const int hi = i == 7, hj = j == 7, hk = k == 7;
-    if (bi + bj + bk == 3) return 72 + hi + 2 * hj + 4 * hk;
-    if (!bi) return (hj + 2 * hk) * 6 + (i - 1);
-    if (!bj) return 24 + (hi + 2 * hk) * 6 + (j - 1);
-    return 48 + (hi + 2 * hj) * 6 + (k - 1);
-}
-// nb == 1 only: face (0..5 = -x,+x,-y,+y,-z,+z) and the in-face coordinates (lower axis first)
-__host__ __device__ __forceinline__ int gs_st_face(int i, int j, int k, int &a, int &b)
-{
-    if (i == 0 || i == 7) {
-        a = j, b = k;
-        return i == 7;
-    }
-    if (j == 0 || j == 7) {
-        a = i, b = k;
-        return 2 + (j == 7);
-    }
-    a = i, b = j;
-    return 4 + (k == 7);
-}
-
+// (node classes / slot numbering of an 8^3 tile: gs_st_nb, gs_st_slot, gs_st_face in ctx.cuh)
 // Builds the structured view (host, set-up only).  Classification of a group of the local map:
 //   S  (assembled in place)   : a member is shared with another rank, or the group mixes node classes / is not a clean pair
 //   P  (gathered through ftab): exactly two face-interior members, and all 36 pairs of both faces follow one affine map

@@ -527,8 +527,13 @@ __global__ void __launch_bounds__(NL *NL *EPB)
     constexpr int NH = NL - 2, NLP = (NL % 2 == 0) ? NL + 1 : NL, L2 = NL * NL, H2 = NH * NH, H3 = NH * NH * NH;
     constexpr int TILE = NL * NL * NLP;
     __shared__ double s_t[EPB][TILE];
-    __shared__ double s_S[EPB][3][L2];
+    __shared__ __align__(16) double s_S[EPB][3][L2];
     __shared__ double s_lam[EPB][3][NL];
+    // The 1-D operators are read from shared memory as a broadcast by every line of the element: with NL even the entries are
+    // fetched in pairs (LDS.128: one issue slot of the shared-memory pipe per two FMAs per lane instead of two slots per FMA --
+    // the kernel was bound by that pipe: 100 LDS.64 for 100 DFMA per line, profiles/r2p_ubench_dmma.txt).  The summation
+    // order of every output is unchanged.
+    constexpr bool PAIRS = (NL % 2 == 0);
     const int es = threadIdx.x / L2, tl = threadIdx.x % L2, p = tl % NL, q = tl / NL;
     const int el = blockIdx.x * EPB + es;
     const bool act = el < nel;
@@ -573,12 +578,27 @@ __global__ void __launch_bounds__(NL *NL *EPB)
             const double *S = s_S[es][d];
 #pragma unroll
             for (int i = 0; i < NL; i++) in[i] = T[base + i * stride];
+            if (PAIRS) {
 #pragma unroll
-            for (int a = 0; a < NL; a++) {
-                double s = 0.0;
+                for (int a = 0; a < NL; a++) out[a] = 0.0;
 #pragma unroll
-                for (int i = 0; i < NL; i++) s = fma(S[i * NL + a], in[i], s);
-                out[a] = s;
+                for (int i = 0; i < NL; i++) {
+                    const double2 *Srow = reinterpret_cast<const double2 *>(S + i * NL);
+#pragma unroll
+                    for (int a2 = 0; a2 < NL / 2; a2++) {
+                        const double2 sv = Srow[a2];
+                        out[2 * a2] = fma(sv.x, in[i], out[2 * a2]);
+                        out[2 * a2 + 1] = fma(sv.y, in[i], out[2 * a2 + 1]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int a = 0; a < NL; a++) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int i = 0; i < NL; i++) s = fma(S[i * NL + a], in[i], s);
+                    out[a] = s;
+                }
             }
             if (d == 2 && dfull == nullptr) {  // last forward pass: apply D = 1/(lam_r + lam_s + lam_t) (hsmg.f:740-752)
                 const double ep = eps[el], lrs = s_lam[es][0][p] + s_lam[es][1][q];
@@ -610,8 +630,18 @@ __global__ void __launch_bounds__(NL *NL *EPB)
 #pragma unroll
             for (int a = 0; a < NL; a++) {
                 double s = 0.0;
+                if (PAIRS) {
+                    const double2 *Srow = reinterpret_cast<const double2 *>(S + a * NL);
 #pragma unroll
-                for (int i = 0; i < NL; i++) s = fma(S[a * NL + i], in[i], s);
+                    for (int i2 = 0; i2 < NL / 2; i2++) {
+                        const double2 sv = Srow[i2];
+                        s = fma(sv.x, in[2 * i2], s);
+                        s = fma(sv.y, in[2 * i2 + 1], s);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NL; i++) s = fma(S[a * NL + i], in[i], s);
+                }
                 out[a] = s;
             }
 #pragma unroll
@@ -709,6 +739,68 @@ __global__ void __launch_bounds__(256)
         double s = 0.0;
         for (int k = 0; k < nu; k++) s = fma(M[c * nu + k], A[k * nv * nv + ab], s);
         oe[t] = accumulate ? oe[t] + s : s;
+    }
+}
+
+// The same operation with the two level sizes known at compile time (the level pairs of lx1 = 4, 6, 8: all index arithmetic
+// and the contraction loops unroll) and EPB elements per CTA, TPE threads each: ncu of the generic kernel at 32^3 elements
+// showed DRAM 25 % active behind barrier and shared-memory stalls (profiles/r2g_ncu_summary.md).  Same summation order per
+// output, hence the same bits as the generic kernel.
+template <int NV, int NU, int EPB, bool TRANSPOSE>
+__global__ void __launch_bounds__(64 * EPB)
+    mg_tensor3_t_kernel(double *__restrict__ out, const double *__restrict__ u, const double *__restrict__ wt,
+                        const double *__restrict__ mat, int accumulate, int nel)
+{
+    constexpr int TPE = 64, NM = NV > NU ? NV : NU, M3 = NM * NM * NM, NU3 = NU * NU * NU, NV3 = NV * NV * NV;
+    __shared__ double s_A[EPB][M3], s_B[EPB][M3];
+    __shared__ double s_M[NV * NU];
+    const int es = threadIdx.x / TPE, tl = threadIdx.x % TPE;
+    const int el = blockIdx.x * EPB + es;
+    const bool act = el < nel;
+    for (int t = threadIdx.x; t < NV * NU; t += TPE * EPB) {
+        const int a = t / NU, i = t % NU;
+        s_M[t] = TRANSPOSE ? mat[i * NV + a] : mat[t];
+    }
+    double *A = s_A[es], *B = s_B[es];
+    if (act) {
+        const double *ue = u + (size_t)el * NU3;
+        const double *we = wt ? wt + (size_t)el * NU3 : nullptr;
+#pragma unroll
+        for (int t = tl; t < NU3; t += TPE) A[t] = we ? ue[t] * we[t] : ue[t];
+    }
+    __syncthreads();
+    if (act) {
+#pragma unroll
+        for (int t = tl; t < NV * NU * NU; t += TPE) {   // r: B[a,j,k] = sum_i M[a,i] A[i,j,k]
+            const int a = t % NV, jk = t / NV;
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < NU; i++) s = fma(s_M[a * NU + i], A[jk * NU + i], s);
+            B[t] = s;
+        }
+    }
+    __syncthreads();
+    if (act) {
+#pragma unroll
+        for (int t = tl; t < NV * NV * NU; t += TPE) {   // s: A[a,b,k] = sum_j M[b,j] B[a,j,k]
+            const int a = t % NV, b = (t / NV) % NV, k = t / (NV * NV);
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < NU; j++) s = fma(s_M[b * NU + j], B[(k * NU + j) * NV + a], s);
+            A[t] = s;
+        }
+    }
+    __syncthreads();
+    if (act) {
+        double *oe = out + (size_t)el * NV3;
+#pragma unroll
+        for (int t = tl; t < NV3; t += TPE) {            // t: out[a,b,c] = sum_k M[c,k] A[a,b,k]
+            const int ab = t % (NV * NV), c = t / (NV * NV);
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < NU; k++) s = fma(s_M[c * NU + k], A[k * NV * NV + ab], s);
+            oe[t] = accumulate ? oe[t] + s : s;
+        }
     }
 }
 
@@ -1651,6 +1743,20 @@ inline void mg_tensor3(double *out, const double *u, const double *wt, const dou
                        bool accumulate, int nel)
 {
     if (nel <= 0) return;
+    static const bool templated = !(getenv("NEKB_MG_TENSOR3_GENERIC") && atoi(getenv("NEKB_MG_TENSOR3_GENERIC")));
+#define NEKB_T3(NV_, NU_, EPB_)                                                                                                  \
+    if (templated && nv == NV_ && nu == NU_) {                                                                                  \
+        if (transpose)                                                                                                          \
+            mg_tensor3_t_kernel<NV_, NU_, EPB_, true><<<(nel + EPB_ - 1) / EPB_, 64 * EPB_, 0, ctx().stream>>>(out, u, wt, J,   \
+                                                                                                              accumulate, nel); \
+        else                                                                                                                    \
+            mg_tensor3_t_kernel<NV_, NU_, EPB_, false><<<(nel + EPB_ - 1) / EPB_, 64 * EPB_, 0, ctx().stream>>>(out, u, wt, J,  \
+                                                                                                               accumulate, nel);\
+        NEKB_LAUNCHED();                                                                                                        \
+        return;                                                                                                                 \
+    }
+    NEKB_T3(4, 8, 4) NEKB_T3(8, 4, 4) NEKB_T3(2, 4, 8) NEKB_T3(4, 2, 8) NEKB_T3(4, 6, 4) NEKB_T3(6, 4, 4)
+#undef NEKB_T3
     const int nm = nv > nu ? nv : nu;
     const size_t smem = sizeof(double) * (2 * (size_t)nm * nm * nm + (size_t)nv * nu);
     NEKB_REQUIRE(smem <= 48 * 1024, "mg_tensor3: level too large for the default shared-memory window");

@@ -29,14 +29,15 @@ def main():
     same = []
     for dims in () if a.skip_small else ((3, 2, 2), (4, 4, 3), (1, 1, 1), (2, 1, 1)):
         us = []
-        for flag in ("0", "3", "4"):
+        for flag in ("0", "3", "4", "6"):
             os.environ["NEKB_GS_FUSE_UPDATE"] = flag
             nek.finalize()
             nek.init(0, 8, 3)
             b = BP5(*dims, lx1=8, deform=0.05)
             it, _, h = b.solve(-1e-8, 30, history=True)
             us.append((b.get("u1").copy(), h.copy()))
-        same.append([bool(np.array_equal(us[0][0], u[0]) and np.array_equal(us[0][1], u[1])) for u in us[1:]])
+        same.append([bool(np.array_equal(us[0][0], u[0]) and np.array_equal(us[0][1], u[1])) for u in us[1:]] +
+                    [float(np.abs(us[0][0] - u[0]).max() / np.abs(us[0][0]).max()) for u in us[1:]])
     out["bit_identical_small"] = same
     nek.finalize()
     nek.init(0, 8, 3)

@@ -221,7 +221,7 @@ def test_structured_gather_update_is_bit_identical_to_gs_op_plus_update(nek, dim
     maxit = 30
     uref, itref, hist = case.cggos(r1, e1, tol=-1e-8, maxit=maxit, history=True)
     us = []
-    for flag in ("0", "3", "4", "5"):
+    for flag in ("0", "3", "4", "5", "6"):
         monkeypatch.setenv("NEKB_GS_FUSE_UPDATE", flag)
         h, _ = nek.setupds(8, case.nel, case.vertex)
         nek.set_field_handle(1, h)
@@ -232,10 +232,11 @@ def test_structured_gather_update_is_bit_identical_to_gs_op_plus_update(nek, dim
         us.append(u)
         nek.fgslib_gs_free(h)
     # 3 (node-organised) and 5 (branch-free) keep the stock kernel's thread -> node mapping and grid, hence its reduction tree:
-    # bit-identical.  4 (element-organised, 128-thread CTAs) sums (r,r) in another grouping: same operations per node, scalars
-    # equal to rounding.
+    # bit-identical.  4 (element-organised, 128-thread CTAs) and 6 (the default: one warp per element behind a TMA ring) sum
+    # (r,r) in another grouping: same operations per node, scalars equal to rounding.
     assert np.array_equal(us[0], us[1]) and np.array_equal(us[0], us[3])
-    assert relmax(us[2], us[0]) <= 1e-12
+    assert relmax(us[2], us[0]) <= 1e-12 and relmax(us[4], us[0]) <= 1e-12
+    assert relmax(us[4], uref) <= TOL_HIST
     assert relmax(us[1], uref) <= TOL_HIST
 
 
