@@ -19,6 +19,8 @@ inline void comm_allreduce_max(double *dev, int count);
 inline int fdm_h1_kfldfdm();
 inline void set_fdm_prec_h1b_dev(double *d, const double *h1, const double *h2, int nel);
 inline void fdm_h1_apply(double *z, const double *r, const double *d, const double *mask, int nel, int gs_handle);
+inline void cggo_pres_coarse(double *w, const double *r, const double *mult, int nel);  // gmres.cuh: crs_solve_h1 (navier8.f:1490-1535)
+inline void cggo_pres_ortho(double *z, int64_t n);                                      // gmres.cuh: ortho (navier1.f:223-256)
 
 constexpr int CG_THREADS = 256;
 constexpr int CG_PART_STRIDE = 1024;  // partial-sum region per kernel kind
@@ -828,6 +830,12 @@ inline void launch_cggos_update6(double *r, const double *ap, const unsigned cha
         r, ap, code, h.ftab.p, h.etab.p, h.gval.p, nel, sc, partials);
 }
 
+// a += b (core/math.f add2)
+__global__ void __launch_bounds__(CG_THREADS) add2_kernel(double *__restrict__ a, const double *__restrict__ b, int64_t n)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) a[t] += b[t];
+}
+
 // u += alpha * p with the device-resident alpha (the u update of the final iteration)
 __global__ void __launch_bounds__(CG_THREADS)
     axpy_alpha_kernel(double *__restrict__ u, const double *__restrict__ p, int64_t n, const CgScalars *sc)
@@ -1047,6 +1055,7 @@ struct CggoArgs {
     int nel;
     double vol;
     int istep;
+    bool pres = false;   // name = 'PRES' with param(42) = 1: the plain-PCG pressure solve (hmholtz.f:710-712, :737-751)
 };
 
 // hmholtz.f:695-697: r=f, x=0, p=0 ; :699 fmax = glamax(f)
@@ -1270,7 +1279,9 @@ inline void setprec_run(double *dpc, const double *h1, const double *h2, int nel
 
 // Returns niterhm.  hist_host (may be NULL): 3 doubles per executed iteration (rtz1, rbn2, rho).
 // Includes the all-Neumann null-space correction (ifmcor, :705-720, :749-752).  The 'PRES' branch (:641-657) is taken by
-// the callers (cggo_, hmholtz_, hsolve_ forward to hmh_gmres); :731-746 (crs_solve_h1 inside PCG for 'PRES') is not provided.
+// the callers (cggo_, hmholtz_, hsolve_ forward to hmh_gmres / hmh_flex_cg for param(42) = 0 / 2); with param(42) = 1 they come
+// here with a.pres set: no ifmcor (:710-711), Schwarz + coarse-grid correction z = fdm_h1(r) + crs_solve_h1(r) (:741-744) or
+// Jacobi (kfldfdm < 0), and ortho(z) (:747-748) in every iteration.
 // lx1 = 8 Jacobi solves normally go through the fused path (hcg.cuh cggo_solve); this routine is the general one.
 inline int cggo_run(const CggoArgs &a, double tin, int maxit, double *hist_host)
 {
@@ -1324,10 +1335,11 @@ inline int cggo_run(const CggoArgs &a, double tin, int maxit, double *hist_host)
     NEKB_CUDA(cudaMemcpyAsync(&skmin, &sc->work[3], sizeof(double), cudaMemcpyDeviceToHost, s));
     NEKB_CUDA(cudaStreamSynchronize(s));
     skmin = -skmin;  // glmin(mask)
-    const bool ifmcor = skmin > 0.0 && h2max == 0.0;
+    const bool ifmcor = !a.pres && skmin > 0.0 && h2max == 0.0;   // :710-712: 'PRES' skips the mean correction of r
     double smean = 0.0;
     DevBuf<double> &bsum = c.work[5];
-    const bool explicit_z = schwarz || ifmcor;
+    const bool explicit_z = schwarz || ifmcor || a.pres;
+    if (a.pres) z.ensure(n);
     if (ifmcor) {
         NEKB_REQUIRE(c.bm1.n >= (size_t)n, "cggo: bm1 must be registered for the null-space correction");
         z.ensure(n), bsum.ensure(n);
@@ -1352,12 +1364,18 @@ inline int cggo_run(const CggoArgs &a, double tin, int maxit, double *hist_host)
     while (result < 0) {
         for (int b = 0; b < batch; b++) {
             if (explicit_z) {
-                if (schwarz)  // :737-745 (fields other than 'PRES': no coarse correction)
+                if (schwarz) {  // :737-745
                     fdm_h1_apply(z.p, r.p, d.p, a.mask, a.nel, a.gs_handle);
-                else {
+                    if (a.pres) {   // :742-744 crs_solve_h1(w,r) ; z += w  ("currently, crs grd only for P")
+                        cggo_pres_coarse(w.p, r.p, a.mult, a.nel);
+                        add2_kernel<<<grid, CG_THREADS, 0, s>>>(z.p, w.p, n);
+                        NEKB_LAUNCHED();
+                    }
+                } else {
                     cggo_z_kernel<<<grid, CG_THREADS, 0, s>>>(z.p, r.p, d.p, n, sc);
                     NEKB_LAUNCHED();
                 }
+                if (a.pres) cggo_pres_ortho(z.p, n);   // :747-748
                 if (ifmcor) {  // :749-752 rmean = smean*glsc2(z,bm1) ; z += rmean
                     cggo_sum2_kernel<<<grid, CG_THREADS, 0, s>>>(z.p, c.bm1.p, n, &sc->work[3], sc, c.partials.p, &sc->counter[0]);
                     NEKB_LAUNCHED();

@@ -337,4 +337,46 @@ inline int hmh_gmres_run(double *res, const double *h1, const double *h2, const 
     return iter;
 }
 
+// ---------------------------------------------------------------------------------------------- cggo('PRES'), param(42) = 1
+// The two pieces the plain-PCG pressure solve adds to the Schwarz branch of cggo (core/hmholtz.f:737-748; cg.cuh cggo_run):
+//
+// crs_solve_h1 (core/navier8.f:1490-1535): w = J crs_solve( J^T (vmult * r) ) with the bilinear (vertex) basis
+// h1_basis(i, 0..1) = (1 -+ z_i) / 2 (set_h1_basis_bilin :1537-1550; map_f_to_c_h1_bilin :1605-1646 and map_c_to_f_h1_bilin
+// :1555-1603 are the same r, s, t contraction sequence as the multigrid transfers, so mg_tensor3 serves) and the coarse solver
+// of the registered pressure multigrid (h1mg_setup built it from the same set_up_h1_crs data).  vmult is COMMON /SOLN/ vmult
+// when registered, else the mult the caller handed to cggo.
+struct PresCoarse {
+    DevBuf<double> J;        // [lx1][2]
+    DevBuf<double> vc, uc;   // [nel][8]
+    int lx1 = 0;
+};
+inline PresCoarse &pres_coarse()
+{
+    static PresCoarse p;
+    return p;
+}
+inline void cggo_pres_coarse(double *w, const double *r, const double *mult, int nel)
+{
+    Ctx &c = ctx();
+    H1mg &M = h1mg();
+    NEKB_REQUIRE(M.ready && !M.pnpn2 && M.nel == nel,
+                 "cggo('PRES'), param(42) = 1: crs_solve_h1 needs the pressure coarse solver (nekb_h1mg_setup) on the same elements");
+    PresCoarse &P = pres_coarse();
+    const int nx = c.nx;
+    if (P.lx1 != nx) {
+        std::vector<double> J((size_t)nx * 2);
+        for (int i = 0; i < nx; i++) J[(size_t)i * 2] = 0.5 * (1.0 - c.z_host[i]), J[(size_t)i * 2 + 1] = 0.5 * (1.0 + c.z_host[i]);
+        P.J.upload(J.data(), J.size(), c.stream);
+        P.lx1 = nx;
+    }
+    P.vc.ensure((size_t)nel * 8), P.uc.ensure((size_t)nel * 8);
+    const int64_t n = (int64_t)nel * c.nxyz;
+    const double *vm = c.vmult.n >= (size_t)n ? c.vmult.p : mult;
+    mg_tensor3(P.vc.p, r, vm, P.J.p, 2, nx, true, false, nel);    // col3(uf,vf,vmult) ; map_f_to_c_h1_bilin
+    crs_solve_dev(M, P.uc.p, P.vc.p);                             // crs_solve(xxth(ifield),uc,vc)
+    mg_tensor3(w, P.uc.p, nullptr, P.J.p, nx, 2, false, false, nel);   // map_c_to_f_h1_bilin
+}
+// ortho (core/navier1.f:223-256) on the velocity-mesh pressure: the mean over all nelgv * lx1^3 entries goes when ifvcor is set
+inline void cggo_pres_ortho(double *z, int64_t n) { gm_ortho(z, n); }
+
 }  // namespace nekb

@@ -11,8 +11,9 @@
 //     x_c += alpha_c p_c ;  z = d r_c ;  p_c = z + beta_c p_c ;  w_c = h1 D^T G D p_c + (h2 B) p_c
 // with the six factor tiles, h1, h2*B and d fetched ONCE per element (cp.async.bulk + mbarrier ring, as ax_cg_kernel), masks
 // are packed to one byte per node for all components, and the residual update is fused with the two dot products of the
-// next iteration:    front 6 + 9/NRHS, gs 2.4, rho 2 + 1.1/NRHS, update 3 + 2.1/NRHS words  ->  17.5 words per component at
-// NRHS = 3 (25.6 at NRHS = 1) instead of 30.
+// next iteration:    front 6 + 9/NRHS, gs 2.4, update 3 + 2.1/NRHS words  ->  15.1 words per component at NRHS = 3 (22.5 at
+// NRHS = 1) instead of 30; rho = (w,p) is summed inside the front kernel from the un-assembled w (round 1 spent a pass of
+// 2 + 1.1/NRHS words on it).
 #pragma once
 #include "cg.cuh"
 
@@ -48,7 +49,7 @@ struct HcgSmem {
 template <int NX, int NRHS, int PIPES, int STAGES, bool HAS_H2>
 __global__ void __launch_bounds__(NX *NX *NRHS *PIPES, 1)
     hcg_front_kernel(HcgPtrs P, const double *__restrict__ g, const double *__restrict__ h1, const double *__restrict__ h2b,
-                     const double *__restrict__ d, int nel, const HcgScalars *__restrict__ sc)
+                     const double *__restrict__ d, int nel, HcgScalars *sc, double *partials)
 {
     using L = HcgSmem<NX, NRHS, PIPES, STAGES>;
     constexpr int N2 = L::N2, N3 = L::N3, GT = N2 * NRHS;
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(NX *NX *NRHS *PIPES, 1)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *smem = reinterpret_cast<double *>(smem_raw);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + PIPES * L::pipe_doubles);
+    double *s_red = reinterpret_cast<double *>(bars + PIPES * STAGES);   // 64 doubles: [0,16) warp sums, [16,64) reduction scratch
 
     const int pipe = threadIdx.x / GT, tp = threadIdx.x % GT;
     const int comp = tp / N2, ij = tp % N2, i = ij % NX, j = ij / NX;
@@ -117,6 +119,10 @@ __global__ void __launch_bounds__(NX *NX *NRHS *PIPES, 1)
     }
 
     double *__restrict__ pg = P.p[comp], *__restrict__ xg = P.x[comp], *__restrict__ wg = P.w[comp];
+    // rho_c = (w_c, p_c)_{mask mult} of hmholtz.f:798-801 is accumulated here from the UN-assembled w: p is continuous and zero on
+    // masked nodes (p = d r + beta p with r, d assembled and masked), so sum_nodes mult*mask*dssum(w)*p = sum_nodes w_local*p --
+    // the identity bp5.usr's own ax_e_bp5 uses for pap.  This replaces a pass over w, p, mult and the mask bytes per iteration.
+    double rho_loc = 0.0;
     int it = 0;
     for (int e = first; e < nel; e += stride, it++) {
         const int stage = it % STAGES;
@@ -173,6 +179,7 @@ __global__ void __launch_bounds__(NX *NX *NRHS *PIPES, 1)
                 }
                 if (HAS_H2) acc = fma(sh2[k * N2 + ij], ucol[k], acc);   // :225 addcol4(au,helm2,bm1,u)
                 wg[eo + k * N2 + ij] = acc;
+                rho_loc = fma(ucol[k], acc, rho_loc);
             }
         }
         // every group of the pipeline is past its last read of the stage before the TMA engine may refill it
@@ -183,6 +190,24 @@ __global__ void __launch_bounds__(NX *NX *NRHS *PIPES, 1)
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 issue(stage, en);
             }
+        }
+    }
+    // per-component sums in a fixed order: warp -> CTA (warps of the component in index order) -> grid (CTAs in index order)
+    {
+        const double ws = warp_sum(rho_loc);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = ws;
+        __syncthreads();
+        constexpr int WPG = N2 / 32;   // warps per component group
+#pragma unroll
+        for (int c = 0; c < NRHS; c++) {
+            if (!act[c]) continue;     // uniform over the grid
+            double b = 0.0;
+            if (threadIdx.x == 0)
+                for (int pp = 0; pp < PIPES; pp++)
+                    for (int q = 0; q < WPG; q++) b += s_red[(pp * NRHS + c) * WPG + q];
+            HcgComp *hc = &sc->c[c];
+            grid_reduce(b, partials + c * CG_PART_STRIDE, &sc->counter[c], s_red + 16, [=](double tot) { hc->rho = tot; });
         }
     }
 }
@@ -381,7 +406,8 @@ inline int hcg_enabled()
 }
 
 template <int NRHS, int PIPES, int STAGES>
-inline void hcg_launch_front(const HcgPtrs &P, const double *h1, const double *h2b, const double *d, int nel, const HcgScalars *sc)
+inline void hcg_launch_front(const HcgPtrs &P, const double *h1, const double *h2b, const double *d, int nel, HcgScalars *sc,
+                             double *partials)
 {
     Ctx &c = ctx();
     using L = HcgSmem<8, NRHS, PIPES, STAGES>;
@@ -393,9 +419,9 @@ inline void hcg_launch_front(const HcgPtrs &P, const double *h1, const double *h
     }
     const int grid = grid_for((nel + PIPES - 1) / PIPES, 1);
     if (h2b)
-        hcg_front_kernel<8, NRHS, PIPES, STAGES, true><<<grid, 64 * NRHS * PIPES, L::bytes, c.stream>>>(P, c.g.p, h1, h2b, d, nel, sc);
+        hcg_front_kernel<8, NRHS, PIPES, STAGES, true><<<grid, 64 * NRHS * PIPES, L::bytes, c.stream>>>(P, c.g.p, h1, h2b, d, nel, sc, partials);
     else
-        hcg_front_kernel<8, NRHS, PIPES, STAGES, false><<<grid, 64 * NRHS * PIPES, L::bytes, c.stream>>>(P, c.g.p, h1, h2b, d, nel, sc);
+        hcg_front_kernel<8, NRHS, PIPES, STAGES, false><<<grid, 64 * NRHS * PIPES, L::bytes, c.stream>>>(P, c.g.p, h1, h2b, d, nel, sc, partials);
     NEKB_LAUNCHED();
 }
 
@@ -515,6 +541,8 @@ inline bool hcg_run(int nrhs, double *const *x, const double *const *f, const do
         dots_allreduce();
     };
     update(true);
+    const char *rk = getenv("NEKB_HCG_RHO_KERNEL");
+    const bool rho_kernel = rk && atoi(rk) != 0;
     int launched = 0;
     const int batch = 8;
     HcgScalars res;
@@ -524,15 +552,17 @@ inline bool hcg_run(int nrhs, double *const *x, const double *const *f, const do
                                              c.param[22], S.hist.p, hstride);
             NEKB_LAUNCHED();
             if (nrhs == 3)
-                hcg_launch_front<3, 1, 3>(P, h1, has_h2 ? S.h2b.p : nullptr, S.d.p, nel, sc);
+                hcg_launch_front<3, 1, 3>(P, h1, has_h2 ? S.h2b.p : nullptr, S.d.p, nel, sc, S.partials.p);
             else
-                hcg_launch_front<1, 2, 2>(P, h1, has_h2 ? S.h2b.p : nullptr, S.d.p, nel, sc);
+                hcg_launch_front<1, 2, 2>(P, h1, has_h2 ? S.h2b.p : nullptr, S.d.p, nel, sc, S.partials.p);
             for (int k = 0; k < nrhs; k++) gs_op(gs_handle, P.w[k], 1, nullptr);   // :797 dssum (done components: harmless)
-            if (nrhs == 3)
-                hcg_rho_kernel<3><<<grid, CG_THREADS, 0, s>>>(P, S.mcode.p, mult, n, sc, S.partials.p);
-            else
-                hcg_rho_kernel<1><<<grid, CG_THREADS, 0, s>>>(P, S.mcode.p, mult, n, sc, S.partials.p);
-            NEKB_LAUNCHED();
+            if (rho_kernel) {   // NEKB_HCG_RHO_KERNEL=1: rho from the assembled w in a pass of its own (round-1 form), for comparison
+                if (nrhs == 3)
+                    hcg_rho_kernel<3><<<grid, CG_THREADS, 0, s>>>(P, S.mcode.p, mult, n, sc, S.partials.p);
+                else
+                    hcg_rho_kernel<1><<<grid, CG_THREADS, 0, s>>>(P, S.mcode.p, mult, n, sc, S.partials.p);
+                NEKB_LAUNCHED();
+            }
             if (c.nranks > 1)
                 for (int k = 0; k < nrhs; k++) comm_allreduce_sum(&sc->c[k].rho, 1);
             update(false);
@@ -577,7 +607,9 @@ inline int cggo_solve(const CggoArgs &a, double tin, int maxit, double *hist_hos
 inline int cggo_solve_impl(const CggoArgs &a, double tin, int maxit, double *hist_host)
 {
     tin = cggo_tin(tin);  // restol(ifield), hmholtz.f:676
-    if (hcg_applicable(1)) {
+    // :677 'PRES' with param(21) != 0: tol = |param(21)| (a negative tin still wins, :679)
+    if (a.pres && tin >= 0.0 && ctx().param[21] != 0.0) tin = fabs(ctx().param[21]);
+    if (hcg_applicable(1) && !a.pres) {
         double *xs[1] = {a.x};
         const double *fs[1] = {a.f}, *ms[1] = {a.mask};
         int it = 0;

@@ -903,10 +903,29 @@ void cggo_(double *x, const double *f, const double *h1, const double *h2, const
         if (name_len >= 4 && !strncmp(name, "PRES", 4)) {
             // hmholtz.f:641-657: ifsplit .and. name.eq.'PRES' -> x = f; hmh_gmres(x,h1,h2,mult,iter); niterhm = iter.
             // (ifsplit is implied by a completed h1mg_setup, which only the Pn-Pn pressure solver performs.)
-            NEKB_REQUIRE(h1mg().ready, "cggo('PRES'): the pressure multigrid is not set up (nekb_h1mg_setup); the plain-PCG pressure "
-                                       "branch (ifsplit = .false.) is not provided");
-            NEKB_REQUIRE(c.param[42] == 0.0 || c.param[42] == 2.0,
-                         "cggo('PRES'): param(42) = 1 (plain PCG with crs_solve_h1) is not provided; 0 = GMRES, 2 = flexible CG");
+            NEKB_REQUIRE(h1mg().ready, "cggo('PRES'): the pressure multigrid / coarse solver is not set up (nekb_h1mg_setup)");
+            NEKB_REQUIRE(c.param[42] == 0.0 || c.param[42] == 1.0 || c.param[42] == 2.0, "cggo('PRES'): param(42) must be 0, 1 or 2");
+            if (c.param[42] == 1.0) {   // the plain PCG below with the 'PRES' extras (coarse-grid correction, ortho)
+                const size_t n = (size_t)c.nelv * c.nxyz;
+                NEKB_REQUIRE(binv != nullptr || c.binvm1.n >= n, "cggo('PRES'): binvm1 not available");
+                const double *src[5] = {f, h1, h2, mask, mult};
+                for (int k = 0; k < 7; k++) c.stage[k].ensure(n);
+                for (int k = 0; k < 5; k++)
+                    NEKB_CUDA(cudaMemcpyAsync(c.stage[k + 1].p, src[k], n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+                const double *d_binv = c.binvm1.p;
+                if (binv != nullptr) {
+                    NEKB_CUDA(cudaMemcpyAsync(c.stage[6].p, binv, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+                    d_binv = c.stage[6].p;
+                }
+                NEKB_REQUIRE(c.volvm1 > 0.0, "volvm1 not registered (nekb_set_step_info)");
+                CggoArgs a{c.stage[0].p, c.stage[1].p, c.stage[2].p, c.stage[3].p, c.stage[4].p, c.stage[5].p, d_binv,
+                           field_handle(), c.nelv, c.volvm1, c.istep};
+                a.pres = true;
+                c.niterhm = cggo_solve(a, *tin, *maxit, nullptr);
+                NEKB_CUDA(cudaMemcpyAsync(x, c.stage[0].p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+                NEKB_CUDA(cudaStreamSynchronize(c.stream));
+                return;
+            }
             const size_t np_ = (size_t)c.nelv * c.nxyz;
             if (x != f) memcpy(x, f, np_ * sizeof(double));
             int iter = *maxit;
@@ -1874,9 +1893,16 @@ static int hsolve_dev(const char *name, size_t name_len, double *u, double *r, c
             if (c.param[22] != 0.0) t = fabs(c.param[22]);
             t = chktcg1_dev(t, r, h1, ifh2 ? h2 : nullptr, vmk, vml, binv_chk, nel, vol);
         }
+        if (pres && c.param[42] == 1.0) {                                      // cggo :660-846 with the 'PRES' extras
+            NEKB_REQUIRE(h1mg().ready, "hsolve('PRES'): needs nekb_h1mg_setup (the coarse solver of crs_solve_h1)");
+            CggoArgs a{u, r, h1, h2, vmk, vml, bi, field_handle(), nel, vol, c.istep};
+            a.pres = true;
+            fdm_h1_state().kfldfdm = 4;   // hmholtz.f:50 (hsolve reaches cggo through hmholtz / hmhzpf): ldim + 1 for 'PRES'
+            return cggo_solve(a, t, maxit, nullptr);
+        }
         if (pres) {                                                            // cggo :641-657
             NEKB_REQUIRE(h1mg().ready && (c.param[42] == 0.0 || c.param[42] == 2.0),
-                         "hsolve('PRES'): needs nekb_h1mg_setup and param(42) = 0 (GMRES) or 2 (flexible CG)");
+                         "hsolve('PRES'): needs nekb_h1mg_setup and param(42) = 0 (GMRES), 1 (PCG) or 2 (flexible CG)");
             NEKB_CUDA(cudaMemcpyAsync(u, r, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, c.stream));
             if (c.param[42] == 2.0) return hmh_flex_cg_body(u, h1, ifh2 ? h2 : nullptr, vml, maxit);
             return hmh_gmres_body(u, h1, ifh2 ? h2 : nullptr, vml, maxit);

@@ -678,9 +678,26 @@ class FdmH1:
         return self.case.dssum(z) * mask
 
 
-def cggo_schwarz(case, fdm, f, h1, h2, mask, tin, maxit, istep=1, history=False):
-    """core/hmholtz.f:611-846 cggo with kfldfdm >= 0 (Schwarz branch :737-745) for a field other than 'PRES', without the
-    null-space correction.  Returns (x, niter[, hist rows (rtz1, rbn2, rho)])."""
+def crs_solve_h1(case, mg, v, mult):
+    """core/navier8.f:1490-1535 crs_solve_h1: uf = J crs_solve(J^T (vmult * vf)) with the bilinear vertex basis
+    h1_basis(i, 0:2) = (1 -+ z_i)/2 (:1537-1550), restriction :1605-1646, prolongation :1555-1603 (r, then s, then t)."""
+    nx, E = case.nx, case.nel
+    J = np.stack([0.5 * (1.0 - case.z), 0.5 * (1.0 + case.z)], axis=1)        # [lx1, 2]
+    uf = (v * mult).reshape(E, nx, nx, nx)                                     # [e, k, j, i]
+    t = np.einsum("ia,ekji->ekja", J, uf)                                      # mxm(h1_basist, 2, uf, lx1, v, ...)
+    t = np.einsum("jb,ekja->ekba", J, t)
+    vc = np.einsum("kc,ekba->ecba", J, t).reshape(-1)
+    uc = mg.crs_solve(vc).reshape(E, 2, 2, 2)
+    t = np.einsum("ia,ecba->ecbi", J, uc)
+    t = np.einsum("jb,ecbi->ecji", J, t)
+    return np.einsum("kc,ecji->ekji", J, t).reshape(-1)
+
+
+def cggo_schwarz(case, fdm, f, h1, h2, mask, tin, maxit, istep=1, history=False, pres_mg=None, ifvcor=False):
+    """core/hmholtz.f:611-846 cggo with kfldfdm >= 0 (Schwarz branch :737-745) without the null-space correction.  With
+    pres_mg (an H1MG holding the coarse solver): the name = 'PRES' form of param(42) = 1 -- z = fdm_h1(r) + crs_solve_h1(r)
+    (:741-744), then ortho(z) (:747-748, core/navier1.f:223-256: the plain mean over all entries goes when ifvcor).
+    Returns (x, niter[, hist rows (rtz1, rbn2, rho)])."""
     n = case.n
     mult, binv = case.mult, case.binv()
     vol = case.bm1().sum()
@@ -695,6 +712,10 @@ def cggo_schwarz(case, fdm, f, h1, h2, mask, tin, maxit, istep=1, history=False)
     it_done = niter
     for it in range(1, niter + 1):
         z = fdm.apply(r, d, mask)
+        if pres_mg is not None:
+            z = z + crs_solve_h1(case, pres_mg, r, mult)
+            if ifvcor:
+                z = z - z.sum() / n
         rtz2 = rtz1
         rtz1 = float(np.sum(z * r * mult))
         rbn2 = float(np.sqrt(np.sum(mult * binv * r * r) / vol))

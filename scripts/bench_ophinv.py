@@ -5,7 +5,8 @@ Runs the same fixed number of PCG iterations (tolh < 0 and tiny, so no component
   fused    -- hcg.cuh, one 3-right-hand-side PCG (default path)
   stock    -- NEKB_HCG=0: cggo_run, one component after the other, one kernel per reference statement
 and prints one JSON line with ms per iteration-and-component for both, the speed-up, and the achieved HBM GB/s of the
-fused path against its algorithmic 17.5 words per point, component and iteration (hcg.cuh header).
+fused path against its algorithmic 15.1 words per point, component and iteration (hcg.cuh header; 17.5 with
+NEKB_HCG_RHO_KERNEL=1, the round-1 form with a pass of its own for rho).
 """
 import argparse
 import ctypes as C
@@ -19,7 +20,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-WORDS_FUSED = 17.5
+WORDS_FUSED = 17.5 if os.environ.get("NEKB_HCG_RHO_KERNEL", "0") not in ("", "0") else 15.1
 WORDS_STOCK = 30.0
 
 

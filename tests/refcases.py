@@ -216,8 +216,8 @@ def ref_bp5():
                 r1=v("r1")[:n].copy(), u1=v("u1")[:n].copy())
 
 
-def _pressure(name, nx=8):
-    return _pressure_case(case_of(name, nx))
+def _pressure(name, nx=8, pcg=False):
+    return _pressure_case(case_of(name, nx), pcg=pcg)
 
 
 def channel_case(dims=(4, 4, 4), nx=8):
@@ -267,7 +267,7 @@ def pressure_inputs(case, pmask):
     return rhs, b
 
 
-def _pressure_case(case, with_geometry=False, capped=0):
+def _pressure_case(case, with_geometry=False, capped=0, pcg=False):
     """set_overlap -> hsmg_setup/h1mg_setup/set_up_h1_crs (navier6.f:29-101, hsmg.f:22-47,2234-2270, navier8.f:83-233),
     h1mg_solve (hsmg.f:1855-1949) and hmh_gmres (gmres.f:304-545) incl. chktcg1 and ortho."""
     rc = _ref(case)
@@ -292,7 +292,24 @@ def _pressure_case(case, with_geometry=False, capped=0):
     gm_last = np.array([abs(R.var("gamma_gmres")[j]) / np.sqrt(R.get("volvm1"))])
     xf, itf = b.copy(), C.c_int(100)
     R.call("hmh_flex_cg", xf, h1, h2, case.mult, itf)            # core/hmholtz.f:2164 (param(42) = 2)
-    out = dict(pmask=pmask, rhs=rhs, rhs_out=r, z=z, b=b, x=x, it=np.array([it.value]), tol=np.array([tol]),
+    pcg_out = {}
+    if pcg:
+        # the plain PCG pressure solve (param(42) = 1): cggo('PRES') = Schwarz (fdm_h1, field ldim+1) + crs_solve_h1 + ortho
+        # (core/hmholtz.f:660-846 with :710-712, :741-748); hmholtz sets kfldfdm and calls set_fdm_prec_h1A on first use (:22-50)
+        R.var("param")[41] = 1.0
+        R.call("set_fdm_prec_h1a")
+        kt4 = R.var("ktype")[:, :, 4].copy(order="F")
+        for key, rhs_p in (("pcg", b), ("pcg_pert", ulp_perturbed(b))):
+            xp = np.zeros(n)
+            R.set("ifsolv", 0), R.set("kfldfdm", 4), R.set("ifield", 1), R.set("istep", 1)
+            with _Logged(R) as lg:
+                R.call("cggo", xp, rhs_p.copy(), h1, h2, pmask, case.mult, 1, tol, 200, 1, rc.fld("binvm1"), "PRES")
+            (hist_p, tol_p), = lg.cggo()
+            pcg_out.update({f"x_{key}": xp, f"it_{key}": np.array([R.get("niterhm")]), f"{key}_rbn2": hist_p, "pcg_tol": np.array([tol_p])})
+        pcg_out["ktype_pres"] = kt4[:case.nel].astype(np.int32)
+        R.set("kfldfdm", -1)
+        R.var("param")[41] = 0.0
+    out = dict(pmask=pmask, rhs=rhs, rhs_out=r, z=z, b=b, x=x, it=np.array([it.value]), tol=np.array([tol]), **pcg_out,
                x_fcg=xf, it_fcg=np.array([itf.value]), gmres_s=gm_s, gmres_rnorm_last=gm_last,
                ifvcor=np.array([int(R.get("ifvcor"))]), volvm1=np.array([R.get("volvm1")]))
     if capped:                                                     # the same GMRES stopped after `capped` iterations
@@ -323,7 +340,7 @@ def _velocity_solve(rc, case):
 def ref_channel():
     """BASELINE config 5 (turbChannel mesh, 4 x 4 x 4 elements): pressure multigrid / GMRES / flexible CG with the constant
     null space on a periodic, wall-stretched box, and one velocity Helmholtz solve."""
-    return _pressure_case(channel_case(), with_geometry=True)
+    return _pressure_case(channel_case(), with_geometry=True, pcg=True)
 
 
 GOLDEN_CHANNEL_FULL = os.path.join(os.path.dirname(GOLDEN), "ref_channel_full.npz")
@@ -374,11 +391,11 @@ def ref_ethier():
 
 
 def ref_h1mg():
-    return _pressure("core")
+    return _pressure("core", pcg=True)
 
 
 def ref_h1mg_neumann():
-    return _pressure("neumann")
+    return _pressure("neumann", pcg=True)
 
 
 def ref_h1mg_lx6():

@@ -165,6 +165,51 @@ def test_h1mg_solve_and_hmh_gmres_against_the_reference(nek, name, mesh):
     assert it == g["it_fcg"][0] and relmax(res, g["x_fcg"]) <= 1e-9
 
 
+@pytest.mark.parametrize("name,mesh", [("h1mg", "core"), ("h1mg_neumann", "neumann")])
+def test_plain_pcg_pressure_solve_param42_1_against_the_reference(nek, name, mesh):
+    """cggo('PRES') with param(42) = 1 (core/hmholtz.f:660-846): Schwarz smoother of the pressure field (fdm_h1) + crs_solve_h1
+    (navier8.f:1490-1535: bilinear restriction, the coarse solver of the registered multigrid, bilinear prolongation) + ortho in
+    every iteration, against the reference's own run: identical count (or a proven margin event), solution to 1e-6."""
+    g, case = G[name], refcases.case_of(mesh)
+    gc = G["core"]
+    null = bool(g["ifvcor"][0])
+    E, n = case.nel, case.n
+    nek.set_nel(E, E)
+    nek.set_gll(gc["zgm1"], gc["wxm1"])
+    nek.set_dxyz(gc["dxm1"], np.ascontiguousarray(gc["dxm1"].T))
+    nek.set_geom(*[gc[f"g{i}m1"] for i in range(1, 7)], gc["bm1"])
+    nek.set_ifdfrm(None)
+    fbc = refcases.fbc_of(mesh, case)
+    nek.h1mg_setup(fbc, case.xm1, case.ym1, case.zm1, case.vertex, E, null)
+    h, _ = nek.setupds(8, E, case.vertex)
+    nek.set_ifield(1)
+    nek.set_field_handle(1, h)
+    tol = float(g["tol"][0])
+    binv = gc["binvm1"] if mesh == "core" else case.binv()
+    nek.set_step_info(1, float(g["volvm1"][0]))
+    nek.set_pressure_state(g["pmask"], binv, tol, tol, null, E)
+    nek.fdm_h1_setup((fbc == 0).astype(np.int32), g["pmask"], case.xm1, case.ym1, case.zm1, E)   # set_fdm_prec_h1A, field ldim+1
+    assert np.array_equal(nek.fdm_h1_get("ktype", E).reshape(E, 3), g["ktype_pres"])
+    nek.set_param(42, 1.0)
+    nek.set_param(21, tol)
+    nek.set_kfldfdm(4)
+    try:
+        x = np.zeros(n)
+        it = nek.cggo(x, g["b"], np.ones(n), np.zeros(n), g["pmask"], gc["vmult"], 1, tol, 200, 1, binv, "PRES")
+        hist = nek.last_history()
+    finally:
+        nek.set_param(42, 0.0)
+        nek.set_param(21, 0.0)
+        nek.set_kfldfdm(-1)
+    assert g["it_pcg"][0] < 200
+    refcases.count_or_margin(it, int(g["it_pcg"][0]), hist[:, 1], g["pcg_rbn2"], float(g["pcg_tol"][0]), g["pcg_pert_rbn2"],
+                             what=f"plain PCG pressure solve ({name})")
+    assert relmax(x, g["x_pcg"]) <= 1e-6
+    k = min(12, len(hist), len(g["pcg_rbn2"]))
+    assert relmax(hist[:k, 1], g["pcg_rbn2"][:k]) <= 1e-9
+    nek.fgslib_gs_free(h)
+
+
 def test_fdm_h1_and_schwarz_cggo_against_the_reference(nek):
     g, case = G["fdm"], refcases.case_of("fdm")
     E, n = case.nel, case.n

@@ -121,6 +121,30 @@ def test_h1mg_solve_and_hmh_gmres(name, mesh):
     assert it == g["it_fcg"][0] and relmax(x, g["x_fcg"]) <= 1e-10      # hmh_flex_cg (param(42) = 2)
 
 
+@pytest.mark.parametrize("name,mesh", [("h1mg", "core"), ("h1mg_neumann", "neumann"), ("channel", None)])
+def test_plain_pcg_pressure_solve_param42_1(name, mesh):
+    """cggo('PRES') with param(42) = 1 (core/hmholtz.f:660-846 with :710-712, :741-748): Schwarz (fdm_h1 of the pressure field)
+    + crs_solve_h1 (navier8.f:1490-1535) + ortho in every iteration.  Golden = the reference's own cggo; identical count (or a
+    proven margin event: the Schwarz-preconditioned CG amplifies rounding, refcases.count_or_margin), solution to 1e-8 (the
+    tolerance of the solve)."""
+    g = G[name]
+    c = refcases.case_of(mesh) if mesh else refcases.channel_case()
+    fbc = refcases.fbc_of(mesh, c) if mesh else refcases.channel_fbc(c)
+    null = bool(g["ifvcor"][0])
+    mg = hsmg.H1MG(c, fbc, null_space=null)
+    fdm = hsmg.FdmH1(c, (fbc == 0).astype(np.int32), g["pmask"])
+    assert np.array_equal(fdm.ktype, g["ktype_pres"])
+    n, tol = c.n, float(g["tol"][0])
+    x, it, hist = hsmg.cggo_schwarz(c, fdm, g["b"], np.ones(n), np.zeros(n), g["pmask"], tol, 200, history=True, pres_mg=mg,
+                                    ifvcor=null)
+    assert g["it_pcg"][0] < 200
+    refcases.count_or_margin(it, int(g["it_pcg"][0]), hist[:, 1], g["pcg_rbn2"], float(g["pcg_tol"][0]), g["pcg_pert_rbn2"],
+                             what=f"plain PCG pressure solve ({name})")
+    assert relmax(x, g["x_pcg"]) <= 1e-6
+    k = min(12, len(hist), len(g["pcg_rbn2"]))                      # the residual history before rounding has been amplified
+    assert relmax(hist[:k, 1], g["pcg_rbn2"][:k]) <= 1e-9
+
+
 def test_fdm_h1_and_cggo_schwarz_branch():
     g, c = G["fdm"], refcases.case_of("fdm")
     fi = (hsmg.box_fbc(c, (1, 1, 1, 1, 1, 1)) == 0).astype(np.int32)
