@@ -731,8 +731,11 @@ inline void launch_ax_cg_affine(const double *r, double *p, double *u, double *w
 //   ut        from the lane's own k-columns in registers with D(k,m) from the constant bank, as in v4
 //   back:  D^T wr through shared memory (own-address STS.64, one LDS.128 fragment per plane), D^T ws from the lane's own values,
 //          D^T wt accumulated in registers; the DMMA accumulator starts from that register sum.
-// Per element a lane issues 80 LDS/STS.64 + 16 LDS.128 (v4: 2 x (154 + 67 + 27)), 64 DMMA and ~520 DFMA; no block or group
-// barrier (only __syncwarp), ~170 registers.
+// Per element a lane issues 112 LDS/STS.64 + 16 LDS.128 (v4: 2 x (154 + 67 + 27)), 64 DMMA and ~520 DFMA; no block or group
+// barrier (only __syncwarp).  The own-node accesses (words t*8 + g of a plane) are two-way bank conflicts per half warp (ncu:
+// 95 M conflicts per launch); the alternative ownership (j = g, i = 2t, 2t+1: own nodes one 16-byte word, conflict-free, but two
+// LDS.64 per B fragment) measured 2-4 % SLOWER (profiles/r2z_*: 1.12-1.14 vs 1.07-1.09 ms) and was dropped -- the kernel is
+// DRAM-bound, not shared-memory-bound.
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
 {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));

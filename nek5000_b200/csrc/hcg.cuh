@@ -14,6 +14,10 @@
 // next iteration:    front 6 + 9/NRHS, gs 2.4, update 3 + 2.1/NRHS words  ->  15.1 words per component at NRHS = 3 (22.5 at
 // NRHS = 1) instead of 30; rho = (w,p) is summed inside the front kernel from the un-assembled w (round 1 spent a pass of
 // 2 + 1.1/NRHS words on it).
+// Tried and rejected on measurement (round 2, profiles/r2y_ophinv*.json): the structured gather of cggos_update6_kernel applied
+// here (one warp per element behind a TMA ring of r_c, w_c, mult, d, binv stages, face partners / edge values gathered in the
+// update): a 3-component stage is 37 KB, so only 3 warps fit an SM and the kernel ran 2x slower than gs_op + hcg_update_kernel
+// (6.9 vs 3.2 ms per iteration and component); with one component (5 warps) it was a draw (4.03 vs 4.00 ms).
 #pragma once
 #include "cg.cuh"
 
