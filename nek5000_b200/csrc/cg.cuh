@@ -851,14 +851,10 @@ __global__ void cggos_hist_kernel(const CgScalars *sc, double *hist, int slot)
     hist[3 * slot + 1] = sc->work[1];
 }
 
-inline int axcg_variant()
+inline int axcg_variant()   // read per solve: the parity tests run the kept kernel forms side by side in one process
 {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("NEKB_AXCG_VARIANT");
-        v = e ? atoi(e) : 0;
-    }
-    return v;
+    const char *e = getenv("NEKB_AXCG_VARIANT");
+    return e ? atoi(e) : 0;
 }
 inline int gs_fuse_update_enabled()  // read per solve, so one process can time both forms
 {
@@ -911,10 +907,11 @@ inline int cggos_run_fused(const CggosArgs &a, int maxit, double *hist_host, boo
     cggos_init2_kernel<<<grid, CG_THREADS, 0, s>>>(a.u, r.p, a.rhs, a.mult, n, sc, c.partials.p + 1 * CG_PART_STRIDE);
     NEKB_LAUNCHED();
     comm_allreduce_sum(&sc->work[1], 1);
+    const int axv = axcg_variant();
     for (int iter = 1; iter <= maxit; iter++) {
         prof_begin(PROF_AX);
-        if (affine) {   // per-element constants instead of per-node factors (ax.cuh kernel v4); stages are 12 KB
-            switch (axcg_variant()) {
+        if (affine) {   // per-element constants instead of per-node factors (ax.cuh kernels v4 / v5); stages are 12 KB
+            switch (axv) {
                 case 1: launch_ax_cg_affine<8, 4, 4>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
                 case 2: launch_ax_cg_affine<8, 6, 3>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
                 case 3: launch_ax_cg_affine<8, 8, 2>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
@@ -928,7 +925,7 @@ inline int cggos_run_fused(const CggosArgs &a, int maxit, double *hist_host, boo
                 default: launch_ax_cg_affine_mma<8, 2>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
             }
         } else
-        switch (axcg_variant()) {  // element groups per CTA x ring stages (36 KB each): bytes in flight vs. threads per SM
+        switch (axv) {  // element groups per CTA x ring stages (36 KB each): bytes in flight vs. threads per SM
             case 1: launch_ax_cg<8, 2, 3>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
             case 2: launch_ax_cg<8, 2, 2>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;
             case 3: launch_ax_cg<8, 3, 2>(r.p, p.p, a.u, ap.p, a.nel, iter == 1, &sc->work[0]); break;   // default before kernel v6

@@ -267,6 +267,33 @@ def test_affine_operator_kernel_is_chosen_from_the_factors_and_agrees_with_the_g
         nek.fgslib_gs_free(h)
 
 
+@pytest.mark.parametrize("kw,affine,variants", [(dict(), 1, ("0", "7", "11", "14")), (dict(deform=0.05), 0, ("0", "3", "1", "10", "11"))])
+def test_operator_kernel_forms_agree(nek, monkeypatch, kw, affine, variants):
+    """The CG-fused operator kernel exists in several forms behind NEKB_AXCG_VARIANT: one warp per element with the in-plane
+    contractions on mma.sync.m8n8k4.f64 (default; other warp / stage counts: 11, 14 affine, 10, 11 general) and 64 threads per
+    element with DFMA contractions (7 affine, 3 / 1 general).  Same operator, different summation order inside the contractions:
+    the solves must agree to 1e-12 with each other and with the oracle as the default does."""
+    from nek5000_b200 import lib
+    case = oracle.Case(4, 3, 2, nx=8, **kw)
+    register(nek, case, bp5=True)
+    h, _ = nek.setupds(8, case.nel, case.vertex)
+    nek.set_field_handle(1, h)
+    nek.set_ifield(1)
+    assert lib().nekb_ax_affine_active() == affine
+    e1, r1 = case.bp5_problem()
+    uref, itref, hist = case.cggos(r1, e1, tol=-1e-8, maxit=30, history=True)
+    us = []
+    for v in variants:
+        monkeypatch.setenv("NEKB_AXCG_VARIANT", v)
+        u = np.zeros(case.n)
+        assert nek.cggos(u, r1, e1, case.mult, np.ones(case.n), -1e-8, 30, "bp5") == 30
+        us.append(u)
+    monkeypatch.delenv("NEKB_AXCG_VARIANT")
+    for u in us:
+        assert relmax(u, us[0]) <= 1e-12 and relmax(u, uref) <= TOL_HIST
+    nek.fgslib_gs_free(h)
+
+
 @pytest.mark.parametrize("ifh2", [False, True])
 def test_cggo_iterations_and_solution(nek, ifh2):
     """Stock cggo (hmholtz.f:611-846).  CG amplifies rounding differences exponentially with the iteration number
