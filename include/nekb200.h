@@ -115,8 +115,12 @@ void axhelm_(double *au, const double *u, const double *helm1, const double *hel
 /* core/hmholtz.f:380 setprec(dpcm1,helm1,helm2,imsh,isd) incl. dssum + invcol1 (:520-521). */
 void setprec_(double *dpcm1, const double *helm1, const double *helm2, const int *imsh, const int *isd);
 /* core/hmholtz.f:611 cggo(x,f,h1,h2,mask,mult,imsh,tin,maxit,isd,binv,name): Jacobi-PCG branch
- * (kfldfdm<0).  name is character*4 with gfortran's hidden trailing length.  The iteration count
- * is left in nekb_niterhm() (reference: common /iterhm/ niterhm, :638). */
+ * (kfldfdm<0) and Schwarz branch (kfldfdm>=0, fdm_h1, :737-745).  name is character*4 with gfortran's
+ * hidden trailing length.  name = 'PRES' follows param(42) as the reference does (:641-657): 0 ->
+ * hmh_gmres, 2 -> hmh_flex_cg, 1 -> this routine's own PCG with the 'PRES' extras (:710-712,
+ * :741-748: coarse-grid correction crs_solve_h1 on the coarse solver of nekb_h1mg_setup, ortho in
+ * every iteration, tol = |param(21)| when non-zero).  The iteration count is left in
+ * nekb_niterhm() (reference: common /iterhm/ niterhm, :638). */
 void cggo_(double *x, const double *f, const double *h1, const double *h2, const double *mask,
            const double *mult, const int *imsh, const double *tin, const int *maxit, const int *isd,
            const double *binv, const char *name, size_t name_len);
