@@ -400,17 +400,17 @@ def ref_h1mg_neumann():
 
 def ref_h1mg_lx6():
     """The same at lx1 = 6 (multigrid orders 1, 3, 5; core/hsmg.f:2272-2337)."""
-    return _pressure("core", 6)
+    return _pressure("core", 6, pcg=True)
 
 
 def ref_h1mg_lx4():
     """lx1 = 4: the two-level form (mg_h1_lmax = 2, orders 1, 3; core/hsmg.f:2293)."""
-    return _pressure("core", 4)
+    return _pressure("core", 4, pcg=True)
 
 
 def ref_h1mg_lx10():
     """lx1 = 10: orders 1, 3, 9."""
-    return _pressure("core", 10)
+    return _pressure("core", 10, pcg=True)
 
 
 def ref_periodic():

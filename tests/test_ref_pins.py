@@ -308,6 +308,15 @@ def test_h1mg_and_gmres_at_other_orders(nx, orders):
     assert it == g["it"][0] and relmax(x, g["x"]) <= 1e-11
     x, it = hsmg.hmh_flex_cg(c, mg, g["b"], np.ones(n), np.zeros(n), g["pmask"], c.mult, float(g["tol"][0]), 100)
     assert it == g["it_fcg"][0] and relmax(x, g["x_fcg"]) <= 1e-10
+    # the plain-PCG pressure solve (param(42) = 1) at this order: fdm_h1 of the pressure field + crs_solve_h1 + ortho
+    fbc = refcases.fbc_of("core", c)
+    fdm = hsmg.FdmH1(c, (fbc == 0).astype(np.int32), g["pmask"])
+    assert np.array_equal(fdm.ktype, g["ktype_pres"])
+    tol = float(g["tol"][0])
+    x, it, hist = hsmg.cggo_schwarz(c, fdm, g["b"], np.ones(n), np.zeros(n), g["pmask"], tol, 200, history=True, pres_mg=mg)
+    refcases.count_or_margin(it, int(g["it_pcg"][0]), hist[:, 1], g["pcg_rbn2"], float(g["pcg_tol"][0]), g["pcg_pert_rbn2"],
+                             what=f"plain PCG pressure solve (lx1 = {nx})")
+    assert g["it_pcg"][0] < 200 and relmax(x, g["x_pcg"]) <= 1e-6
 
 
 def test_periodic_numbering_bit_exact():
