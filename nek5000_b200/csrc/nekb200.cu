@@ -1897,8 +1897,13 @@ static int hsolve_dev(const char *name, size_t name_len, double *u, double *r, c
             NEKB_REQUIRE(h1mg().ready, "hsolve('PRES'): needs nekb_h1mg_setup (the coarse solver of crs_solve_h1)");
             CggoArgs a{u, r, h1, h2, vmk, vml, bi, field_handle(), nel, vol, c.istep};
             a.pres = true;
-            fdm_h1_state().kfldfdm = 4;   // hmholtz.f:50 (hsolve reaches cggo through hmholtz / hmhzpf): ldim + 1 for 'PRES'
-            return cggo_solve(a, t, maxit, nullptr);
+            // hmholtz.f:50 (hsolve reaches cggo through hmholtz / hmhzpf): kfldfdm = ldim + 1 for 'PRES'; the next hmholtz call
+            // of the reference resets it, so the value registered before is put back for whatever solve comes next
+            const int kf_prev = fdm_h1_state().kfldfdm;
+            fdm_h1_state().kfldfdm = 4;
+            const int it_pcg = cggo_solve(a, t, maxit, nullptr);
+            fdm_h1_state().kfldfdm = kf_prev;
+            return it_pcg;
         }
         if (pres) {                                                            // cggo :641-657
             NEKB_REQUIRE(h1mg().ready && (c.param[42] == 0.0 || c.param[42] == 2.0),
